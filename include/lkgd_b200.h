@@ -1,0 +1,199 @@
+/* lkgd_b200 - C ABI of the B200-native (sm_100a) kernels behind the LKGD / Stable-Video-Diffusion denoise
+ * hot path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
+ *
+ * The reference (caoql98/LKGD) has no FFI: its extension point is Python module injection
+ * (pipeline/pipeline_stable_video_diffusion_controlnet.py:122-143, run_models/run_inference.py:279-281).
+ * Each entry point below replaces the ATen / cuDNN / cuBLAS calls that the cited reference lines (or the
+ * diffusers==0.27.2 block they import) issue; the Python facade in lkgd_b200/ binds them with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions: all launches go to the caller's `stream` (a cudaStream_t passed as void*); no hidden device
+ * allocation; the caller owns every buffer; activations are channels-last bf16: a tensor [B,F,H,W,C] is a
+ * row-major matrix [M = B*F*H*W, C].  Return value: 0 on success, <0 = LKGD_E*.
+ */
+#ifndef LKGD_B200_H_
+#define LKGD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LKGD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LKGD_API __attribute__((visibility("default")))
+#else
+#define LKGD_API
+#endif
+
+#define LKGD_OK 0
+#define LKGD_ESHAPE (-1) /* unsupported / inconsistent shape        */
+#define LKGD_EALIGN (-2) /* pointer or pitch not 16-byte aligned    */
+#define LKGD_EARCH (-3)  /* device is not sm_100                    */
+#define LKGD_EWS (-4)    /* workspace too small                     */
+#define LKGD_ECUDA (-5)  /* CUDA runtime / driver error (see lkgd_last_cuda_error) */
+
+LKGD_API int lkgd_abi_version(void);
+LKGD_API const char* lkgd_strerror(int code);
+LKGD_API const char* lkgd_last_cuda_error(void);
+/* 0 if device `dev` is a compute-capability-10.x part, LKGD_EARCH otherwise. */
+LKGD_API int lkgd_device_check(int dev);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+LKGD_API uint64_t lkgd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution on tcgen05 tensor cores (TMA -> smem -> UMMA, fp32 accum in TMEM).
+ *   out[m, n] = s0 * act( sum_k A[m,k] * Bw[n,k] + bias[n] + rowvec[g(m), n] ) + s1*res1[m,n] + s2*res2[m,n]
+ * Replaces: nn.Linear projections / GEGLU feed-forward (diffusers attention.py, restated in the reference at
+ * patch/patch.py:390-686), Conv2d 3x3 + Conv3d (3,1,1) of SpatioTemporalResBlock, down/up-sampler convs,
+ * conv_in / conv_out (models/unet_spatio_temporal_condition_controlnet.py:127-132,240-245,431,500),
+ * LoRA update (models/lora_layer.py:417-443) as a second K segment, AlphaBlender mix and residual adds as
+ * epilogue terms.
+ * A-operand modes:
+ *   LINEAR  : A is [M, K0] row-major bf16 (pitch lda elements).
+ *   CONV3X3 : A is NHWC [NIMG, Hin, Win, C0]; output pixel (ho,wo) gathers 3x3 taps with pad 1, stride 1 or 2;
+ *             Bw is [N, 9*C0] with k = (ky*3+kx)*C0 + c.
+ *   TCONV3  : A is [B, F, HW, C0]; output (b,f,p) gathers frames f-1,f,f+1 (zero pad); Bw is [N, 3*C0].
+ * Optional second K segment (LoRA / shortcut / concat source): A1 [M, K1] (same addressing mode, centre tap),
+ * Bw1 [N, K1].
+ * GEGLU: Bw rows are pre-interleaved per 256-row tile (128 value rows then their 128 gate rows); the output
+ * has N/2 columns: out = (acc_h + b_h) * gelu_erf(acc_g + b_g).
+ */
+enum { LKGD_A_LINEAR = 0, LKGD_A_CONV3X3 = 1, LKGD_A_TCONV3 = 2 };
+enum { LKGD_ACT_NONE = 0, LKGD_ACT_SILU = 1, LKGD_ACT_GEGLU = 2 };
+/* row -> rowvec index g(m) with HW = rows per frame, F frames, B = batch:
+ *   NONE; FRAME: m/HW; FRAMEPOS: (m/HW)%F; BATCH: m/(HW*F);
+ *   TCTX_0272: ((m/(HW*F))*HW + m%HW) % B  (diffusers 0.27.2 temporal-context quirk) */
+enum { LKGD_RV_NONE = 0, LKGD_RV_FRAME = 1, LKGD_RV_FRAMEPOS = 2, LKGD_RV_BATCH = 3, LKGD_RV_TCTX_0272 = 4 };
+
+typedef struct lkgd_gemm_args {
+  int32_t a_mode;     /* LKGD_A_*                                             */
+  int32_t M, N;       /* output rows, Bw rows (GEGLU: N counts value+gate rows) */
+  int32_t K0;         /* channels per tap of segment 0 (LINEAR: K)            */
+  int32_t K1;         /* channels of segment 1, 0 = none                      */
+  const void* A;      /* bf16                                                 */
+  int32_t lda;        /* LINEAR: row pitch of A in elements (>= K0)           */
+  const void* A1;     /* bf16 [M, K1] (or same layout as A with C = K1)       */
+  int32_t lda1;
+  const void* Bw;     /* bf16 [N, taps*K0], row pitch ldb                     */
+  int32_t ldb;
+  const void* Bw1;    /* bf16 [N, K1], row pitch ldb1                         */
+  int32_t ldb1;
+  /* conv geometry (CONV3X3: NIMG,Hin,Win,stride; TCONV3: B=NIMG, F, HW) */
+  int32_t NIMG, Hin, Win, stride;
+  int32_t F, HW;
+  /* epilogue */
+  const float* bias;  /* [N] or NULL                                          */
+  const float* rowvec;/* [G, N] fp32 or NULL                                  */
+  int32_t rv_mode, rv_HW, rv_F, rv_B;
+  int32_t act;        /* LKGD_ACT_*                                           */
+  float s0;
+  const void* res1;   /* bf16 [M, ldr1] or NULL                               */
+  int32_t ldr1;
+  float s1;
+  const void* res2;
+  int32_t ldr2;
+  float s2;
+  void* out;          /* bf16 or fp32 [M, ldo]                                */
+  int32_t ldo;
+  int32_t out_f32;    /* 1: fp32 output                                       */
+  int32_t n_store;    /* store only columns < n_store (0 = all)               */
+} lkgd_gemm_args;
+
+LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);
+/* Reference-quality SIMT implementation of the same contract (tests only: on-GPU checker at large sizes). */
+LKGD_API int lkgd_gemm_simt_check(const lkgd_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over channels-last data.  x is [NS, R, C1] (+ optional second source [NS, R, C2] that is
+ * concatenated on the channel axis: torch.cat([hidden, skip], 1) of the up blocks), statistics per
+ * (sample, group) over R * (C/G) elements.  Spatial resblock: NS = B*F, R = H*W.  Temporal resblock
+ * (5-D GroupNorm, statistics ACROSS frames): NS = B, R = F*H*W.  Output bf16 [NS, R, C1+C2].
+ * Replaces nn.GroupNorm + SiLU (diffusers resnet.py ResnetBlock2D / TemporalResnetBlock; the reference's
+ * conv_norm_out + conv_act, ...controlnet.py:237-238,498-499; TransformerSpatioTemporalModel.norm).
+ * workspace: lkgd_groupnorm_workspace(NS, C) bytes.
+ */
+LKGD_API size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C);
+LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R, int32_t groups,
+                   const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* workspace,
+                   size_t ws_bytes, void* stream);
+
+/* LayerNorm over the last axis of a [M, C] bf16 matrix (C <= 2048, C % 8 == 0) with optional fused
+ *   s = x + addvec[g(m)]   (fp32 addvec [G, C]; frame positional embedding or KV-length-1 cross-attention term)
+ * sum_out (bf16, may alias x, may be NULL) receives s; out receives LN(s)*gamma+beta.
+ * Replaces nn.LayerNorm norm1/norm2/norm3/norm_in (patch/patch.py:415-416,529-530,555-556,599,610,664,670). */
+LKGD_API int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                   const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B, void* sum_out,
+                   void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Spatial self-attention (and general cross-attention), flash-style on tcgen05: per (image, head)
+ *   O = softmax(Q K^T * scale) V,  non-causal, no mask.
+ * q/k/v point at the first head's first element; consecutive heads are `d` elements apart inside a token row;
+ * token rows are ld{q,k,v} elements apart; images are Nq (resp. Nk) rows apart.  d in {16,32,64}.
+ * Replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0 for transformer_blocks.*.attn1/attn2. */
+LKGD_API int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
+                   int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, float scale,
+                   void* stream);
+/* SIMT checker with the same contract (tests only). */
+LKGD_API int lkgd_attention_simt_check(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                              void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
+                              int32_t Nk, float scale, void* stream);
+
+/* Temporal self-attention over the frame axis without a transpose: qkv is the fused projection
+ * [B, F, HW, 3*C] (q | k | v, C = heads*d); sequence (b, p, head) attends over its F frames (F <= 32).
+ * out is [B, F, HW, C].  Replaces temporal_transformer_blocks.*.attn1 (patch/patch.py:592-597,659-661). */
+LKGD_API int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, int32_t F, int32_t HW, int32_t heads, int32_t d,
+                            float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Small fp32 helpers of the conditioning path (M <= 64 rows).
+ *   y[m, n] = act_out( sum_k act_in(x[m,k]) * W[n,k] + b[n] )     W fp32 [N, K]
+ * act codes: 0 none, 1 SiLU, 3 LeakyReLU(0.1).
+ * Replaces TimestepEmbedding MLPs, resnet time_emb_proj, KV-length-1 cross-attention to_v / to_out
+ * (...controlnet.py:406-419) and the LKGD fuse MLPs (unet_spatio_temporal_condition.py:595). */
+LKGD_API int lkgd_small_linear(const float* x, int32_t ldx, const float* W, const float* b, float* y, int32_t ldy, int32_t M,
+                      int32_t N, int32_t K, int32_t act_in, int32_t act_out, void* stream);
+/* Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[m] = [cos(t_m f_k) | sin(t_m f_k)]. */
+LKGD_API int lkgd_timestep_embedding(const float* t, int32_t M, int32_t dim, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Layout / glue kernels (HBM-bound, 128-bit vectorised).
+ */
+/* out[n,f,h,w,0:C0] = src0[n % N0, f, :, h, w] * scale0 ; out[..., C0:C0+C1] = src1[n % N1, ...]; rest 0.
+ * src are fp32 NCHW-per-frame [N?, F, C?, H, W]; out is bf16 [N, F, H, W, Cpad].  Fuses the CFG duplication,
+ * scheduler.scale_model_input and the image-latent concat (pipeline...controlnet.py:579-584). */
+LKGD_API int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* src1, int32_t N1,
+                    int32_t C1, void* out, int32_t N, int32_t F, int32_t H, int32_t W, int32_t Cpad, void* stream);
+/* src fp32 [N*F, H, W, ld] channels-last -> dst fp32 [N, F, C, H, W]. */
+LKGD_API int lkgd_unpack_output(const float* src, int32_t ld, float* dst, int32_t NF, int32_t C, int32_t H, int32_t W,
+                       void* stream);
+/* generic NCHW fp32 [N, C, H, W] <-> NHWC bf16 [N, H, W, C] converters (ControlNet residual exchange). */
+LKGD_API int lkgd_nchw_to_nhwc(const float* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
+LKGD_API int lkgd_nhwc_to_nchw(const void* src, float* dst, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
+/* nearest 2x upsample, channels-last bf16 [N,H,W,C] -> [N,2H,2W,C] (Upsample2D before its conv). */
+LKGD_API int lkgd_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* channel concat of two channels-last matrices: dst[m] = [a[m, 0:Ca] | b[m, 0:Cb]]. */
+LKGD_API int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t M, void* stream);
+/* y[i] = alpha * x[i] + beta * y[i] on bf16 (ControlNet residual injection with the F6 multipliers:
+ * ...controlnet.py:453-462,472-473). n % 8 == 0. */
+LKGD_API int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fused classifier-free-guidance combine + Euler (Karras sigmas, v-prediction) step, fp32.
+ *   v      = u + g[f] * (c - u)           u = pred[s], c = pred[S + s]   (pred channels-last fp32 [2S*F,H,W,ld])
+ *   x0     = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1)
+ *   x_next = x + (x - x0) / sigma * (sigma_next - sigma)
+ * x / x_next are fp32 [S, F, C, H, W] (reference layout).  If S_pred == S (no CFG) v = pred.
+ * Replaces pipeline...controlnet.py:614-616 and utils/scheduling_euler_discrete_karras_fix.py:481-520. */
+LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
+                        float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W,
+                        float sigma, float sigma_next, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKGD_B200_H_ */

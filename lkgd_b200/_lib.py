@@ -1,0 +1,97 @@
+"""ctypes binding of liblkgd_b200.so (the C ABI declared in include/lkgd_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  The library is built
+in-tree by ``lkgd_b200/build.py`` (``__graft_entry__.build()``)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
+
+A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+RV_NONE, RV_FRAME, RV_FRAMEPOS, RV_BATCH, RV_TCTX_0272 = 0, 1, 2, 3, 4
+SL_NONE, SL_SILU, SL_LEAKY = 0, 1, 3
+
+i32, f32, vp, i64, sz = C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_size_t
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``lkgd_gemm_args``."""
+    _fields_ = [
+        ("a_mode", i32), ("M", i32), ("N", i32), ("K0", i32), ("K1", i32),
+        ("A", vp), ("lda", i32), ("A1", vp), ("lda1", i32),
+        ("Bw", vp), ("ldb", i32), ("Bw1", vp), ("ldb1", i32),
+        ("NIMG", i32), ("Hin", i32), ("Win", i32), ("stride", i32), ("F", i32), ("HW", i32),
+        ("bias", vp), ("rowvec", vp), ("rv_mode", i32), ("rv_HW", i32), ("rv_F", i32), ("rv_B", i32),
+        ("act", i32), ("s0", f32), ("res1", vp), ("ldr1", i32), ("s1", f32),
+        ("res2", vp), ("ldr2", i32), ("s2", f32),
+        ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/lkgd_b200.h declares
+SIGNATURES = {
+    "lkgd_abi_version": (i32, []),
+    "lkgd_strerror": (C.c_char_p, [i32]),
+    "lkgd_last_cuda_error": (C.c_char_p, []),
+    "lkgd_device_check": (i32, [i32]),
+    "lkgd_launch_count": (C.c_uint64, []),
+    "lkgd_gemm": (i32, [C.POINTER(GemmArgs), vp]),
+    "lkgd_gemm_simt_check": (i32, [C.POINTER(GemmArgs), vp]),
+    "lkgd_groupnorm_workspace": (sz, [i32, i32]),
+    "lkgd_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, sz, vp]),
+    "lkgd_layernorm": (i32, [vp, i32, i32, vp, vp, f32, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "lkgd_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "lkgd_attention_simt_check": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "lkgd_attention_temporal": (i32, [vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "lkgd_small_linear": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "lkgd_timestep_embedding": (i32, [vp, i32, i32, vp, vp]),
+    "lkgd_pack_input": (i32, [vp, i32, i32, f32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "lkgd_unpack_output": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "lkgd_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "lkgd_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "lkgd_upsample2x": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "lkgd_concat_channels": (i32, [vp, i32, vp, i32, vp, i64, vp]),
+    "lkgd_axpby": (i32, [vp, f32, vp, f32, i64, vp]),
+    "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
+}
+
+_lib = None
+
+
+class LkgdError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the shared library and binds every symbol.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise LkgdError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(lkgd_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.lkgd_abi_version() != 1:
+        raise LkgdError(f"ABI version mismatch: library reports {lib.lkgd_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    """Maps C error codes to exceptions; shape / alignment problems are ValueError like the reference's
+    configuration errors (models/unet_spatio_temporal_condition_controlnet.py:101-124)."""
+    if rc == 0:
+        return
+    lib = load()
+    msg = lib.lkgd_strerror(rc).decode()
+    if rc in (-1, -2):
+        raise ValueError(f"{what}: {msg}")
+    if rc == -5:
+        msg += ": " + lib.lkgd_last_cuda_error().decode()
+    raise LkgdError(f"{what}: {msg}")

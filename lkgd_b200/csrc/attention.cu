@@ -1,0 +1,347 @@
+// Attention kernels.
+//  * attn_flash_kernel: spatial self-attention (and general cross-attention), flash-style on tcgen05.
+//      warps 0-3: online softmax (one query row per thread), O accumulation in registers, epilogue
+//      warp  4  : TMEM alloc + TMA producer (Q once, K/V double-buffered)
+//      warp  5  : tcgen05.mma issuer:  S = Q K^T (TMEM cols 0..127),  PV = P V (TMEM cols 128..191)
+//    P (bf16) is written by the softmax warps into SWIZZLE_128B K-major smem and consumed as the A operand;
+//    V is consumed as an MN-major B operand straight from its TMA tile (no transpose anywhere).
+//    ~112 KB smem and 256 TMEM columns per CTA -> two CTAs per SM overlap softmax with MMA.
+//  * attn_temporal_kernel: attention over the frame axis (F <= 32), one warp per (batch, pixel, head),
+//    reading the fused qkv projection in place (frame stride HW*3C) - HBM-bound, SIMT.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lkgd {
+
+constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
+constexpr int AT_TILE = AT_BQ * AT_D * 2;  // 16 KB
+constexpr int AT_THREADS = 192;
+constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + 2 * AT_TILE /*P*/ + 128;
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* out;
+  int ldo, heads, d, Nq, Nk;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_TILE;
+  uint8_t* sV = smem + 3 * AT_TILE;
+  uint8_t* sP = smem + 5 * AT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, img = blockIdx.z;
+  const int T = (p.Nk + AT_BK - 1) / AT_BK;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 128);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, AT_TILE);
+      tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
+        tma_load_4d(sK + st * AT_TILE, &p.tmK, &kv_full[st], 0, head, j * AT_BK, img);
+        tma_load_4d(sV + st * AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BK, img);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_BK);             // N = 128 keys
+      const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);     // P_j is in smem, S columns are free again
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < AT_BK / 16; ++ks) {
+          const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (ks >> 2) * AT_TILE)) + 2 * (ks & 3);
+          const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + st * AT_TILE + ks * 2048));
+          umma_bf16(tmem_O, pdesc, vdesc, idesc_o, ks != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < T) {
+          const int sn = (j + 1) & 1;
+          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + sn * AT_TILE));
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / accumulate / epilogue
+    const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[AT_D];
+#pragma unroll
+    for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+    uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv_valid = min(AT_BK, p.Nk - j * AT_BK);
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < AT_BK; c += 32) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + c, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = ex2f(m_run - m_new);
+      // pass 2: p = 2^(s*c - m), packed to bf16 into the swizzled K-major P tile
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < AT_BK; c += 32) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + c, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_new)) : 0.f;
+          float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_new)) : 0.f;
+          // the row sum uses the same bf16-rounded values the MMA will see
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          float2 hf = __bfloat1622float2(h);
+          lsum += hf.x + hf.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint8_t* blk = prow + (c >> 6) * AT_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 63) >> 3) + q;   // 16-byte chunk index within the 128-byte row
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      tc_fence_before();          // S reads are complete before the MMA warp may overwrite S
+      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(p_full);
+      // accumulate O = O*alpha + P_j V_j
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < AT_D; c += 32) {
+        uint32_t t[32];
+        tmem_ld32(tmem_O + lane_addr + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(t[i]));
+      }
+      tc_fence_before();
+    }
+    if (q0 + r < p.Nq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
+      if (p.d == AT_D) {
+#pragma unroll
+        for (int c = 0; c < AT_D; c += 8)
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
+                         pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+      } else {
+#pragma unroll
+        for (int c = 0; c < AT_D; ++c)
+          if (c < p.d) orow[c] = __float2bfloat16(o[c] * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- temporal
+template <int D>
+__global__ void __launch_bounds__(128) attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int B, int F, int HW,
+                                                            int heads, float scale) {
+  __shared__ __align__(16) __nv_bfloat16 sK[4][32][D];
+  __shared__ __align__(16) __nv_bfloat16 sV[4][32][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long seq = (long long)blockIdx.x * 4 + warp;
+  const long long total = (long long)B * HW * heads;
+  if (seq >= total) return;
+  const int head = (int)(seq % heads);
+  const int pix = (int)((seq / heads) % HW);
+  const int b = (int)(seq / ((long long)heads * HW));
+  const int C = heads * D;
+  const size_t ld = (size_t)3 * C;
+  constexpr int VPR = D / 8;  // 16-byte vectors per row
+  const __nv_bfloat16* base = qkv + ((size_t)b * F * HW + pix) * ld + head * D;
+  for (int idx = lane; idx < F * VPR; idx += 32) {
+    const int j = idx / VPR, v = idx % VPR;
+    const __nv_bfloat16* row = base + (size_t)j * HW * ld;
+    *reinterpret_cast<uint4*>(&sK[warp][j][v * 8]) = __ldg(reinterpret_cast<const uint4*>(row + C + v * 8));
+    *reinterpret_cast<uint4*>(&sV[warp][j][v * 8]) = __ldg(reinterpret_cast<const uint4*>(row + 2 * C + v * 8));
+  }
+  __syncwarp();
+  if (lane >= F) return;
+  float q[D];
+  {
+    const __nv_bfloat16* row = base + (size_t)lane * HW * ld;
+#pragma unroll
+    for (int v = 0; v < VPR; ++v) {
+      float f[8];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row + v * 8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[v * 8 + i] = f[i] * scale;
+    }
+  }
+  float s[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < F) {
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < D; t += 2) {
+        const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sK[warp][j][t]));
+        acc = fmaf(q[t], kk.x, acc);
+        acc = fmaf(q[t + 1], kk.y, acc);
+      }
+      s[j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+  float l = 0.f;
+  float o[D];
+#pragma unroll
+  for (int t = 0; t < D; ++t) o[t] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < F) {
+      const float pj = __expf(s[j] - mx);
+      l += pj;
+#pragma unroll
+      for (int t = 0; t < D; t += 2) {
+        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sV[warp][j][t]));
+        o[t] = fmaf(pj, vv.x, o[t]);
+        o[t + 1] = fmaf(pj, vv.y, o[t + 1]);
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  __nv_bfloat16* orow = out + (((size_t)b * F + lane) * HW + pix) * C + head * D;
+#pragma unroll
+  for (int v = 0; v < VPR; ++v)
+    *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(
+        pack_bf16x2(o[v * 8] * inv, o[v * 8 + 1] * inv), pack_bf16x2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv),
+        pack_bf16x2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv), pack_bf16x2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv));
+}
+
+static int attn_tmap(CUtensorMap* tm, const void* base, int ld, int heads, int d, int N, int n_img) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)n_img};
+  uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * N};
+  uint32_t box[4] = {AT_D, 1, AT_BQ, 1};
+  return make_tmap(tm, base, 4, dims, strides, box);
+}
+
+}  // namespace lkgd
+
+using namespace lkgd;
+
+extern "C" int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                              void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
+                              int32_t Nk, float scale, void* stream) {
+  if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d > AT_D || d % 8 || d <= 0) return LKGD_ESHAPE;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return LKGD_EALIGN;
+  if (heads > 65535 || n_img > 65535) return LKGD_ESHAPE;
+  AttnParams p;
+  int rc;
+  if ((rc = attn_tmap(&p.tmQ, q, ldq, heads, d, Nq, n_img))) return rc;
+  if ((rc = attn_tmap(&p.tmK, k, ldk, heads, d, Nk, n_img))) return rc;
+  if ((rc = attn_tmap(&p.tmV, v, ldv, heads, d, Nk, n_img))) return rc;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr = true;
+  }
+  dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
+  attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, int32_t F, int32_t HW, int32_t heads,
+                                       int32_t d, float scale, void* stream) {
+  if (B <= 0 || F <= 0 || F > 32 || HW <= 0 || heads <= 0) return LKGD_ESHAPE;
+  if (!aligned16(qkv) || !aligned16(out)) return LKGD_EALIGN;
+  const long long total = (long long)B * HW * heads;
+  const unsigned grid = (unsigned)((total + 3) / 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  switch (d) {
+    case 16: attn_temporal_kernel<16><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
+    case 32: attn_temporal_kernel<32><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
+    case 64: attn_temporal_kernel<64><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
+    default: return LKGD_ESHAPE;
+  }
+  return launch_epilogue();
+}

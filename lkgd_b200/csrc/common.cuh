@@ -1,0 +1,22 @@
+// Shared host-side helpers: error plumbing, launch counter, SM count, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/lkgd_b200.h"
+
+namespace lkgd {
+
+int set_cuda_error(cudaError_t e);          // records the message, returns LKGD_ECUDA
+int launch_epilogue();                      // counts the launch, checks cudaGetLastError()
+int sm_count();
+// bf16 tiled tensor map, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides in bytes for dims 1..rank-1.
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+              const uint32_t* box);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace lkgd

@@ -1,0 +1,447 @@
+// Persistent warp-specialised GEMM / implicit-GEMM convolution for sm_100a.
+//   warp 0 (one lane): TMA producer      - cp.async.bulk.tensor tiles of A (2-D / 4-D box, zero-filled halo) and B
+//   warp 1 (one lane): tcgen05.mma issuer - 128 x BN x 16 UMMAs, fp32 accumulators in TMEM (2 x 256 columns)
+//   warps 2..5       : epilogue           - tcgen05.ld -> bias / row-vector / act / GEGLU / residual mix -> global
+// smem ring: 4 stages x (A 128x64 bf16 = 16 KB, B BNx64 bf16 <= 32 KB), SWIZZLE_128B everywhere.
+// See include/lkgd_b200.h (lkgd_gemm) for the contract and the reference call sites it replaces.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lkgd {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (max BN = 256)
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MAX_TAPS = 9;
+
+struct GemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  CUtensorMap tmA1;
+  CUtensorMap tmB1;
+  int mode, M, N, BN;
+  int kb0, ntaps, kb1, k0;           // k-blocks per tap, taps, k-blocks of segment 1, channels per tap
+  int H, W, TW, TH, tiles_w, tiles_h;  // conv output geometry + tile patch
+  int HW, F, tiles_p;                  // tconv
+  int m_tiles, n_tiles;
+  signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  int rv_mode, rv_HW, rv_F, rv_B;
+  int act;
+  float s0, s1, s2;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  int ldr1, ldr2;
+  void* out;
+  int ldo, out_f32, n_store;
+};
+
+__device__ __forceinline__ int rowvec_index(int mode, int m, int HW, int F, int B) {
+  switch (mode) {
+    case LKGD_RV_FRAME: return m / HW;
+    case LKGD_RV_FRAMEPOS: return (m / HW) % F;
+    case LKGD_RV_BATCH: return m / (HW * F);
+    case LKGD_RV_TCTX_0272: return ((m / (HW * F)) * HW + (m % HW)) % B;
+    default: return 0;
+  }
+}
+
+struct TileCoord {
+  int c1, c2, c3;  // TMA coordinates of the tile origin (besides the channel coordinate)
+};
+
+__device__ __forceinline__ void tile_origin(const GemmParams& p, int m_tile, TileCoord& t) {
+  if (p.mode == LKGD_A_LINEAR) {
+    t.c1 = m_tile * BM; t.c2 = 0; t.c3 = 0;
+  } else if (p.mode == LKGD_A_CONV3X3) {
+    int per_img = p.tiles_w * p.tiles_h;
+    int img = m_tile / per_img, r = m_tile % per_img;
+    t.c1 = (r % p.tiles_w) * p.TW;   // w0
+    t.c2 = (r / p.tiles_w) * p.TH;   // h0
+    t.c3 = img;
+  } else {  // TCONV3: tile = (bf, tile_p)
+    int bf = m_tile / p.tiles_p;
+    t.c1 = (m_tile % p.tiles_p) * BM;  // p0
+    t.c2 = bf % p.F;                   // f
+    t.c3 = bf / p.F;                   // b
+  }
+}
+
+// output row for local row r of a tile; returns -1 when the row is outside the tensor
+__device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoord& t, int r) {
+  if (p.mode == LKGD_A_LINEAR) {
+    int m = t.c1 + r;
+    return m < p.M ? m : -1;
+  } else if (p.mode == LKGD_A_CONV3X3) {
+    int w = t.c1 + r % p.TW, h = t.c2 + r / p.TW;
+    return (w < p.W && h < p.H) ? ((long long)t.c3 * p.H + h) * p.W + w : -1;
+  } else {
+    int pp = t.c1 + r;
+    return pp < p.HW ? ((long long)(t.c3 * p.F + t.c2)) * p.HW + pp : -1;
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kiters = p.ntaps * p.kb0 + p.kb1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+      fence_barrier_init();
+      tma_prefetch_desc(&p.tmA[0]);
+      tma_prefetch_desc(&p.tmB);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile % p.n_tiles) * p.BN;
+      TileCoord tc; tile_origin(p, m_tile, tc);
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx_bytes);
+        void* dA = smA + stage * A_STAGE_BYTES;
+        void* dB = smB + stage * B_STAGE_BYTES;
+        const bool seg1 = it >= p.ntaps * p.kb0;
+        int tap = 0, kb, dx = 0, dy = 0;
+        const CUtensorMap* mA;
+        if (!seg1) {
+          tap = it / p.kb0; kb = it % p.kb0;
+          mA = &p.tmA[p.tap_map[tap]]; dx = p.tap_dx[tap]; dy = p.tap_dy[tap];
+        } else {
+          kb = it - p.ntaps * p.kb0;
+          mA = &p.tmA1;
+        }
+        if (p.mode == LKGD_A_LINEAR) tma_load_2d(dA, mA, &full[stage], kb * BK, tc.c1);
+        else if (p.mode == LKGD_A_CONV3X3) tma_load_4d(dA, mA, &full[stage], kb * BK, tc.c1 + dx, tc.c2 + dy, tc.c3);
+        else tma_load_4d(dA, mA, &full[stage], kb * BK, tc.c1, tc.c2 + dy, tc.c3);
+        if (!seg1) tma_load_2d(dB, &p.tmB, &full[stage], tap * p.k0 + kb * BK, n0);
+        else tma_load_2d(dB, &p.tmB1, &full[stage], kb * BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t idesc = umma_idesc_bf16(p.BN);
+    int tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int as = tile_iter & 1;
+      mbar_wait(&tempty[as], ((tile_iter >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * 256;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(smA + stage * A_STAGE_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(smB + stage * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        umma_commit(&empty[stage]);
+        if (it == kiters - 1) umma_commit(&tfull[as]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane each)
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;                       // row of the tile owned by this thread
+    const bool geglu = p.act == LKGD_ACT_GEGLU;
+    const int bn_out = geglu ? p.BN / 2 : p.BN;
+    const int n_store = p.n_store > 0 ? p.n_store : (geglu ? p.N / 2 : p.N);
+    int tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int as = tile_iter & 1;
+      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+      TileCoord tc; tile_origin(p, m_tile, tc);
+      const long long m = tile_row(p, tc, r);
+      mbar_wait(&tfull[as], (tile_iter >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(lane_base) << 16);
+      const float* rv = nullptr;
+      if (p.rowvec != nullptr && m >= 0)
+        rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * (geglu ? p.N / 2 : p.N);
+      for (int c = 0; c < bn_out; c += 16) {
+        uint32_t a[16], g[16];
+        tmem_ld16(taddr + c, a);
+        if (geglu) tmem_ld16(taddr + bn_out + c, g);
+        tmem_ld_wait();
+        if (m < 0) continue;
+        const int n_in = n_tile * p.BN + c;            // column in Bw / bias space (value half for GEGLU)
+        const int n_out = n_tile * bn_out + c;         // output column
+        if (n_out >= n_store) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += (n_in + j < p.N) ? __ldg(p.bias + n_in + j) : 0.f;
+        }
+        if (geglu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float gate = __uint_as_float(g[j]) + (p.bias != nullptr ? __ldg(p.bias + n_in + bn_out + j) : 0.f);
+            v[j] *= gelu_erf_f(gate);
+          }
+        }
+        if (rv != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += (n_out + j < n_store) ? __ldg(rv + n_out + j) : 0.f;
+        }
+        if (p.act == LKGD_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        }
+        const bool full16 = n_out + 16 <= n_store;
+        if (p.s0 != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.s0;
+        }
+        if (p.res1 != nullptr) {
+          const __nv_bfloat16* rp = p.res1 + (size_t)m * p.ldr1 + n_out;
+          if (full16 && (p.ldr1 & 7) == 0) {
+            float f[8];
+            uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+            uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+            unpack_bf16x8(q0, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += p.s1 * f[j];
+            unpack_bf16x8(q1, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 + j] += p.s1 * f[j];
+          } else {
+            for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += p.s1 * __bfloat162float(rp[j]);
+          }
+        }
+        if (p.res2 != nullptr) {
+          const __nv_bfloat16* rp = p.res2 + (size_t)m * p.ldr2 + n_out;
+          if (full16 && (p.ldr2 & 7) == 0) {
+            float f[8];
+            uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+            uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+            unpack_bf16x8(q0, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += p.s2 * f[j];
+            unpack_bf16x8(q1, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 + j] += p.s2 * f[j];
+          } else {
+            for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += p.s2 * __bfloat162float(rp[j]);
+          }
+        }
+        if (p.out_f32) {
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n_out;
+          if (full16 && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 16 && n_out + j < n_store; ++j) op[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n_out;
+          if (full16 && (p.ldo & 7) == 0) {
+            uint4 q0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+            uint4 q1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            reinterpret_cast<uint4*>(op)[0] = q0;
+            reinterpret_cast<uint4*>(op)[1] = q1;
+          } else {
+            for (int j = 0; j < 16 && n_out + j < n_store; ++j) op[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+static int choose_bn(int N, bool geglu) {
+  if (geglu) return 256;
+  int n16 = (N + 15) / 16 * 16;
+  if (n16 <= 256) return n16;
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 256;  // tail tile handled by TMA zero-fill + store masking
+}
+
+static void choose_patch(int H, int W, int& TW, int& TH) {
+  // TW * TH = 128 pixels per tile; minimise padded area, prefer wide patches (longer contiguous runs)
+  long best = -1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    int th = 128 / tw;
+    long area = (long)((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
+    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
+  }
+}
+
+static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
+  memset(&p, 0, sizeof(p));
+  if (a->M <= 0 || a->N <= 0 || a->K0 <= 0) return LKGD_ESHAPE;
+  if (a->K0 % 8 || a->K1 % 8 || a->ldb % 8 || (a->K1 && a->ldb1 % 8)) return LKGD_EALIGN;
+  const bool geglu = a->act == LKGD_ACT_GEGLU;
+  if (geglu && (a->N % 256)) return LKGD_ESHAPE;
+  p.mode = a->a_mode; p.M = a->M; p.N = a->N;
+  p.BN = choose_bn(a->N, geglu);
+  p.k0 = a->K0;
+  p.kb0 = (a->K0 + BK - 1) / BK;
+  p.kb1 = a->K1 > 0 ? (a->K1 + BK - 1) / BK : 0;
+  p.n_tiles = (a->N + p.BN - 1) / p.BN;
+  int rc;
+  if (a->a_mode == LKGD_A_LINEAR) {
+    if (a->lda % 8 || (a->K1 && a->lda1 % 8)) return LKGD_EALIGN;
+    p.ntaps = 1; p.tap_map[0] = 0;
+    p.m_tiles = (a->M + BM - 1) / BM;
+    uint64_t dims[2] = {(uint64_t)a->K0, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    if ((rc = make_tmap(&p.tmA[0], a->A, 2, dims, strides, box))) return rc;
+    if (a->K1) {
+      uint64_t d1[2] = {(uint64_t)a->K1, (uint64_t)a->M};
+      uint64_t s1[1] = {(uint64_t)a->lda1 * 2};
+      if ((rc = make_tmap(&p.tmA1, a->A1, 2, d1, s1, box))) return rc;
+    }
+  } else if (a->a_mode == LKGD_A_CONV3X3) {
+    const int s = a->stride;
+    if (s != 1 && s != 2) return LKGD_ESHAPE;
+    const int Ho = (a->Hin - 1) / s + 1, Wo = (a->Win - 1) / s + 1;
+    if ((long long)a->NIMG * Ho * Wo != a->M) return LKGD_ESHAPE;
+    p.H = Ho; p.W = Wo;
+    choose_patch(Ho, Wo, p.TW, p.TH);
+    p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
+    p.m_tiles = a->NIMG * p.tiles_w * p.tiles_h;
+    p.ntaps = 9;
+    uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    const uint64_t C = a->K0;
+    if (s == 1) {
+      uint64_t dims[4] = {C, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->NIMG};
+      uint64_t strides[3] = {C * 2, C * 2 * a->Win, C * 2 * a->Win * a->Hin};
+      if ((rc = make_tmap(&p.tmA[0], a->A, 4, dims, strides, box))) return rc;
+      for (int t = 0; t < 9; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = t % 3 - 1; p.tap_dy[t] = t / 3 - 1; }
+    } else {
+      // four parity planes of the input; tap (ky,kx) reads plane ((ky+1)&1, (kx+1)&1) at offset (ky==0?-1:0)
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          uint64_t dims[4] = {C, (uint64_t)((a->Win - px + 1) / 2), (uint64_t)((a->Hin - py + 1) / 2),
+                              (uint64_t)a->NIMG};
+          if (dims[1] == 0 || dims[2] == 0) return LKGD_ESHAPE;
+          uint64_t strides[3] = {C * 2 * 2, C * 2 * a->Win * 2, C * 2 * a->Win * a->Hin};
+          const char* base = reinterpret_cast<const char*>(a->A) + ((size_t)py * a->Win + px) * C * 2;
+          if ((rc = make_tmap(&p.tmA[py * 2 + px], base, 4, dims, strides, box))) return rc;
+        }
+      for (int t = 0; t < 9; ++t) {
+        int ky = t / 3, kx = t % 3;
+        p.tap_map[t] = (signed char)((((ky + 1) & 1) * 2) + ((kx + 1) & 1));
+        p.tap_dy[t] = ky == 0 ? -1 : 0; p.tap_dx[t] = kx == 0 ? -1 : 0;
+      }
+    }
+    if (a->K1) {  // centre-tap segment over an [NIMG, Ho, Wo, K1] tensor
+      uint64_t C1 = a->K1;
+      uint64_t dims[4] = {C1, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)a->NIMG};
+      uint64_t strides[3] = {C1 * 2, C1 * 2 * Wo, C1 * 2 * Wo * Ho};
+      if ((rc = make_tmap(&p.tmA1, a->A1, 4, dims, strides, box))) return rc;
+    }
+  } else if (a->a_mode == LKGD_A_TCONV3) {
+    if ((long long)a->NIMG * a->F * a->HW != a->M) return LKGD_ESHAPE;
+    p.HW = a->HW; p.F = a->F;
+    p.tiles_p = (a->HW + BM - 1) / BM;
+    p.m_tiles = a->NIMG * a->F * p.tiles_p;
+    p.ntaps = 3;
+    for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = 0; p.tap_dy[t] = t - 1; }
+    uint32_t box[4] = {BK, BM, 1, 1};
+    const uint64_t C = a->K0;
+    uint64_t dims[4] = {C, (uint64_t)a->HW, (uint64_t)a->F, (uint64_t)a->NIMG};
+    uint64_t strides[3] = {C * 2, C * 2 * a->HW, C * 2 * a->HW * a->F};
+    if ((rc = make_tmap(&p.tmA[0], a->A, 4, dims, strides, box))) return rc;
+    if (a->K1) {
+      uint64_t C1 = a->K1;
+      uint64_t d1[4] = {C1, (uint64_t)a->HW, (uint64_t)a->F, (uint64_t)a->NIMG};
+      uint64_t s1[3] = {C1 * 2, C1 * 2 * a->HW, C1 * 2 * a->HW * a->F};
+      if ((rc = make_tmap(&p.tmA1, a->A1, 4, d1, s1, box))) return rc;
+    }
+  } else {
+    return LKGD_ESHAPE;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.ntaps * a->K0, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)p.BN};
+    if ((rc = make_tmap(&p.tmB, a->Bw, 2, dims, strides, box))) return rc;
+    if (a->K1) {
+      uint64_t d1[2] = {(uint64_t)a->K1, (uint64_t)a->N};
+      uint64_t s1[1] = {(uint64_t)a->ldb1 * 2};
+      if ((rc = make_tmap(&p.tmB1, a->Bw1, 2, d1, s1, box))) return rc;
+    }
+  }
+  p.bias = a->bias; p.rowvec = a->rowvec;
+  p.rv_mode = a->rowvec ? a->rv_mode : LKGD_RV_NONE;
+  p.rv_HW = a->rv_HW > 0 ? a->rv_HW : 1; p.rv_F = a->rv_F > 0 ? a->rv_F : 1; p.rv_B = a->rv_B > 0 ? a->rv_B : 1;
+  p.act = a->act; p.s0 = a->s0; p.s1 = a->s1; p.s2 = a->s2;
+  p.res1 = reinterpret_cast<const __nv_bfloat16*>(a->res1); p.ldr1 = a->ldr1;
+  p.res2 = reinterpret_cast<const __nv_bfloat16*>(a->res2); p.ldr2 = a->ldr2;
+  p.out = a->out; p.ldo = a->ldo; p.out_f32 = a->out_f32; p.n_store = a->n_store;
+  return LKGD_OK;
+}
+
+}  // namespace lkgd
+
+using namespace lkgd;
+
+extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
+  if (a == nullptr || a->A == nullptr || a->Bw == nullptr || a->out == nullptr) return LKGD_ESHAPE;
+  GemmParams p;
+  int rc = fill_params(a, p);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  int sms = sm_count();
+  if (grid > sms) grid = sms;
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return launch_epilogue();
+}

@@ -1,0 +1,274 @@
+// Bandwidth-bound glue of the denoise step: layout packing, upsample / concat, residual injection, the fp32
+// conditioning helpers and the fused CFG + Euler-Karras update.  See include/lkgd_b200.h for the contract.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lkgd {
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == 1) return silu_f(x);
+  if (act == 3) return x > 0.f ? x : 0.1f * x;
+  return x;
+}
+
+// one warp per output column n; loops over the (few) rows m
+__global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
+                                    const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int N, int K,
+                                    int act_in, int act_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* w = W + (size_t)n * K;
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (m0 + i < M) acc[i] = fmaf(act_apply(__ldg(x + (size_t)(m0 + i) * ldx + k), act_in), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane == 0) {
+      for (int i = 0; i < 8 && m0 + i < M; ++i)
+        y[(size_t)(m0 + i) * ldy + n] = act_apply(acc[i] + (b ? b[n] : 0.f), act_out);
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int M, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * half) return;
+  const int m = idx / half, k = idx % half;
+  const float freq = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float arg = t[m] * freq;
+  out[(size_t)m * dim + k] = cosf(arg);          // flip_sin_to_cos=True: [cos | sin]
+  out[(size_t)m * dim + half + k] = sinf(arg);
+  if ((dim & 1) && k == 0) out[(size_t)m * dim + dim - 1] = 0.f;
+}
+
+// out[n,f,h,w,c] (bf16, Cpad channels) from NCHW-per-frame fp32 sources; thread = one pixel, 8 channels per store
+__global__ void pack_input_kernel(const float* __restrict__ s0, int N0, int C0, float scale0,
+                                  const float* __restrict__ s1, int N1, int C1, __nv_bfloat16* __restrict__ out,
+                                  int N, int F, int HW, int Cpad) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * F * HW;
+  if (pix >= total) return;
+  const int p = (int)(pix % HW);
+  const int f = (int)((pix / HW) % F);
+  const int n = (int)(pix / ((long long)HW * F));
+  __nv_bfloat16* o = out + pix * Cpad;
+  for (int c8 = 0; c8 < Cpad; c8 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c8 + i;
+      float val = 0.f;
+      if (c < C0) val = s0[(((size_t)(n % N0) * F + f) * C0 + c) * HW + p] * scale0;
+      else if (c < C0 + C1) val = s1[(((size_t)(n % N1) * F + f) * C1 + (c - C0)) * HW + p];
+      v[i] = val;
+    }
+    *reinterpret_cast<uint4*>(o + c8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+__global__ void unpack_output_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, long long NF,
+                                     int C, int HW) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NF * C * HW) return;
+  const int p = (int)(idx % HW);
+  const int c = (int)((idx / HW) % C);
+  const long long nf = idx / ((long long)HW * C);
+  dst[idx] = src[(nf * HW + p) * ld + c];
+}
+
+// 32x32 smem-tiled transposes between [N, C, HW] fp32 and [N, HW, C] bf16
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) dst[((size_t)n * HW + p) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[((size_t)n * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W,
+                                  int vecs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over output vectors
+  const long long total = (long long)N * 4 * H * W * vecs;
+  if (idx >= total) return;
+  const int v = (int)(idx % vecs);
+  long long pix = idx / vecs;
+  const int wo = (int)(pix % (2 * W));
+  const int ho = (int)((pix / (2 * W)) % (2 * H));
+  const int n = (int)(pix / ((long long)4 * H * W));
+  dst[idx] = __ldg(src + (((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * vecs + v);
+}
+
+__global__ void concat_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb,
+                              uint4* __restrict__ dst, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vt = va + vb;
+  if (idx >= M * vt) return;
+  const long long m = idx / vt;
+  const int v = (int)(idx % vt);
+  dst[idx] = v < va ? __ldg(a + m * va + v) : __ldg(b + m * vb + (v - va));
+}
+
+__global__ void axpby_kernel(const uint4* __restrict__ x, float alpha, uint4* __restrict__ y, float beta,
+                             long long nvec) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nvec) return;
+  float fx[8], fy[8];
+  unpack_bf16x8(__ldg(x + idx), fx);
+  unpack_bf16x8(y[idx], fy);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fy[i] = alpha * fx[i] + beta * fy[i];
+  y[idx] = make_uint4(pack_bf16x2(fy[0], fy[1]), pack_bf16x2(fy[2], fy[3]), pack_bf16x2(fy[4], fy[5]),
+                      pack_bf16x2(fy[6], fy[7]));
+}
+
+// thread = one (s, f, c, p) element of the fp32 latent; pred is channels-last [2S*F*HW, ld]
+__global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg, const float* __restrict__ guidance,
+                                 const float* __restrict__ x, float* __restrict__ x_next, float* __restrict__ v_out,
+                                 int S, int F, int C, int HW, float sigma, float sigma_next) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)S * F * C * HW;
+  if (idx >= total) return;
+  const int p = (int)(idx % HW);
+  const int c = (int)((idx / HW) % C);
+  const int f = (int)((idx / ((long long)HW * C)) % F);
+  const int s = (int)(idx / ((long long)HW * C * F));
+  const size_t row_u = ((size_t)s * F + f) * HW + p;
+  float v = pred[row_u * ld + c];
+  if (cfg) {
+    const size_t row_c = ((size_t)(S + s) * F + f) * HW + p;
+    const float cnd = pred[row_c * ld + c];
+    v = v + guidance[f] * (cnd - v);
+  }
+  if (v_out) v_out[idx] = v;
+  const float xs = x[idx];
+  const float s2 = sigma * sigma + 1.0f;
+  const float x0 = v * (-sigma / sqrtf(s2)) + xs / s2;
+  const float deriv = (xs - x0) / sigma;
+  x_next[idx] = xs + deriv * (sigma_next - sigma);
+}
+
+}  // namespace lkgd
+
+using namespace lkgd;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" int lkgd_small_linear(const float* x, int32_t ldx, const float* W, const float* b, float* y, int32_t ldy,
+                                 int32_t M, int32_t N, int32_t K, int32_t act_in, int32_t act_out, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || M > 4096) return LKGD_ESHAPE;
+  small_linear_kernel<<<blocks_for(N, 8), 256, 0, ST(stream)>>>(x, ldx, W, b, y, ldy, M, N, K, act_in, act_out);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_timestep_embedding(const float* t, int32_t M, int32_t dim, float* out, void* stream) {
+  if (M <= 0 || dim < 2) return LKGD_ESHAPE;
+  timestep_embedding_kernel<<<blocks_for((long long)M * (dim / 2), 128), 128, 0, ST(stream)>>>(t, M, dim, out);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* src1, int32_t N1,
+                               int32_t C1, void* out, int32_t N, int32_t F, int32_t H, int32_t W, int32_t Cpad,
+                               void* stream) {
+  if (src1 == nullptr) { C1 = 0; N1 = 1; }
+  if (N <= 0 || F <= 0 || Cpad % 8 || C0 + C1 > Cpad || N0 <= 0 || N1 <= 0) return LKGD_ESHAPE;
+  if (!aligned16(out)) return LKGD_EALIGN;
+  const long long total = (long long)N * F * H * W;
+  pack_input_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src0, N0, C0, scale0, src1, N1, C1,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out), N, F,
+                                                                   H * W, Cpad);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_unpack_output(const float* src, int32_t ld, float* dst, int32_t NF, int32_t C, int32_t H,
+                                  int32_t W, void* stream) {
+  if (NF <= 0 || C <= 0 || C > ld) return LKGD_ESHAPE;
+  const long long total = (long long)NF * C * H * W;
+  unpack_output_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src, ld, dst, NF, C, H * W);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_nchw_to_nhwc(const float* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+                                 void* stream) {
+  if (N <= 0 || C <= 0 || N > 65535) return LKGD_ESHAPE;
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, ST(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, H * W);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_nhwc_to_nchw(const void* src, float* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+                                 void* stream) {
+  if (N <= 0 || C <= 0 || N > 65535) return LKGD_ESHAPE;
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, C, H * W);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (C % 8 || N <= 0) return LKGD_ESHAPE;
+  if (!aligned16(src) || !aligned16(dst)) return LKGD_EALIGN;
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src),
+                                                                   reinterpret_cast<uint4*>(dst), N, H, W, C / 8);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t M,
+                                    void* stream) {
+  if (Ca % 8 || Cb % 8 || M <= 0) return LKGD_ESHAPE;
+  if (!aligned16(a) || !aligned16(b) || !aligned16(dst)) return LKGD_EALIGN;
+  const long long total = (long long)M * ((Ca + Cb) / 8);
+  concat_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(a), Ca / 8,
+                                                               reinterpret_cast<const uint4*>(b), Cb / 8,
+                                                               reinterpret_cast<uint4*>(dst), M);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64_t n, void* stream) {
+  if (n <= 0 || n % 8) return LKGD_ESHAPE;
+  if (!aligned16(x) || !aligned16(y)) return LKGD_EALIGN;
+  axpby_kernel<<<blocks_for(n / 8, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(x), alpha,
+                                                              reinterpret_cast<uint4*>(y), beta, n / 8);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
+                                   float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H,
+                                   int32_t W, float sigma, float sigma_next, void* stream) {
+  if (S <= 0 || F <= 0 || C <= 0 || C > ld || sigma <= 0.f) return LKGD_ESHAPE;
+  const long long total = (long long)S * F * C * H * W;
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, S, F,
+                                                                  C, H * W, sigma, sigma_next);
+  return launch_epilogue();
+}

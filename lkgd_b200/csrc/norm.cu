@@ -1,0 +1,265 @@
+// GroupNorm(+SiLU) and LayerNorm for channels-last bf16 activations: HBM-bound, 128-bit vectorised.
+// GroupNorm is two kernels: (1) per-(sample, channel) sum / sum-of-squares -> fp64 atomics, (2) normalise.
+// See include/lkgd_b200.h for the contract and the reference modules replaced.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lkgd {
+
+// thread layout shared by both GroupNorm kernels: blockDim.x = vecs * rows_par, thread -> (row lane, 8-ch vector)
+struct GnGeom {
+  int C1, C2, C, vecs, rows_par, R, rows_per_cta;
+};
+
+__device__ __forceinline__ uint4 gn_load(const __nv_bfloat16* x1, const __nv_bfloat16* x2, const GnGeom& g,
+                                         long long row, int v) {
+  const int c = v * 8;
+  if (c < g.C1) return __ldg(reinterpret_cast<const uint4*>(x1 + row * g.C1 + c));
+  return __ldg(reinterpret_cast<const uint4*>(x2 + row * g.C2 + (c - g.C1)));
+}
+
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, GnGeom g,
+                                double* __restrict__ sums /* [NS][C][2] */) {
+  extern __shared__ float sh[];  // [rows_par][vecs][16]
+  const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
+  const int ns = blockIdx.y;
+  const int r0 = blockIdx.x * g.rows_per_cta;
+  const int r1 = min(r0 + g.rows_per_cta, g.R);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+    float f[8];
+    unpack_bf16x8(gn_load(x1, x2, g, (long long)ns * g.R + r, v), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+  }
+  float* my = sh + (size_t)threadIdx.x * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { my[i] = s[i]; my[8 + i] = q[i]; }
+  __syncthreads();
+  // thread t < vecs*16 reduces one (vector, component) over the row lanes
+  for (int t = threadIdx.x; t < g.vecs * 16; t += blockDim.x) {
+    const int vv = t / 16, comp = t % 16;
+    float acc = 0.f;
+    for (int rr = 0; rr < g.rows_par; ++rr) acc += sh[((size_t)rr * g.vecs + vv) * 16 + comp];
+    const int c = vv * 8 + (comp & 7);
+    atomicAdd(&sums[((size_t)ns * g.C + c) * 2 + (comp >> 3)], (double)acc);
+  }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, GnGeom g,
+                                const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int groups, int silu,
+                                __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sh[];  // scale[C], shift[C], mean[groups], rstd[groups]
+  float* scale = sh;
+  float* shift = sh + g.C;
+  float* gmean = sh + 2 * g.C;
+  float* grstd = gmean + groups;
+  const int ns = blockIdx.y;
+  const int cpg = g.C / groups;
+  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      s += sums[((size_t)ns * g.C + c) * 2];
+      q += sums[((size_t)ns * g.C + c) * 2 + 1];
+    }
+    const double n = (double)cpg * g.R;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = grstd[gi] * gamma[c];
+    scale[c] = sc;
+    shift[c] = beta[c] - gmean[gi] * sc;
+  }
+  __syncthreads();
+  const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
+  const int r0 = blockIdx.x * g.rows_per_cta;
+  const int r1 = min(r0 + g.rows_per_cta, g.R);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = scale[v * 8 + i]; sf[i] = shift[v * 8 + i]; }
+  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+    const long long row = (long long)ns * g.R + r;
+    float f[8];
+    unpack_bf16x8(gn_load(x1, x2, g, row, v), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], sc[i], sf[i]);
+      f[i] = silu ? silu_f(y) : y;
+    }
+    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                         pack_bf16x2(f[6], f[7]));
+    *reinterpret_cast<uint4*>(out + row * g.C + v * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm
+constexpr int LN_MAXV = 8;  // up to 8 x (32 lanes x 8 channels) = 2048 channels
+
+__device__ __forceinline__ int ln_rowvec_index(int mode, long long m, int HW, int F, int B) {
+  switch (mode) {
+    case LKGD_RV_FRAME: return (int)(m / HW);
+    case LKGD_RV_FRAMEPOS: return (int)((m / HW) % F);
+    case LKGD_RV_BATCH: return (int)(m / ((long long)HW * F));
+    case LKGD_RV_TCTX_0272: return (int)(((m / ((long long)HW * F)) * HW + (m % HW)) % B);
+    default: return 0;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        const float* __restrict__ addvec, int rv_mode, int rv_HW,
+                                                        int rv_F, int rv_B, __nv_bfloat16* sum_out,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float f[NV][8];
+  const __nv_bfloat16* xr = x + row * C;
+  const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * C : nullptr;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(xr + v * 8), f[j]);
+      if (av) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + v * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + v * 8) + 1);
+        f[j][0] += a0.x; f[j][1] += a0.y; f[j][2] += a0.z; f[j][3] += a0.w;
+        f[j][4] += a1.x; f[j][5] += a1.y; f[j][6] += a1.z; f[j][7] += a1.w;
+        // the residual stream is bf16: normalise what is actually stored
+        uint4 o = make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]),
+                             pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
+        if (sum_out) *reinterpret_cast<uint4*>(sum_out + row * C + v * 8) = o;
+        unpack_bf16x8(o, f[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[j][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (lane + 32 * j < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; q = fmaf(d, d, q); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (f[j][i] - mean) * rstd * gg[i] + bb[i];
+      *reinterpret_cast<uint4*>(out + row * C + v * 8) =
+          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                     pack_bf16x2(y[6], y[7]));
+    }
+  }
+}
+
+static GnGeom gn_geom(int C1, int C2, int R) {
+  GnGeom g;
+  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R;
+  g.rows_par = 512 / g.vecs;
+  if (g.rows_par < 1) g.rows_par = 1;
+  if (g.rows_par > R) g.rows_par = R;
+  // ~8 rows per thread per CTA keeps >= 2 waves of CTAs at SVD sizes while amortising the prologue
+  g.rows_per_cta = g.rows_par * 8;
+  return g;
+}
+
+}  // namespace lkgd
+
+using namespace lkgd;
+
+extern "C" size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C) { return (size_t)NS * C * 2 * sizeof(double); }
+
+extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R,
+                              int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                              void* out, void* workspace, size_t ws_bytes, void* stream) {
+  if (x2 == nullptr) C2 = 0;
+  const int C = C1 + C2;
+  if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
+  if (!aligned16(x1) || !aligned16(out) || (x2 && !aligned16(x2))) return LKGD_EALIGN;
+  if (ws_bytes < lkgd_groupnorm_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GnGeom g = gn_geom(C1, C2, R);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, lkgd_groupnorm_workspace(NS, C), st);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
+  const int threads = g.vecs * g.rows_par;
+  const size_t sh1 = (size_t)threads * 16 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  gn_stats_kernel<<<grid, threads, sh1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1),
+                                              reinterpret_cast<const __nv_bfloat16*>(x2), g,
+                                              reinterpret_cast<double*>(workspace));
+  int rc = launch_epilogue();
+  if (rc) return rc;
+  const size_t sh2 = (size_t)(2 * C + 2 * groups) * sizeof(float);
+  gn_apply_kernel<<<grid, threads, sh2, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1),
+                                              reinterpret_cast<const __nv_bfloat16*>(x2), g,
+                                              reinterpret_cast<const double*>(workspace), gamma, beta, eps, groups,
+                                              silu, reinterpret_cast<__nv_bfloat16*>(out));
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                              const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B,
+                              void* sum_out, void* out, void* stream) {
+  if (M <= 0 || C <= 0 || C % 8 || C > LN_MAXV * 256) return LKGD_ESHAPE;
+  if (!aligned16(x) || !aligned16(out) || (sum_out && !aligned16(sum_out)) || (addvec && !aligned16(addvec)) ||
+      !aligned16(gamma) || !aligned16(beta))
+    return LKGD_EALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 8;
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  const int nv = (C / 8 + 31) / 32;
+  if (rv_HW <= 0) rv_HW = 1;
+  if (rv_F <= 0) rv_F = 1;
+  if (rv_B <= 0) rv_B = 1;
+#define LN_LAUNCH(NV)                                                                                              \
+  layernorm_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, gamma, beta, eps,    \
+                                             addvec, rv_mode, rv_HW, rv_F, rv_B,                                   \
+                                             reinterpret_cast<__nv_bfloat16*>(sum_out),                            \
+                                             reinterpret_cast<__nv_bfloat16*>(out))
+  switch (nv) {
+    case 1: LN_LAUNCH(1); break;
+    case 2: LN_LAUNCH(2); break;
+    case 3: LN_LAUNCH(3); break;
+    case 4: LN_LAUNCH(4); break;
+    case 5: LN_LAUNCH(5); break;
+    default: LN_LAUNCH(8); break;
+  }
+#undef LN_LAUNCH
+  return launch_epilogue();
+}

@@ -1,0 +1,438 @@
+"""Block-graph executor of the SVD / LKGD spatio-temporal UNet on the lkgd_b200 CUDA kernels.
+
+Resident activation layout: channels-last bf16, one row per (batch, frame, pixel): ``[B*F*H*W, C]``.  Spatial
+ops see it as [B*F, HW, C]; temporal ops address the same buffer as [B, F, HW, C] (frame stride HW*C) - there
+is no physical transpose between the spatial and temporal halves of a block (the reference alternates NCHW,
+[BF,HW,C] and [B*HW,F,C]: patch/patch.py:592-597,682-684).
+
+``Packed*`` objects hold kernel-ready weights (bf16 [N,K] K-major, conv kernels as [Cout, tap, Cin], fused QKV,
+tile-interleaved GEGLU, fp32 norms / embeddings MLPs).  The arithmetic order follows SURVEY.md Appendix A
+(diffusers 0.27.2) and the reference forward ``models/unet_spatio_temporal_condition_controlnet.py:358-508``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import modules as M
+from . import ops
+from .ops import (A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU, ACT_NONE, ACT_SILU, RV_BATCH, RV_FRAMEPOS, RV_NONE,
+                  RV_TCTX_0272, bf16)
+
+SL_SILU, SL_LEAKY = 1, 3
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _b16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(bf16).contiguous()
+
+
+def _lin_parts(mod):
+    """(weight fp32 [N,K], bias fp32 | None, lora (A [r,K], B*scaling [N,r]) | None) of a Linear / LoraLinear."""
+    if isinstance(mod, M.LoraLinear):
+        base = mod.base_layer
+        lora = None
+        if not mod.merged:
+            a = mod.lora_A[mod.adapter_name].weight
+            b = mod.lora_B[mod.adapter_name].weight
+            lora = (_f32(a), _f32(b) * mod.scaling)
+        return _f32(base.weight), (None if base.bias is None else _f32(base.bias)), lora
+    return _f32(mod.weight), (None if mod.bias is None else _f32(mod.bias)), None
+
+
+def _merged_weight(mod) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    w, b, lora = _lin_parts(mod)
+    if lora is not None:
+        w = w + lora[1] @ lora[0]          # W + s * B A   (reference models/lora_layer.py:406)
+    return w, b
+
+
+def _conv3x3_weight(conv, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None):
+    w = conv.weight.detach().to(torch.float32)               # [Cout, Cin, 3, 3]
+    co, ci = w.shape[:2]
+    cin_pad, cout_pad = cin_pad or ci, cout_pad or co
+    wk = torch.zeros(cout_pad, 3, 3, cin_pad, device=w.device, dtype=torch.float32)
+    wk[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+    b = torch.zeros(cout_pad, device=w.device, dtype=torch.float32)
+    b[:co] = conv.bias.detach().to(torch.float32)
+    return wk.reshape(cout_pad, 9 * cin_pad).to(bf16).contiguous(), b
+
+
+@dataclass
+class Norm:
+    g: torch.Tensor
+    b: torch.Tensor
+    eps: float
+
+    @staticmethod
+    def of(mod) -> "Norm":
+        return Norm(_f32(mod.weight), _f32(mod.bias), float(mod.eps))
+
+
+@dataclass
+class Dense:
+    """bf16 GEMM weight [+ LoRA pair] + fp32 bias."""
+    w: torch.Tensor
+    b: Optional[torch.Tensor]
+    lora_a: Optional[torch.Tensor] = None    # [r_pad, K] bf16   (t = x A^T)
+    lora_b: Optional[torch.Tensor] = None    # [N, r_pad] bf16   (scaled B)
+
+
+class PackedResBlock:
+    def __init__(self, blk: M.SpatioTemporalResBlock):
+        s, t = blk.spatial_res_block, blk.temporal_res_block
+        self.cin, self.cout = s.in_channels, s.out_channels
+        self.n1, self.n2 = Norm.of(s.norm1), Norm.of(s.norm2)
+        self.w1, self.b1 = _conv3x3_weight(s.conv1)
+        self.w2, self.b2 = _conv3x3_weight(s.conv2)
+        self.temb_w, self.temb_b = _f32(s.time_emb_proj.weight), _f32(s.time_emb_proj.bias)
+        if s.conv_shortcut is not None:
+            self.wsc = _b16(s.conv_shortcut.weight.reshape(self.cout, self.cin))
+            self.bsc = _f32(s.conv_shortcut.bias)
+        else:
+            self.wsc = self.bsc = None
+        self.tn1, self.tn2 = Norm.of(t.norm1), Norm.of(t.norm2)
+        c = self.cout
+        # Conv3d weight [C, C, 3, 1, 1] -> [C, kt, Cin]
+        self.tw1 = _b16(t.conv1.weight[..., 0, 0].permute(0, 2, 1).reshape(c, 3 * c))
+        self.tw2 = _b16(t.conv2.weight[..., 0, 0].permute(0, 2, 1).reshape(c, 3 * c))
+        self.tb1, self.tb2 = _f32(t.conv1.bias), _f32(t.conv2.bias)
+        self.ttemb_w, self.ttemb_b = _f32(t.time_emb_proj.weight), _f32(t.time_emb_proj.bias)
+        self.alpha = float(torch.sigmoid(blk.time_mixer.mix_factor.detach().float()).item())
+
+
+def _dense(mod, fold_lora: bool) -> Dense:
+    w, b, lora = _lin_parts(mod)
+    if lora is None:
+        return Dense(w.to(bf16).contiguous(), b)
+    if not fold_lora:
+        return Dense((w + lora[1] @ lora[0]).to(bf16).contiguous(), b)
+    a, bs = lora
+    r = a.shape[0]
+    r_pad = (r + 7) // 8 * 8
+    ap = torch.zeros(r_pad, a.shape[1], device=a.device)
+    ap[:r] = a
+    bp = torch.zeros(bs.shape[0], r_pad, device=a.device)
+    bp[:, :r] = bs
+    return Dense(w.to(bf16).contiguous(), b, ap.to(bf16).contiguous(), bp.to(bf16).contiguous())
+
+
+def _qkv(attn: M.Attention, fold_lora: bool) -> Dense:
+    """Fused [3C, C] projection; LoRA on q/k/v becomes one [3r, C] down-projection and a block-diagonal
+    [3C, 3r] up-projection consumed as the GEMM's second K segment."""
+    parts = [_lin_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
+    has_lora = any(p[2] is not None for p in parts)
+    if not has_lora or not fold_lora:
+        ws = [(p[0] + p[2][1] @ p[2][0]) if p[2] is not None else p[0] for p in parts]
+        return Dense(torch.cat(ws, 0).to(bf16).contiguous(), None)
+    n, k = parts[0][0].shape
+    r = max(p[2][0].shape[0] for p in parts if p[2] is not None)
+    r_pad = (r + 7) // 8 * 8
+    a_cat = torch.zeros(3 * r_pad, k, device=parts[0][0].device)
+    b_blk = torch.zeros(3 * n, 3 * r_pad, device=parts[0][0].device)
+    for i, p in enumerate(parts):
+        if p[2] is None:
+            continue
+        a, bs = p[2]
+        a_cat[i * r_pad:i * r_pad + a.shape[0]] = a
+        b_blk[i * n:(i + 1) * n, i * r_pad:i * r_pad + a.shape[0]] = bs
+    w = torch.cat([p[0] for p in parts], 0)
+    return Dense(w.to(bf16).contiguous(), None, a_cat.to(bf16).contiguous(), b_blk.to(bf16).contiguous())
+
+
+def _geglu(ff: M.FeedForward, fold_lora: bool):
+    w, b = _merged_weight(ff.net[0].proj)
+    wp, bp = ops.pack_geglu(w.to(bf16), b)
+    return Dense(wp, bp), _dense(ff.net[2], fold_lora)
+
+
+class PackedCross:
+    """attn2: fp32 to_v / to_out for the KV-length-1 collapse + bf16 q/k/v/out for KV > 1."""
+
+    def __init__(self, attn: M.Attention):
+        self.heads, self.d = attn.heads, attn.dim_head
+        self.wv, _ = _merged_weight(attn.to_v)
+        self.wo, self.bo = _merged_weight(attn.to_out[0])
+        self._attn = attn
+        self._general = None
+
+    def general(self):
+        if self._general is None:
+            a = self._attn
+            wq, _ = _merged_weight(a.to_q)
+            wk, _ = _merged_weight(a.to_k)
+            self._general = (wq.to(bf16).contiguous(), torch.cat([wk, self.wv], 0).to(bf16).contiguous(),
+                             self.wo.to(bf16).contiguous())
+        return self._general
+
+
+class PackedTransformer:
+    def __init__(self, t: M.TransformerSpatioTemporalModel, fold_lora: bool):
+        self.heads, self.d, self.c = t.heads, t.dim_head, t.in_channels
+        self.norm = Norm.of(t.norm)
+        self.proj_in, self.proj_out = _dense(t.proj_in, fold_lora), _dense(t.proj_out, fold_lora)
+        sb, tb = t.transformer_blocks[0], t.temporal_transformer_blocks[0]
+        self.s_ln1, self.s_ln2, self.s_ln3 = Norm.of(sb.norm1), Norm.of(sb.norm2), Norm.of(sb.norm3)
+        self.s_qkv, self.s_out = _qkv(sb.attn1, fold_lora), _dense(sb.attn1.to_out[0], fold_lora)
+        self.s_cross = PackedCross(sb.attn2)
+        self.s_ff1, self.s_ff2 = _geglu(sb.ff, fold_lora)
+        self.t_lnin, self.t_ln1, self.t_ln2, self.t_ln3 = (Norm.of(tb.norm_in), Norm.of(tb.norm1), Norm.of(tb.norm2),
+                                                           Norm.of(tb.norm3))
+        self.t_ffin1, self.t_ffin2 = _geglu(tb.ff_in, fold_lora)
+        self.t_qkv, self.t_out = _qkv(tb.attn1, fold_lora), _dense(tb.attn1.to_out[0], fold_lora)
+        self.t_cross = PackedCross(tb.attn2)
+        self.t_ff1, self.t_ff2 = _geglu(tb.ff, fold_lora)
+        self.alpha = float(torch.sigmoid(t.time_mixer.mix_factor.detach().float()).item())
+        pe = t.time_pos_embed
+        self.pe = (_f32(pe.linear_1.weight), _f32(pe.linear_1.bias), _f32(pe.linear_2.weight), _f32(pe.linear_2.bias))
+        self._pos_cache: Dict[int, torch.Tensor] = {}
+
+    def pos_emb(self, F: int) -> torch.Tensor:
+        """time_pos_embed(Timesteps(C)(arange(F))) -> fp32 [F, C]; input-independent, cached per F."""
+        if F not in self._pos_cache:
+            dev = self.pe[0].device
+            e = ops.timestep_embedding(torch.arange(F, device=dev, dtype=torch.float32), self.c)
+            h = ops.small_linear(e, self.pe[0], self.pe[1], act_out=SL_SILU)
+            self._pos_cache[F] = ops.small_linear(h, self.pe[2], self.pe[3])
+        return self._pos_cache[F]
+
+
+@dataclass
+class Geom:
+    B: int
+    F: int
+    H: int
+    W: int
+
+    @property
+    def BF(self):
+        return self.B * self.F
+
+    @property
+    def HW(self):
+        return self.H * self.W
+
+    @property
+    def M(self):
+        return self.B * self.F * self.H * self.W
+
+    def rv(self, mode):
+        return (mode, self.HW, self.F, self.B)
+
+    def down(self):
+        return Geom(self.B, self.F, (self.H - 1) // 2 + 1, (self.W - 1) // 2 + 1)
+
+    def up(self):
+        return Geom(self.B, self.F, self.H * 2, self.W * 2)
+
+
+def dense(x: torch.Tensor, d: Dense, **kw) -> torch.Tensor:
+    """x W^T (+ LoRA second segment) through lkgd_gemm."""
+    if d.lora_a is not None:
+        t = ops.gemm(x, d.lora_a)
+        return ops.gemm(x, d.w, bias=d.b, A1=t, Bw1=d.lora_b, **kw)
+    return ops.gemm(x, d.w, bias=d.b, **kw)
+
+
+class Conditioning:
+    """Everything that depends only on (timestep, added_time_ids, context): computed once per forward with the
+    fp32 small-linear kernel, consumed as GEMM row-vectors / LayerNorm add-vectors."""
+
+    def __init__(self, emb: torch.Tensor, ctx: torch.Tensor):
+        self.emb = emb          # fp32 [B, 4*C0]  (time + added-time embedding, reference ...controlnet.py:406-419)
+        self.ctx = ctx          # fp32 [B, L, D]
+
+    def temb(self, w, b):       # time_emb_proj(SiLU(emb)) -> [B, Cout]
+        return ops.small_linear(self.emb, w, b, act_in=SL_SILU)
+
+    def cross_vec(self, pc: PackedCross):
+        """KV-length-1 cross-attention == to_out(to_v(ctx)) for every query (softmax over one key is 1)."""
+        v = ops.small_linear(self.ctx[:, 0].contiguous(), pc.wv)
+        return ops.small_linear(v, pc.wo, pc.bo)
+
+
+def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor], g: Geom, cond: Conditioning):
+    temb_s = cond.temb(p.temb_w, p.temb_b)
+    temb_t = cond.temb(p.ttemb_w, p.ttemb_b)
+    h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
+    h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH))
+    h = ops.groupnorm(h, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True)
+    if p.wsc is not None:
+        if skip is None:
+            sc = ops.gemm(x, p.wsc, bias=p.bsc)
+        else:
+            c1 = x.shape[1]
+            sc = ops.gemm(x, p.wsc[:, :c1], bias=p.bsc, A1=skip, Bw1=p.wsc[:, c1:])
+    else:
+        if skip is not None:
+            raise ValueError("resblock with concatenated input must have a shortcut conv")
+        sc = x
+    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc)
+    # temporal half: GroupNorm statistics across frames, (3,1,1) conv over the frame axis, AlphaBlender
+    t = ops.groupnorm(s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True)
+    t = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=temb_t, rv=g.rv(RV_BATCH))
+    t = ops.groupnorm(t, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True)
+    # alpha*s + (1-alpha)*(s + conv2(t)) == s + (1-alpha)*conv2(t)
+    return ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=s, s1=1.0)
+
+
+def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor):
+    """KV > 1: h + to_out(attention(to_q(n), to_k(ctx), to_v(ctx))); rows of batch b see ctx[b]."""
+    wq, wkv, wo = pc.general()
+    B, L, D = ctx.shape
+    c = pc.heads * pc.d
+    q = ops.gemm(n, wq)
+    kv = ops.gemm(ctx.reshape(B * L, D).to(bf16).contiguous(), wkv)
+    a = ops.attention(q, kv[:, :c], kv[:, c:], n_img=B, heads=pc.heads, d=pc.d, Nq=g.F * g.HW, Nk=L)
+    return ops.gemm(a, wo, bias=pc.bo, res1=h)
+
+
+def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Conditioning, tctx_mode: int):
+    C = p.c
+    kv1 = cond.ctx.shape[1] == 1
+    h = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False)
+    h = dense(h, p.proj_in)
+    # ---- spatial block (patch/patch.py:390-580)
+    n = ops.layernorm(h, p.s_ln1.g, p.s_ln1.b, p.s_ln1.eps)
+    qkv = dense(n, p.s_qkv)
+    a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, Nq=g.HW,
+                      Nk=g.HW)
+    h = dense(a, p.s_out, res1=h)
+    if kv1:
+        n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross),
+                          rv=g.rv(RV_BATCH), sum_out=h)
+    else:
+        n = ops.layernorm(h, p.s_ln2.g, p.s_ln2.b, p.s_ln2.eps)
+        h = _cross_general(p.s_cross, n, cond.ctx, g, h)
+        n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps)
+    ff = dense(n, p.s_ff1, act=ACT_GEGLU)
+    xs = dense(ff, p.s_ff2, res1=h)                                                   # x_spatial
+    # ---- temporal block (patch/patch.py:582-686) on the same rows, frame stride HW*C
+    t0 = torch.empty_like(xs)
+    n = ops.layernorm(xs, p.t_lnin.g, p.t_lnin.b, p.t_lnin.eps, addvec=p.pos_emb(g.F), rv=g.rv(RV_FRAMEPOS),
+                      sum_out=t0)                                                      # t0 = x_spatial + emb[f]
+    ff = dense(n, p.t_ffin1, act=ACT_GEGLU)
+    t = dense(ff, p.t_ffin2, res1=t0)
+    n = ops.layernorm(t, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
+    qkv = dense(n, p.t_qkv)
+    a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
+    t = dense(a, p.t_out, res1=t)
+    if kv1:
+        n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec(p.t_cross),
+                          rv=g.rv(tctx_mode), sum_out=t)
+    else:
+        if tctx_mode != RV_BATCH and g.B > 1:
+            raise NotImplementedError("temporal cross-attention with KV length > 1 needs time_context_order="
+                                      "'b_major' (or batch 1): the 0.27.2 (hw,b) interleave is only implemented "
+                                      "for the KV-length-1 context the reference always uses")
+        n = ops.layernorm(t, p.t_ln2.g, p.t_ln2.b, p.t_ln2.eps)
+        t = _cross_general(p.t_cross, n, cond.ctx, g, t)
+        n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps)
+    ff = dense(n, p.t_ff1, act=ACT_GEGLU)
+    # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t)
+    mix = dense(ff, p.t_ff2, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
+    return dense(mix, p.proj_out, res1=x)
+
+
+class PackedUNet:
+    """Kernel-ready copy of a UNet's weights + the forward schedule (down / mid / up, skip handling)."""
+
+    def __init__(self, unet, fold_lora: bool = True):
+        cfg = unet.config
+        self.cfg = cfg
+        self.c0 = cfg.block_out_channels[0]
+        self.cin = cfg.in_channels
+        self.cin_pad = 64
+        self.conv_in_w, self.conv_in_b = _conv3x3_weight(unet.conv_in, cin_pad=self.cin_pad)
+        te, ae = unet.time_embedding, unet.add_embedding
+        self.te = tuple(_f32(t) for t in (te.linear_1.weight, te.linear_1.bias, te.linear_2.weight, te.linear_2.bias))
+        self.ae = tuple(_f32(t) for t in (ae.linear_1.weight, ae.linear_1.bias, ae.linear_2.weight, ae.linear_2.bias))
+        self.down = []
+        for blk in unet.down_blocks:
+            res = [PackedResBlock(r) for r in blk.resnets]
+            att = [PackedTransformer(a, fold_lora) for a in blk.attentions] if blk.has_cross_attention else None
+            ds = _conv3x3_weight(blk.downsamplers[0].conv) if blk.downsamplers is not None else None
+            self.down.append((res, att, ds))
+        mb = unet.mid_block
+        self.mid = ([PackedResBlock(r) for r in mb.resnets], [PackedTransformer(a, fold_lora) for a in mb.attentions])
+        self.up = []
+        for blk in getattr(unet, "up_blocks", []):
+            res = [PackedResBlock(r) for r in blk.resnets]
+            att = [PackedTransformer(a, fold_lora) for a in blk.attentions] if blk.has_cross_attention else None
+            us = _conv3x3_weight(blk.upsamplers[0].conv) if blk.upsamplers is not None else None
+            self.up.append((res, att, us))
+        if hasattr(unet, "conv_out"):
+            self.norm_out = Norm.of(unet.conv_norm_out)
+            self.cout = cfg.out_channels
+            self.conv_out_w, self.conv_out_b = _conv3x3_weight(unet.conv_out, cout_pad=max(32, (self.cout + 15) // 16 * 16))
+        order = getattr(cfg, "time_context_order", "hw_major_0272")
+        if order not in ("hw_major_0272", "b_major"):
+            raise ValueError(f"time_context_order must be 'hw_major_0272' or 'b_major', got {order}")
+        self.tctx_mode = RV_TCTX_0272 if order == "hw_major_0272" else RV_BATCH
+
+    # ------------------------------------------------------------------------------------------
+    def time_embedding(self, timestep: torch.Tensor, added_time_ids: torch.Tensor) -> torch.Tensor:
+        """emb = time_embedding(Timesteps(t)) + add_embedding(Timesteps(added_time_ids).reshape(B,-1)) in fp32."""
+        B = added_time_ids.shape[0]
+        t = timestep.to(torch.float32).reshape(-1).expand(B).contiguous()
+        e = ops.timestep_embedding(t, self.c0)
+        e = ops.small_linear(ops.small_linear(e, self.te[0], self.te[1], act_out=SL_SILU), self.te[2], self.te[3])
+        a = ops.timestep_embedding(added_time_ids.to(torch.float32).reshape(-1), self.cfg.addition_time_embed_dim)
+        a = a.reshape(B, -1)
+        a = ops.small_linear(ops.small_linear(a, self.ae[0], self.ae[1], act_out=SL_SILU), self.ae[2], self.ae[3])
+        ops.axpy_f32(a, e)
+        return e
+
+    def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None):
+        """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms)."""
+        x = ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b, res1=stem_add)
+        skips, geoms = [x], [g]
+        for res, att, ds in self.down:
+            for i, r in enumerate(res):
+                x = run_resblock(r, x, None, g, cond)
+                if att is not None:
+                    x = run_transformer(att[i], x, g, cond, self.tctx_mode)
+                skips.append(x)
+                geoms.append(g)
+            if ds is not None:
+                x = ops.gemm(x, ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1])
+                g = g.down()
+                skips.append(x)
+                geoms.append(g)
+        res, att = self.mid
+        x = run_resblock(res[0], x, None, g, cond)
+        for a, r in zip(att, res[1:]):
+            x = run_transformer(a, x, g, cond, self.tctx_mode)
+            x = run_resblock(r, x, None, g, cond)
+        return x, skips, geoms, g
+
+    def decoder(self, x: torch.Tensor, skips: List[torch.Tensor], g: Geom, cond: Conditioning) -> torch.Tensor:
+        for res, att, us in self.up:
+            for i, r in enumerate(res):
+                x = run_resblock(r, x, skips.pop(), g, cond)
+                if att is not None:
+                    x = run_transformer(att[i], x, g, cond, self.tctx_mode)
+            if us is not None:
+                x = ops.upsample2x(x, g.BF, g.H, g.W)
+                g = g.up()
+                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1])
+        h = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, self.norm_out.eps, NS=g.BF, R=g.HW, silu=True)
+        # conv_out: N padded to 32 rows of zeros, only the first `cout` columns are stored (fp32)
+        return ops.gemm(h, self.conv_out_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_out_b,
+                        out_f32=True, n_store=self.cout)
+
+
+def residual_multipliers(n_down_blocks: int, skips_per_block: Sequence[int]) -> List[int]:
+    """Reference quirk F6: the ControlNet residual add sits inside the down-block loop and ``zip`` truncates
+    (models/unet_spatio_temporal_condition_controlnet.py:453-462), so a skip produced by down block j (conv_in
+    counts with block 0) ends up with ``n_down_blocks - j`` times its residual: (4,4,4,4,3,3,3,2,2,2,1,1)."""
+    mult = []
+    for j, n in enumerate(skips_per_block):
+        mult += [n_down_blocks - j] * n
+    return mult

@@ -1,0 +1,335 @@
+"""Kernel parity on the GPU (through the C ABI): each CUDA kernel against a plain PyTorch fp32 evaluation of
+the same op on bf16-rounded inputs, and against the SIMT checker kernels at sizes the CPU cannot do."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def rnd(*shape, dev, scale=1.0, dtype=bf16, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed if seed is not None else (hash(shape) & 0xFFFF))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (1000, 320, 320), (128, 32, 32), (4096, 960, 320),
+                                   (300, 1280, 1280), (130, 48, 72)])
+def test_gemm_linear(cuda, M, N, K):
+    from lkgd_b200 import ops
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    b = rnd(N, dev=cuda, dtype=torch.float32)
+    out = ops.gemm(A, W, bias=b)
+    ref = A.float() @ W.float().t() + b
+    assert rel_l2(out.float(), ref) < 4e-3
+    chk = ops.gemm(A, W, bias=b, checker=True)
+    assert rel_l2(out.float(), chk.float()) < 3e-3
+
+
+def test_gemm_column_slice_and_f32_out(cuda):
+    from lkgd_b200 import ops
+    M, K, N = 512, 64, 192
+    wide = rnd(M, 3 * K, dev=cuda)
+    A = wide[:, K:2 * K]
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    out = ops.gemm(A, W, out_f32=True)
+    ref = A.float() @ W.float().t()
+    assert out.dtype == torch.float32
+    assert rel_l2(out, ref) < 1e-5
+
+
+def test_gemm_epilogue_terms(cuda):
+    from lkgd_b200 import ops
+    B_, Fr, HW, N, K = 2, 3, 64, 320, 128
+    M = B_ * Fr * HW
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    b = rnd(N, dev=cuda, dtype=torch.float32)
+    r1, r2 = rnd(M, N, dev=cuda, seed=1), rnd(M, N, dev=cuda, seed=2)
+    base = A.float() @ W.float().t() + b
+    m = torch.arange(M, device=cuda)
+    for mode, G, idx in [(ops.RV_FRAME, B_ * Fr, m // HW), (ops.RV_FRAMEPOS, Fr, (m // HW) % Fr),
+                         (ops.RV_BATCH, B_, m // (HW * Fr)),
+                         (ops.RV_TCTX_0272, B_, ((m // (HW * Fr)) * HW + m % HW) % B_)]:
+        rv = rnd(G, N, dev=cuda, dtype=torch.float32, seed=mode)
+        out = ops.gemm(A, W, bias=b, rowvec=rv, rv=(mode, HW, Fr, B_), act=ops.ACT_SILU, s0=0.3, res1=r1, s1=0.7,
+                       res2=r2, s2=-1.5)
+        ref = 0.3 * F.silu(base + rv[idx]) + 0.7 * r1.float() - 1.5 * r2.float()
+        assert rel_l2(out.float(), ref) < 4e-3, mode
+
+
+def test_gemm_n_store_conv_out_shape(cuda):
+    from lkgd_b200 import ops
+    M, K = 700, 64
+    A = rnd(M, K, dev=cuda)
+    W = torch.zeros(32, K, device=cuda, dtype=bf16)
+    W[:4] = rnd(4, K, dev=cuda, scale=K ** -0.5)
+    b = torch.zeros(32, device=cuda)
+    b[:4] = 0.5
+    out = ops.gemm(A, W, bias=b, out_f32=True, n_store=4)
+    assert out.shape == (M, 4)
+    assert rel_l2(out, A.float() @ W[:4].float().t() + 0.5) < 1e-5
+
+
+@pytest.mark.parametrize("C", [32, 320])
+def test_gemm_geglu(cuda, C):
+    from lkgd_b200 import ops
+    M = 384
+    A = rnd(M, C, dev=cuda)
+    W = rnd(8 * C, C, dev=cuda, scale=C ** -0.5)
+    b = rnd(8 * C, dev=cuda, dtype=torch.float32)
+    Wp, bp = ops.pack_geglu(W, b)
+    out = ops.gemm(A, Wp, bias=bp, act=ops.ACT_GEGLU)
+    proj = A.float() @ W.float().t() + b
+    h, g = proj.chunk(2, dim=-1)
+    ref = h * F.gelu(g)
+    assert out.shape == (M, 4 * C)
+    assert rel_l2(out.float(), ref) < 4e-3
+    chk = ops.gemm(A, Wp, bias=bp, act=ops.ACT_GEGLU, checker=True)
+    assert rel_l2(out.float(), chk.float()) < 3e-3
+
+
+@pytest.mark.parametrize("r", [8, 64])
+def test_gemm_lora_second_segment(cuda, r):
+    from lkgd_b200 import ops
+    M, K, N = 640, 320, 320
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    T = rnd(M, r, dev=cuda)
+    Bl = rnd(N, r, dev=cuda, scale=0.1)
+    out = ops.gemm(A, W, A1=T, Bw1=Bl)
+    ref = A.float() @ W.float().t() + T.float() @ Bl.float().t()
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("NIMG,H,W,Cin,Cout,stride", [(3, 18, 32, 64, 128, 1), (2, 16, 16, 32, 64, 1),
+                                                      (2, 9, 16, 128, 64, 1), (2, 36, 64, 64, 64, 2),
+                                                      (3, 10, 16, 32, 32, 2), (1, 72, 128, 64, 320, 1),
+                                                      (2, 5, 8, 64, 64, 1)])
+def test_gemm_conv3x3(cuda, NIMG, H, W, Cin, Cout, stride):
+    from lkgd_b200 import ops
+    x = rnd(NIMG, Cin, H, W, dev=cuda)                      # NCHW reference layout
+    w = rnd(Cout, Cin, 3, 3, dev=cuda, scale=(9 * Cin) ** -0.5)
+    b = rnd(Cout, dev=cuda, dtype=torch.float32)
+    ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1)        # [N, Cout, Ho, Wo]
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_k = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = ops.gemm(x_nhwc, w_k, mode=ops.A_CONV3X3, conv=(NIMG, H, W, stride), bias=b)
+    Ho, Wo = ref.shape[2:]
+    got = out.float().view(NIMG, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref) < 4e-3
+
+
+@pytest.mark.parametrize("B_,Fr,HW,C,N", [(2, 5, 200, 64, 64), (1, 8, 1024, 32, 32), (2, 3, 144, 128, 128),
+                                          (1, 1, 64, 64, 64)])
+def test_gemm_tconv3(cuda, B_, Fr, HW, C, N):
+    from lkgd_b200 import ops
+    x = rnd(B_, C, Fr, HW, 1, dev=cuda)                     # [B,C,F,H,W] with H*W flattened
+    w = rnd(N, C, 3, 1, 1, dev=cuda, scale=(3 * C) ** -0.5)
+    b = rnd(N, dev=cuda, dtype=torch.float32)
+    ref = F.conv3d(x.float(), w.float(), b, padding=(1, 0, 0))              # [B,N,F,HW,1]
+    x_cl = x[..., 0].permute(0, 2, 3, 1).contiguous()                        # [B,F,HW,C]
+    w_k = w[..., 0, 0].permute(0, 2, 1).reshape(N, 3 * C).contiguous()       # k = kt*C + c
+    out = ops.gemm(x_cl, w_k, mode=ops.A_TCONV3, tconv=(B_, Fr, HW), bias=b)
+    got = out.float().view(B_, Fr, HW, N).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref[..., 0]) < 4e-3
+
+
+def test_gemm_large_vs_checker(cuda):
+    """SVD level-0 projection shape (M = 2*25*72*128 would be 460800; one CFG half of 14 frames here)."""
+    from lkgd_b200 import ops
+    M, N, K = 14 * 9216, 320, 320
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    out = ops.gemm(A, W)
+    chk = ops.gemm(A, W, checker=True)
+    assert rel_l2(out.float(), chk.float()) < 3e-3
+    assert torch.isfinite(out.float()).all()
+
+
+# ------------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("NS,R,C1,C2,silu", [(4, 1024, 32, 0, True), (3, 576, 320, 0, True), (2, 2304, 640, 320, True),
+                                             (2, 8 * 144, 1280, 0, True), (5, 200, 64, 0, False),
+                                             (2, 144, 1280, 1280, True)])
+def test_groupnorm(cuda, NS, R, C1, C2, silu):
+    from lkgd_b200 import ops
+    x1 = rnd(NS * R, C1, dev=cuda) + 0.5
+    x2 = rnd(NS * R, C2, dev=cuda, scale=2.0) if C2 else None
+    Ct = C1 + C2
+    g = rnd(Ct, dev=cuda, dtype=torch.float32) * 0.2 + 1.0
+    b = rnd(Ct, dev=cuda, dtype=torch.float32, seed=3) * 0.2
+    out = ops.groupnorm(x1, g, b, 1e-5, NS=NS, R=R, x2=x2, silu=silu)
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+    xr = x.float().view(NS, R, Ct).permute(0, 2, 1)                       # [NS, C, R]
+    ref = F.group_norm(xr, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(NS * R, Ct)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,C", [(1000, 32), (777, 320), (512, 640), (300, 1280)])
+def test_layernorm(cuda, M, C):
+    from lkgd_b200 import ops
+    x = rnd(M, C, dev=cuda) * 2 + 0.3
+    g = rnd(C, dev=cuda, dtype=torch.float32) * 0.2 + 1.0
+    b = rnd(C, dev=cuda, dtype=torch.float32, seed=5) * 0.2
+    out = ops.layernorm(x, g, b, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_layernorm_fused_add(cuda):
+    from lkgd_b200 import ops
+    B_, Fr, HW, C = 2, 4, 50, 320
+    M = B_ * Fr * HW
+    x = rnd(M, C, dev=cuda)
+    g = torch.ones(C, device=cuda)
+    b = torch.zeros(C, device=cuda)
+    emb = rnd(Fr, C, dev=cuda, dtype=torch.float32)
+    s = torch.empty_like(x)
+    out = ops.layernorm(x, g, b, 1e-5, addvec=emb, rv=(ops.RV_FRAMEPOS, HW, Fr, B_), sum_out=s)
+    f_idx = (torch.arange(M, device=cuda) // HW) % Fr
+    s_ref = (x.float() + emb[f_idx]).to(bf16)
+    assert torch.equal(s, s_ref)
+    assert rel_l2(out.float(), F.layer_norm(s_ref.float(), (C,), g, b, 1e-5)) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, n_img, heads, d, Nq, Nk):
+    qf = q.float().view(n_img, Nq, heads, d).transpose(1, 2)
+    kf = k.float().view(n_img, Nk, heads, d).transpose(1, 2)
+    vf = v.float().view(n_img, Nk, heads, d).transpose(1, 2)
+    w = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1)
+    return (w @ vf).transpose(1, 2).reshape(n_img * Nq, heads * d)
+
+
+@pytest.mark.parametrize("n_img,heads,d,N", [(2, 2, 64, 128), (2, 5, 64, 576), (3, 2, 16, 1024), (1, 4, 32, 144),
+                                             (2, 10, 64, 2304), (1, 1, 64, 100)])
+def test_attention_self(cuda, n_img, heads, d, N):
+    from lkgd_b200 import ops
+    Cn = heads * d
+    qkv = rnd(n_img * N, 3 * Cn, dev=cuda)
+    q, k, v = qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:]
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N)
+    ref = _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), n_img, heads, d, N, N)
+    assert rel_l2(out.float(), ref) < 6e-3
+
+
+def test_attention_cross_kv_len(cuda):
+    from lkgd_b200 import ops
+    n_img, heads, d, Nq, Nk = 2, 3, 64, 300, 77
+    q = rnd(n_img * Nq, heads * d, dev=cuda)
+    k = rnd(n_img * Nk, heads * d, dev=cuda, seed=1)
+    v = rnd(n_img * Nk, heads * d, dev=cuda, seed=2)
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=Nq, Nk=Nk)
+    assert rel_l2(out.float(), _attn_ref(q, k, v, n_img, heads, d, Nq, Nk)) < 6e-3
+    chk = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=Nq, Nk=Nk, checker=True)
+    assert rel_l2(out.float(), chk.float()) < 6e-3
+
+
+def test_attention_svd_l0_vs_checker(cuda):
+    from lkgd_b200 import ops
+    n_img, heads, d, N = 1, 5, 64, 9216
+    Cn = heads * d
+    qkv = rnd(n_img * N, 3 * Cn, dev=cuda)
+    q, k, v = qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:]
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N)
+    chk = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N, checker=True)
+    assert rel_l2(out.float(), chk.float()) < 6e-3
+
+
+@pytest.mark.parametrize("B_,Fr,HW,heads,d", [(2, 8, 64, 2, 16), (2, 25, 144, 5, 64), (1, 14, 100, 4, 32),
+                                              (1, 1, 40, 2, 64)])
+def test_attention_temporal(cuda, B_, Fr, HW, heads, d):
+    from lkgd_b200 import ops
+    Cn = heads * d
+    qkv = rnd(B_ * Fr * HW, 3 * Cn, dev=cuda)
+    out = ops.attention_temporal(qkv, B=B_, F=Fr, HW=HW, heads=heads, d=d)
+    t = qkv.float().view(B_, Fr, HW, 3, heads, d).permute(3, 0, 2, 4, 1, 5)     # [3,B,HW,h,F,d]
+    w = torch.softmax(t[0] @ t[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+    ref = (w @ t[2]).permute(0, 3, 1, 2, 4).reshape(B_ * Fr * HW, Cn)            # [B,F,HW,h,d]
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- glue
+def test_small_linear_and_timestep_embedding(cuda):
+    from lkgd_b200 import ops
+    x = rnd(3, 1280, dev=cuda, dtype=torch.float32)
+    W = rnd(320, 1280, dev=cuda, dtype=torch.float32, scale=0.03)
+    b = rnd(320, dev=cuda, dtype=torch.float32)
+    y = ops.small_linear(x, W, b, act_in=1, act_out=3)
+    ref = F.leaky_relu(F.silu(x) @ W.t() + b, 0.1)
+    assert rel_l2(y, ref) < 1e-5
+    t = torch.tensor([1.6377, -0.92, 6.0, 127.0, 0.02], device=cuda)
+    e = ops.timestep_embedding(t, 320)
+    k = torch.arange(160, device=cuda, dtype=torch.float32)
+    arg = t[:, None] * torch.exp(-math.log(10000.0) * k / 160)[None]
+    assert rel_l2(e, torch.cat([arg.cos(), arg.sin()], -1)) < 1e-5
+
+
+def test_pack_unpack_layouts(cuda):
+    from lkgd_b200 import ops
+    S, Fr, H, W = 2, 3, 8, 16
+    lat = rnd(S, Fr, 4, H, W, dev=cuda, dtype=torch.float32)
+    img = rnd(2 * S, Fr, 4, H, W, dev=cuda, dtype=torch.float32, seed=9)
+    out = ops.pack_input(lat, 0.25, img, N=2 * S, Cpad=64)
+    ref = torch.zeros(2 * S, Fr, H, W, 64, device=cuda)
+    ref[..., :4] = (torch.cat([lat, lat]) * 0.25).permute(0, 1, 3, 4, 2)
+    ref[..., 4:8] = img.permute(0, 1, 3, 4, 2)
+    assert torch.equal(out.view(2 * S, Fr, H, W, 64), ref.to(bf16))
+    src = rnd(S * Fr * H * W, 8, dev=cuda, dtype=torch.float32)
+    un = ops.unpack_output(src[:, :4], S, Fr, 4, H, W)
+    assert torch.equal(un, src[:, :4].reshape(S, Fr, H, W, 4).permute(0, 1, 4, 2, 3))
+    x = rnd(5, 48, 9, 7, dev=cuda, dtype=torch.float32)
+    cl = ops.nchw_to_nhwc(x)
+    assert torch.equal(cl.view(5, 9, 7, 48), x.permute(0, 2, 3, 1).to(bf16))
+    assert torch.equal(ops.nhwc_to_nchw(cl, 5, 9, 7), x.to(bf16).float())
+
+
+def test_upsample_concat_axpby(cuda):
+    from lkgd_b200 import ops
+    N, H, W, Cn = 3, 5, 6, 64
+    x = rnd(N * H * W, Cn, dev=cuda)
+    up = ops.upsample2x(x, N, H, W)
+    ref = F.interpolate(x.float().view(N, H, W, Cn).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    assert torch.equal(up.view(N, 2 * H, 2 * W, Cn), ref.permute(0, 2, 3, 1).to(bf16))
+    y = rnd(N * H * W, 32, dev=cuda, seed=4)
+    assert torch.equal(ops.concat_channels(x, y), torch.cat([x, y], 1))
+    acc = x.clone()
+    ops.axpby(rnd(N * H * W, Cn, dev=cuda, seed=6), 3.0, acc, 1.0)
+    assert rel_l2(acc.float(), x.float() + 3.0 * rnd(N * H * W, Cn, dev=cuda, seed=6).float()) < 4e-3
+
+
+def test_cfg_euler_step_matches_formula(cuda):
+    """KAT from SURVEY Appendix C (i=3: sigma 322.4537 -> 244.0231, x=1.5, v=-0.25 -> 1.1959649)."""
+    from lkgd_b200 import ops
+    S, Fr, Cn, H, W = 1, 2, 4, 4, 4
+    x = torch.full((S, Fr, Cn, H, W), 1.5, device=cuda)
+    pred = torch.zeros(2 * S * Fr * H * W, 4, device=cuda)
+    pred[: S * Fr * H * W] = -0.25
+    pred[S * Fr * H * W:] = -0.25
+    g = torch.tensor([1.0, 3.0], device=cuda)
+    xn, v = ops.cfg_euler_step(pred, g, x, 322.45367431640625, 244.0230712890625, cfg=True, want_v=True)
+    assert torch.allclose(v, torch.full_like(v, -0.25))
+    assert abs(float(xn.flatten()[0]) - 1.1959649324417114) < 2e-6
+    # general case vs the reference formula in fp32
+    x = rnd(2, 3, 4, 8, 8, dev=cuda, dtype=torch.float32) * 700
+    u = rnd(2, 3, 8, 8, 4, dev=cuda, dtype=torch.float32, seed=1)
+    c = rnd(2, 3, 8, 8, 4, dev=cuda, dtype=torch.float32, seed=2)
+    g = torch.linspace(1, 3, 3, device=cuda)
+    pred = torch.cat([u, c]).reshape(-1, 4)
+    sig, sig_n = 700.0, 545.729248046875
+    xn, v = ops.cfg_euler_step(pred, g, x, sig, sig_n, cfg=True, want_v=True)
+    vv = (u + g[None, :, None, None, None] * (c - u)).permute(0, 1, 4, 2, 3)
+    x0 = vv * (-sig / (sig ** 2 + 1) ** 0.5) + x / (sig ** 2 + 1)
+    ref = x + (x - x0) / sig * (sig_n - sig)
+    assert rel_l2(v, vv) < 1e-6
+    assert rel_l2(xn, ref) < 1e-6
