@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the LKGD / SVD-XT denoise hot path (BASELINE.json).
+
+Workload (config.workload = "C3"): one classifier-free-guided Euler-Karras denoise step of the SVD-XT
+spatio-temporal UNet, 25 frames at 576x1024 (72x128 latents), CFG batch 2, LoRA r=64 on the temporal attn1
+q/k/v projections and the latent-knowledge (LKGD) cross-attention conditioning; random-init weights, synthetic
+inputs.  A "step" = fused pack kernel -> UNet -> fused CFG + Euler kernel.
+
+    python bench.py --gpus N --steps K --warmup W           # ours  (N>1: launched under torchrun, 1 rank/GPU)
+    python bench.py --impl reference ...                    # the reference's CPU path (oracle port) on host cores
+
+Multi-GPU: independent initial-frame samples are sharded one per rank (no collective on the data path, weak
+scaling); value = steps all ranks completed / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (unet config key, frames, h, w, lora rank, lkgd)
+    "C3": ("svd_xt", 25, 72, 128, 64, True),
+    "C2": ("svd_xt", 14, 72, 128, 0, False),
+    "C1": ("reduced", 8, 32, 32, 0, False),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_inputs(S, F, h, w, lkgd, device="cpu", seed=0):
+    """latents ~ N(0,1) (scaled by init_noise_sigma later), image_latents ~ N(0,1) with a zero uncond
+    half, CLIP embedding ~ N(0,1) with a zero uncond half, domain / flow features ~ N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    noise = torch.randn(S, F, 4, h, w, generator=g)
+    cond_lat = torch.randn(S, 1, 4, h, w, generator=g).repeat(1, F, 1, 1, 1)
+    image_latents = torch.cat([torch.zeros_like(cond_lat), cond_lat])
+    emb = torch.randn(S, 1, 1024, generator=g)
+    image_embeddings = torch.cat([torch.zeros_like(emb), emb])
+    extra = (torch.randn(1, 1, 1000, generator=g), torch.randn(1, 1, 1000, generator=g)) if lkgd else ()
+    return noise, image_latents, image_embeddings, extra
+
+
+def init_weights_(model, seed=0):
+    """Default-initialiser-equivalent random weights generated directly on the GPU (no checkpoints exist here);
+    zero-inits that would hide work are overridden as in SURVEY 8(d)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("mix_factor"):
+                p.copy_(torch.rand(p.shape, generator=g, device="cuda") * 2 - 1)
+            elif "lora_B" in n or n.startswith("quaternion_lora_texts"):
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda") * 0.02)
+            elif "lora_A" in n:
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda") / p.shape[0])
+            elif p.ndim >= 2:
+                fan_in = p[0].numel()
+                p.copy_((torch.rand(p.shape, generator=g, device="cuda") * 2 - 1) * fan_in ** -0.5)
+            elif ".norm" in n and n.endswith("weight") or "conv_norm_out.weight" in n:
+                p.fill_(1.0)
+            elif n.endswith("bias") and (".norm" in n or "conv_norm_out" in n):
+                p.zero_()
+            else:
+                p.copy_((torch.rand(p.shape, generator=g, device="cuda") * 2 - 1) * 0.02)
+
+
+def build_ours(workload, device):
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import SVD_SCHEDULER_CONFIG, EulerDiscreteScheduler
+    from lkgd_b200.unet import (REDUCED_CONFIG, SVD_XT_CONFIG, UNetSpatioTemporalConditionControlNetModel,
+                                UNetSpatioTemporalConditionModel)
+    key, F, h, w, rank, lkgd = CONFIGS[workload]
+    cfg = dict(SVD_XT_CONFIG if key == "svd_xt" else REDUCED_CONFIG, num_frames=F)
+    if lkgd and cfg["cross_attention_dim"] != 1024:
+        cfg["cross_attention_dim"] = 1024
+    cls = UNetSpatioTemporalConditionModel if lkgd else UNetSpatioTemporalConditionControlNetModel
+    with torch.device("meta"):
+        unet = cls(**cfg)
+        if rank:
+            unet.add_lora(rank)
+    unet = unet.to_empty(device=device)
+    init_weights_(unet)
+    unet.invalidate()
+    pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))
+    return pipe, cfg, (F, h, w, rank, lkgd)
+
+
+def cpu_oracle_rate(workload, max_seconds=40.0):
+    """Times the oracle (fp32 PyTorch, eager, all host threads) on a BOUNDED sample of the workload: the same
+    full-width UNet on a reduced frame count / latent size, scaled to denoise steps/s by algorithmic FLOPs."""
+    import oracle as O
+    from lkgd_b200.flops import unet_flops
+    from lkgd_b200.unet import REDUCED_CONFIG, SVD_XT_CONFIG
+    key, F, h, w, rank, lkgd = CONFIGS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(SVD_XT_CONFIG if key == "svd_xt" else REDUCED_CONFIG)
+    if key == "svd_xt":
+        Fs, hs, ws = 2, 16, 16          # sample: full-width SVD-XT UNet, CFG batch 2, 2 frames, 16x16 latents
+    else:
+        Fs, hs, ws = F, h, w
+    cfg["num_frames"] = Fs
+    if lkgd:
+        cfg["cross_attention_dim"] = 1024
+    cls = O.UNetSpatioTemporalConditionModel if lkgd else O.UNetSpatioTemporalConditionControlNetModel
+    torch.manual_seed(0)
+    t0 = time.time()
+    with torch.device("meta"):
+        model = cls(**cfg)
+        if rank:
+            O.add_lora(model, rank)
+    model = model.to_empty(device="cpu")
+    with torch.no_grad():
+        for p in model.parameters():
+            p.uniform_(-0.02, 0.02)
+    model.eval()
+    build_s = time.time() - t0
+    noise, img_lat, emb, extra = synth_inputs(1, Fs, hs, ws, lkgd)
+    sched = O.EulerDiscreteScheduler(**O.scheduler.SVD_SCHEDULER_CONFIG)
+    sched.set_timesteps(25)
+    ids = O.add_time_ids_inference(6, 127, 0.02, 1)
+    lat = noise * sched.init_noise_sigma
+    times = []
+    t_start = time.time()
+    for it in range(4):
+        sched._step_index = None
+        t1 = time.time()
+        O.denoise_loop(model, sched, lat, img_lat, emb, ids, 25, 1.0, 3.0, unet_extra_args=extra, max_steps=1)
+        times.append(time.time() - t1)
+        if time.time() - t_start > max_seconds:
+            break
+    t_step = min(times[1:]) if len(times) > 1 else times[0]
+    f_sample = unet_flops(cfg, 2, Fs, hs, ws, lora_rank=rank)["total"]
+    f_full = unet_flops(dict(cfg, num_frames=F), 2, F, h, w, lora_rank=rank)["total"]
+    value = (1.0 / t_step) * (f_sample / f_full)
+    return dict(value=value, unit="denoise_steps/s", cores=cores, kind="port",
+                sample=(f"oracle (fp32 PyTorch eager, {cores} threads) full-width UNet CFG step at {Fs} frames "
+                        f"{hs}x{ws} latents: {t_step:.2f} s/step = {f_sample / t_step / 1e12:.3f} TFLOP/s; scaled to the "
+                        f"{F}f {h}x{w} step by algorithmic FLOPs ({f_sample / 1e12:.2f} vs {f_full / 1e12:.1f} TFLOP); "
+                        f"model build {build_s:.0f} s not timed")), t_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, t_step = cpu_oracle_rate(args.workload)
+    key, F, h, w, lrank, lkgd = CONFIGS[args.workload]
+    line = {
+        "impl": "reference", "metric": "denoise_steps_per_s", "value": cb["value"], "unit": "denoise_steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: SVD-XT CFG denoise step {F}f {h}x{w} latents, LoRA r={lrank}, "
+                               f"LKGD={lkgd} (CPU oracle on a bounded sample, FLOP-scaled)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "denoise_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=list(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel event breakdown to this JSON file")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from lkgd_b200 import _lib, ops
+    from lkgd_b200.flops import unet_flops
+    ops.device_check(local)
+
+    pipe, cfg, (F, h, w, lrank, lkgd) = build_ours(args.workload, device)
+    S = 1   # one initial-frame sample per GPU (weak scaling: every rank denoises its own sample)
+    noise, img_lat, emb, extra = synth_inputs(S, F, h, w, lkgd, seed=rank)
+    kw = dict(domain_features=extra[0], flow_features=extra[1]) if lkgd else {}
+    st = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, **kw)
+    lat0 = (noise * pipe.scheduler.init_noise_sigma).to(device)
+    n_sig = 25
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    lat = lat0
+    for i in range(args.warmup):
+        lat, _ = pipe.denoise_step(st, i % n_sig, lat)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        lat, _ = pipe.denoise_step(st, (args.warmup + i) % n_sig, lat)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(lat).all())
+
+    # ---------------------------------------------------------------- end to end through the public API
+    pin_noise = lat0.cpu().pin_memory()
+    pin_img, pin_emb = img_lat.pin_memory(), emb.pin_memory()
+    pin_out = torch.empty_like(pin_noise).pin_memory()
+    h2d = pin_noise.numel() * 4 + pin_img.numel() * 4 + pin_emb.numel() * 4
+    d2h = pin_out.numel() * 4
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        lat_d = pin_noise.to(device, non_blocking=True)
+        st["image_latents"] = pin_img.to(device, non_blocking=True)
+        st["image_embeddings"] = pin_emb.to(device, non_blocking=True)
+        out, _ = pipe.denoise_step(st, (args.warmup + i) % n_sig, lat_d)
+        pin_out.copy_(out, non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---------------------------------------------------------------- per-kernel breakdown (one extra step, events)
+    roof = None
+    if rank == 0:
+        _lib.PROF.records, _lib.PROF.enabled = [], True
+        pipe.denoise_step(st, 5, lat0)
+        torch.cuda.synchronize()
+        _lib.PROF.enabled = False
+        by = {}
+        for name, a, b, meta in _lib.PROF.records:
+            d = by.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+            if meta and "flops" in meta:
+                d["flops"] += meta["flops"]
+        total_ms = sum(d["ms"] for d in by.values())
+        pk = peaks()
+        gm = by.get("lkgd_gemm", dict(ms=1e-9, calls=0, flops=0.0))
+        achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (GEMM + implicit-GEMM conv)",
+                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+                "launches_per_step": gm["calls"], "algorithmic_tflop_per_step": gm["flops"] / 1e12,
+                "kernel_ms_per_step": gm["ms"], "share_of_step": gm["ms"] / total_ms,
+                "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
+        at = by.get("lkgd_attention")
+        if at:
+            roof["attention_tflops"] = at["flops"] / (at["ms"] * 1e-3) / 1e12
+        if args.profile_out:
+            json.dump({"by_kernel": by, "gemm_calls": [dict(meta, ms=a.elapsed_time(b)) for n, a, b, meta in
+                                                        _lib.PROF.records if n == "lkgd_gemm" and meta]},
+                      open(args.profile_out, "w"), indent=1)
+
+    if rank == 0:
+        steps_total = args.steps * world
+        value = steps_total / (ms * 1e-3)
+        flops = unet_flops(cfg, 2, F, h, w, lora_rank=lrank)["total"]
+        line = {
+            "metric": "denoise_steps_per_s", "value": value, "unit": "denoise_steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: SVD-XT CFG denoise step, {F} frames 576x1024 ({h}x{w} latents), "
+                                   f"CFG batch 2, LoRA r={lrank} folded in the temporal qkv GEMMs, LKGD cond={lkgd}; "
+                                   "1 sample per GPU",
+                       "frames_per_s_per_gpu": F * args.steps / (ms * 1e-3),
+                       "algorithmic_tflop_per_step": flops / 1e12,
+                       "model_tflops_per_gpu": flops / 1e12 / (ms / args.steps * 1e-3),
+                       "l2": "per-step working set (3 GB bf16 weights + multi-GB activations) >> 126 MB L2; "
+                             "no explicit flush needed",
+                       "output_finite": finite},
+            "e2e": {"value": steps_total / (ms_e2e * 1e-3), "unit": "denoise_steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_oracle_rate(args.workload)
+            except Exception as ex:  # the CPU leg must never sink the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "denoise_steps/s", "cores": os.cpu_count(),
+                                        "kind": "port", "sample": f"failed: {ex!r}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

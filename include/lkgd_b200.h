@@ -160,6 +160,14 @@ LKGD_API int lkgd_small_linear(const float* x, int32_t ldx, const float* W, cons
 /* Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[m] = [cos(t_m f_k) | sin(t_m f_k)]. */
 LKGD_API int lkgd_timestep_embedding(const float* t, int32_t M, int32_t dim, float* out, void* stream);
 
+/* y += alpha * x on fp32 (embedding sums). */
+LKGD_API int lkgd_axpy_f32(const float* x, float alpha, float* y, int64_t n, void* stream);
+/* y = alpha * x on fp32 (scheduler.scale_model_input, utils/scheduling_euler_discrete_karras_fix.py:284-285). */
+LKGD_API int lkgd_scale_f32(const float* x, float alpha, float* y, int64_t n, void* stream);
+/* mode 0: (a,b) = (re,im) -> o0 = |z|, o1 = atan2(im,re);  mode 1: (a,b) = (mag,pha) -> o0 = mag cos, o1 = mag sin.
+ * The torch.abs / torch.angle / cos / sin of the LKGD spectral fuse (unet_spatio_temporal_condition.py:559-580). */
+LKGD_API int lkgd_polar(const float* a, const float* b, float* o0, float* o1, int32_t n, int32_t mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Layout / glue kernels (HBM-bound, 128-bit vectorised).
  */
@@ -187,7 +195,8 @@ LKGD_API int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64_t
  *   v      = u + g[f] * (c - u)           u = pred[s], c = pred[S + s]   (pred channels-last fp32 [2S*F,H,W,ld])
  *   x0     = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1)
  *   x_next = x + (x - x0) / sigma * (sigma_next - sigma)
- * x / x_next are fp32 [S, F, C, H, W] (reference layout).  If S_pred == S (no CFG) v = pred.
+ * x / x_next are fp32 [S, F, C, H, W] (reference layout).  cfg == 0: v = pred.  ld == 0: pred is laid out like x
+ * ([2S or S, F, C, H, W], the reference's own layout) instead of channels-last rows.
  * Replaces pipeline...controlnet.py:614-616 and utils/scheduling_euler_discrete_karras_fix.py:481-520. */
 LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
                         float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W,

@@ -48,6 +48,9 @@ SIGNATURES = {
     "lkgd_attention_temporal": (i32, [vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_small_linear": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "lkgd_timestep_embedding": (i32, [vp, i32, i32, vp, vp]),
+    "lkgd_axpy_f32": (i32, [vp, f32, vp, i64, vp]),
+    "lkgd_scale_f32": (i32, [vp, f32, vp, i64, vp]),
+    "lkgd_polar": (i32, [vp, vp, vp, vp, i32, i32, vp]),
     "lkgd_pack_input": (i32, [vp, i32, i32, f32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     "lkgd_unpack_output": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "lkgd_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -59,6 +62,36 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing of the C-ABI launches (bench.py's roofline section).  Off by default;
+    when off the wrapper costs one attribute test per call."""
+    enabled = False
+    records = []      # (symbol, start_event, end_event, meta dict)
+    meta = None       # set by ops.* just before a call (e.g. {"flops": ..})
+
+
+PROF = Profiler()
+_TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
+          "lkgd_small_linear", "lkgd_timestep_embedding", "lkgd_pack_input", "lkgd_unpack_output",
+          "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_axpy_f32",
+          "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32"}
+
+
+def _timed(name, fn):
+    def call(*args):
+        if not PROF.enabled:
+            return fn(*args)
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROF.records.append((name, e0, e1, PROF.meta))
+        PROF.meta = None
+        return rc
+    return call
 
 
 class LkgdError(RuntimeError):
@@ -79,6 +112,8 @@ def load() -> C.CDLL:
         fn.restype, fn.argtypes = res, args
     if lib.lkgd_abi_version() != 1:
         raise LkgdError(f"ABI version mismatch: library reports {lib.lkgd_abi_version()}, binding expects 1")
+    for name in _TIMED:
+        setattr(lib, name, _timed(name, getattr(lib, name)))
     _lib = lib
     return lib
 

@@ -154,6 +154,11 @@ __global__ void axpby_kernel(const uint4* __restrict__ x, float alpha, uint4* __
 }
 
 // thread = one (s, f, c, p) element of the fp32 latent; pred is channels-last [2S*F*HW, ld]
+__global__ void scale_f32_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y, long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) y[idx] = alpha * x[idx];
+}
+
 __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg, const float* __restrict__ guidance,
                                  const float* __restrict__ x, float* __restrict__ x_next, float* __restrict__ v_out,
                                  int S, int F, int C, int HW, float sigma, float sigma_next) {
@@ -164,19 +169,40 @@ __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg
   const int c = (int)((idx / HW) % C);
   const int f = (int)((idx / ((long long)HW * C)) % F);
   const int s = (int)(idx / ((long long)HW * C * F));
-  const size_t row_u = ((size_t)s * F + f) * HW + p;
-  float v = pred[row_u * ld + c];
-  if (cfg) {
-    const size_t row_c = ((size_t)(S + s) * F + f) * HW + p;
-    const float cnd = pred[row_c * ld + c];
-    v = v + guidance[f] * (cnd - v);
+  float v, cnd = 0.f;
+  if (ld > 0) {   // channels-last prediction rows
+    v = pred[(((size_t)s * F + f) * HW + p) * ld + c];
+    if (cfg) cnd = pred[(((size_t)(S + s) * F + f) * HW + p) * ld + c];
+  } else {        // ld == 0: prediction in the latent's own [.,F,C,H,W] layout
+    v = pred[idx];
+    if (cfg) cnd = pred[total + idx];
   }
+  if (cfg) v = v + guidance[f] * (cnd - v);
   if (v_out) v_out[idx] = v;
   const float xs = x[idx];
   const float s2 = sigma * sigma + 1.0f;
   const float x0 = v * (-sigma / sqrtf(s2)) + xs / s2;
   const float deriv = (xs - x0) / sigma;
   x_next[idx] = xs + deriv * (sigma_next - sigma);
+}
+
+__global__ void axpy_f32_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y, long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) y[idx] = fmaf(alpha, x[idx], y[idx]);
+}
+
+// mode 0: (re, im) -> (mag, pha) = (|z|, atan2(im, re));  mode 1: (mag, pha) -> (re, im)
+__global__ void polar_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o0,
+                             float* __restrict__ o1, int n, int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  if (mode == 0) {
+    o0[idx] = hypotf(a[idx], b[idx]);
+    o1[idx] = atan2f(b[idx], a[idx]);
+  } else {
+    o0[idx] = a[idx] * cosf(b[idx]);
+    o1[idx] = a[idx] * sinf(b[idx]);
+  }
 }
 
 }  // namespace lkgd
@@ -266,9 +292,28 @@ extern "C" int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64
 extern "C" int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
                                    float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H,
                                    int32_t W, float sigma, float sigma_next, void* stream) {
-  if (S <= 0 || F <= 0 || C <= 0 || C > ld || sigma <= 0.f) return LKGD_ESHAPE;
+  if (S <= 0 || F <= 0 || C <= 0 || (ld != 0 && C > ld) || sigma <= 0.f) return LKGD_ESHAPE;
   const long long total = (long long)S * F * C * H * W;
   cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, S, F,
                                                                   C, H * W, sigma, sigma_next);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_axpy_f32(const float* x, float alpha, float* y, int64_t n, void* stream) {
+  if (n <= 0) return LKGD_ESHAPE;
+  axpy_f32_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(x, alpha, y, n);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_polar(const float* a, const float* b, float* o0, float* o1, int32_t n, int32_t mode,
+                          void* stream) {
+  if (n <= 0 || (mode != 0 && mode != 1)) return LKGD_ESHAPE;
+  polar_kernel<<<blocks_for(n, 128), 128, 0, ST(stream)>>>(a, b, o0, o1, n, mode);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_scale_f32(const float* x, float alpha, float* y, int64_t n, void* stream) {
+  if (n <= 0) return LKGD_ESHAPE;
+  scale_f32_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(x, alpha, y, n);
   return launch_epilogue();
 }

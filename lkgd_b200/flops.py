@@ -1,0 +1,76 @@
+"""Algorithmic work of one UNet forward (SURVEY.md Appendix B formulas): conv 2*k*Cin*Cout*px, linear 2*M*N*K,
+attention 4*N^2*C per sequence batch.  Used for the roofline numbers in bench.py / DESIGN.md."""
+from __future__ import annotations
+
+from typing import Dict
+
+
+def unet_flops(cfg: dict, B: int, F: int, H: int, W: int, lora_rank: int = 0, count_dead_cross_attn: bool = True
+               ) -> Dict[str, float]:
+    chans = cfg["block_out_channels"]
+    n = len(chans)
+    heads = cfg["num_attention_heads"]
+    heads = tuple(heads) if isinstance(heads, (tuple, list)) else (heads,) * n
+    lpb = cfg["layers_per_block"]
+    lpb = tuple(lpb) if isinstance(lpb, (tuple, list)) else (lpb,) * n
+    xdim = cfg["cross_attention_dim"]
+    xdim = tuple(xdim) if isinstance(xdim, (tuple, list)) else (xdim,) * n
+    out: Dict[str, float] = dict(conv3x3=0.0, tconv=0.0, shortcut=0.0, proj=0.0, geglu_ff=0.0, spatial_attn=0.0,
+                                 temporal_attn=0.0, cross_attn=0.0, lora=0.0)
+    BF = B * F
+
+    def res(cin, cout, h, w):
+        px = BF * h * w
+        out["conv3x3"] += 2 * 9 * cin * cout * px + 2 * 9 * cout * cout * px
+        out["tconv"] += 2 * (2 * 3 * cout * cout * px)
+        if cin != cout:
+            out["shortcut"] += 2 * cin * cout * px
+
+    def tr(c, h, w, xd):
+        m = BF * h * w
+        hw = h * w
+        out["proj"] += 2 * (2 * m * c * c)                       # proj_in / proj_out
+        out["proj"] += 2 * (4 * 2 * m * c * c)                   # spatial + temporal q,k,v,out
+        out["geglu_ff"] += 3 * (2 * m * c * 8 * c + 2 * m * 4 * c * c)
+        out["spatial_attn"] += BF * 4 * hw * hw * c
+        out["temporal_attn"] += B * hw * 4 * F * F * c
+        if count_dead_cross_attn:                                # as the reference executes it
+            out["cross_attn"] += 2 * (2 * 2 * m * c * c)
+        out["cross_attn"] += 2 * (2 * 2 * B * xd * c)
+        if lora_rank:
+            out["lora"] += 3 * (2 * m * c * lora_rank + 2 * m * lora_rank * c)
+
+    h, w = H, W
+    px = BF * h * w
+    out["conv3x3"] += 2 * 9 * cfg["in_channels"] * chans[0] * px
+    c = chans[0]
+    skip_c = [c]
+    for i, t in enumerate(cfg["down_block_types"]):
+        for j in range(lpb[i]):
+            res(c, chans[i], h, w)
+            c = chans[i]
+            if t.startswith("CrossAttn"):
+                tr(c, h, w, xdim[i])
+            skip_c.append(c)
+        if i != n - 1:
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            out["conv3x3"] += 2 * 9 * c * c * BF * h * w
+            skip_c.append(c)
+    res(c, c, h, w)
+    tr(c, h, w, xdim[-1])
+    res(c, c, h, w)
+    rc = list(reversed(chans))
+    rh = list(reversed(lpb))
+    rx = list(reversed(xdim))
+    for i, t in enumerate(cfg["up_block_types"]):
+        for j in range(rh[i] + 1):
+            res(c + skip_c.pop(), rc[i], h, w)
+            c = rc[i]
+            if t.startswith("CrossAttn"):
+                tr(c, h, w, rx[i])
+        if i != n - 1:
+            h, w = h * 2, w * 2
+            out["conv3x3"] += 2 * 9 * c * c * BF * h * w
+    out["conv3x3"] += 2 * 9 * c * cfg["out_channels"] * BF * h * w
+    out["total"] = sum(out.values())
+    return out

@@ -202,9 +202,9 @@ class CrossAttnDownBlockSpatioTemporal(Container):
     def __init__(self, in_channels, out_channels, temb, num_layers=2, tlayers=1, heads=1, xdim=1024,
                  add_downsample=True, eps=1e-6):
         super().__init__()
+        self.attentions = _attns(num_layers, heads, out_channels, tlayers, xdim)   # diffusers registers these first
         self.resnets = _resnets([(in_channels if i == 0 else out_channels, out_channels) for i in range(num_layers)],
                                 temb, eps)
-        self.attentions = _attns(num_layers, heads, out_channels, tlayers, xdim)
         self.downsamplers = nn.ModuleList([Downsample2D(out_channels)]) if add_downsample else None
 
 
@@ -213,8 +213,8 @@ class UNetMidBlockSpatioTemporal(Container):
 
     def __init__(self, in_channels, temb, num_layers=1, tlayers=1, heads=1, xdim=1024, eps=1e-5):
         super().__init__()
-        self.resnets = _resnets([(in_channels, in_channels)] * (num_layers + 1), temb, eps)
         self.attentions = _attns(num_layers, heads, in_channels, tlayers, xdim)
+        self.resnets = _resnets([(in_channels, in_channels)] * (num_layers + 1), temb, eps)
 
 
 def _up_chans(in_channels, prev_output_channel, out_channels, num_layers):
@@ -238,8 +238,8 @@ class CrossAttnUpBlockSpatioTemporal(Container):
     def __init__(self, in_channels, prev_output_channel, out_channels, temb, num_layers=3, tlayers=1, heads=1,
                  xdim=1024, add_upsample=True, eps=1e-6):
         super().__init__()
-        self.resnets = _resnets(_up_chans(in_channels, prev_output_channel, out_channels, num_layers), temb, eps)
         self.attentions = _attns(num_layers, heads, out_channels, tlayers, xdim)
+        self.resnets = _resnets(_up_chans(in_channels, prev_output_channel, out_channels, num_layers), temb, eps)
         self.upsamplers = nn.ModuleList([Upsample2D(out_channels)]) if add_upsample else None
 
 

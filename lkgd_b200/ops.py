@@ -110,6 +110,9 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     a.out, a.ldo, a.out_f32, a.n_store = out.data_ptr(), out.stride(0), int(out_f32), n_store
     lib = L.load()
     fn = lib.lkgd_gemm_simt_check if checker else lib.lkgd_gemm
+    if L.PROF.enabled:
+        L.PROF.meta = {"flops": 2.0 * M * N * (taps * a.K0 + a.K1), "mode": mode, "M": M, "N": N,
+                       "K": taps * a.K0 + a.K1}
     L.check(fn(C.byref(a), _stream()), "lkgd_gemm")
     return out
 
@@ -182,6 +185,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, n_img: int, 
     scale = d ** -0.5 if scale is None else scale
     lib = L.load()
     fn = lib.lkgd_attention_simt_check if checker else lib.lkgd_attention
+    if L.PROF.enabled:
+        L.PROF.meta = {"flops": 4.0 * n_img * heads * Nq * Nk * d}
     L.check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
                out.stride(0), n_img, heads, d, Nq, Nk, scale, _stream()), "lkgd_attention")
     return out
@@ -224,6 +229,36 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     L.check(L.load().lkgd_timestep_embedding(t.data_ptr(), t.numel(), dim, out.data_ptr(), _stream()),
             "lkgd_timestep_embedding")
     return out
+
+
+def axpy_f32(x: torch.Tensor, y: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """y += alpha * x in place (fp32)."""
+    _need_cuda(x, y)
+    if x.dtype != torch.float32 or y.dtype != torch.float32 or not x.is_contiguous() or not y.is_contiguous() \
+            or x.numel() != y.numel():
+        raise ValueError("axpy_f32: contiguous fp32 tensors of equal size")
+    L.check(L.load().lkgd_axpy_f32(x.data_ptr(), alpha, y.data_ptr(), x.numel(), _stream()), "lkgd_axpy_f32")
+    return y
+
+
+def scale_f32(x: torch.Tensor, alpha: float) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype != torch.float32:
+        raise ValueError("scale_f32: fp32 tensor expected")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.load().lkgd_scale_f32(x.data_ptr(), alpha, y.data_ptr(), x.numel(), _stream()), "lkgd_scale_f32")
+    return y
+
+
+def polar(a: torch.Tensor, b: torch.Tensor, mode: int):
+    """mode 0: (re, im) -> (mag, pha); mode 1: (mag, pha) -> (re, im).  fp32 contiguous."""
+    _need_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    o0, o1 = torch.empty_like(a), torch.empty_like(a)
+    L.check(L.load().lkgd_polar(a.data_ptr(), b.data_ptr(), o0.data_ptr(), o1.data_ptr(), a.numel(), mode,
+                                _stream()), "lkgd_polar")
+    return o0, o1
 
 
 # ----------------------------------------------------------------------------------------------- glue
@@ -299,13 +334,25 @@ def axpby(x: torch.Tensor, alpha: float, y: torch.Tensor, beta: float) -> torch.
 
 def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torch.Tensor, sigma: float,
                    sigma_next: float, *, cfg: bool, want_v: bool = False):
-    """pred fp32 channels-last [(2)S*F*H*W, ld]; x fp32 [S,F,C,H,W] -> (x_next, v or None)."""
+    """pred fp32: channels-last rows [(2)S*F*H*W, ld] (2-D) or the latent's own layout [(2)S,F,C,H,W] (5-D);
+    x fp32 [S,F,C,H,W] -> (x_next, v or None)."""
     _need_cuda(pred, guidance, x)
     S, F, Cn, H, W = x.shape
     x = x.contiguous()
+    if pred.dtype != torch.float32 or x.dtype != torch.float32:
+        raise ValueError("cfg_euler_step works in fp32")
+    if pred.dim() == 5:
+        pred = pred.contiguous()
+        ld = 0
+        if pred.numel() != (2 if cfg else 1) * x.numel():
+            raise ValueError("prediction shape does not match the latent")
+    else:
+        ld = pred.stride(0)
+        if pred.shape[0] != (2 if cfg else 1) * S * F * H * W:
+            raise ValueError("prediction rows do not match the latent")
     x_next = torch.empty_like(x)
     v = torch.empty_like(x) if want_v else None
-    L.check(L.load().lkgd_cfg_euler_step(pred.data_ptr(), pred.stride(0), int(cfg), _ptr(guidance), x.data_ptr(),
+    L.check(L.load().lkgd_cfg_euler_step(pred.data_ptr(), ld, int(cfg), _ptr(guidance), x.data_ptr(),
                                          x_next.data_ptr(), _ptr(v), S, F, Cn, H, W, sigma, sigma_next, _stream()),
             "lkgd_cfg_euler_step")
     return x_next, v

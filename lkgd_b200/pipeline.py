@@ -1,0 +1,184 @@
+"""Latent-space Stable-Video-Diffusion sampling loop on the lkgd_b200 engine.
+
+Mirrors the denoising part of the reference pipelines' ``__call__``
+(pipeline/pipeline_stable_video_diffusion_controlnet.py:364-646: added-time ids :517-526, timesteps :529,
+latents :535-545, guidance ramp :553-558, loop :577-630).  VAE / CLIP encode-decode sit either side of the hot
+path and are NOT part of this package: the caller passes what ``_encode_image`` /
+``_encode_vae_image`` return (``image_embeddings`` [2S,1,1024] uncond-first, ``image_latents`` [2S,F,4,h,w]) and
+receives latents (``output_type="latent"``).
+
+Per step the loop launches: one fused pack kernel (CFG duplication + scale_model_input + image-latent concat +
+NCHW->channels-last), [ControlNet], the UNet, and one fused CFG-combine + Euler-Karras kernel reading the UNet's
+channels-last fp32 prediction directly."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import Conditioning, Geom
+from .scheduler import EulerDiscreteScheduler
+from .unet import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionModel
+
+
+@dataclass
+class StableVideoDiffusionPipelineOutput:
+    frames: torch.Tensor
+
+
+def _append_dims(x, target_dims):
+    dims_to_append = target_dims - x.ndim
+    if dims_to_append < 0:
+        raise ValueError(f"input has {x.ndim} dims but target_dims is {target_dims}, which is less")
+    return x[(...,) + (None,) * dims_to_append]
+
+
+class StableVideoDiffusionPipeline:
+    """``unet`` may be the plain/ControlNet-accepting UNet or the LKGD UNet (then ``domain_features`` and
+    ``flow_features`` are required, the signature the reference's missing LKGD pipeline would have - SURVEY F11)."""
+
+    def __init__(self, unet, scheduler: EulerDiscreteScheduler, controlnet: Optional[ControlNetSDVModel] = None):
+        self.unet, self.scheduler, self.controlnet = unet, scheduler, controlnet
+        self._guidance_scale = None
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    def _get_add_time_ids(self, fps, motion_bucket_id, noise_aug_strength, dtype, batch_size, num_videos_per_prompt,
+                          do_classifier_free_guidance):
+        """Inference order [fps, motion_bucket_id, noise_aug_strength] (reference pipeline :239-266)."""
+        add_time_ids = [fps, motion_bucket_id, noise_aug_strength]
+        passed = self.unet.config.addition_time_embed_dim * len(add_time_ids)
+        expected = self.unet.add_embedding.linear_1.in_features
+        if expected != passed:
+            raise ValueError(f"Model expects an added time embedding vector of length {expected}, but a vector of "
+                             f"{passed} was created. The model has an incorrect config.")
+        ids = torch.tensor([add_time_ids], dtype=dtype).repeat(batch_size * num_videos_per_prompt, 1)
+        return torch.cat([ids, ids]) if do_classifier_free_guidance else ids
+
+    def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator,
+                        latents=None):
+        shape = (batch_size, num_frames, num_channels_latents // 2, height, width)   # latent-space sizes
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}.")
+        if latents is None:
+            if isinstance(generator, list):
+                latents = torch.cat([torch.randn((1,) + shape[1:], generator=g, device=g.device, dtype=dtype).to(device)
+                                     for g in generator])
+            else:
+                gdev = generator.device if generator is not None else device
+                latents = torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
+        else:
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma.to(latents.device)
+
+    @torch.no_grad()
+    def prepare(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, num_frames: Optional[int] = None,
+                num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
+                fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
+                num_videos_per_prompt: int = 1, controlnet_condition: Optional[torch.Tensor] = None,
+                controlnet_cond_scale: float = 1.0, domain_features: Optional[torch.Tensor] = None,
+                flow_features: Optional[torch.Tensor] = None) -> dict:
+        """Everything ``__call__`` does before the loop (reference :475-558): validates, builds added-time ids,
+        timesteps, the frame-wise guidance ramp, and moves the conditioning to the device.  Returns the loop state
+        consumed by ``denoise_step``."""
+        unet, sched = self.unet, self.scheduler
+        device = unet.device
+        do_cfg = max_guidance_scale > 1.0          # reference :485 (quirk D1: local, not the property)
+        n_lat = image_latents.shape[0]
+        S = n_lat // 2 if do_cfg else n_lat
+        num_frames = num_frames if num_frames is not None else unet.config.num_frames
+        if image_latents.shape[1] != num_frames:
+            raise ValueError("image_latents must be repeated over num_frames ([2S, F, 4, h, w])")
+        if image_embeddings.shape[0] != n_lat:
+            raise ValueError("image_embeddings and image_latents must have the same (CFG-duplicated) batch")
+        lkgd = isinstance(unet, UNetSpatioTemporalConditionModel)
+        if lkgd and (domain_features is None or flow_features is None):
+            raise ValueError("the LKGD UNet needs domain_features and flow_features")
+        fps = fps - 1                              # reference :482: the model was conditioned on fps - 1
+        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, torch.float32, S,
+                                                num_videos_per_prompt, do_cfg).to(device)
+        sched.set_timesteps(num_inference_steps, device=device)
+        guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames).unsqueeze(0).to(device)
+        self._guidance_scale = _append_dims(guidance.repeat(S * num_videos_per_prompt, 1), 5)
+        if controlnet_condition is not None and self.controlnet is None:
+            raise ValueError("controlnet_condition given but the pipeline has no controlnet")
+        if controlnet_condition is not None:
+            cc = controlnet_condition
+            if cc.ndim == 4:
+                cc = cc.unsqueeze(0)
+            cc = torch.cat([cc] * 2) if do_cfg else cc      # reference :547-550 duplicates unconditionally (D3)
+            controlnet_condition = cc.to(device=device, dtype=torch.float32)
+        return dict(S=S * num_videos_per_prompt, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
+                    w=image_latents.shape[-1], do_cfg=do_cfg, added_time_ids=added_time_ids,
+                    guidance=guidance.reshape(-1).to(torch.float32).contiguous(),
+                    image_latents=image_latents.to(device=device, dtype=torch.float32).contiguous(),
+                    image_embeddings=image_embeddings.to(device), controlnet_condition=controlnet_condition,
+                    controlnet_cond_scale=controlnet_cond_scale,
+                    extra=(domain_features.to(device), flow_features.to(device)) if lkgd else ())
+
+    @torch.no_grad()
+    def denoise_step(self, st: dict, i: int, latents: torch.Tensor, want_v: bool = False):
+        """One iteration of the reference's denoising loop (:577-619) for step index ``i``: fused
+        dup/scale/concat/layout kernel -> [ControlNet] -> UNet -> fused CFG + Euler-Karras kernel.
+        ``latents``: fp32 [S,F,4,h,w] on the device.  Returns (next latents, guided prediction or None)."""
+        sched, unet = self.scheduler, self.unet
+        pk = unet.packed()
+        sched.index_for(i)
+        sigma = float(sched._sigmas_host[i])
+        t = float(sched._timesteps_host[i])
+        # CFG duplication + scale_model_input + concat(image_latents) + layout, one kernel (:579-584)
+        x = ops.pack_input(latents, float(1.0 / np.sqrt(np.float32(sigma) ** 2 + 1)), st["image_latents"],
+                           N=st["n_batch"], Cpad=pk.cin_pad)
+        g = Geom(st["n_batch"], st["F"], st["h"], st["w"])
+        kw = {}
+        if st["controlnet_condition"] is not None:
+            down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
+                                                       st["controlnet_condition"], st["controlnet_cond_scale"])
+            kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
+        rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
+                                   added_time_ids=st["added_time_ids"], **kw)
+        return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
+                                   want_v=want_v)
+
+    @torch.no_grad()
+    def __call__(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, num_frames: Optional[int] = None,
+                 num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
+                 fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
+                 num_videos_per_prompt: int = 1, generator=None, latents: Optional[torch.Tensor] = None,
+                 controlnet_condition: Optional[torch.Tensor] = None, controlnet_cond_scale: float = 1.0,
+                 domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
+                 output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
+                 return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False):
+        if output_type != "latent":
+            raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
+                             "VAE of your choice (SURVEY.md section 8f, N1)")
+        st = self.prepare(image_embeddings, image_latents, num_frames, num_inference_steps, min_guidance_scale,
+                          max_guidance_scale, fps, motion_bucket_id, noise_aug_strength, num_videos_per_prompt,
+                          controlnet_condition, controlnet_cond_scale, domain_features, flow_features)
+        device = self.unet.device
+        latents = self.prepare_latents(st["S"], st["F"], self.unet.config.in_channels, st["h"], st["w"],
+                                       torch.float32, device, generator, latents).to(torch.float32).contiguous()
+        timesteps = self.scheduler.timesteps
+        traj: List[torch.Tensor] = []
+        preds: List[torch.Tensor] = []
+        for i in range(len(timesteps)):
+            if max_steps is not None and i >= max_steps:
+                break
+            latents, v = self.denoise_step(st, i, latents, want_v=return_trajectory)
+            if return_trajectory:
+                preds.append(v)
+                traj.append(latents)
+            if callback_on_step_end is not None:
+                out = callback_on_step_end(self, i, timesteps[i], {"latents": latents})
+                latents = out.pop("latents", latents)
+        if return_trajectory:
+            return latents, preds, traj
+        if not return_dict:
+            return latents
+        return StableVideoDiffusionPipelineOutput(frames=latents)

@@ -1,0 +1,638 @@
+"""Reference-facing UNet / ControlNet modules: same constructor arguments, parameter names, ``forward``
+signatures and error behaviour as the reference classes, with the forward pass executed by the CUDA engine.
+
+  UNetSpatioTemporalConditionControlNetModel  <- models/unet_spatio_temporal_condition_controlnet.py:69-245,358-508
+  UNetSpatioTemporalConditionModel (LKGD)     <- models/unet_spatio_temporal_condition.py:72-298,448-693
+  ControlNetSDVModel                          <- models/controlnet_sdv.py:160-316,441-578,581-638
+
+Inference only in this round (``forward`` runs under no_grad; training backward is SURVEY.md section 8 row a14/a15,
+not built yet)."""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import modules as M
+from . import ops
+from .engine import Conditioning, Geom, PackedUNet, SL_LEAKY, SL_SILU, _conv3x3_weight, _f32, residual_multipliers
+from .ops import A_CONV3X3, ACT_SILU, bf16
+
+SVD_XT_CONFIG = dict(
+    sample_size=96, in_channels=8, out_channels=4,
+    down_block_types=("CrossAttnDownBlockSpatioTemporal",) * 3 + ("DownBlockSpatioTemporal",),
+    up_block_types=("UpBlockSpatioTemporal",) + ("CrossAttnUpBlockSpatioTemporal",) * 3,
+    block_out_channels=(320, 640, 1280, 1280), addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=768, layers_per_block=2, cross_attention_dim=1024,
+    transformer_layers_per_block=1, num_attention_heads=(5, 10, 20, 20), num_frames=25,
+)
+REDUCED_CONFIG = dict(
+    sample_size=32, in_channels=8, out_channels=4,
+    down_block_types=("CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+    up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal"),
+    block_out_channels=(32, 64), addition_time_embed_dim=32,
+    projection_class_embeddings_input_dim=96, layers_per_block=2, cross_attention_dim=32,
+    transformer_layers_per_block=1, num_attention_heads=(2, 4), num_frames=8,
+)
+
+TEMPORAL_QKV = r".*temporal_transformer_blocks\.0\.attn1\.to_[qkv]$"     # train_models/train_svd_lora.py:1081-1088
+ALL_ATTN_PROJ = r".*\.(to_q|to_k|to_v|to_out\.0)$"                        # run_models/run_inference_flow_lora.py:326-331
+
+
+@dataclass
+class UNetSpatioTemporalConditionOutput:
+    sample: torch.Tensor = None
+
+
+@dataclass
+class ControlNetOutput:
+    down_block_res_samples: Tuple[torch.Tensor]
+    mid_block_res_sample: torch.Tensor
+
+
+class ChannelsLast:
+    """A [N, H, W, C] bf16 activation kept in the engine's layout (rows = pixels).  Passing these between
+    ``ControlNetSDVModel`` and the UNet skips the NCHW round trip of the reference's residual hand-off."""
+
+    def __init__(self, rows: torch.Tensor, N: int, H: int, W: int):
+        self.rows, self.N, self.H, self.W = rows, N, H, W
+
+    def to_nchw(self) -> torch.Tensor:
+        return ops.nhwc_to_nchw(self.rows, self.N, self.H, self.W)
+
+
+def _tuple(v, n):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+
+
+class _Base(nn.Module):
+    _supports_gradient_checkpointing = True
+
+    # -------------------------------------------------------------------- construction helpers
+    def _build_encoder(self, in_channels, down_block_types, block_out_channels, layers_per_block,
+                       transformer_layers_per_block, num_attention_heads, cross_attention_dim, addition_time_embed_dim,
+                       projection_class_embeddings_input_dim):
+        n = len(down_block_types)
+        heads, xdim = _tuple(num_attention_heads, n), _tuple(cross_attention_dim, n)
+        lpb, tlpb = _tuple(layers_per_block, n), _tuple(transformer_layers_per_block, n)
+        c0 = block_out_channels[0]
+        temb = c0 * 4
+        self.conv_in = M.Conv2d(in_channels, c0, 3, padding=1)
+        self.time_embedding = M.TimestepEmbedding(c0, temb)
+        self.add_embedding = M.TimestepEmbedding(projection_class_embeddings_input_dim, temb)
+        self.down_blocks = nn.ModuleList()
+        out_c = c0
+        for i, t in enumerate(down_block_types):
+            in_c, out_c = out_c, block_out_channels[i]
+            last = i == n - 1
+            if t == "CrossAttnDownBlockSpatioTemporal":
+                blk = M.CrossAttnDownBlockSpatioTemporal(in_c, out_c, temb, lpb[i], tlpb[i], heads[i], xdim[i],
+                                                         add_downsample=not last)
+            elif t == "DownBlockSpatioTemporal":
+                blk = M.DownBlockSpatioTemporal(in_c, out_c, temb, lpb[i], add_downsample=not last)
+            else:
+                raise ValueError(f"{t} does not exist.")
+            self.down_blocks.append(blk)
+        return heads, xdim, lpb, tlpb, temb
+
+    # -------------------------------------------------------------------- diffusers-style surface
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def attn_processors(self):
+        """Attention runs in fixed CUDA kernels; the processor API is kept as a read-only shim
+        (reference ...controlnet.py:249-271)."""
+        return {n + ".processor": "lkgd_b200" for n, m in self.named_modules() if isinstance(m, M.Attention)}
+
+    def set_attn_processor(self, processor):
+        return None
+
+    def set_default_attn_processor(self):
+        return None
+
+    def enable_forward_chunking(self, chunk_size=None, dim=0):
+        if dim not in (0, 1):      # reference ...controlnet.py:341-342
+            raise ValueError(f"Make sure to set `dim` to either 0 or 1, not {dim}")
+        return None                # feed-forward chunking is a memory knob of the reference; not needed here
+
+    def _set_gradient_checkpointing(self, module, value=False):
+        return None
+
+    # -------------------------------------------------------------------- LoRA (peft add_adapter equivalent)
+    def add_lora(self, r: int, lora_alpha: Optional[float] = None, target: str = TEMPORAL_QKV,
+                 init_lora_weights="gaussian", adapter_name: str = "default") -> List[str]:
+        """Wraps every Linear whose qualified name matches ``target`` (reference train_svd_lora.py:1081-1102)."""
+        lora_alpha = r if lora_alpha is None else lora_alpha
+        pat = re.compile(target)
+        hits = [n for n, m in self.named_modules() if isinstance(m, M.Linear) and pat.match(n)
+                and ".lora_" not in n and not n.endswith("base_layer")]
+        for name in hits:
+            parent_name, _, leaf = name.rpartition(".")
+            parent = self.get_submodule(parent_name) if parent_name else self
+            old = parent[int(leaf)] if leaf.isdigit() else getattr(parent, leaf)
+            new = M.LoraLinear(old, r, lora_alpha, init_lora_weights, adapter_name)
+            if leaf.isdigit():
+                parent[int(leaf)] = new
+            else:
+                setattr(parent, leaf, new)
+        self.invalidate()
+        return hits
+
+    def merge_lora(self):
+        """W += scaling * B A (reference models/lora_layer.py:300-361)."""
+        for m in self.modules():
+            if isinstance(m, M.LoraLinear) and not m.merged:
+                a, b = m.lora_A[m.adapter_name].weight, m.lora_B[m.adapter_name].weight
+                m.base_layer.weight.data += ((b.float() @ a.float()) * m.scaling).to(m.base_layer.weight.dtype)
+                m.merged = True
+        self.invalidate()
+
+    # -------------------------------------------------------------------- engine plumbing
+    def invalidate(self):
+        """Call after changing parameters: the kernel-ready weight copies are rebuilt on the next forward."""
+        self._packed = None
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._packed = None
+        return out
+
+    def packed(self) -> PackedUNet:
+        if getattr(self, "_packed", None) is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("lkgd_b200 runs on CUDA devices only: move the module with .to('cuda') "
+                                   "(there is no CPU or PyTorch fallback)")
+            ops.device_check(self.device.index or 0)
+            with torch.no_grad():
+                self._packed = PackedUNet(self, fold_lora=getattr(self, "fold_lora", True))
+        return self._packed
+
+    def _timestep_tensor(self, timestep, sample) -> torch.Tensor:
+        """python scalar, 0-d or [B] tensor (reference ...controlnet.py:389-404)."""
+        if not torch.is_tensor(timestep):
+            return torch.tensor([float(timestep)], dtype=torch.float32, device=sample.device)
+        t = timestep.to(device=sample.device, dtype=torch.float32)
+        return t[None] if t.ndim == 0 else t
+
+    def _pack_sample(self, sample: torch.Tensor, pk: PackedUNet) -> Tuple[torch.Tensor, Geom]:
+        if sample.ndim != 5:
+            raise ValueError(f"sample must be [batch, frames, channels, height, width], got {tuple(sample.shape)}")
+        B, F, C, H, W = sample.shape
+        if C != self.config.in_channels:
+            raise ValueError(f"sample has {C} channels, the model expects {self.config.in_channels}")
+        n_down = sum(1 for d in pk.down if d[2] is not None)
+        if H % (1 << n_down) or W % (1 << n_down):
+            # the reference has no upsample_size forwarding, skip shapes would not match
+            raise ValueError(f"height and width must be divisible by {1 << n_down}, got {H}x{W}")
+        x = ops.pack_input(sample, 1.0, None, N=B, Cpad=pk.cin_pad)
+        return x, Geom(B, F, H, W)
+
+    def _context(self, encoder_hidden_states: torch.Tensor, *extra) -> torch.Tensor:
+        return encoder_hidden_states.to(torch.float32).contiguous()
+
+
+class UNetSpatioTemporalConditionControlNetModel(_Base):
+    """SVD UNet that additionally accepts ControlNet residuals."""
+
+    def __init__(self, sample_size: Optional[int] = None, in_channels: int = 8, out_channels: int = 4,
+                 down_block_types: Tuple[str] = SVD_XT_CONFIG["down_block_types"],
+                 up_block_types: Tuple[str] = SVD_XT_CONFIG["up_block_types"],
+                 block_out_channels: Tuple[int] = (320, 640, 1280, 1280), addition_time_embed_dim: int = 256,
+                 projection_class_embeddings_input_dim: int = 768, layers_per_block: Union[int, Tuple[int]] = 2,
+                 cross_attention_dim: Union[int, Tuple[int]] = 1024,
+                 transformer_layers_per_block: Union[int, Tuple[int]] = 1,
+                 num_attention_heads: Union[int, Tuple[int]] = (5, 10, 10, 20), num_frames: int = 25,
+                 time_context_order: str = "hw_major_0272"):
+        super().__init__()
+        self._init_root()
+        n = len(down_block_types)
+        if len(up_block_types) != n:
+            raise ValueError(f"Must provide the same number of `down_block_types` as `up_block_types`. "
+                             f"`down_block_types`: {down_block_types}. `up_block_types`: {up_block_types}.")
+        if len(block_out_channels) != n:
+            raise ValueError(f"Must provide the same number of `block_out_channels` as `down_block_types`. "
+                             f"`block_out_channels`: {block_out_channels}. `down_block_types`: {down_block_types}.")
+        if not isinstance(num_attention_heads, int) and len(num_attention_heads) != n:
+            raise ValueError(f"Must provide the same number of `num_attention_heads` as `down_block_types`. "
+                             f"`num_attention_heads`: {num_attention_heads}. `down_block_types`: {down_block_types}.")
+        if isinstance(cross_attention_dim, (list, tuple)) and len(cross_attention_dim) != n:
+            raise ValueError(f"Must provide the same number of `cross_attention_dim` as `down_block_types`. "
+                             f"`cross_attention_dim`: {cross_attention_dim}. `down_block_types`: {down_block_types}.")
+        if not isinstance(layers_per_block, int) and len(layers_per_block) != n:
+            raise ValueError(f"Must provide the same number of `layers_per_block` as `down_block_types`. "
+                             f"`layers_per_block`: {layers_per_block}. `down_block_types`: {down_block_types}.")
+        if time_context_order not in ("hw_major_0272", "b_major"):
+            raise ValueError(f"time_context_order must be 'hw_major_0272' or 'b_major', got {time_context_order}")
+        self.config = SimpleNamespace(
+            sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+            down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
+            block_out_channels=tuple(block_out_channels), addition_time_embed_dim=addition_time_embed_dim,
+            projection_class_embeddings_input_dim=projection_class_embeddings_input_dim,
+            layers_per_block=layers_per_block, cross_attention_dim=cross_attention_dim,
+            transformer_layers_per_block=transformer_layers_per_block, num_attention_heads=num_attention_heads,
+            num_frames=num_frames, time_context_order=time_context_order)
+        self.sample_size = sample_size
+        heads, xdim, lpb, tlpb, temb = self._build_encoder(
+            in_channels, down_block_types, block_out_channels, layers_per_block, transformer_layers_per_block,
+            num_attention_heads, cross_attention_dim, addition_time_embed_dim, projection_class_embeddings_input_dim)
+        self.up_blocks = nn.ModuleList()   # registered before the LKGD modules and mid_block (reference order)
+        self._init_extra()
+        self.mid_block = M.UNetMidBlockSpatioTemporal(block_out_channels[-1], temb, 1, tlpb[-1], heads[-1], xdim[-1])
+        rc, rh, rl, rx, rt = (list(reversed(v)) for v in (block_out_channels, heads, lpb, xdim, tlpb))
+        out_c = rc[0]
+        self.num_upsamplers = 0
+        for i, t in enumerate(up_block_types):
+            last = i == n - 1
+            prev_c, out_c = out_c, rc[i]
+            in_c = rc[min(i + 1, n - 1)]
+            if not last:
+                self.num_upsamplers += 1
+            if t == "CrossAttnUpBlockSpatioTemporal":
+                blk = M.CrossAttnUpBlockSpatioTemporal(in_c, prev_c, out_c, temb, rl[i] + 1, rt[i], rh[i], rx[i],
+                                                       add_upsample=not last)
+            elif t == "UpBlockSpatioTemporal":
+                blk = M.UpBlockSpatioTemporal(in_c, prev_c, out_c, temb, rl[i] + 1, add_upsample=not last)
+            else:
+                raise ValueError(f"{t} does not exist.")
+            self.up_blocks.append(blk)
+        self.conv_norm_out = M.GroupNorm(32, block_out_channels[0], eps=1e-5)
+        self.conv_out = M.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
+        self._packed = None
+
+    def _init_root(self):
+        pass
+
+    def _init_extra(self):
+        pass
+
+    # -------------------------------------------------------------------- forward
+    def _residual_rows(self, r, g: Geom) -> torch.Tensor:
+        if isinstance(r, ChannelsLast):
+            return r.rows
+        if r.ndim != 4:
+            raise ValueError("ControlNet residuals must be [batch*frames, C, H, W] tensors or ChannelsLast")
+        return ops.nchw_to_nhwc(r)
+
+    @torch.no_grad()
+    def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor, *extra,
+                       down_block_additional_residuals=None, mid_block_additional_residual=None,
+                       added_time_ids: torch.Tensor = None) -> torch.Tensor:
+        """Engine-layout forward.  ``x``: bf16 channels-last rows [B*F*H*W, 64] (input channels zero-padded to 64,
+        see ``ops.pack_input``).  Returns the fp32 channels-last prediction [B*F*H*W, out_channels]."""
+        if added_time_ids is None:
+            raise ValueError("added_time_ids is required")
+        pk = self.packed()
+        if encoder_hidden_states.shape[0] != g.B or added_time_ids.shape[0] != g.B:
+            raise ValueError("encoder_hidden_states / added_time_ids batch does not match sample")
+        emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
+        cond = Conditioning(emb, self._context(encoder_hidden_states, *extra))
+        x, skips, geoms, gm = pk.encoder(x, g, cond)
+        if mid_block_additional_residual is not None:
+            ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)
+        if down_block_additional_residuals is not None:
+            per_block = [len(d[0]) + (1 if d[2] is not None else 0) for d in pk.down]
+            per_block[0] += 1   # conv_in output travels with block 0
+            mult = residual_multipliers(len(pk.down), per_block)
+            # zip truncation of the reference: extra residuals / skips are ignored
+            for s, r, m, gs in zip(skips, down_block_additional_residuals, mult, geoms):
+                ops.axpby(self._residual_rows(r, gs), float(m), s, 1.0)
+        return pk.decoder(x, skips, gm, cond)
+
+    @torch.no_grad()
+    def forward_rows(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, *extra, **kw):
+        x, g = self._pack_sample(sample, self.packed())
+        return self.forward_packed(x, g, timestep, encoder_hidden_states, *extra, **kw), g
+
+    def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
+                encoder_hidden_states: torch.Tensor,
+                down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
+                mid_block_additional_residual: Optional[torch.Tensor] = None, return_dict: bool = True,
+                added_time_ids: torch.Tensor = None):
+        rows, g = self.forward_rows(sample, timestep, encoder_hidden_states,
+                                    down_block_additional_residuals=down_block_additional_residuals,
+                                    mid_block_additional_residual=mid_block_additional_residual,
+                                    added_time_ids=added_time_ids)
+        out = ops.unpack_output(rows, g.B, g.F, self.config.out_channels, g.H, g.W)
+        if out.dtype != sample.dtype:
+            out = out.to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return UNetSpatioTemporalConditionOutput(sample=out)
+
+
+# --------------------------------------------------------------------------------------------------- LKGD
+class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetModel):
+    """LKGD UNet: the latent-knowledge block (reference unet_spatio_temporal_condition.py:197-225,536-613) fuses the
+    CLIP embedding with domain / flow ViT features (grouped 1x1 conv, quaternion linear, rFFT magnitude / phase
+    fuse, iFFT, MLP) into the one-token cross-attention context."""
+
+    def _init_root(self):
+        self.quaternion_lora_texts = nn.Parameter(torch.zeros(256))
+        self.quaternion_lora_texts_fft_mag = nn.Parameter(torch.zeros(129))
+        self.quaternion_lora_texts_fft_pha = nn.Parameter(torch.zeros(129))
+
+    def _init_extra(self):
+        def dw():
+            return M.Conv1d(1024, 256, kernel_size=1, groups=256, bias=False)
+        self.quaternion_lora_dconv, self.quaternion_lora_lconv, self.quaternion_lora_fconv = dw(), dw(), dw()
+        self.quaternion_lora_fuse = M.QuaternionLinear(1024, 512)
+        self.quaternion_lora_fuse_fft_mag = M.QuaternionLinear(512, 256)
+        self.quaternion_lora_fuse_fft_pha = M.QuaternionLinear(512, 256)
+        self.quaternion_lora_fuse_fft_mag0 = M.Linear(4, 1)
+        self.quaternion_lora_fuse_fft_pha0 = M.Linear(4, 1)
+        self.quaternion_lora_fuse_sf = nn.Sequential(M.Linear(1024, 256), nn.LeakyReLU(0.1), M.Linear(256, 1024))
+
+    def invalidate(self):
+        super().invalidate()
+        self._lk = None
+
+    def _lk_pack(self):
+        """Weight preprocessing (once): every linear stage of the block as a dense fp32 matrix for the
+        small-linear kernel - grouped conv (+ the 1000->1024 linear interpolation folded in), Hamilton matrices,
+        rDFT(256) and irDFT(512) bases."""
+        if getattr(self, "_lk", None) is not None:
+            return self._lk
+        dev = self.device
+        f64 = torch.float64
+
+        def grouped(conv):          # Conv1d(1024->256, k=1, groups=256): out_j = sum_m w[j,m] x[4j+m]
+            w = conv.weight.detach().to(f64).reshape(256, 4)
+            full = torch.zeros(256, 1024, dtype=f64, device=dev)
+            j = torch.arange(256, device=dev)
+            for m in range(4):
+                full[j, 4 * j + m] = w[:, m]
+            return full
+
+        # F.interpolate(size=1024, mode="linear", align_corners=False) as a [1024, 1000] matrix
+        o = torch.arange(1024, dtype=f64, device=dev)
+        src = ((o + 0.5) * (1000 / 1024) - 0.5).clamp(min=0)
+        i0 = src.floor().long().clamp(max=999)
+        i1 = (i0 + 1).clamp(max=999)
+        lam = src - i0
+        interp = torch.zeros(1024, 1000, dtype=f64, device=dev)
+        interp[torch.arange(1024, device=dev), i0] += 1 - lam
+        interp[torch.arange(1024, device=dev), i1] += lam
+
+        def ham(q):                 # y = x @ W  ->  small_linear weight is W^T [out, in]
+            r, i, j, k = (getattr(q, n).detach().to(f64) for n in ("r_weight", "i_weight", "j_weight", "k_weight"))
+            W = torch.cat([torch.cat([r, -i, -j, -k], 0), torch.cat([i, r, -k, j], 0),
+                           torch.cat([j, k, r, -i], 0), torch.cat([k, -j, i, r], 0)], 1)
+            return W.t().contiguous().float(), _f32(q.bias)
+
+        n = torch.arange(256, dtype=f64, device=dev)
+        k = torch.arange(129, dtype=f64, device=dev)
+        ang = 2 * math.pi * k[:, None] * n[None, :] / 256
+        t = torch.arange(512, dtype=f64, device=dev)
+        k2 = torch.arange(257, dtype=f64, device=dev)
+        ang2 = 2 * math.pi * t[:, None] * k2[None, :] / 512
+        wgt = torch.full((257,), 2.0, dtype=f64, device=dev)
+        wgt[0] = wgt[256] = 1.0
+        ir = (torch.cos(ang2) * wgt / 512)
+        ii = (-torch.sin(ang2) * wgt / 512)
+        ii[:, 0] = 0
+        ii[:, 256] = 0              # irfft ignores the imaginary part of the DC and Nyquist bins
+        sf = self.quaternion_lora_fuse_sf
+        self._lk = dict(
+            lconv=grouped(self.quaternion_lora_lconv).float().contiguous(),
+            dconv=(grouped(self.quaternion_lora_dconv) @ interp).float().contiguous(),
+            fconv=(grouped(self.quaternion_lora_fconv) @ interp).float().contiguous(),
+            fuse=ham(self.quaternion_lora_fuse), mag=ham(self.quaternion_lora_fuse_fft_mag),
+            pha=ham(self.quaternion_lora_fuse_fft_pha),
+            dft_re=torch.cos(ang).float().contiguous(), dft_im=(-torch.sin(ang)).float().contiguous(),
+            idft=torch.cat([ir, ii], 1).float().contiguous(),
+            mag0=(_f32(self.quaternion_lora_fuse_fft_mag0.weight), _f32(self.quaternion_lora_fuse_fft_mag0.bias)),
+            pha0=(_f32(self.quaternion_lora_fuse_fft_pha0.weight), _f32(self.quaternion_lora_fuse_fft_pha0.bias)),
+            sf0=(_f32(sf[0].weight), _f32(sf[0].bias)), sf2=(_f32(sf[2].weight), _f32(sf[2].bias)),
+            texts=_f32(self.quaternion_lora_texts), tmag=_f32(self.quaternion_lora_texts_fft_mag),
+            tpha=_f32(self.quaternion_lora_texts_fft_pha))
+        return self._lk
+
+    def _context(self, encoder_hidden_states, domain_features, flow_features) -> torch.Tensor:
+        if encoder_hidden_states.shape[1] != 1 or encoder_hidden_states.shape[2] != 1024:
+            raise ValueError("the latent-knowledge block expects encoder_hidden_states of shape [B, 1, 1024]")
+        lk = self._lk_pack()
+        dev = encoder_hidden_states.device
+        B = encoder_hidden_states.shape[0]
+        f32 = torch.float32
+        ctx = encoder_hidden_states.to(f32).reshape(B, 1024).contiguous()
+        dom = domain_features.to(f32).reshape(-1, 1000).contiguous()
+        flo = flow_features.to(f32).reshape(-1, 1000).contiguous()
+        Bd = dom.shape[0]
+        cat = torch.empty(B, 1024, device=dev, dtype=f32)          # [lh | ld | lf | texts]
+        ops.small_linear(ctx, lk["lconv"], out=cat[:, 0:256])
+        if Bd == B:
+            ops.small_linear(dom, lk["dconv"], out=cat[:, 256:512])
+            ops.small_linear(flo, lk["fconv"], out=cat[:, 512:768])
+        elif Bd == 1 and B == 2:                                   # quirk D8: duplicated only for a CFG pair
+            for b in range(B):
+                ops.small_linear(dom, lk["dconv"], out=cat[b:b + 1, 256:512])
+                ops.small_linear(flo[:1], lk["fconv"], out=cat[b:b + 1, 512:768])
+        else:
+            raise ValueError(f"domain_features batch {Bd} is incompatible with encoder_hidden_states batch {B}")
+        cat[:, 768:] = lk["texts"]
+        spatial = torch.empty(B, 1024, device=dev, dtype=f32)      # [spatial 512 | freq 512]
+        ops.small_linear(cat, *lk["fuse"], out=spatial[:, :512])
+        # rFFT(256) of the three lowered vectors as real DFT mat-vecs, then |.| and angle
+        mags = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        phas = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        for i in range(3):
+            v = cat[:, 256 * i:256 * (i + 1)]
+            re = ops.small_linear(v, lk["dft_re"])
+            im = ops.small_linear(v, lk["dft_im"])
+            m_, p_ = ops.polar(re, im, 0)
+            mags[:, i], phas[:, i] = m_, p_
+        mags[:, 3], phas[:, 3] = lk["tmag"], lk["tpha"]
+        mag = ops.small_linear(mags[:, :, :128].reshape(B, 512), *lk["mag"])
+        pha = ops.small_linear(phas[:, :, :128].reshape(B, 512), *lk["pha"])
+        mag0 = ops.small_linear(mags[:, :, 128].contiguous(), *lk["mag0"])
+        pha0 = ops.small_linear(phas[:, :, 128].contiguous(), *lk["pha0"])
+        re, im = ops.polar(torch.cat([mag, mag0], 1), torch.cat([pha, pha0], 1), 1)        # [B, 257] each
+        ops.small_linear(torch.cat([re, im], 1), lk["idft"], out=spatial[:, 512:])          # irFFT -> 512 samples
+        h = ops.small_linear(spatial, *lk["sf0"], act_out=SL_LEAKY)
+        return ops.small_linear(h, *lk["sf2"]).reshape(B, 1, 1024)
+
+    @torch.no_grad()
+    def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states,
+                domain_features, flow_features,
+                down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
+                mid_block_additional_residual: Optional[torch.Tensor] = None, return_dict: bool = True,
+                added_time_ids: torch.Tensor = None):
+        rows, g = self.forward_rows(sample, timestep, encoder_hidden_states, domain_features, flow_features,
+                                    down_block_additional_residuals=down_block_additional_residuals,
+                                    mid_block_additional_residual=mid_block_additional_residual,
+                                    added_time_ids=added_time_ids)
+        out = ops.unpack_output(rows, g.B, g.F, self.config.out_channels, g.H, g.W)
+        if out.dtype != sample.dtype:
+            out = out.to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return UNetSpatioTemporalConditionOutput(sample=out)
+
+
+# --------------------------------------------------------------------------------------------------- ControlNet
+class ControlNetConditioningEmbeddingSVD(M.Container):
+    def __init__(self, conditioning_embedding_channels, conditioning_channels=3,
+                 block_out_channels=(16, 32, 96, 256)):
+        super().__init__()
+        self.conv_in = M.Conv2d(conditioning_channels, block_out_channels[0], 3, padding=1)
+        self.blocks = nn.ModuleList()
+        for i in range(len(block_out_channels) - 1):
+            cin, cout = block_out_channels[i], block_out_channels[i + 1]
+            self.blocks.append(M.Conv2d(cin, cin, 3, padding=1))
+            self.blocks.append(M.Conv2d(cin, cout, 3, padding=1, stride=2))
+        self.conv_out = M.Conv2d(block_out_channels[-1], conditioning_embedding_channels, 3, padding=1)
+        nn.init.zeros_(self.conv_out.weight)
+        nn.init.zeros_(self.conv_out.bias)
+
+
+def _zero_conv(c):
+    m = M.Conv2d(c, c, 1)
+    nn.init.zeros_(m.weight)
+    nn.init.zeros_(m.bias)
+    return m
+
+
+class ControlNetSDVModel(_Base):
+    def __init__(self, sample_size=None, in_channels=8, out_channels=4,
+                 down_block_types=SVD_XT_CONFIG["down_block_types"], block_out_channels=(320, 640, 1280, 1280),
+                 addition_time_embed_dim=256, projection_class_embeddings_input_dim=768, layers_per_block=2,
+                 cross_attention_dim=1024, transformer_layers_per_block=1, num_attention_heads=(5, 10, 10, 20),
+                 num_frames=25, conditioning_channels=3, conditioning_embedding_out_channels=(16, 32, 96, 256),
+                 time_context_order="hw_major_0272"):
+        super().__init__()
+        n = len(down_block_types)
+        if len(block_out_channels) != n:
+            raise ValueError(f"Must provide the same number of `block_out_channels` as `down_block_types`. "
+                             f"`block_out_channels`: {block_out_channels}. `down_block_types`: {down_block_types}.")
+        self.config = SimpleNamespace(
+            sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+            down_block_types=tuple(down_block_types), block_out_channels=tuple(block_out_channels),
+            addition_time_embed_dim=addition_time_embed_dim,
+            projection_class_embeddings_input_dim=projection_class_embeddings_input_dim,
+            layers_per_block=layers_per_block, cross_attention_dim=cross_attention_dim,
+            transformer_layers_per_block=transformer_layers_per_block, num_attention_heads=num_attention_heads,
+            num_frames=num_frames, conditioning_channels=conditioning_channels,
+            conditioning_embedding_out_channels=tuple(conditioning_embedding_out_channels),
+            time_context_order=time_context_order)
+        heads, xdim, lpb, tlpb, temb = self._build_encoder(
+            in_channels, down_block_types, block_out_channels, layers_per_block, transformer_layers_per_block,
+            num_attention_heads, cross_attention_dim, addition_time_embed_dim, projection_class_embeddings_input_dim)
+        self.controlnet_cond_embedding = ControlNetConditioningEmbeddingSVD(
+            block_out_channels[0], conditioning_channels, tuple(conditioning_embedding_out_channels))
+        self.controlnet_down_blocks = nn.ModuleList([_zero_conv(block_out_channels[0])])
+        for i in range(n):
+            last = i == n - 1
+            for _ in range(lpb[i] + (0 if last else 1)):
+                self.controlnet_down_blocks.append(_zero_conv(block_out_channels[i]))
+        self.controlnet_mid_block = _zero_conv(block_out_channels[-1])
+        self.mid_block = M.UNetMidBlockSpatioTemporal(block_out_channels[-1], temb, 1, tlpb[-1], heads[-1], xdim[-1])
+        self._packed = None
+        self._cn = None
+
+    def invalidate(self):
+        super().invalidate()
+        self._cn = None
+
+    @classmethod
+    def from_unet(cls, unet, controlnet_conditioning_channel_order: str = "rgb",
+                  conditioning_embedding_out_channels=(16, 32, 96, 256), load_weights_from_unet: bool = True,
+                  conditioning_channels: int = 3):
+        c = unet.config
+        net = cls(in_channels=c.in_channels, down_block_types=c.down_block_types,
+                  block_out_channels=c.block_out_channels, addition_time_embed_dim=c.addition_time_embed_dim,
+                  transformer_layers_per_block=c.transformer_layers_per_block,
+                  cross_attention_dim=c.cross_attention_dim, num_attention_heads=c.num_attention_heads,
+                  num_frames=c.num_frames, sample_size=c.sample_size, layers_per_block=c.layers_per_block,
+                  projection_class_embeddings_input_dim=c.projection_class_embeddings_input_dim,
+                  conditioning_channels=conditioning_channels,
+                  conditioning_embedding_out_channels=conditioning_embedding_out_channels,
+                  time_context_order=getattr(c, "time_context_order", "hw_major_0272"))
+        if load_weights_from_unet:
+            for name in ("conv_in", "time_embedding", "add_embedding", "down_blocks", "mid_block"):
+                getattr(net, name).load_state_dict(getattr(unet, name).state_dict())
+        return net.to(unet.device)
+
+    def _cn_pack(self):
+        if getattr(self, "_cn", None) is None:
+            ce = self.controlnet_cond_embedding
+            convs = [ce.conv_in] + list(ce.blocks) + [ce.conv_out]
+            packed = []
+            cin_pad = 64
+            for cv in convs:
+                cout = cv.out_channels
+                cout_pad = (cout + 15) // 16 * 16
+                w, b = _conv3x3_weight(cv, cin_pad=cin_pad, cout_pad=cout_pad)
+                packed.append((w, b, cv.stride[0], cout_pad))
+                cin_pad = cout_pad
+            zero = [(cv.weight.detach().reshape(cv.out_channels, cv.in_channels).to(bf16).contiguous(), _f32(cv.bias))
+                    for cv in list(self.controlnet_down_blocks) + [self.controlnet_mid_block]]
+            self._cn = (packed, zero)
+        return self._cn
+
+    @torch.no_grad()
+    def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
+                       added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor] = None,
+                       conditioning_scale: float = 1.0):
+        """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
+        pk = self.packed()
+        convs, zero = self._cn_pack()
+        emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
+        cond = Conditioning(emb, encoder_hidden_states.to(torch.float32).contiguous())
+        stem_add = None
+        if controlnet_cond is not None:
+            if controlnet_cond.ndim != 5:
+                raise ValueError("controlnet_cond must be [batch, frames, channels, height, width]")
+            b_, f_, cc, hc, wc = controlnet_cond.shape
+            e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=64)
+            hh, ww = hc, wc
+            for i, (w, b, stride, _) in enumerate(convs):
+                last = i == len(convs) - 1
+                e = ops.gemm(e, w, mode=A_CONV3X3, conv=(b_ * f_, hh, ww, stride), bias=b,
+                             act=0 if last else ACT_SILU)
+                if stride == 2:
+                    hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+            if (hh, ww) != (g.H, g.W) or b_ * f_ != g.BF:
+                raise ValueError("controlnet_cond resolution must be 8x the latent resolution")
+            stem_add = e
+        x, skips, geoms, gm = pk.encoder(x, g, cond, stem_add=stem_add)
+        s = float(conditioning_scale)
+        down = [ChannelsLast(ops.gemm(sk, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
+                for sk, (w, b), gs in zip(skips, zero[:-1], geoms)]
+        mid = ChannelsLast(ops.gemm(x, zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
+        return down, mid
+
+    @torch.no_grad()
+    def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
+                encoder_hidden_states: torch.Tensor, added_time_ids: torch.Tensor,
+                controlnet_cond: torch.FloatTensor = None, image_only_indicator: Optional[torch.Tensor] = None,
+                return_dict: bool = True, guess_mode: bool = False, conditioning_scale: float = 1.0,
+                output_layout: str = "nchw"):
+        """``image_only_indicator`` and ``guess_mode`` are accepted and ignored like the reference (quirk D7).
+        ``output_layout="nhwc"`` returns ``ChannelsLast`` residuals for the UNet's fast path."""
+        x, g = self._pack_sample(sample, self.packed())
+        down, mid = self.forward_packed(x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond,
+                                        conditioning_scale)
+        if output_layout == "nchw":
+            down = [d.to_nchw().to(sample.dtype) for d in down]
+            mid = mid.to_nchw().to(sample.dtype)
+        elif output_layout != "nhwc":
+            raise ValueError("output_layout must be 'nchw' or 'nhwc'")
+        if not return_dict:
+            return (down, mid)
+        return ControlNetOutput(down_block_res_samples=down, mid_block_res_sample=mid)
