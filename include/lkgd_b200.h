@@ -91,7 +91,7 @@ typedef struct lkgd_gemm_args {
   int32_t rv_mode, rv_HW, rv_F, rv_B;
   int32_t act;        /* LKGD_ACT_*                                           */
   float s0;
-  const void* res1;   /* bf16 [M, ldr1] or NULL                               */
+  const void* res1;   /* bf16 (or fp32, see res1_f32) [M, ldr1] or NULL      */
   int32_t ldr1;
   float s1;
   const void* res2;
@@ -101,6 +101,8 @@ typedef struct lkgd_gemm_args {
   int32_t ldo;
   int32_t out_f32;    /* 1: fp32 output                                       */
   int32_t n_store;    /* store only columns < n_store (0 = all)               */
+  int32_t res1_f32;   /* 1: res1 is fp32 (the residual stream is kept in fp32) */
+  int32_t res2_f32;
 } lkgd_gemm_args;
 
 LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);
@@ -114,20 +116,22 @@ LKGD_API int lkgd_gemm_simt_check(const lkgd_gemm_args* args, void* stream);
  * (5-D GroupNorm, statistics ACROSS frames): NS = B, R = F*H*W.  Output bf16 [NS, R, C1+C2].
  * Replaces nn.GroupNorm + SiLU (diffusers resnet.py ResnetBlock2D / TemporalResnetBlock; the reference's
  * conv_norm_out + conv_act, ...controlnet.py:237-238,498-499; TransformerSpatioTemporalModel.norm).
+ * x_f32 = 1: the sources are fp32 (the residual stream is kept in fp32); the output is always bf16 (a GEMM operand).
  * workspace: lkgd_groupnorm_workspace(NS, C) bytes.
  */
 LKGD_API size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C);
 LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R, int32_t groups,
-                   const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* workspace,
-                   size_t ws_bytes, void* stream);
+                   const float* gamma, const float* beta, float eps, int32_t silu, int32_t x_f32, void* out,
+                   void* workspace, size_t ws_bytes, void* stream);
 
 /* LayerNorm over the last axis of a [M, C] bf16 matrix (C <= 2048, C % 8 == 0) with optional fused
  *   s = x + addvec[g(m)]   (fp32 addvec [G, C]; frame positional embedding or KV-length-1 cross-attention term)
- * sum_out (bf16, may alias x, may be NULL) receives s; out receives LN(s)*gamma+beta.
+ * sum_out (same dtype as x: bf16, or fp32 when x_f32 = 1; may alias x, may be NULL) receives s; out (bf16) receives
+ * LN(s)*gamma+beta.
  * Replaces nn.LayerNorm norm1/norm2/norm3/norm_in (patch/patch.py:415-416,529-530,555-556,599,610,664,670). */
 LKGD_API int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
-                   const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B, void* sum_out,
-                   void* out, void* stream);
+                   const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B, int32_t x_f32,
+                   void* sum_out, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Spatial self-attention (and general cross-attention), flash-style on tcgen05: per (image, head)
@@ -182,13 +186,20 @@ LKGD_API int lkgd_unpack_output(const float* src, int32_t ld, float* dst, int32_
 /* generic NCHW fp32 [N, C, H, W] <-> NHWC bf16 [N, H, W, C] converters (ControlNet residual exchange). */
 LKGD_API int lkgd_nchw_to_nhwc(const float* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
 LKGD_API int lkgd_nhwc_to_nchw(const void* src, float* dst, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
-/* nearest 2x upsample, channels-last bf16 [N,H,W,C] -> [N,2H,2W,C] (Upsample2D before its conv). */
-LKGD_API int lkgd_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
-/* channel concat of two channels-last matrices: dst[m] = [a[m, 0:Ca] | b[m, 0:Cb]]. */
-LKGD_API int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t M, void* stream);
-/* y[i] = alpha * x[i] + beta * y[i] on bf16 (ControlNet residual injection with the F6 multipliers:
- * ...controlnet.py:453-462,472-473). n % 8 == 0. */
-LKGD_API int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64_t n, void* stream);
+/* nearest 2x upsample, channels-last [N,H,W,C] (bf16, or fp32 when src_f32) -> bf16 [N,2H,2W,C]
+ * (Upsample2D before its conv; the fp32 residual stream is narrowed to the conv's bf16 operand on the way). */
+LKGD_API int lkgd_upsample2x(const void* src, int32_t src_f32, void* dst, int32_t N, int32_t H, int32_t W, int32_t C,
+                    void* stream);
+/* fp32 -> bf16 narrowing of a residual-stream tensor that a GEMM reads raw (shortcut / downsampler convs). */
+LKGD_API int lkgd_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* channel concat of two channels-last matrices (bf16, or fp32 when src_f32) into bf16:
+ * dst[m] = [a[m, 0:Ca] | b[m, 0:Cb]]. */
+LKGD_API int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, int32_t src_f32, void* dst,
+                         int64_t M, void* stream);
+/* y[i] = alpha * x[i] + beta * y[i]; x / y each bf16 or fp32 (ControlNet residual injection with the F6
+ * multipliers: ...controlnet.py:453-462,472-473). n % 8 == 0. */
+LKGD_API int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int32_t y_f32, float beta, int64_t n,
+               void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Fused classifier-free-guidance combine + Euler (Karras sigmas, v-prediction) step, fp32.

@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("bias", vp), ("rowvec", vp), ("rv_mode", i32), ("rv_HW", i32), ("rv_F", i32), ("rv_B", i32),
         ("act", i32), ("s0", f32), ("res1", vp), ("ldr1", i32), ("s1", f32),
         ("res2", vp), ("ldr2", i32), ("s2", f32),
-        ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32),
+        ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32), ("res1_f32", i32), ("res2_f32", i32),
     ]
 
 
@@ -41,8 +41,8 @@ SIGNATURES = {
     "lkgd_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "lkgd_gemm_simt_check": (i32, [C.POINTER(GemmArgs), vp]),
     "lkgd_groupnorm_workspace": (sz, [i32, i32]),
-    "lkgd_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, sz, vp]),
-    "lkgd_layernorm": (i32, [vp, i32, i32, vp, vp, f32, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "lkgd_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, sz, vp]),
+    "lkgd_layernorm": (i32, [vp, i32, i32, vp, vp, f32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "lkgd_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_attention_simt_check": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_attention_temporal": (i32, [vp, vp, i32, i32, i32, i32, i32, f32, vp]),
@@ -55,9 +55,10 @@ SIGNATURES = {
     "lkgd_unpack_output": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "lkgd_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "lkgd_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, vp]),
-    "lkgd_upsample2x": (i32, [vp, vp, i32, i32, i32, i32, vp]),
-    "lkgd_concat_channels": (i32, [vp, i32, vp, i32, vp, i64, vp]),
-    "lkgd_axpby": (i32, [vp, f32, vp, f32, i64, vp]),
+    "lkgd_upsample2x": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "lkgd_cast_bf16": (i32, [vp, vp, i64, vp]),
+    "lkgd_concat_channels": (i32, [vp, i32, vp, i32, i32, vp, i64, vp]),
+    "lkgd_axpby": (i32, [vp, i32, f32, vp, i32, f32, i64, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
 }
 
@@ -75,7 +76,7 @@ class Profiler:
 PROF = Profiler()
 _TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
           "lkgd_small_linear", "lkgd_timestep_embedding", "lkgd_pack_input", "lkgd_unpack_output",
-          "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_axpy_f32",
+          "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_cast_bf16", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_axpy_f32",
           "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32"}
 
 

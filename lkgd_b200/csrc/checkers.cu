@@ -76,8 +76,12 @@ __global__ void gemm_check_kernel(const lkgd_gemm_args a) {
   if (a.rowvec) v += a.rowvec[(size_t)chk_rowvec_index(a.rv_mode, m, max(a.rv_HW, 1), max(a.rv_F, 1), max(a.rv_B, 1)) * n_cols + n_out];
   if (a.act == LKGD_ACT_SILU) v = silu_f(v);
   v *= a.s0;
-  if (a.res1) v += a.s1 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res1)[m * a.ldr1 + n_out]);
-  if (a.res2) v += a.s2 * __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res2)[m * a.ldr2 + n_out]);
+  if (a.res1)
+    v += a.s1 * (a.res1_f32 ? reinterpret_cast<const float*>(a.res1)[m * a.ldr1 + n_out]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res1)[m * a.ldr1 + n_out]));
+  if (a.res2)
+    v += a.s2 * (a.res2_f32 ? reinterpret_cast<const float*>(a.res2)[m * a.ldr2 + n_out]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res2)[m * a.ldr2 + n_out]));
   if (a.out_f32) reinterpret_cast<float*>(a.out)[m * a.ldo + n_out] = v;
   else reinterpret_cast<__nv_bfloat16*>(a.out)[m * a.ldo + n_out] = __float2bfloat16(v);
 }

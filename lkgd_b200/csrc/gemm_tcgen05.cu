@@ -35,9 +35,9 @@ struct GemmParams {
   int rv_mode, rv_HW, rv_F, rv_B;
   int act;
   float s0, s1, s2;
-  const __nv_bfloat16* res1;
-  const __nv_bfloat16* res2;
-  int ldr1, ldr2;
+  const void* res1;
+  const void* res2;
+  int ldr1, ldr2, res1_f32, res2_f32;
   void* out;
   int ldo, out_f32, n_store;
 };
@@ -84,6 +84,38 @@ __device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoo
   } else {
     int pp = t.c1 + r;
     return pp < p.HW ? ((long long)(t.c3 * p.F + t.c2)) * p.HW + pp : -1;
+  }
+}
+
+// v[0..15] += scale * res[m, n_out .. n_out+15]  (bf16 or fp32 residual, vectorised when the chunk is full)
+__device__ __forceinline__ void add_residual(float (&v)[16], const void* res, int f32, int ld, long long m, int n_out,
+                                             float scale, bool full16, int n_store) {
+  if (f32) {
+    const float* rp = reinterpret_cast<const float*>(res) + (size_t)m * ld + n_out;
+    if (full16 && (ld & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
+        v[4 * j] += scale * q.x; v[4 * j + 1] += scale * q.y; v[4 * j + 2] += scale * q.z; v[4 * j + 3] += scale * q.w;
+      }
+    } else {
+      for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += scale * rp[j];
+    }
+  } else {
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(res) + (size_t)m * ld + n_out;
+    if (full16 && (ld & 7) == 0) {
+      float f[8];
+      uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+      unpack_bf16x8(q0, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += scale * f[j];
+      unpack_bf16x8(q1, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 + j] += scale * f[j];
+    } else {
+      for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += scale * __bfloat162float(rp[j]);
+    }
   }
 }
 
@@ -227,38 +259,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] *= p.s0;
         }
-        if (p.res1 != nullptr) {
-          const __nv_bfloat16* rp = p.res1 + (size_t)m * p.ldr1 + n_out;
-          if (full16 && (p.ldr1 & 7) == 0) {
-            float f[8];
-            uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-            uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            unpack_bf16x8(q0, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += p.s1 * f[j];
-            unpack_bf16x8(q1, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[8 + j] += p.s1 * f[j];
-          } else {
-            for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += p.s1 * __bfloat162float(rp[j]);
-          }
-        }
-        if (p.res2 != nullptr) {
-          const __nv_bfloat16* rp = p.res2 + (size_t)m * p.ldr2 + n_out;
-          if (full16 && (p.ldr2 & 7) == 0) {
-            float f[8];
-            uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-            uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            unpack_bf16x8(q0, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += p.s2 * f[j];
-            unpack_bf16x8(q1, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[8 + j] += p.s2 * f[j];
-          } else {
-            for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += p.s2 * __bfloat162float(rp[j]);
-          }
-        }
+        if (p.res1 != nullptr) add_residual(v, p.res1, p.res1_f32, p.ldr1, m, n_out, p.s1, full16, n_store);
+        if (p.res2 != nullptr) add_residual(v, p.res2, p.res2_f32, p.ldr2, m, n_out, p.s2, full16, n_store);
         if (p.out_f32) {
           float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n_out;
           if (full16 && (p.ldo & 3) == 0) {
@@ -418,8 +420,8 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
   p.rv_mode = a->rowvec ? a->rv_mode : LKGD_RV_NONE;
   p.rv_HW = a->rv_HW > 0 ? a->rv_HW : 1; p.rv_F = a->rv_F > 0 ? a->rv_F : 1; p.rv_B = a->rv_B > 0 ? a->rv_B : 1;
   p.act = a->act; p.s0 = a->s0; p.s1 = a->s1; p.s2 = a->s2;
-  p.res1 = reinterpret_cast<const __nv_bfloat16*>(a->res1); p.ldr1 = a->ldr1;
-  p.res2 = reinterpret_cast<const __nv_bfloat16*>(a->res2); p.ldr2 = a->ldr2;
+  p.res1 = a->res1; p.ldr1 = a->ldr1; p.res1_f32 = a->res1_f32;
+  p.res2 = a->res2; p.ldr2 = a->ldr2; p.res2_f32 = a->res2_f32;
   p.out = a->out; p.ldo = a->ldo; p.out_f32 = a->out_f32; p.n_store = a->n_store;
   return LKGD_OK;
 }

@@ -117,8 +117,17 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
-__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W,
-                                  int vecs) {
+__device__ __forceinline__ uint4 load8_as_bf16(const void* base, long long vec_index, int f32) {
+  if (f32) {
+    const float4* p = reinterpret_cast<const float4*>(base) + 2 * vec_index;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+  return __ldg(reinterpret_cast<const uint4*>(base) + vec_index);
+}
+
+__global__ void upsample2x_kernel(const void* __restrict__ src, int src_f32, uint4* __restrict__ dst, int N, int H,
+                                  int W, int vecs) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over output vectors
   const long long total = (long long)N * 4 * H * W * vecs;
   if (idx >= total) return;
@@ -127,30 +136,51 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restri
   const int wo = (int)(pix % (2 * W));
   const int ho = (int)((pix / (2 * W)) % (2 * H));
   const int n = (int)(pix / ((long long)4 * H * W));
-  dst[idx] = __ldg(src + (((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * vecs + v);
+  dst[idx] = load8_as_bf16(src, (((long long)n * H + (ho >> 1)) * W + (wo >> 1)) * vecs + v, src_f32);
 }
 
-__global__ void concat_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb,
+__global__ void concat_kernel(const void* __restrict__ a, int va, const void* __restrict__ b, int vb, int src_f32,
                               uint4* __restrict__ dst, long long M) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vt = va + vb;
   if (idx >= M * vt) return;
   const long long m = idx / vt;
   const int v = (int)(idx % vt);
-  dst[idx] = v < va ? __ldg(a + m * va + v) : __ldg(b + m * vb + (v - va));
+  dst[idx] = v < va ? load8_as_bf16(a, m * va + v, src_f32) : load8_as_bf16(b, m * vb + (v - va), src_f32);
 }
 
-__global__ void axpby_kernel(const uint4* __restrict__ x, float alpha, uint4* __restrict__ y, float beta,
-                             long long nvec) {
+__device__ __forceinline__ void load8_f(const void* base, long long vec_index, int f32, float (&f)[8]) {
+  if (f32) {
+    const float4* p = reinterpret_cast<const float4*>(base) + 2 * vec_index;
+    const float4 a = p[0], b = p[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack_bf16x8(reinterpret_cast<const uint4*>(base)[vec_index], f);
+  }
+}
+
+__global__ void axpby_kernel(const void* __restrict__ x, int x_f32, float alpha, void* __restrict__ y, int y_f32,
+                             float beta, long long nvec) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nvec) return;
   float fx[8], fy[8];
-  unpack_bf16x8(__ldg(x + idx), fx);
-  unpack_bf16x8(y[idx], fy);
+  load8_f(x, idx, x_f32, fx);
+  load8_f(y, idx, y_f32, fy);
 #pragma unroll
   for (int i = 0; i < 8; ++i) fy[i] = alpha * fx[i] + beta * fy[i];
-  y[idx] = make_uint4(pack_bf16x2(fy[0], fy[1]), pack_bf16x2(fy[2], fy[3]), pack_bf16x2(fy[4], fy[5]),
-                      pack_bf16x2(fy[6], fy[7]));
+  if (y_f32) {
+    float4* p = reinterpret_cast<float4*>(y) + 2 * idx;
+    p[0] = make_float4(fy[0], fy[1], fy[2], fy[3]);
+    p[1] = make_float4(fy[4], fy[5], fy[6], fy[7]);
+  } else {
+    reinterpret_cast<uint4*>(y)[idx] = make_uint4(pack_bf16x2(fy[0], fy[1]), pack_bf16x2(fy[2], fy[3]),
+                                                  pack_bf16x2(fy[4], fy[5]), pack_bf16x2(fy[6], fy[7]));
+  }
+}
+
+__global__ void cast_bf16_kernel(const void* __restrict__ src, uint4* __restrict__ dst, long long nvec) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < nvec) dst[idx] = load8_as_bf16(src, idx, 1);
 }
 
 // thread = one (s, f, c, p) element of the fp32 latent; pred is channels-last [2S*F*HW, ld]
@@ -198,7 +228,7 @@ __global__ void polar_kernel(const float* __restrict__ a, const float* __restric
   if (idx >= n) return;
   if (mode == 0) {
     o0[idx] = hypotf(a[idx], b[idx]);
-    o1[idx] = atan2f(b[idx], a[idx]);
+    o1[idx] = atan2f(b[idx] + 0.0f, a[idx]);   // -0 + 0 = +0: a zero imaginary part gives angle 0 / +pi like torch.angle
   } else {
     o0[idx] = a[idx] * cosf(b[idx]);
     o1[idx] = a[idx] * sinf(b[idx]);
@@ -261,31 +291,38 @@ extern "C" int lkgd_nhwc_to_nchw(const void* src, float* dst, int32_t N, int32_t
   return launch_epilogue();
 }
 
-extern "C" int lkgd_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+extern "C" int lkgd_upsample2x(const void* src, int32_t src_f32, void* dst, int32_t N, int32_t H, int32_t W,
+                               int32_t C, void* stream) {
   if (C % 8 || N <= 0) return LKGD_ESHAPE;
   if (!aligned16(src) || !aligned16(dst)) return LKGD_EALIGN;
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src),
-                                                                   reinterpret_cast<uint4*>(dst), N, H, W, C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src, src_f32, reinterpret_cast<uint4*>(dst), N,
+                                                                   H, W, C / 8);
   return launch_epilogue();
 }
 
-extern "C" int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t M,
-                                    void* stream) {
+extern "C" int lkgd_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0 || n % 8) return LKGD_ESHAPE;
+  if (!aligned16(src) || !aligned16(dst)) return LKGD_EALIGN;
+  cast_bf16_kernel<<<blocks_for(n / 8, 256), 256, 0, ST(stream)>>>(src, reinterpret_cast<uint4*>(dst), n / 8);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, int32_t src_f32, void* dst,
+                                    int64_t M, void* stream) {
   if (Ca % 8 || Cb % 8 || M <= 0) return LKGD_ESHAPE;
   if (!aligned16(a) || !aligned16(b) || !aligned16(dst)) return LKGD_EALIGN;
   const long long total = (long long)M * ((Ca + Cb) / 8);
-  concat_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(a), Ca / 8,
-                                                               reinterpret_cast<const uint4*>(b), Cb / 8,
+  concat_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(a, Ca / 8, b, Cb / 8, src_f32,
                                                                reinterpret_cast<uint4*>(dst), M);
   return launch_epilogue();
 }
 
-extern "C" int lkgd_axpby(const void* x, float alpha, void* y, float beta, int64_t n, void* stream) {
+extern "C" int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int32_t y_f32, float beta, int64_t n,
+                          void* stream) {
   if (n <= 0 || n % 8) return LKGD_ESHAPE;
   if (!aligned16(x) || !aligned16(y)) return LKGD_EALIGN;
-  axpby_kernel<<<blocks_for(n / 8, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(x), alpha,
-                                                              reinterpret_cast<uint4*>(y), beta, n / 8);
+  axpby_kernel<<<blocks_for(n / 8, 256), 256, 0, ST(stream)>>>(x, x_f32, alpha, y, y_f32, beta, n / 8);
   return launch_epilogue();
 }
 

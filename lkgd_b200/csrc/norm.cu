@@ -8,17 +8,25 @@ namespace lkgd {
 
 // thread layout shared by both GroupNorm kernels: blockDim.x = vecs * rows_par, thread -> (row lane, 8-ch vector)
 struct GnGeom {
-  int C1, C2, C, vecs, rows_par, R, rows_per_cta;
+  int C1, C2, C, vecs, rows_par, R, rows_per_cta, x_f32;
 };
 
-__device__ __forceinline__ uint4 gn_load(const __nv_bfloat16* x1, const __nv_bfloat16* x2, const GnGeom& g,
-                                         long long row, int v) {
+// 8 consecutive channels of (row, vector v) from the first or the second (concatenated) source; bf16 or fp32 input
+__device__ __forceinline__ void gn_load(const void* x1, const void* x2, const GnGeom& g, long long row, int v,
+                                        float (&f)[8]) {
   const int c = v * 8;
-  if (c < g.C1) return __ldg(reinterpret_cast<const uint4*>(x1 + row * g.C1 + c));
-  return __ldg(reinterpret_cast<const uint4*>(x2 + row * g.C2 + (c - g.C1)));
+  const void* base = c < g.C1 ? x1 : x2;
+  const long long off = c < g.C1 ? row * g.C1 + c : row * g.C2 + (c - g.C1);
+  if (g.x_f32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off)), f);
+  }
 }
 
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, GnGeom g,
+__global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
                                 double* __restrict__ sums /* [NS][C][2] */) {
   extern __shared__ float sh[];  // [rows_par][vecs][16]
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
@@ -30,7 +38,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   for (int r = r0 + rl; r < r1; r += g.rows_par) {
     float f[8];
-    unpack_bf16x8(gn_load(x1, x2, g, (long long)ns * g.R + r, v), f);
+    gn_load(x1, x2, g, (long long)ns * g.R + r, v, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
   }
@@ -48,7 +56,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   }
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, GnGeom g,
+__global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
                                 const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int groups, int silu,
                                 __nv_bfloat16* __restrict__ out) {
@@ -89,7 +97,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   for (int r = r0 + rl; r < r1; r += g.rows_par) {
     const long long row = (long long)ns * g.R + r;
     float f[8];
-    unpack_bf16x8(gn_load(x1, x2, g, row, v), f);
+    gn_load(x1, x2, g, row, v, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(f[i], sc[i], sf[i]);
@@ -114,36 +122,53 @@ __device__ __forceinline__ int ln_rowvec_index(int mode, long long m, int HW, in
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C,
+template <int NV, bool XF32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, int M, int C,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         const float* __restrict__ addvec, int rv_mode, int rv_HW,
-                                                        int rv_F, int rv_B, __nv_bfloat16* sum_out,
+                                                        int rv_F, int rv_B, void* sum_out_v,
                                                         __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   float f[NV][8];
-  const __nv_bfloat16* xr = x + row * C;
+  const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(xv) + row * C;   // XF32 == false
+  const float* xr32 = reinterpret_cast<const float*>(xv) + row * C;                 // XF32 == true
   const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * C : nullptr;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int v = lane + 32 * j;
     if (v < nvec) {
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(xr + v * 8), f[j]);
+      if (XF32) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xr32 + v * 8);
+        const float4 x1 = *(reinterpret_cast<const float4*>(xr32 + v * 8) + 1);
+        f[j][0] = x0.x; f[j][1] = x0.y; f[j][2] = x0.z; f[j][3] = x0.w;
+        f[j][4] = x1.x; f[j][5] = x1.y; f[j][6] = x1.z; f[j][7] = x1.w;
+      } else {
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(xr + v * 8), f[j]);
+      }
       if (av) {
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + v * 8));
         const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + v * 8) + 1);
         f[j][0] += a0.x; f[j][1] += a0.y; f[j][2] += a0.z; f[j][3] += a0.w;
         f[j][4] += a1.x; f[j][5] += a1.y; f[j][6] += a1.z; f[j][7] += a1.w;
-        // the residual stream is bf16: normalise what is actually stored
-        uint4 o = make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]),
-                             pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
-        if (sum_out) *reinterpret_cast<uint4*>(sum_out + row * C + v * 8) = o;
-        unpack_bf16x8(o, f[j]);
+        if (XF32) {
+          if (sum_out_v) {
+            float* so = reinterpret_cast<float*>(sum_out_v) + row * C + v * 8;
+            *reinterpret_cast<float4*>(so) = make_float4(f[j][0], f[j][1], f[j][2], f[j][3]);
+            *(reinterpret_cast<float4*>(so) + 1) = make_float4(f[j][4], f[j][5], f[j][6], f[j][7]);
+          }
+        } else {
+          // bf16 residual stream: normalise what is actually stored
+          uint4 o = make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]),
+                               pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
+          if (sum_out_v)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(sum_out_v) + row * C + v * 8) = o;
+          unpack_bf16x8(o, f[j]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += f[j][i];
@@ -183,9 +208,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
-static GnGeom gn_geom(int C1, int C2, int R) {
+static GnGeom gn_geom(int C1, int C2, int R, int x_f32) {
   GnGeom g;
-  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R;
+  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
   g.rows_par = 512 / g.vecs;
   if (g.rows_par < 1) g.rows_par = 1;
   if (g.rows_par > R) g.rows_par = R;
@@ -202,14 +227,14 @@ extern "C" size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C) { return (size
 
 extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R,
                               int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
-                              void* out, void* workspace, size_t ws_bytes, void* stream) {
+                              int32_t x_f32, void* out, void* workspace, size_t ws_bytes, void* stream) {
   if (x2 == nullptr) C2 = 0;
   const int C = C1 + C2;
   if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
   if (!aligned16(x1) || !aligned16(out) || (x2 && !aligned16(x2))) return LKGD_EALIGN;
   if (ws_bytes < lkgd_groupnorm_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  GnGeom g = gn_geom(C1, C2, R);
+  GnGeom g = gn_geom(C1, C2, R, x_f32);
   cudaError_t e = cudaMemsetAsync(workspace, 0, lkgd_groupnorm_workspace(NS, C), st);
   if (e != cudaSuccess) return set_cuda_error(e);
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
@@ -220,14 +245,11 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  gn_stats_kernel<<<grid, threads, sh1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1),
-                                              reinterpret_cast<const __nv_bfloat16*>(x2), g,
-                                              reinterpret_cast<double*>(workspace));
+  gn_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, g, reinterpret_cast<double*>(workspace));
   int rc = launch_epilogue();
   if (rc) return rc;
   const size_t sh2 = (size_t)(2 * C + 2 * groups) * sizeof(float);
-  gn_apply_kernel<<<grid, threads, sh2, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1),
-                                              reinterpret_cast<const __nv_bfloat16*>(x2), g,
+  gn_apply_kernel<<<grid, threads, sh2, st>>>(x1, x2, g,
                                               reinterpret_cast<const double*>(workspace), gamma, beta, eps, groups,
                                               silu, reinterpret_cast<__nv_bfloat16*>(out));
   return launch_epilogue();
@@ -235,7 +257,7 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
 
 extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
                               const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B,
-                              void* sum_out, void* out, void* stream) {
+                              int32_t x_f32, void* sum_out, void* out, void* stream) {
   if (M <= 0 || C <= 0 || C % 8 || C > LN_MAXV * 256) return LKGD_ESHAPE;
   if (!aligned16(x) || !aligned16(out) || (sum_out && !aligned16(sum_out)) || (addvec && !aligned16(addvec)) ||
       !aligned16(gamma) || !aligned16(beta))
@@ -248,10 +270,14 @@ extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* 
   if (rv_F <= 0) rv_F = 1;
   if (rv_B <= 0) rv_B = 1;
 #define LN_LAUNCH(NV)                                                                                              \
-  layernorm_kernel<NV><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, gamma, beta, eps,    \
-                                             addvec, rv_mode, rv_HW, rv_F, rv_B,                                   \
-                                             reinterpret_cast<__nv_bfloat16*>(sum_out),                            \
-                                             reinterpret_cast<__nv_bfloat16*>(out))
+  do {                                                                                                             \
+    if (x_f32)                                                                                                     \
+      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, rv_mode, rv_HW, rv_F,    \
+                                                       rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));      \
+    else                                                                                                           \
+      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, rv_mode, rv_HW, rv_F,   \
+                                                        rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));     \
+  } while (0)
   switch (nv) {
     case 1: LN_LAUNCH(1); break;
     case 2: LN_LAUNCH(2); break;

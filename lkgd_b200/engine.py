@@ -1,6 +1,9 @@
 """Block-graph executor of the SVD / LKGD spatio-temporal UNet on the lkgd_b200 CUDA kernels.
 
-Resident activation layout: channels-last bf16, one row per (batch, frame, pixel): ``[B*F*H*W, C]``.  Spatial
+Resident activation layout: channels-last, one row per (batch, frame, pixel): ``[B*F*H*W, C]``.  The RESIDUAL
+STREAM (block inputs / outputs, skip tensors, the running hidden state inside a transformer) is kept in fp32 - with
+~190 sequential residual updates per forward, rounding it to bf16 at every add costs ~1.5e-2 rel-L2 by itself, above
+the 1e-2 parity bar; everything a tensor-core GEMM reads (norm outputs, attention outputs, GEGLU products) is bf16.  Spatial
 ops see it as [B*F, HW, C]; temporal ops address the same buffer as [B, F, HW, C] (frame stride HW*C) - there
 is no physical transpose between the spatial and temporal halves of a block (the reference alternates NCHW,
 [BF,HW,C] and [B*HW,F,C]: patch/patch.py:592-597,682-684).
@@ -258,28 +261,30 @@ class Conditioning:
 
 
 def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor], g: Geom, cond: Conditioning):
+    """x (and skip) are fp32 stream tensors; returns the fp32 block output."""
     temb_s = cond.temb(p.temb_w, p.temb_b)
     temb_t = cond.temb(p.ttemb_w, p.ttemb_b)
     h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
-    h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH))
+    h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH),
+                 out_f32=True)        # only GroupNorm reads it: keep fp32 instead of rounding twice
     h = ops.groupnorm(h, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True)
     if p.wsc is not None:
-        if skip is None:
-            sc = ops.gemm(x, p.wsc, bias=p.bsc)
-        else:
-            c1 = x.shape[1]
-            sc = ops.gemm(x, p.wsc[:, :c1], bias=p.bsc, A1=skip, Bw1=p.wsc[:, c1:])
+        # the 1x1 shortcut reads the raw input: narrow (and concatenate) it to the GEMM's bf16 operand
+        xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
+        sc = ops.gemm(xa, p.wsc, bias=p.bsc, out_f32=True)
     else:
         if skip is not None:
             raise ValueError("resblock with concatenated input must have a shortcut conv")
         sc = x
-    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc)
+    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True)
     # temporal half: GroupNorm statistics across frames, (3,1,1) conv over the frame axis, AlphaBlender
     t = ops.groupnorm(s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True)
-    t = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=temb_t, rv=g.rv(RV_BATCH))
+    t = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=temb_t, rv=g.rv(RV_BATCH),
+                 out_f32=True)
     t = ops.groupnorm(t, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True)
     # alpha*s + (1-alpha)*(s + conv2(t)) == s + (1-alpha)*conv2(t)
-    return ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=s, s1=1.0)
+    return ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=s, s1=1.0,
+                    out_f32=True)
 
 
 def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor):
@@ -290,20 +295,20 @@ def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom,
     q = ops.gemm(n, wq)
     kv = ops.gemm(ctx.reshape(B * L, D).to(bf16).contiguous(), wkv)
     a = ops.attention(q, kv[:, :c], kv[:, c:], n_img=B, heads=pc.heads, d=pc.d, Nq=g.F * g.HW, Nk=L)
-    return ops.gemm(a, wo, bias=pc.bo, res1=h)
+    return ops.gemm(a, wo, bias=pc.bo, res1=h, out_f32=True)
 
 
 def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Conditioning, tctx_mode: int):
     C = p.c
     kv1 = cond.ctx.shape[1] == 1
     h = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False)
-    h = dense(h, p.proj_in)
+    h = dense(h, p.proj_in, out_f32=True)                                             # fp32 hidden stream
     # ---- spatial block (patch/patch.py:390-580)
     n = ops.layernorm(h, p.s_ln1.g, p.s_ln1.b, p.s_ln1.eps)
     qkv = dense(n, p.s_qkv)
     a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, Nq=g.HW,
                       Nk=g.HW)
-    h = dense(a, p.s_out, res1=h)
+    h = dense(a, p.s_out, res1=h, out_f32=True)
     if kv1:
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross),
                           rv=g.rv(RV_BATCH), sum_out=h)
@@ -312,17 +317,17 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         h = _cross_general(p.s_cross, n, cond.ctx, g, h)
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps)
     ff = dense(n, p.s_ff1, act=ACT_GEGLU)
-    xs = dense(ff, p.s_ff2, res1=h)                                                   # x_spatial
+    xs = dense(ff, p.s_ff2, res1=h, out_f32=True)                                     # x_spatial
     # ---- temporal block (patch/patch.py:582-686) on the same rows, frame stride HW*C
     t0 = torch.empty_like(xs)
     n = ops.layernorm(xs, p.t_lnin.g, p.t_lnin.b, p.t_lnin.eps, addvec=p.pos_emb(g.F), rv=g.rv(RV_FRAMEPOS),
                       sum_out=t0)                                                      # t0 = x_spatial + emb[f]
     ff = dense(n, p.t_ffin1, act=ACT_GEGLU)
-    t = dense(ff, p.t_ffin2, res1=t0)
+    t = dense(ff, p.t_ffin2, res1=t0, out_f32=True)
     n = ops.layernorm(t, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
     qkv = dense(n, p.t_qkv)
     a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
-    t = dense(a, p.t_out, res1=t)
+    t = dense(a, p.t_out, res1=t, out_f32=True)
     if kv1:
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec(p.t_cross),
                           rv=g.rv(tctx_mode), sum_out=t)
@@ -335,9 +340,9 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         t = _cross_general(p.t_cross, n, cond.ctx, g, t)
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps)
     ff = dense(n, p.t_ff1, act=ACT_GEGLU)
-    # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t)
+    # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t); bf16 because proj_out reads it as its GEMM operand
     mix = dense(ff, p.t_ff2, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
-    return dense(mix, p.proj_out, res1=x)
+    return dense(mix, p.proj_out, res1=x, out_f32=True)
 
 
 class PackedUNet:
@@ -391,7 +396,8 @@ class PackedUNet:
 
     def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None):
         """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms)."""
-        x = ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b, res1=stem_add)
+        x = ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b, res1=stem_add,
+                     out_f32=True)
         skips, geoms = [x], [g]
         for res, att, ds in self.down:
             for i, r in enumerate(res):
@@ -401,7 +407,8 @@ class PackedUNet:
                 skips.append(x)
                 geoms.append(g)
             if ds is not None:
-                x = ops.gemm(x, ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1])
+                x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1],
+                             out_f32=True)
                 g = g.down()
                 skips.append(x)
                 geoms.append(g)
@@ -421,7 +428,7 @@ class PackedUNet:
             if us is not None:
                 x = ops.upsample2x(x, g.BF, g.H, g.W)
                 g = g.up()
-                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1])
+                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True)
         h = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, self.norm_out.eps, NS=g.BF, R=g.HW, silu=True)
         # conv_out: N padded to 32 rows of zeros, only the first `cout` columns are stored (fp32)
         return ops.gemm(h, self.conv_out_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_out_b,

@@ -97,8 +97,9 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N):
         raise ValueError("bias must be fp32 [N]")
     for r in (res1, res2):
-        if r is not None and (r.dtype != bf16 or r.dim() != 2 or r.shape[0] != M or r.stride(1) != 1):
-            raise ValueError("residuals must be bf16 [M, >=n] row-major")
+        if r is not None and (r.dtype not in (bf16, torch.float32) or r.dim() != 2 or r.shape[0] != M
+                              or r.stride(1) != 1):
+            raise ValueError("residuals must be bf16 or fp32 [M, >=n] row-major")
     if rowvec is not None and (rowvec.dtype != torch.float32 or rowvec.shape[-1] != n_cols
                                or not rowvec.is_contiguous()):
         raise ValueError("rowvec must be contiguous fp32 [G, n]")
@@ -108,6 +109,8 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     a.res1, a.ldr1, a.s1 = _ptr(res1), (res1.stride(0) if res1 is not None else 0), s1
     a.res2, a.ldr2, a.s2 = _ptr(res2), (res2.stride(0) if res2 is not None else 0), s2
     a.out, a.ldo, a.out_f32, a.n_store = out.data_ptr(), out.stride(0), int(out_f32), n_store
+    a.res1_f32 = int(res1 is not None and res1.dtype == torch.float32)
+    a.res2_f32 = int(res2 is not None and res2.dtype == torch.float32)
     lib = L.load()
     fn = lib.lkgd_gemm_simt_check if checker else lib.lkgd_gemm
     if L.PROF.enabled:
@@ -133,15 +136,15 @@ def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor]):
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, NS: int, R: int,
               x2: Optional[torch.Tensor] = None, groups: int = 32, silu: bool = True,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x1 [NS*R, C1] (+ x2 [NS*R, C2]) bf16 channels-last -> [NS*R, C1+C2] bf16."""
+    """x1 [NS*R, C1] (+ x2 [NS*R, C2]) bf16 or fp32 channels-last -> [NS*R, C1+C2] bf16."""
     _need_cuda(x1, x2, gamma, beta)
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     Ct = C1 + C2
-    if x1.dtype != bf16 or not x1.is_contiguous() or x1.numel() != NS * R * C1:
-        raise ValueError("groupnorm: x1 must be contiguous bf16 [NS*R, C1]")
-    if x2 is not None and (x2.dtype != bf16 or not x2.is_contiguous() or x2.numel() != NS * R * C2):
-        raise ValueError("groupnorm: x2 must be contiguous bf16 [NS*R, C2]")
+    if x1.dtype not in (bf16, torch.float32) or not x1.is_contiguous() or x1.numel() != NS * R * C1:
+        raise ValueError("groupnorm: x1 must be contiguous bf16/fp32 [NS*R, C1]")
+    if x2 is not None and (x2.dtype != x1.dtype or not x2.is_contiguous() or x2.numel() != NS * R * C2):
+        raise ValueError("groupnorm: x2 must be contiguous [NS*R, C2] of x1's dtype")
     if gamma.dtype != torch.float32 or gamma.numel() != Ct or beta.numel() != Ct:
         raise ValueError("groupnorm: gamma/beta must be fp32 [C]")
     lib = L.load()
@@ -150,7 +153,8 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     ws_bytes = lib.lkgd_groupnorm_workspace(NS, Ct)
     ws = torch.empty(ws_bytes, device=x1.device, dtype=torch.uint8)
     L.check(lib.lkgd_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
-                               eps, int(silu), out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "lkgd_groupnorm")
+                               eps, int(silu), int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                               _stream()), "lkgd_groupnorm")
     return out
 
 
@@ -158,15 +162,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
               addvec: Optional[torch.Tensor] = None, rv: Tuple[int, int, int, int] = (RV_NONE, 1, 1, 1),
               sum_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, gamma, beta, addvec)
-    if x.dtype != bf16 or x.dim() != 2 or not x.is_contiguous():
-        raise ValueError("layernorm: x must be contiguous bf16 [M, C]")
+    if x.dtype not in (bf16, torch.float32) or x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("layernorm: x must be contiguous bf16/fp32 [M, C]")
+    if sum_out is not None and (sum_out.dtype != x.dtype or not sum_out.is_contiguous()):
+        raise ValueError("layernorm: sum_out must be contiguous and of x's dtype")
     M, Cn = x.shape
     if addvec is not None and (addvec.dtype != torch.float32 or addvec.shape[-1] != Cn or not addvec.is_contiguous()):
         raise ValueError("layernorm: addvec must be contiguous fp32 [G, C]")
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty((M, Cn), device=x.device, dtype=bf16)
     L.check(L.load().lkgd_layernorm(x.data_ptr(), M, Cn, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
-                                    rv[0], rv[1], rv[2], rv[3], _ptr(sum_out), out.data_ptr(), _stream()),
+                                    rv[0], rv[1], rv[2], rv[3], int(x.dtype == torch.float32), _ptr(sum_out),
+                                    out.data_ptr(), _stream()),
             "lkgd_layernorm")
     return out
 
@@ -310,7 +317,8 @@ def upsample2x(src: torch.Tensor, N: int, H: int, W: int) -> torch.Tensor:
     _need_cuda(src)
     Cn = src.shape[-1]
     out = torch.empty((N * 4 * H * W, Cn), device=src.device, dtype=bf16)
-    L.check(L.load().lkgd_upsample2x(src.data_ptr(), out.data_ptr(), N, H, W, Cn, _stream()), "lkgd_upsample2x")
+    L.check(L.load().lkgd_upsample2x(src.data_ptr(), int(src.dtype == torch.float32), out.data_ptr(), N, H, W, Cn,
+                                     _stream()), "lkgd_upsample2x")
     return out
 
 
@@ -318,18 +326,36 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _need_cuda(a, b)
     M = a.shape[0]
     out = torch.empty((M, a.shape[1] + b.shape[1]), device=a.device, dtype=bf16)
-    L.check(L.load().lkgd_concat_channels(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], out.data_ptr(), M,
-                                          _stream()), "lkgd_concat_channels")
+    if a.dtype != b.dtype or not a.is_contiguous() or not b.is_contiguous():
+        raise ValueError("concat_channels: contiguous sources of one dtype")
+    L.check(L.load().lkgd_concat_channels(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1],
+                                          int(a.dtype == torch.float32), out.data_ptr(), M, _stream()),
+            "lkgd_concat_channels")
     return out
 
 
 def axpby(x: torch.Tensor, alpha: float, y: torch.Tensor, beta: float) -> torch.Tensor:
-    """y = alpha*x + beta*y in place on bf16."""
+    """y = alpha*x + beta*y in place; x and y each bf16 or fp32."""
     _need_cuda(x, y)
-    if x.dtype != bf16 or y.dtype != bf16 or x.numel() != y.numel() or not x.is_contiguous() or not y.is_contiguous():
-        raise ValueError("axpby: contiguous bf16 tensors of equal size")
-    L.check(L.load().lkgd_axpby(x.data_ptr(), alpha, y.data_ptr(), beta, x.numel(), _stream()), "lkgd_axpby")
+    ok = (bf16, torch.float32)
+    if x.dtype not in ok or y.dtype not in ok or x.numel() != y.numel() or not x.is_contiguous() \
+            or not y.is_contiguous():
+        raise ValueError("axpby: contiguous bf16/fp32 tensors of equal size")
+    L.check(L.load().lkgd_axpby(x.data_ptr(), int(x.dtype == torch.float32), alpha, y.data_ptr(),
+                                int(y.dtype == torch.float32), beta, x.numel(), _stream()), "lkgd_axpby")
     return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy (a residual-stream tensor that a GEMM reads raw)."""
+    _need_cuda(x)
+    if x.dtype == bf16:
+        return x
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("cast_bf16: contiguous fp32 tensor expected")
+    out = torch.empty(x.shape, device=x.device, dtype=bf16)
+    L.check(L.load().lkgd_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "lkgd_cast_bf16")
+    return out
 
 
 def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torch.Tensor, sigma: float,

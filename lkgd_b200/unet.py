@@ -398,6 +398,10 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         n = torch.arange(256, dtype=f64, device=dev)
         k = torch.arange(129, dtype=f64, device=dev)
         ang = 2 * math.pi * k[:, None] * n[None, :] / 256
+        dft_im = -torch.sin(ang)
+        dft_im[0] = 0
+        dft_im[128] = 0           # rfft returns an exactly-zero imaginary part for the DC and Nyquist bins; the phase
+        #                           (torch.angle) is discontinuous there, so the zeros must be exact, not ~1e-13
         t = torch.arange(512, dtype=f64, device=dev)
         k2 = torch.arange(257, dtype=f64, device=dev)
         ang2 = 2 * math.pi * t[:, None] * k2[None, :] / 512
@@ -414,7 +418,7 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
             fconv=(grouped(self.quaternion_lora_fconv) @ interp).float().contiguous(),
             fuse=ham(self.quaternion_lora_fuse), mag=ham(self.quaternion_lora_fuse_fft_mag),
             pha=ham(self.quaternion_lora_fuse_fft_pha),
-            dft_re=torch.cos(ang).float().contiguous(), dft_im=(-torch.sin(ang)).float().contiguous(),
+            dft_re=torch.cos(ang).float().contiguous(), dft_im=dft_im.float().contiguous(),
             idft=torch.cat([ir, ii], 1).float().contiguous(),
             mag0=(_f32(self.quaternion_lora_fuse_fft_mag0.weight), _f32(self.quaternion_lora_fuse_fft_mag0.bias)),
             pha0=(_f32(self.quaternion_lora_fuse_fft_pha0.weight), _f32(self.quaternion_lora_fuse_fft_pha0.bias)),
@@ -612,9 +616,9 @@ class ControlNetSDVModel(_Base):
             stem_add = e
         x, skips, geoms, gm = pk.encoder(x, g, cond, stem_add=stem_add)
         s = float(conditioning_scale)
-        down = [ChannelsLast(ops.gemm(sk, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
+        down = [ChannelsLast(ops.gemm(ops.cast_bf16(sk), w, bias=b, s0=s), gs.BF, gs.H, gs.W)
                 for sk, (w, b), gs in zip(skips, zero[:-1], geoms)]
-        mid = ChannelsLast(ops.gemm(x, zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
+        mid = ChannelsLast(ops.gemm(ops.cast_bf16(x), zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
         return down, mid
 
     @torch.no_grad()

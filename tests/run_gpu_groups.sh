@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$
 i=0
 for k in "gemm_linear" "gemm_column or gemm_epilogue or gemm_n_store" "gemm_geglu" "gemm_lora" "gemm_conv3x3" \
          "gemm_tconv3" "gemm_large" "groupnorm" "layernorm" "attention_self" "attention_cross" "attention_svd" \
-         "attention_temporal" "small_linear or pack_unpack or upsample or cfg_euler"; do
+         "attention_temporal" "small_linear or pack_unpack or upsample or cfg_euler or fp32_residual"; do
   i=$((i+1))
   timeout 240 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "$k" -p no:cacheprovider > "$out/group_$i.log" 2>&1
   echo "group $i [$k] exit $?" | tee -a "$out/summary.txt"

@@ -333,3 +333,48 @@ def test_cfg_euler_step_matches_formula(cuda):
     ref = x + (x - x0) / sig * (sig_n - sig)
     assert rel_l2(v, vv) < 1e-6
     assert rel_l2(xn, ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- fp32 stream
+def test_fp32_residual_stream_variants(cuda):
+    """The residual stream is fp32: norms read it, GEMM epilogues add / write it, glue narrows it to bf16."""
+    from lkgd_b200 import ops
+    M, K, N = 640, 128, 320
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    r1 = rnd(M, N, dev=cuda, dtype=torch.float32, seed=1)
+    r2 = rnd(M, N, dev=cuda, seed=2)
+    out = ops.gemm(A, W, res1=r1, s1=1.0, res2=r2, s2=0.5, s0=0.25, out_f32=True)
+    ref = 0.25 * (A.float() @ W.float().t()) + r1 + 0.5 * r2.float()
+    assert out.dtype == torch.float32 and rel_l2(out, ref) < 1e-5
+    chk = ops.gemm(A, W, res1=r1, s1=1.0, res2=r2, s2=0.5, s0=0.25, out_f32=True, checker=True)
+    assert rel_l2(out, chk) < 1e-5
+    # GroupNorm / LayerNorm on fp32 input
+    NS, R, C1, C2 = 2, 300, 64, 32
+    x1 = rnd(NS * R, C1, dev=cuda, dtype=torch.float32) + 0.3
+    x2 = rnd(NS * R, C2, dev=cuda, dtype=torch.float32, seed=4) * 2
+    g = rnd(C1 + C2, dev=cuda, dtype=torch.float32) * 0.2 + 1
+    b = rnd(C1 + C2, dev=cuda, dtype=torch.float32, seed=6) * 0.2
+    got = ops.groupnorm(x1, g, b, 1e-6, NS=NS, R=R, x2=x2, silu=True)
+    xr = torch.cat([x1, x2], 1).view(NS, R, -1).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, g, b, 1e-6)).permute(0, 2, 1).reshape(NS * R, -1)
+    assert got.dtype == bf16 and rel_l2(got.float(), ref) < 4e-3
+    x = rnd(500, 320, dev=cuda, dtype=torch.float32) * 3
+    gg, bb = torch.ones(320, device=cuda), torch.zeros(320, device=cuda)
+    add = rnd(5, 320, dev=cuda, dtype=torch.float32, seed=8)
+    s = torch.empty_like(x)
+    got = ops.layernorm(x, gg, bb, 1e-5, addvec=add, rv=(ops.RV_FRAME, 100, 1, 1), sum_out=s)
+    s_ref = x + add[torch.arange(500, device=cuda) // 100]
+    assert torch.equal(s, s_ref)
+    assert rel_l2(got.float(), F.layer_norm(s_ref, (320,), gg, bb, 1e-5)) < 4e-3
+    # glue: cast, upsample (fp32 -> bf16), concat (fp32 -> bf16), axpby (bf16 into fp32)
+    assert torch.equal(ops.cast_bf16(x), x.to(bf16))
+    xs = rnd(2 * 3 * 4, 64, dev=cuda, dtype=torch.float32)
+    up = ops.upsample2x(xs, 2, 3, 4)
+    ref = F.interpolate(xs.view(2, 3, 4, 64).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    assert torch.equal(up.view(2, 6, 8, 64), ref.permute(0, 2, 3, 1).to(bf16))
+    assert torch.equal(ops.concat_channels(x1, x2), torch.cat([x1, x2], 1).to(bf16))
+    y = x.clone()
+    xb = rnd(500, 320, dev=cuda, seed=12)
+    ops.axpby(xb, 4.0, y, 1.0)
+    assert rel_l2(y, x + 4.0 * xb.float()) < 1e-6
