@@ -1,0 +1,123 @@
+"""GPU: the CUDA path (through the C ABI) against golden vectors produced by running the reference's own files
+(tests/golden/make_reference_golden.py).  Tolerances are BASELINE.json's: bf16 prediction rel-L2 <= 1e-2,
+fp32 scheduler <= 1e-4, trajectory <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import (B, F, H, REDUCED4, SCHED, T_STEP, W, fill_seeded_, golden, rel, seeded_tensor, t,
+                         unet_inputs, unet_residuals)
+
+pytestmark = pytest.mark.gpu
+G = golden()
+
+
+@pytest.mark.parametrize("n", [25, 10])
+def test_scheduler_kernels_vs_reference_trajectory(cuda, n):
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    s = EulerDiscreteScheduler(**SCHED)
+    s.set_timesteps(n, device=cuda)
+    x = (seeded_tensor("sched/x0", (1, 3, 4, 8, 8)) * s.init_noise_sigma).to(cuda)
+    worst = 0.0
+    for i, ts in enumerate(s.timesteps):
+        xin = s.scale_model_input(x, ts)
+        assert rel(xin, G[f"sched{n}/scaled"][i]) < 1e-6
+        x = s.step(seeded_tensor(f"sched/v{i}", x.shape).to(cuda), ts, x).prev_sample
+        worst = max(worst, rel(x, G[f"sched{n}/traj"][i]))
+    print("scheduler worst rel-L2", worst)
+    assert worst < 1e-4
+    assert s.step_index == n
+
+
+def _product_unet(cuda, cls=None, cfg=REDUCED4, seed=0):
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    cls = cls or UNetSpatioTemporalConditionControlNetModel
+    return fill_seeded_(cls(**cfg), seed=seed).to(cuda)
+
+
+def test_unet_vs_reference(cuda):
+    p = _product_unet(cuda)
+    sample, ctx, ids = (v.to(cuda) for v in unet_inputs())
+    a = p(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0]
+    b = p(sample, 0.75, ctx, added_time_ids=ids).sample
+    ea, eb = rel(a, G["unet/out"]), rel(b, G["unet/out_float_t"])
+    print("unet rel-L2", ea, eb)
+    assert ea < 1e-2 and eb < 1e-2
+
+
+def test_unet_residual_injection_vs_reference(cuda):
+    p = _product_unet(cuda)
+    sample, ctx, ids = (v.to(cuda) for v in unet_inputs())
+    res, mid = unet_residuals()
+    a = p(sample, T_STEP, ctx, down_block_additional_residuals=[r.to(cuda) for r in res],
+          mid_block_additional_residual=mid.to(cuda), added_time_ids=ids).sample
+    e = rel(a, G["unet/out_residuals"])
+    print("unet+residuals rel-L2", e)
+    assert e < 1e-2
+
+
+def test_lkgd_vs_reference(cuda):
+    from lkgd_b200.unet import UNetSpatioTemporalConditionModel
+    p = _product_unet(cuda, UNetSpatioTemporalConditionModel, dict(REDUCED4, cross_attention_dim=1024))
+    sample, _, ids = (v.to(cuda) for v in unet_inputs())
+    ctx = seeded_tensor("lkgd/ctx", (B, 1, 1024)).to(cuda)
+    dom, flo = seeded_tensor("lkgd/domain", (1, 1, 1000)).to(cuda), seeded_tensor("lkgd/flow", (1, 1, 1000)).to(cuda)
+    c = p._context(ctx, dom, flo)
+    assert rel(c.reshape(B, 1024), G["lkgd/context"]) < 1e-4            # fp32 conditioning block
+    a = p(sample, T_STEP, ctx, dom, flo, added_time_ids=ids).sample     # D8: batch-1 features duplicated
+    dom2 = seeded_tensor("lkgd/domain2", (B, 1, 1000)).to(cuda)
+    flo2 = seeded_tensor("lkgd/flow2", (B, 1, 1000)).to(cuda)
+    assert rel(p._context(ctx, dom2, flo2).reshape(B, 1024), G["lkgd/context_b2"]) < 1e-4
+    a2 = p(sample, T_STEP, ctx, dom2, flo2, added_time_ids=ids).sample
+    e, e2 = rel(a, G["lkgd/out"]), rel(a2, G["lkgd/out_b2"])
+    print("lkgd rel-L2", e, e2)
+    assert e < 1e-2 and e2 < 1e-2
+
+
+def _product_controlnet(cuda):
+    from lkgd_b200.unet import ControlNetSDVModel
+    cfg = {k: v for k, v in REDUCED4.items() if k != "up_block_types"}
+    return fill_seeded_(ControlNetSDVModel(**cfg, conditioning_channels=2), seed=1).to(cuda)
+
+
+def test_controlnet_vs_reference(cuda):
+    cn = _product_controlnet(cuda)
+    sample, ctx, ids = (v.to(cuda) for v in unet_inputs())
+    cond = seeded_tensor("cn/cond", (B, F, 2, 8 * H, 8 * W)).clamp(-1, 1).to(cuda)
+    down, mid = cn(sample, T_STEP, ctx, ids, controlnet_cond=cond, conditioning_scale=0.7, return_dict=False)
+    assert len(down) == 6
+    errs = [rel(d, G[f"cn/down{i}"]) for i, d in enumerate(down)] + [rel(mid, G["cn/mid"])]
+    print("controlnet rel-L2", errs)
+    assert max(errs) < 1e-2
+
+
+def test_lora_folded_and_merged_vs_reference(cuda):
+    """models/lora_layer.py Linear.forward / merge, executed as the GEMM's second K segment and as W += s*B*A."""
+    from lkgd_b200 import modules as M
+    from lkgd_b200 import engine, ops
+    base = M.Linear(32, 48)
+    lo = fill_seeded_(M.LoraLinear(base, 4, 4, "gaussian", "default"), seed=2).to(cuda)
+    x = seeded_tensor("lora/x", (5, 7, 32)).reshape(35, 32).to(cuda).to(torch.bfloat16)
+    d = engine._dense(lo, fold_lora=True)
+    y = engine.dense(x, d, out_f32=True)
+    assert rel(y.reshape(5, 7, 48), G["lora/y"]) < 1e-2
+    dm = engine._dense(lo, fold_lora=False)
+    assert rel(dm.w.float(), G["lora/merged_weight"]) < 5e-3            # bf16 storage of the merged weight
+    assert rel(engine.dense(x, dm, out_f32=True).reshape(5, 7, 48), G["lora/y_merged"]) < 1e-2
+
+
+def test_pipeline_loop_vs_reference(cuda):
+    """6 CFG Euler-Karras steps with ControlNet residual injection vs the latents the reference pipeline produced."""
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    pipe = StableVideoDiffusionPipeline(_product_unet(cuda), EulerDiscreteScheduler(**SCHED), _product_controlnet(cuda))
+    cond = seeded_tensor("pipe/cond", (F, 2, 8 * H, 8 * W)).clamp(-1, 1)
+    lat0 = seeded_tensor("pipe/latents", (1, F, 4, H, W))
+    final, preds, traj = pipe(t(G["pipe/image_embeddings"]), t(G["pipe/image_latents"]), num_frames=F,
+                              num_inference_steps=6, fps=7, motion_bucket_id=127, noise_aug_strength=0.02,
+                              latents=lat0, controlnet_condition=cond, controlnet_cond_scale=0.7,
+                              return_trajectory=True)
+    assert np.allclose(pipe.guidance_scale.cpu().numpy(), G["pipe/guidance"])
+    errs = [rel(x, G["pipe/steps"][i]) for i, x in enumerate(traj)]
+    print("pipeline per-step latents rel-L2", errs)
+    assert max(errs) < 2e-2 and rel(final, G["pipe/final"]) < 2e-2

@@ -1,0 +1,281 @@
+"""CPU: the oracle (oracle/) against golden vectors produced by RUNNING THE REFERENCE'S OWN FILES
+(tests/golden/make_reference_golden.py: scheduler, UNet wiring, LKGD conditioning, ControlNet, residual injection,
+LoRA layer, pipeline CFG loop - with only the un-vendored diffusers/peft/core_qnn pieces shimmed), plus the
+reference's parameter-name dumps and the known-answer values of SURVEY.md Appendix C."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from golden_util import (B, F, H, REDUCED4, SCHED, T_STEP, W, fill_seeded_, golden, rel, seeded_tensor, t,
+                         unet_inputs, unet_residuals)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = golden()
+
+
+# ------------------------------------------------------------------------------------------------ scheduler
+@pytest.mark.parametrize("n", [25, 10])
+def test_scheduler_schedule_bit_exact(n):
+    s = O.EulerDiscreteScheduler(**SCHED)
+    assert np.array_equal(s.sigmas[:8].numpy(), G["sched/init_sigmas_head"])      # the "fix": Karras at __init__
+    assert np.array_equal(s.timesteps[:8].numpy(), G["sched/init_timesteps_head"])
+    s.set_timesteps(n)
+    assert np.array_equal(s.sigmas.numpy(), G[f"sched{n}/sigmas"])
+    assert np.array_equal(s.timesteps.numpy(), G[f"sched{n}/timesteps"])
+    assert float(s.init_noise_sigma) == float(G[f"sched{n}/init_noise_sigma"])
+
+
+@pytest.mark.parametrize("n", [25, 10])
+def test_scheduler_trajectory_bit_exact(n):
+    s = O.EulerDiscreteScheduler(**SCHED)
+    s.set_timesteps(n)
+    x = seeded_tensor("sched/x0", (1, 3, 4, 8, 8)) * s.init_noise_sigma
+    for i, ts in enumerate(s.timesteps):
+        xin = s.scale_model_input(x, ts)
+        assert np.array_equal(xin.numpy(), G[f"sched{n}/scaled"][i])
+        o = s.step(seeded_tensor(f"sched/v{i}", x.shape), ts, x)
+        assert np.array_equal(o.prev_sample.numpy(), G[f"sched{n}/traj"][i]), i
+        assert np.array_equal(o.pred_original_sample.numpy(), G[f"sched{n}/x0"][i]), i
+        x = o.prev_sample
+
+
+def test_scheduler_add_noise_and_errors():
+    s = O.EulerDiscreteScheduler(**SCHED)
+    orig, noise = seeded_tensor("sched/orig", (4, 2, 4, 4, 4)), seeded_tensor("sched/noise", (4, 2, 4, 4, 4))
+    got = s.add_noise(orig, noise, t(G["sched/add_noise_t"]))
+    assert np.array_equal(got.numpy(), G["sched/add_noise"])
+    s.set_timesteps(25)
+    with pytest.raises(ValueError):                 # integer timesteps are rejected (reference :458-469, D6)
+        s.step(torch.zeros(1), 3, torch.zeros(1))
+
+
+def test_scheduler_kat_appendix_c():
+    s = O.EulerDiscreteScheduler(**SCHED)
+    s.set_timesteps(25)
+    sig = s.sigmas.numpy()
+    np.testing.assert_allclose(sig[:5], [700.0, 545.729248046875, 421.5691223144531, 322.45367431640625,
+                                         244.0230712890625], rtol=1e-6)
+    np.testing.assert_allclose(sig[20:], [0.15740464627742767, 0.06639907509088516, 0.02480258047580719,
+                                          0.007882495410740376, 0.0020000000949949026, 0.0], rtol=1e-6)
+    np.testing.assert_allclose(s.timesteps.numpy()[:5], [1.6377700567245483, 1.575530767440796, 1.5109959840774536,
+                                                         1.443989872932434, 1.3743157386779785], rtol=1e-6)
+    np.testing.assert_allclose(float(s.init_noise_sigma), 700.000732421875, rtol=1e-7)
+    s._step_index = 3
+    x, v = torch.full((1,), 1.5), torch.full((1,), -0.25)
+    np.testing.assert_allclose(float(s.scale_model_input(x, s.timesteps[3])), 0.004651808645576239, rtol=1e-6)
+    o = s.step(v, s.timesteps[3], x)
+    np.testing.assert_allclose(float(o.pred_original_sample), 0.25001323223114014, rtol=1e-5)
+    np.testing.assert_allclose(float(o.prev_sample), 1.1959649324417114, rtol=1e-6)
+    g = O.guidance_ramp(1.0, 3.0, 14).flatten().numpy()
+    np.testing.assert_allclose(g[:4], [1.0, 1.1538461446762085, 1.307692289352417, 1.4615384340286255], rtol=1e-6)
+    assert g[-1] == 3.0
+
+
+# ------------------------------------------------------------------------------------------------ structure
+def test_param_names_match_reference_dumps():
+    d = json.load(open(os.path.join(HERE, "golden", "param_names.json")))
+    with torch.device("meta"):
+        m = O.UNetSpatioTemporalConditionModel(**dict(O.SVD_XT_CONFIG, num_attention_heads=(5, 10, 20, 20)))
+        O.add_lora(m, 4)
+    names = {n for n, _ in m.named_parameters()}
+    want = set(d["frozen"]) | set(d["trainable"])
+    assert names == want, (sorted(names - want)[:5], sorted(want - names)[:5])
+    trainable = {n for n in names if "lora_" in n}       # incl. quaternion_lora_* (F10)
+    assert trainable == set(d["trainable"])
+
+
+# ------------------------------------------------------------------------------------------------ UNet wiring
+def _oracle_unet():
+    return fill_seeded_(O.UNetSpatioTemporalConditionControlNetModel(**REDUCED4)).eval()
+
+
+def test_unet_forward_matches_reference():
+    o = _oracle_unet()
+    sample, ctx, ids = unet_inputs()
+    with torch.no_grad():
+        a = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids, return_dict=False)[0]
+        b = o(sample, 0.75, ctx, added_time_ids=ids).sample
+    assert rel(a, G["unet/out"]) < 1e-6
+    assert rel(b, G["unet/out_float_t"]) < 1e-6
+    assert int(G["unet/n_params"]) == sum(p.numel() for p in o.parameters())
+
+
+def test_unet_residual_injection_matches_reference():
+    """F6: the residual add sits inside the down-block loop (multipliers (2,2,2,2,1,1) for the 2-level config)."""
+    o = _oracle_unet()
+    sample, ctx, ids = unet_inputs()
+    res, mid = unet_residuals()
+    with torch.no_grad():
+        a = o(sample, torch.tensor(T_STEP), ctx, down_block_additional_residuals=res,
+              mid_block_additional_residual=mid, added_time_ids=ids).sample
+    assert rel(a, G["unet/out_residuals"]) < 1e-6
+    assert rel(G["unet/out"], G["unet/out_residuals"]) > 1e-2     # the residuals matter
+
+
+def test_lkgd_conditioning_matches_reference():
+    o = fill_seeded_(O.UNetSpatioTemporalConditionModel(**dict(REDUCED4, cross_attention_dim=1024))).eval()
+    sample, _, ids = unet_inputs()
+    ctx = seeded_tensor("lkgd/ctx", (B, 1, 1024))
+    dom, flo = seeded_tensor("lkgd/domain", (1, 1, 1000)), seeded_tensor("lkgd/flow", (1, 1, 1000))
+    with torch.no_grad():
+        c = o._condition(ctx, dom, flo)
+        a = o(sample, torch.tensor(T_STEP), ctx, dom, flo, added_time_ids=ids).sample
+        dom2, flo2 = seeded_tensor("lkgd/domain2", (B, 1, 1000)), seeded_tensor("lkgd/flow2", (B, 1, 1000))
+        c2 = o._condition(ctx, dom2, flo2)
+        a2 = o(sample, torch.tensor(T_STEP), ctx, dom2, flo2, added_time_ids=ids).sample
+    assert rel(c.reshape(B, 1024), G["lkgd/context"]) < 1e-5
+    assert rel(a, G["lkgd/out"]) < 1e-5
+    assert rel(c2.reshape(B, 1024), G["lkgd/context_b2"]) < 1e-5
+    assert rel(a2, G["lkgd/out_b2"]) < 1e-5
+
+
+def test_controlnet_matches_reference():
+    cfg = {k: v for k, v in REDUCED4.items() if k != "up_block_types"}
+    o = fill_seeded_(O.ControlNetSDVModel(**cfg, conditioning_channels=2), seed=1).eval()
+    sample, ctx, ids = unet_inputs()
+    cond = seeded_tensor("cn/cond", (B, F, 2, 8 * H, 8 * W)).clamp(-1, 1)
+    with torch.no_grad():
+        down, mid = o(sample, torch.tensor(T_STEP), ctx, ids, controlnet_cond=cond, conditioning_scale=0.7,
+                      return_dict=False)
+    assert len(down) == int(G["cn/n_down"]) == 6
+    for i, d in enumerate(down):
+        assert rel(d, G[f"cn/down{i}"]) < 1e-6, i
+    assert rel(mid, G["cn/mid"]) < 1e-6
+
+
+def test_lora_matches_reference_layer():
+    base = torch.nn.Linear(32, 48)
+    lo = O.LoraLinear(base, 4, 4, "gaussian")
+    fill_seeded_(lo, seed=2)
+    x = seeded_tensor("lora/x", (5, 7, 32))
+    with torch.no_grad():
+        assert rel(lo(x), G["lora/y"]) < 1e-6
+        assert rel(lo.get_delta_weight(), G["lora/delta"]) < 1e-6
+        lo.merge()
+        assert rel(lo.base_layer.weight, G["lora/merged_weight"]) < 1e-6
+        assert rel(lo(x), G["lora/y_merged"]) < 1e-6
+    lo8 = O.LoraLinear(torch.nn.Linear(32, 48), 8, 4, True)
+    assert lo8.scaling == float(G["lora/scaling_r8_a4"]) == 0.5
+    assert float(lo8.lora_B["default"].weight.detach().abs().max()) == float(G["lora/B_default_is_zero"]) == 0.0
+
+
+def test_pipeline_loop_matches_reference():
+    """The reference pipeline's own __call__ (CFG dup, scale, concat, ControlNet, UNet with residual injection,
+    frame-wise guidance, Euler-Karras step) for 6 steps vs the oracle's denoise_loop."""
+    unet = _oracle_unet()
+    cfg = {k: v for k, v in REDUCED4.items() if k != "up_block_types"}
+    cn = fill_seeded_(O.ControlNetSDVModel(**cfg, conditioning_channels=2), seed=1).eval()
+    sched = O.EulerDiscreteScheduler(**SCHED)
+    sched.set_timesteps(6)
+    lat0 = seeded_tensor("pipe/latents", (1, F, 4, H, W)) * sched.init_noise_sigma
+    cond = seeded_tensor("pipe/cond", (F, 2, 8 * H, 8 * W)).clamp(-1, 1).unsqueeze(0)
+    cond = torch.cat([cond] * 2)
+    ids = O.add_time_ids_inference(6, 127, 0.02, 1)
+    final, preds, traj = O.denoise_loop(unet, sched, lat0, t(G["pipe/image_latents"]), t(G["pipe/image_embeddings"]),
+                                        ids, 6, 1.0, 3.0, controlnet=cn, controlnet_cond=cond,
+                                        controlnet_cond_scale=0.7, return_trajectory=True)
+    assert np.array_equal(O.guidance_ramp(1.0, 3.0, F).numpy(), G["pipe/guidance"])
+    for i, x in enumerate(traj):
+        assert rel(x, G["pipe/steps"][i]) < 1e-5, i
+    assert rel(final, G["pipe/final"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ algebraic KATs
+def test_lora_default_init_is_identity_and_merge_equivalence():
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(16, 24)
+    lo = O.LoraLinear(lin, 4, 4, "gaussian")
+    x = torch.randn(3, 16)
+    with torch.no_grad():
+        assert torch.equal(lo(x), lin(x))                 # B = 0 (reference lora_layer.py:145)
+        lo.lora_B["default"].weight.normal_(0, 0.1)
+        y = lo(x)
+        lo.merge()
+        assert rel(lo(x), y) < 1e-6
+
+
+def test_controlnet_zero_convs_are_identity_for_the_unet():
+    o = _oracle_unet()
+    cfg = {k: v for k, v in REDUCED4.items() if k != "up_block_types"}
+    torch.manual_seed(0)
+    cn = O.ControlNetSDVModel(**cfg, conditioning_channels=3).eval()      # default zero-init (controlnet_sdv.py:804-807)
+    sample, ctx, ids = unet_inputs()
+    with torch.no_grad():
+        down, mid = cn(sample, 0.5, ctx, ids, controlnet_cond=torch.rand(B, F, 3, 8 * H, 8 * W), return_dict=False)
+        assert all(float(d.abs().max()) == 0.0 for d in down) and float(mid.abs().max()) == 0.0
+        a = o(sample, 0.5, ctx, added_time_ids=ids).sample
+        b = o(sample, 0.5, ctx, down_block_additional_residuals=down, mid_block_additional_residual=mid,
+              added_time_ids=ids).sample
+    assert torch.equal(a, b)
+
+
+def test_residual_multipliers_f6():
+    """Constant residuals r_i = i+1 on a UNet whose skips are otherwise unchanged show m = (2,2,2,2,1,1)."""
+    from lkgd_b200.engine import residual_multipliers
+    assert residual_multipliers(4, [4, 3, 3, 2]) == [4, 4, 4, 4, 3, 3, 3, 2, 2, 2, 1, 1]
+    assert residual_multipliers(2, [4, 2]) == [2, 2, 2, 2, 1, 1]
+    # the same multipliers out of the oracle's loop: feed unit residuals and look at what reaches the up blocks
+    o = _oracle_unet()
+    sample, ctx, ids = unet_inputs()
+    res, mid = unet_residuals()
+    seen = []
+    hooks = [r.register_forward_pre_hook(lambda m, a: seen.append(a[0].detach().clone()))
+             for blk in o.up_blocks for r in blk.resnets]
+    with torch.no_grad():
+        o(sample, 0.5, ctx, added_time_ids=ids)
+        base = list(seen)
+        seen.clear()
+        o(sample, 0.5, ctx, down_block_additional_residuals=res, added_time_ids=ids)
+    for h in hooks:
+        h.remove()
+    mult = [2, 2, 2, 2, 1, 1]
+    # up-block resnet k consumes skip 5-k as the trailing channels of its concatenated input
+    for k, (a, b) in enumerate(zip(base, seen)):
+        i = 5 - k
+        c = res[i].shape[1]
+        assert rel(b[:, -c:] - a[:, -c:], mult[i] * res[i]) < 1e-5, k
+
+
+def test_kv1_cross_attention_identity():
+    torch.manual_seed(0)
+    at = O.Attention(32, 2, 16, cross_attention_dim=24).eval()
+    x, ctx = torch.randn(3, 10, 32), torch.randn(3, 1, 24)
+    with torch.no_grad():
+        want = at.to_out[0](at.to_v(ctx)).expand(3, 10, 32)
+        assert rel(at(x, ctx), want) < 1e-6           # softmax over one key == 1
+
+
+def test_cfg_identities():
+    p = torch.randn(2, 5, 4, 3, 3)
+    assert torch.allclose(O.cfg_combine(p, O.guidance_ramp(1.0, 1.0, 5)), p[1:], atol=1e-6)
+    q = torch.cat([p[:1], p[:1]])
+    assert torch.allclose(O.cfg_combine(q, O.guidance_ramp(1.0, 3.0, 5)), p[:1])
+
+
+def test_alphablender_limits_and_single_frame():
+    ab = O.AlphaBlender()
+    xs, xt = torch.randn(2, 3, 4, 2, 2), torch.randn(2, 3, 4, 2, 2)
+    iof = torch.zeros(2, 4)
+    with torch.no_grad():
+        ab.mix_factor.fill_(50.0)
+        assert torch.allclose(ab(xs, xt, iof), xs)
+        ab.mix_factor.fill_(-50.0)
+        assert torch.allclose(ab(xs, xt, iof), xt)
+
+
+def test_add_time_ids_orderings_f12():
+    assert O.add_time_ids_inference(6, 127, 0.02, 1, do_cfg=False).tolist() == [[6.0, 127.0, pytest.approx(0.02)]]
+    assert O.add_time_ids_training(6, 127, 0.02, 1).tolist() == [[6.0, pytest.approx(0.02), 127.0]]
+
+
+def test_oracle_fp64_self_consistency():
+    o = _oracle_unet()
+    sample, ctx, ids = unet_inputs()
+    with torch.no_grad():
+        a = o(sample, 0.5, ctx, added_time_ids=ids).sample
+        b = o.double()(sample.double(), 0.5, ctx.double(), added_time_ids=ids.double()).sample
+    assert rel(a, b) < 1e-5

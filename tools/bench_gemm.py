@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Micro-benchmark of lkgd_gemm on the shapes that dominate the C3 denoise step (from profiles/*prof*.json).
+Usage: python tools/bench_gemm.py [--only i,j] [--iters N]   (CUDA events, L2 flushed between calls)"""
+import argparse, json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lkgd_b200 import ops
+from lkgd_b200.ops import A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU
+
+bf16 = torch.bfloat16
+# (name, mode, M or geometry, N, K0, epilogue)
+SHAPES = [
+    ("ff1_L0_geglu", "lin", 460800, 2560, 320, "geglu"),
+    ("ff1_L1_geglu", "lin", 115200, 5120, 640, "geglu"),
+    ("ff1_L2_geglu", "lin", 28800, 10240, 1280, "geglu"),
+    ("proj_L0_res32", "lin", 460800, 320, 320, "res32"),
+    ("qkv_L0_bf16", "lin", 460800, 960, 320, "bf16"),
+    ("ff2_L0_res32", "lin", 460800, 320, 1280, "res32"),
+    ("ff2_L1_res32", "lin", 115200, 640, 2560, "res32"),
+    ("proj_L1_res32", "lin", 115200, 640, 640, "res32"),
+    ("proj_L2_res32", "lin", 28800, 1280, 1280, "res32"),
+    ("ff2_L2_res32", "lin", 28800, 1280, 5120, "res32"),
+    ("conv_L0_f32", "conv", (50, 72, 128), 320, 320, "f32"),
+    ("conv_L0_res32", "conv", (50, 72, 128), 320, 320, "res32"),
+    ("conv_L1_f32", "conv", (50, 36, 64), 640, 640, "f32"),
+    ("conv_L2_f32", "conv", (50, 18, 32), 1280, 1280, "f32"),
+    ("conv_L3_f32", "conv", (50, 9, 16), 1280, 1280, "f32"),
+    ("tconv_L0_f32", "tconv", (2, 25, 9216), 320, 320, "f32"),
+    ("tconv_L1_res32", "tconv", (2, 25, 2304), 640, 640, "res32"),
+    ("tconv_L3_f32", "tconv", (2, 25, 144), 1280, 1280, "f32"),
+]
+
+
+def run(shape, iters, flush):
+    name, mode, geo, N, K0, epi = shape
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    if mode == "lin":
+        M = geo
+        A = torch.randn(M, K0, device=dev, dtype=bf16, generator=g)
+        taps, kw = 1, dict(mode=A_LINEAR)
+    elif mode == "conv":
+        n, h, w = geo
+        M = n * h * w
+        A = torch.randn(M, K0, device=dev, dtype=bf16, generator=g)
+        taps, kw = 9, dict(mode=A_CONV3X3, conv=(n, h, w, 1))
+    else:
+        b, f, hw = geo
+        M = b * f * hw
+        A = torch.randn(M, K0, device=dev, dtype=bf16, generator=g)
+        taps, kw = 3, dict(mode=A_TCONV3, tconv=(b, f, hw))
+    W = (torch.randn(N, taps * K0, device=dev, dtype=bf16, generator=g) * (taps * K0) ** -0.5)
+    bias = torch.randn(N, device=dev, generator=g)
+    n_out = N // 2 if epi == "geglu" else N
+    out_b = 4 if epi in ("f32", "res32") else 2
+    bytes_ = M * K0 * 2 + N * taps * K0 * 2 + M * n_out * out_b
+    if epi == "geglu":
+        W, bias = ops.pack_geglu(W, bias)
+        kw.update(act=ACT_GEGLU)
+    elif epi == "res32":
+        kw.update(res1=torch.randn(M, N, device=dev, generator=g), out_f32=True)
+        bytes_ += M * N * 4
+    elif epi == "f32":
+        kw.update(out_f32=True)
+    out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if out_b == 4 else bf16)
+    for _ in range(2):
+        ops.gemm(A, W, bias=bias, out=out, **kw)
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(A, W, bias=bias, out=out, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    flops = 2.0 * M * N * taps * K0
+    return dict(name=name, M=M, N=N, K=taps * K0, epi=epi, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
+                gbs=round(bytes_ / ms / 1e6, 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    sel = [int(i) for i in a.only.split(",")] if a.only else range(len(SHAPES))
+    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+    res = []
+    for i in sel:
+        r = run(SHAPES[i], a.iters, flush)
+        res.append(r)
+        print(json.dumps(r), flush=True)
+    if a.out:
+        json.dump(res, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
