@@ -59,6 +59,8 @@ LKGD_API uint64_t lkgd_launch_count(void);
  *   TCONV3  : A is [B, F, HW, C0]; output (b,f,p) gathers frames f-1,f,f+1 (zero pad); Bw is [N, 3*C0].
  * Optional second K segment (LoRA / shortcut / concat source): A1 [M, K1] (same addressing mode, centre tap),
  * Bw1 [N, K1].
+ * Residuals: res1 / res2 rows must be 16-byte addressable (pointer, pitch and column count); res2 requires res1
+ * and the same element type.
  * GEGLU: Bw rows are pre-interleaved per 256-row tile (128 value rows then their 128 gate rows); the output
  * has N/2 columns: out = (acc_h + b_h) * gelu_erf(acc_g + b_g).
  */

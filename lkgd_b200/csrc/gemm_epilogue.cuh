@@ -1,0 +1,266 @@
+// Epilogue of the tcgen05 GEMM (included by gemm_tcgen05.cu after GemmParams / tile_row are defined).
+//
+// Eight epilogue warps, two per TMEM lane quarter, alternate 64-byte column chunks of the 128 x BN accumulator tile:
+//   cp.async prefetch of the residual chunk into a per-warp, XOR-swizzled smem buffer (double-buffered, so one chunk
+//   of HBM latency is always in flight per warp)  ->  tcgen05.ld  ->  bias (from smem) / row vector / SiLU / GEGLU /
+//   scaled residuals in registers  ->  per-warp smem transpose  ->  16-byte global stores coalesced along rows.
+#pragma once
+
+namespace lkgd {
+
+// ---- per-warp staging buffers: 32 rows x RB bytes (RB = 32 or 64), 16-byte pieces XOR-swizzled so that both the
+// row-per-lane accesses and the coalesced (several lanes per row) accesses are bank-conflict free.
+template <int RB>
+__device__ __forceinline__ uint32_t stg_off(int row, int piece) {
+  constexpr int P = RB / 16;             // pieces per row: 2 or 4
+  constexpr int RPL = 8 / P;             // rows per 128-byte line
+  return static_cast<uint32_t>(row * RB + ((piece ^ ((row / RPL) & (P - 1))) << 4));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU in 13 instructions.  gelu(x) = relu(x) - |x| h,  h = 0.5 erfc(|x| / sqrt 2) = (sum a_i/2 t^i) exp(-x^2/2),
+// t = 1 / (1 + p |x| / sqrt 2)   (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7 - far below the bf16 rounding of
+// the product it feeds; the reference computes F.gelu(gate) with the exact erf form).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float u = ax * 0.84932180028801904f;                     // sqrt(log2(e) / 2):  exp(-x^2/2) = 2^(-u^2)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.0f)));   // p / sqrt 2
+  float q = fmaf(t, 0.5307027145f, -0.7265760135f);
+  q = fmaf(q, t, 0.7107068705f);
+  q = fmaf(q, t, -0.142248368f);
+  q = fmaf(q, t, 0.127414796f);
+  const float h = q * t * ex2_approx(-u * u);
+  return fmaf(-ax, h, fmaxf(x, 0.f));
+}
+
+// Epilogue of one 128 x BN tile for one warp (32 TMEM lanes = 32 tile rows, alternate column chunks).
+//   CW   accumulator columns per chunk: 32 when every operand is bf16, else 16 (a chunk is 64 B of the widest row)
+//   OES  output element size (2 / 4);  RES residual element size (0 = none, 2, 4);  NRES number of residuals
+// Row-per-lane accesses touch this lane's own staging row; "coalesced" accesses walk 16-byte pieces so that
+// consecutive lanes cover consecutive bytes of a global row (P pieces per row, 32 / P rows per instruction).
+template <int CW, int OES, int RES, int NRES, bool GEGLU>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& tc, int n_tile, uint32_t taddr,
+                                              int lane_base, int lane, int half, uint32_t stg,
+                                              const float* __restrict__ sbias) {
+  constexpr int OB = CW * OES;                 // output row bytes per chunk: 64 or 32
+  constexpr int PO = OB / 16;
+  constexpr int RB = RES ? CW * RES : 64;      // residual row bytes per chunk
+  constexpr int PR = RB / 16;
+  const int bn_out = GEGLU ? p.BN / 2 : p.BN;
+  const int n_cols = GEGLU ? p.N / 2 : p.N;
+  const int out_col_base = n_tile * bn_out;
+  // columns this tile may touch: inside the matrix (n_store) and inside the tile (a chunk may overhang bn_out)
+  const int n_store = min(p.n_store > 0 ? p.n_store : n_cols, out_col_base + bn_out);
+  const int nchunks = (bn_out + CW - 1) / CW;
+  const long long m = tile_row(p, tc, lane_base + lane);
+  const float* rv = nullptr;
+  if (p.rowvec != nullptr && m >= 0)
+    rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * n_cols;
+
+  // coalesced-side geometry, fixed for the tile: row pointers (nullptr = row outside the tensor) and smem offsets
+  char* orow[PO];
+  const char* r1row[PR];
+  const char* r2row[PR];
+#pragma unroll
+  for (int j = 0; j < PO; ++j) {
+    const long long mr = tile_row(p, tc, lane_base + lane / PO + (32 / PO) * j);
+    orow[j] = mr >= 0 ? reinterpret_cast<char*>(p.out) + (size_t)mr * p.ldo * OES + (lane % PO) * 16 : nullptr;
+  }
+#pragma unroll
+  for (int j = 0; j < PR; ++j) {
+    r1row[j] = r2row[j] = nullptr;
+    if (NRES >= 1) {
+      const long long mr = tile_row(p, tc, lane_base + lane / PR + (32 / PR) * j);
+      if (mr >= 0) {
+        r1row[j] = reinterpret_cast<const char*>(p.res1) + (size_t)mr * p.ldr1 * RES + (lane % PR) * 16;
+        if (NRES == 2) r2row[j] = reinterpret_cast<const char*>(p.res2) + (size_t)mr * p.ldr2 * RES + (lane % PR) * 16;
+      }
+    }
+  }
+  const uint32_t o_co = stg_off<OB>(lane / PO, lane % PO);        // + 512 * j
+  const uint32_t r_co = stg_off<RB>(lane / PR, lane % PR);
+  const int o_pc_col = (lane % PO) * (16 / OES);                  // first column of this lane's coalesced piece
+  const int r_pc_col = RES ? (lane % PR) * (16 / (RES ? RES : 4)) : 0;
+
+  auto issue = [&](int c, uint32_t buf) {
+    const int col0 = out_col_base + c * CW;
+    const bool col_ok = col0 + r_pc_col < n_store;
+#pragma unroll
+    for (int j = 0; j < PR; ++j) {
+      const bool ok = col_ok && r1row[j] != nullptr;
+      cp_async16(buf + r_co + 512 * j, ok ? r1row[j] + (size_t)col0 * RES : reinterpret_cast<const char*>(p.res1),
+                 ok ? 16u : 0u);
+      if (NRES == 2)
+        cp_async16(buf + 2048 + r_co + 512 * j,
+                   ok ? r2row[j] + (size_t)col0 * RES : reinterpret_cast<const char*>(p.res2), ok ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+
+  int k = 0;
+  for (int c = half; c < nchunks; c += 2, ++k) {
+    const uint32_t buf = stg + ((NRES == 2) ? 0 : (k & 1) * 2048);
+    if (NRES == 2) {
+      issue(c, buf);                                       // both residuals: single-buffered
+    } else if (NRES == 1) {
+      if (k == 0) issue(c, buf);
+      if (c + 2 < nchunks) issue(c + 2, buf ^ 2048);       // this warp's next chunk, other buffer
+    }
+    uint32_t a[CW], g[GEGLU ? CW : 1];
+    if (CW == 16) {
+      tmem_ld16(taddr + c * CW, *reinterpret_cast<uint32_t(*)[16]>(a));
+      if (GEGLU) tmem_ld16(taddr + bn_out + c * CW, *reinterpret_cast<uint32_t(*)[16]>(g));
+    } else {
+      tmem_ld32(taddr + c * CW, *reinterpret_cast<uint32_t(*)[32]>(a));
+      if (GEGLU) tmem_ld32(taddr + bn_out + c * CW, *reinterpret_cast<uint32_t(*)[32]>(g));
+    }
+    const int n_out = out_col_base + c * CW;       // output column
+    const bool use_rv = rv != nullptr;
+    float v[CW];
+    tmem_ld_wait();
+    // bias of the tile sits in smem (value half, then - GEGLU - the gate half at +bn_out): broadcast LDS.128
+#pragma unroll
+    for (int j = 0; j < CW; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * CW + j);
+      v[j] = __uint_as_float(a[j]) + b4.x;
+      v[j + 1] = __uint_as_float(a[j + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(a[j + 2]) + b4.z;
+      v[j + 3] = __uint_as_float(a[j + 3]) + b4.w;
+      if (GEGLU) {
+        const float4 g4 = *reinterpret_cast<const float4*>(sbias + bn_out + c * CW + j);
+        v[j] *= gelu_erf_fast(__uint_as_float(g[j % (GEGLU ? CW : 1)]) + g4.x);
+        v[j + 1] *= gelu_erf_fast(__uint_as_float(g[(j + 1) % (GEGLU ? CW : 1)]) + g4.y);
+        v[j + 2] *= gelu_erf_fast(__uint_as_float(g[(j + 2) % (GEGLU ? CW : 1)]) + g4.z);
+        v[j + 3] *= gelu_erf_fast(__uint_as_float(g[(j + 3) % (GEGLU ? CW : 1)]) + g4.w);
+      }
+    }
+    if (use_rv) {                                  // per-row vector (time embedding / context term), L1/L2 resident
+      if (n_out + CW <= n_cols && (n_cols & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv + n_out + j));
+          v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] += (n_out + j < n_cols) ? __ldg(rv + n_out + j) : 0.f;
+      }
+    }
+    if (p.act == LKGD_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = silu_f(v[j]);
+    }
+    if (p.s0 != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] *= p.s0;
+    }
+    if (NRES >= 1) {
+      if (NRES == 1 && c + 2 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      const uint32_t own = buf + lane * RB;
+      const int sw = (lane / (8 / PR)) & (PR - 1);
+#pragma unroll
+      for (int r = 0; r < NRES; ++r) {
+        const float scale = r == 0 ? p.s1 : p.s2;
+#pragma unroll
+        for (int q = 0; q < PR; ++q) {
+          const uint4 u = lds128(own + r * 2048 + ((q ^ sw) << 4));
+          if (RES == 4) {
+            v[(4 * q) % CW] = fmaf(scale, __uint_as_float(u.x), v[(4 * q) % CW]);
+            v[(4 * q + 1) % CW] = fmaf(scale, __uint_as_float(u.y), v[(4 * q + 1) % CW]);
+            v[(4 * q + 2) % CW] = fmaf(scale, __uint_as_float(u.z), v[(4 * q + 2) % CW]);
+            v[(4 * q + 3) % CW] = fmaf(scale, __uint_as_float(u.w), v[(4 * q + 3) % CW]);
+          } else {
+            float f[8];
+            unpack_bf16x8(u, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[(8 * q + e) % CW] = fmaf(scale, f[e], v[(8 * q + e) % CW]);
+          }
+        }
+      }
+      __syncwarp();            // every lane has consumed its residual row before the buffer is reused for the output
+    }
+    if (p.fast_io) {
+      // stage the output chunk (row per lane), then write it out with 16-byte pieces coalesced along rows
+      const uint32_t own = buf + lane * OB;
+      const int sw = (lane / (8 / PO)) & (PO - 1);
+#pragma unroll
+      for (int q = 0; q < PO; ++q) {
+        uint4 u;
+        if (OES == 4) {
+          u = make_uint4(__float_as_uint(v[(4 * q) % CW]), __float_as_uint(v[(4 * q + 1) % CW]),
+                         __float_as_uint(v[(4 * q + 2) % CW]), __float_as_uint(v[(4 * q + 3) % CW]));
+        } else {
+          u = make_uint4(pack_bf16x2(v[(8 * q) % CW], v[(8 * q + 1) % CW]), pack_bf16x2(v[(8 * q + 2) % CW], v[(8 * q + 3) % CW]),
+                         pack_bf16x2(v[(8 * q + 4) % CW], v[(8 * q + 5) % CW]), pack_bf16x2(v[(8 * q + 6) % CW], v[(8 * q + 7) % CW]));
+        }
+        sts128(own + ((q ^ sw) << 4), u);
+      }
+      __syncwarp();
+      const bool col_ok = n_out + o_pc_col < n_store;
+#pragma unroll
+      for (int j = 0; j < PO; ++j) {
+        if (col_ok && orow[j] != nullptr)
+          *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = lds128(buf + o_co + 512 * j);
+      }
+      __syncwarp();            // staging buffer free again (next prefetch may overwrite it)
+    } else if (m >= 0) {
+      // generic path: unaligned pitches / odd column counts - scalar stores from the owning lane
+      if (OES == 4) {
+        float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n_out;
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (n_out + j < n_store) op[j] = v[j];
+      } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n_out;
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (n_out + j < n_store) op[j] = __float2bfloat16(v[j]);
+      }
+    }
+  }
+}
+
+// runtime -> compile-time epilogue variant
+__device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, const TileCoord& tc, int n_tile, uint32_t taddr,
+                                                  int lane_base, int lane, int half, uint32_t stg,
+                                                  const float* sbias) {
+#define LKGD_EPI(CW, OES, RES, NRES, GG) \
+  epilogue_tile<CW, OES, RES, NRES, GG>(p, tc, n_tile, taddr, lane_base, lane, half, stg, sbias)
+  const int nres = p.res1 == nullptr ? 0 : (p.res2 == nullptr ? 1 : 2);
+  if (p.act == LKGD_ACT_GEGLU) {
+    if (p.out_f32) LKGD_EPI(16, 4, 0, 0, true); else LKGD_EPI(32, 2, 0, 0, true);
+  } else if (p.out_f32) {
+    if (nres == 0) LKGD_EPI(16, 4, 0, 0, false);
+    else if (p.res1_f32) { if (nres == 1) LKGD_EPI(16, 4, 4, 1, false); else LKGD_EPI(16, 4, 4, 2, false); }
+    else { if (nres == 1) LKGD_EPI(16, 4, 2, 1, false); else LKGD_EPI(16, 4, 2, 2, false); }
+  } else {
+    if (nres == 0) LKGD_EPI(32, 2, 0, 0, false);
+    else if (p.res1_f32) { if (nres == 1) LKGD_EPI(16, 2, 4, 1, false); else LKGD_EPI(16, 2, 4, 2, false); }
+    else { if (nres == 1) LKGD_EPI(32, 2, 2, 1, false); else LKGD_EPI(32, 2, 2, 2, false); }
+  }
+#undef LKGD_EPI
+}
+
+}  // namespace lkgd

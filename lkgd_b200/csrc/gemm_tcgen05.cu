@@ -1,8 +1,12 @@
 // Persistent warp-specialised GEMM / implicit-GEMM convolution for sm_100a.
 //   warp 0 (one lane): TMA producer      - cp.async.bulk.tensor tiles of A (2-D / 4-D box, zero-filled halo) and B
 //   warp 1 (one lane): tcgen05.mma issuer - 128 x BN x 16 UMMAs, fp32 accumulators in TMEM (2 x 256 columns)
-//   warps 2..5       : epilogue           - tcgen05.ld -> bias / row-vector / act / GEGLU / residual mix -> global
-// smem ring: 4 stages x (A 128x64 bf16 = 16 KB, B BNx64 bf16 <= 32 KB), SWIZZLE_128B everywhere.
+//   warps 2..9       : epilogue           - two warps per TMEM lane quarter, alternating 64-byte column chunks:
+//                        cp.async prefetch of the residual chunk into per-warp swizzled smem (double-buffered),
+//                        tcgen05.ld -> bias / row-vector / act / GEGLU / residual mix in registers ->
+//                        per-warp smem transpose -> coalesced 16-byte global stores.
+// smem: S stages x (A 128x64 bf16 = 16 KB, B BNx64 bf16 = BN*128 B), SWIZZLE_128B; S = 4 (BN = 256) .. 8;
+//       + 8 x 4 KB epilogue staging.
 // See include/lkgd_b200.h (lkgd_gemm) for the contract and the reference call sites it replaces.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -11,11 +15,14 @@ namespace lkgd {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (max BN = 256)
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARP_BYTES = 4096;              // two 2 KB chunk buffers (32 rows x 64 B)
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int BIAS_BYTES = 2 * 256 * 4;           // bias of the current / next tile (double-buffered)
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
 constexpr int MAX_TAPS = 9;
 
 struct GemmParams {
@@ -24,8 +31,9 @@ struct GemmParams {
   CUtensorMap tmA1;
   CUtensorMap tmB1;
   int mode, M, N, BN;
+  int stages, stage_bytes;
   int kb0, ntaps, kb1, k0;           // k-blocks per tap, taps, k-blocks of segment 1, channels per tap
-  int H, W, TW, TH, tiles_w, tiles_h;  // conv output geometry + tile patch
+  int H, W, TW, TH, tw_shift, tiles_w, tiles_h;  // conv output geometry + tile patch (TW a power of two)
   int HW, F, tiles_p;                  // tconv
   int m_tiles, n_tiles;
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
@@ -40,6 +48,7 @@ struct GemmParams {
   int ldr1, ldr2, res1_f32, res2_f32;
   void* out;
   int ldo, out_f32, n_store;
+  int fast_io;                         // 1: every out / residual row segment is 16-byte addressable
 };
 
 __device__ __forceinline__ int rowvec_index(int mode, int m, int HW, int F, int B) {
@@ -79,7 +88,7 @@ __device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoo
     int m = t.c1 + r;
     return m < p.M ? m : -1;
   } else if (p.mode == LKGD_A_CONV3X3) {
-    int w = t.c1 + r % p.TW, h = t.c2 + r / p.TW;
+    int w = t.c1 + (r & (p.TW - 1)), h = t.c2 + (r >> p.tw_shift);
     return (w < p.W && h < p.H) ? ((long long)t.c3 * p.H + h) * p.W + w : -1;
   } else {
     int pp = t.c1 + r;
@@ -87,58 +96,33 @@ __device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoo
   }
 }
 
-// v[0..15] += scale * res[m, n_out .. n_out+15]  (bf16 or fp32 residual, vectorised when the chunk is full)
-__device__ __forceinline__ void add_residual(float (&v)[16], const void* res, int f32, int ld, long long m, int n_out,
-                                             float scale, bool full16, int n_store) {
-  if (f32) {
-    const float* rp = reinterpret_cast<const float*>(res) + (size_t)m * ld + n_out;
-    if (full16 && (ld & 3) == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
-        v[4 * j] += scale * q.x; v[4 * j + 1] += scale * q.y; v[4 * j + 2] += scale * q.z; v[4 * j + 3] += scale * q.w;
-      }
-    } else {
-      for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += scale * rp[j];
-    }
-  } else {
-    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(res) + (size_t)m * ld + n_out;
-    if (full16 && (ld & 7) == 0) {
-      float f[8];
-      uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-      uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-      unpack_bf16x8(q0, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += scale * f[j];
-      unpack_bf16x8(q1, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 + j] += scale * f[j];
-    } else {
-      for (int j = 0; j < 16 && n_out + j < n_store; ++j) v[j] += scale * __bfloat162float(rp[j]);
-    }
-  }
-}
+}  // namespace lkgd
+
+#include "gemm_epilogue.cuh"
+
+namespace lkgd {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* sm_epi = smem + p.stages * p.stage_bytes;
+  float* sm_bias = reinterpret_cast<float*>(sm_epi + EPI_WARPS * EPI_WARP_BYTES);       // 2 x 256 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_epi + EPI_WARPS * EPI_WARP_BYTES + BIAS_BYTES);
+  uint64_t* full = bars;                         // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;           // [MAX_STAGES]
+  uint64_t* tfull = bars + 2 * MAX_STAGES;       // [2]
+  uint64_t* tempty = bars + 2 * MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int kiters = p.ntaps * p.kb0 + p.kb1;
+  const int S = p.stages;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+      for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
       fence_barrier_init();
       tma_prefetch_desc(&p.tmA[0]);
       tma_prefetch_desc(&p.tmB);
@@ -161,8 +145,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], tx_bytes);
-        void* dA = smA + stage * A_STAGE_BYTES;
-        void* dB = smB + stage * B_STAGE_BYTES;
+        void* dA = smem + stage * p.stage_bytes;
+        void* dB = smem + stage * p.stage_bytes + A_STAGE_BYTES;
         const bool seg1 = it >= p.ntaps * p.kb0;
         int tap = 0, kb, dx = 0, dy = 0;
         const CUtensorMap* mA;
@@ -178,7 +162,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         else tma_load_4d(dA, mA, &full[stage], kb * BK, tc.c1, tc.c2 + dy, tc.c3);
         if (!seg1) tma_load_2d(dB, &p.tmB, &full[stage], tap * p.k0 + kb * BK, n0);
         else tma_load_2d(dB, &p.tmB1, &full[stage], kb * BK, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -194,96 +178,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smA + stage * A_STAGE_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smB + stage * B_STAGE_BYTES));
+        const uint64_t adesc = umma_desc_sw128(smem_u32(smem + stage * p.stage_bytes));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + stage * p.stage_bytes + A_STAGE_BYTES));
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
         umma_commit(&empty[stage]);
         if (it == kiters - 1) umma_commit(&tfull[as]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane each)
-    const int lane_base = (warp & 3) * 32;
-    const int r = lane_base + lane;                       // row of the tile owned by this thread
-    const bool geglu = p.act == LKGD_ACT_GEGLU;
-    const int bn_out = geglu ? p.BN / 2 : p.BN;
-    const int n_store = p.n_store > 0 ? p.n_store : (geglu ? p.N / 2 : p.N);
+    // ------------------------------------------------------------------ epilogue (8 warps, 2 per TMEM lane quarter)
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
+    const int lane_base = (warp & 3) * 32;                // TMEM lanes this warp may read
+    const int half = ew >> 2;                             // which alternate chunks it takes
+    const uint32_t stg = smem_u32(sm_epi + ew * EPI_WARP_BYTES);
     int tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int as = tile_iter & 1;
       const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
       TileCoord tc; tile_origin(p, m_tile, tc);
-      const long long m = tile_row(p, tc, r);
+      // bias of this tile -> smem (overlaps the tile's MMAs); buffer `as` was last read two tiles ago and every
+      // epilogue warp has passed the previous tile's barrier since
+      float* sb = sm_bias + as * 256;
+      {
+        const int n = n_tile * p.BN + et;
+        sb[et] = (p.bias != nullptr && et < p.BN && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull[as], (tile_iter >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(lane_base) << 16);
-      const float* rv = nullptr;
-      if (p.rowvec != nullptr && m >= 0)
-        rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * (geglu ? p.N / 2 : p.N);
-      for (int c = 0; c < bn_out; c += 16) {
-        uint32_t a[16], g[16];
-        tmem_ld16(taddr + c, a);
-        if (geglu) tmem_ld16(taddr + bn_out + c, g);
-        tmem_ld_wait();
-        if (m < 0) continue;
-        const int n_in = n_tile * p.BN + c;            // column in Bw / bias space (value half for GEGLU)
-        const int n_out = n_tile * bn_out + c;         // output column
-        if (n_out >= n_store) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += (n_in + j < p.N) ? __ldg(p.bias + n_in + j) : 0.f;
-        }
-        if (geglu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float gate = __uint_as_float(g[j]) + (p.bias != nullptr ? __ldg(p.bias + n_in + bn_out + j) : 0.f);
-            v[j] *= gelu_erf_f(gate);
-          }
-        }
-        if (rv != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += (n_out + j < n_store) ? __ldg(rv + n_out + j) : 0.f;
-        }
-        if (p.act == LKGD_ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
-        }
-        const bool full16 = n_out + 16 <= n_store;
-        if (p.s0 != 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= p.s0;
-        }
-        if (p.res1 != nullptr) add_residual(v, p.res1, p.res1_f32, p.ldr1, m, n_out, p.s1, full16, n_store);
-        if (p.res2 != nullptr) add_residual(v, p.res2, p.res2_f32, p.ldr2, m, n_out, p.s2, full16, n_store);
-        if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n_out;
-          if (full16 && (p.ldo & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 16 && n_out + j < n_store; ++j) op[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n_out;
-          if (full16 && (p.ldo & 7) == 0) {
-            uint4 q0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                  pack_bf16x2(v[6], v[7]));
-            uint4 q1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                  pack_bf16x2(v[14], v[15]));
-            reinterpret_cast<uint4*>(op)[0] = q0;
-            reinterpret_cast<uint4*>(op)[1] = q1;
-          } else {
-            for (int j = 0; j < 16 && n_out + j < n_store; ++j) op[j] = __float2bfloat16(v[j]);
-          }
-        }
-      }
+      epilogue_dispatch(p, tc, n_tile, taddr, lane_base, lane, half, stg, sb);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -351,6 +279,8 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
     if ((long long)a->NIMG * Ho * Wo != a->M) return LKGD_ESHAPE;
     p.H = Ho; p.W = Wo;
     choose_patch(Ho, Wo, p.TW, p.TH);
+    p.tw_shift = 0;
+    while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
     p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
     p.m_tiles = a->NIMG * p.tiles_w * p.tiles_h;
     p.ntaps = 9;
@@ -423,6 +353,20 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
   p.res1 = a->res1; p.ldr1 = a->ldr1; p.res1_f32 = a->res1_f32;
   p.res2 = a->res2; p.ldr2 = a->ldr2; p.res2_f32 = a->res2_f32;
   p.out = a->out; p.ldo = a->ldo; p.out_f32 = a->out_f32; p.n_store = a->n_store;
+  p.stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_WARPS * EPI_WARP_BYTES) / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  {
+    // 16-byte addressable row segments everywhere -> staged, coalesced epilogue I/O
+    const int oes = a->out_f32 ? 4 : 2;
+    const int n_cols = geglu ? a->N / 2 : a->N;
+    const int n_store = a->n_store > 0 ? a->n_store : n_cols;
+    bool ok = aligned16(a->out) && ((size_t)a->ldo * oes) % 16 == 0 && (n_store * oes) % 16 == 0;
+    if (a->res1) { const int es = a->res1_f32 ? 4 : 2; ok = ok && aligned16(a->res1) && ((size_t)a->ldr1 * es) % 16 == 0 && (n_store * es) % 16 == 0; }
+    if (a->res2) { const int es = a->res2_f32 ? 4 : 2; ok = ok && aligned16(a->res2) && ((size_t)a->ldr2 * es) % 16 == 0 && (n_store * es) % 16 == 0; }
+    if ((a->bias && !aligned16(a->bias)) || (a->rowvec && !aligned16(a->rowvec))) return LKGD_EALIGN;
+    p.fast_io = ok ? 1 : 0;
+  }
   return LKGD_OK;
 }
 
@@ -437,13 +381,16 @@ extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
+  if (!p.fast_io && (a->res1 || a->res2)) return LKGD_EALIGN;   // residual rows must be 16-byte addressable
+  if (a->res2 && (!a->res1 || (a->res1_f32 != 0) != (a->res2_f32 != 0))) return LKGD_ESHAPE;   // res2 needs res1 of the same dtype
+  const int smem_bytes = 1024 + p.stages * p.stage_bytes + EPI_WARPS * EPI_WARP_BYTES + BIAS_BYTES + BAR_BYTES;
   int grid = p.m_tiles * p.n_tiles;
   int sms = sm_count();
   if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
 }

@@ -343,12 +343,21 @@ def test_fp32_residual_stream_variants(cuda):
     A = rnd(M, K, dev=cuda)
     W = rnd(N, K, dev=cuda, scale=K ** -0.5)
     r1 = rnd(M, N, dev=cuda, dtype=torch.float32, seed=1)
-    r2 = rnd(M, N, dev=cuda, seed=2)
+    r2 = rnd(M, N, dev=cuda, dtype=torch.float32, seed=2)
     out = ops.gemm(A, W, res1=r1, s1=1.0, res2=r2, s2=0.5, s0=0.25, out_f32=True)
     ref = 0.25 * (A.float() @ W.float().t()) + r1 + 0.5 * r2.float()
     assert out.dtype == torch.float32 and rel_l2(out, ref) < 1e-5
     chk = ops.gemm(A, W, res1=r1, s1=1.0, res2=r2, s2=0.5, s0=0.25, out_f32=True, checker=True)
     assert rel_l2(out, chk) < 1e-5
+    # the AlphaBlender mix: bf16 output (proj_out's GEMM operand) from two fp32 residual-stream tensors
+    mix = ops.gemm(A, W, res1=r1, s1=0.4, res2=r2, s2=0.6, s0=0.4)
+    assert mix.dtype == bf16 and rel_l2(mix.float(), 0.4 * (A.float() @ W.float().t()) + 0.4 * r1 + 0.6 * r2) < 4e-3
+    # bf16 residual into an fp32 output (ControlNet condition embedding added to conv_in)
+    rb = rnd(M, N, dev=cuda, seed=3)
+    o2 = ops.gemm(A, W, res1=rb, out_f32=True)
+    assert rel_l2(o2, A.float() @ W.float().t() + rb.float()) < 1e-5
+    with pytest.raises(ValueError):      # two residuals must share a dtype
+        ops.gemm(A, W, res1=r1, res2=rb, out_f32=True)
     # GroupNorm / LayerNorm on fp32 input
     NS, R, C1, C2 = 2, 300, 64, 32
     x1 = rnd(NS * R, C1, dev=cuda, dtype=torch.float32) + 0.3
