@@ -7,6 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+ABI_VERSION = 1
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -111,8 +112,8 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.lkgd_abi_version() != 1:
-        raise LkgdError(f"ABI version mismatch: library reports {lib.lkgd_abi_version()}, binding expects 1")
+    if lib.lkgd_abi_version() != ABI_VERSION:
+        raise LkgdError(f"ABI version mismatch: library reports {lib.lkgd_abi_version()}, binding expects {ABI_VERSION}")
     for name in _TIMED:
         setattr(lib, name, _timed(name, getattr(lib, name)))
     _lib = lib

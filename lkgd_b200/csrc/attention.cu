@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
       tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        while (!mbar_try_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1)) __nanosleep(64);   // off the critical path: back off
         mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
         tma_load_4d(sK + st * AT_TILE, &p.tmK, &kv_full[st], 0, head, j * AT_BK, img);
         tma_load_4d(sV + st * AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BK, img);
@@ -99,14 +99,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
         const int st = j & 1;
         mbar_wait(p_full, j & 1);     // P_j is in smem, S columns are free again
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks) {
-          const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (ks >> 2) * AT_TILE)) + 2 * (ks & 3);
-          const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + st * AT_TILE + ks * 2048));
-          umma_bf16(tmem_O, pdesc, vdesc, idesc_o, ks != 0);
-        }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        // S_{j+1} = Q K_{j+1}^T first: the softmax warps wait for it, nobody waits for P_j V_j
         if (j + 1 < T) {
           const int sn = (j + 1) & 1;
           mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
@@ -116,36 +109,84 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
           for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
           umma_commit(s_full);
         }
+#pragma unroll
+        for (int ks = 0; ks < AT_BK / 16; ++ks) {
+          const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (ks >> 2) * AT_TILE)) + 2 * (ks & 3);
+          const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + st * AT_TILE + ks * 2048));
+          umma_bf16(tmem_O, pdesc, vdesc, idesc_o, (j | ks) != 0);     // O accumulates in TMEM across KV blocks
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(o_full);          // phase j: P_j V_j has landed in O (and the P tile may be overwritten)
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax / accumulate / epilogue
+    // ---------------------------------------------------------------- softmax / epilogue
+    // One query row per thread.  O stays in TMEM and accumulates across KV blocks; the running maximum is only
+    // raised when a row's block maximum exceeds it by more than 2^8 ("lazy rescale"): then the warp multiplies its
+    // O rows in TMEM by 2^(m_old - m_new).  p = 2^(s*c - m) <= 256 otherwise, exact enough in bf16 / fp32.
     const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[AT_D];
-#pragma unroll
-    for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
     uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
     for (int j = 0; j < T; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);      // S_j = Q K_j^T is in TMEM
       tc_fence_after();
       const int kv_valid = min(AT_BK, p.Nk - j * AT_BK);
-      // pass 1: row maximum
-      float mx = -INFINITY;
+      // pass 1: row maximum (64 columns per TMEM wait, four independent chains)
+      float mx;
+      {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < AT_BK; c += 32) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c, s);
-        tmem_ld_wait();
+        for (int c = 0; c < AT_BK; c += 64) {
+          uint32_t s0[32], s1[32];
+          tmem_ld32(tmem_S + lane_addr + c, s0);
+          tmem_ld32(tmem_S + lane_addr + c + 32, s1);
+          tmem_ld_wait();
+          if (c + 64 <= kv_valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            for (int i = 0; i < 32; i += 2) {
+              m4[(i >> 1) & 1] = fmaxf(m4[(i >> 1) & 1], fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
+              m4[2 + ((i >> 1) & 1)] = fmaxf(m4[2 + ((i >> 1) & 1)], fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (c + i < kv_valid) m4[i & 1] = fmaxf(m4[i & 1], __uint_as_float(s0[i]));
+              if (c + 32 + i < kv_valid) m4[2 + (i & 1)] = fmaxf(m4[2 + (i & 1)], __uint_as_float(s1[i]));
+            }
+          }
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2f(m_run - m_new);
-      // pass 2: p = 2^(s*c - m), packed to bf16 into the swizzled K-major P tile
+      const float m_blk = mx * p.scale_log2;
+      if (j == 0) {
+        m_run = m_blk;
+      } else {
+        const bool grow = m_blk > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(o_full, (j - 1) & 1);              // P_{j-1} V_{j-1} must have landed before O is rescaled
+          tc_fence_after();
+          const float m_new = grow ? m_blk : m_run;
+          const float alpha = ex2f(m_run - m_new);     // 1 for the rows that keep their maximum
+#pragma unroll
+          for (int c = 0; c < AT_D; c += 32) {
+            uint32_t t[32];
+            tmem_ld32(tmem_O + lane_addr + c, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st32(tmem_O + lane_addr + c, t);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_run = m_new;
+        }
+      }
       float lsum = 0.f;
+      // pass 2: p = 2^(s*c - m) in f32, packed to bf16 into the swizzled K-major P tile (free once P_{j-1} V_{j-1}
+      // has been consumed by the tensor core)
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j > 0) mbar_wait(o_full, (j - 1) & 1);
 #pragma unroll
       for (int c = 0; c < AT_BK; c += 32) {
         uint32_t s[32];
@@ -154,13 +195,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_new)) : 0.f;
-          float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_new)) : 0.f;
-          // the row sum uses the same bf16-rounded values the MMA will see
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          float2 hf = __bfloat1622float2(h);
-          lsum += hf.x + hf.y;
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          const float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run)) : 0.f;
+          const float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run)) : 0.f;
+          ls4[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         uint8_t* blk = prow + (c >> 6) * AT_TILE;
 #pragma unroll
@@ -170,24 +208,24 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      tc_fence_before();          // S reads are complete before the MMA warp may overwrite S
+      lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      l_run += lsum;
+      tc_fence_before();          // S reads (and O rescale) are complete before the MMA warp may touch S / O
       fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
       mbar_arrive(p_full);
-      // accumulate O = O*alpha + P_j V_j
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < AT_D; c += 32) {
-        uint32_t t[32];
-        tmem_ld32(tmem_O + lane_addr + c, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(t[i]));
-      }
-      tc_fence_before();
     }
+    mbar_wait(o_full, (T - 1) & 1);
+    tc_fence_after();
+    float o[AT_D];
+#pragma unroll
+    for (int c = 0; c < AT_D; c += 32) {
+      uint32_t t[32];
+      tmem_ld32(tmem_O + lane_addr + c, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(t[i]);
+    }
+    tc_fence_before();
     if (q0 + r < p.Nq) {
       const float inv = 1.0f / l_run;
       __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;

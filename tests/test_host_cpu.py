@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(lib):
     exported = {ln.split()[-1] for ln in exported.splitlines() if " T " in ln}
     assert set(syms) <= exported
     assert {s for s in exported if not s.startswith("lkgd_")} <= {"_init", "_fini"}     # nothing else leaks
-    assert lib.lkgd_abi_version() == 1
+    assert lib.lkgd_abi_version() == _lib.ABI_VERSION
     assert lib.lkgd_strerror(0) is not None and b"shape" in lib.lkgd_strerror(-1).lower()
 
 
