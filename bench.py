@@ -146,7 +146,26 @@ def build_ours(workload, device):
     return pipe, cfg, (F, h, w, rank, lkgd)
 
 
-def cpu_oracle_rate(workload, max_seconds=40.0):
+def workload_desc(workload):
+    key, F, h, w, lrank, lkgd = CONFIGS[workload]
+    return (f"{workload}: SVD-XT CFG denoise step, {F} frames 576x1024 ({h}x{w} latents), CFG batch 2, LoRA r={lrank} "
+            f"folded in the temporal qkv GEMMs, LKGD cond={lkgd}; 1 sample per GPU")
+
+
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, averaged over the launches of one
+    step, from the committed ncu capture (profiles/*gemm_traffic*.json; a profiler number is never timed here)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*gemm_traffic*.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1])).get("avg_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_oracle_rate(workload, max_seconds=40.0, iters=4):
     """Times the oracle (fp32 PyTorch, eager, all host threads) on a BOUNDED sample of the workload: the same
     full-width UNet on a reduced frame count / latent size, scaled to denoise steps/s by algorithmic FLOPs."""
     import oracle as O
@@ -183,7 +202,7 @@ def cpu_oracle_rate(workload, max_seconds=40.0):
     lat = noise * sched.init_noise_sigma
     times = []
     t_start = time.time()
-    for it in range(4):
+    for it in range(max(2, iters)):
         sched._step_index = None
         t1 = time.time()
         O.denoise_loop(model, sched, lat, img_lat, emb, ids, 25, 1.0, 3.0, unet_extra_args=extra, max_steps=1)
@@ -205,14 +224,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, t_step = cpu_oracle_rate(args.workload)
+    # each "step" is one bounded sample (full-width UNet, CFG batch 2, 2 frames of 16x16 latents); W untimed + K timed
+    cb, t_step = cpu_oracle_rate(args.workload, max_seconds=150.0, iters=min(args.warmup, 1) + min(args.steps, 6))
     key, F, h, w, lrank, lkgd = CONFIGS[args.workload]
     line = {
         "impl": "reference", "metric": "denoise_steps_per_s", "value": cb["value"], "unit": "denoise_steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: SVD-XT CFG denoise step {F}f {h}x{w} latents, LoRA r={lrank}, "
-                               f"LKGD={lkgd} (CPU oracle on a bounded sample, FLOP-scaled)"},
+        "config": {"workload": workload_desc(args.workload),
+                   "reference_arm": "the reference's CPU PyTorch path (fp32 oracle port; the reference itself cannot be "
+                                    "installed: no diffusers/peft/core_qnn), every step a bounded sample, FLOP-scaled"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "denoise_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -323,18 +344,23 @@ def main():
         _lib.PROF.enabled = False
         by = {}
         for name, a, b, meta in _lib.PROF.records:
-            d = by.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
+            d = by.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
             d["ms"] += a.elapsed_time(b)
             d["calls"] += 1
             if meta and "flops" in meta:
                 d["flops"] += meta["flops"]
+            if meta and "bytes" in meta:
+                d["bytes"] += meta["bytes"]
         total_ms = sum(d["ms"] for d in by.values())
         pk = peaks()
         gm = by.get("lkgd_gemm", dict(ms=1e-9, calls=0, flops=0.0))
         achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (GEMM + implicit-GEMM conv)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+                "frac": achieved / pk["tf_sustained"], "traffic": gemm_traffic(),
+                "traffic_unit": "bytes per launch (dram read+write, ncu, averaged over the step's launches)",
+                "peak_source": pk["source"] + ", sustained",
+                "achieved_def": "algorithmic 2*M*N*K summed over the step's GEMM/conv launches / their summed CUDA-event durations",
                 "launches_per_step": gm["calls"], "algorithmic_tflop_per_step": gm["flops"] / 1e12,
                 "kernel_ms_per_step": gm["ms"], "share_of_step": gm["ms"] / total_ms,
                 "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
@@ -354,9 +380,7 @@ def main():
             "metric": "denoise_steps_per_s", "value": value, "unit": "denoise_steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: SVD-XT CFG denoise step, {F} frames 576x1024 ({h}x{w} latents), "
-                                   f"CFG batch 2, LoRA r={lrank} folded in the temporal qkv GEMMs, LKGD cond={lkgd}; "
-                                   "1 sample per GPU",
+            "config": {"workload": workload_desc(args.workload),
                        "frames_per_s_per_gpu": F * args.steps / (ms * 1e-3),
                        "algorithmic_tflop_per_step": flops / 1e12,
                        "model_tflops_per_gpu": flops / 1e12 / (ms / args.steps * 1e-3),

@@ -150,6 +150,8 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     lib = L.load()
     if out is None:
         out = torch.empty((NS * R, Ct), device=x1.device, dtype=bf16)
+    if L.PROF.enabled:   # algorithmic bytes: input read twice (statistics, then normalise) + bf16 output
+        L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2)}
     ws_bytes = lib.lkgd_groupnorm_workspace(NS, Ct)
     ws = torch.empty(ws_bytes, device=x1.device, dtype=torch.uint8)
     L.check(lib.lkgd_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
@@ -171,6 +173,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise ValueError("layernorm: addvec must be contiguous fp32 [G, C]")
     if out is None:
         out = torch.empty((M, Cn), device=x.device, dtype=bf16)
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": M * Cn * (x.element_size() + 2 + (x.element_size() if sum_out is not None else 0))}
     L.check(L.load().lkgd_layernorm(x.data_ptr(), M, Cn, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
                                     rv[0], rv[1], rv[2], rv[3], int(x.dtype == torch.float32), _ptr(sum_out),
                                     out.data_ptr(), _stream()),
@@ -208,6 +212,8 @@ def attention_temporal(qkv: torch.Tensor, *, B: int, F: int, HW: int, heads: int
     if out is None:
         out = torch.empty((B * F * HW, Cn), device=qkv.device, dtype=bf16)
     scale = d ** -0.5 if scale is None else scale
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": B * F * HW * Cn * 2 * 4}
     L.check(L.load().lkgd_attention_temporal(qkv.data_ptr(), out.data_ptr(), B, F, HW, heads, d, scale, _stream()),
             "lkgd_attention_temporal")
     return out
