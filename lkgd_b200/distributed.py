@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing of the sampling path.  One process per GPU, ``torch.distributed``.
+
+The denoise step shards only where it splits naturally:
+  * independent samples -> ``shard_range``: every rank denoises its own samples, NO data-path collective;
+  * the classifier-free-guidance pair -> ``CFGPair``: rank 2k runs the unconditional half, rank 2k+1 the conditional
+    half (batch 1 each), and ONE exchange per step (an all-gather of the [S*F*H*W, 4] fp32 prediction, 3.7 MB at
+    25 frames 72x128) feeds the fused CFG + Euler kernel, which both ranks run so the latents stay replicated.
+Frames are never a shard axis: temporal conv / attention and the 5-D GroupNorm couple all of them.
+The reference has none of this (single process, ``pipeline...controlnet.py:577-619``); backend-agnostic on purpose so
+the host logic is covered by world-size-2 ``gloo`` tests on CPU."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of ``n`` independent samples for ``rank`` (first ``n % world`` ranks get one
+    more)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class CFGPair:
+    """Two ranks that share one sample's classifier-free-guidance batch.  ``role`` 0 = unconditional half (first in the
+    reference's ``torch.cat([uncond, cond])`` order, pipeline :206-232), 1 = conditional half."""
+
+    def __init__(self, group, role: int):
+        if role not in (0, 1):
+            raise ValueError("role must be 0 (uncond) or 1 (cond)")
+        self.group, self.role = group, role
+
+    @staticmethod
+    def from_world() -> "CFGPair":
+        """Ranks (2k, 2k+1) of the default group form pair k.  Collective: every rank must call it."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world % 2:
+            raise ValueError("the CFG pair split needs an even number of ranks")
+        mine = None
+        for k in range(world // 2):
+            g = dist.new_group([2 * k, 2 * k + 1])
+            if rank // 2 == k:
+                mine = g
+        return CFGPair(mine, rank % 2)
+
+    def batch_slice(self, S: int) -> Tuple[int, int]:
+        """Rows of the CFG-duplicated batch [uncond(S) | cond(S)] this rank computes."""
+        return self.role * S, (self.role + 1) * S
+
+    def exchange(self, pred_rows: torch.Tensor) -> torch.Tensor:
+        """[n, c] prediction of this half -> [2n, c] (uncond rows first) on both ranks: the one collective per step."""
+        pred_rows = pred_rows.contiguous()
+        parts = [torch.empty_like(pred_rows) for _ in range(2)]
+        dist.all_gather(parts, pred_rows, group=self.group)
+        return torch.cat(parts, 0)
+
+
+def gather_samples(latents: torch.Tensor, dst: int = 0) -> Optional[List[torch.Tensor]]:
+    """Collects every rank's finished latents on ``dst`` (outside the timed / data path)."""
+    world = dist.get_world_size()
+    out = [torch.empty_like(latents) for _ in range(world)] if dist.get_rank() == dst else None
+    dist.gather(latents.contiguous(), out, dst=dst)
+    return out

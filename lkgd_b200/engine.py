@@ -247,9 +247,12 @@ class Conditioning:
     """Everything that depends only on (timestep, added_time_ids, context): computed once per forward with the
     fp32 small-linear kernel, consumed as GEMM row-vectors / LayerNorm add-vectors."""
 
-    def __init__(self, emb: torch.Tensor, ctx: torch.Tensor):
+    def __init__(self, emb: torch.Tensor, ctx: torch.Tensor, ctx_t: Optional[torch.Tensor] = None):
         self.emb = emb          # fp32 [B, 4*C0]  (time + added-time embedding, reference ...controlnet.py:406-419)
         self.ctx = ctx          # fp32 [B, L, D]
+        # contexts the TEMPORAL cross-attention indexes (diffusers 0.27.2 picks ctx[row % B_total], SURVEY F8): the
+        # local batch normally; every CFG half's context when the pair is split across two GPUs
+        self.ctx_t = ctx if ctx_t is None else ctx_t
 
     def temb(self, w, b):       # time_emb_proj(SiLU(emb)) -> [B, Cout]
         return ops.small_linear(self.emb, w, b, act_in=SL_SILU)
@@ -257,6 +260,10 @@ class Conditioning:
     def cross_vec(self, pc: PackedCross):
         """KV-length-1 cross-attention == to_out(to_v(ctx)) for every query (softmax over one key is 1)."""
         v = ops.small_linear(self.ctx[:, 0].contiguous(), pc.wv)
+        return ops.small_linear(v, pc.wo, pc.bo)
+
+    def cross_vec_t(self, pc: PackedCross):
+        v = ops.small_linear(self.ctx_t[:, 0].contiguous(), pc.wv)
         return ops.small_linear(v, pc.wo, pc.bo)
 
 
@@ -329,8 +336,12 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
     t = dense(a, p.t_out, res1=t, out_f32=True)
     if kv1:
-        n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec(p.t_cross),
-                          rv=g.rv(tctx_mode), sum_out=t)
+        if cond.ctx_t is cond.ctx:
+            n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec(p.t_cross),
+                              rv=g.rv(tctx_mode), sum_out=t)
+        else:   # CFG pair split: index the full set of contexts exactly as the unsplit B_total batch would
+            n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
+                              rv=(tctx_mode, g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
     else:
         if tctx_mode != RV_BATCH and g.B > 1:
             raise NotImplementedError("temporal cross-attention with KV length > 1 needs time_context_order="

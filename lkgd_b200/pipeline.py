@@ -83,7 +83,7 @@ class StableVideoDiffusionPipeline:
                 fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
                 num_videos_per_prompt: int = 1, controlnet_condition: Optional[torch.Tensor] = None,
                 controlnet_cond_scale: float = 1.0, domain_features: Optional[torch.Tensor] = None,
-                flow_features: Optional[torch.Tensor] = None) -> dict:
+                flow_features: Optional[torch.Tensor] = None, cfg_pair=None) -> dict:
         """Everything ``__call__`` does before the loop (reference :475-558): validates, builds added-time ids,
         timesteps, the frame-wise guidance ramp, and moves the conditioning to the device.  Returns the loop state
         consumed by ``denoise_step``."""
@@ -114,7 +114,9 @@ class StableVideoDiffusionPipeline:
                 cc = cc.unsqueeze(0)
             cc = torch.cat([cc] * 2) if do_cfg else cc      # reference :547-550 duplicates unconditionally (D3)
             controlnet_condition = cc.to(device=device, dtype=torch.float32)
-        return dict(S=S * num_videos_per_prompt, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
+        if cfg_pair is not None and (not do_cfg or controlnet_condition is not None):
+            raise ValueError("cfg_pair needs classifier-free guidance and (for now) no ControlNet")
+        return dict(cfg_pair=cfg_pair, S=S * num_videos_per_prompt, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
                     w=image_latents.shape[-1], do_cfg=do_cfg, added_time_ids=added_time_ids,
                     guidance=guidance.reshape(-1).to(torch.float32).contiguous(),
                     image_latents=image_latents.to(device=device, dtype=torch.float32).contiguous(),
@@ -132,9 +134,20 @@ class StableVideoDiffusionPipeline:
         sched.index_for(i)
         sigma = float(sched._sigmas_host[i])
         t = float(sched._timesteps_host[i])
+        scale = float(1.0 / np.sqrt(np.float32(sigma) ** 2 + 1))
+        pair = st.get("cfg_pair")
+        if pair is not None:
+            # CFG pair split (lkgd_b200/distributed.py): this rank runs one half of [uncond | cond] with batch S, then
+            # the two halves' predictions are exchanged once and both ranks take the fused CFG + Euler step
+            lo, hi = pair.batch_slice(st["S"])
+            x = ops.pack_input(latents, scale, st["image_latents"][lo:hi].contiguous(), N=st["S"], Cpad=pk.cin_pad)
+            g = Geom(st["S"], st["F"], st["h"], st["w"])
+            rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
+                                       added_time_ids=st["added_time_ids"], batch_slice=(lo, hi))
+            rows = pair.exchange(rows)
+            return sched.step_cfg_rows(rows, st["guidance"], latents, cfg=True, want_v=want_v)
         # CFG duplication + scale_model_input + concat(image_latents) + layout, one kernel (:579-584)
-        x = ops.pack_input(latents, float(1.0 / np.sqrt(np.float32(sigma) ** 2 + 1)), st["image_latents"],
-                           N=st["n_batch"], Cpad=pk.cin_pad)
+        x = ops.pack_input(latents, scale, st["image_latents"], N=st["n_batch"], Cpad=pk.cin_pad)
         g = Geom(st["n_batch"], st["F"], st["h"], st["w"])
         kw = {}
         if st["controlnet_condition"] is not None:
@@ -153,14 +166,14 @@ class StableVideoDiffusionPipeline:
                  num_videos_per_prompt: int = 1, generator=None, latents: Optional[torch.Tensor] = None,
                  controlnet_condition: Optional[torch.Tensor] = None, controlnet_cond_scale: float = 1.0,
                  domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
-                 output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
+                 cfg_pair=None, output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
                  return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False):
         if output_type != "latent":
             raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
                              "VAE of your choice (SURVEY.md section 8f, N1)")
         st = self.prepare(image_embeddings, image_latents, num_frames, num_inference_steps, min_guidance_scale,
                           max_guidance_scale, fps, motion_bucket_id, noise_aug_strength, num_videos_per_prompt,
-                          controlnet_condition, controlnet_cond_scale, domain_features, flow_features)
+                          controlnet_condition, controlnet_cond_scale, domain_features, flow_features, cfg_pair)
         device = self.unet.device
         latents = self.prepare_latents(st["S"], st["F"], self.unet.config.in_channels, st["h"], st["w"],
                                        torch.float32, device, generator, latents).to(torch.float32).contiguous()

@@ -292,16 +292,32 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor, *extra,
                        down_block_additional_residuals=None, mid_block_additional_residual=None,
-                       added_time_ids: torch.Tensor = None) -> torch.Tensor:
+                       added_time_ids: torch.Tensor = None, batch_slice: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """Engine-layout forward.  ``x``: bf16 channels-last rows [B*F*H*W, 64] (input channels zero-padded to 64,
-        see ``ops.pack_input``).  Returns the fp32 channels-last prediction [B*F*H*W, out_channels]."""
+        see ``ops.pack_input``).  Returns the fp32 channels-last prediction [B*F*H*W, out_channels].
+
+        ``batch_slice=(lo, hi)``: ``x`` holds only rows ``lo:hi`` of the batch that ``encoder_hidden_states`` /
+        ``added_time_ids`` (and the LKGD features) describe - the CFG pair split across two GPUs.  The
+        conditioning is computed for the whole batch (it is microscopic) so that the temporal cross-attention can
+        index every half's context exactly like the unsplit reference batch does (diffusers 0.27.2 quirk F8)."""
         if added_time_ids is None:
             raise ValueError("added_time_ids is required")
         pk = self.packed()
-        if encoder_hidden_states.shape[0] != g.B or added_time_ids.shape[0] != g.B:
+        ctx_all = self._context(encoder_hidden_states, *extra)
+        ids = added_time_ids.to(x.device)
+        ctx_t = None
+        if batch_slice is not None:
+            lo, hi = batch_slice
+            if hi - lo != g.B or hi > encoder_hidden_states.shape[0]:
+                raise ValueError("batch_slice does not match the packed sample")
+            if pk.tctx_mode != 3 and g.HW % 2 and ctx_all.shape[0] > 1:     # RV_BATCH == 3
+                raise ValueError("the split batch needs an even number of latent pixels (0.27.2 context order)")
+            ctx_t = ctx_all if pk.tctx_mode != 3 else None
+            ctx_all, ids = ctx_all[lo:hi].contiguous(), ids[lo:hi].contiguous()
+        if ctx_all.shape[0] != g.B or ids.shape[0] != g.B:
             raise ValueError("encoder_hidden_states / added_time_ids batch does not match sample")
-        emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
-        cond = Conditioning(emb, self._context(encoder_hidden_states, *extra))
+        emb = pk.time_embedding(self._timestep_tensor(timestep, x), ids)
+        cond = Conditioning(emb, ctx_all, ctx_t)
         x, skips, geoms, gm = pk.encoder(x, g, cond)
         if mid_block_additional_residual is not None:
             ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)

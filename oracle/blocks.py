@@ -184,6 +184,10 @@ class TransformerSpatioTemporalModel(nn.Module):
         inner = heads * dim_head
         self.in_channels = in_channels
         self.time_context_order = time_context_order
+        # test hook for the CFG-pair split (tests/test_distributed_cpu.py): (first-frame contexts of the WHOLE batch
+        # [B_total, L, D], index of this half's first batch element) - rows then index the contexts exactly as the
+        # unsplit batch would under the 0.27.2 order
+        self.cfg_split = None
         self.norm = nn.GroupNorm(32, in_channels, eps=1e-6)
         self.proj_in = nn.Linear(in_channels, inner)
         self.transformer_blocks = nn.ModuleList(
@@ -207,6 +211,10 @@ class TransformerSpatioTemporalModel(nn.Module):
         else:
             raise ValueError(self.time_context_order)
         time_context = time_context.reshape(h * w * b, ctx_first.shape[1], ctx.shape[-1])
+        if self.cfg_split is not None and self.time_context_order == "hw_major_0272":
+            full, b0 = self.cfg_split
+            rows = torch.arange(b * h * w, device=x.device) + b0 * h * w          # row index inside the unsplit batch
+            time_context = full[rows % full.shape[0]]
 
         res = x
         x = self.norm(x)

@@ -1,0 +1,54 @@
+"""torchrun worker (2 ranks, NCCL): the CFG pair split across two GPUs must reproduce the single-GPU unsplit step.
+Launched by tests/test_multigpu_gpu.py; prints one JSON line on rank 0."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+from golden_util import REDUCED4, SCHED, fill_seeded_, rel, seeded_tensor  # noqa: E402
+
+
+def main():
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from lkgd_b200.distributed import CFGPair
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionModel
+    pair = CFGPair.from_world()
+    res = {}
+    for name, cls, cfg in (("plain_0272", UNetSpatioTemporalConditionControlNetModel, REDUCED4),
+                           ("plain_b_major", UNetSpatioTemporalConditionControlNetModel,
+                            dict(REDUCED4, time_context_order="b_major")),
+                           ("lkgd", UNetSpatioTemporalConditionModel, dict(REDUCED4, cross_attention_dim=1024))):
+        F_, H_, W_ = 4, 16, 16
+        xd = cfg["cross_attention_dim"]
+        unet = fill_seeded_(cls(**cfg)).to(dev)
+        img = torch.cat([torch.zeros(1, F_, 4, H_, W_), seeded_tensor("d/img", (1, 1, 4, H_, W_)).repeat(1, F_, 1, 1, 1)])
+        emb = torch.cat([torch.zeros(1, 1, xd), seeded_tensor("d/emb", (1, 1, xd))])
+        kw = {}
+        if name == "lkgd":
+            kw = dict(domain_features=seeded_tensor("d/dom", (1, 1, 1000)), flow_features=seeded_tensor("d/flow", (1, 1, 1000)))
+        lat = seeded_tensor("d/lat", (1, F_, 4, H_, W_))
+        pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED))
+        split = pipe(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, cfg_pair=pair,
+                     return_dict=False, **kw)
+        pipe2 = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED))
+        whole = pipe2(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, return_dict=False, **kw)
+        other = split.clone()
+        dist.broadcast(other, src=0)
+        res[name] = dict(split_vs_unsplit=rel(split, whole), replicated=bool(torch.equal(other, split)))
+    if rank == 0:
+        print("RESULT " + json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
