@@ -252,12 +252,45 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------- temporal
+// One warp per (batch, pixel, head): the F <= 32 frames of that pixel are a 32 x D problem - far too small for a
+// tcgen05 tile, HBM-bound as a whole (reads q|k|v once, writes o once).  cp.async pulls the three F x D tiles out of
+// the fused projection in place (frame stride HW*3C, 16-byte pieces coalesced along d), ldmatrix + mma.sync
+// m16n8k16 do S = Q K^T and O = P V with the softmax between them in the accumulator fragments, and the result
+// leaves through smem as full 16-byte row pieces.
+template <int D>
+struct TAttn {
+  static constexpr int P = D / 8;            // 16-byte chunks per row
+  static constexpr int RPL = 8 / P > 0 ? 8 / P : 1;
+  static constexpr int ROW = D * 2;          // row pitch in bytes
+  static constexpr int TILE = 32 * ROW;      // one 32 x D tile
+  __device__ static __forceinline__ uint32_t off(int row, int chunk) {   // XOR swizzle: ldmatrix conflict-free
+    return static_cast<uint32_t>(row * ROW + ((chunk ^ ((row / RPL) & (P - 1))) << 4));
+  }
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
 template <int D>
 __global__ void __launch_bounds__(128) attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out, int B, int F, int HW,
-                                                            int heads, float scale) {
-  __shared__ __align__(16) __nv_bfloat16 sK[4][32][D];
-  __shared__ __align__(16) __nv_bfloat16 sV[4][32][D];
+                                                            int heads, float scale_log2) {
+  using T = TAttn<D>;
+  extern __shared__ __align__(128) uint8_t tsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seq = (long long)blockIdx.x * 4 + warp;
   const long long total = (long long)B * HW * heads;
@@ -267,67 +300,128 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __nv_bfloat16*
   const int b = (int)(seq / ((long long)heads * HW));
   const int C = heads * D;
   const size_t ld = (size_t)3 * C;
-  constexpr int VPR = D / 8;  // 16-byte vectors per row
+  const uint32_t sQ = smem_u32(tsm + warp * 3 * T::TILE), sK = sQ + T::TILE, sV = sK + T::TILE;
   const __nv_bfloat16* base = qkv + ((size_t)b * F * HW + pix) * ld + head * D;
-  for (int idx = lane; idx < F * VPR; idx += 32) {
-    const int j = idx / VPR, v = idx % VPR;
-    const __nv_bfloat16* row = base + (size_t)j * HW * ld;
-    *reinterpret_cast<uint4*>(&sK[warp][j][v * 8]) = __ldg(reinterpret_cast<const uint4*>(row + C + v * 8));
-    *reinterpret_cast<uint4*>(&sV[warp][j][v * 8]) = __ldg(reinterpret_cast<const uint4*>(row + 2 * C + v * 8));
+  // ---- global -> smem: 32 rows (frames, zero-filled beyond F) x P chunks per tile
+#pragma unroll
+  for (int j = 0; j < T::P; ++j) {
+    const int i = lane + 32 * j;
+    const int row = i / T::P, ch = i % T::P;
+    const bool ok = row < F;
+    const __nv_bfloat16* src = base + (ok ? (size_t)row * HW * ld + ch * 8 : 0);
+    const uint32_t o = T::off(row, ch);
+    cp_async_16(sQ + o, src, ok ? 16u : 0u);
+    cp_async_16(sK + o, src + C, ok ? 16u : 0u);
+    cp_async_16(sV + o, src + 2 * C, ok ? 16u : 0u);
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncwarp();
-  if (lane >= F) return;
-  float q[D];
-  {
-    const __nv_bfloat16* row = base + (size_t)lane * HW * ld;
+  // ---- S = Q K^T : 2 m-tiles (query frames) x 4 n-tiles (key frames)
+  float sacc[2][4][4];
 #pragma unroll
-    for (int v = 0; v < VPR; ++v) {
-      float f[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row + v * 8)), f);
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[v * 8 + i] = f[i] * scale;
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    uint32_t a[2][4], kb[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) ldsm_x4(sQ + T::off(mt * 16 + (lane & 15), ks * 2 + (lane >> 4)), a[mt]);
+#pragma unroll
+    for (int np = 0; np < 2; ++np)     // two key n-tiles per ldmatrix.x4: {nt0 k-lo, nt0 k-hi, nt1 k-lo, nt1 k-hi}
+      ldsm_x4(sK + T::off(np * 16 + (lane >> 4) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)), kb[np]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(sacc[mt][nt], a[mt], kb[nt >> 1][(nt & 1) * 2], kb[nt >> 1][(nt & 1) * 2 + 1]);
+  }
+  // ---- softmax over the key frames (columns nt*8 + 2*(lane%4) + {0,1}); rows lane/4 and lane/4 + 8 of each m-tile
+  uint32_t pa[2][2][4];     // P as bf16 A fragments: [m-tile][k-step of 16 keys]
+  float inv_l[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = nt * 8 + 2 * (lane & 3) + e;
+          if (key >= F) sacc[mt][nt][hr * 2 + e] = -INFINITY;
+          mx = fmaxf(mx, sacc[mt][nt][hr * 2 + e]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float moff = mx * scale_log2;
+      float l = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = ex2f(fmaf(sacc[mt][nt][hr * 2 + e], scale_log2, -moff));
+          sacc[mt][nt][hr * 2 + e] = pv;
+          l += pv;
+        }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      inv_l[mt][hr] = 1.0f / l;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      pa[mt][kk][0] = pack_bf16x2(sacc[mt][2 * kk][0], sacc[mt][2 * kk][1]);
+      pa[mt][kk][1] = pack_bf16x2(sacc[mt][2 * kk][2], sacc[mt][2 * kk][3]);
+      pa[mt][kk][2] = pack_bf16x2(sacc[mt][2 * kk + 1][0], sacc[mt][2 * kk + 1][1]);
+      pa[mt][kk][3] = pack_bf16x2(sacc[mt][2 * kk + 1][2], sacc[mt][2 * kk + 1][3]);
     }
   }
-  float s[32];
-  float mx = -INFINITY;
+  // ---- O = P V : V tile is [key][d] = K x N row-major -> transposed ldmatrix
+  float oacc[2][D / 8][4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < F) {
-      float acc = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int t = 0; t < D; t += 2) {
-        const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sK[warp][j][t]));
-        acc = fmaf(q[t], kk.x, acc);
-        acc = fmaf(q[t + 1], kk.y, acc);
+    for (int nd = 0; nd < D / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[mt][nd][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+    for (int np = 0; np < D / 16; ++np) {   // {keys lo d0, keys hi d0, keys lo d1, keys hi d1}
+      uint32_t vb[4];
+      ldsm_x4_t(sV + T::off(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), np * 2 + (lane >> 4)), vb);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16_16816(oacc[mt][np * 2], pa[mt][kk], vb[0], vb[1]);
+        mma_bf16_16816(oacc[mt][np * 2 + 1], pa[mt][kk], vb[2], vb[3]);
       }
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
     }
   }
-  float l = 0.f;
-  float o[D];
+  // ---- normalise, stage through the (now free) Q tile, write full 16-byte pieces of each frame's row
+  __syncwarp();
 #pragma unroll
-  for (int t = 0; t < D; ++t) o[t] = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < F) {
-      const float pj = __expf(s[j] - mx);
-      l += pj;
+    for (int nd = 0; nd < D / 8; ++nd)
 #pragma unroll
-      for (int t = 0; t < D; t += 2) {
-        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sV[warp][j][t]));
-        o[t] = fmaf(pj, vv.x, o[t]);
-        o[t + 1] = fmaf(pj, vv.y, o[t + 1]);
+      for (int hr = 0; hr < 2; ++hr) {
+        const int row = mt * 16 + hr * 8 + (lane >> 2);
+        const uint32_t v = pack_bf16x2(oacc[mt][nd][hr * 2] * inv_l[mt][hr], oacc[mt][nd][hr * 2 + 1] * inv_l[mt][hr]);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + T::off(row, nd) + (lane & 3) * 4), "r"(v) : "memory");
       }
+  __syncwarp();
+  __nv_bfloat16* obase = out + ((size_t)b * F * HW + pix) * C + head * D;
+#pragma unroll
+  for (int j = 0; j < T::P; ++j) {
+    const int i = lane + 32 * j;
+    const int row = i / T::P, ch = i % T::P;
+    if (row < F) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sQ + T::off(row, ch)));
+      *reinterpret_cast<uint4*>(obase + (size_t)row * HW * C + ch * 8) = v;
     }
   }
-  const float inv = 1.0f / l;
-  __nv_bfloat16* orow = out + (((size_t)b * F + lane) * HW + pix) * C + head * D;
-#pragma unroll
-  for (int v = 0; v < VPR; ++v)
-    *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(
-        pack_bf16x2(o[v * 8] * inv, o[v * 8 + 1] * inv), pack_bf16x2(o[v * 8 + 2] * inv, o[v * 8 + 3] * inv),
-        pack_bf16x2(o[v * 8 + 4] * inv, o[v * 8 + 5] * inv), pack_bf16x2(o[v * 8 + 6] * inv, o[v * 8 + 7] * inv));
 }
 
 static int attn_tmap(CUtensorMap* tm, const void* base, int ld, int heads, int d, int N, int n_img) {
@@ -375,10 +469,17 @@ extern "C" int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const float sl2 = scale * 1.4426950408889634f;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_temporal_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * TAttn<64>::TILE);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr = true;
+  }
   switch (d) {
-    case 16: attn_temporal_kernel<16><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
-    case 32: attn_temporal_kernel<32><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
-    case 64: attn_temporal_kernel<64><<<grid, 128, 0, st>>>(x, o, B, F, HW, heads, scale); break;
+    case 16: attn_temporal_kernel<16><<<grid, 128, 4 * 3 * TAttn<16>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
+    case 32: attn_temporal_kernel<32><<<grid, 128, 4 * 3 * TAttn<32>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
+    case 64: attn_temporal_kernel<64><<<grid, 128, 4 * 3 * TAttn<64>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
     default: return LKGD_ESHAPE;
   }
   return launch_epilogue();
