@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 1
+#define LKGD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -105,6 +105,7 @@ typedef struct lkgd_gemm_args {
   int32_t n_store;    /* store only columns < n_store (0 = all)               */
   int32_t res1_f32;   /* 1: res1 is fp32 (the residual stream is kept in fp32) */
   int32_t res2_f32;
+  int32_t rv_ld;      /* row pitch of rowvec in floats (0 = contiguous: N, or N/2 for GEGLU); multiple of 4 */
 } lkgd_gemm_args;
 
 LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);
@@ -127,13 +128,14 @@ LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t 
                    void* workspace, size_t ws_bytes, void* stream);
 
 /* LayerNorm over the last axis of a [M, C] bf16 matrix (C <= 2048, C % 8 == 0) with optional fused
- *   s = x + addvec[g(m)]   (fp32 addvec [G, C]; frame positional embedding or KV-length-1 cross-attention term)
+ *   s = x + addvec[g(m)]   (fp32 addvec [G, C], row pitch addvec_ld floats (0 = C); frame positional embedding or
+ *                           KV-length-1 cross-attention term)
  * sum_out (same dtype as x: bf16, or fp32 when x_f32 = 1; may alias x, may be NULL) receives s; out (bf16) receives
  * LN(s)*gamma+beta.
  * Replaces nn.LayerNorm norm1/norm2/norm3/norm_in (patch/patch.py:415-416,529-530,555-556,599,610,664,670). */
 LKGD_API int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
-                   const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B, int32_t x_f32,
-                   void* sum_out, void* out, void* stream);
+                   const float* addvec, int32_t addvec_ld, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B,
+                   int32_t x_f32, void* sum_out, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Spatial self-attention (and general cross-attention), flash-style on tcgen05: per (image, head)

@@ -73,7 +73,7 @@ __global__ void gemm_check_kernel(const lkgd_gemm_args a) {
   } else {
     v = chk_dot(a, m, n_out) + (a.bias ? a.bias[n_out] : 0.f);
   }
-  if (a.rowvec) v += a.rowvec[(size_t)chk_rowvec_index(a.rv_mode, m, max(a.rv_HW, 1), max(a.rv_F, 1), max(a.rv_B, 1)) * n_cols + n_out];
+  if (a.rowvec) v += a.rowvec[(size_t)chk_rowvec_index(a.rv_mode, m, max(a.rv_HW, 1), max(a.rv_F, 1), max(a.rv_B, 1)) * (a.rv_ld > 0 ? a.rv_ld : n_cols) + n_out];
   if (a.act == LKGD_ACT_SILU) v = silu_f(v);
   v *= a.s0;
   if (a.res1)

@@ -76,7 +76,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   const long long m = tile_row(p, tc, lane_base + lane);
   const float* rv = nullptr;
   if (p.rowvec != nullptr && m >= 0)
-    rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * n_cols;
+    rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * p.rv_ld;
 
   // coalesced-side geometry, fixed for the tile: row pointers (nullptr = row outside the tensor) and smem offsets
   char* orow[PO];
@@ -156,7 +156,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       }
     }
     if (use_rv) {                                  // per-row vector (time embedding / context term), L1/L2 resident
-      if (n_out + CW <= n_cols && (n_cols & 3) == 0) {
+      if (n_out + CW <= n_cols) {      // rv_ld % 4 == 0 and 16-byte aligned base: vector loads
 #pragma unroll
         for (int j = 0; j < CW; j += 4) {
           const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv + n_out + j));

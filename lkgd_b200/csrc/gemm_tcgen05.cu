@@ -40,7 +40,7 @@ struct GemmParams {
   // epilogue
   const float* bias;
   const float* rowvec;
-  int rv_mode, rv_HW, rv_F, rv_B;
+  int rv_mode, rv_HW, rv_F, rv_B, rv_ld;
   int act;
   float s0, s1, s2;
   const void* res1;
@@ -349,6 +349,8 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
   p.bias = a->bias; p.rowvec = a->rowvec;
   p.rv_mode = a->rowvec ? a->rv_mode : LKGD_RV_NONE;
   p.rv_HW = a->rv_HW > 0 ? a->rv_HW : 1; p.rv_F = a->rv_F > 0 ? a->rv_F : 1; p.rv_B = a->rv_B > 0 ? a->rv_B : 1;
+  p.rv_ld = a->rv_ld > 0 ? a->rv_ld : (geglu ? a->N / 2 : a->N);
+  if (a->rowvec && p.rv_ld % 4) return LKGD_EALIGN;
   p.act = a->act; p.s0 = a->s0; p.s1 = a->s1; p.s2 = a->s2;
   p.res1 = a->res1; p.ldr1 = a->ldr1; p.res1_f32 = a->res1_f32;
   p.res2 = a->res2; p.ldr2 = a->ldr2; p.res2_f32 = a->res2_f32;

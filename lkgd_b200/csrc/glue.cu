@@ -11,32 +11,48 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-// one warp per output column n; loops over the (few) rows m
+// one warp per output column n; rows m in groups of 4; 128-bit loads when K % 4 == 0 and the pitches allow
 __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
                                     const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int N, int K,
-                                    int act_in, int act_out) {
+                                    int act_in, int act_out, int vec) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   const float* w = W + (size_t)n * K;
-  for (int m0 = 0; m0 < M; m0 += 8) {
-    float acc[8];
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+      const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll 4
+      for (int k = lane; k < K / 4; k += 32) {
+        const float4 wv = __ldg(w4 + k);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(w + k);
+        for (int i = 0; i < 4; ++i)
+          if (m0 + i < M) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)(m0 + i) * ldx) + k);
+            acc[i] = fmaf(act_apply(xv.x, act_in), wv.x, acc[i]);
+            acc[i] = fmaf(act_apply(xv.y, act_in), wv.y, acc[i]);
+            acc[i] = fmaf(act_apply(xv.z, act_in), wv.z, acc[i]);
+            acc[i] = fmaf(act_apply(xv.w, act_in), wv.w, acc[i]);
+          }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(w + k);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (m0 + i < M) acc[i] = fmaf(act_apply(__ldg(x + (size_t)(m0 + i) * ldx + k), act_in), wv, acc[i]);
+        for (int i = 0; i < 4; ++i)
+          if (m0 + i < M) acc[i] = fmaf(act_apply(__ldg(x + (size_t)(m0 + i) * ldx + k), act_in), wv, acc[i]);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
     if (lane == 0) {
-      for (int i = 0; i < 8 && m0 + i < M; ++i)
-        y[(size_t)(m0 + i) * ldy + n] = act_apply(acc[i] + (b ? b[n] : 0.f), act_out);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (m0 + i < M) y[(size_t)(m0 + i) * ldy + n] = act_apply(acc[i] + (b ? b[n] : 0.f), act_out);
     }
   }
 }
@@ -244,7 +260,8 @@ static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t
 extern "C" int lkgd_small_linear(const float* x, int32_t ldx, const float* W, const float* b, float* y, int32_t ldy,
                                  int32_t M, int32_t N, int32_t K, int32_t act_in, int32_t act_out, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || M > 4096) return LKGD_ESHAPE;
-  small_linear_kernel<<<blocks_for(N, 8), 256, 0, ST(stream)>>>(x, ldx, W, b, y, ldy, M, N, K, act_in, act_out);
+  const int vec = (K % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(W);
+  small_linear_kernel<<<blocks_for(N, 8), 256, 0, ST(stream)>>>(x, ldx, W, b, y, ldy, M, N, K, act_in, act_out, vec);
   return launch_epilogue();
 }
 

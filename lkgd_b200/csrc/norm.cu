@@ -126,8 +126,8 @@ template <int NV, bool XF32>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, int M, int C,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
-                                                        const float* __restrict__ addvec, int rv_mode, int rv_HW,
-                                                        int rv_F, int rv_B, void* sum_out_v,
+                                                        const float* __restrict__ addvec, int addvec_ld, int rv_mode,
+                                                        int rv_HW, int rv_F, int rv_B, void* sum_out_v,
                                                         __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   float f[NV][8];
   const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(xv) + row * C;   // XF32 == false
   const float* xr32 = reinterpret_cast<const float*>(xv) + row * C;                 // XF32 == true
-  const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * C : nullptr;
+  const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * addvec_ld : nullptr;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -256,8 +256,8 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
 }
 
 extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps,
-                              const float* addvec, int32_t rv_mode, int32_t rv_HW, int32_t rv_F, int32_t rv_B,
-                              int32_t x_f32, void* sum_out, void* out, void* stream) {
+                              const float* addvec, int32_t addvec_ld, int32_t rv_mode, int32_t rv_HW, int32_t rv_F,
+                              int32_t rv_B, int32_t x_f32, void* sum_out, void* out, void* stream) {
   if (M <= 0 || C <= 0 || C % 8 || C > LN_MAXV * 256) return LKGD_ESHAPE;
   if (!aligned16(x) || !aligned16(out) || (sum_out && !aligned16(sum_out)) || (addvec && !aligned16(addvec)) ||
       !aligned16(gamma) || !aligned16(beta))
@@ -266,17 +266,19 @@ extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* 
   const int rows_per_cta = 8;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
   const int nv = (C / 8 + 31) / 32;
+  if (addvec_ld <= 0) addvec_ld = C;
+  if (addvec_ld % 4) return LKGD_EALIGN;
   if (rv_HW <= 0) rv_HW = 1;
   if (rv_F <= 0) rv_F = 1;
   if (rv_B <= 0) rv_B = 1;
 #define LN_LAUNCH(NV)                                                                                              \
   do {                                                                                                             \
     if (x_f32)                                                                                                     \
-      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, rv_mode, rv_HW, rv_F,    \
-                                                       rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));      \
+      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, rv_HW,\
+                                                       rv_F, rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));      \
     else                                                                                                           \
-      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, rv_mode, rv_HW, rv_F,   \
-                                                        rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));     \
+      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode,      \
+                                                        rv_HW, rv_F, rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));     \
   } while (0)
   switch (nv) {
     case 1: LN_LAUNCH(1); break;

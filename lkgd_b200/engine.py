@@ -160,8 +160,12 @@ class PackedCross:
 
     def __init__(self, attn: M.Attention):
         self.heads, self.d = attn.heads, attn.dim_head
-        self.wv, _ = _merged_weight(attn.to_v)
-        self.wo, self.bo = _merged_weight(attn.to_out[0])
+        wv, _ = _merged_weight(attn.to_v)
+        wo, self.bo = _merged_weight(attn.to_out[0])
+        # softmax over ONE key is exactly 1, so attn2(x, ctx) = to_out(to_v(ctx)) = (Wo Wv) ctx + bo for every query:
+        # one [C, D] matrix per cross-attention, product taken in fp64
+        self.wov = (wo.double() @ wv.double()).float().contiguous()
+        self.off = 0                # column offset inside the batched cross-vector matrix (set by PackedUNet)
         self._attn = attn
         self._general = None
 
@@ -170,8 +174,10 @@ class PackedCross:
             a = self._attn
             wq, _ = _merged_weight(a.to_q)
             wk, _ = _merged_weight(a.to_k)
-            self._general = (wq.to(bf16).contiguous(), torch.cat([wk, self.wv], 0).to(bf16).contiguous(),
-                             self.wo.to(bf16).contiguous())
+            wv, _ = _merged_weight(a.to_v)
+            wo, _ = _merged_weight(a.to_out[0])
+            self._general = (wq.to(bf16).contiguous(), torch.cat([wk, wv], 0).to(bf16).contiguous(),
+                             wo.to(bf16).contiguous())
         return self._general
 
 
@@ -244,33 +250,38 @@ def dense(x: torch.Tensor, d: Dense, **kw) -> torch.Tensor:
 
 
 class Conditioning:
-    """Everything that depends only on (timestep, added_time_ids, context): computed once per forward with the
-    fp32 small-linear kernel, consumed as GEMM row-vectors / LayerNorm add-vectors."""
+    """Everything that depends only on (timestep, added_time_ids, context), computed ONCE per forward by three
+    batched fp32 mat-vec launches over weights concatenated at pack time, and consumed as GEMM row-vectors /
+    LayerNorm add-vectors (column slices of the batched results):
+      * every resblock's ``time_emb_proj(SiLU(emb))`` (44 projections of the same input);
+      * every KV-length-1 cross-attention term ``to_out(to_v(ctx))``, spatial and temporal."""
 
-    def __init__(self, emb: torch.Tensor, ctx: torch.Tensor, ctx_t: Optional[torch.Tensor] = None):
+    def __init__(self, pk: "PackedUNet", emb: torch.Tensor, ctx: torch.Tensor, ctx_t: Optional[torch.Tensor] = None):
         self.emb = emb          # fp32 [B, 4*C0]  (time + added-time embedding, reference ...controlnet.py:406-419)
         self.ctx = ctx          # fp32 [B, L, D]
         # contexts the TEMPORAL cross-attention indexes (diffusers 0.27.2 picks ctx[row % B_total], SURVEY F8): the
         # local batch normally; every CFG half's context when the pair is split across two GPUs
         self.ctx_t = ctx if ctx_t is None else ctx_t
+        self.temb_all = ops.small_linear(emb, pk.temb_w, pk.temb_b, act_in=SL_SILU)
+        self.xs_all = self.xt_all = None
+        if ctx.shape[1] == 1 and pk.xs_w is not None:
+            self.xs_all = ops.small_linear(ctx[:, 0].contiguous(), pk.xs_w, pk.xs_b)
+            self.xt_all = ops.small_linear(self.ctx_t[:, 0].contiguous(), pk.xt_w, pk.xt_b)
 
-    def temb(self, w, b):       # time_emb_proj(SiLU(emb)) -> [B, Cout]
-        return ops.small_linear(self.emb, w, b, act_in=SL_SILU)
+    def temb(self, off: int, n: int):       # time_emb_proj(SiLU(emb)) -> [B, Cout] (view)
+        return self.temb_all[:, off:off + n]
 
-    def cross_vec(self, pc: PackedCross):
-        """KV-length-1 cross-attention == to_out(to_v(ctx)) for every query (softmax over one key is 1)."""
-        v = ops.small_linear(self.ctx[:, 0].contiguous(), pc.wv)
-        return ops.small_linear(v, pc.wo, pc.bo)
+    def cross_vec(self, pc: PackedCross):   # spatial attn2 term -> [B, C] (view)
+        return self.xs_all[:, pc.off:pc.off + pc.wov.shape[0]]
 
     def cross_vec_t(self, pc: PackedCross):
-        v = ops.small_linear(self.ctx_t[:, 0].contiguous(), pc.wv)
-        return ops.small_linear(v, pc.wo, pc.bo)
+        return self.xt_all[:, pc.off:pc.off + pc.wov.shape[0]]
 
 
 def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor], g: Geom, cond: Conditioning):
     """x (and skip) are fp32 stream tensors; returns the fp32 block output."""
-    temb_s = cond.temb(p.temb_w, p.temb_b)
-    temb_t = cond.temb(p.ttemb_w, p.ttemb_b)
+    temb_s = cond.temb(p.off_s, p.cout)
+    temb_t = cond.temb(p.off_t, p.cout)
     h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
     h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH),
                  out_f32=True)        # only GroupNorm reads it: keep fp32 instead of rounding twice
@@ -336,12 +347,9 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
     t = dense(a, p.t_out, res1=t, out_f32=True)
     if kv1:
-        if cond.ctx_t is cond.ctx:
-            n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec(p.t_cross),
-                              rv=g.rv(tctx_mode), sum_out=t)
-        else:   # CFG pair split: index the full set of contexts exactly as the unsplit B_total batch would
-            n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
-                              rv=(tctx_mode, g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
+        # under a CFG pair split ctx_t holds every half's context: index it exactly as the unsplit batch would
+        n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
+                          rv=(tctx_mode, g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
     else:
         if tctx_mode != RV_BATCH and g.B > 1:
             raise NotImplementedError("temporal cross-attention with KV length > 1 needs time_context_order="
@@ -387,10 +395,41 @@ class PackedUNet:
             self.norm_out = Norm.of(unet.conv_norm_out)
             self.cout = cfg.out_channels
             self.conv_out_w, self.conv_out_b = _conv3x3_weight(unet.conv_out, cout_pad=max(32, (self.cout + 15) // 16 * 16))
+        self._batch_conditioning()
         order = getattr(cfg, "time_context_order", "hw_major_0272")
         if order not in ("hw_major_0272", "b_major"):
             raise ValueError(f"time_context_order must be 'hw_major_0272' or 'b_major', got {order}")
         self.tctx_mode = RV_TCTX_0272 if order == "hw_major_0272" else RV_BATCH
+
+    def _batch_conditioning(self):
+        """Concatenates every time_emb_proj and every fused KV=1 cross-attention matrix so that one launch each
+        serves the whole forward; the per-block tensors become views of the concatenation."""
+        res = [r for blk in self.down for r in blk[0]] + list(self.mid[0]) + [r for blk in self.up for r in blk[0]]
+        tr = [a for blk in self.down if blk[1] for a in blk[1]] + list(self.mid[1]) + \
+             [a for blk in self.up if blk[1] for a in blk[1]]
+        ws, bs, off = [], [], 0
+        for r in res:
+            r.off_s, r.off_t = off, off + r.cout
+            ws += [r.temb_w, r.ttemb_w]
+            bs += [r.temb_b, r.ttemb_b]
+            off += 2 * r.cout
+            r.temb_w = r.temb_b = r.ttemb_w = r.ttemb_b = None
+        self.temb_w, self.temb_b = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
+        self.xs_w = self.xs_b = self.xt_w = self.xt_b = None
+        if tr:
+            for name, key in (("xs", "s_cross"), ("xt", "t_cross")):
+                off, w, b = 0, [], []
+                for t in tr:
+                    pc = getattr(t, key)
+                    pc.off = off
+                    w.append(pc.wov)
+                    b.append(pc.bo)
+                    off += pc.wov.shape[0]
+                setattr(self, name + "_w", torch.cat(w, 0).contiguous())
+                setattr(self, name + "_b", torch.cat(b, 0).contiguous())
+                for t in tr:                     # keep only the shape; the matrix lives in the concatenation
+                    pc = getattr(t, key)
+                    pc.wov = getattr(self, name + "_w")[pc.off:pc.off + pc.wov.shape[0]]
 
     # ------------------------------------------------------------------------------------------
     def time_embedding(self, timestep: torch.Tensor, added_time_ids: torch.Tensor) -> torch.Tensor:

@@ -100,11 +100,12 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
         if r is not None and (r.dtype not in (bf16, torch.float32) or r.dim() != 2 or r.shape[0] != M
                               or r.stride(1) != 1):
             raise ValueError("residuals must be bf16 or fp32 [M, >=n] row-major")
-    if rowvec is not None and (rowvec.dtype != torch.float32 or rowvec.shape[-1] != n_cols
-                               or not rowvec.is_contiguous()):
-        raise ValueError("rowvec must be contiguous fp32 [G, n]")
+    if rowvec is not None and (rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.shape[-1] != n_cols
+                               or rowvec.stride(1) != 1):
+        raise ValueError("rowvec must be fp32 [G, n] with unit column stride (column slices of a wider matrix allowed)")
     a.bias, a.rowvec = _ptr(bias), _ptr(rowvec)
     a.rv_mode, a.rv_HW, a.rv_F, a.rv_B = rv
+    a.rv_ld = rowvec.stride(0) if rowvec is not None else 0
     a.act, a.s0 = act, s0
     a.res1, a.ldr1, a.s1 = _ptr(res1), (res1.stride(0) if res1 is not None else 0), s1
     a.res2, a.ldr2, a.s2 = _ptr(res2), (res2.stride(0) if res2 is not None else 0), s2
@@ -169,14 +170,15 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if sum_out is not None and (sum_out.dtype != x.dtype or not sum_out.is_contiguous()):
         raise ValueError("layernorm: sum_out must be contiguous and of x's dtype")
     M, Cn = x.shape
-    if addvec is not None and (addvec.dtype != torch.float32 or addvec.shape[-1] != Cn or not addvec.is_contiguous()):
-        raise ValueError("layernorm: addvec must be contiguous fp32 [G, C]")
+    if addvec is not None and (addvec.dtype != torch.float32 or addvec.dim() != 2 or addvec.shape[-1] != Cn
+                               or addvec.stride(1) != 1):
+        raise ValueError("layernorm: addvec must be fp32 [G, C] with unit column stride")
     if out is None:
         out = torch.empty((M, Cn), device=x.device, dtype=bf16)
     if L.PROF.enabled:
         L.PROF.meta = {"bytes": M * Cn * (x.element_size() + 2 + (x.element_size() if sum_out is not None else 0))}
     L.check(L.load().lkgd_layernorm(x.data_ptr(), M, Cn, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(addvec),
-                                    rv[0], rv[1], rv[2], rv[3], int(x.dtype == torch.float32), _ptr(sum_out),
+                                    addvec.stride(0) if addvec is not None else 0, rv[0], rv[1], rv[2], rv[3], int(x.dtype == torch.float32), _ptr(sum_out),
                                     out.data_ptr(), _stream()),
             "lkgd_layernorm")
     return out

@@ -317,7 +317,7 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
         if ctx_all.shape[0] != g.B or ids.shape[0] != g.B:
             raise ValueError("encoder_hidden_states / added_time_ids batch does not match sample")
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), ids)
-        cond = Conditioning(emb, ctx_all, ctx_t)
+        cond = Conditioning(pk, emb, ctx_all, ctx_t)
         x, skips, geoms, gm = pk.encoder(x, g, cond)
         if mid_block_additional_residual is not None:
             ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)
@@ -613,7 +613,7 @@ class ControlNetSDVModel(_Base):
         pk = self.packed()
         convs, zero = self._cn_pack()
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
-        cond = Conditioning(emb, encoder_hidden_states.to(torch.float32).contiguous())
+        cond = Conditioning(pk, emb, encoder_hidden_states.to(torch.float32).contiguous())
         stem_add = None
         if controlnet_cond is not None:
             if controlnet_cond.ndim != 5:
