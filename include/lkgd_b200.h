@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 2
+#define LKGD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -216,6 +216,86 @@ LKGD_API int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int3
 LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
                         float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W,
                         float sigma, float sigma_next, void* stream);
+
+/* ======================================================================================================
+ * Training step (LoRA fine-tuning): the backward of the path above.  Reference: train_models/train_svd_lora.py
+ * :1445-1689 - EDM preconditioning :1503-1530, loss :1651-1672, accelerator.backward :1683 (PyTorch autograd of the
+ * diffusers blocks), clip_grad_norm_ :1684-1686, AdamW :1225-1231, DDP gradient all-reduce :1300-1302.
+ * Data gradients of the GEMMs / convolutions reuse lkgd_gemm with transposed (and, for convolutions, tap-flipped)
+ * weights; the entries below are the remaining backward kernels.
+ * ====================================================================================================== */
+
+/* Spatial attention forward that also returns the log-sum-exp the backward needs:
+ * lse[img, head, row] = log2( sum_k 2^(s_k * scale * log2 e) )  (fp32, [n_img, heads, Nq]). */
+LKGD_API int lkgd_attention_lse(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                                void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq, int32_t Nk,
+                                float scale, float* lse, void* stream);
+/* Backward of O = softmax(Q K^T scale) V per (image, head), self-attention (Nq = Nk = N), d in {16,32,64}.
+ * o / dO share the pitch ldo; dq / dk / dv may be column slices of one fused [rows, 3C] gradient.
+ * workspace: lkgd_attention_bwd_workspace(n_img, heads, N) bytes. */
+LKGD_API size_t lkgd_attention_bwd_workspace(int32_t n_img, int32_t heads, int32_t N);
+LKGD_API int lkgd_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                                const void* o, const void* dO, int32_t ldo, const float* lse, void* dq, int32_t lddq,
+                                void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t n_img, int32_t heads, int32_t d,
+                                int32_t N, float scale, void* workspace, size_t ws_bytes, void* stream);
+/* Backward of lkgd_attention_temporal: qkv [B,F,HW,3C], dO [B,F,HW,C] -> dqkv [B,F,HW,3C] (all bf16). */
+LKGD_API int lkgd_attention_temporal_bwd(const void* qkv, const void* dO, void* dqkv, int32_t B, int32_t F, int32_t HW,
+                                         int32_t heads, int32_t d, float scale, void* stream);
+
+/* GroupNorm(+SiLU) backward.  x1/x2/NS/R/groups/gamma/beta/eps/silu/x_f32 as in lkgd_groupnorm; fwd_sums is the
+ * workspace the forward call filled (per-(sample, channel) sum and sum of squares); dy is bf16 [NS*R, C].
+ *   dx = GN'(dy) [+ add]      add: optional [NS*R, C] (bf16, or fp32 when add_f32)
+ * written to  out1 (fp32 [NS*R, C1], += when acc1), out2 (fp32 [NS*R, C2], += when acc2; the concatenated skip's
+ * share) and / or out_bf16 (bf16 [NS*R, C], the value stored in out1/out2 after accumulation) - each may be NULL. */
+LKGD_API size_t lkgd_groupnorm_bwd_workspace(int32_t NS, int32_t C);
+LKGD_API int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R,
+                                int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                                int32_t x_f32, const void* dy, const void* fwd_sums, const void* add, int32_t add_f32,
+                                float* out1, int32_t acc1, float* out2, int32_t acc2, void* out_bf16, void* workspace,
+                                size_t ws_bytes, void* stream);
+/* LayerNorm backward: x fp32 [M, C] (the normalised input), dy [M, C] (bf16, or fp32 when dy_f32);
+ * G (fp32 [M, C]) = (accumulate ? G : 0) + LN'(dy); g_bf16 (optional) receives the new G as bf16. */
+LKGD_API int lkgd_layernorm_bwd(const float* x, const void* dy, int32_t dy_f32, int32_t M, int32_t C, const float* gamma,
+                                float eps, float* G, int32_t accumulate, void* g_bf16, void* stream);
+/* GEGLU on the tile-interleaved projection output pre [M, 2H] (lkgd_gemm GEGLU weight order, act NONE):
+ * fwd: out[m, j] = value * gelu_erf(gate);  bwd: dpre from dout [M, H]. */
+LKGD_API int lkgd_geglu_fwd(const void* pre, void* out, int64_t M, int32_t H, void* stream);
+LKGD_API int lkgd_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int32_t H, void* stream);
+/* out[g(m), c] += G[m, c]: gradient of the per-context vectors added by LayerNorm's addvec (rv modes as above;
+ * n_groups <= 8; out must be zero-initialised by the caller, fp32 [n_groups, C]). */
+LKGD_API int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t rv_mode, int32_t rv_HW, int32_t rv_F,
+                                 int32_t rv_B, int32_t n_groups, float* out, void* stream);
+/* Nearest-2x upsample backward: out fp32 [N,H,W,C] = 2x2 block sums of in [N,2H,2W,C] (bf16 / fp32). */
+LKGD_API int lkgd_downsum2x(const void* in, int32_t in_f32, float* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                            void* stream);
+/* Stride-2 conv data gradient helper: out bf16 [N,Hin,Win,C], out[2ho,2wo] = in[ho,wo] (in [N,Ho,Wo,C]), else 0. */
+LKGD_API int lkgd_zero_stuff2x(const void* in, int32_t in_f32, void* out, int32_t N, int32_t Hin, int32_t Win, int32_t C,
+                               void* stream);
+/* out[i, j] += alpha * sum_m X[m, i] * Y[m, j]: LoRA weight gradients (models/lora_layer.py:437 under autograd). */
+LKGD_API int lkgd_gemm_tn(const void* X, int64_t ldx, int32_t I, const void* Y, int64_t ldy, int32_t J, int64_t M,
+                          float alpha, float* out, int64_t ldo, void* stream);
+/* EDM training wrapper (train_svd_lora.py:1503-1530): noisy = latents + noise * sigma[b] (fp32 [B,F,C,H,W]);
+ * x_in (bf16 rows [B*F*H*W, Cpad]) = [noisy / sqrt(sigma^2+1) | cond[b] (fp32 [B,C,H,W], repeated over frames) | 0]. */
+LKGD_API int lkgd_edm_precondition(const float* latents, const float* noise, const float* sigma, const float* cond,
+                                   float* noisy, void* x_in, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                                   int32_t Cpad, void* stream);
+/* Weighted-MSE loss of the v-prediction wrapper and its gradient (train_svd_lora.py:1651-1672):
+ *   den = pred * c_out + c_skip * noisy;  loss = mean_b mean_{f,c,h,w} (1+s^2)/s^2 (den - target)^2   (double, device)
+ *   dpred (bf16 rows [B*F*H*W, Cpad], zero padded) = grad_scale * dloss/dpred.  pred: fp32 rows, pitch ld. */
+LKGD_API int lkgd_edm_loss(const float* pred, int32_t ld, const float* noisy, const float* target, const float* sigma,
+                           double* loss, void* dpred, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W, int32_t Cpad,
+                           float grad_scale, void* stream);
+/* *out = sum x^2 (double, device): clip_grad_norm_ (train_svd_lora.py:1684-1686). */
+LKGD_API int lkgd_sumsq(const float* x, int64_t n, double* out, void* stream);
+/* torch.optim.AdamW step over flat fp32 buffers; the gradient is scaled by grad_scale (1/world after the all-reduce)
+ * and clipped to max_norm using *sumsq (both optional: sumsq NULL or max_norm <= 0 disables clipping). */
+LKGD_API int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int32_t step, float grad_scale, const double* sumsq,
+                        float max_norm, void* stream);
+/* dst[r, c] = bf16(alpha * src[r, c]) with row pitches (repacking fp32 master LoRA weights into the GEMM operands,
+ * scaled bf16 copies of gradient tensors). */
+LKGD_API int lkgd_cast2d_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
+                              float alpha, void* stream);
 
 #ifdef __cplusplus
 }

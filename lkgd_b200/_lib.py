@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -62,6 +62,27 @@ SIGNATURES = {
     "lkgd_concat_channels": (i32, [vp, i32, vp, i32, i32, vp, i64, vp]),
     "lkgd_axpby": (i32, [vp, i32, f32, vp, i32, f32, i64, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
+    # ---- training step
+    "lkgd_attention_lse": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]),
+    "lkgd_attention_bwd_workspace": (sz, [i32, i32, i32]),
+    "lkgd_attention_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
+                                 i32, f32, vp, sz, vp]),
+    "lkgd_attention_temporal_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "lkgd_groupnorm_bwd_workspace": (sz, [i32, i32]),
+    "lkgd_groupnorm_bwd": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, vp, i32, vp, i32, vp,
+                                 i32, vp, vp, sz, vp]),
+    "lkgd_layernorm_bwd": (i32, [vp, vp, i32, i32, i32, vp, f32, vp, i32, vp, vp]),
+    "lkgd_geglu_fwd": (i32, [vp, vp, i64, i32, vp]),
+    "lkgd_geglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
+    "lkgd_colsum_grouped": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "lkgd_downsum2x": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "lkgd_zero_stuff2x": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "lkgd_gemm_tn": (i32, [vp, i64, i32, vp, i64, i32, i64, f32, vp, i64, vp]),
+    "lkgd_edm_precondition": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "lkgd_edm_loss": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "lkgd_sumsq": (i32, [vp, i64, vp, vp]),
+    "lkgd_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
+    "lkgd_cast2d_bf16": (i32, [vp, i64, vp, i64, i32, i32, f32, vp]),
 }
 
 _lib = None
@@ -79,7 +100,11 @@ PROF = Profiler()
 _TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
           "lkgd_small_linear", "lkgd_timestep_embedding", "lkgd_pack_input", "lkgd_unpack_output",
           "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_cast_bf16", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_axpy_f32",
-          "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32"}
+          "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32",
+          "lkgd_attention_lse", "lkgd_attention_bwd", "lkgd_attention_temporal_bwd", "lkgd_groupnorm_bwd",
+          "lkgd_layernorm_bwd", "lkgd_geglu_fwd", "lkgd_geglu_bwd", "lkgd_colsum_grouped", "lkgd_downsum2x",
+          "lkgd_zero_stuff2x", "lkgd_gemm_tn", "lkgd_edm_precondition", "lkgd_edm_loss", "lkgd_sumsq", "lkgd_adamw",
+          "lkgd_cast2d_bf16"}
 
 
 def _timed(name, fn):

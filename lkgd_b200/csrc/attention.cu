@@ -23,6 +23,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   int ldo, heads, d, Nq, Nk;
   float scale_log2;
+  float* lse;       // optional [n_img, heads, Nq]: log2-domain log-sum-exp of the scaled scores (training backward)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
     tc_fence_before();
     if (q0 + r < p.Nq) {
       const float inv = 1.0f / l_run;
+      if (p.lse != nullptr) p.lse[((size_t)img * p.heads + head) * p.Nq + q0 + r] = m_run + log2f(l_run);
       __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
       if (p.d == AT_D) {
 #pragma unroll
@@ -435,9 +437,9 @@ static int attn_tmap(CUtensorMap* tm, const void* base, int ld, int heads, int d
 
 using namespace lkgd;
 
-extern "C" int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
-                              void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
-                              int32_t Nk, float scale, void* stream) {
+static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                          void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
+                          int32_t Nk, float scale, float* lse, void* stream) {
   if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d > AT_D || d % 8 || d <= 0) return LKGD_ESHAPE;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return LKGD_EALIGN;
   if (heads > 65535 || n_img > 65535) return LKGD_ESHAPE;
@@ -449,6 +451,7 @@ extern "C" int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
@@ -458,6 +461,19 @@ extern "C" int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
   attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
+}
+
+extern "C" int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                              void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
+                              int32_t Nk, float scale, void* stream) {
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, n_img, heads, d, Nq, Nk, scale, nullptr, stream);
+}
+
+extern "C" int lkgd_attention_lse(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                                  void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
+                                  int32_t Nk, float scale, float* lse, void* stream) {
+  if (lse == nullptr) return LKGD_ESHAPE;
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, n_img, heads, d, Nq, Nk, scale, lse, stream);
 }
 
 extern "C" int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, int32_t F, int32_t HW, int32_t heads,

@@ -1,0 +1,716 @@
+// Backward / training kernels of the LoRA fine-tuning step (reference train_models/train_svd_lora.py:1445-1689):
+// GroupNorm(+SiLU) and LayerNorm backward, GEGLU forward / backward on the tile-interleaved projection, grouped column
+// sums (gradient of the KV-length-1 cross-attention vectors), 2x2 sum (nearest-upsample backward), zero stuffing
+// (stride-2 conv data gradient), EDM preconditioning + weighted-MSE loss forward/backward, fused AdamW, sum of squares.
+// All HBM-bound, 128-bit vectorised.  Contracts: include/lkgd_b200.h.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lkgd {
+
+__device__ __forceinline__ void ld8_f32(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void st8_f32(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void ld8_any(const void* base, long long off, int is_f32, float (&f)[8]) {
+  if (is_f32) ld8_f32(reinterpret_cast<const float*>(base) + off, f);
+  else ld8_bf16(reinterpret_cast<const __nv_bfloat16*>(base) + off, f);
+}
+
+// ------------------------------------------------------------------------------------------- GroupNorm backward
+// Same thread layout as the forward kernels (norm.cu): blockDim.x = vecs * rows_par, thread -> (row lane, 8 channels).
+struct GnbGeom {
+  int C1, C2, C, vecs, rows_par, R, rows_per_cta, x_f32, groups, silu;
+  float eps;
+};
+
+__device__ __forceinline__ void gnb_load_x(const void* x1, const void* x2, const GnbGeom& g, long long row, int v,
+                                           float (&f)[8]) {
+  const int c = v * 8;
+  if (c < g.C1) ld8_any(x1, row * g.C1 + c, g.x_f32, f);
+  else ld8_any(x2, row * g.C2 + (c - g.C1), g.x_f32, f);
+}
+
+// smem prologue shared by both passes: per-channel a[c] = rstd*gamma, b[c] = beta - mean*rstd*gamma, plus the group's
+// mean / rstd, from the forward's per-channel (sum, sum of squares)
+__device__ __forceinline__ void gnb_prologue(const GnbGeom& g, int ns, const double* fsums, const float* gamma,
+                                             const float* beta, float* sa, float* sb, float* gmean, float* grstd) {
+  const int cpg = g.C / g.groups;
+  for (int gi = threadIdx.x; gi < g.groups; gi += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      s += fsums[((size_t)ns * g.C + c) * 2];
+      q += fsums[((size_t)ns * g.C + c) * 2 + 1];
+    }
+    const double n = (double)cpg * g.R;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(var + (double)g.eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = grstd[gi] * gamma[c];
+    sa[c] = sc;
+    sb[c] = beta[c] - gmean[gi] * sc;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
+
+// pass 1: per (sample, channel)  sum g  and  sum g * xhat,   g = dy * act'(z) * gamma
+__global__ void gn_bwd_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+                                    const __nv_bfloat16* __restrict__ dy, GnbGeom g,
+                                    const double* __restrict__ fsums, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, double* __restrict__ bsums) {
+  extern __shared__ float sh[];
+  float* sa = sh;
+  float* sb = sh + g.C;
+  float* gmean = sh + 2 * g.C;
+  float* grstd = gmean + g.groups;
+  float* red = grstd + g.groups;   // [threads][16]
+  const int ns = blockIdx.y;
+  gnb_prologue(g, ns, fsums, gamma, beta, sa, sb, gmean, grstd);
+  const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
+  const int cpg = g.C / g.groups;
+  const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
+  float a[8], b[8], gm[8], xm[8], xr[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    a[i] = sa[c]; b[i] = sb[c]; gm[i] = gamma[c];
+    xm[i] = gmean[c / cpg]; xr[i] = grstd[c / cpg];
+    s1[i] = 0.f; s2[i] = 0.f;
+  }
+  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+    const long long row = (long long)ns * g.R + r;
+    float f[8], d[8];
+    gnb_load_x(x1, x2, g, row, v, f);
+    ld8_bf16(dy + row * g.C + v * 8, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(f[i], a[i], b[i]);
+      const float gg = d[i] * (g.silu ? silu_grad(z) : 1.0f) * gm[i];
+      s1[i] += gg;
+      s2[i] = fmaf(gg, (f[i] - xm[i]) * xr[i], s2[i]);
+    }
+  }
+  float* my = red + (size_t)threadIdx.x * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { my[i] = s1[i]; my[8 + i] = s2[i]; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < g.vecs * 16; t += blockDim.x) {
+    const int vv = t / 16, comp = t % 16;
+    float acc = 0.f;
+    for (int rr = 0; rr < g.rows_par; ++rr) acc += red[((size_t)rr * g.vecs + vv) * 16 + comp];
+    const int c = vv * 8 + (comp & 7);
+    atomicAdd(&bsums[((size_t)ns * g.C + c) * 2 + (comp >> 3)], (double)acc);
+  }
+}
+
+// pass 2: dx = rstd * (g - mean(g) - xhat * mean(g xhat))  [+ add], written to up to three destinations
+__global__ void gn_bwd_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+                                    const __nv_bfloat16* __restrict__ dy, GnbGeom g, const double* __restrict__ fsums,
+                                    const double* __restrict__ bsums, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const void* __restrict__ add, int add_f32,
+                                    float* __restrict__ out1, int acc1, float* __restrict__ out2, int acc2,
+                                    __nv_bfloat16* __restrict__ out_bf16) {
+  extern __shared__ float sh[];
+  float* sa = sh;
+  float* sb = sh + g.C;
+  float* gmean = sh + 2 * g.C;
+  float* grstd = gmean + g.groups;
+  float* m1 = grstd + g.groups;    // [groups] mean(g)
+  float* m2 = m1 + g.groups;       // [groups] mean(g * xhat)
+  const int ns = blockIdx.y;
+  const int cpg = g.C / g.groups;
+  gnb_prologue(g, ns, fsums, gamma, beta, sa, sb, gmean, grstd);
+  for (int gi = threadIdx.x; gi < g.groups; gi += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      s += bsums[((size_t)ns * g.C + c) * 2];
+      q += bsums[((size_t)ns * g.C + c) * 2 + 1];
+    }
+    const double n = (double)cpg * g.R;
+    m1[gi] = (float)(s / n);
+    m2[gi] = (float)(q / n);
+  }
+  __syncthreads();
+  const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
+  const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
+  float a[8], b[8], gm[8], xm[8], xr[8], k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    a[i] = sa[c]; b[i] = sb[c]; gm[i] = gamma[c];
+    xm[i] = gmean[c / cpg]; xr[i] = grstd[c / cpg];
+    k1[i] = m1[c / cpg]; k2[i] = m2[c / cpg];
+  }
+  const int c0 = v * 8;
+  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+    const long long row = (long long)ns * g.R + r;
+    float f[8], d[8], o[8];
+    gnb_load_x(x1, x2, g, row, v, f);
+    ld8_bf16(dy + row * g.C + c0, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(f[i], a[i], b[i]);
+      const float gg = d[i] * (g.silu ? silu_grad(z) : 1.0f) * gm[i];
+      const float xh = (f[i] - xm[i]) * xr[i];
+      o[i] = xr[i] * (gg - k1[i] - xh * k2[i]);
+    }
+    if (add != nullptr) {
+      float e[8];
+      ld8_any(add, row * g.C + c0, add_f32, e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += e[i];
+    }
+    float* dst = nullptr;
+    int acc = 0;
+    if (c0 < g.C1) { if (out1) { dst = out1 + row * g.C1 + c0; acc = acc1; } }
+    else if (out2) { dst = out2 + row * g.C2 + (c0 - g.C1); acc = acc2; }
+    if (dst != nullptr) {
+      if (acc) {
+        float e[8];
+        ld8_f32(dst, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += e[i];
+      }
+      st8_f32(dst, o);
+    }
+    if (out_bf16 != nullptr) st8_bf16(out_bf16 + row * g.C + c0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm backward
+// one warp per row; G += rstd * (g - mean(g) - xhat * mean(g xhat)),  g = dy * gamma;  optional bf16 copy of the new G
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const void* __restrict__ dy,
+                                                     int dy_f32, int M, int C, const float* __restrict__ gamma,
+                                                     float eps, float* __restrict__ G, int accumulate,
+                                                     __nv_bfloat16* __restrict__ g_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float f[NV][8], d[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+      ld8_f32(x + row * C + v * 8, f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[j][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    if (lane + 32 * j < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float t = f[j][i] - mean; q = fmaf(t, t, q); }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+      float gm[8];
+      ld8_f32(gamma + v * 8, gm);
+      ld8_any(dy, row * C + v * 8, dy_f32, d[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[j][i] = (f[j][i] - mean) * rstd;       // xhat
+        d[j][i] *= gm[i];                        // g
+        s1 += d[j][i];
+        s2 = fmaf(d[j][i], f[j][i], s2);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  s1 /= C; s2 /= C;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = rstd * (d[j][i] - s1 - f[j][i] * s2);
+      float* gp = G + row * C + v * 8;
+      if (accumulate) {
+        float e[8];
+        ld8_f32(gp, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] += e[i];
+      }
+      st8_f32(gp, o8);
+      if (g_bf16) st8_bf16(g_bf16 + row * C + v * 8, o8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- GEGLU
+// pre: [M, 2H] bf16 in the GEMM's tile-interleaved order: tile t holds 128 value columns then their 128 gate columns.
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  return fmaf(x * 0.3989422804014327f, __expf(-0.5f * x * x), cdf);
+}
+
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long M,
+                                 int H) {
+  const int hv = H / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * hv) return;
+  const long long m = idx / hv;
+  const int j = (int)(idx % hv) * 8;            // output column
+  const int t = j >> 7, jj = j & 127;
+  const __nv_bfloat16* p = pre + m * 2 * H + t * 256 + jj;
+  float a[8], gt[8], o[8];
+  ld8_bf16(p, a);
+  ld8_bf16(p + 128, gt);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = a[i] * gelu_erf_f(gt[i]);
+  st8_bf16(out + m * H + j, o);
+}
+
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dout,
+                                 __nv_bfloat16* __restrict__ dpre, long long M, int H) {
+  const int hv = H / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * hv) return;
+  const long long m = idx / hv;
+  const int j = (int)(idx % hv) * 8;
+  const int t = j >> 7, jj = j & 127;
+  const long long off = m * 2 * H + t * 256 + jj;
+  float a[8], gt[8], d[8], da[8], dg[8];
+  ld8_bf16(pre + off, a);
+  ld8_bf16(pre + off + 128, gt);
+  ld8_bf16(dout + m * H + j, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    da[i] = d[i] * gelu_erf_f(gt[i]);
+    dg[i] = d[i] * a[i] * gelu_grad_f(gt[i]);
+  }
+  st8_bf16(dpre + off, da);
+  st8_bf16(dpre + off + 128, dg);
+}
+
+// ------------------------------------------------------------------------------------------- grouped column sums
+__device__ __forceinline__ int rv_index(int mode, long long m, int HW, int F, int B) {
+  switch (mode) {
+    case LKGD_RV_FRAME: return (int)(m / HW);
+    case LKGD_RV_FRAMEPOS: return (int)((m / HW) % F);
+    case LKGD_RV_BATCH: return (int)(m / ((long long)HW * F));
+    case LKGD_RV_TCTX_0272: return (int)(((m / ((long long)HW * F)) * HW + (m % HW)) % B);
+    default: return 0;
+  }
+}
+
+constexpr int CS_MAXG = 8;
+// grid (col blocks of 128 columns, row chunks); thread = one column over a chunk of rows, up to CS_MAXG groups
+__global__ void colsum_grouped_kernel(const float* __restrict__ G, long long M, int C, int rows_per_cta, int mode, int HW,
+                                      int F, int B, int n_groups, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float acc[CS_MAXG];
+#pragma unroll
+  for (int i = 0; i < CS_MAXG; ++i) acc[i] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const int gi = rv_index(mode, r, HW, F, B);
+    const float v = G[r * C + c];
+#pragma unroll
+    for (int i = 0; i < CS_MAXG; ++i) acc[i] += (i == gi) ? v : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < CS_MAXG; ++i)
+    if (i < n_groups && acc[i] != 0.f) atomicAdd(out + (size_t)i * C + c, acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------- resampling gradients
+// nearest-2x upsample backward: out[n,h,w,:] = sum of the 2x2 block of in [N,2H,2W,C]
+__global__ void downsum2x_kernel(const void* __restrict__ in, int in_f32, float* __restrict__ out, int N, int H, int W,
+                                 int C) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * H * W * cv) return;
+  const int v = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int w = (int)(pix % W), h = (int)((pix / W) % H);
+  const long long n = pix / ((long long)W * H);
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float f[8];
+      ld8_any(in, ((n * 2 * H + 2 * h + dy) * 2 * W + 2 * w + dx) * C + v * 8, in_f32, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += f[i];
+    }
+  st8_f32(out + pix * C + v * 8, o);
+}
+
+// stride-2 conv data gradient: out [N,Hin,Win,C] bf16 with out[2ho,2wo] = in[ho,wo], zero elsewhere
+__global__ void zero_stuff2x_kernel(const void* __restrict__ in, int in_f32, __nv_bfloat16* __restrict__ out, int N,
+                                    int Hin, int Win, int Ho, int Wo, int C) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Hin * Win * cv) return;
+  const int v = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int w = (int)(pix % Win), h = (int)((pix / Win) % Hin);
+  const long long n = pix / ((long long)Win * Hin);
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+    ld8_any(in, ((n * Ho + (h >> 1)) * Wo + (w >> 1)) * C + v * 8, in_f32, f);
+  st8_bf16(out + pix * C + v * 8, f);
+}
+
+// ------------------------------------------------------------------------------------------- EDM wrapper + loss
+// noisy = latents + noise * sigma[b];  x_in = [noisy / sqrt(sigma^2 + 1) | cond[b] | 0...]   (train_svd_lora.py:1503-1530)
+__global__ void edm_precondition_kernel(const float* __restrict__ lat, const float* __restrict__ noise,
+                                        const float* __restrict__ sigma, const float* __restrict__ cond,
+                                        float* __restrict__ noisy, __nv_bfloat16* __restrict__ xin, int B, int F, int C,
+                                        int HW, int Cpad) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * F * HW) return;
+  const int p = (int)(pix % HW);
+  const int f = (int)((pix / HW) % F);
+  const int b = (int)(pix / ((long long)HW * F));
+  const float sg = sigma[b];
+  const float cin = rsqrtf(sg * sg + 1.0f);
+  __nv_bfloat16* o = xin + pix * Cpad;
+  for (int c8 = 0; c8 < Cpad; c8 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c8 + i;
+      float val = 0.f;
+      if (c < C) {
+        const size_t e = (((size_t)b * F + f) * C + c) * HW + p;
+        const float nz = fmaf(noise[e], sg, lat[e]);
+        noisy[e] = nz;
+        val = nz * cin;
+      } else if (c < 2 * C) {
+        val = cond[((size_t)b * C + (c - C)) * HW + p];
+      }
+      v[i] = val;
+    }
+    st8_bf16(o + c8, v);
+  }
+}
+
+// denoised = pred * c_out + c_skip * noisy;  loss = mean_b mean_{f,c,h,w} w(sigma) (denoised - target)^2
+// (train_svd_lora.py:1651-1672); dpred = dloss/dpred as channels-last bf16 rows [B*F*HW, Cpad] (zero padded)
+__global__ void edm_loss_kernel(const float* __restrict__ pred, int ld, const float* __restrict__ noisy,
+                                const float* __restrict__ target, const float* __restrict__ sigma,
+                                double* __restrict__ loss, __nv_bfloat16* __restrict__ dpred, int B, int F, int C, int HW,
+                                int Cpad, float grad_scale) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double part = 0.0;
+  if (pix < (long long)B * F * HW) {
+    const int p = (int)(pix % HW);
+    const int f = (int)((pix / HW) % F);
+    const int b = (int)(pix / ((long long)HW * F));
+    const float sg = sigma[b];
+    const float c_out = -sg * rsqrtf(sg * sg + 1.0f), c_skip = 1.0f / (sg * sg + 1.0f);
+    const float wgt = (1.0f + sg * sg) / (sg * sg);
+    const float inv_n = 1.0f / ((float)F * C * HW * B);
+    for (int c8 = 0; c8 < Cpad; c8 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c8 + i;
+        float gval = 0.f;
+        if (c < C) {
+          const size_t e = (((size_t)b * F + f) * C + c) * HW + p;
+          const float diff = fmaf(pred[pix * ld + c], c_out, c_skip * noisy[e]) - target[e];
+          part += (double)(wgt * diff * diff * inv_n);
+          gval = 2.0f * wgt * diff * c_out * inv_n * grad_scale;
+        }
+        v[i] = gval;
+      }
+      if (dpred) st8_bf16(dpred + pix * Cpad + c8, v);
+    }
+  }
+  // block reduction -> one atomic per block
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(loss, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- optimizer
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double part = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    part += (double)x[i] * x[i];
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction); the gradient is first multiplied by
+// grad_scale * min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6))  (clip_grad_norm_; sumsq may be NULL)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+                             float bc1, float bc2, float grad_scale, const double* __restrict__ sumsq, float max_norm) {
+  float gs = grad_scale;
+  if (sumsq != nullptr && max_norm > 0.f) {
+    const float norm = (float)sqrt(*sumsq) * grad_scale;
+    const float clip = max_norm / (norm + 1e-6f);
+    if (clip < 1.0f) gs *= clip;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = fmaf(beta1, m[i], (1.0f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    pi -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    p[i] = pi;
+  }
+}
+
+__global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                   long long ldd, int rows, int cols, float alpha) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const long long r = idx / cols;
+  const int c = (int)(idx % cols);
+  dst[r * ldd + c] = __float2bfloat16(src[r * lds + c] * alpha);
+}
+
+static GnbGeom gnb_geom(int C1, int C2, int R, int x_f32, int groups, int silu, float eps) {
+  GnbGeom g;
+  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
+  g.groups = groups; g.silu = silu; g.eps = eps;
+  g.rows_par = 256 / g.vecs;
+  if (g.rows_par < 1) g.rows_par = 1;
+  if (g.rows_par > R) g.rows_par = R;
+  g.rows_per_cta = g.rows_par * 8;
+  return g;
+}
+
+}  // namespace lkgd
+
+using namespace lkgd;
+
+extern "C" size_t lkgd_groupnorm_bwd_workspace(int32_t NS, int32_t C) { return (size_t)NS * C * 2 * sizeof(double); }
+
+extern "C" int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R,
+                                  int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                                  int32_t x_f32, const void* dy, const void* fwd_sums, const void* add, int32_t add_f32,
+                                  float* out1, int32_t acc1, float* out2, int32_t acc2, void* out_bf16, void* workspace,
+                                  size_t ws_bytes, void* stream) {
+  if (x2 == nullptr) C2 = 0;
+  const int C = C1 + C2;
+  if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
+  if (dy == nullptr || fwd_sums == nullptr) return LKGD_ESHAPE;
+  if (!aligned16(x1) || !aligned16(dy) || (x2 && !aligned16(x2)) || (add && !aligned16(add)) ||
+      (out1 && !aligned16(out1)) || (out2 && !aligned16(out2)) || (out_bf16 && !aligned16(out_bf16)))
+    return LKGD_EALIGN;
+  if (ws_bytes < lkgd_groupnorm_bwd_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GnbGeom g = gnb_geom(C1, C2, R, x_f32, groups, silu, eps);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, lkgd_groupnorm_bwd_workspace(NS, C), st);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
+  const int threads = g.vecs * g.rows_par;
+  const size_t sh_pro = (size_t)(2 * C + 4 * groups) * sizeof(float);
+  const size_t sh1 = sh_pro + (size_t)threads * 16 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  gn_bwd_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, reinterpret_cast<const __nv_bfloat16*>(dy), g,
+                                                  reinterpret_cast<const double*>(fwd_sums), gamma, beta,
+                                                  reinterpret_cast<double*>(workspace));
+  int rc = launch_epilogue();
+  if (rc) return rc;
+  gn_bwd_apply_kernel<<<grid, threads, sh_pro, st>>>(x1, x2, reinterpret_cast<const __nv_bfloat16*>(dy), g,
+                                                     reinterpret_cast<const double*>(fwd_sums),
+                                                     reinterpret_cast<const double*>(workspace), gamma, beta, add,
+                                                     add_f32, out1, acc1, out2, acc2,
+                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_layernorm_bwd(const float* x, const void* dy, int32_t dy_f32, int32_t M, int32_t C,
+                                  const float* gamma, float eps, float* G, int32_t accumulate, void* g_bf16,
+                                  void* stream) {
+  if (M <= 0 || C <= 0 || C % 8 || C > 2048) return LKGD_ESHAPE;
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(G) || !aligned16(gamma) || (g_bf16 && !aligned16(g_bf16)))
+    return LKGD_EALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  const int nv = (C / 8 + 31) / 32;
+#define LNB(NV) ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(x, dy, dy_f32, M, C, gamma, eps, G, accumulate, \
+                                                        reinterpret_cast<__nv_bfloat16*>(g_bf16))
+  switch (nv) {
+    case 1: LNB(1); break;
+    case 2: LNB(2); break;
+    case 3: LNB(3); break;
+    case 4: LNB(4); break;
+    case 5: LNB(5); break;
+    default: LNB(8); break;
+  }
+#undef LNB
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_geglu_fwd(const void* pre, void* out, int64_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0 || H % 128) return LKGD_ESHAPE;
+  if (!aligned16(pre) || !aligned16(out)) return LKGD_EALIGN;
+  const long long n = M * (H / 8);
+  geglu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<__nv_bfloat16*>(out), M, H);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int32_t H, void* stream) {
+  if (M <= 0 || H <= 0 || H % 128) return LKGD_ESHAPE;
+  if (!aligned16(pre) || !aligned16(dout) || !aligned16(dpre)) return LKGD_EALIGN;
+  const long long n = M * (H / 8);
+  geglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dout),
+      reinterpret_cast<__nv_bfloat16*>(dpre), M, H);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t rv_mode, int32_t rv_HW, int32_t rv_F,
+                                   int32_t rv_B, int32_t n_groups, float* out, void* stream) {
+  if (M <= 0 || C <= 0 || n_groups <= 0 || n_groups > CS_MAXG) return LKGD_ESHAPE;
+  if (rv_HW <= 0) rv_HW = 1;
+  if (rv_F <= 0) rv_F = 1;
+  if (rv_B <= 0) rv_B = 1;
+  const int rows_per_cta = 256;
+  dim3 grid((C + 127) / 128, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+  colsum_grouped_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, rv_mode, rv_HW,
+                                                                                   rv_F, rv_B, n_groups, out);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_downsum2x(const void* in, int32_t in_f32, float* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                              void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return LKGD_ESHAPE;
+  if (!aligned16(in) || !aligned16(out)) return LKGD_EALIGN;
+  const long long n = (long long)N * H * W * (C / 8);
+  downsum2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, in_f32, out, N,
+                                                                                                     H, W, C);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_zero_stuff2x(const void* in, int32_t in_f32, void* out, int32_t N, int32_t Hin, int32_t Win,
+                                 int32_t C, void* stream) {
+  if (N <= 0 || Hin <= 0 || Win <= 0 || C <= 0 || C % 8) return LKGD_ESHAPE;
+  if (!aligned16(in) || !aligned16(out)) return LKGD_EALIGN;
+  const int Ho = (Hin - 1) / 2 + 1, Wo = (Win - 1) / 2 + 1;
+  const long long n = (long long)N * Hin * Win * (C / 8);
+  zero_stuff2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, in_f32, reinterpret_cast<__nv_bfloat16*>(out), N, Hin, Win, Ho, Wo, C);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_edm_precondition(const float* latents, const float* noise, const float* sigma, const float* cond,
+                                     float* noisy, void* x_in, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                                     int32_t Cpad, void* stream) {
+  if (B <= 0 || F <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 8 || Cpad < 2 * C) return LKGD_ESHAPE;
+  if (!aligned16(x_in)) return LKGD_EALIGN;
+  const long long n = (long long)B * F * H * W;
+  edm_precondition_kernel<<<(unsigned)((n + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      latents, noise, sigma, cond, noisy, reinterpret_cast<__nv_bfloat16*>(x_in), B, F, C, H * W, Cpad);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_edm_loss(const float* pred, int32_t ld, const float* noisy, const float* target, const float* sigma,
+                             double* loss, void* dpred, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                             int32_t Cpad, float grad_scale, void* stream) {
+  if (B <= 0 || F <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 8 || Cpad < C || ld < C) return LKGD_ESHAPE;
+  if (dpred && !aligned16(dpred)) return LKGD_EALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(double), st);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const long long n = (long long)B * F * H * W;
+  edm_loss_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pred, ld, noisy, target, sigma, loss,
+                                                               reinterpret_cast<__nv_bfloat16*>(dpred), B, F, C, H * W,
+                                                               Cpad, grad_scale);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_sumsq(const float* x, int64_t n, double* out, void* stream) {
+  if (n <= 0) return LKGD_ESHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, out);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int32_t step, float grad_scale, const double* sumsq,
+                          float max_norm, void* stream) {
+  if (n <= 0 || step <= 0) return LKGD_ESHAPE;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, sumsq, max_norm);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
+                                float alpha, void* stream) {
+  if (rows <= 0 || cols <= 0 || lds < cols || ldd < cols) return LKGD_ESHAPE;
+  const long long n = (long long)rows * cols;
+  cast2d_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
+  return launch_epilogue();
+}

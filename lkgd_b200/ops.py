@@ -136,8 +136,9 @@ def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------- norms
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, NS: int, R: int,
               x2: Optional[torch.Tensor] = None, groups: int = 32, silu: bool = True,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x1 [NS*R, C1] (+ x2 [NS*R, C2]) bf16 or fp32 channels-last -> [NS*R, C1+C2] bf16."""
+              out: Optional[torch.Tensor] = None, return_stats: bool = False):
+    """x1 [NS*R, C1] (+ x2 [NS*R, C2]) bf16 or fp32 channels-last -> [NS*R, C1+C2] bf16.
+    ``return_stats``: also return the per-(sample, channel) sums the backward reuses."""
     _need_cuda(x1, x2, gamma, beta)
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
@@ -158,7 +159,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     L.check(lib.lkgd_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
                                eps, int(silu), int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
                                _stream()), "lkgd_groupnorm")
-    return out
+    return (out, ws) if return_stats else out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *,
@@ -187,8 +188,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 # ----------------------------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, n_img: int, heads: int, d: int, Nq: int,
               Nk: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
-              checker: bool = False) -> torch.Tensor:
-    """q [n_img*Nq, >=heads*d], k/v [n_img*Nk, >=heads*d] (column slices of a fused projection are fine)."""
+              checker: bool = False, return_lse: bool = False):
+    """q [n_img*Nq, >=heads*d], k/v [n_img*Nk, >=heads*d] (column slices of a fused projection are fine).
+    ``return_lse``: also return the fp32 [n_img, heads, Nq] log2-sum-exp the backward needs."""
     _need_cuda(q, k, v)
     for t in (q, k, v):
         if t.dtype != bf16 or t.dim() != 2 or t.stride(1) != 1:
@@ -200,6 +202,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, n_img: int, 
     fn = lib.lkgd_attention_simt_check if checker else lib.lkgd_attention
     if L.PROF.enabled:
         L.PROF.meta = {"flops": 4.0 * n_img * heads * Nq * Nk * d}
+    if return_lse:
+        lse = torch.empty((n_img, heads, Nq), device=q.device, dtype=torch.float32)
+        L.check(lib.lkgd_attention_lse(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                       out.data_ptr(), out.stride(0), n_img, heads, d, Nq, Nk, scale, lse.data_ptr(),
+                                       _stream()), "lkgd_attention_lse")
+        return out, lse
     L.check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
                out.stride(0), n_img, heads, d, Nq, Nk, scale, _stream()), "lkgd_attention")
     return out
@@ -390,3 +398,246 @@ def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torc
                                          x_next.data_ptr(), _ptr(v), S, F, Cn, H, W, sigma, sigma_next, _stream()),
             "lkgd_cfg_euler_step")
     return x_next, v
+
+
+# ----------------------------------------------------------------------------------------------- training step
+def attention_bwd(q, k, v, o, dO, lse, dq, dk, dv, *, n_img: int, heads: int, d: int, N: int,
+                  scale: Optional[float] = None):
+    """Backward of ``attention`` (self-attention): fills dq / dk / dv (bf16, column slices allowed)."""
+    _need_cuda(q, k, v, o, dO, lse, dq, dk, dv)
+    for t in (q, k, v, o, dO, dq, dk, dv):
+        if t.dtype != bf16 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("attention_bwd operands must be bf16 2-D row-major (column slices allowed)")
+    if o.stride(0) != dO.stride(0):
+        raise ValueError("attention_bwd: o and dO must share a row pitch")
+    if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != n_img * heads * N:
+        raise ValueError("attention_bwd: lse must be contiguous fp32 [n_img, heads, N]")
+    scale = d ** -0.5 if scale is None else scale
+    lib = L.load()
+    ws_bytes = lib.lkgd_attention_bwd_workspace(n_img, heads, N)
+    ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+    if L.PROF.enabled:
+        L.PROF.meta = {"flops": 10.0 * n_img * heads * N * N * d}
+    L.check(lib.lkgd_attention_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                   o.data_ptr(), dO.data_ptr(), o.stride(0), lse.data_ptr(), dq.data_ptr(),
+                                   dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), n_img, heads,
+                                   d, N, scale, ws.data_ptr(), ws_bytes, _stream()), "lkgd_attention_bwd")
+
+
+def attention_temporal_bwd(qkv: torch.Tensor, dO: torch.Tensor, *, B: int, F: int, HW: int, heads: int, d: int,
+                           scale: Optional[float] = None) -> torch.Tensor:
+    _need_cuda(qkv, dO)
+    Cn = heads * d
+    if qkv.dtype != bf16 or not qkv.is_contiguous() or qkv.numel() != B * F * HW * 3 * Cn:
+        raise ValueError("attention_temporal_bwd: qkv must be contiguous bf16 [B*F*HW, 3*heads*d]")
+    if dO.dtype != bf16 or not dO.is_contiguous() or dO.numel() != B * F * HW * Cn:
+        raise ValueError("attention_temporal_bwd: dO must be contiguous bf16 [B*F*HW, heads*d]")
+    out = torch.empty_like(qkv)
+    scale = d ** -0.5 if scale is None else scale
+    L.check(L.load().lkgd_attention_temporal_bwd(qkv.data_ptr(), dO.data_ptr(), out.data_ptr(), B, F, HW, heads, d,
+                                                 scale, _stream()), "lkgd_attention_temporal_bwd")
+    return out
+
+
+def groupnorm_bwd(x1: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float, *, NS: int, R: int, x2: Optional[torch.Tensor] = None, groups: int = 32,
+                  silu: bool = True, add: Optional[torch.Tensor] = None, out1: Optional[torch.Tensor] = None,
+                  acc1: bool = False, out2: Optional[torch.Tensor] = None, acc2: bool = False,
+                  out_bf16: Optional[torch.Tensor] = None):
+    """Backward of ``groupnorm`` (see lkgd_groupnorm_bwd): dy bf16 [NS*R, C]; results go to out1 / out2 (fp32, the
+    two concatenated sources' gradients, optionally accumulated) and / or out_bf16."""
+    _need_cuda(x1, x2, dy, stats, gamma, beta, add, out1, out2, out_bf16)
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    Ct = C1 + C2
+    if dy.dtype != bf16 or not dy.is_contiguous() or dy.numel() != NS * R * Ct:
+        raise ValueError("groupnorm_bwd: dy must be contiguous bf16 [NS*R, C]")
+    if x1.dtype not in (bf16, torch.float32) or not x1.is_contiguous() or x1.numel() != NS * R * C1:
+        raise ValueError("groupnorm_bwd: x1 must be contiguous [NS*R, C1]")
+    if x2 is not None and (x2.dtype != x1.dtype or not x2.is_contiguous() or x2.numel() != NS * R * C2):
+        raise ValueError("groupnorm_bwd: x2 must be contiguous [NS*R, C2] of x1's dtype")
+    if add is not None and (add.dtype not in (bf16, torch.float32) or not add.is_contiguous()
+                            or add.numel() != NS * R * Ct):
+        raise ValueError("groupnorm_bwd: add must be contiguous bf16/fp32 [NS*R, C]")
+    for o, cn in ((out1, C1), (out2, C2)):
+        if o is not None and (o.dtype != torch.float32 or not o.is_contiguous() or o.numel() != NS * R * cn):
+            raise ValueError("groupnorm_bwd: out1 / out2 must be contiguous fp32 [NS*R, C1 / C2]")
+    if out_bf16 is not None and (out_bf16.dtype != bf16 or not out_bf16.is_contiguous()
+                                 or out_bf16.numel() != NS * R * Ct):
+        raise ValueError("groupnorm_bwd: out_bf16 must be contiguous bf16 [NS*R, C]")
+    lib = L.load()
+    ws_bytes = lib.lkgd_groupnorm_bwd_workspace(NS, Ct)
+    ws = torch.empty(ws_bytes, device=x1.device, dtype=torch.uint8)
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2 * 2 + 4)}
+    L.check(lib.lkgd_groupnorm_bwd(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
+                                   eps, int(silu), int(x1.dtype == torch.float32), dy.data_ptr(), stats.data_ptr(),
+                                   _ptr(add), int(add is not None and add.dtype == torch.float32), _ptr(out1),
+                                   int(acc1), _ptr(out2), int(acc2), _ptr(out_bf16), ws.data_ptr(), ws_bytes,
+                                   _stream()), "lkgd_groupnorm_bwd")
+
+
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, G: torch.Tensor, *,
+                  accumulate: bool = True, g_bf16: Optional[torch.Tensor] = None):
+    """G (fp32 [M, C]) (+)= LayerNorm'(dy) for the fp32 input ``x``; optional bf16 copy of the new G."""
+    _need_cuda(x, dy, gamma, G, g_bf16)
+    M, Cn = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous() or G.dtype != torch.float32 or not G.is_contiguous() \
+            or G.shape != x.shape:
+        raise ValueError("layernorm_bwd: x and G must be contiguous fp32 [M, C]")
+    if dy.dtype not in (bf16, torch.float32) or not dy.is_contiguous() or dy.shape != x.shape:
+        raise ValueError("layernorm_bwd: dy must be contiguous bf16/fp32 [M, C]")
+    if g_bf16 is not None and (g_bf16.dtype != bf16 or not g_bf16.is_contiguous() or g_bf16.shape != x.shape):
+        raise ValueError("layernorm_bwd: g_bf16 must be contiguous bf16 [M, C]")
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": M * Cn * (4 + dy.element_size() + 8)}
+    L.check(L.load().lkgd_layernorm_bwd(x.data_ptr(), dy.data_ptr(), int(dy.dtype == torch.float32), M, Cn,
+                                        gamma.data_ptr(), eps, G.data_ptr(), int(accumulate), _ptr(g_bf16), _stream()),
+            "lkgd_layernorm_bwd")
+    return G
+
+
+def geglu_fwd(pre: torch.Tensor) -> torch.Tensor:
+    _need_cuda(pre)
+    if pre.dtype != bf16 or pre.dim() != 2 or not pre.is_contiguous() or pre.shape[1] % 256:
+        raise ValueError("geglu_fwd: pre must be contiguous bf16 [M, 2H], H % 128 == 0")
+    M, H2 = pre.shape
+    out = torch.empty((M, H2 // 2), device=pre.device, dtype=bf16)
+    L.check(L.load().lkgd_geglu_fwd(pre.data_ptr(), out.data_ptr(), M, H2 // 2, _stream()), "lkgd_geglu_fwd")
+    return out
+
+
+def geglu_bwd(pre: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    _need_cuda(pre, dout)
+    M, H2 = pre.shape
+    if pre.dtype != bf16 or not pre.is_contiguous() or dout.dtype != bf16 or not dout.is_contiguous() \
+            or dout.shape != (M, H2 // 2):
+        raise ValueError("geglu_bwd: pre bf16 [M, 2H], dout bf16 [M, H], contiguous")
+    dpre = torch.empty_like(pre)
+    L.check(L.load().lkgd_geglu_bwd(pre.data_ptr(), dout.data_ptr(), dpre.data_ptr(), M, H2 // 2, _stream()),
+            "lkgd_geglu_bwd")
+    return dpre
+
+
+def colsum_grouped(G: torch.Tensor, n_groups: int, rv: Tuple[int, int, int, int], out: Optional[torch.Tensor] = None):
+    """out[g(m)] += G[m] (fp32); ``out`` is created zeroed when not given."""
+    _need_cuda(G, out)
+    if G.dtype != torch.float32 or G.dim() != 2 or not G.is_contiguous():
+        raise ValueError("colsum_grouped: G must be contiguous fp32 [M, C]")
+    M, Cn = G.shape
+    if out is None:
+        out = torch.zeros((n_groups, Cn), device=G.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.shape != (n_groups, Cn):
+        raise ValueError("colsum_grouped: out must be contiguous fp32 [n_groups, C]")
+    L.check(L.load().lkgd_colsum_grouped(G.data_ptr(), M, Cn, rv[0], rv[1], rv[2], rv[3], n_groups, out.data_ptr(),
+                                         _stream()), "lkgd_colsum_grouped")
+    return out
+
+
+def downsum2x(x: torch.Tensor, N: int, H: int, W: int) -> torch.Tensor:
+    """[N*2H*2W, C] (bf16 / fp32) -> fp32 [N*H*W, C]: backward of the nearest 2x upsample."""
+    _need_cuda(x)
+    Cn = x.shape[-1]
+    if x.dtype not in (bf16, torch.float32) or not x.is_contiguous() or x.numel() != N * 4 * H * W * Cn:
+        raise ValueError("downsum2x: contiguous [N*2H*2W, C] expected")
+    out = torch.empty((N * H * W, Cn), device=x.device, dtype=torch.float32)
+    L.check(L.load().lkgd_downsum2x(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(), N, H, W, Cn,
+                                    _stream()), "lkgd_downsum2x")
+    return out
+
+
+def zero_stuff2x(x: torch.Tensor, N: int, Hin: int, Win: int) -> torch.Tensor:
+    """[N*Ho*Wo, C] -> bf16 [N*Hin*Win, C] with the values at even (h, w) and zeros elsewhere."""
+    _need_cuda(x)
+    Cn = x.shape[-1]
+    Ho, Wo = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
+    if x.dtype not in (bf16, torch.float32) or not x.is_contiguous() or x.numel() != N * Ho * Wo * Cn:
+        raise ValueError("zero_stuff2x: contiguous [N*Ho*Wo, C] expected")
+    out = torch.empty((N * Hin * Win, Cn), device=x.device, dtype=bf16)
+    L.check(L.load().lkgd_zero_stuff2x(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(), N, Hin, Win, Cn,
+                                       _stream()), "lkgd_zero_stuff2x")
+    return out
+
+
+def gemm_tn(X: torch.Tensor, Y: torch.Tensor, out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """out[i, j] += alpha * sum_m X[m, i] Y[m, j];  X / Y bf16 [M, *] (column slices allowed), out fp32."""
+    _need_cuda(X, Y, out)
+    for t in (X, Y):
+        if t.dtype != bf16 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("gemm_tn operands must be bf16 2-D row-major (column slices allowed)")
+    if X.shape[0] != Y.shape[0] or out.dtype != torch.float32 or out.dim() != 2 or out.stride(1) != 1 \
+            or out.shape != (X.shape[1], Y.shape[1]):
+        raise ValueError("gemm_tn: out must be fp32 [X.cols, Y.cols]")
+    if L.PROF.enabled:
+        L.PROF.meta = {"flops": 2.0 * X.shape[0] * X.shape[1] * Y.shape[1]}
+    L.check(L.load().lkgd_gemm_tn(X.data_ptr(), X.stride(0), X.shape[1], Y.data_ptr(), Y.stride(0), Y.shape[1],
+                                  X.shape[0], alpha, out.data_ptr(), out.stride(0), _stream()), "lkgd_gemm_tn")
+    return out
+
+
+def edm_precondition(latents: torch.Tensor, noise: torch.Tensor, sigma: torch.Tensor, cond: torch.Tensor, Cpad: int):
+    """-> (noisy fp32 [B,F,C,H,W], x_in bf16 rows [B*F*H*W, Cpad])."""
+    _need_cuda(latents, noise, sigma, cond)
+    B, F, Cn, H, W = latents.shape
+    for t in (latents, noise, sigma, cond):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("edm_precondition: contiguous fp32 tensors expected")
+    if noise.shape != latents.shape or sigma.numel() != B or cond.shape != (B, Cn, H, W):
+        raise ValueError("edm_precondition: shape mismatch")
+    noisy = torch.empty_like(latents)
+    x_in = torch.empty((B * F * H * W, Cpad), device=latents.device, dtype=bf16)
+    L.check(L.load().lkgd_edm_precondition(latents.data_ptr(), noise.data_ptr(), sigma.data_ptr(), cond.data_ptr(),
+                                           noisy.data_ptr(), x_in.data_ptr(), B, F, Cn, H, W, Cpad, _stream()),
+            "lkgd_edm_precondition")
+    return noisy, x_in
+
+
+def edm_loss(pred: torch.Tensor, noisy: torch.Tensor, target: torch.Tensor, sigma: torch.Tensor, Cpad: int,
+             grad_scale: float = 1.0, want_grad: bool = True):
+    """pred fp32 rows [B*F*H*W, ld] -> (loss: device double scalar tensor, dpred bf16 rows [B*F*H*W, Cpad] | None)."""
+    _need_cuda(pred, noisy, target, sigma)
+    B, F, Cn, H, W = noisy.shape
+    if pred.dtype != torch.float32 or pred.dim() != 2 or pred.stride(1) != 1 or pred.shape[0] != B * F * H * W:
+        raise ValueError("edm_loss: pred must be fp32 rows [B*F*H*W, >=C]")
+    for t in (noisy, target, sigma):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("edm_loss: contiguous fp32 tensors expected")
+    loss = torch.empty((), device=pred.device, dtype=torch.float64)
+    dpred = torch.empty((B * F * H * W, Cpad), device=pred.device, dtype=bf16) if want_grad else None
+    L.check(L.load().lkgd_edm_loss(pred.data_ptr(), pred.stride(0), noisy.data_ptr(), target.data_ptr(),
+                                   sigma.data_ptr(), loss.data_ptr(), _ptr(dpred), B, F, Cn, H, W, Cpad, grad_scale,
+                                   _stream()), "lkgd_edm_loss")
+    return loss, dpred
+
+
+def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("sumsq: contiguous fp32 tensor expected")
+    if out is None:
+        out = torch.empty((), device=x.device, dtype=torch.float64)
+    L.check(L.load().lkgd_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "lkgd_sumsq")
+    return out
+
+
+def adamw(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, beta1: float = 0.9,
+          beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 1e-2, step: int, grad_scale: float = 1.0,
+          sumsq_buf: Optional[torch.Tensor] = None, max_norm: float = 0.0):
+    _need_cuda(p, g, m, v, sumsq_buf)
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise ValueError("adamw: flat contiguous fp32 buffers of equal size expected")
+    L.check(L.load().lkgd_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                eps, weight_decay, step, grad_scale, _ptr(sumsq_buf), max_norm, _stream()),
+            "lkgd_adamw")
+
+
+def cast2d_bf16(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """dst (bf16, 2-D, row pitch free) = alpha * src (fp32, 2-D, row pitch free)."""
+    _need_cuda(src, dst)
+    if src.dtype != torch.float32 or dst.dtype != bf16 or src.dim() != 2 or dst.shape != src.shape \
+            or src.stride(1) != 1 or dst.stride(1) != 1:
+        raise ValueError("cast2d_bf16: fp32 -> bf16 2-D tensors of equal shape with unit column stride")
+    L.check(L.load().lkgd_cast2d_bf16(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
+                                      src.shape[1], alpha, _stream()), "lkgd_cast2d_bf16")
+    return dst
