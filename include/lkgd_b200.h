@@ -262,16 +262,18 @@ LKGD_API int lkgd_layernorm_bwd(const float* x, const void* dy, int32_t dy_f32, 
 LKGD_API int lkgd_geglu_fwd(const void* pre, void* out, int64_t M, int32_t H, void* stream);
 LKGD_API int lkgd_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int32_t H, void* stream);
 /* out[g(m), c] += G[m, c]: gradient of the per-context vectors added by LayerNorm's addvec (rv modes as above;
- * n_groups <= 8; out must be zero-initialised by the caller, fp32 [n_groups, C]). */
+ * n_groups <= 8; out must be zero-initialised by the caller, fp32 [n_groups, C] with row pitch ldo). */
 LKGD_API int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t rv_mode, int32_t rv_HW, int32_t rv_F,
-                                 int32_t rv_B, int32_t n_groups, float* out, void* stream);
+                                 int32_t rv_B, int32_t n_groups, float* out, int64_t ldo, void* stream);
 /* Nearest-2x upsample backward: out fp32 [N,H,W,C] = 2x2 block sums of in [N,2H,2W,C] (bf16 / fp32). */
 LKGD_API int lkgd_downsum2x(const void* in, int32_t in_f32, float* out, int32_t N, int32_t H, int32_t W, int32_t C,
                             void* stream);
 /* Stride-2 conv data gradient helper: out bf16 [N,Hin,Win,C], out[2ho,2wo] = in[ho,wo] (in [N,Ho,Wo,C]), else 0. */
 LKGD_API int lkgd_zero_stuff2x(const void* in, int32_t in_f32, void* out, int32_t N, int32_t Hin, int32_t Win, int32_t C,
                                void* stream);
-/* out[i, j] += alpha * sum_m X[m, i] * Y[m, j]: LoRA weight gradients (models/lora_layer.py:437 under autograd). */
+/* out[i, j] += alpha * sum_m X[m, i] * Y[m, j]: LoRA weight gradients (models/lora_layer.py:437 under autograd).
+ * X / Y rows are read in 8-column pieces: when I or J is not a multiple of 8 the rows must be readable up to the next
+ * multiple (a column slice of a wider, padded matrix). */
 LKGD_API int lkgd_gemm_tn(const void* X, int64_t ldx, int32_t I, const void* Y, int64_t ldy, int32_t J, int64_t M,
                           float alpha, float* out, int64_t ldo, void* stream);
 /* EDM training wrapper (train_svd_lora.py:1503-1530): noisy = latents + noise * sigma[b] (fp32 [B,F,C,H,W]);
@@ -292,10 +294,10 @@ LKGD_API int lkgd_sumsq(const float* x, int64_t n, double* out, void* stream);
 LKGD_API int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, int32_t step, float grad_scale, const double* sumsq,
                         float max_norm, void* stream);
-/* dst[r, c] = bf16(alpha * src[r, c]) with row pitches (repacking fp32 master LoRA weights into the GEMM operands,
+/* dst[r*ldd + c] = bf16(alpha * src[r*lds + c*src_cs]) (src_cs = 1: plain; = pitch of a transposed view) (repacking fp32 master LoRA weights into the GEMM operands,
  * scaled bf16 copies of gradient tensors). */
-LKGD_API int lkgd_cast2d_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
-                              float alpha, void* stream);
+LKGD_API int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, void* dst, int64_t ldd, int32_t rows,
+                              int32_t cols, float alpha, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,7 @@ SIGNATURES = {
     "lkgd_layernorm_bwd": (i32, [vp, vp, i32, i32, i32, vp, f32, vp, i32, vp, vp]),
     "lkgd_geglu_fwd": (i32, [vp, vp, i64, i32, vp]),
     "lkgd_geglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
-    "lkgd_colsum_grouped": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "lkgd_colsum_grouped": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
     "lkgd_downsum2x": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "lkgd_zero_stuff2x": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "lkgd_gemm_tn": (i32, [vp, i64, i32, vp, i64, i32, i64, f32, vp, i64, vp]),
@@ -82,7 +82,7 @@ SIGNATURES = {
     "lkgd_edm_loss": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_sumsq": (i32, [vp, i64, vp, vp]),
     "lkgd_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
-    "lkgd_cast2d_bf16": (i32, [vp, i64, vp, i64, i32, i32, f32, vp]),
+    "lkgd_cast2d_bf16": (i32, [vp, i64, i64, vp, i64, i32, i32, f32, vp]),
 }
 
 _lib = None

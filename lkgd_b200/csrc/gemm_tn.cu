@@ -94,7 +94,7 @@ using namespace lkgd;
 
 extern "C" int lkgd_gemm_tn(const void* X, int64_t ldx, int32_t I, const void* Y, int64_t ldy, int32_t J, int64_t M,
                             float alpha, float* out, int64_t ldo, void* stream) {
-  if (I <= 0 || J <= 0 || M <= 0 || I % 8 || J % 8) return LKGD_ESHAPE;
+  if (I <= 0 || J <= 0 || M <= 0) return LKGD_ESHAPE;
   if (ldx % 8 || ldy % 8 || !aligned16(X) || !aligned16(Y)) return LKGD_EALIGN;
   const int gi = (I + 63) / 64, gj = (J + 63) / 64;
   long long splits = (2LL * sm_count() + gi * gj - 1) / (gi * gj);

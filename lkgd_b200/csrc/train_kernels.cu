@@ -337,7 +337,7 @@ __device__ __forceinline__ int rv_index(int mode, long long m, int HW, int F, in
 constexpr int CS_MAXG = 8;
 // grid (col blocks of 128 columns, row chunks); thread = one column over a chunk of rows, up to CS_MAXG groups
 __global__ void colsum_grouped_kernel(const float* __restrict__ G, long long M, int C, int rows_per_cta, int mode, int HW,
-                                      int F, int B, int n_groups, float* __restrict__ out) {
+                                      int F, int B, int n_groups, float* __restrict__ out, long long ldo) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
@@ -353,7 +353,7 @@ __global__ void colsum_grouped_kernel(const float* __restrict__ G, long long M, 
   }
 #pragma unroll
   for (int i = 0; i < CS_MAXG; ++i)
-    if (i < n_groups && acc[i] != 0.f) atomicAdd(out + (size_t)i * C + c, acc[i]);
+    if (i < n_groups && acc[i] != 0.f) atomicAdd(out + (size_t)i * ldo + c, acc[i]);
 }
 
 // ------------------------------------------------------------------------------------------- resampling gradients
@@ -515,13 +515,13 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
-__global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
-                                   long long ldd, int rows, int cols, float alpha) {
+__global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds, long long cs,
+                                   __nv_bfloat16* __restrict__ dst, long long ldd, int rows, int cols, float alpha) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * cols) return;
   const long long r = idx / cols;
   const int c = (int)(idx % cols);
-  dst[r * ldd + c] = __float2bfloat16(src[r * lds + c] * alpha);
+  dst[r * ldd + c] = __float2bfloat16(src[r * lds + c * cs] * alpha);
 }
 
 static GnbGeom gnb_geom(int C1, int C2, int R, int x_f32, int groups, int silu, float eps) {
@@ -624,15 +624,15 @@ extern "C" int lkgd_geglu_bwd(const void* pre, const void* dout, void* dpre, int
 }
 
 extern "C" int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t rv_mode, int32_t rv_HW, int32_t rv_F,
-                                   int32_t rv_B, int32_t n_groups, float* out, void* stream) {
-  if (M <= 0 || C <= 0 || n_groups <= 0 || n_groups > CS_MAXG) return LKGD_ESHAPE;
+                                   int32_t rv_B, int32_t n_groups, float* out, int64_t ldo, void* stream) {
+  if (M <= 0 || C <= 0 || n_groups <= 0 || n_groups > CS_MAXG || ldo < C) return LKGD_ESHAPE;
   if (rv_HW <= 0) rv_HW = 1;
   if (rv_F <= 0) rv_F = 1;
   if (rv_B <= 0) rv_B = 1;
   const int rows_per_cta = 256;
   dim3 grid((C + 127) / 128, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
   colsum_grouped_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, rv_mode, rv_HW,
-                                                                                   rv_F, rv_B, n_groups, out);
+                                                                                   rv_F, rv_B, n_groups, out, ldo);
   return launch_epilogue();
 }
 
@@ -706,11 +706,11 @@ extern "C" int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t 
   return launch_epilogue();
 }
 
-extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows, int32_t cols,
-                                float alpha, void* stream) {
-  if (rows <= 0 || cols <= 0 || lds < cols || ldd < cols) return LKGD_ESHAPE;
+extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, void* dst, int64_t ldd, int32_t rows,
+                                int32_t cols, float alpha, void* stream) {
+  if (rows <= 0 || cols <= 0 || ldd < cols || src_cs <= 0) return LKGD_ESHAPE;
   const long long n = (long long)rows * cols;
   cast2d_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
+      src, lds, src_cs, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
   return launch_epilogue();
 }

@@ -184,6 +184,7 @@ class PackedCross:
 class PackedTransformer:
     def __init__(self, t: M.TransformerSpatioTemporalModel, fold_lora: bool):
         self.heads, self.d, self.c = t.heads, t.dim_head, t.in_channels
+        self.src = t                # the module (training looks up the LoRA parameters it owns)
         self.norm = Norm.of(t.norm)
         self.proj_in, self.proj_out = _dense(t.proj_in, fold_lora), _dense(t.proj_out, fold_lora)
         sb, tb = t.transformer_blocks[0], t.temporal_transformer_blocks[0]

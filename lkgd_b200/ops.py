@@ -527,10 +527,10 @@ def colsum_grouped(G: torch.Tensor, n_groups: int, rv: Tuple[int, int, int, int]
     M, Cn = G.shape
     if out is None:
         out = torch.zeros((n_groups, Cn), device=G.device, dtype=torch.float32)
-    elif out.dtype != torch.float32 or not out.is_contiguous() or out.shape != (n_groups, Cn):
-        raise ValueError("colsum_grouped: out must be contiguous fp32 [n_groups, C]")
+    elif out.dtype != torch.float32 or out.stride(1) != 1 or out.shape != (n_groups, Cn):
+        raise ValueError("colsum_grouped: out must be fp32 [n_groups, C] with unit column stride")
     L.check(L.load().lkgd_colsum_grouped(G.data_ptr(), M, Cn, rv[0], rv[1], rv[2], rv[3], n_groups, out.data_ptr(),
-                                         _stream()), "lkgd_colsum_grouped")
+                                         out.stride(0), _stream()), "lkgd_colsum_grouped")
     return out
 
 
@@ -633,11 +633,11 @@ def adamw(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *,
 
 
 def cast2d_bf16(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
-    """dst (bf16, 2-D, row pitch free) = alpha * src (fp32, 2-D, row pitch free)."""
+    """dst (bf16, 2-D, row pitch free) = alpha * src (fp32, 2-D, any strides: transposed views allowed)."""
     _need_cuda(src, dst)
     if src.dtype != torch.float32 or dst.dtype != bf16 or src.dim() != 2 or dst.shape != src.shape \
-            or src.stride(1) != 1 or dst.stride(1) != 1:
-        raise ValueError("cast2d_bf16: fp32 -> bf16 2-D tensors of equal shape with unit column stride")
-    L.check(L.load().lkgd_cast2d_bf16(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
-                                      src.shape[1], alpha, _stream()), "lkgd_cast2d_bf16")
+            or dst.stride(1) != 1:
+        raise ValueError("cast2d_bf16: fp32 -> bf16 2-D tensors of equal shape, dst with unit column stride")
+    L.check(L.load().lkgd_cast2d_bf16(src.data_ptr(), src.stride(0), src.stride(1), dst.data_ptr(), dst.stride(0),
+                                      src.shape[0], src.shape[1], alpha, _stream()), "lkgd_cast2d_bf16")
     return dst

@@ -1,0 +1,451 @@
+"""LoRA fine-tuning step of the SVD / LKGD UNet on the lkgd_b200 kernels: forward with saved activations, a
+hand-scheduled backward through the block graph, LoRA weight gradients, fused clip + AdamW, one flat all-reduce.
+
+Mirrors one iteration of the reference training loop ``train_models/train_svd_lora.py:1445-1689``:
+EDM noising + input preconditioning (:1503-1530), ``unet(inp_noisy_latents, timesteps, encoder_hidden_states,
+[domain_features, flow_features,] added_time_ids=...)`` (:1634-1642), the v-prediction wrapper and weighted MSE
+(:1651-1672), ``accelerator.backward`` (:1683), ``clip_grad_norm_`` (:1684-1686), ``optimizer.step`` (:1687), and the
+DDP gradient all-reduce that ``accelerator.prepare`` installs (:1300-1302).  Trainable parameters are the LoRA pairs
+on ``temporal_transformer_blocks.*.attn1.to_{q,k,v}`` (:1081-1088); every other weight is frozen, so the backward only
+propagates data gradients (GEMMs / convolutions re-run with transposed, tap-flipped weights on the same tcgen05
+kernel) plus the two skinny weight-gradient GEMMs per LoRA pair.
+
+There is no autograd here and no PyTorch compute: the backward schedule is written out per block, the gradient of the
+residual stream is kept in fp32 like the forward stream, GEMM operands are bf16.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace as NS
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import modules as M
+from . import ops
+from .engine import (Conditioning, Geom, PackedResBlock, PackedTransformer, PackedUNet, dense)
+from .ops import A_CONV3X3, A_TCONV3, RV_BATCH, RV_FRAMEPOS, bf16
+
+
+# ------------------------------------------------------------------------------------------------- data-gradient weights
+def _t(w: torch.Tensor) -> torch.Tensor:
+    return w.t().contiguous()
+
+
+def _conv_dgrad(w: torch.Tensor, taps: int) -> torch.Tensor:
+    """[Co, taps*Ci] ([Co, tap, Ci]) -> [Ci, taps*Co] with the taps reversed: the data gradient of a stride-1 'same'
+    convolution is the convolution of the output gradient with the flipped, channel-swapped kernel."""
+    co = w.shape[0]
+    ci = w.shape[1] // taps
+    return w.reshape(co, taps, ci).flip(1).permute(2, 1, 0).reshape(ci, taps * co).contiguous()
+
+
+def res_train_weights(p: PackedResBlock) -> NS:
+    if getattr(p, "_tw", None) is None:
+        p._tw = NS(w1=_conv_dgrad(p.w1, 9), w2=_conv_dgrad(p.w2, 9), tw1=_conv_dgrad(p.tw1, 3),
+                   tw2=_conv_dgrad(p.tw2, 3), wsc=None if p.wsc is None else _t(p.wsc))
+    return p._tw
+
+
+def tr_train_weights(p: PackedTransformer) -> NS:
+    if getattr(p, "_tw", None) is None:
+        for d in (p.proj_in, p.proj_out, p.s_qkv, p.s_out, p.s_ff2, p.t_ffin2, p.t_out, p.t_ff2, p.s_ff1, p.t_ffin1,
+                  p.t_ff1):
+            if d.lora_a is not None:
+                raise NotImplementedError("training supports LoRA on the temporal attn1 q/k/v projections only "
+                                          "(the reference's adapter config, train_svd_lora.py:1081-1088)")
+        p._tw = NS(proj_in=_t(p.proj_in.w), proj_out=_t(p.proj_out.w), s_qkv=_t(p.s_qkv.w), s_out=_t(p.s_out.w),
+                   s_ff1=_t(p.s_ff1.w), s_ff2=_t(p.s_ff2.w), t_ffin1=_t(p.t_ffin1.w), t_ffin2=_t(p.t_ffin2.w),
+                   t_qkv=_t(p.t_qkv.w), t_out=_t(p.t_out.w), t_ff1=_t(p.t_ff1.w), t_ff2=_t(p.t_ff2.w),
+                   lora_aT=None if p.t_qkv.lora_a is None else _t(p.t_qkv.lora_a),
+                   lora_bT=None if p.t_qkv.lora_b is None else _t(p.t_qkv.lora_b))
+    return p._tw
+
+
+# ------------------------------------------------------------------------------------------------- resblock
+def resblock_fwd(p: PackedResBlock, x, skip, g: Geom, cond: Conditioning):
+    """engine.run_resblock with the tensors the backward needs kept (GroupNorm inputs + statistics)."""
+    S = NS(x=x, skip=skip)
+    h, S.st1 = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True, return_stats=True)
+    S.c1 = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=cond.temb(p.off_s, p.cout),
+                    rv=g.rv(RV_BATCH), out_f32=True)
+    h, S.st2 = ops.groupnorm(S.c1, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True, return_stats=True)
+    if p.wsc is not None:
+        xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
+        sc = ops.gemm(xa, p.wsc, bias=p.bsc, out_f32=True)
+    else:
+        if skip is not None:
+            raise ValueError("resblock with concatenated input must have a shortcut conv")
+        sc = x
+    S.s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True)
+    t, S.st3 = ops.groupnorm(S.s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True, return_stats=True)
+    S.c3 = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=cond.temb(p.off_t, p.cout),
+                    rv=g.rv(RV_BATCH), out_f32=True)
+    t, S.st4 = ops.groupnorm(S.c3, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True, return_stats=True)
+    out = ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=S.s, s1=1.0,
+                   out_f32=True)
+    return out, S
+
+
+def resblock_bwd(p: PackedResBlock, S, G: torch.Tensor, g: Geom):
+    """G: fp32 gradient of the block output (consumed: overwritten with the gradient of ``s``).  Returns
+    (dx fp32 [M, C1], dskip fp32 [M, C2] | None)."""
+    tw = res_train_weights(p)
+    M_, C = G.shape
+    tc = dict(mode=A_TCONV3, tconv=(g.B, g.F, g.HW))
+    cv = dict(mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1))
+    # out = s + (1 - alpha) * (tconv2(t2) + b)
+    gb = torch.empty((M_, C), device=G.device, dtype=bf16)
+    ops.cast2d_bf16(G, gb, alpha=1.0 - p.alpha)
+    d = ops.gemm(gb, tw.tw2, **tc)                                           # d t2
+    ops.groupnorm_bwd(S.c3, d, S.st4, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True, out_bf16=gb)
+    d = ops.gemm(gb, tw.tw1, **tc)                                           # d t1
+    ops.groupnorm_bwd(S.s, d, S.st3, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True, out1=G, acc1=True,
+                      out_bf16=gb)                                           # G = ds (fp32), gb = bf16(ds)
+    d = ops.gemm(gb, tw.w2, **cv)                                            # d h2
+    dc1 = torch.empty_like(d)
+    ops.groupnorm_bwd(S.c1, d, S.st2, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True, out_bf16=dc1)
+    d = ops.gemm(dc1, tw.w1, **cv)                                           # d h1 [M, C1 + C2]
+    add = ops.gemm(gb, tw.wsc) if tw.wsc is not None else G                  # shortcut path
+    c1 = S.x.shape[1]
+    dx = torch.empty((M_, c1), device=G.device, dtype=torch.float32)
+    dskip = None if S.skip is None else torch.empty((M_, S.skip.shape[1]), device=G.device, dtype=torch.float32)
+    ops.groupnorm_bwd(S.x, d, S.st1, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=S.skip, silu=True, add=add,
+                      out1=dx, out2=dskip)
+    return dx, dskip
+
+
+# ------------------------------------------------------------------------------------------------- transformer
+def _ff_fwd(n, d1, d2, **kw):
+    pre = ops.gemm(n, d1.w, bias=d1.b)             # tile-interleaved [M, 8C]; GEGLU applied by its own kernel so the
+    return pre, dense(ops.geglu_fwd(pre), d2, **kw)  # backward can re-read the pre-activation
+
+
+def transformer_fwd(p: PackedTransformer, x, g: Geom, cond: Conditioning, tctx_mode: int):
+    if cond.ctx.shape[1] != 1:
+        raise NotImplementedError("training covers the KV-length-1 context the reference always uses (SURVEY F7)")
+    C = p.c
+    S = NS(x=x)
+    h, S.st0 = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False, return_stats=True)
+    S.h_a = dense(h, p.proj_in, out_f32=True)
+    n = ops.layernorm(S.h_a, p.s_ln1.g, p.s_ln1.b, p.s_ln1.eps)
+    S.s_qkv = dense(n, p.s_qkv)
+    S.s_o, S.s_lse = ops.attention(S.s_qkv[:, :C], S.s_qkv[:, C:2 * C], S.s_qkv[:, 2 * C:], n_img=g.BF, heads=p.heads,
+                                   d=p.d, Nq=g.HW, Nk=g.HW, return_lse=True)
+    S.h_b = dense(S.s_o, p.s_out, res1=S.h_a, out_f32=True)
+    n = ops.layernorm(S.h_b, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross), rv=g.rv(RV_BATCH),
+                      sum_out=S.h_b)
+    S.s_pre, S.xs = _ff_fwd(n, p.s_ff1, p.s_ff2, res1=S.h_b, out_f32=True)
+    S.t0 = torch.empty_like(S.xs)
+    n = ops.layernorm(S.xs, p.t_lnin.g, p.t_lnin.b, p.t_lnin.eps, addvec=p.pos_emb(g.F), rv=g.rv(RV_FRAMEPOS),
+                      sum_out=S.t0)
+    S.t_pre_in, S.t_a = _ff_fwd(n, p.t_ffin1, p.t_ffin2, res1=S.t0, out_f32=True)
+    S.t_n1 = ops.layernorm(S.t_a, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
+    q = p.t_qkv
+    if q.lora_a is not None:
+        S.t_tl = ops.gemm(S.t_n1, q.lora_a)
+        S.t_qkv = ops.gemm(S.t_n1, q.w, bias=q.b, A1=S.t_tl, Bw1=q.lora_b)
+    else:
+        S.t_tl = None
+        S.t_qkv = ops.gemm(S.t_n1, q.w, bias=q.b)
+    a = ops.attention_temporal(S.t_qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
+    S.t_b = dense(a, p.t_out, res1=S.t_a, out_f32=True)
+    S.n_tctx = cond.ctx_t.shape[0]
+    n = ops.layernorm(S.t_b, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
+                      rv=(tctx_mode, g.HW, g.F, S.n_tctx), sum_out=S.t_b)
+    S.t_pre, mix = _ff_fwd(n, p.t_ff1, p.t_ff2, s0=1.0 - p.alpha, res1=S.t_b, s1=1.0 - p.alpha, res2=S.xs, s2=p.alpha)
+    out = dense(mix, p.proj_out, res1=x, out_f32=True)
+    return out, S
+
+
+def _ff_bwd(gb, pre, w2T, w1T):
+    """bf16 gradient of the feed-forward output -> bf16 gradient of its (LayerNorm-ed) input."""
+    return ops.gemm(ops.geglu_bwd(pre, ops.gemm(gb, w2T)), w1T)
+
+
+def transformer_bwd(p: PackedTransformer, S, G: torch.Tensor, g: Geom, tctx_mode: int, lora_grads=None,
+                    cross_grads=None):
+    """G: fp32 gradient of the transformer output; overwritten with the gradient of its input ``x`` and returned.
+    ``lora_grads``: dict with fp32 ``A`` [3, r, C] and ``B`` [3, C, r] accumulators of this layer's q/k/v adapters
+    (+ ``scaling``).  ``cross_grads``: (d_xs [B, C] view, d_xt [n_ctx, C] view) accumulators of the two KV-length-1
+    cross-attention vectors (LKGD conditioning gradient)."""
+    tw = tr_train_weights(p)
+    M_, C = G.shape
+    dev = G.device
+    gb = ops.cast_bf16(G)
+    dmix = ops.gemm(gb, tw.proj_out, out_f32=True)                # mix = (1-a)(ff + t_b) + a xs
+    Gt = ops.scale_f32(dmix, 1.0 - p.alpha)
+    ops.cast2d_bf16(dmix, gb, alpha=1.0 - p.alpha)
+    # ---- temporal block, last to first
+    ops.layernorm_bwd(S.t_b, _ff_bwd(gb, S.t_pre, tw.t_ff2, tw.t_ff1), p.t_ln3.g, p.t_ln3.eps, Gt, g_bf16=gb)
+    if cross_grads is not None:
+        ops.colsum_grouped(Gt, S.n_tctx, (tctx_mode, g.HW, g.F, S.n_tctx), out=cross_grads[1])
+    da = ops.gemm(gb, tw.t_out)
+    dqkv = ops.attention_temporal_bwd(S.t_qkv, da, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
+    if S.t_tl is not None:
+        dtl = ops.gemm(dqkv, tw.lora_bT)                          # [M, 3 r_pad]
+        if lora_grads is not None:
+            r = lora_grads["A"].shape[1]
+            r_pad = S.t_tl.shape[1] // 3
+            for i in range(3):
+                ops.gemm_tn(dqkv[:, i * C:(i + 1) * C], S.t_tl[:, i * r_pad:i * r_pad + r], lora_grads["B"][i],
+                            alpha=lora_grads["scaling"])
+                ops.gemm_tn(dtl[:, i * r_pad:i * r_pad + r], S.t_n1, lora_grads["A"][i])
+        dn = ops.gemm(dqkv, tw.t_qkv, A1=dtl, Bw1=tw.lora_aT)
+    else:
+        dn = ops.gemm(dqkv, tw.t_qkv)
+    ops.layernorm_bwd(S.t_a, dn, p.t_ln1.g, p.t_ln1.eps, Gt, g_bf16=gb)
+    ops.layernorm_bwd(S.t0, _ff_bwd(gb, S.t_pre_in, tw.t_ffin2, tw.t_ffin1), p.t_lnin.g, p.t_lnin.eps, Gt)
+    # ---- spatial block: d xs = d t0 + alpha * d mix
+    ops.axpby(dmix, p.alpha, Gt, 1.0)
+    Gs = Gt
+    ops.cast2d_bf16(Gs, gb)
+    ops.layernorm_bwd(S.h_b, _ff_bwd(gb, S.s_pre, tw.s_ff2, tw.s_ff1), p.s_ln3.g, p.s_ln3.eps, Gs, g_bf16=gb)
+    if cross_grads is not None:
+        ops.colsum_grouped(Gs, g.B, g.rv(RV_BATCH), out=cross_grads[0])
+    da = ops.gemm(gb, tw.s_out)
+    dqkv = torch.empty((M_, 3 * C), device=dev, dtype=bf16)
+    ops.attention_bwd(S.s_qkv[:, :C], S.s_qkv[:, C:2 * C], S.s_qkv[:, 2 * C:], S.s_o, da, S.s_lse, dqkv[:, :C],
+                      dqkv[:, C:2 * C], dqkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, N=g.HW)
+    ops.layernorm_bwd(S.h_a, ops.gemm(dqkv, tw.s_qkv), p.s_ln1.g, p.s_ln1.eps, Gs, g_bf16=gb)
+    dh0 = ops.gemm(gb, tw.proj_in)
+    ops.groupnorm_bwd(S.x, dh0, S.st0, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False, out1=G, acc1=True)
+    return G
+
+
+# ------------------------------------------------------------------------------------------------- whole UNet
+class TrainGraph:
+    """Forward-with-save / backward of a PackedUNet.  One instance per step (holds the saved activations)."""
+
+    def __init__(self, pk: PackedUNet):
+        self.pk = pk
+        self.tape: List[Tuple] = []
+
+    # ---- forward: PackedUNet.encoder + decoder with a tape
+    def forward(self, x: torch.Tensor, g: Geom, cond: Conditioning) -> torch.Tensor:
+        pk, tape = self.pk, self.tape
+        tm = pk.tctx_mode
+        x = ops.gemm(x, pk.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=pk.conv_in_b, out_f32=True)
+        skips = [x]
+        tape.append(("skip", 0))
+        for res, att, ds in pk.down:
+            for i, r in enumerate(res):
+                x, S = resblock_fwd(r, x, None, g, cond)
+                tape.append(("res", r, S, g, None))
+                if att is not None:
+                    x, S = transformer_fwd(att[i], x, g, cond, tm)
+                    tape.append(("tr", att[i], S, g))
+                tape.append(("skip", len(skips)))
+                skips.append(x)
+            if ds is not None:
+                gin = g
+                x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1], out_f32=True)
+                g = g.down()
+                tape.append(("down", ds, gin))
+                tape.append(("skip", len(skips)))
+                skips.append(x)
+        res, att = pk.mid
+        x, S = resblock_fwd(res[0], x, None, g, cond)
+        tape.append(("res", res[0], S, g, None))
+        for a, r in zip(att, res[1:]):
+            x, S = transformer_fwd(a, x, g, cond, tm)
+            tape.append(("tr", a, S, g))
+            x, S = resblock_fwd(r, x, None, g, cond)
+            tape.append(("res", r, S, g, None))
+        for res, att, us in pk.up:
+            for i, r in enumerate(res):
+                k = len(skips) - 1
+                x, S = resblock_fwd(r, x, skips.pop(), g, cond)
+                tape.append(("res", r, S, g, k))
+                if att is not None:
+                    x, S = transformer_fwd(att[i], x, g, cond, tm)
+                    tape.append(("tr", att[i], S, g))
+            if us is not None:
+                gin = g
+                x = ops.upsample2x(x, g.BF, g.H, g.W)
+                g = g.up()
+                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True)
+                tape.append(("up", us, gin, g))
+        h, st = ops.groupnorm(x, pk.norm_out.g, pk.norm_out.b, pk.norm_out.eps, NS=g.BF, R=g.HW, silu=True,
+                              return_stats=True)
+        tape.append(("out", x, st, g))
+        return ops.gemm(h, pk.conv_out_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=pk.conv_out_b, out_f32=True,
+                        n_store=pk.cout)
+
+    # ---- backward
+    def backward(self, dpred: torch.Tensor, lora_grads: Optional[Dict] = None, cross_grads=None):
+        """dpred: bf16 rows [M, conv_out_w.shape[0]] (gradient of the prediction, zero padded).  Walks the tape in
+        reverse; stops below the first (in forward order) block that owns a trainable parameter."""
+        pk = self.pk
+        tm = pk.tctx_mode
+        tw = getattr(pk, "_tw", None)
+        if tw is None:
+            tw = pk._tw = NS(conv_out=_conv_dgrad(pk.conv_out_w, 9),
+                             ups={id(b[2]): _conv_dgrad(b[2][0], 9) for b in pk.up if b[2] is not None},
+                             downs={id(b[2]): _conv_dgrad(b[2][0], 9) for b in pk.down if b[2] is not None})
+        first_tr = next(i for i, e in enumerate(self.tape) if e[0] == "tr")
+        dskips: Dict[int, torch.Tensor] = {}
+        G = None
+        for idx in range(len(self.tape) - 1, first_tr - 1, -1):
+            e = self.tape[idx]
+            kind = e[0]
+            if kind == "out":
+                _, x, st, g = e
+                dh = ops.gemm(dpred, tw.conv_out, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1))
+                G = torch.empty_like(x)
+                ops.groupnorm_bwd(x, dh, st, pk.norm_out.g, pk.norm_out.b, pk.norm_out.eps, NS=g.BF, R=g.HW, silu=True,
+                                  out1=G)
+            elif kind == "up":
+                _, us, gin, gout = e
+                d = ops.gemm(ops.cast_bf16(G), tw.ups[id(us)], mode=A_CONV3X3, conv=(gout.BF, gout.H, gout.W, 1))
+                G = ops.downsum2x(d, gin.BF, gin.H, gin.W)
+            elif kind == "down":
+                _, ds, gin = e
+                z = ops.zero_stuff2x(G, gin.BF, gin.H, gin.W)
+                G = ops.gemm(z, tw.downs[id(ds)], mode=A_CONV3X3, conv=(gin.BF, gin.H, gin.W, 1), out_f32=True)
+            elif kind == "skip":
+                k = e[1]
+                if k in dskips:
+                    ops.axpby(dskips.pop(k), 1.0, G, 1.0)
+            elif kind == "tr":
+                _, p, S, g = e
+                lg = None if lora_grads is None else lora_grads.get(id(p))
+                cg = None if cross_grads is None else cross_grads(p)
+                G = transformer_bwd(p, S, G, g, tm, lg, cg)
+            elif kind == "res":
+                _, p, S, g, k = e
+                G, dskip = resblock_bwd(p, S, G, g)
+                if dskip is not None:
+                    dskips[k] = dskip
+        self.tape = []
+        return G
+
+
+# ------------------------------------------------------------------------------------------------- trainer
+class LoraTrainer:
+    """Owns the trainable state of a LoRA fine-tuning run: ONE flat fp32 parameter buffer (the module's LoRA
+    parameters become views of it), flat gradient / Adam moment buffers, the bf16 GEMM operands derived from the
+    parameters, and the step: forward -> loss -> backward -> [all-reduce] -> clip -> AdamW -> repack.
+
+    ``group``: a ``torch.distributed`` process group (or None): the flat gradient is summed across ranks with one
+    ``all_reduce`` per step and averaged inside the optimizer kernel - the data-parallel gradient sync the reference
+    gets from DDP (train_svd_lora.py:1300-1302)."""
+
+    def __init__(self, unet, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
+                 max_grad_norm: float = 1.0, group=None, world_size: int = 1):
+        self.unet, self.group, self.world = unet, group, world_size
+        self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
+        self.step_count = 0
+        if not getattr(unet, "fold_lora", True):
+            raise ValueError("training needs the LoRA pairs folded into the GEMM (fold_lora=True)")
+        pk = unet.packed()
+        self.layers = [a for blk in pk.down if blk[1] for a in blk[1]] + list(pk.mid[1]) + \
+                      [a for blk in pk.up if blk[1] for a in blk[1]]
+        mods = []
+        for p in self.layers:
+            attn = p.src.temporal_transformer_blocks[0].attn1
+            trio = (attn.to_q, attn.to_k, attn.to_v)
+            if not all(isinstance(m, M.LoraLinear) and not m.merged for m in trio):
+                raise ValueError("every temporal attn1 q/k/v projection must carry an unmerged LoRA adapter "
+                                 "(unet.add_lora(r) with the default target)")
+            mods.append(trio)
+        r = mods[0][0].r
+        dev = unet.device
+        n = sum(3 * 2 * r * p.c for p in self.layers)
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.sumsq = torch.zeros((), device=dev, dtype=torch.float64)
+        self.slots: Dict[int, Dict] = {}
+        off = 0
+        with torch.no_grad():
+            for p, trio in zip(self.layers, mods):
+                C = p.c
+                pa = self.flat_p[off:off + 3 * r * C].view(3, r, C)
+                ga = self.flat_g[off:off + 3 * r * C].view(3, r, C)
+                off += 3 * r * C
+                pb = self.flat_p[off:off + 3 * C * r].view(3, C, r)
+                gb = self.flat_g[off:off + 3 * C * r].view(3, C, r)
+                off += 3 * C * r
+                for i, m in enumerate(trio):
+                    a, b = m.lora_A[m.adapter_name].weight, m.lora_B[m.adapter_name].weight
+                    pa[i].copy_(a)
+                    pb[i].copy_(b)
+                    a.data, b.data = pa[i], pb[i]          # the module's parameters now alias the flat buffer
+                self.slots[id(p)] = dict(A=ga, B=gb, pA=pa, pB=pb, scaling=float(trio[0].scaling), r=r)
+        self.repack()
+
+    # ---- fp32 master parameters -> the bf16 operands the GEMMs read (forward: A_cat, B_blk; backward: transposes)
+    def repack(self):
+        for p in self.layers:
+            s = self.slots[id(p)]
+            tw = tr_train_weights(p)
+            C, r = p.c, s["r"]
+            r_pad = p.t_qkv.lora_a.shape[0] // 3
+            for i in range(3):
+                ops.cast2d_bf16(s["pA"][i], p.t_qkv.lora_a[i * r_pad:i * r_pad + r])
+                ops.cast2d_bf16(s["pA"][i].t(), tw.lora_aT[:, i * r_pad:i * r_pad + r])
+                ops.cast2d_bf16(s["pB"][i], p.t_qkv.lora_b[i * C:(i + 1) * C, i * r_pad:i * r_pad + r], alpha=s["scaling"])
+                ops.cast2d_bf16(s["pB"][i].t(), tw.lora_bT[i * r_pad:i * r_pad + r, i * C:(i + 1) * C],
+                                alpha=s["scaling"])
+
+    def named_grads(self):
+        """(qualified parameter name, fp32 gradient view) in the reference's naming
+        (``...attn1.to_q.lora_A.<adapter>.weight``; train_svd_lora_train.txt)."""
+        names = {id(m): n for n, m in self.unet.named_modules()}
+        out = []
+        for p in self.layers:
+            attn = p.src.temporal_transformer_blocks[0].attn1
+            s = self.slots[id(p)]
+            for i, m in enumerate((attn.to_q, attn.to_k, attn.to_v)):
+                base = names[id(m)]
+                out.append((f"{base}.lora_A.{m.adapter_name}.weight", s["A"][i]))
+                out.append((f"{base}.lora_B.{m.adapter_name}.weight", s["B"][i]))
+        return out
+
+    # ---- one training step
+    def forward_backward(self, latents: torch.Tensor, noise: torch.Tensor, sigmas: torch.Tensor,
+                         cond_latents: torch.Tensor, encoder_hidden_states: torch.Tensor, added_time_ids: torch.Tensor,
+                         *extra, zero_grad: bool = True) -> torch.Tensor:
+        """latents / noise fp32 [B,F,4,h,w], sigmas fp32 [B], cond_latents fp32 [B,4,h,w] (first-frame latent, already
+        masked by the conditioning dropout), encoder_hidden_states [B,1,D], added_time_ids [B,3], extra =
+        (domain_features, flow_features) for the LKGD UNet.  Returns the loss (device double scalar); the LoRA
+        gradients are accumulated into the flat gradient buffer."""
+        unet = self.unet
+        pk = unet.packed()
+        dev = unet.device
+        B, F, Cl, h, w = latents.shape
+        f32 = torch.float32
+        latents, noise = latents.to(dev, f32).contiguous(), noise.to(dev, f32).contiguous()
+        sigmas = sigmas.to(dev, f32).contiguous()
+        if zero_grad:
+            self.flat_g.zero_()
+        noisy, x_in = ops.edm_precondition(latents, noise, sigmas, cond_latents.to(dev, f32).contiguous(), pk.cin_pad)
+        timesteps = 0.25 * torch.log(sigmas)                      # train_svd_lora.py:1508-1509 (host-side scalar math)
+        ctx = unet._context(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
+        emb = pk.time_embedding(timesteps, added_time_ids.to(dev))
+        cond = Conditioning(pk, emb, ctx)
+        g = Geom(B, F, h, w)
+        graph = TrainGraph(pk)
+        pred = graph.forward(x_in, g, cond)
+        loss, dpred = ops.edm_loss(pred, noisy, latents, sigmas, pk.conv_out_w.shape[0])
+        graph.backward(dpred, lora_grads=self.slots)
+        return loss
+
+    def optimizer_step(self):
+        """[all-reduce(sum)] -> grad-norm -> clip + AdamW (gradient averaged over ranks in-kernel) -> repack."""
+        if self.group is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        scale = 1.0 / self.world
+        ops.sumsq(self.flat_g, self.sumsq)
+        ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, beta1=self.betas[0],
+                  beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.step_count, grad_scale=scale,
+                  sumsq_buf=self.sumsq, max_norm=self.max_norm)
+        self.repack()
+
+    def train_step(self, *args, **kw) -> torch.Tensor:
+        loss = self.forward_backward(*args, **kw)
+        self.optimizer_step()
+        return loss

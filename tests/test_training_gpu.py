@@ -1,0 +1,117 @@
+"""Training-step parity on the GPU: loss and LoRA gradients of the hand-scheduled CUDA backward
+(lkgd_b200/training.py) against PyTorch autograd through the fp32 CPU oracle on identical weights and inputs -
+the computation the reference's ``accelerator.backward(loss)`` performs (train_models/train_svd_lora.py:1503-1530,
+1634-1642,1651-1683).  Tolerance: bf16 operands in ~400 chained GEMMs; per-tensor gradient rel-L2 <= 5e-2, all
+gradients together <= 3e-2, loss <= 1e-2 relative."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from test_unet_gpu import _pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _train_inputs(B, F, h, w, xdim, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(B, F, 4, h, w, generator=g)
+    noise = torch.randn(B, F, 4, h, w, generator=g)
+    cond = torch.randn(B, 4, h, w, generator=g)
+    ctx = torch.randn(B, 1, xdim, generator=g)
+    sig = torch.tensor([0.8, 3.0, 0.3, 11.0][:B])
+    return lat, noise, cond, ctx, sig
+
+
+def _oracle_step(o, lat, noise, cond, ctx, sig, ids, extra=()):
+    from oracle.pipeline import train_loss, train_precondition
+    noisy, timesteps, inp = train_precondition(lat, noise, sig)
+    x = torch.cat([inp, cond.unsqueeze(1).repeat(1, lat.shape[1], 1, 1, 1)], dim=2)
+    for p in o.parameters():
+        p.requires_grad_(False)
+    for n, p in o.named_parameters():
+        if "lora_" in n:
+            p.requires_grad_(True)
+            p.grad = None
+    pred = o(x, timesteps, ctx, *extra, added_time_ids=ids, return_dict=False)[0]
+    loss = train_loss(pred, noisy, lat, sig)
+    loss.backward()
+    return float(loss), {n: p.grad.clone() for n, p in o.named_parameters() if p.requires_grad}
+
+
+def _compare(trainer, ref_grads, ref_loss, loss, tol_each=5e-2, tol_all=3e-2):
+    assert abs(float(loss) - ref_loss) < 1e-2 * abs(ref_loss), (float(loss), ref_loss)
+    got = dict(trainer.named_grads())
+    assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+    worst, num, den = ("", 0.0), 0.0, 0.0
+    for n, gref in ref_grads.items():
+        e = rel_l2(got[n], gref)
+        num += float((got[n].double().cpu() - gref.double()).pow(2).sum())
+        den += float(gref.double().pow(2).sum())
+        if e > worst[1]:
+            worst = (n, e)
+    total = (num / den) ** 0.5
+    print(f"loss {float(loss):.6f} vs {ref_loss:.6f}; grads: all {total:.3e}, worst {worst[1]:.3e} ({worst[0]})")
+    assert worst[1] < tol_each, worst
+    assert total < tol_all, total
+
+
+@pytest.mark.parametrize("B,r", [(2, 8), (1, 4)])
+def test_lora_gradients_reduced(cuda, B, r):
+    import oracle as O
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel,
+                 dict(REDUCED_CONFIG), cuda, lora=dict(r=r))
+    lat, noise, cond, ctx, sig = _train_inputs(B, 8, 16, 16, 32)
+    ids = O.add_time_ids_training(5, 127, 0.02, B)
+    ref_loss, ref_grads = _oracle_step(o, lat, noise, cond, ctx, sig, ids)
+    tr = LoraTrainer(p)
+    loss = tr.forward_backward(lat.to(cuda), noise.to(cuda), sig.to(cuda), cond.to(cuda), ctx.to(cuda), ids.to(cuda))
+    _compare(tr, ref_grads, ref_loss, loss)
+
+
+def test_lora_gradients_three_levels_d64(cuda):
+    """64-wide heads (the SVD head size), a stride-2 chain of two downsamplers, 5 frames, non-square latents."""
+    import oracle as O
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(sample_size=32, in_channels=8, out_channels=4,
+               down_block_types=("CrossAttnDownBlockSpatioTemporal",) * 2 + ("DownBlockSpatioTemporal",),
+               up_block_types=("UpBlockSpatioTemporal",) + ("CrossAttnUpBlockSpatioTemporal",) * 2,
+               block_out_channels=(64, 128, 128), addition_time_embed_dim=32, projection_class_embeddings_input_dim=96,
+               layers_per_block=2, cross_attention_dim=64, transformer_layers_per_block=1,
+               num_attention_heads=(1, 2, 2), num_frames=5)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda,
+                 lora=dict(r=16))
+    lat, noise, cond, ctx, sig = _train_inputs(2, 5, 24, 40, 64)
+    ids = O.add_time_ids_training(5, 127, 0.02, 2)
+    ref_loss, ref_grads = _oracle_step(o, lat, noise, cond, ctx, sig, ids)
+    tr = LoraTrainer(p)
+    loss = tr.forward_backward(lat.to(cuda), noise.to(cuda), sig.to(cuda), cond.to(cuda), ctx.to(cuda), ids.to(cuda))
+    _compare(tr, ref_grads, ref_loss, loss)
+
+
+def test_train_steps_reduce_loss_and_alias_parameters(cuda):
+    """A few optimizer steps on one fixed batch: the loss must fall, and the module's LoRA parameters (state_dict)
+    must be the tensors the optimizer kernel updates."""
+    import oracle as O
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel,
+                 dict(REDUCED_CONFIG), cuda, lora=dict(r=8))
+    lat, noise, cond, ctx, sig = (t.to(cuda) for t in _train_inputs(2, 8, 16, 16, 32))
+    ids = O.add_time_ids_training(5, 127, 0.02, 2).to(cuda)
+    tr = LoraTrainer(p, lr=2e-3, weight_decay=0.0, max_grad_norm=1.0)
+    before = {n: v.detach().clone() for n, v in p.state_dict().items() if "lora_" in n}
+    losses = [float(tr.train_step(lat, noise, sig, cond, ctx, ids)) for _ in range(6)]
+    print("losses", losses)
+    assert losses[-1] < losses[0]
+    after = {n: v for n, v in p.state_dict().items() if "lora_" in n}
+    moved = sum(float((after[n] - before[n]).abs().sum()) > 0 for n in before)
+    assert moved == len(before)
+    assert all(torch.isfinite(v).all() for v in after.values())
+    # the forward the sampler runs sees the trained adapters: packed operands were refreshed from the parameters
+    pk = p.packed()
+    lay = tr.layers[0]
+    s = tr.slots[id(lay)]
+    assert torch.equal(lay.t_qkv.lora_a[:s["r"]], s["pA"][0].to(torch.bfloat16))
