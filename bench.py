@@ -33,6 +33,8 @@ CONFIGS = {
     "C3": ("svd_xt", 25, 72, 128, 64, True),
     "C2": ("svd_xt", 14, 72, 128, 0, False),
     "C1": ("reduced", 8, 32, 32, 0, False),
+    # LoRA fine-tuning step (BASELINE.json configs[4]): forward + backward + clip + AdamW, 14 frames 320x512, b=1 / GPU
+    "C5": ("svd_xt", 14, 40, 64, 64, False),
 }
 
 
@@ -220,6 +222,126 @@ def cpu_oracle_rate(workload, max_seconds=40.0, iters=4):
                         f"model build {build_s:.0f} s not timed")), t_step
 
 
+def train_flops(cfg, B, F, h, w, rank):
+    """Algorithmic work of one LoRA training step: forward + data gradients of every GEMM / conv above the first
+    adapter (~ the forward's dense FLOPs again) + attention backward (2.5x its forward) + LoRA weight gradients."""
+    from lkgd_b200.flops import unet_flops
+    f = unet_flops(cfg, B, F, h, w, lora_rank=rank, count_dead_cross_attn=False)
+    dense = f["conv3x3"] + f["tconv"] + f["shortcut"] + f["proj"] + f["geglu_ff"] + f["lora"]
+    attn = f["spatial_attn"] + f["temporal_attn"]
+    return f["total"] + dense + 2.5 * attn + f["lora"]
+
+
+def run_train(args):
+    """--workload C5: one LoRA fine-tuning step per "step" (reference train_models/train_svd_lora.py:1445-1689)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from lkgd_b200 import _lib, ops
+    from lkgd_b200.training import LoraTrainer
+    ops.device_check(local)
+    pipe, cfg, (F, h, w, lrank, lkgd) = build_ours(args.workload, device)
+    unet = pipe.unet
+    tr = LoraTrainer(unet, lr=1e-4, world_size=world)
+    B = 1
+    g = torch.Generator().manual_seed(100 + rank)
+    host = dict(lat=torch.randn(B, F, 4, h, w, generator=g).pin_memory(),
+                noise=torch.randn(B, F, 4, h, w, generator=g).pin_memory(),
+                cond=torch.randn(B, 4, h, w, generator=g).pin_memory(),
+                ctx=torch.randn(B, 1, 1024, generator=g).pin_memory(),
+                sig=torch.tensor([1.3] * B).pin_memory())
+    ids = torch.tensor([[5.0, 0.02, 127.0]] * B, device=device)      # training order (utils/util.py:295, quirk F12)
+    dev = {k: v.to(device) for k, v in host.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(d):
+        return tr.train_step(d["lat"], d["noise"], d["sig"], d["cond"], d["ctx"], ids)
+
+    for _ in range(args.warmup):
+        step(dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: the batch comes from pinned host memory and the loss is read back every step
+    h2d = sum(v.numel() * 4 for v in host.values())
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        loss_host = float(step(d))
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        _lib.PROF.records, _lib.PROF.enabled = [], True
+        step(dev)
+        torch.cuda.synchronize()
+        _lib.PROF.enabled = False
+        by = {}
+        for name, a, b, meta in _lib.PROF.records:
+            d = by.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+            if meta and "flops" in meta:
+                d["flops"] += meta["flops"]
+        total_ms = sum(d["ms"] for d in by.values())
+        pk = peaks()
+        gm = by.get("lkgd_gemm", dict(ms=1e-9, calls=0, flops=0.0))
+        achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
+        flops = train_flops(cfg, B, F, h, w, lrank)
+        line = {
+            "metric": "train_steps_per_s", "value": args.steps * world / (ms * 1e-3), "unit": "train_steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"C5: SVD LoRA fine-tuning step (forward + backward + clip + AdamW), {F} frames 320x512 "
+                                   f"({h}x{w} latents), batch 1 per GPU, LoRA r={lrank} on temporal attn1 q/k/v, "
+                                   f"{'one flat NCCL all-reduce of the LoRA gradients per step' if world > 1 else 'single GPU'}",
+                       "algorithmic_tflop_per_step": flops / 1e12,
+                       "model_tflops_per_gpu": flops / 1e12 / (ms / args.steps * 1e-3),
+                       "trainable_parameters": int(tr.flat_p.numel()), "loss": loss_host,
+                       "l2": "3 GB of bf16 weights (+ their transposed copies) stream through every step; >> 126 MB L2"},
+            "e2e": {"value": args.steps * world / (ms_e2e * 1e-3), "unit": "train_steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (forward + data-gradient GEMMs / convs)",
+                         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tf_sustained"], "traffic": None,
+                         "peak_source": pk["source"] + ", sustained", "launches_per_step": gm["calls"],
+                         "kernel_ms_per_step": gm["ms"], "share_of_step": gm["ms"] / total_ms,
+                         "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -257,6 +379,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C5":
+        return run_train(args)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -299,6 +299,28 @@ LKGD_API int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t n,
 LKGD_API int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, void* dst, int64_t ldd, int32_t rows,
                               int32_t cols, float alpha, void* stream);
 
+
+/* ---- backward of the fp32 conditioning helpers (latent-knowledge block under autograd,
+ * models/unet_spatio_temporal_condition.py:536-595; trainable 'quaternion' parameters, train_svd_lora.py:1068-1073).
+ * lkgd_small_linear backward with dy' = dy * act_out'(y) (act_out 0 or 3 = LeakyReLU(0.1), y = the forward output):
+ *   dx[m,k] (=|+=) sum_n dy'[m,n] W[n,k]     (dx NULL: skipped)
+ *   dW[n,k] += sum_m dy'[m,n] x[m,k];  db[n] += sum_m dy'[m,n]     (each may be NULL) */
+LKGD_API int lkgd_small_linear_bwd(const float* dy, int32_t lddy, const float* y, int32_t ldy, int32_t act_out,
+                                   const float* x, int32_t ldx, const float* W, float* dx, int32_t lddx,
+                                   int32_t dx_accumulate, float* dW, float* db, int32_t M, int32_t N, int32_t K,
+                                   void* stream);
+/* backward of lkgd_polar: mode 0 (a,b) = (re,im), (d0,d1) = (d mag, d pha) -> (o0,o1) = (d re, d im);
+ * mode 1 (a,b) = (mag,pha), (d0,d1) = (d re, d im) -> (o0,o1) = (d mag, d pha). */
+LKGD_API int lkgd_polar_bwd(const float* a, const float* b, const float* d0, const float* d1, float* o0, float* o1,
+                            int32_t n, int32_t mode, void* stream);
+/* Conv1d(4G -> G, kernel 1, groups G) weight gradient: dw[j, m] += sum_b dy[b, j] * x[b, 4j + m]. */
+LKGD_API int lkgd_grouped1x1_bwd_w(const float* dy, int32_t lddy, const float* x, int32_t ldx, float* dw, int32_t B,
+                                   int32_t G, void* stream);
+/* Folds the dense gradient dWt [out, in] of a quaternion linear layer back onto its r / i / j / k components
+ * ([in/4, out/4] each, +=). */
+LKGD_API int lkgd_hamilton_bwd(const float* dWt, int32_t in, int32_t out, float* dr, float* di, float* dj, float* dk,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,10 @@ SIGNATURES = {
     "lkgd_sumsq": (i32, [vp, i64, vp, vp]),
     "lkgd_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
     "lkgd_cast2d_bf16": (i32, [vp, i64, i64, vp, i64, i32, i32, f32, vp]),
+    "lkgd_small_linear_bwd": (i32, [vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
+    "lkgd_polar_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "lkgd_grouped1x1_bwd_w": (i32, [vp, i32, vp, i32, vp, i32, i32, vp]),
+    "lkgd_hamilton_bwd": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -524,6 +524,96 @@ __global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds,
   dst[r * ldd + c] = __float2bfloat16(src[r * lds + c * cs] * alpha);
 }
 
+
+// ------------------------------------------------------------------------------------------- small fp32 backward
+// (latent-knowledge conditioning block, reference models/unet_spatio_temporal_condition.py:536-595 under autograd)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {       // derivative expressed with the OUTPUT y
+  if (act == 3) return y > 0.f ? 1.0f : 0.1f;                               // LeakyReLU(0.1)
+  return 1.0f;
+}
+// dx[m, k] = sum_n dy[m, n] * act'(y[m, n]) * W[n, k]
+__global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                          int act_out, const float* __restrict__ W, float* __restrict__ dx, int lddx,
+                                          int M, int N, int K, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float g = dy[(size_t)m * lddy + n];
+    if (act_out) g *= act_grad_from_out(y[(size_t)m * ldy + n], act_out);
+    acc = fmaf(g, W[(size_t)n * K + k], acc);
+  }
+  float* o = dx + (size_t)m * lddx + k;
+  *o = accumulate ? *o + acc : acc;
+}
+// dW[n, k] += sum_m dy'[m, n] * act_in(x[m, k]);  db[n] += sum_m dy'[m, n]
+__global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                          int act_out, const float* __restrict__ x, int ldx, float* __restrict__ dW,
+                                          float* __restrict__ db, int M, int N, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k >= K) return;
+  float acc = 0.f, bacc = 0.f;
+  for (int m = 0; m < M; ++m) {
+    float g = dy[(size_t)m * lddy + n];
+    if (act_out) g *= act_grad_from_out(y[(size_t)m * ldy + n], act_out);
+    acc = fmaf(g, x[(size_t)m * ldx + k], acc);
+    bacc += g;
+  }
+  if (dW) dW[(size_t)n * K + k] += acc;
+  if (db && k == 0) db[n] += bacc;
+}
+// mode 0: forward (re, im) -> (mag, pha); given d mag, d pha -> d re, d im.
+// mode 1: forward (mag, pha) -> (re, im) = mag (cos, sin) pha; given d re, d im -> d mag, d pha.
+__global__ void polar_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ d0,
+                                 const float* __restrict__ d1, float* __restrict__ o0, float* __restrict__ o1, int n,
+                                 int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 0) {
+    const float re = a[i], im = b[i];
+    const float m2 = re * re + im * im;
+    if (m2 > 0.f) {
+      const float inv = rsqrtf(m2);
+      o0[i] = d0[i] * re * inv - d1[i] * im / m2;
+      o1[i] = d0[i] * im * inv + d1[i] * re / m2;
+    } else {
+      o0[i] = 0.f; o1[i] = 0.f;
+    }
+  } else {
+    const float mag = a[i], pha = b[i];
+    float sn, cs;
+    sincosf(pha, &sn, &cs);
+    o0[i] = d0[i] * cs + d1[i] * sn;
+    o1[i] = mag * (d1[i] * cs - d0[i] * sn);
+  }
+}
+// Conv1d(4G -> G, k=1, groups=G) weight gradient: dw[j, m] += sum_b dy[b, j] * x[b, 4 j + m]
+__global__ void grouped1x1_bwd_w_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                        float* __restrict__ dw, int B, int G) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * 4) return;
+  const int j = idx >> 2;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc = fmaf(dy[(size_t)b * lddy + j], x[(size_t)b * ldx + idx], acc);
+  dw[idx] += acc;
+}
+// Hamilton-product weight: dWt is the dense gradient [out, in] of y = x @ W (W [in, out] assembled from r,i,j,k blocks
+// [in/4, out/4]); folds it back onto the four quaternion components (+=).
+__global__ void hamilton_bwd_kernel(const float* __restrict__ dWt, int in, int out, float* __restrict__ dr,
+                                    float* __restrict__ di, float* __restrict__ dj, float* __restrict__ dk) {
+  const int i4 = in / 4, o4 = out / 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= i4 * o4) return;
+  const int p = idx / o4, q = idx % o4;
+  auto D = [&](int a, int b) { return dWt[(size_t)(b * o4 + q) * in + a * i4 + p]; };
+  dr[idx] += D(0, 0) + D(1, 1) + D(2, 2) + D(3, 3);
+  di[idx] += D(0, 1) - D(1, 0) + D(2, 3) - D(3, 2);
+  dj[idx] += D(0, 2) - D(2, 0) + D(3, 1) - D(1, 3);
+  dk[idx] += D(0, 3) - D(3, 0) + D(1, 2) - D(2, 1);
+}
+
 static GnbGeom gnb_geom(int C1, int C2, int R, int x_f32, int groups, int silu, float eps) {
   GnbGeom g;
   g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
@@ -712,5 +802,52 @@ extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, v
   const long long n = (long long)rows * cols;
   cast2d_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, lds, src_cs, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_small_linear_bwd(const float* dy, int32_t lddy, const float* y, int32_t ldy, int32_t act_out,
+                                     const float* x, int32_t ldx, const float* W, float* dx, int32_t lddx,
+                                     int32_t dx_accumulate, float* dW, float* db, int32_t M, int32_t N, int32_t K,
+                                     void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || dy == nullptr) return LKGD_ESHAPE;
+  if (act_out != 0 && act_out != 3) return LKGD_ESHAPE;
+  if (act_out && y == nullptr) return LKGD_ESHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = LKGD_OK;
+  if (dx != nullptr) {
+    if (W == nullptr) return LKGD_ESHAPE;
+    dim3 grid((K + 127) / 128, M);
+    small_linear_bwd_x_kernel<<<grid, 128, 0, st>>>(dy, lddy, y, ldy, act_out, W, dx, lddx, M, N, K, dx_accumulate);
+    if ((rc = launch_epilogue())) return rc;
+  }
+  if (dW != nullptr || db != nullptr) {
+    if (x == nullptr) return LKGD_ESHAPE;
+    dim3 grid((K + 127) / 128, N);
+    small_linear_bwd_w_kernel<<<grid, 128, 0, st>>>(dy, lddy, y, ldy, act_out, x, ldx, dW, db, M, N, K);
+    rc = launch_epilogue();
+  }
+  return rc;
+}
+
+extern "C" int lkgd_polar_bwd(const float* a, const float* b, const float* d0, const float* d1, float* o0, float* o1,
+                              int32_t n, int32_t mode, void* stream) {
+  if (n <= 0 || (mode != 0 && mode != 1)) return LKGD_ESHAPE;
+  polar_bwd_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, d0, d1, o0, o1, n, mode);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_grouped1x1_bwd_w(const float* dy, int32_t lddy, const float* x, int32_t ldx, float* dw, int32_t B,
+                                     int32_t G, void* stream) {
+  if (B <= 0 || G <= 0) return LKGD_ESHAPE;
+  grouped1x1_bwd_w_kernel<<<(G * 4 + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, dw,
+                                                                                                  B, G);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_hamilton_bwd(const float* dWt, int32_t in, int32_t out, float* dr, float* di, float* dj, float* dk,
+                                 void* stream) {
+  if (in <= 0 || out <= 0 || in % 4 || out % 4) return LKGD_ESHAPE;
+  const int n = (in / 4) * (out / 4);
+  hamilton_bwd_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dWt, in, out, dr, di, dj, dk);
   return launch_epilogue();
 }

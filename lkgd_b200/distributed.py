@@ -5,6 +5,9 @@ The denoise step shards only where it splits naturally:
   * the classifier-free-guidance pair -> ``CFGPair``: rank 2k runs the unconditional half, rank 2k+1 the conditional
     half (batch 1 each), and ONE exchange per step (an all-gather of the [S*F*H*W, 4] fp32 prediction, 3.7 MB at
     25 frames 72x128) feeds the fused CFG + Euler kernel, which both ranks run so the latents stay replicated.
+  * LoRA training -> ``allreduce_flat_``: replicas; the ONE flat fp32 gradient buffer of all trainable tensors is summed
+    with a single all-reduce per optimizer step (the averaging 1/world is folded into the optimizer kernel) - what DDP's
+    bucketed all-reduce does for the reference (train_models/train_svd_lora.py:1300-1302,1683).
 Frames are never a shard axis: temporal conv / attention and the 5-D GroupNorm couple all of them.
 The reference has none of this (single process, ``pipeline...controlnet.py:577-619``); backend-agnostic on purpose so
 the host logic is covered by world-size-2 ``gloo`` tests on CPU."""
@@ -66,3 +69,16 @@ def gather_samples(latents: torch.Tensor, dst: int = 0) -> Optional[List[torch.T
     out = [torch.empty_like(latents) for _ in range(world)] if dist.get_rank() == dst else None
     dist.gather(latents.contiguous(), out, dst=dst)
     return out
+
+
+def allreduce_flat_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM of a flat gradient buffer across ``group`` (default group when None).  One collective per optimizer
+    step; no-op without an initialised process group or with a single rank."""
+    if not dist.is_available() or not dist.is_initialized():
+        return flat
+    if dist.get_world_size(group) == 1:
+        return flat
+    if flat.dim() != 1 or not flat.is_contiguous():
+        raise ValueError("allreduce_flat_ expects one contiguous 1-D buffer (all trainable gradients back to back)")
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat

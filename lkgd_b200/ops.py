@@ -641,3 +641,65 @@ def cast2d_bf16(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> tor
     L.check(L.load().lkgd_cast2d_bf16(src.data_ptr(), src.stride(0), src.stride(1), dst.data_ptr(), dst.stride(0),
                                       src.shape[0], src.shape[1], alpha, _stream()), "lkgd_cast2d_bf16")
     return dst
+
+
+def small_linear_bwd(dy: torch.Tensor, W: Optional[torch.Tensor] = None, *, x: Optional[torch.Tensor] = None,
+                     y: Optional[torch.Tensor] = None, act_out: int = 0, want_dx: bool = True,
+                     dx: Optional[torch.Tensor] = None, dW: Optional[torch.Tensor] = None,
+                     db: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Backward of ``small_linear`` (fp32): returns dx [M, K] (or accumulates into the given ``dx``); ``dW`` [N, K] and
+    ``db`` [N] are accumulated in place when given (they need ``x``).  ``act_out`` / ``y``: the forward's output
+    activation and output (LeakyReLU only)."""
+    _need_cuda(dy, W, x, y, dx, dW, db)
+    M, N = dy.shape
+    ref = W if W is not None else dW
+    K = ref.shape[1]
+    for t in (dy, x, y, dx):
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError("small_linear_bwd: fp32 2-D tensors with unit column stride expected")
+    for t in (W, dW):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.shape != (N, K)):
+            raise ValueError("small_linear_bwd: W / dW must be contiguous fp32 [N, K]")
+    if db is not None and (db.dtype != torch.float32 or not db.is_contiguous() or db.numel() != N):
+        raise ValueError("small_linear_bwd: db must be contiguous fp32 [N]")
+    acc = dx is not None
+    if want_dx and dx is None:
+        dx = torch.empty((M, K), device=dy.device, dtype=torch.float32)
+    if not want_dx:
+        dx = None
+    L.check(L.load().lkgd_small_linear_bwd(dy.data_ptr(), dy.stride(0), _ptr(y), y.stride(0) if y is not None else 0,
+                                           act_out, _ptr(x), x.stride(0) if x is not None else 0, _ptr(W), _ptr(dx),
+                                           dx.stride(0) if dx is not None else 0, int(acc), _ptr(dW), _ptr(db), M, N, K,
+                                           _stream()), "lkgd_small_linear_bwd")
+    return dx
+
+
+def polar_bwd(a: torch.Tensor, b: torch.Tensor, d0: torch.Tensor, d1: torch.Tensor, mode: int):
+    _need_cuda(a, b, d0, d1)
+    a, b, d0, d1 = (t.contiguous() for t in (a, b, d0, d1))
+    o0, o1 = torch.empty_like(a), torch.empty_like(a)
+    L.check(L.load().lkgd_polar_bwd(a.data_ptr(), b.data_ptr(), d0.data_ptr(), d1.data_ptr(), o0.data_ptr(),
+                                    o1.data_ptr(), a.numel(), mode, _stream()), "lkgd_polar_bwd")
+    return o0, o1
+
+
+def grouped1x1_bwd_w(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor):
+    """dw [G, 4] (contiguous fp32, +=) from dy [B, G] and x [B, 4G] (row pitches free)."""
+    _need_cuda(dy, x, dw)
+    B, G = dy.shape
+    if x.shape != (B, 4 * G) or dw.numel() != 4 * G or not dw.is_contiguous() or dy.stride(1) != 1 or x.stride(1) != 1:
+        raise ValueError("grouped1x1_bwd_w: dy [B, G], x [B, 4G], dw [G, 4]")
+    L.check(L.load().lkgd_grouped1x1_bwd_w(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(), B, G,
+                                           _stream()), "lkgd_grouped1x1_bwd_w")
+
+
+def hamilton_bwd(dWt: torch.Tensor, dr: torch.Tensor, di: torch.Tensor, dj: torch.Tensor, dk: torch.Tensor):
+    _need_cuda(dWt, dr, di, dj, dk)
+    out_f, in_f = dWt.shape
+    for t in (dr, di, dj, dk):
+        if not t.is_contiguous() or t.numel() != (in_f // 4) * (out_f // 4) or t.dtype != torch.float32:
+            raise ValueError("hamilton_bwd: component gradients must be contiguous fp32 [in/4, out/4]")
+    if not dWt.is_contiguous():
+        raise ValueError("hamilton_bwd: dWt must be contiguous [out, in]")
+    L.check(L.load().lkgd_hamilton_bwd(dWt.data_ptr(), in_f, out_f, dr.data_ptr(), di.data_ptr(), dj.data_ptr(),
+                                       dk.data_ptr(), _stream()), "lkgd_hamilton_bwd")

@@ -326,7 +326,7 @@ class LoraTrainer:
     parameters become views of it), flat gradient / Adam moment buffers, the bf16 GEMM operands derived from the
     parameters, and the step: forward -> loss -> backward -> [all-reduce] -> clip -> AdamW -> repack.
 
-    ``group``: a ``torch.distributed`` process group (or None): the flat gradient is summed across ranks with one
+    ``world_size`` > 1 (+ optional ``group``, default group when None): the flat gradient is summed across ranks with one
     ``all_reduce`` per step and averaged inside the optimizer kernel - the data-parallel gradient sync the reference
     gets from DDP (train_svd_lora.py:1300-1302)."""
 
@@ -434,9 +434,9 @@ class LoraTrainer:
 
     def optimizer_step(self):
         """[all-reduce(sum)] -> grad-norm -> clip + AdamW (gradient averaged over ranks in-kernel) -> repack."""
-        if self.group is not None and self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        if self.world > 1:
+            from .distributed import allreduce_flat_
+            allreduce_flat_(self.flat_g, self.group)
         self.step_count += 1
         scale = 1.0 / self.world
         ops.sumsq(self.flat_g, self.sumsq)

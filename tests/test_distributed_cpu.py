@@ -145,3 +145,65 @@ def test_cfg_pair_split_equals_unsplit_step(order):
     ref = O.denoise_loop(unet, sched, lat, img, emb, O.add_time_ids_inference(6, 127, 0.02, 1), 25, 1.0, 3.0,
                          max_steps=1)
     assert rel(out[0], ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- training all-reduce
+def _dp_oracle(order="b_major"):
+    import oracle as O
+    unet = fill_seeded_(O.UNetSpatioTemporalConditionControlNetModel(**dict(REDUCED4, time_context_order=order)))
+    O.add_lora(unet, r=4)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            if "lora_" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    for n, p in unet.named_parameters():
+        p.requires_grad_("lora_" in n)
+    return unet.eval()
+
+
+def _dp_batch():
+    F_, H_, W_ = 4, 8, 8
+    return dict(lat=seeded_tensor("dp/lat", (2, F_, 4, H_, W_)), noise=seeded_tensor("dp/noise", (2, F_, 4, H_, W_)),
+                cond=seeded_tensor("dp/cond", (2, 4, H_, W_)), ctx=seeded_tensor("dp/ctx", (2, 1, 32)),
+                sig=torch.tensor([0.7, 2.5]))
+
+
+def _dp_flat_grad(unet, b, rows):
+    """Loss + flat LoRA gradient (all trainable tensors back to back, registration order) of the samples ``rows``."""
+    import oracle as O
+    from oracle.pipeline import train_loss, train_precondition
+    lat, noise, cond, ctx, sig = (b[k][rows] for k in ("lat", "noise", "cond", "ctx", "sig"))
+    noisy, ts, inp = train_precondition(lat, noise, sig)
+    x = torch.cat([inp, cond.unsqueeze(1).repeat(1, lat.shape[1], 1, 1, 1)], dim=2)
+    ids = O.add_time_ids_training(5, 127, 0.02, lat.shape[0])
+    unet.zero_grad()
+    loss = train_loss(unet(x, ts, ctx, added_time_ids=ids, return_dict=False)[0], noisy, lat, sig)
+    loss.backward()
+    return torch.cat([p.grad.reshape(-1) for p in unet.parameters() if p.requires_grad])
+
+
+def _dp_worker(rank, world):
+    """Each rank: gradient of ITS sample into one flat buffer, then the one collective of the training step."""
+    from lkgd_b200.distributed import allreduce_flat_
+    flat = _dp_flat_grad(_dp_oracle(), _dp_batch(), slice(rank, rank + 1)).contiguous()
+    local = flat.clone()
+    allreduce_flat_(flat)
+    return local, flat
+
+
+def test_flat_gradient_allreduce_equals_big_batch_gradient():
+    """Two replicas with one sample each + one flat all-reduce (sum) + the 1/world the optimizer kernel applies ==
+    the gradient of the two-sample batch on one process: the data-parallel contract of the reference's DDP wrap
+    (train_models/train_svd_lora.py:1300-1302)."""
+    out = _run(_dp_worker, 2)
+    assert torch.equal(out[0][1], out[1][1])                                  # both ranks hold the same reduced buffer
+    assert torch.allclose(out[0][1], out[0][0] + out[1][0], rtol=0, atol=0)    # it is the plain sum
+    whole = _dp_flat_grad(_dp_oracle(), _dp_batch(), slice(0, 2))
+    assert rel(out[0][1] / 2, whole) < 1e-5
+
+
+def test_allreduce_flat_is_a_noop_without_a_group_and_rejects_views():
+    from lkgd_b200.distributed import allreduce_flat_
+    x = torch.arange(6.0)
+    assert allreduce_flat_(x) is x and torch.equal(x, torch.arange(6.0))

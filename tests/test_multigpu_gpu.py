@@ -24,3 +24,20 @@ def test_cfg_pair_split_two_gpus(cuda):
     for name, r in res.items():
         assert r["replicated"], name                       # both ranks hold identical latents after every step
         assert r["split_vs_unsplit"] < 2e-3, (name, r)     # same kernels, batch 1 vs 2: only accumulation-order noise
+
+
+def test_data_parallel_lora_training_two_gpus(cuda):
+    """One flat NCCL all-reduce of the LoRA gradients per step: reduced gradient == sum of the per-rank gradients,
+    parameters stay replicated after the optimizer step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "mgpu_train.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    for r in json.loads(line[len("RESULT "):]):
+        print(r)
+        assert r["params_replicated"]
+        assert r["local_matches_solo"] < 1e-3        # atomics in the weight-gradient GEMM: summation-order noise only
+        assert r["reduced_is_sum"] < 1e-3
