@@ -350,7 +350,10 @@ class LoraTrainer:
             mods.append(trio)
         r = mods[0][0].r
         dev = unet.device
-        n = sum(3 * 2 * r * p.c for p in self.layers)
+        # the latent-knowledge block's 'quaternion' parameters are trained with the adapters (train_svd_lora.py:1068-1073)
+        self.lk_params = [(n_, p_) for n_, p_ in unet.named_parameters() if "quaternion" in n_] \
+            if hasattr(unet, "_context_train") else []
+        n = sum(3 * 2 * r * p.c for p in self.layers) + sum(p_.numel() for _, p_ in self.lk_params)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -373,6 +376,15 @@ class LoraTrainer:
                     pb[i].copy_(b)
                     a.data, b.data = pa[i], pb[i]          # the module's parameters now alias the flat buffer
                 self.slots[id(p)] = dict(A=ga, B=gb, pA=pa, pB=pb, scaling=float(trio[0].scaling), r=r)
+            self.lk_grads: Dict[str, torch.Tensor] = {}
+            for name, prm in self.lk_params:
+                k = prm.numel()
+                view = self.flat_p[off:off + k].view(prm.shape)
+                view.copy_(prm)
+                prm.data = view
+                self.lk_grads[name] = self.flat_g[off:off + k].view(prm.shape)
+                off += k
+        assert off == n
         self.repack()
 
     # ---- fp32 master parameters -> the bf16 operands the GEMMs read (forward: A_cat, B_blk; backward: transposes)
@@ -388,6 +400,8 @@ class LoraTrainer:
                 ops.cast2d_bf16(s["pB"][i], p.t_qkv.lora_b[i * C:(i + 1) * C, i * r_pad:i * r_pad + r], alpha=s["scaling"])
                 ops.cast2d_bf16(s["pB"][i].t(), tw.lora_bT[i * r_pad:i * r_pad + r, i * C:(i + 1) * C],
                                 alpha=s["scaling"])
+        if self.lk_params:
+            self.unet._lk = None          # dense matrices of the latent-knowledge block are rebuilt from the parameters
 
     def named_grads(self):
         """(qualified parameter name, fp32 gradient view) in the reference's naming
@@ -401,7 +415,7 @@ class LoraTrainer:
                 base = names[id(m)]
                 out.append((f"{base}.lora_A.{m.adapter_name}.weight", s["A"][i]))
                 out.append((f"{base}.lora_B.{m.adapter_name}.weight", s["B"][i]))
-        return out
+        return out + list(self.lk_grads.items())
 
     # ---- one training step
     def forward_backward(self, latents: torch.Tensor, noise: torch.Tensor, sigmas: torch.Tensor,
@@ -422,14 +436,28 @@ class LoraTrainer:
             self.flat_g.zero_()
         noisy, x_in = ops.edm_precondition(latents, noise, sigmas, cond_latents.to(dev, f32).contiguous(), pk.cin_pad)
         timesteps = 0.25 * torch.log(sigmas)                      # train_svd_lora.py:1508-1509 (host-side scalar math)
-        ctx = unet._context(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
+        lk_saved = cross = None
+        if self.lk_params:
+            ctx, lk_saved = unet._context_train(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
+            d_xs = torch.zeros((B, pk.xs_w.shape[0]), device=dev, dtype=f32)    # gradients of every KV=1 cross-attention
+            d_xt = torch.zeros((B, pk.xt_w.shape[0]), device=dev, dtype=f32)    # vector, all layers side by side
+
+            def cross(p):
+                return (d_xs[:, p.s_cross.off:p.s_cross.off + p.c], d_xt[:, p.t_cross.off:p.t_cross.off + p.c])
+        else:
+            ctx = unet._context(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
         emb = pk.time_embedding(timesteps, added_time_ids.to(dev))
         cond = Conditioning(pk, emb, ctx)
         g = Geom(B, F, h, w)
         graph = TrainGraph(pk)
         pred = graph.forward(x_in, g, cond)
         loss, dpred = ops.edm_loss(pred, noisy, latents, sigmas, pk.conv_out_w.shape[0])
-        graph.backward(dpred, lora_grads=self.slots)
+        graph.backward(dpred, lora_grads=self.slots, cross_grads=cross)
+        if lk_saved is not None:
+            # cross vectors = ctx @ W^T + b for the concatenated [sum C, 1024] matrices: fold back onto the context
+            dctx = ops.small_linear_bwd(d_xs, pk.xs_w)
+            ops.small_linear_bwd(d_xt, pk.xt_w, dx=dctx)
+            unet._context_backward(lk_saved, dctx, self.lk_grads)
         return loss
 
     def optimizer_step(self):

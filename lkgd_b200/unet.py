@@ -429,6 +429,9 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         ii[:, 256] = 0              # irfft ignores the imaginary part of the DC and Nyquist bins
         sf = self.quaternion_lora_fuse_sf
         self._lk = dict(
+            interp=interp.float().contiguous(),
+            dconv_g=grouped(self.quaternion_lora_dconv).float().contiguous(),
+            fconv_g=grouped(self.quaternion_lora_fconv).float().contiguous(),
             lconv=grouped(self.quaternion_lora_lconv).float().contiguous(),
             dconv=(grouped(self.quaternion_lora_dconv) @ interp).float().contiguous(),
             fconv=(grouped(self.quaternion_lora_fconv) @ interp).float().contiguous(),
@@ -486,6 +489,97 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         ops.small_linear(torch.cat([re, im], 1), lk["idft"], out=spatial[:, 512:])          # irFFT -> 512 samples
         h = ops.small_linear(spatial, *lk["sf0"], act_out=SL_LEAKY)
         return ops.small_linear(h, *lk["sf2"]).reshape(B, 1, 1024)
+
+    # -------------------------------------------------------------------- training: forward with save / backward
+    def _context_train(self, encoder_hidden_states, domain_features, flow_features):
+        """``_context`` with the intermediates the backward needs.  Differs only in evaluating the linear
+        interpolation and the grouped conv as two mat-vecs (their weights are trained separately)."""
+        from types import SimpleNamespace as NS
+        lk = self._lk_pack()
+        dev = encoder_hidden_states.device
+        B = encoder_hidden_states.shape[0]
+        f32 = torch.float32
+        S = NS(B=B)
+        S.ctx = encoder_hidden_states.to(f32).reshape(B, 1024).contiguous()
+        dom = domain_features.to(f32).reshape(-1, 1000).contiguous()
+        flo = flow_features.to(f32).reshape(-1, 1000).contiguous()
+        if dom.shape[0] not in (B, 1) or (dom.shape[0] == 1 and B > 2):
+            raise ValueError(f"domain_features batch {dom.shape[0]} is incompatible with encoder_hidden_states batch {B}")
+        S.dom_i = ops.small_linear(dom, lk["interp"]).expand(B, 1024).contiguous()
+        S.flo_i = ops.small_linear(flo, lk["interp"]).expand(B, 1024).contiguous()
+        S.cat = cat = torch.empty(B, 1024, device=dev, dtype=f32)
+        ops.small_linear(S.ctx, lk["lconv"], out=cat[:, 0:256])
+        ops.small_linear(S.dom_i, lk["dconv_g"], out=cat[:, 256:512])
+        ops.small_linear(S.flo_i, lk["fconv_g"], out=cat[:, 512:768])
+        cat[:, 768:] = lk["texts"]
+        S.spatial = spatial = torch.empty(B, 1024, device=dev, dtype=f32)
+        ops.small_linear(cat, *lk["fuse"], out=spatial[:, :512])
+        mags = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        phas = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        S.re, S.im = [], []
+        for i in range(3):
+            v = cat[:, 256 * i:256 * (i + 1)]
+            re, im = ops.small_linear(v, lk["dft_re"]), ops.small_linear(v, lk["dft_im"])
+            S.re.append(re)
+            S.im.append(im)
+            mags[:, i], phas[:, i] = ops.polar(re, im, 0)
+        mags[:, 3], phas[:, 3] = lk["tmag"], lk["tpha"]
+        S.magin, S.phain = mags[:, :, :128].reshape(B, 512), phas[:, :, :128].reshape(B, 512)
+        S.mag128, S.pha128 = mags[:, :, 128].contiguous(), phas[:, :, 128].contiguous()
+        mag, pha = ops.small_linear(S.magin, *lk["mag"]), ops.small_linear(S.phain, *lk["pha"])
+        mag0, pha0 = ops.small_linear(S.mag128, *lk["mag0"]), ops.small_linear(S.pha128, *lk["pha0"])
+        S.magc, S.phac = torch.cat([mag, mag0], 1), torch.cat([pha, pha0], 1)
+        re, im = ops.polar(S.magc, S.phac, 1)
+        S.reim = torch.cat([re, im], 1)
+        ops.small_linear(S.reim, lk["idft"], out=spatial[:, 512:])
+        S.h = ops.small_linear(spatial, *lk["sf0"], act_out=SL_LEAKY)
+        return ops.small_linear(S.h, *lk["sf2"]).reshape(B, 1, 1024), S
+
+    def _context_backward(self, S, dctx: torch.Tensor, grads: dict):
+        """dctx: fp32 [B, 1024] gradient of the block output.  ``grads``: parameter name -> fp32 accumulator of that
+        parameter's shape (the 29 ``quaternion_lora_*`` tensors the reference trains, train_svd_lora.py:1068-1073)."""
+        lk = self._lk_pack()
+        B, dev, f32 = S.B, dctx.device, torch.float32
+        q = "quaternion_lora_"
+
+        def gw(name):
+            return grads[q + name]
+
+        def colsum(t, name):
+            ops.colsum_grouped(t.contiguous(), 1, (ops.RV_NONE, 1, 1, 1), out=gw(name).reshape(1, -1))
+
+        def qlinear(dy, x, name, key):
+            wt = lk[key][0]
+            dwt = torch.zeros_like(wt)
+            dx = ops.small_linear_bwd(dy, wt, x=x, dW=dwt, db=gw(name + ".bias"))
+            ops.hamilton_bwd(dwt, *(gw(f"{name}.{c}_weight") for c in "rijk"))
+            return dx
+
+        dh = ops.small_linear_bwd(dctx, lk["sf2"][0], x=S.h, dW=gw("fuse_sf.2.weight"), db=gw("fuse_sf.2.bias"))
+        dsp = ops.small_linear_bwd(dh, lk["sf0"][0], x=S.spatial, y=S.h, act_out=SL_LEAKY, dW=gw("fuse_sf.0.weight"),
+                                   db=gw("fuse_sf.0.bias"))
+        dreim = ops.small_linear_bwd(dsp[:, 512:], lk["idft"])
+        dmagc, dphac = ops.polar_bwd(S.magc, S.phac, dreim[:, :257], dreim[:, 257:], 1)
+        dmags = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        dphas = torch.empty(B, 4, 129, device=dev, dtype=f32)
+        dmags[:, :, :128] = qlinear(dmagc[:, :256], S.magin, "fuse_fft_mag", "mag").view(B, 4, 128)
+        dphas[:, :, :128] = qlinear(dphac[:, :256], S.phain, "fuse_fft_pha", "pha").view(B, 4, 128)
+        dmags[:, :, 128] = ops.small_linear_bwd(dmagc[:, 256:257], lk["mag0"][0], x=S.mag128,
+                                                dW=gw("fuse_fft_mag0.weight"), db=gw("fuse_fft_mag0.bias"))
+        dphas[:, :, 128] = ops.small_linear_bwd(dphac[:, 256:257], lk["pha0"][0], x=S.pha128,
+                                                dW=gw("fuse_fft_pha0.weight"), db=gw("fuse_fft_pha0.bias"))
+        colsum(dmags[:, 3], "texts_fft_mag")
+        colsum(dphas[:, 3], "texts_fft_pha")
+        dcat = qlinear(dsp[:, :512], S.cat, "fuse", "fuse")
+        for i in range(3):
+            dre, dim = ops.polar_bwd(S.re[i], S.im[i], dmags[:, i], dphas[:, i], 0)
+            sl = dcat[:, 256 * i:256 * (i + 1)]
+            ops.small_linear_bwd(dre, lk["dft_re"], dx=sl)
+            ops.small_linear_bwd(dim, lk["dft_im"], dx=sl)
+        colsum(dcat[:, 768:], "texts")
+        ops.grouped1x1_bwd_w(dcat[:, 0:256], S.ctx, gw("lconv.weight"))
+        ops.grouped1x1_bwd_w(dcat[:, 256:512], S.dom_i, gw("dconv.weight"))
+        ops.grouped1x1_bwd_w(dcat[:, 512:768], S.flo_i, gw("fconv.weight"))
 
     @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states,
