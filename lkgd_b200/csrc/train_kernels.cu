@@ -324,36 +324,49 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __
 }
 
 // ------------------------------------------------------------------------------------------- grouped column sums
-__device__ __forceinline__ int rv_index(int mode, long long m, int HW, int F, int B) {
+__device__ __forceinline__ int rv_index(int mode, long long m64, int HW, int F, int B) {
+  const unsigned m = (unsigned)m64, hw = (unsigned)HW, hwf = (unsigned)HW * (unsigned)F;   // rows < 2^31 (GEMM M is int32)
   switch (mode) {
-    case LKGD_RV_FRAME: return (int)(m / HW);
-    case LKGD_RV_FRAMEPOS: return (int)((m / HW) % F);
-    case LKGD_RV_BATCH: return (int)(m / ((long long)HW * F));
-    case LKGD_RV_TCTX_0272: return (int)(((m / ((long long)HW * F)) * HW + (m % HW)) % B);
+    case LKGD_RV_FRAME: return (int)(m / hw);
+    case LKGD_RV_FRAMEPOS: return (int)((m / hw) % (unsigned)F);
+    case LKGD_RV_BATCH: return (int)(m / hwf);
+    case LKGD_RV_TCTX_0272: return (int)(((m / hwf) * hw + (m % hw)) % (unsigned)B);
     default: return 0;
   }
 }
 
 constexpr int CS_MAXG = 8;
-// grid (col blocks of 128 columns, row chunks); thread = one column over a chunk of rows, up to CS_MAXG groups
-__global__ void colsum_grouped_kernel(const float* __restrict__ G, long long M, int C, int rows_per_cta, int mode, int HW,
-                                      int F, int B, int n_groups, float* __restrict__ out, long long ldo) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// grid (column blocks of 128, row chunks); block = 128 columns x 4 row lanes; each thread walks its rows with 32-bit
+// index arithmetic (frame / pixel counters advanced incrementally), per-group partial sums reduced through smem, one
+// atomic per (group, column) per CTA
+__global__ void __launch_bounds__(512) colsum_grouped_kernel(const float* __restrict__ G, long long M, int C,
+                                                             int rows_per_cta, int mode, int HW, int F, int B,
+                                                             int n_groups, float* __restrict__ out, long long ldo) {
+  __shared__ float red[4][CS_MAXG][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const int c = blockIdx.x * 128 + tx;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
   float acc[CS_MAXG];
 #pragma unroll
   for (int i = 0; i < CS_MAXG; ++i) acc[i] = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const int gi = rv_index(mode, r, HW, F, B);
-    const float v = G[r * C + c];
+  if (c < C) {
+    for (long long r = r0 + ty; r < r1; r += 4) {
+      const int gi = rv_index(mode, r, HW, F, B);
+      const float v = __ldg(G + r * C + c);
 #pragma unroll
-    for (int i = 0; i < CS_MAXG; ++i) acc[i] += (i == gi) ? v : 0.f;
+      for (int i = 0; i < CS_MAXG; ++i) acc[i] += (i == gi) ? v : 0.f;
+    }
   }
 #pragma unroll
-  for (int i = 0; i < CS_MAXG; ++i)
-    if (i < n_groups && acc[i] != 0.f) atomicAdd(out + (size_t)i * ldo + c, acc[i]);
+  for (int i = 0; i < CS_MAXG; ++i) red[ty][i][tx] = acc[i];
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 0; i < n_groups; ++i) {
+      const float s = red[0][i][tx] + red[1][i][tx] + red[2][i][tx] + red[3][i][tx];
+      if (s != 0.f) atomicAdd(out + (size_t)i * ldo + c, s);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------- resampling gradients
@@ -513,6 +526,21 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     pi -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
     p[i] = pi;
   }
+}
+
+// contiguous-row fast path: 8 elements per thread, 128-bit loads / stores
+__global__ void cast2d_bf16_vec_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                       long long ldd, int rows, int cols, float alpha) {
+  const int cv = cols / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cv) return;
+  const long long r = idx / cv;
+  const int c = (int)(idx % cv) * 8;
+  float f[8];
+  ld8_f32(src + r * lds + c, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= alpha;
+  st8_bf16(dst + r * ldd + c, f);
 }
 
 __global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds, long long cs,
@@ -719,9 +747,14 @@ extern "C" int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t
   if (rv_HW <= 0) rv_HW = 1;
   if (rv_F <= 0) rv_F = 1;
   if (rv_B <= 0) rv_B = 1;
-  const int rows_per_cta = 256;
-  dim3 grid((C + 127) / 128, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
-  colsum_grouped_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, rv_mode, rv_HW,
+  // ~4 CTAs per SM; at least 64 rows per CTA so the atomics stay a small share
+  const int col_blocks = (C + 127) / 128;
+  long long want = (4LL * sm_count() + col_blocks - 1) / col_blocks;
+  long long rpc = (M + want - 1) / want;
+  if (rpc < 64) rpc = 64;
+  const int rows_per_cta = (int)rpc;
+  dim3 grid(col_blocks, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+  colsum_grouped_kernel<<<grid, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, rv_mode, rv_HW,
                                                                                    rv_F, rv_B, n_groups, out, ldo);
   return launch_epilogue();
 }
@@ -799,6 +832,12 @@ extern "C" int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t 
 extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, void* dst, int64_t ldd, int32_t rows,
                                 int32_t cols, float alpha, void* stream) {
   if (rows <= 0 || cols <= 0 || ldd < cols || src_cs <= 0) return LKGD_ESHAPE;
+  if (src_cs == 1 && cols % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0 && aligned16(src) && aligned16(dst)) {
+    const long long nv = (long long)rows * (cols / 8);
+    cast2d_bf16_vec_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
+    return launch_epilogue();
+  }
   const long long n = (long long)rows * cols;
   cast2d_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, lds, src_cs, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);

@@ -400,7 +400,7 @@ class LoraTrainer:
                 ops.cast2d_bf16(s["pB"][i], p.t_qkv.lora_b[i * C:(i + 1) * C, i * r_pad:i * r_pad + r], alpha=s["scaling"])
                 ops.cast2d_bf16(s["pB"][i].t(), tw.lora_bT[i * r_pad:i * r_pad + r, i * C:(i + 1) * C],
                                 alpha=s["scaling"])
-        if self.lk_params:
+        if self.lk_params and not torch.cuda.is_current_stream_capturing():
             self.unet._lk = None          # dense matrices of the latent-knowledge block are rebuilt from the parameters
 
     def named_grads(self):
@@ -460,7 +460,7 @@ class LoraTrainer:
             unet._context_backward(lk_saved, dctx, self.lk_grads)
         return loss
 
-    def optimizer_step(self):
+    def optimizer_step(self, repack: bool = True):
         """[all-reduce(sum)] -> grad-norm -> clip + AdamW (gradient averaged over ranks in-kernel) -> repack."""
         if self.world > 1:
             from .distributed import allreduce_flat_
@@ -471,9 +471,49 @@ class LoraTrainer:
         ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, beta1=self.betas[0],
                   beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.step_count, grad_scale=scale,
                   sumsq_buf=self.sumsq, max_norm=self.max_norm)
-        self.repack()
+        if repack:
+            self.repack()
 
     def train_step(self, *args, **kw) -> torch.Tensor:
+        if self._graph is not None:
+            return self._graphed_step(*args)
         loss = self.forward_backward(*args, **kw)
         self.optimizer_step()
         return loss
+
+    # ---- CUDA graphs: the step is ~1300 small launches at training sizes (14 frames, 40x64 latents) and would be
+    # bound by the Python / driver launch path; every shape is static, so forward+backward and the repack are captured
+    # once and replayed.  The optimizer (host-side step count) and the NCCL all-reduce stay outside the graphs.
+    _graph = None
+
+    def capture(self, *batch):
+        """Captures forward_backward (and the repack) for batches shaped like ``batch`` (device tensors: latents, noise,
+        sigmas, cond_latents, encoder_hidden_states, added_time_ids[, domain_features, flow_features]).  Call after at
+        least one eager step (lazy weight preprocessing and one-time kernel attributes must not happen under capture)."""
+        dev = self.unet.device
+        self._static = [b.to(dev).clone() for b in batch]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.forward_backward(*self._static)            # warm the allocator on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        if self.lk_params:
+            self.unet._lk = None       # rebuilt INSIDE the capture: every replay re-derives the dense matrices of the
+            #                            latent-knowledge block from the parameters the optimizer just updated
+        with torch.cuda.graph(g1):
+            self._static_loss = self.forward_backward(*self._static)
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self.repack()
+        self._graph = (g1, g2)
+        return self
+
+    def _graphed_step(self, *batch) -> torch.Tensor:
+        for s, b in zip(self._static, batch):
+            if s.data_ptr() != b.data_ptr():
+                s.copy_(b, non_blocking=True)
+        self._graph[0].replay()
+        self.optimizer_step(repack=False)
+        self._graph[1].replay()
+        return self._static_loss

@@ -378,23 +378,14 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         super().invalidate()
         self._lk = None
 
-    def _lk_pack(self):
-        """Weight preprocessing (once): every linear stage of the block as a dense fp32 matrix for the
-        small-linear kernel - grouped conv (+ the 1000->1024 linear interpolation folded in), Hamilton matrices,
-        rDFT(256) and irDFT(512) bases."""
-        if getattr(self, "_lk", None) is not None:
-            return self._lk
+    def _lk_const(self):
+        """Parameter-independent matrices of the block, built once per device: the 1000->1024 linear interpolation,
+        the rDFT(256) and irDFT(512) bases."""
         dev = self.device
+        c = getattr(self, "_lkc", None)
+        if c is not None and c["interp64"].device == dev:
+            return c
         f64 = torch.float64
-
-        def grouped(conv):          # Conv1d(1024->256, k=1, groups=256): out_j = sum_m w[j,m] x[4j+m]
-            w = conv.weight.detach().to(f64).reshape(256, 4)
-            full = torch.zeros(256, 1024, dtype=f64, device=dev)
-            j = torch.arange(256, device=dev)
-            for m in range(4):
-                full[j, 4 * j + m] = w[:, m]
-            return full
-
         # F.interpolate(size=1024, mode="linear", align_corners=False) as a [1024, 1000] matrix
         o = torch.arange(1024, dtype=f64, device=dev)
         src = ((o + 0.5) * (1000 / 1024) - 0.5).clamp(min=0)
@@ -404,13 +395,6 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         interp = torch.zeros(1024, 1000, dtype=f64, device=dev)
         interp[torch.arange(1024, device=dev), i0] += 1 - lam
         interp[torch.arange(1024, device=dev), i1] += lam
-
-        def ham(q):                 # y = x @ W  ->  small_linear weight is W^T [out, in]
-            r, i, j, k = (getattr(q, n).detach().to(f64) for n in ("r_weight", "i_weight", "j_weight", "k_weight"))
-            W = torch.cat([torch.cat([r, -i, -j, -k], 0), torch.cat([i, r, -k, j], 0),
-                           torch.cat([j, k, r, -i], 0), torch.cat([k, -j, i, r], 0)], 1)
-            return W.t().contiguous().float(), _f32(q.bias)
-
         n = torch.arange(256, dtype=f64, device=dev)
         k = torch.arange(129, dtype=f64, device=dev)
         ang = 2 * math.pi * k[:, None] * n[None, :] / 256
@@ -427,18 +411,45 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         ii = (-torch.sin(ang2) * wgt / 512)
         ii[:, 0] = 0
         ii[:, 256] = 0              # irfft ignores the imaginary part of the DC and Nyquist bins
+        self._lkc = dict(interp64=interp, interp=interp.float().contiguous(), j256=torch.arange(256, device=dev),
+                         dft_re=torch.cos(ang).float().contiguous(), dft_im=dft_im.float().contiguous(),
+                         idft=torch.cat([ir, ii], 1).float().contiguous())
+        return self._lkc
+
+    def _lk_pack(self):
+        """Weight preprocessing (once per parameter change): every linear stage of the block as a dense fp32 matrix for
+        the small-linear kernel - grouped conv (+ the 1000->1024 linear interpolation folded in), Hamilton matrices.
+        Only device-side tensor ops on the parameters (safe under CUDA-graph capture: training re-derives these inside
+        the captured step); the parameter-independent bases come from ``_lk_const``."""
+        if getattr(self, "_lk", None) is not None:
+            return self._lk
+        dev = self.device
+        f64 = torch.float64
+        c = self._lk_const()
+        j = c["j256"]
+
+        def grouped(conv):          # Conv1d(1024->256, k=1, groups=256): out_j = sum_m w[j,m] x[4j+m]
+            w = conv.weight.detach().to(f64).reshape(256, 4)
+            full = torch.zeros(256, 1024, dtype=f64, device=dev)
+            for m in range(4):
+                full[j, 4 * j + m] = w[:, m]
+            return full
+
+        def ham(q):                 # y = x @ W  ->  small_linear weight is W^T [out, in]
+            r, i, j_, k = (getattr(q, n).detach().to(f64) for n in ("r_weight", "i_weight", "j_weight", "k_weight"))
+            W = torch.cat([torch.cat([r, -i, -j_, -k], 0), torch.cat([i, r, -k, j_], 0),
+                           torch.cat([j_, k, r, -i], 0), torch.cat([k, -j_, i, r], 0)], 1)
+            return W.t().contiguous().float(), _f32(q.bias)
+
         sf = self.quaternion_lora_fuse_sf
+        gd, gf = grouped(self.quaternion_lora_dconv), grouped(self.quaternion_lora_fconv)
         self._lk = dict(
-            interp=interp.float().contiguous(),
-            dconv_g=grouped(self.quaternion_lora_dconv).float().contiguous(),
-            fconv_g=grouped(self.quaternion_lora_fconv).float().contiguous(),
+            interp=c["interp"], dconv_g=gd.float().contiguous(), fconv_g=gf.float().contiguous(),
             lconv=grouped(self.quaternion_lora_lconv).float().contiguous(),
-            dconv=(grouped(self.quaternion_lora_dconv) @ interp).float().contiguous(),
-            fconv=(grouped(self.quaternion_lora_fconv) @ interp).float().contiguous(),
+            dconv=(gd @ c["interp64"]).float().contiguous(), fconv=(gf @ c["interp64"]).float().contiguous(),
             fuse=ham(self.quaternion_lora_fuse), mag=ham(self.quaternion_lora_fuse_fft_mag),
             pha=ham(self.quaternion_lora_fuse_fft_pha),
-            dft_re=torch.cos(ang).float().contiguous(), dft_im=dft_im.float().contiguous(),
-            idft=torch.cat([ir, ii], 1).float().contiguous(),
+            dft_re=c["dft_re"], dft_im=c["dft_im"], idft=c["idft"],
             mag0=(_f32(self.quaternion_lora_fuse_fft_mag0.weight), _f32(self.quaternion_lora_fuse_fft_mag0.bias)),
             pha0=(_f32(self.quaternion_lora_fuse_fft_pha0.weight), _f32(self.quaternion_lora_fuse_fft_pha0.bias)),
             sf0=(_f32(sf[0].weight), _f32(sf[0].bias)), sf2=(_f32(sf[2].weight), _f32(sf[2].bias)),
