@@ -125,7 +125,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       issue(c, buf);                                       // both residuals: single-buffered
     } else if (NRES == 1) {
       if (k == 0) issue(c, buf);
-      if (c + 2 < nchunks) issue(c + 2, buf ^ 2048);       // this warp's next chunk, other buffer
+      if (c + 2 < nchunks) issue(c + 2, stg + ((k + 1) & 1) * 2048);   // this warp's next chunk, other buffer
+      //                                (not `buf ^ 2048`: the staging base is only 1024-byte aligned)
     }
     uint32_t a[CW], g[GEGLU ? CW : 1];
     if (CW == 16) {

@@ -8,6 +8,9 @@
 // smem: S stages x (A 128x64 bf16 = 16 KB, B BNx64 bf16 = BN*128 B), SWIZZLE_128B; S = 4 (BN = 256) .. 8;
 //       + 8 x 4 KB epilogue staging.
 // See include/lkgd_b200.h (lkgd_gemm) for the contract and the reference call sites it replaces.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -102,6 +105,12 @@ __device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoo
 
 namespace lkgd {
 
+// CTA2 = false: one CTA per 128 x BN tile (cta_group::1).
+// CTA2 = true : a cluster of two CTAs shares one 256 x BN tile (cta_group::2): CTA r holds A rows r*128.. and HALF of the
+//               B tile (rows r*BN/2..); the leader (rank 0) issues 256 x BN x 16 UMMAs that read both halves, so every SM
+//               pulls 16 KB + BN*64 B per k-block instead of 16 KB + BN*128 B (the main loop is L2->smem bound).
+//               Accumulator rows stay in each CTA's own TMEM; both CTAs run their own epilogue.
+template <bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -115,78 +124,104 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile stream index (pair or CTA)
+  const int n_workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles;                // 256-row (pair) or 128-row units
+  const int total_tiles = m_units * p.n_tiles;
   const int kiters = p.ntaps * p.kb0 + p.kb1;
   const int S = p.stages;
+  const int bn_load = CTA2 ? p.BN / 2 : p.BN;                                // B rows this CTA loads per stage
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CTA2 ? 2 * EPI_WARPS : EPI_WARPS); }
       fence_barrier_init();
       tma_prefetch_desc(&p.tmA[0]);
       tma_prefetch_desc(&p.tmB);
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    if (CTA2) tmem_alloc_2cta(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n0 = (tile % p.n_tiles) * p.BN;
-      TileCoord tc; tile_origin(p, m_tile, tc);
-      for (int it = 0; it < kiters; ++it) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx_bytes);
-        void* dA = smem + stage * p.stage_bytes;
-        void* dB = smem + stage * p.stage_bytes + A_STAGE_BYTES;
-        const bool seg1 = it >= p.ntaps * p.kb0;
-        int tap = 0, kb, dx = 0, dy = 0;
-        const CUtensorMap* mA;
-        if (!seg1) {
-          tap = it / p.kb0; kb = it % p.kb0;
-          mA = &p.tmA[p.tap_map[tap]]; dx = p.tap_dx[tap]; dy = p.tap_dy[tap];
-        } else {
-          kb = it - p.ntaps * p.kb0;
-          mA = &p.tmA1;
-        }
-        if (p.mode == LKGD_A_LINEAR) tma_load_2d(dA, mA, &full[stage], kb * BK, tc.c1);
-        else if (p.mode == LKGD_A_CONV3X3) tma_load_4d(dA, mA, &full[stage], kb * BK, tc.c1 + dx, tc.c2 + dy, tc.c3);
-        else tma_load_4d(dA, mA, &full[stage], kb * BK, tc.c1, tc.c2 + dy, tc.c3);
-        if (!seg1) tma_load_2d(dB, &p.tmB, &full[stage], tap * p.k0 + kb * BK, n0);
-        else tma_load_2d(dB, &p.tmB1, &full[stage], kb * BK, n0);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+    // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
+    // One thread: every instruction here is on a dependent scalar chain, so the k loop carries NO index arithmetic -
+    // taps / k-blocks are nested loops, smem and barrier addresses advance incrementally (measured: ~500 cycles per
+    // k-block of divisions, table look-ups and address conversions before this rewrite, vs 320-512 cycles of MMA).
+    const uint32_t tx_bytes = (A_STAGE_BYTES + bn_load * BK * 2) * (CTA2 ? 2 : 1);
+    const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
+    const uint32_t full_remote0 = CTA2 ? mapa_shared(full0, 0) : full0;   // where the load bytes are counted
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    uint32_t stage = 0, phase = 0, sa = smem0;
+    const bool lin = p.mode == LKGD_A_LINEAR;
+    auto step = [&](const CUtensorMap* mA, int a0, int a1, int a2, int a3, const CUtensorMap* mB, int b0, int b1) {
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+      if (!CTA2 || rank == 0) mbar_expect_tx_a(full0 + stage * 8, tx_bytes);
+      const uint32_t fb = full_remote0 + stage * 8;
+      if (CTA2) {
+        if (lin) tma_load_2d_2cta_a(sa, mA, fb, a0, a1); else tma_load_4d_2cta_a(sa, mA, fb, a0, a1, a2, a3);
+        tma_load_2d_2cta_a(sa + A_STAGE_BYTES, mB, fb, b0, b1);
+      } else {
+        if (lin) tma_load_2d_a(sa, mA, fb, a0, a1); else tma_load_4d_a(sa, mA, fb, a0, a1, a2, a3);
+        tma_load_2d_a(sa + A_STAGE_BYTES, mB, fb, b0, b1);
       }
+      sa += stage_bytes;
+      if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; sa = smem0; }
+    };
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      const int m_unit = tile / p.n_tiles;
+      const int m_tile = CTA2 ? m_unit * 2 + rank : m_unit;
+      const int n0 = (tile - m_unit * p.n_tiles) * p.BN + rank * bn_load;
+      TileCoord tc; tile_origin(p, m_tile, tc);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const CUtensorMap* mA = &p.tmA[p.tap_map[tap]];
+        const int c1 = tc.c1 + (p.mode == LKGD_A_CONV3X3 ? p.tap_dx[tap] : 0);
+        const int c2 = tc.c2 + p.tap_dy[tap];
+        int kcol = 0, bcol = tap * p.k0;
+#pragma unroll 1
+        for (int kb = 0; kb < p.kb0; ++kb, kcol += BK, bcol += BK) step(mA, kcol, c1, c2, tc.c3, &p.tmB, bcol, n0);
+      }
+      int kcol = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < p.kb1; ++kb, kcol += BK) step(&p.tmA1, kcol, tc.c1, tc.c2, tc.c3, &p.tmB1, kcol, n0);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    int stage = 0; uint32_t phase = 0;
-    const uint32_t idesc = umma_idesc_bf16(p.BN);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
+    const uint32_t idesc = umma_idesc_bf16(p.BN, CTA2 ? 256 : 128);
+    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+    const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem));
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem) + A_STAGE_BYTES);
+    const uint64_t dstep = (uint64_t)(p.stage_bytes >> 4);      // the address field counts 16-byte units
+    uint32_t stage = 0, phase = 0;
+    uint64_t ad = adesc0, bd = bdesc0;
     int tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++tile_iter) {
       const int as = tile_iter & 1;
-      mbar_wait(&tempty[as], ((tile_iter >> 1) & 1) ^ 1);
+      mbar_wait_a(tempty0 + as * 8, ((tile_iter >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * 256;
+      uint32_t acc = 0;
+#pragma unroll 1
       for (int it = 0; it < kiters; ++it) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait_a(full0 + stage * 8, phase);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smem + stage * p.stage_bytes));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + stage * p.stage_bytes + A_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-        umma_commit(&empty[stage]);
-        if (it == kiters - 1) umma_commit(&tfull[as]);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < BK / 16; ++k) {
+          if (CTA2) umma_bf16_2cta(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
+          else umma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
+          acc = 1;
+        }
+        if (CTA2) umma_commit_2cta_a(empty0 + stage * 8); else umma_commit_a(empty0 + stage * 8);
+        ad += dstep; bd += dstep;
+        if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; ad = adesc0; bd = bdesc0; }
       }
+      if (CTA2) umma_commit_2cta_a(tfull0 + as * 8); else umma_commit_a(tfull0 + as * 8);
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue (8 warps, 2 per TMEM lane quarter)
@@ -196,9 +231,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int half = ew >> 2;                             // which alternate chunks it takes
     const uint32_t stg = smem_u32(sm_epi + ew * EPI_WARP_BYTES);
     int tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++tile_iter) {
       const int as = tile_iter & 1;
-      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+      const int m_tile = CTA2 ? (tile / p.n_tiles) * 2 + rank : tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
       TileCoord tc; tile_origin(p, m_tile, tc);
       // bias of this tile -> smem (overlaps the tile's MMAs); buffer `as` was last read two tiles ago and every
       // epilogue warp has passed the previous tile's barrier since
@@ -211,24 +247,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       mbar_wait(&tfull[as], (tile_iter >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(lane_base) << 16);
-      epilogue_dispatch(p, tc, n_tile, taddr, lane_base, lane, half, stg, sb);
+      if (m_tile < p.m_tiles)        // the odd CTA of the last pair may have no rows of its own
+        epilogue_dispatch(p, tc, n_tile, taddr, lane_base, lane, half, stg, sb);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_remote(mapa_shared(smem_u32(&tempty[as]), 0));   // the leader's MMA warp waits for both
+        else mbar_arrive(&tempty[as]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (CTA2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ----------------------------------------------------------------------------------------------- host side
 static int choose_bn(int N, bool geglu) {
   if (geglu) return 256;
+  if (const char* e = getenv("LKGD_GEMM_BN")) {       // tuning experiments only
+    int bn = atoi(e);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0) return bn;
+  }
   int n16 = (N + 15) / 16 * 16;
   if (n16 <= 256) return n16;
   for (int bn = 256; bn >= 128; bn -= 16)
@@ -246,7 +291,19 @@ static void choose_patch(int H, int W, int& TW, int& TH) {
   }
 }
 
-static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
+// CTA pairs (cta_group::2) halve the weight-tile traffic per SM but couple the two CTAs' epilogues to one MMA stream.
+// Measured on the C3 shapes (tools/bench_gemm.py, profiles/r01c_gemm_microbench.json): they win when the main loop is
+// long and wide (BN = 256 with K >= 1280: +5..25 %, any tile with K >= 2880: +2..20 %), lose on the short-K,
+// epilogue-bound L0 layers (-5..-12 %).
+static bool use_cta_pairs(int m_tiles, int n_tiles, int BN, long long k_total) {
+  if (getenv("LKGD_GEMM_1CTA")) return false;
+  if (BN % 16) return false;
+  if (getenv("LKGD_GEMM_2CTA")) return m_tiles >= 2;
+  if (m_tiles < 8) return false;
+  return (BN == 256 && k_total >= 1280) || k_total >= 2880;
+}
+
+static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
   memset(&p, 0, sizeof(p));
   if (a->M <= 0 || a->N <= 0 || a->K0 <= 0) return LKGD_ESHAPE;
   if (a->K0 % 8 || a->K1 % 8 || a->ldb % 8 || (a->K1 && a->ldb1 % 8)) return LKGD_EALIGN;
@@ -335,10 +392,12 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
   } else {
     return LKGD_ESHAPE;
   }
+  cta2 = use_cta_pairs(p.m_tiles, p.n_tiles, p.BN, (long long)p.ntaps * a->K0 + a->K1);
+  const int bn_load = cta2 ? p.BN / 2 : p.BN;
   {
     uint64_t dims[2] = {(uint64_t)p.ntaps * a->K0, (uint64_t)a->N};
     uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.BN};
+    uint32_t box[2] = {BK, (uint32_t)bn_load};
     if ((rc = make_tmap(&p.tmB, a->Bw, 2, dims, strides, box))) return rc;
     if (a->K1) {
       uint64_t d1[2] = {(uint64_t)a->K1, (uint64_t)a->N};
@@ -355,7 +414,7 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p) {
   p.res1 = a->res1; p.ldr1 = a->ldr1; p.res1_f32 = a->res1_f32;
   p.res2 = a->res2; p.ldr2 = a->ldr2; p.res2_f32 = a->res2_f32;
   p.out = a->out; p.ldo = a->ldo; p.out_f32 = a->out_f32; p.n_store = a->n_store;
-  p.stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  p.stage_bytes = A_STAGE_BYTES + bn_load * BK * 2;
   p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_WARPS * EPI_WARP_BYTES) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   {
@@ -379,20 +438,53 @@ using namespace lkgd;
 extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
   if (a == nullptr || a->A == nullptr || a->Bw == nullptr || a->out == nullptr) return LKGD_ESHAPE;
   GemmParams p;
-  int rc = fill_params(a, p);
+  bool cta2 = false;
+  int rc = fill_params(a, p, cta2);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
   if (!p.fast_io && (a->res1 || a->res2)) return LKGD_EALIGN;   // residual rows must be 16-byte addressable
   if (a->res2 && (!a->res1 || (a->res1_f32 != 0) != (a->res2_f32 != 0))) return LKGD_ESHAPE;   // res2 needs res1 of the same dtype
   const int smem_bytes = 1024 + p.stages * p.stage_bytes + EPI_WARPS * EPI_WARP_BYTES + BIAS_BYTES + BAR_BYTES;
-  int grid = p.m_tiles * p.n_tiles;
   int sms = sm_count();
+  if (cta2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // persistent pairs: never launch more clusters than can be co-resident (a GPC with an odd SM count strands one SM)
+    static int max_pairs = 0;
+    if (max_pairs == 0) {
+      cfg.gridDim = dim3(sms);
+      cfg.dynamicSmemBytes = SMEM_LIMIT;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sms / 2 - 4;
+      }
+      max_pairs = n;
+      cfg.dynamicSmemBytes = smem_bytes;
+    }
+    int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    if (pairs > max_pairs) pairs = max_pairs;
+    cfg.gridDim = dim3(2 * pairs);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    return launch_epilogue();
+  }
+  int grid = p.m_tiles * p.n_tiles;
   if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
 }

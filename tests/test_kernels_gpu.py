@@ -387,3 +387,65 @@ def test_fp32_residual_stream_variants(cuda):
     xb = rnd(500, 320, dev=cuda, seed=12)
     ops.axpby(xb, 4.0, y, 1.0)
     assert rel_l2(y, x + 4.0 * xb.float()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- CTA pairs
+def _both_gemm_variants(fn):
+    """Runs ``fn`` with the one-CTA kernel and with the cta_group::2 pair kernel forced (LKGD_GEMM_1CTA / _2CTA are read
+    per call)."""
+    import os
+    os.environ["LKGD_GEMM_1CTA"] = "1"
+    try:
+        one = fn().clone()
+    finally:
+        del os.environ["LKGD_GEMM_1CTA"]
+    os.environ["LKGD_GEMM_2CTA"] = "1"
+    try:
+        two = fn().clone()
+    finally:
+        del os.environ["LKGD_GEMM_2CTA"]
+    return one, two
+
+
+@pytest.mark.parametrize("M,N,K", [(1536, 320, 2880), (1536, 160, 512), (1536, 640, 512), (1536, 256, 512),
+                                   (1100, 1280, 1280), (130, 48, 72)])
+def test_gemm_cta_pairs_match_single_cta_linear(cuda, M, N, K):
+    """Same accumulation order in both kernels -> bit-identical results, for every epilogue flavour (this caught a
+    staging-buffer toggle that assumed a 4 KB aligned base: only BN = 160 pair tiles broke it)."""
+    from lkgd_b200 import ops
+    A = rnd(M, K, dev=cuda, seed=1)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5, seed=2)
+    b = rnd(N, dev=cuda, dtype=torch.float32, seed=3)
+    r = rnd(M, N, dev=cuda, dtype=torch.float32, seed=4)
+    rb = r.to(bf16)
+    cases = {"plain": dict(), "f32": dict(out_f32=True), "res32->f32": dict(res1=r, out_f32=True),
+             "res32->bf16": dict(res1=r), "resbf->bf16": dict(res1=rb), "resbf->f32": dict(res1=rb, out_f32=True),
+             "2res32": dict(res1=r, res2=r, s2=0.5, out_f32=True), "2resbf": dict(res1=rb, res2=rb, s1=0.3, s2=-1.0)}
+    for name, kw in cases.items():
+        one, two = _both_gemm_variants(lambda: ops.gemm(A, W, bias=b, **kw))
+        assert torch.equal(one, two), name
+    if N % 256 == 0:
+        Wp, bp = ops.pack_geglu(W, b)
+        one, two = _both_gemm_variants(lambda: ops.gemm(A, Wp, bias=bp, act=ops.ACT_GEGLU))
+        assert torch.equal(one, two)
+    ref = A.float() @ W.float().t() + b + r
+    assert rel_l2(ops.gemm(A, W, bias=b, res1=r, out_f32=True), ref) < 1e-5
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,stride", [(6, 16, 16, 320, 320, 1), (5, 12, 20, 192, 640, 1), (3, 16, 16, 64, 32, 1),
+                                                (6, 16, 16, 128, 256, 2)])
+def test_gemm_cta_pairs_match_single_cta_conv(cuda, n, h, w, ci, co, stride):
+    from lkgd_b200 import ops
+    A = rnd(n * h * w, ci, dev=cuda, seed=1)
+    W = rnd(co, 9 * ci, dev=cuda, scale=(9 * ci) ** -0.5, seed=2)
+    b = rnd(co, dev=cuda, dtype=torch.float32, seed=3)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    r = rnd(n * ho * wo, co, dev=cuda, dtype=torch.float32, seed=4)
+    for kw in (dict(out_f32=True), dict(res1=r, out_f32=True), dict()):
+        one, two = _both_gemm_variants(lambda: ops.gemm(A, W, mode=ops.A_CONV3X3, conv=(n, h, w, stride), bias=b, **kw))
+        assert torch.equal(one, two)
+    Bt, Ft, HWt = 2, n, h * w // 2
+    At = rnd(Bt * Ft * HWt, ci, dev=cuda, seed=5)
+    Wt = rnd(co, 3 * ci, dev=cuda, scale=(3 * ci) ** -0.5, seed=6)
+    one, two = _both_gemm_variants(lambda: ops.gemm(At, Wt, mode=ops.A_TCONV3, tconv=(Bt, Ft, HWt), out_f32=True))
+    assert torch.equal(one, two)
