@@ -188,18 +188,29 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
       // has been consumed by the tensor core)
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
       if (j > 0) mbar_wait(o_full, (j - 1) & 1);
+      const bool full_blk = kv_valid == AT_BK;     // every block but possibly the last: no per-element masking
 #pragma unroll
       for (int c = 0; c < AT_BK; c += 32) {
         uint32_t s[32];
         tmem_ld32(tmem_S + lane_addr + c, s);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (full_blk) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run)) : 0.f;
-          const float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run)) : 0.f;
-          ls4[(i >> 1) & 3] += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run));
+            const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run));
+            ls4[(i >> 1) & 3] += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run)) : 0.f;
+            const float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run)) : 0.f;
+            ls4[(i >> 1) & 3] += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
         }
         uint8_t* blk = prow + (c >> 6) * AT_TILE;
 #pragma unroll

@@ -1,6 +1,8 @@
 // GroupNorm(+SiLU) and LayerNorm for channels-last bf16 activations: HBM-bound, 128-bit vectorised.
 // GroupNorm is two kernels: (1) per-(sample, channel) sum / sum-of-squares -> fp64 atomics, (2) normalise.
 // See include/lkgd_b200.h for the contract and the reference modules replaced.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -36,11 +38,23 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  for (int r = r0 + rl; r < r1; r += g.rows_par) {
-    float f[8];
-    gn_load(x1, x2, g, (long long)ns * g.R + r, v, f);
+  // four rows' loads are issued before any is consumed (memory-level parallelism: one row per thread in flight left
+  // the kernel latency-bound at ~60 % of HBM bandwidth)
+  for (int r = r0 + rl; r < r1; r += 4 * g.rows_par) {
+    float f[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * g.rows_par;
+      if (rr < r1) gn_load(x1, x2, g, (long long)ns * g.R + rr, v, f[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[u][i]; q[i] = fmaf(f[u][i], f[u][i], q[i]); }
   }
   float* my = sh + (size_t)threadIdx.x * 16;
 #pragma unroll
@@ -56,24 +70,23 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, const void* __restr
   }
 }
 
-__global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
-                                const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int groups, int silu,
-                                __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float sh[];  // scale[C], shift[C], mean[groups], rstd[groups]
-  float* scale = sh;
-  float* shift = sh + g.C;
-  float* gmean = sh + 2 * g.C;
-  float* grstd = gmean + groups;
-  const int ns = blockIdx.y;
-  const int cpg = g.C / groups;
+// per (sample, channel) scale = rstd * gamma, shift = beta - mean * rstd * gamma, once per call (grid = NS): the apply
+// CTAs then start streaming immediately instead of each re-deriving the statistics of all groups in a prologue
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, int groups, int C, int R,
+                                   float2* __restrict__ ss /* [NS][C] (scale, shift) */) {
+  extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  float* gmean = sh;
+  float* grstd = sh + groups;
+  const int ns = blockIdx.x;
+  const int cpg = C / groups;
   for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
     double s = 0.0, q = 0.0;
     for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-      s += sums[((size_t)ns * g.C + c) * 2];
-      q += sums[((size_t)ns * g.C + c) * 2 + 1];
+      s += sums[((size_t)ns * C + c) * 2];
+      q += sums[((size_t)ns * C + c) * 2 + 1];
     }
-    const double n = (double)cpg * g.R;
+    const double n = (double)cpg * R;
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -81,31 +94,49 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
     grstd[gi] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int gi = c / cpg;
     const float sc = grstd[gi] * gamma[c];
-    scale[c] = sc;
-    shift[c] = beta[c] - gmean[gi] * sc;
+    ss[(size_t)ns * C + c] = make_float2(sc, beta[c] - gmean[gi] * sc);
   }
-  __syncthreads();
+}
+
+__global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
+                                const float2* __restrict__ ss, int silu, __nv_bfloat16* __restrict__ out) {
+  const int ns = blockIdx.y;
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
   const int r0 = blockIdx.x * g.rows_per_cta;
   const int r1 = min(r0 + g.rows_per_cta, g.R);
   float sc[8], sf[8];
+  {
+    const float4* p4 = reinterpret_cast<const float4*>(ss + (size_t)ns * g.C + v * 8);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sc[i] = scale[v * 8 + i]; sf[i] = shift[v * 8 + i]; }
-  for (int r = r0 + rl; r < r1; r += g.rows_par) {
-    const long long row = (long long)ns * g.R + r;
-    float f[8];
-    gn_load(x1, x2, g, row, v, f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = fmaf(f[i], sc[i], sf[i]);
-      f[i] = silu ? silu_f(y) : y;
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(p4 + i);
+      sc[2 * i] = t.x; sf[2 * i] = t.y; sc[2 * i + 1] = t.z; sf[2 * i + 1] = t.w;
     }
-    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                         pack_bf16x2(f[6], f[7]));
-    *reinterpret_cast<uint4*>(out + row * g.C + v * 8) = o;
+  }
+  for (int r = r0 + rl; r < r1; r += 4 * g.rows_par) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * g.rows_par;
+      if (rr < r1) gn_load(x1, x2, g, (long long)ns * g.R + rr, v, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * g.rows_par;
+      if (rr < r1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = fmaf(f[u][i], sc[i], sf[i]);
+          f[u][i] = silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(out + ((long long)ns * g.R + rr) * g.C + v * 8) =
+            make_uint4(pack_bf16x2(f[u][0], f[u][1]), pack_bf16x2(f[u][2], f[u][3]), pack_bf16x2(f[u][4], f[u][5]),
+                       pack_bf16x2(f[u][6], f[u][7]));
+      }
+    }
   }
 }
 
@@ -122,7 +153,9 @@ __device__ __forceinline__ int ln_rowvec_index(int mode, long long m, int HW, in
   }
 }
 
-template <int NV, bool XF32>
+// One warp per row, ROWS rows per warp in flight (all loads of an iteration are issued before the first reduction:
+// with a single 1.3 KB row per warp the kernel was latency-bound at ~50 % of HBM bandwidth), grid-stride over rows.
+template <int NV, bool XF32, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, int M, int C,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
@@ -131,79 +164,99 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  float f[NV][8];
-  const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(xv) + row * C;   // XF32 == false
-  const float* xr32 = reinterpret_cast<const float*>(xv) + row * C;                 // XF32 == true
-  const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * addvec_ld : nullptr;
-  float s = 0.f;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row0 = warp_id * ROWS; row0 < M; row0 += warps * ROWS) {
+    float f[ROWS][NV][8];
+    // ---- loads (+ fused add) of all rows of this iteration
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int v = lane + 32 * j;
-    if (v < nvec) {
-      if (XF32) {
-        const float4 x0 = *reinterpret_cast<const float4*>(xr32 + v * 8);
-        const float4 x1 = *(reinterpret_cast<const float4*>(xr32 + v * 8) + 1);
-        f[j][0] = x0.x; f[j][1] = x0.y; f[j][2] = x0.z; f[j][3] = x0.w;
-        f[j][4] = x1.x; f[j][5] = x1.y; f[j][6] = x1.z; f[j][7] = x1.w;
-      } else {
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(xr + v * 8), f[j]);
-      }
-      if (av) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + v * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + v * 8) + 1);
-        f[j][0] += a0.x; f[j][1] += a0.y; f[j][2] += a0.z; f[j][3] += a0.w;
-        f[j][4] += a1.x; f[j][5] += a1.y; f[j][6] += a1.z; f[j][7] += a1.w;
-        if (XF32) {
-          if (sum_out_v) {
-            float* so = reinterpret_cast<float*>(sum_out_v) + row * C + v * 8;
-            *reinterpret_cast<float4*>(so) = make_float4(f[j][0], f[j][1], f[j][2], f[j][3]);
-            *(reinterpret_cast<float4*>(so) + 1) = make_float4(f[j][4], f[j][5], f[j][6], f[j][7]);
+    for (int u = 0; u < ROWS; ++u) {
+      const long long row = row0 + u;
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int v = lane + 32 * j;
+          if (v < nvec) {
+            if (XF32) {
+              const float* xr32 = reinterpret_cast<const float*>(xv) + row * C;
+              const float4 x0 = *reinterpret_cast<const float4*>(xr32 + v * 8);
+              const float4 x1 = *(reinterpret_cast<const float4*>(xr32 + v * 8) + 1);
+              f[u][j][0] = x0.x; f[u][j][1] = x0.y; f[u][j][2] = x0.z; f[u][j][3] = x0.w;
+              f[u][j][4] = x1.x; f[u][j][5] = x1.y; f[u][j][6] = x1.z; f[u][j][7] = x1.w;
+            } else {
+              const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(xv) + row * C;
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(xr + v * 8), f[u][j]);
+            }
           }
-        } else {
-          // bf16 residual stream: normalise what is actually stored
-          uint4 o = make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]),
-                               pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
-          if (sum_out_v)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(sum_out_v) + row * C + v * 8) = o;
-          unpack_bf16x8(o, f[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const long long row = row0 + u;
+      if (row >= M) break;
+      const float* av = addvec ? addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * addvec_ld : nullptr;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int v = lane + 32 * j;
+        if (v < nvec) {
+          if (av) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + v * 8));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + v * 8) + 1);
+            f[u][j][0] += a0.x; f[u][j][1] += a0.y; f[u][j][2] += a0.z; f[u][j][3] += a0.w;
+            f[u][j][4] += a1.x; f[u][j][5] += a1.y; f[u][j][6] += a1.z; f[u][j][7] += a1.w;
+            if (XF32) {
+              if (sum_out_v) {
+                float* so = reinterpret_cast<float*>(sum_out_v) + row * C + v * 8;
+                *reinterpret_cast<float4*>(so) = make_float4(f[u][j][0], f[u][j][1], f[u][j][2], f[u][j][3]);
+                *(reinterpret_cast<float4*>(so) + 1) = make_float4(f[u][j][4], f[u][j][5], f[u][j][6], f[u][j][7]);
+              }
+            } else {
+              // bf16 residual stream: normalise what is actually stored
+              uint4 o = make_uint4(pack_bf16x2(f[u][j][0], f[u][j][1]), pack_bf16x2(f[u][j][2], f[u][j][3]),
+                                   pack_bf16x2(f[u][j][4], f[u][j][5]), pack_bf16x2(f[u][j][6], f[u][j][7]));
+              if (sum_out_v)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(sum_out_v) + row * C + v * 8) = o;
+              unpack_bf16x8(o, f[u][j]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += f[u][j][i];
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += f[j][i];
-    }
-  }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / C;
+      float q = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+      for (int j = 0; j < NV; ++j) {
+        if (lane + 32 * j < nvec) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    if (lane + 32 * j < nvec) {
+          for (int i = 0; i < 8; ++i) { const float d = f[u][j][i] - mean; q = fmaf(d, d, q); }
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; q = fmaf(d, d, q); }
-    }
-  }
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / C + eps);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
+      for (int j = 0; j < NV; ++j) {
+        const int v = lane + 32 * j;
+        if (v < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float y[8];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int v = lane + 32 * j;
-    if (v < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float y[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = (f[j][i] - mean) * rstd * gg[i] + bb[i];
-      *reinterpret_cast<uint4*>(out + row * C + v * 8) =
-          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                     pack_bf16x2(y[6], y[7]));
+          for (int i = 0; i < 8; ++i) y[i] = (f[u][j][i] - mean) * rstd * gg[i] + bb[i];
+          *reinterpret_cast<uint4*>(out + row * C + v * 8) =
+              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                         pack_bf16x2(y[6], y[7]));
+        }
+      }
     }
   }
 }
@@ -214,8 +267,11 @@ static GnGeom gn_geom(int C1, int C2, int R, int x_f32) {
   g.rows_par = 512 / g.vecs;
   if (g.rows_par < 1) g.rows_par = 1;
   if (g.rows_par > R) g.rows_par = R;
-  // ~8 rows per thread per CTA keeps >= 2 waves of CTAs at SVD sizes while amortising the prologue
-  g.rows_per_cta = g.rows_par * 8;
+  // 16 rows per thread per CTA (four batches of four loads in flight): >= 2 waves of CTAs at SVD sizes, and half the
+  // fp64 atomics / CTA launches of the 8-row version
+  static int rows_mult = 0;
+  if (rows_mult == 0) { const char* e = getenv("LKGD_GN_ROWS"); rows_mult = e ? atoi(e) : 16; if (rows_mult < 4) rows_mult = 4; }
+  g.rows_per_cta = g.rows_par * rows_mult;
   return g;
 }
 
@@ -223,7 +279,10 @@ static GnGeom gn_geom(int C1, int C2, int R, int x_f32) {
 
 using namespace lkgd;
 
-extern "C" size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C) { return (size_t)NS * C * 2 * sizeof(double); }
+// [NS][C][2] doubles (sum, sum of squares; what the backward re-reads) followed by [NS][C] float2 (scale, shift)
+extern "C" size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C) {
+  return (size_t)NS * C * (2 * sizeof(double) + sizeof(float2));
+}
 
 extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R,
                               int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
@@ -235,7 +294,8 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
   if (ws_bytes < lkgd_groupnorm_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GnGeom g = gn_geom(C1, C2, R, x_f32);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, lkgd_groupnorm_workspace(NS, C), st);
+  const size_t sums_bytes = (size_t)NS * C * 2 * sizeof(double);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sums_bytes, st);
   if (e != cudaSuccess) return set_cuda_error(e);
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
   const int threads = g.vecs * g.rows_par;
@@ -248,10 +308,12 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
   gn_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, g, reinterpret_cast<double*>(workspace));
   int rc = launch_epilogue();
   if (rc) return rc;
-  const size_t sh2 = (size_t)(2 * C + 2 * groups) * sizeof(float);
-  gn_apply_kernel<<<grid, threads, sh2, st>>>(x1, x2, g,
-                                              reinterpret_cast<const double*>(workspace), gamma, beta, eps, groups,
-                                              silu, reinterpret_cast<__nv_bfloat16*>(out));
+  float2* ss = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sums_bytes);
+  gn_finalize_kernel<<<NS, 256, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const double*>(workspace), gamma, beta,
+                                                                 eps, groups, C, R, ss);
+  rc = launch_epilogue();
+  if (rc) return rc;
+  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out));
   return launch_epilogue();
 }
 
@@ -263,30 +325,32 @@ extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* 
       !aligned16(gamma) || !aligned16(beta))
     return LKGD_EALIGN;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rows_per_cta = 8;
-  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
   const int nv = (C / 8 + 31) / 32;
   if (addvec_ld <= 0) addvec_ld = C;
   if (addvec_ld % 4) return LKGD_EALIGN;
   if (rv_HW <= 0) rv_HW = 1;
   if (rv_F <= 0) rv_F = 1;
   if (rv_B <= 0) rv_B = 1;
-#define LN_LAUNCH(NV)                                                                                              \
+#define LN_LAUNCH(NV, ROWS)                                                                                        \
   do {                                                                                                             \
+    int g_ = (M + 8 * (ROWS) - 1) / (8 * (ROWS));                                                                  \
+    if (g_ > 8 * sm_count()) g_ = 8 * sm_count();                                                                  \
     if (x_f32)                                                                                                     \
-      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, rv_HW,\
-                                                       rv_F, rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));      \
+      layernorm_kernel<NV, true, ROWS><<<g_, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode,  \
+                                                           rv_HW, rv_F, rv_B, sum_out,                             \
+                                                           reinterpret_cast<__nv_bfloat16*>(out));                 \
     else                                                                                                           \
-      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode,      \
-                                                        rv_HW, rv_F, rv_B, sum_out, reinterpret_cast<__nv_bfloat16*>(out));     \
+      layernorm_kernel<NV, false, ROWS><<<g_, 256, 0, st>>>(x, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, \
+                                                            rv_HW, rv_F, rv_B, sum_out,                            \
+                                                            reinterpret_cast<__nv_bfloat16*>(out));                \
   } while (0)
   switch (nv) {
-    case 1: LN_LAUNCH(1); break;
-    case 2: LN_LAUNCH(2); break;
-    case 3: LN_LAUNCH(3); break;
-    case 4: LN_LAUNCH(4); break;
-    case 5: LN_LAUNCH(5); break;
-    default: LN_LAUNCH(8); break;
+    case 1: LN_LAUNCH(1, 4); break;
+    case 2: LN_LAUNCH(2, 4); break;
+    case 3: LN_LAUNCH(3, 2); break;
+    case 4: LN_LAUNCH(4, 2); break;
+    case 5: LN_LAUNCH(5, 2); break;
+    default: LN_LAUNCH(8, 1); break;
   }
 #undef LN_LAUNCH
   return launch_epilogue();
