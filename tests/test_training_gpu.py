@@ -184,3 +184,34 @@ def test_cuda_graph_step_matches_eager(cuda):
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-4
     assert rel_l2(g1, g0) < 8e-2          # Adam's g / sqrt(v) amplifies atomics-order noise of near-zero gradients
     assert rel_l2(p1, p0) < 5e-3          # first Adam steps move every weight by ~lr * sign(g): noise flips a few signs
+
+
+def test_trained_adapters_survive_the_wire_format(cuda, tmp_path):
+    """train a few steps -> pytorch_lora_weights.safetensors (the file the reference's loop writes) -> fresh model
+    without adapters -> identical forward."""
+    import oracle as O
+    from lkgd_b200 import lora_io
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionModel
+    cfg = dict(REDUCED_CONFIG, cross_attention_dim=1024)
+    o, p = _pair(O.UNetSpatioTemporalConditionModel, UNetSpatioTemporalConditionModel, cfg, cuda, lora=dict(r=8))
+    B = 2
+    lat, noise, cond, ctx, sig = (t.to(cuda) for t in _train_inputs(B, 8, 16, 16, 1024))
+    g = torch.Generator().manual_seed(9)
+    dom, flo = torch.randn(B, 1, 1000, generator=g).to(cuda), torch.randn(B, 1, 1000, generator=g).to(cuda)
+    ids = O.add_time_ids_training(5, 127, 0.02, B).to(cuda)
+    tr = LoraTrainer(p, lr=1e-3)
+    for _ in range(3):
+        tr.train_step(lat, noise, sig, cond, ctx, ids, dom, flo)
+    path = lora_io.save_lora_weights(p, str(tmp_path))
+    base = {k: v for k, v in o.state_dict().items() if ".lora_" not in k}       # frozen weights only
+    fresh = UNetSpatioTemporalConditionModel(**cfg)
+    fresh.load_state_dict({k.replace(".base_layer", ""): v for k, v in base.items()}, strict=True)
+    fresh = fresh.to(cuda)
+    res = lora_io.load_lora_weights(fresh, path)
+    assert not res["unexpected"] and len(res["loaded"]) == 36 + 29
+    x = torch.randn(B, 8, 8, 16, 16, generator=g).to(cuda)
+    p.invalidate()                      # re-derive the packed operands from the trained parameters on both sides
+    a = p(x, 1.3, ctx, dom, flo, added_time_ids=ids).sample
+    b = fresh(x, 1.3, ctx, dom, flo, added_time_ids=ids).sample
+    assert torch.equal(a, b)
