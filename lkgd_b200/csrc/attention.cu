@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
       for (int j = 0; j < T; ++j) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BK);             // N = 128 keys
       const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));

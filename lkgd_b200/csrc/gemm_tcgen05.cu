@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
     // One thread: every instruction here is on a dependent scalar chain, so the k loop carries NO index arithmetic -
     // taps / k-blocks are nested loops, smem and barrier addresses advance incrementally (measured: ~500 cycles per
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll 1
       for (int kb = 0; kb < p.kb1; ++kb, kcol += BK) step(&p.tmA1, kcol, tc.c1, tc.c2, tc.c3, &p.tmB1, kcol, n0);
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0 && elect_one()) {
     // ------------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
     const uint32_t idesc = umma_idesc_bf16(p.BN, CTA2 ? 256 : 128);
     const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
@@ -293,14 +293,14 @@ static void choose_patch(int H, int W, int& TW, int& TH) {
 
 // CTA pairs (cta_group::2) halve the weight-tile traffic per SM but couple the two CTAs' epilogues to one MMA stream.
 // Measured on the C3 shapes (tools/bench_gemm.py, profiles/r01c_gemm_microbench.json): they win when the main loop is
-// long and wide (BN = 256 with K >= 1280: +5..25 %, any tile with K >= 2880: +2..20 %), lose on the short-K,
-// epilogue-bound L0 layers (-5..-12 %).
+// long and wide (BN = 256 with K >= 1280: +10..30 %, any tile with K >= 2560: +10..25 %), lose on the short-K,
+// epilogue-bound layers (-1..-13 %).
 static bool use_cta_pairs(int m_tiles, int n_tiles, int BN, long long k_total) {
   if (getenv("LKGD_GEMM_1CTA")) return false;
   if (BN % 16) return false;
   if (getenv("LKGD_GEMM_2CTA")) return m_tiles >= 2;
   if (m_tiles < 8) return false;
-  return (BN == 256 && k_total >= 1280) || k_total >= 2880;
+  return (BN == 256 && k_total >= 1280) || k_total >= 2560;
 }
 
 static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {

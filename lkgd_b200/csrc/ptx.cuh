@@ -13,6 +13,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One elected lane of a fully active warp.  Branching on elect.sync (rather than on lane == 0) lets ptxas treat the
+// region as single-threaded: operands of UTMALDG / UTCHMMA / UTCBAR go to uniform registers directly instead of through
+// a per-instruction ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop (~80 cycles each on the pipeline threads).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
