@@ -8,6 +8,8 @@
 //    ~112 KB smem and 256 TMEM columns per CTA -> two CTAs per SM overlap softmax with MMA.
 //  * attn_temporal_kernel: attention over the frame axis (F <= 32), one warp per (batch, pixel, head),
 //    reading the fused qkv projection in place (frame stride HW*3C) - HBM-bound, SIMT.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,7 +34,227 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+constexpr int AT_BH = 64;   // keys per softmax step: half of a 128-key K/V stage
+
+// Pipeline (per CTA; two CTAs share an SM):
+//   TMA warp     : Q once; K/V in 128-key stages (double-buffered)
+//   MMA warp     : S_h = Q K_h^T for 64-key half-blocks h into TWO 64-column TMEM buffers (S_{h+2} is issued as soon as
+//                  the softmax warps have copied S_h into registers), O += P_h V_h
+//   softmax warps: ONE tcgen05.ld of the 64 scores of a row into registers -> s_free -> row max -> lazy rescale ->
+//                  p = 2^(s c - m) -> bf16 P tile in smem -> p_full.  The scores are read from TMEM once, and the next
+//                  two QK^T products are already done or in flight while a half-block's exponentials are computed, so the
+//                  softmax warps never wait for the tensor core (the previous kernel waited ~20 % of its time for S).
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_TILE;
+  uint8_t* sV = smem + 3 * AT_TILE;
+  uint8_t* sP = smem + 5 * AT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2]  S buffer b holds Q K_h^T (h & 1 == b)
+  uint64_t* s_free = bars + 7;    // [2]  every softmax warp has copied S buffer b into registers
+  uint64_t* p_full = bars + 9;    // [2]  P_h is in smem buffer b (one barrier per buffer: a consumer never lags two phases)
+  uint64_t* pv_done = bars + 11;  // [2]  P_h V_h has landed in O (and P buffer b may be overwritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, img = blockIdx.z;
+  const int T = (p.Nk + AT_BK - 1) / AT_BK;     // 128-key K/V stages
+  const int H = (p.Nk + AT_BH - 1) / AT_BH;     // 64-key softmax steps
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+        mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&pv_done[i], 1);
+        mbar_init(&p_full[i], 128);
+      }
+      fence_barrier_init();
+      tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;   // S buffers at columns 0 / 64, O at 128..191
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, AT_TILE);
+      tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        while (!mbar_try_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1)) __nanosleep(64);   // off the critical path: back off
+        mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
+        tma_load_4d(sK + st * AT_TILE, &p.tmK, &kv_full[st], 0, head, j * AT_BK, img);
+        tma_load_4d(sV + st * AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BK, img);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_BH);             // N = 64 keys
+      const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      const uint32_t sK0 = smem_u32(sK), sV0 = smem_u32(sV), sP0 = smem_u32(sP);
+      auto issue_qk = [&](int h) {
+        const int st = (h >> 1) & 1;
+        if ((h & 1) == 0) {            // first half of K/V stage h / 2
+          mbar_wait(&kv_full[st], (h >> 2) & 1);
+          tc_fence_after();
+        }
+        const uint64_t kdesc = umma_desc_sw128(sK0 + st * AT_TILE + (h & 1) * (AT_BH * 128));
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tmem_S + (h & 1) * AT_BH, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[h & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (H > 1) issue_qk(1);
+      for (int h = 0; h < H; ++h) {
+        const int b = h & 1, st = (h >> 1) & 1;
+        if (h + 2 < H) {               // S buffer b is in the softmax warps' registers: refill it two steps ahead
+          mbar_wait(&s_free[b], (h >> 1) & 1);
+          tc_fence_after();
+          issue_qk(h + 2);
+        }
+        mbar_wait(&p_full[b], (h >> 1) & 1);      // P_h is in smem
+        tc_fence_after();
+        const uint64_t pdesc = umma_desc_sw128(sP0 + b * AT_TILE);
+#pragma unroll
+        for (int ks = 0; ks < AT_BH / 16; ++ks) {
+          const uint64_t vdesc = umma_desc_sw128(sV0 + st * AT_TILE + (b * 4 + ks) * 2048);
+          umma_bf16(tmem_O, pdesc + 2 * ks, vdesc, idesc_o, (h | ks) != 0);     // O accumulates in TMEM
+        }
+        umma_commit(&pv_done[b]);
+        if (b == 1 || h == H - 1) umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / epilogue
+    // One query row per thread.  O stays in TMEM and accumulates across KV blocks; the running maximum is only
+    // raised when a row's block maximum exceeds it by more than 2^8 ("lazy rescale"): then the warp multiplies its
+    // O rows in TMEM by 2^(m_old - m_new).  p = 2^(s*c - m) <= 256 otherwise, exact enough in bf16 / fp32.
+    const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t prow = smem_u32(sP) + (r >> 3) * 1024 + (r & 7) * 128;
+    const float sc = p.scale_log2;
+    for (int h = 0; h < H; ++h) {
+      const int b = h & 1;
+      mbar_wait(&s_full[b], (h >> 1) & 1);      // S_h = Q K_h^T is in TMEM
+      tc_fence_after();
+      uint32_t s[AT_BH];
+      tmem_ld32(tmem_S + lane_addr + b * AT_BH, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_S + lane_addr + b * AT_BH + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&s_free[b]);   // the tensor core may overwrite this S buffer (with S_{h+2})
+      const int kv_valid = p.Nk - h * AT_BH;
+      if (kv_valid < AT_BH) {                   // last, partial half-block: -inf scores give p = 0
+#pragma unroll
+        for (int i = 0; i < AT_BH; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;
+      }
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < AT_BH; i += 2)
+        m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+      const float m_blk = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+      if (h == 0) {
+        m_run = m_blk;
+      } else {
+        const bool grow = m_blk > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(&pv_done[(h - 1) & 1], ((h - 1) >> 1) & 1);   // P_{h-1} V_{h-1} must have landed before O is rescaled
+          tc_fence_after();
+          const float m_new = grow ? m_blk : m_run;
+          const float alpha = ex2f(m_run - m_new);     // 1 for the rows that keep their maximum
+#pragma unroll
+          for (int c = 0; c < AT_D; c += 32) {
+            uint32_t t[32];
+            tmem_ld32(tmem_O + lane_addr + c, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st32(tmem_O + lane_addr + c, t);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_run = m_new;
+        }
+      }
+      // p = 2^(s*c - m) in f32, packed to bf16 into the swizzled K-major P tile b (free once P_{h-2} V_{h-2} has been
+      // consumed by the tensor core)
+      if (h >= 2) mbar_wait(&pv_done[b], ((h - 2) >> 1) & 1);
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t blk = prow + b * AT_TILE;
+#pragma unroll
+      for (int c = 0; c < AT_BH; c += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float p0 = ex2f(fmaf(__uint_as_float(s[c + i]), sc, -m_run));
+          const float p1 = ex2f(fmaf(__uint_as_float(s[c + i + 1]), sc, -m_run));
+          ls4[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((c >> 3) ^ (r & 7)) << 4)), "r"(pk[0]),
+                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      }
+      l_run += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      tc_fence_before();          // O rescale (if any) is complete before the MMA warp may touch O
+      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full[b]);
+    }
+    mbar_wait(&pv_done[(H - 1) & 1], ((H - 1) >> 1) & 1);
+    tc_fence_after();
+    float o[AT_D];
+#pragma unroll
+    for (int c = 0; c < AT_D; c += 32) {
+      uint32_t t[32];
+      tmem_ld32(tmem_O + lane_addr + c, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(t[i]);
+    }
+    tc_fence_before();
+    if (q0 + r < p.Nq) {
+      const float inv = 1.0f / l_run;
+      if (p.lse != nullptr) p.lse[((size_t)img * p.heads + head) * p.Nq + q0 + r] = m_run + log2f(l_run);
+      __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
+      if (p.d == AT_D) {
+#pragma unroll
+        for (int c = 0; c < AT_D; c += 8)
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
+                         pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+      } else {
+#pragma unroll
+        for (int c = 0; c < AT_D; ++c)
+          if (c < p.d) orow[c] = __float2bfloat16(o[c] * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// Previous pipeline (128-key softmax steps, S read from TMEM twice, single S buffer): kept for A/B timing only
+// (LKGD_ATTN_V1=1).
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_v1_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE;
@@ -467,10 +689,14 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e);
+    e = cudaFuncSetAttribute(attn_flash_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
     attr = true;
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
-  attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  static const bool v1 = getenv("LKGD_ATTN_V1") != nullptr;
+  if (v1) attn_flash_v1_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
 }
 
