@@ -15,10 +15,9 @@
 
 namespace lkgd {
 
-constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
+constexpr int AT_BQ = 128, AT_D = 64;
 constexpr int AT_TILE = AT_BQ * AT_D * 2;  // 16 KB
 constexpr int AT_THREADS = 192;
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + 2 * AT_TILE /*P*/ + 128;
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -34,67 +33,71 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-constexpr int AT_BH = 64;   // keys per softmax step: half of a 128-key K/V stage
+constexpr int AT_BH = 64;                 // keys per softmax step == keys per K/V stage
+constexpr int AT_KV = AT_BH * AT_D * 2;   // 8 KB: one 64-key K (or V) stage
+constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_KV /*K*/ + 2 * AT_KV /*V*/ + 128;
 
-// Pipeline (per CTA; two CTAs share an SM):
-//   TMA warp     : Q once; K/V in 128-key stages (double-buffered)
-//   MMA warp     : S_h = Q K_h^T for 64-key half-blocks h into TWO 64-column TMEM buffers (S_{h+2} is issued as soon as
-//                  the softmax warps have copied S_h into registers), O += P_h V_h
+// Pipeline (per CTA; THREE CTAs share an SM - 48 KB smem, 160 TMEM columns and <= 96 registers each - so that three
+// softmax warps per scheduler hide each other's barrier / TMEM / fence latencies and keep the MUFU pipe, which bounds
+// d = 64 attention, busy):
+//   TMA warp     : Q once; K/V in 64-key stages (double-buffered)
+//   MMA warp     : S_h = Q K_h^T into ONE 64-column TMEM buffer (S_{h+1} is issued as soon as the softmax warps have
+//                  copied S_h into registers), O += P_h V_h with P read from TMEM (no smem round trip for P)
 //   softmax warps: ONE tcgen05.ld of the 64 scores of a row into registers -> s_free -> row max -> lazy rescale ->
-//                  p = 2^(s c - m) -> bf16 P tile in smem -> p_full.  The scores are read from TMEM once, and the next
-//                  two QK^T products are already done or in flight while a half-block's exponentials are computed, so the
-//                  softmax warps never wait for the tensor core (the previous kernel waited ~20 % of its time for S).
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+//                  p = 2^(s c - m) -> packed bf16 pairs -> tcgen05.st into the P columns -> p_full.
+// Shared-memory bandwidth was the co-bottleneck of the earlier versions (P written with st.shared and read back by the
+// tensor core: 32 KB of the 64 KB smem traffic per step).
+__global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE;
-  uint8_t* sV = smem + 3 * AT_TILE;
-  uint8_t* sP = smem + 5 * AT_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
+  uint8_t* sV = sK + 2 * AT_KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * AT_KV);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]  S buffer b holds Q K_h^T (h & 1 == b)
-  uint64_t* s_free = bars + 7;    // [2]  every softmax warp has copied S buffer b into registers
-  uint64_t* p_full = bars + 9;    // [2]  P_h is in smem buffer b (one barrier per buffer: a consumer never lags two phases)
-  uint64_t* pv_done = bars + 11;  // [2]  P_h V_h has landed in O (and P buffer b may be overwritten)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* s_full = bars + 5;    //      S holds Q K_h^T
+  uint64_t* s_free = bars + 6;    //      every softmax warp has copied S into registers
+  uint64_t* p_full = bars + 7;    //      P_h is in TMEM
+  uint64_t* pv_done = bars + 8;   //      P_h V_h has landed in O (and the P columns may be overwritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);     // [2]: 128 columns (S | O) + 32 columns (P)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, img = blockIdx.z;
-  const int T = (p.Nk + AT_BK - 1) / AT_BK;     // 128-key K/V stages
-  const int H = (p.Nk + AT_BH - 1) / AT_BH;     // 64-key softmax steps
+  const int H = (p.Nk + AT_BH - 1) / AT_BH;     // 64-key steps
 
   if (warp == 4) {
     if (lane == 0) {
       mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-        mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&pv_done[i], 1);
-        mbar_init(&p_full[i], 128);
-      }
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(s_free, 4);
+      mbar_init(p_full, 128);
+      mbar_init(pv_done, 1);
       fence_barrier_init();
       tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc_keep_permit(tmem_slot, 128);
+    tmem_alloc(tmem_slot + 1, 32);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;   // S buffers at columns 0 / 64, O at 128..191
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_BH;   // S at columns 0..63, O at 64..127
+  const uint32_t tmem_P = tmem_slot[1];                            // 128 x 64 bf16 = 32 columns
 
   if (warp == 4) {
     if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
-      for (int j = 0; j < T; ++j) {
+      for (int j = 0; j < H; ++j) {
         const int st = j & 1;
         while (!mbar_try_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1)) __nanosleep(64);   // off the critical path: back off
-        mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
-        tma_load_4d(sK + st * AT_TILE, &p.tmK, &kv_full[st], 0, head, j * AT_BK, img);
-        tma_load_4d(sV + st * AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BK, img);
+        mbar_expect_tx(&kv_full[st], 2 * AT_KV);
+        tma_load_4d(sK + st * AT_KV, &p.tmK, &kv_full[st], 0, head, j * AT_BH, img);
+        tma_load_4d(sV + st * AT_KV, &p.tmV, &kv_full[st], 0, head, j * AT_BH, img);
       }
     }
   } else if (warp == 5) {
@@ -102,39 +105,34 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
       const uint32_t idesc_s = umma_idesc_bf16(AT_BH);             // N = 64 keys
       const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      const uint32_t sK0 = smem_u32(sK), sV0 = smem_u32(sV), sP0 = smem_u32(sP);
+      const uint32_t sK0 = smem_u32(sK), sV0 = smem_u32(sV);
       auto issue_qk = [&](int h) {
-        const int st = (h >> 1) & 1;
-        if ((h & 1) == 0) {            // first half of K/V stage h / 2
-          mbar_wait(&kv_full[st], (h >> 2) & 1);
-          tc_fence_after();
-        }
-        const uint64_t kdesc = umma_desc_sw128(sK0 + st * AT_TILE + (h & 1) * (AT_BH * 128));
+        const int st = h & 1;
+        mbar_wait(&kv_full[st], (h >> 1) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(sK0 + st * AT_KV);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tmem_S + (h & 1) * AT_BH, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[h & 1]);
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
-      if (H > 1) issue_qk(1);
       for (int h = 0; h < H; ++h) {
-        const int b = h & 1, st = (h >> 1) & 1;
-        if (h + 2 < H) {               // S buffer b is in the softmax warps' registers: refill it two steps ahead
-          mbar_wait(&s_free[b], (h >> 1) & 1);
+        const int st = h & 1;
+        if (h + 1 < H) {               // S is in the softmax warps' registers: start the next Q K^T now
+          mbar_wait(s_free, h & 1);
           tc_fence_after();
-          issue_qk(h + 2);
+          issue_qk(h + 1);
         }
-        mbar_wait(&p_full[b], (h >> 1) & 1);      // P_h is in smem
+        mbar_wait(p_full, h & 1);      // P_h is in smem
         tc_fence_after();
-        const uint64_t pdesc = umma_desc_sw128(sP0 + b * AT_TILE);
 #pragma unroll
         for (int ks = 0; ks < AT_BH / 16; ++ks) {
-          const uint64_t vdesc = umma_desc_sw128(sV0 + st * AT_TILE + (b * 4 + ks) * 2048);
-          umma_bf16(tmem_O, pdesc + 2 * ks, vdesc, idesc_o, (h | ks) != 0);     // O accumulates in TMEM
+          const uint64_t vdesc = umma_desc_sw128(sV0 + st * AT_KV + ks * 2048);
+          umma_bf16_ts(tmem_O, tmem_P + ks * 8, vdesc, idesc_o, (h | ks) != 0);     // O accumulates in TMEM
         }
-        umma_commit(&pv_done[b]);
-        if (b == 1 || h == H - 1) umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[st]);
       }
     }
   } else {
@@ -145,20 +143,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
     const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t prow = smem_u32(sP) + (r >> 3) * 1024 + (r & 7) * 128;
     const float sc = p.scale_log2;
     for (int h = 0; h < H; ++h) {
-      const int b = h & 1;
-      mbar_wait(&s_full[b], (h >> 1) & 1);      // S_h = Q K_h^T is in TMEM
+      mbar_wait(s_full, h & 1);                 // S_h = Q K_h^T is in TMEM
       tc_fence_after();
       uint32_t s[AT_BH];
-      tmem_ld32(tmem_S + lane_addr + b * AT_BH, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld32(tmem_S + lane_addr + b * AT_BH + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld32(tmem_S + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_S + lane_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_wait();
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&s_free[b]);   // the tensor core may overwrite this S buffer (with S_{h+2})
+      if (lane == 0) mbar_arrive(s_free);       // the tensor core may overwrite S (with S_{h+1})
       const int kv_valid = p.Nk - h * AT_BH;
-      if (kv_valid < AT_BH) {                   // last, partial half-block: -inf scores give p = 0
+      if (kv_valid < AT_BH) {                   // last, partial step: -inf scores give p = 0
 #pragma unroll
         for (int i = 0; i < AT_BH; ++i)
           if (i >= kv_valid) s[i] = 0xff800000u;
@@ -171,318 +167,78 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_kernel(const __grid_
       if (h == 0) {
         m_run = m_blk;
       } else {
+        mbar_wait(pv_done, (h - 1) & 1);        // P_{h-1} V_{h-1} has landed: O may be rescaled, P may be overwritten
         const bool grow = m_blk > m_run + 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&pv_done[(h - 1) & 1], ((h - 1) >> 1) & 1);   // P_{h-1} V_{h-1} must have landed before O is rescaled
           tc_fence_after();
           const float m_new = grow ? m_blk : m_run;
           const float alpha = ex2f(m_run - m_new);     // 1 for the rows that keep their maximum
 #pragma unroll
-          for (int c = 0; c < AT_D; c += 32) {
-            uint32_t t[32];
-            tmem_ld32(tmem_O + lane_addr + c, t);
+          for (int c = 0; c < AT_D; c += 16) {
+            uint32_t t[16];
+            tmem_ld16(tmem_O + lane_addr + c, t);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            tmem_st32(tmem_O + lane_addr + c, t);
+            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c, t);
           }
           tmem_st_wait();
           l_run *= alpha;
           m_run = m_new;
         }
       }
-      // p = 2^(s*c - m) in f32, packed to bf16 into the swizzled K-major P tile b (free once P_{h-2} V_{h-2} has been
-      // consumed by the tensor core)
-      if (h >= 2) mbar_wait(&pv_done[b], ((h - 2) >> 1) & 1);
+      // p = 2^(s*c - m) in f32, packed to bf16 pairs in place (word j = keys 2j, 2j+1) and stored to the P columns
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t blk = prow + b * AT_TILE;
 #pragma unroll
-      for (int c = 0; c < AT_BH; c += 8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const float p0 = ex2f(fmaf(__uint_as_float(s[c + i]), sc, -m_run));
-          const float p1 = ex2f(fmaf(__uint_as_float(s[c + i + 1]), sc, -m_run));
-          ls4[(i >> 1) & 3] += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((c >> 3) ^ (r & 7)) << 4)), "r"(pk[0]),
-                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      for (int i = 0; i < AT_BH; i += 2) {
+        const float p0 = ex2f(fmaf(__uint_as_float(s[i]), sc, -m_run));
+        const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), sc, -m_run));
+        ls4[(i >> 1) & 3] += p0 + p1;
+        s[i >> 1] = pack_bf16x2(p0, p1);
       }
+      tmem_st32(tmem_P + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       l_run += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      tc_fence_before();          // O rescale (if any) is complete before the MMA warp may touch O
-      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(&p_full[b]);
-    }
-    mbar_wait(&pv_done[(H - 1) & 1], ((H - 1) >> 1) & 1);
-    tc_fence_after();
-    float o[AT_D];
-#pragma unroll
-    for (int c = 0; c < AT_D; c += 32) {
-      uint32_t t[32];
-      tmem_ld32(tmem_O + lane_addr + c, t);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(t[i]);
-    }
-    tc_fence_before();
-    if (q0 + r < p.Nq) {
-      const float inv = 1.0f / l_run;
-      if (p.lse != nullptr) p.lse[((size_t)img * p.heads + head) * p.Nq + q0 + r] = m_run + log2f(l_run);
-      __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
-      if (p.d == AT_D) {
-#pragma unroll
-        for (int c = 0; c < AT_D; c += 8)
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
-                         pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
-      } else {
-#pragma unroll
-        for (int c = 0; c < AT_D; ++c)
-          if (c < p.d) orow[c] = __float2bfloat16(o[c] * inv);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    __syncwarp();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// Previous pipeline (128-key softmax steps, S read from TMEM twice, single S buffer): kept for A/B timing only
-// (LKGD_ATTN_V1=1).
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_flash_v1_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + AT_TILE;
-  uint8_t* sV = smem + 3 * AT_TILE;
-  uint8_t* sP = smem + 5 * AT_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, img = blockIdx.z;
-  const int T = (p.Nk + AT_BK - 1) / AT_BK;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-      mbar_init(s_full, 1);
-      mbar_init(p_full, 128);
-      mbar_init(o_full, 1);
-      fence_barrier_init();
-      tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 256);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-
-  if (warp == 4) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, AT_TILE);
-      tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        while (!mbar_try_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1)) __nanosleep(64);   // off the critical path: back off
-        mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
-        tma_load_4d(sK + st * AT_TILE, &p.tmK, &kv_full[st], 0, head, j * AT_BK, img);
-        tma_load_4d(sV + st * AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BK, img);
-      }
-    }
-  } else if (warp == 5) {
-    if (elect_one()) {
-      const uint32_t idesc_s = umma_idesc_bf16(AT_BK);             // N = 128 keys
-      const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);     // P_j is in smem, S columns are free again
-        tc_fence_after();
-        // S_{j+1} = Q K_{j+1}^T first: the softmax warps wait for it, nobody waits for P_j V_j
-        if (j + 1 < T) {
-          const int sn = (j + 1) & 1;
-          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + sn * AT_TILE));
-#pragma unroll
-          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-        }
-#pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks) {
-          const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (ks >> 2) * AT_TILE)) + 2 * (ks & 3);
-          const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + st * AT_TILE + ks * 2048));
-          umma_bf16(tmem_O, pdesc, vdesc, idesc_o, (j | ks) != 0);     // O accumulates in TMEM across KV blocks
-        }
-        umma_commit(&kv_empty[st]);
-        umma_commit(o_full);          // phase j: P_j V_j has landed in O (and the P tile may be overwritten)
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax / epilogue
-    // One query row per thread.  O stays in TMEM and accumulates across KV blocks; the running maximum is only
-    // raised when a row's block maximum exceeds it by more than 2^8 ("lazy rescale"): then the warp multiplies its
-    // O rows in TMEM by 2^(m_old - m_new).  p = 2^(s*c - m) <= 256 otherwise, exact enough in bf16 / fp32.
-    const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(s_full, j & 1);      // S_j = Q K_j^T is in TMEM
-      tc_fence_after();
-      const int kv_valid = min(AT_BK, p.Nk - j * AT_BK);
-      // pass 1: row maximum (64 columns per TMEM wait, four independent chains)
-      float mx;
-      {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < AT_BK; c += 64) {
-          uint32_t s0[32], s1[32];
-          tmem_ld32(tmem_S + lane_addr + c, s0);
-          tmem_ld32(tmem_S + lane_addr + c + 32, s1);
-          tmem_ld_wait();
-          if (c + 64 <= kv_valid) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              m4[(i >> 1) & 1] = fmaxf(m4[(i >> 1) & 1], fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
-              m4[2 + ((i >> 1) & 1)] = fmaxf(m4[2 + ((i >> 1) & 1)], fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (c + i < kv_valid) m4[i & 1] = fmaxf(m4[i & 1], __uint_as_float(s0[i]));
-              if (c + 32 + i < kv_valid) m4[2 + (i & 1)] = fmaxf(m4[2 + (i & 1)], __uint_as_float(s1[i]));
-            }
-          }
-        }
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      }
-      const float m_blk = mx * p.scale_log2;
-      if (j == 0) {
-        m_run = m_blk;
-      } else {
-        const bool grow = m_blk > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(o_full, (j - 1) & 1);              // P_{j-1} V_{j-1} must have landed before O is rescaled
-          tc_fence_after();
-          const float m_new = grow ? m_blk : m_run;
-          const float alpha = ex2f(m_run - m_new);     // 1 for the rows that keep their maximum
-#pragma unroll
-          for (int c = 0; c < AT_D; c += 32) {
-            uint32_t t[32];
-            tmem_ld32(tmem_O + lane_addr + c, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            tmem_st32(tmem_O + lane_addr + c, t);
-          }
-          tmem_st_wait();
-          l_run *= alpha;
-          m_run = m_new;
-        }
-      }
-      float lsum = 0.f;
-      // pass 2: p = 2^(s*c - m) in f32, packed to bf16 into the swizzled K-major P tile (free once P_{j-1} V_{j-1}
-      // has been consumed by the tensor core)
-      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (j > 0) mbar_wait(o_full, (j - 1) & 1);
-      const bool full_blk = kv_valid == AT_BK;     // every block but possibly the last: no per-element masking
-#pragma unroll
-      for (int c = 0; c < AT_BK; c += 32) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c, s);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (full_blk) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run));
-            const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run));
-            ls4[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run)) : 0.f;
-            const float p1 = (c + i + 1 < kv_valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run)) : 0.f;
-            ls4[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-        }
-        uint8_t* blk = prow + (c >> 6) * AT_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 63) >> 3) + q;   // 16-byte chunk index within the 128-byte row
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      l_run += lsum;
-      tc_fence_before();          // S reads (and O rescale) are complete before the MMA warp may touch S / O
-      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
+      tmem_st_wait();
+      tc_fence_before();          // P (and an O rescale, if any) is in TMEM before the MMA warp is signalled
       mbar_arrive(p_full);
     }
-    mbar_wait(o_full, (T - 1) & 1);
+    mbar_wait(pv_done, (H - 1) & 1);
     tc_fence_after();
-    float o[AT_D];
+    if (q0 + r < p.Nq) {
+      if (p.lse != nullptr) p.lse[((size_t)img * p.heads + head) * p.Nq + q0 + r] = m_run + log2f(l_run);
+    }
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
 #pragma unroll
     for (int c = 0; c < AT_D; c += 32) {
       uint32_t t[32];
       tmem_ld32(tmem_O + lane_addr + c, t);
       tmem_ld_wait();
+      if (q0 + r < p.Nq) {
+        if (p.d == AT_D) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(t[i]);
-    }
-    tc_fence_before();
-    if (q0 + r < p.Nq) {
-      const float inv = 1.0f / l_run;
-      if (p.lse != nullptr) p.lse[((size_t)img * p.heads + head) * p.Nq + q0 + r] = m_run + log2f(l_run);
-      __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
-      if (p.d == AT_D) {
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(orow + c + i) =
+                make_uint4(pack_bf16x2(__uint_as_float(t[i]) * inv, __uint_as_float(t[i + 1]) * inv),
+                           pack_bf16x2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv),
+                           pack_bf16x2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv),
+                           pack_bf16x2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv));
+        } else {
 #pragma unroll
-        for (int c = 0; c < AT_D; c += 8)
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
-                         pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
-      } else {
-#pragma unroll
-        for (int c = 0; c < AT_D; ++c)
-          if (c < p.d) orow[c] = __float2bfloat16(o[c] * inv);
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.d) orow[c + i] = __float2bfloat16(__uint_as_float(t[i]) * inv);
+        }
       }
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_P, 32);
   }
 }
 
@@ -659,10 +415,10 @@ __global__ void __launch_bounds__(128) attn_temporal_kernel(const __nv_bfloat16*
   }
 }
 
-static int attn_tmap(CUtensorMap* tm, const void* base, int ld, int heads, int d, int N, int n_img) {
+static int attn_tmap(CUtensorMap* tm, const void* base, int ld, int heads, int d, int N, int n_img, int rows) {
   uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)n_img};
   uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * N};
-  uint32_t box[4] = {AT_D, 1, AT_BQ, 1};
+  uint32_t box[4] = {AT_D, 1, (uint32_t)rows, 1};
   return make_tmap(tm, base, 4, dims, strides, box);
 }
 
@@ -678,9 +434,9 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   if (heads > 65535 || n_img > 65535) return LKGD_ESHAPE;
   AttnParams p;
   int rc;
-  if ((rc = attn_tmap(&p.tmQ, q, ldq, heads, d, Nq, n_img))) return rc;
-  if ((rc = attn_tmap(&p.tmK, k, ldk, heads, d, Nk, n_img))) return rc;
-  if ((rc = attn_tmap(&p.tmV, v, ldv, heads, d, Nk, n_img))) return rc;
+  if ((rc = attn_tmap(&p.tmQ, q, ldq, heads, d, Nq, n_img, AT_BQ))) return rc;
+  if ((rc = attn_tmap(&p.tmK, k, ldk, heads, d, Nk, n_img, AT_BH))) return rc;
+  if ((rc = attn_tmap(&p.tmV, v, ldv, heads, d, Nk, n_img, AT_BH))) return rc;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -689,14 +445,10 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e);
-    e = cudaFuncSetAttribute(attn_flash_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return set_cuda_error(e);
     attr = true;
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
-  static const bool v1 = getenv("LKGD_ATTN_V1") != nullptr;
-  if (v1) attn_flash_v1_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  else attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
 }
 
