@@ -35,12 +35,13 @@ __device__ __forceinline__ float ex2f(float x) {
 
 constexpr int AT_BH = 64;                 // keys per softmax step == keys per K/V stage
 constexpr int AT_KV = AT_BH * AT_D * 2;   // 8 KB: one 64-key K (or V) stage
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_KV /*K*/ + 2 * AT_KV /*V*/ + 128;
+constexpr int AT_NS = 3;                  // K/V stages: two steps of look-ahead cover the TMA latency
+constexpr int AT_SMEM = AT_TILE /*Q*/ + AT_NS * AT_KV /*K*/ + AT_NS * AT_KV /*V*/ + 128;
 
-// Pipeline (per CTA; THREE CTAs share an SM - 48 KB smem, 160 TMEM columns and <= 96 registers each - so that three
+// Pipeline (per CTA; THREE CTAs share an SM - 64 KB smem, 160 TMEM columns and <= 96 registers each - so that three
 // softmax warps per scheduler hide each other's barrier / TMEM / fence latencies and keep the MUFU pipe, which bounds
 // d = 64 attention, busy):
-//   TMA warp     : Q once; K/V in 64-key stages (double-buffered)
+//   TMA warp     : Q once; K/V in 64-key stages (ring of three)
 //   MMA warp     : S_h = Q K_h^T into ONE 64-column TMEM buffer (S_{h+1} is issued as soon as the softmax warps have
 //                  copied S_h into registers), O += P_h V_h with P read from TMEM (no smem round trip for P)
 //   softmax warps: ONE tcgen05.ld of the 64 scores of a row into registers -> s_free -> row max -> lazy rescale ->
@@ -51,16 +52,16 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE;
-  uint8_t* sV = sK + 2 * AT_KV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * AT_KV);
+  uint8_t* sV = sK + AT_NS * AT_KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_NS * AT_KV);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    //      S holds Q K_h^T
-  uint64_t* s_free = bars + 6;    //      every softmax warp has copied S into registers
-  uint64_t* p_full = bars + 7;    //      P_h is in TMEM
-  uint64_t* pv_done = bars + 8;   //      P_h V_h has landed in O (and the P columns may be overwritten)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);     // [2]: 128 columns (S | O) + 32 columns (P)
+  uint64_t* kv_full = bars + 1;            // [AT_NS]
+  uint64_t* kv_empty = bars + 1 + AT_NS;   // [AT_NS]
+  uint64_t* s_full = bars + 1 + 2 * AT_NS; //      S holds Q K_h^T
+  uint64_t* s_free = s_full + 1;           //      every softmax warp has copied S into registers
+  uint64_t* p_full = s_full + 2;           //      P_h is in TMEM
+  uint64_t* pv_done = s_full + 3;          //      P_h V_h has landed in O (and the P columns may be overwritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);     // [2]: 128 columns (S | O) + 32 columns (P)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, img = blockIdx.z;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
   if (warp == 4) {
     if (lane == 0) {
       mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      for (int i = 0; i < AT_NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
       mbar_init(s_full, 1);
       mbar_init(s_free, 4);
       mbar_init(p_full, 128);
@@ -92,12 +93,13 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
     if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
+      int st = 0, ph = 1;
       for (int j = 0; j < H; ++j) {
-        const int st = j & 1;
-        while (!mbar_try_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1)) __nanosleep(64);   // off the critical path: back off
+        while (!mbar_try_wait(&kv_empty[st], ph)) __nanosleep(64);   // off the critical path: back off
         mbar_expect_tx(&kv_full[st], 2 * AT_KV);
         tma_load_4d(sK + st * AT_KV, &p.tmK, &kv_full[st], 0, head, j * AT_BH, img);
         tma_load_4d(sV + st * AT_KV, &p.tmV, &kv_full[st], 0, head, j * AT_BH, img);
+        if (++st == AT_NS) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -106,23 +108,24 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
       const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
       const uint32_t sK0 = smem_u32(sK), sV0 = smem_u32(sV);
-      auto issue_qk = [&](int h) {
-        const int st = h & 1;
-        mbar_wait(&kv_full[st], (h >> 1) & 1);
+      int qst = 0, qph = 0;            // K/V stage (and its phase) of the next Q K^T
+      auto issue_qk = [&]() {
+        mbar_wait(&kv_full[qst], qph);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(sK0 + st * AT_KV);
+        const uint64_t kdesc = umma_desc_sw128(sK0 + qst * AT_KV);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
+        if (++qst == AT_NS) { qst = 0; qph ^= 1; }
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
+      issue_qk();
+      int st = 0;                      // K/V stage of P_h V_h
       for (int h = 0; h < H; ++h) {
-        const int st = h & 1;
         if (h + 1 < H) {               // S is in the softmax warps' registers: start the next Q K^T now
           mbar_wait(s_free, h & 1);
           tc_fence_after();
-          issue_qk(h + 1);
+          issue_qk();
         }
         mbar_wait(p_full, h & 1);      // P_h is in smem
         tc_fence_after();
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
+        if (++st == AT_NS) st = 0;
       }
     }
   } else {
@@ -164,15 +168,33 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
       for (int i = 0; i < AT_BH; i += 2)
         m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
       const float m_blk = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+      // lazy rescale: decided now, applied to O (below) only after P_{h-1} V_{h-1} has landed
+      float alpha = 1.0f;
+      bool rescale = false;
       if (h == 0) {
         m_run = m_blk;
       } else {
-        mbar_wait(pv_done, (h - 1) & 1);        // P_{h-1} V_{h-1} has landed: O may be rescaled, P may be overwritten
         const bool grow = m_blk > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
+        rescale = __any_sync(0xffffffffu, grow);
+        if (grow) {
+          alpha = ex2f(m_run - m_blk);
+          l_run *= alpha;
+          m_run = m_blk;
+        }
+      }
+      // p = 2^(s*c - m) in f32, packed to bf16 pairs in place (word j = keys 2j, 2j+1)
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < AT_BH; i += 2) {
+        const float p0 = ex2f(fmaf(__uint_as_float(s[i]), sc, -m_run));
+        const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), sc, -m_run));
+        ls4[(i >> 1) & 3] += p0 + p1;
+        s[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      if (h > 0) {
+        mbar_wait(pv_done, (h - 1) & 1);        // P_{h-1} V_{h-1} has landed: O may be rescaled, P may be overwritten
+        if (rescale) {
           tc_fence_after();
-          const float m_new = grow ? m_blk : m_run;
-          const float alpha = ex2f(m_run - m_new);     // 1 for the rows that keep their maximum
 #pragma unroll
           for (int c = 0; c < AT_D; c += 16) {
             uint32_t t[16];
@@ -182,19 +204,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
             for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
             tmem_st16(tmem_O + lane_addr + c, t);
           }
-          tmem_st_wait();
-          l_run *= alpha;
-          m_run = m_new;
         }
-      }
-      // p = 2^(s*c - m) in f32, packed to bf16 pairs in place (word j = keys 2j, 2j+1) and stored to the P columns
-      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < AT_BH; i += 2) {
-        const float p0 = ex2f(fmaf(__uint_as_float(s[i]), sc, -m_run));
-        const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), sc, -m_run));
-        ls4[(i >> 1) & 3] += p0 + p1;
-        s[i >> 1] = pack_bf16x2(p0, p1);
       }
       tmem_st32(tmem_P + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       l_run += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
