@@ -38,12 +38,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf-GELU in 10 instructions and ONE MUFU op.  gelu(x) = relu(x) - |x| h(|x|) with h(t) = 0.5 erfc(t / sqrt 2) =
-// Phi(-t), and h(t) = 2^P(t): log2 h is smooth (nearly quadratic), a degree-6 polynomial on [0, 6] (Chebyshev fit,
-// tools/fit_gelu.py) reproduces it to 7e-5, i.e. h to 4.8e-5 relative and gelu to 6.9e-6 absolute - 40x below the bf16
-// rounding of the product it feeds (the reference computes F.gelu(gate) with the exact erf form).  t is clamped at 6
-// (|x| h < 1e-8 beyond).  The previous Abramowitz-Stegun form needed rcp + ex2 (two MUFU ops) and 13 instructions; the
-// GEGLU epilogue is issue / MUFU bound (profiles/r01b_ncu_summary.md).
+// erf-GELU with ONE MUFU op.  gelu(x) = relu(x) - |x| h(|x|) with h(t) = 0.5 erfc(t / sqrt 2) = Phi(-t), and
+// h(t) = 2^P(t): log2 h is smooth (nearly quadratic), a degree-6 polynomial on [0, 6] (Chebyshev fit, tools/fit_gelu.py)
+// reproduces it to 7e-5, i.e. h to 4.8e-5 relative and gelu to 6.9e-6 absolute - 40x below the bf16 rounding of the
+// product it feeds (the reference computes F.gelu(gate) with the exact erf form).  t is clamped at 6 (|x| h < 1e-8
+// beyond).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float ax = fabsf(x);
   const float t = fminf(ax, 6.0f);
@@ -56,12 +55,89 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-ax, ex2_approx(p), fmaxf(x, 0.f));
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes' worth of work)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// GEGLU on NP column pairs in lock step (the Horner chains of the pairs interleave, so no FFMA waits for the previous
+// one): v[i] = (a[i] + bv[i]) * gelu(g[i] + bg[i]).  a / g are accumulator bits, bv / bg point to the tile's bias in smem.
+template <int NP>
+__device__ __forceinline__ void geglu_pairs(const uint32_t* a, const uint32_t* g, const float* bv, const float* bg,
+                                            float* v) {
+  const uint64_t C6 = pk2(2.2999249e-05f, 2.2999249e-05f), C5 = pk2(-6.1149016e-04f, -6.1149016e-04f),
+                 C4 = pk2(7.2001889e-03f, 7.2001889e-03f), C3 = pk2(-5.1208213e-02f, -5.1208213e-02f),
+                 C2 = pk2(-4.6122226e-01f, -4.6122226e-01f), C1 = pk2(-1.1502144e+00f, -1.1502144e+00f),
+                 C0 = pk2(-1.0000589e+00f, -1.0000589e+00f);
+  uint64_t V[NP], T[NP], NA[NP], R[NP], P[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i += 2) {      // two pairs per 16-byte bias load
+    const float4 b4 = *reinterpret_cast<const float4*>(bv + 2 * i);
+    const float4 g4 = *reinterpret_cast<const float4*>(bg + 2 * i);
+    V[i] = add2(pk2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), pk2(b4.x, b4.y));
+    V[i + 1] = add2(pk2(__uint_as_float(a[2 * i + 2]), __uint_as_float(a[2 * i + 3])), pk2(b4.z, b4.w));
+    const uint64_t G0 = add2(pk2(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1])), pk2(g4.x, g4.y));
+    const uint64_t G1 = add2(pk2(__uint_as_float(g[2 * i + 2]), __uint_as_float(g[2 * i + 3])), pk2(g4.z, g4.w));
+    float x0, x1, x2, x3;
+    upk2(G0, x0, x1); upk2(G1, x2, x3);
+    T[i] = pk2(fminf(fabsf(x0), 6.0f), fminf(fabsf(x1), 6.0f));
+    T[i + 1] = pk2(fminf(fabsf(x2), 6.0f), fminf(fabsf(x3), 6.0f));
+    NA[i] = pk2(fminf(x0, -x0), fminf(x1, -x1));            // -|x|
+    NA[i + 1] = pk2(fminf(x2, -x2), fminf(x3, -x3));
+    R[i] = pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));             // relu(x)
+    R[i + 1] = pk2(fmaxf(x2, 0.f), fmaxf(x3, 0.f));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(C6, T[i], C5);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(P[i], T[i], C4);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(P[i], T[i], C3);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(P[i], T[i], C2);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(P[i], T[i], C1);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) P[i] = fma2(P[i], T[i], C0);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float p0, p1;
+    upk2(P[i], p0, p1);
+    P[i] = pk2(ex2_approx(p0), ex2_approx(p1));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const uint64_t Y = mul2(V[i], fma2(NA[i], P[i], R[i]));
+    upk2(Y, v[2 * i], v[2 * i + 1]);
+  }
+}
+
 // Epilogue of one 128 x BN tile for one warp (32 TMEM lanes = 32 tile rows, alternate column chunks).
 //   CW   accumulator columns per chunk: 32 when every operand is bf16, else 16 (a chunk is 64 B of the widest row)
 //   OES  output element size (2 / 4);  RES residual element size (0 = none, 2, 4);  NRES number of residuals
 // Row-per-lane accesses touch this lane's own staging row; "coalesced" accesses walk 16-byte pieces so that
 // consecutive lanes cover consecutive bytes of a global row (P pieces per row, 32 / P rows per instruction).
-template <int CW, int OES, int RES, int NRES, bool GEGLU>
+template <int EG, int CW, int OES, int RES, int NRES, bool GEGLU>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& tc, int n_tile, uint32_t taddr,
                                               int lane_base, int lane, int half, uint32_t stg,
                                               const float* __restrict__ sbias) {
@@ -120,16 +196,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
     cp_async_commit();
   };
 
-  int k = 0;
-  for (int c = half; c < nchunks; c += 2, ++k) {
-    const uint32_t buf = stg + ((NRES == 2) ? 0 : (k & 1) * 2048);
-    if (NRES == 2) {
-      issue(c, buf);                                       // both residuals: single-buffered
-    } else if (NRES == 1) {
-      if (k == 0) issue(c, buf);
-      if (c + 2 < nchunks) issue(c + 2, stg + ((k + 1) & 1) * 2048);   // this warp's next chunk, other buffer
-      //                                (not `buf ^ 2048`: the staging base is only 1024-byte aligned)
+  // Residual ring: a slot is NRES buffers of 2 KB; `dist` chunks of this warp are in flight ahead of the one being
+  // consumed.  Exactly one cp.async group is committed per chunk (empty past the end), so wait_group<dist> means
+  // "this chunk's residual has landed".
+  const int slots = p.epi_bufs / (NRES == 2 ? 2 : 1);      // 1 / 2 (two residuals), 2 / 4 (one)
+  const int dist = slots - 1;
+  constexpr uint32_t SLOT = (NRES == 2 ? 2 : 1) * 2048;
+  if (NRES >= 1) {
+    for (int d = 0; d < dist; ++d) {
+      if (half + d * EG < nchunks) issue(half + d * EG, stg + d * SLOT); else cp_async_commit();
     }
+  }
+  int k = 0, slot = 0, pslot = dist;       // slot of chunk k, slot of chunk k + dist
+  for (int c = half; c < nchunks; c += EG, ++k) {
+    const uint32_t buf = stg + slot * SLOT;
+    if (NRES >= 1) {
+      if (dist == 0) issue(c, buf);                        // single slot: fetch, then wait
+      else if (c + dist * EG < nchunks) issue(c + dist * EG, stg + pslot * SLOT);
+      else cp_async_commit();
+    }
+    if (++slot == slots) slot = 0;
+    if (++pslot >= slots) pslot = 0;
     uint32_t a[CW], g[GEGLU ? CW : 1];
     if (CW == 16) {
       tmem_ld16(taddr + c * CW, *reinterpret_cast<uint32_t(*)[16]>(a));
@@ -143,19 +230,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
     float v[CW];
     tmem_ld_wait();
     // bias of the tile sits in smem (value half, then - GEGLU - the gate half at +bn_out): broadcast LDS.128
+    if (GEGLU) {
 #pragma unroll
-    for (int j = 0; j < CW; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * CW + j);
-      v[j] = __uint_as_float(a[j]) + b4.x;
-      v[j + 1] = __uint_as_float(a[j + 1]) + b4.y;
-      v[j + 2] = __uint_as_float(a[j + 2]) + b4.z;
-      v[j + 3] = __uint_as_float(a[j + 3]) + b4.w;
-      if (GEGLU) {
-        const float4 g4 = *reinterpret_cast<const float4*>(sbias + bn_out + c * CW + j);
-        v[j] *= gelu_erf_fast(__uint_as_float(g[j % (GEGLU ? CW : 1)]) + g4.x);
-        v[j + 1] *= gelu_erf_fast(__uint_as_float(g[(j + 1) % (GEGLU ? CW : 1)]) + g4.y);
-        v[j + 2] *= gelu_erf_fast(__uint_as_float(g[(j + 2) % (GEGLU ? CW : 1)]) + g4.z);
-        v[j + 3] *= gelu_erf_fast(__uint_as_float(g[(j + 3) % (GEGLU ? CW : 1)]) + g4.w);
+      for (int j = 0; j < CW; j += 8)
+        geglu_pairs<4>(a + j, g + (GEGLU ? j : 0), sbias + c * CW + j, sbias + bn_out + c * CW + j, v + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * CW + j);
+        v[j] = __uint_as_float(a[j]) + b4.x;
+        v[j + 1] = __uint_as_float(a[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(a[j + 2]) + b4.z;
+        v[j + 3] = __uint_as_float(a[j + 3]) + b4.w;
       }
     }
     if (use_rv) {                                  // per-row vector (time embedding / context term), L1/L2 resident
@@ -179,7 +265,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       for (int j = 0; j < CW; ++j) v[j] *= p.s0;
     }
     if (NRES >= 1) {
-      if (NRES == 1 && c + 2 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+      if (dist == 3) cp_async_wait<3>(); else if (dist == 1) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncwarp();
       const uint32_t own = buf + lane * RB;
       const int sw = (lane / (8 / PR)) & (PR - 1);
@@ -246,11 +332,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
 }
 
 // runtime -> compile-time epilogue variant
+template <int EG>
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, const TileCoord& tc, int n_tile, uint32_t taddr,
                                                   int lane_base, int lane, int half, uint32_t stg,
                                                   const float* sbias) {
 #define LKGD_EPI(CW, OES, RES, NRES, GG) \
-  epilogue_tile<CW, OES, RES, NRES, GG>(p, tc, n_tile, taddr, lane_base, lane, half, stg, sbias)
+  epilogue_tile<EG, CW, OES, RES, NRES, GG>(p, tc, n_tile, taddr, lane_base, lane, half, stg, sbias)
   const int nres = p.res1 == nullptr ? 0 : (p.res2 == nullptr ? 1 : 2);
   if (p.act == LKGD_ACT_GEGLU) {
     if (p.out_f32) LKGD_EPI(16, 4, 0, 0, true); else LKGD_EPI(32, 2, 0, 0, true);

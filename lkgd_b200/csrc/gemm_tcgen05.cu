@@ -20,9 +20,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_WARP_BYTES = 4096;              // two 2 KB chunk buffers (32 rows x 64 B)
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_BUF_BYTES = 2048;               // one chunk buffer: 32 rows x 64 B
+// EG = epilogue warps per TMEM lane quarter.  EG = 4 (16 warps, 96 registers) was measured on the C3 shapes and lost
+// 5-25 % everywhere (spills, twice the per-tile set-up): only EG = 2 is instantiated.
+constexpr int gemm_threads(int EG) { return 64 + EG * 4 * 32; }
 constexpr int BIAS_BYTES = 2 * 256 * 4;           // bias of the current / next tile (double-buffered)
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
@@ -35,6 +36,7 @@ struct GemmParams {
   CUtensorMap tmB1;
   int mode, M, N, BN;
   int stages, stage_bytes;
+  int epi_bufs;                      // 2 KB residual / output staging buffers per epilogue warp: 2 or 4
   int kb0, ntaps, kb1, k0;           // k-blocks per tap, taps, k-blocks of segment 1, channels per tap
   int H, W, TW, TH, tw_shift, tiles_w, tiles_h;  // conv output geometry + tile patch (TW a power of two)
   int HW, F, tiles_p;                  // tconv
@@ -110,13 +112,14 @@ namespace lkgd {
 //               B tile (rows r*BN/2..); the leader (rank 0) issues 256 x BN x 16 UMMAs that read both halves, so every SM
 //               pulls 16 KB + BN*64 B per k-block instead of 16 KB + BN*128 B (the main loop is L2->smem bound).
 //               Accumulator rows stay in each CTA's own TMEM; both CTAs run their own epilogue.
-template <bool CTA2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+template <bool CTA2, int EG>
+__global__ void __launch_bounds__(gemm_threads(EG), 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int EPI_WARPS = EG * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sm_epi = smem + p.stages * p.stage_bytes;
-  float* sm_bias = reinterpret_cast<float*>(sm_epi + EPI_WARPS * EPI_WARP_BYTES);       // 2 x 256 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_epi + EPI_WARPS * EPI_WARP_BYTES + BIAS_BYTES);
+  float* sm_bias = reinterpret_cast<float*>(sm_epi + EPI_WARPS * p.epi_bufs * EPI_BUF_BYTES);       // 2 x 256 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_epi + EPI_WARPS * p.epi_bufs * EPI_BUF_BYTES + BIAS_BYTES);
   uint64_t* full = bars;                         // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;           // [MAX_STAGES]
   uint64_t* tfull = bars + 2 * MAX_STAGES;       // [2]
@@ -228,8 +231,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int ew = warp - 2;
     const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
     const int lane_base = (warp & 3) * 32;                // TMEM lanes this warp may read
-    const int half = ew >> 2;                             // which alternate chunks it takes
-    const uint32_t stg = smem_u32(sm_epi + ew * EPI_WARP_BYTES);
+    const int half = ew >> 2;                             // which column chunks it takes: half, half + EG, ...
+    const uint32_t stg = smem_u32(sm_epi + ew * p.epi_bufs * EPI_BUF_BYTES);
     int tile_iter = 0;
     for (int tile = worker; tile < total_tiles; tile += n_workers, ++tile_iter) {
       const int as = tile_iter & 1;
@@ -241,14 +244,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       float* sb = sm_bias + as * 256;
       {
         const int n = n_tile * p.BN + et;
-        sb[et] = (p.bias != nullptr && et < p.BN && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        if (et < 256) sb[et] = (p.bias != nullptr && et < p.BN && n < p.N) ? __ldg(p.bias + n) : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       mbar_wait(&tfull[as], (tile_iter >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(lane_base) << 16);
       if (m_tile < p.m_tiles)        // the odd CTA of the last pair may have no rows of its own
-        epilogue_dispatch(p, tc, n_tile, taddr, lane_base, lane, half, stg, sb);
+        epilogue_dispatch<EG>(p, tc, n_tile, taddr, lane_base, lane, half, stg, sb);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -415,7 +418,13 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
   p.res2 = a->res2; p.ldr2 = a->ldr2; p.res2_f32 = a->res2_f32;
   p.out = a->out; p.ldo = a->ldo; p.out_f32 = a->out_f32; p.n_store = a->n_store;
   p.stage_bytes = A_STAGE_BYTES + bn_load * BK * 2;
-  p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_WARPS * EPI_WARP_BYTES) / p.stage_bytes;
+  // Residual prefetch depth.  A warp keeps (epi_bufs - 1) chunks of 2 KB in flight; with 8 warps and one chunk each the
+  // residual stream of the short-K layers is latency-bound (16 KB in flight per SM against ~35 KB needed for a 148th of
+  // the HBM bandwidth).  Four buffers per warp where the main loop is short (K <= 1024: +4..9 % measured in-process
+  // with tools/bench_gemm.py --ab LKGD_GEMM_SHALLOW); longer loops prefer the extra operand stage (-4..11 %).
+  p.epi_bufs = 2;
+  if (a->res1 != nullptr && (long long)p.ntaps * a->K0 + a->K1 <= 1024 && !getenv("LKGD_GEMM_SHALLOW")) p.epi_bufs = 4;
+  p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - 8 * p.epi_bufs * EPI_BUF_BYTES) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   {
     // 16-byte addressable row segments everywhere -> staged, coalesced epilogue I/O
@@ -435,28 +444,20 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
 
 using namespace lkgd;
 
-extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
-  if (a == nullptr || a->A == nullptr || a->Bw == nullptr || a->out == nullptr) return LKGD_ESHAPE;
-  GemmParams p;
-  bool cta2 = false;
-  int rc = fill_params(a, p, cta2);
-  if (rc) return rc;
+template <bool CTA2, int EG>
+static int launch_gemm(const GemmParams& p, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return set_cuda_error(e);
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<CTA2, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  if (!p.fast_io && (a->res1 || a->res2)) return LKGD_EALIGN;   // residual rows must be 16-byte addressable
-  if (a->res2 && (!a->res1 || (a->res1_f32 != 0) != (a->res2_f32 != 0))) return LKGD_ESHAPE;   // res2 needs res1 of the same dtype
-  const int smem_bytes = 1024 + p.stages * p.stage_bytes + EPI_WARPS * EPI_WARP_BYTES + BIAS_BYTES + BAR_BYTES;
-  int sms = sm_count();
-  if (cta2) {
+  const int smem_bytes = 1024 + p.stages * p.stage_bytes + EG * 4 * p.epi_bufs * EPI_BUF_BYTES + BIAS_BYTES + BAR_BYTES;
+  const int sms = sm_count();
+  if (CTA2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(EG));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = reinterpret_cast<cudaStream_t>(stream);
     cudaLaunchAttribute at[1];
@@ -469,7 +470,7 @@ extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
       cfg.gridDim = dim3(sms);
       cfg.dynamicSmemBytes = SMEM_LIMIT;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<CTA2, EG>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = sms / 2 - 4;
       }
@@ -479,12 +480,23 @@ extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
     int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     if (pairs > max_pairs) pairs = max_pairs;
     cfg.gridDim = dim3(2 * pairs);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<CTA2, EG>, p);
     if (e != cudaSuccess) return set_cuda_error(e);
     return launch_epilogue();
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gemm_tcgen05_kernel<CTA2, EG><<<grid, gemm_threads(EG), smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return launch_epilogue();
+}
+
+extern "C" int lkgd_gemm(const lkgd_gemm_args* a, void* stream) {
+  if (a == nullptr || a->A == nullptr || a->Bw == nullptr || a->out == nullptr) return LKGD_ESHAPE;
+  GemmParams p;
+  bool cta2 = false;
+  int rc = fill_params(a, p, cta2);
+  if (rc) return rc;
+  if (!p.fast_io && (a->res1 || a->res2)) return LKGD_EALIGN;   // residual rows must be 16-byte addressable
+  if (a->res2 && (!a->res1 || (a->res1_f32 != 0) != (a->res2_f32 != 0))) return LKGD_ESHAPE;   // res2 needs res1 of the same dtype
+  return cta2 ? launch_gemm<true, 2>(p, stream) : launch_gemm<false, 2>(p, stream);
 }

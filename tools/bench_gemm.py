@@ -28,10 +28,12 @@ SHAPES = [
     ("tconv_L0_f32", "tconv", (2, 25, 9216), 320, 320, "f32"),
     ("tconv_L1_res32", "tconv", (2, 25, 2304), 640, 640, "res32"),
     ("tconv_L3_f32", "tconv", (2, 25, 144), 1280, 1280, "f32"),
+    ("tconv_L0_res32", "tconv", (2, 25, 9216), 320, 320, "res32"),
+    ("proj_L3_res32", "lin", 7200, 1280, 1280, "res32"),
 ]
 
 
-def run(shape, iters, flush):
+def run(shape, iters, flush, ab=None):
     name, mode, geo, N, K0, epi = shape
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
@@ -65,18 +67,32 @@ def run(shape, iters, flush):
     out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if out_b == 4 else bf16)
     for _ in range(2):
         ops.gemm(A, W, bias=bias, out=out, **kw)
-    ts = []
-    for _ in range(iters):
+    ts, ts_b = [], []
+    for it in range(iters * (2 if ab else 1)):
+        # --ab NAME: interleave calls with the environment switch NAME unset / set (the library reads it per call), so
+        # both variants see the same clocks and power state
+        alt = ab is not None and (it & 1)
+        if ab:
+            if alt:
+                os.environ[ab] = "1"
+            else:
+                os.environ.pop(ab, None)
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.gemm(A, W, bias=bias, out=out, **kw)
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        (ts_b if alt else ts).append(e0.elapsed_time(e1))
+    if ab:
+        os.environ.pop(ab, None)
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * M * N * taps * K0
-    return dict(name=name, M=M, N=N, K=taps * K0, epi=epi, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
+    extra = {}
+    if ab:
+        mb = sorted(ts_b)[len(ts_b) // 2]
+        extra = {"ms_" + ab: round(mb, 4), "ratio": round(mb / ms, 3)}
+    return dict(**extra, name=name, M=M, N=N, K=taps * K0, epi=epi, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
                 gbs=round(bytes_ / ms / 1e6, 1))
 
 
@@ -85,12 +101,13 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ab", default=None, help="environment switch to A/B in-process (interleaved calls)")
     a = ap.parse_args()
     sel = [int(i) for i in a.only.split(",")] if a.only else range(len(SHAPES))
     flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
     res = []
     for i in sel:
-        r = run(SHAPES[i], a.iters, flush)
+        r = run(SHAPES[i], a.iters, flush, a.ab)
         res.append(r)
         print(json.dumps(r), flush=True)
     if a.out:
