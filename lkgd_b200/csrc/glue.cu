@@ -36,6 +36,18 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const 
             acc[i] = fmaf(act_apply(xv.w, act_in), wv.w, acc[i]);
           }
       }
+    } else if ((K & 3) == 0) {
+      // operands that are not 16-byte aligned (views into a flat parameter buffer): scalar loads, but the SAME
+      // lane / accumulation order as the vector path - the result must not depend on where a tensor happens to live
+      for (int k = lane; k < K / 4; k += 32) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float wv = __ldg(w + 4 * k + e);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (m0 + i < M) acc[i] = fmaf(act_apply(__ldg(x + (size_t)(m0 + i) * ldx + 4 * k + e), act_in), wv, acc[i]);
+        }
+      }
     } else {
       for (int k = lane; k < K; k += 32) {
         const float wv = __ldg(w + k);

@@ -275,6 +275,25 @@ def test_small_linear_and_timestep_embedding(cuda):
     assert rel_l2(e, torch.cat([arg.cos(), arg.sin()], -1)) < 1e-5
 
 
+def test_small_linear_result_does_not_depend_on_alignment(cuda):
+    """Parameters trained in the flat fp32 buffer are views at 4-byte granularity; the same numbers must give the same
+    bits wherever they live (a 1-ulp difference in the latent-knowledge context flips bf16 roundings downstream)."""
+    from lkgd_b200 import ops
+    x = rnd(2, 512, dev=cuda, dtype=torch.float32)
+    W = rnd(129, 512, dev=cuda, dtype=torch.float32, scale=0.05)
+    b = rnd(129, dev=cuda, dtype=torch.float32)
+    ref = ops.small_linear(x, W, b)
+    for off in (1, 2, 3):
+        buf = torch.empty(W.numel() + 4, device=cuda, dtype=torch.float32)
+        Wm = buf[off:off + W.numel()].view_as(W)
+        Wm.copy_(W)
+        xb = torch.empty(x.numel() + 4, device=cuda, dtype=torch.float32)
+        xm = xb[off:off + x.numel()].view_as(x)
+        xm.copy_(x)
+        assert torch.equal(ops.small_linear(x, Wm, b), ref)
+        assert torch.equal(ops.small_linear(xm, W, b), ref)
+
+
 def test_pack_unpack_layouts(cuda):
     from lkgd_b200 import ops
     S, Fr, H, W = 2, 3, 8, 16
