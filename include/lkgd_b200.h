@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 3
+#define LKGD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -106,6 +106,13 @@ typedef struct lkgd_gemm_args {
   int32_t res1_f32;   /* 1: res1 is fp32 (the residual stream is kept in fp32) */
   int32_t res2_f32;
   int32_t rv_ld;      /* row pitch of rowvec in floats (0 = contiguous: N, or N/2 for GEGLU); multiple of 4 */
+  /* Fused GroupNorm statistics of the stored output (fp32 outputs only): per (frame image, channel) sum and sum of
+   * squares are ADDED to gn_stats [M / gn_rows][N][2] doubles (caller zeroes it), gn_rows = rows per frame image (H*W).
+   * LINEAR mode needs gn_rows % 128 == 0.  The consumer is lkgd_groupnorm_from_stats: the GroupNorm that follows a
+   * conv / projection (diffusers ResnetBlock2D.norm2, TemporalResnetBlock.norm1/2, the next block's norm1) no longer
+   * re-reads the tensor for its statistics. */
+  double* gn_stats;   /* NULL = off                                           */
+  int32_t gn_rows;
 } lkgd_gemm_args;
 
 LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);
@@ -124,6 +131,14 @@ LKGD_API int lkgd_gemm_simt_check(const lkgd_gemm_args* args, void* stream);
  */
 LKGD_API size_t lkgd_groupnorm_workspace(int32_t NS, int32_t C);
 LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t NS, int32_t R, int32_t groups,
+                   const float* gamma, const float* beta, float eps, int32_t silu, int32_t x_f32, void* out,
+                   void* workspace, size_t ws_bytes, void* stream);
+/* Same normalisation with the statistics already accumulated by the producing lkgd_gemm launches (gn_stats):
+ * stats1 / stats2 are [NS * frames_per_sample][C1 or C2][2] doubles (per frame image, channel); frames_per_sample = 1
+ * for the spatial GroupNorms (NS = B*F) and F for the temporal ones (NS = B, statistics across frames).  One pass over
+ * the tensor instead of two. */
+LKGD_API int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const double* stats1, const void* x2, int32_t C2,
+                   const double* stats2, int32_t NS, int32_t R, int32_t frames_per_sample, int32_t groups,
                    const float* gamma, const float* beta, float eps, int32_t silu, int32_t x_f32, void* out,
                    void* workspace, size_t ws_bytes, void* stream);
 

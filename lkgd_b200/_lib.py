@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("act", i32), ("s0", f32), ("res1", vp), ("ldr1", i32), ("s1", f32),
         ("res2", vp), ("ldr2", i32), ("s2", f32),
         ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32), ("res1_f32", i32), ("res2_f32", i32),
-        ("rv_ld", i32),
+        ("rv_ld", i32), ("gn_stats", vp), ("gn_rows", i32),
     ]
 
 
@@ -44,6 +44,8 @@ SIGNATURES = {
     "lkgd_gemm_simt_check": (i32, [C.POINTER(GemmArgs), vp]),
     "lkgd_groupnorm_workspace": (sz, [i32, i32]),
     "lkgd_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, sz, vp]),
+    "lkgd_groupnorm_from_stats": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, sz,
+                                        vp]),
     "lkgd_layernorm": (i32, [vp, i32, i32, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "lkgd_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_attention_simt_check": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),

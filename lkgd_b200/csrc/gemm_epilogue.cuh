@@ -308,10 +308,47 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       }
       __syncwarp();
       const bool col_ok = n_out + o_pc_col < n_store;
+      if (OES == 4 && p.gn_stats != nullptr) {
+        // Fused GroupNorm statistics.  After the transpose this lane holds 4 consecutive columns of 4 rows; the 8 lanes
+        // with the same lane % 4 cover the warp's 32 rows of those columns.  Column sums / sums of squares are reduced
+        // over them with a halving butterfly (7 shuffles) that leaves ONE of the 8 totals in each lane, which then
+        // issues one fp64 atomic: 32 atomics per 32 x 16 chunk.
+        float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < PO; ++j) {
-        if (col_ok && orow[j] != nullptr)
-          *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = lds128(buf + o_co + 512 * j);
+        for (int j = 0; j < PO; ++j) {
+          const uint4 u = lds128(buf + o_co + 512 * j);
+          const bool ok = col_ok && orow[j] != nullptr;
+          if (ok) *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = u;
+          const float x0 = ok ? __uint_as_float(u.x) : 0.f, x1 = ok ? __uint_as_float(u.y) : 0.f,
+                      x2 = ok ? __uint_as_float(u.z) : 0.f, x3 = ok ? __uint_as_float(u.w) : 0.f;
+          w[0] += x0; w[1] += x1; w[2] += x2; w[3] += x3;
+          w[4] = fmaf(x0, x0, w[4]); w[5] = fmaf(x1, x1, w[5]); w[6] = fmaf(x2, x2, w[6]); w[7] = fmaf(x3, x3, w[7]);
+        }
+#pragma unroll
+        for (int n = 4, off = 16; n >= 1; n >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send = up ? w[i] : w[i + n];
+            const float keep = up ? w[i + n] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        // w[0]: quantity (lane & 16 ? sum of squares : sum) of column o_pc_col + 2 * bit3 + bit2 of this chunk
+        const int col = n_out + o_pc_col + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if (col < n_store) {
+          long long frame;
+          if (p.mode == LKGD_A_LINEAR) frame = tc.c1 / p.gn_rows;
+          else if (p.mode == LKGD_A_CONV3X3) frame = tc.c3;
+          else frame = (long long)tc.c3 * p.F + tc.c2;
+          atomicAdd(p.gn_stats + ((size_t)frame * n_cols + col) * 2 + (lane >> 4), (double)w[0]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PO; ++j) {
+          if (col_ok && orow[j] != nullptr)
+            *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = lds128(buf + o_co + 512 * j);
+        }
       }
       __syncwarp();            // staging buffer free again (next prefetch may overwrite it)
     } else if (m >= 0) {

@@ -54,6 +54,8 @@ struct GemmParams {
   void* out;
   int ldo, out_f32, n_store;
   int fast_io;                         // 1: every out / residual row segment is 16-byte addressable
+  double* gn_stats;                    // fused GroupNorm statistics [frames][N][2] (nullptr = off)
+  int gn_rows;                         // rows per frame image
 };
 
 __device__ __forceinline__ int rowvec_index(int mode, int m, int HW, int F, int B) {
@@ -436,6 +438,14 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
     if (a->res2) { const int es = a->res2_f32 ? 4 : 2; ok = ok && aligned16(a->res2) && ((size_t)a->ldr2 * es) % 16 == 0 && (n_store * es) % 16 == 0; }
     if ((a->bias && !aligned16(a->bias)) || (a->rowvec && !aligned16(a->rowvec))) return LKGD_EALIGN;
     p.fast_io = ok ? 1 : 0;
+  }
+  p.gn_stats = a->gn_stats; p.gn_rows = a->gn_rows;
+  if (a->gn_stats != nullptr) {
+    // fp32 output through the staged path, every tile inside one frame image
+    if (!a->out_f32 || geglu || !p.fast_io || a->gn_rows <= 0 || a->M % a->gn_rows) return LKGD_ESHAPE;
+    if (a->a_mode == LKGD_A_LINEAR && a->gn_rows % BM) return LKGD_ESHAPE;
+    if (a->a_mode == LKGD_A_CONV3X3 && (long long)p.H * p.W != a->gn_rows) return LKGD_ESHAPE;
+    if (a->a_mode == LKGD_A_TCONV3 && a->HW != a->gn_rows) return LKGD_ESHAPE;
   }
   return LKGD_OK;
 }

@@ -101,6 +101,43 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const float*
   }
 }
 
+// Same as gn_finalize_kernel, but the per-(sample, channel) sums are gathered from the per-(frame image, channel) sums
+// that the producing GEMM launches accumulated (two sources = the channel concatenation of the up blocks).
+__global__ void gn_finalize_frames_kernel(const double* __restrict__ st1, int C1, const double* __restrict__ st2, int C2,
+                                          int fps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float eps, int groups, int R, float2* __restrict__ ss /* [NS][C] */) {
+  extern __shared__ double shd[];   // [C][2] sums of this sample, then mean / rstd per group (floats) behind them
+  const int C = C1 + C2;
+  float* gmean = reinterpret_cast<float*>(shd + 2 * C);
+  float* grstd = gmean + groups;
+  const int ns = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double* st = c < C1 ? st1 + ((size_t)ns * fps * C1 + c) * 2 : st2 + ((size_t)ns * fps * C2 + (c - C1)) * 2;
+    const size_t pitch = (size_t)(c < C1 ? C1 : C2) * 2;
+    double s = 0.0, q = 0.0;
+    for (int f = 0; f < fps; ++f) { s += st[f * pitch]; q += st[f * pitch + 1]; }
+    shd[2 * c] = s; shd[2 * c + 1] = q;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) { s += shd[2 * c]; q += shd[2 * c + 1]; }
+    const double n = (double)cpg * R;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = grstd[gi] * gamma[c];
+    ss[(size_t)ns * C + c] = make_float2(sc, beta[c] - gmean[gi] * sc);
+  }
+}
+
 __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
                                 const float2* __restrict__ ss, int silu, __nv_bfloat16* __restrict__ out) {
   const int ns = blockIdx.y;
@@ -314,6 +351,31 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
   rc = launch_epilogue();
   if (rc) return rc;
   gn_apply_kernel<<<grid, threads, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out));
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const double* stats1, const void* x2, int32_t C2,
+                                         const double* stats2, int32_t NS, int32_t R, int32_t frames_per_sample,
+                                         int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                                         int32_t x_f32, void* out, void* workspace, size_t ws_bytes, void* stream) {
+  if (x2 == nullptr) C2 = 0;
+  const int C = C1 + C2;
+  if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
+  if (frames_per_sample <= 0 || R % frames_per_sample || stats1 == nullptr || (x2 != nullptr && stats2 == nullptr))
+    return LKGD_ESHAPE;
+  if (!aligned16(x1) || !aligned16(out) || (x2 && !aligned16(x2))) return LKGD_EALIGN;
+  if (ws_bytes < lkgd_groupnorm_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GnGeom g = gn_geom(C1, C2, R, x_f32);
+  const size_t sums_bytes = (size_t)NS * C * 2 * sizeof(double);
+  float2* ss = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sums_bytes);
+  const size_t sh = (size_t)C * 2 * sizeof(double) + 2 * groups * sizeof(float);
+  if (sh > 48 * 1024) return LKGD_ESHAPE;
+  gn_finalize_frames_kernel<<<NS, 256, sh, st>>>(stats1, C1, stats2, C2, frames_per_sample, gamma, beta, eps, groups, R, ss);
+  int rc = launch_epilogue();
+  if (rc) return rc;
+  dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
+  gn_apply_kernel<<<grid, g.vecs * g.rows_par, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out));
   return launch_epilogue();
 }
 

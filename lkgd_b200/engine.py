@@ -284,8 +284,10 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
     temb_s = cond.temb(p.off_s, p.cout)
     temb_t = cond.temb(p.off_t, p.cout)
     h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
+    # gn_rows: the epilogue also accumulates the GroupNorm statistics of what it stores (per frame image, channel), so
+    # the GroupNorm that consumes the tensor reads it once instead of twice
     h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH),
-                 out_f32=True)        # only GroupNorm reads it: keep fp32 instead of rounding twice
+                 out_f32=True, gn_rows=g.HW)        # only GroupNorm reads it: keep fp32 instead of rounding twice
     h = ops.groupnorm(h, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True)
     if p.wsc is not None:
         # the 1x1 shortcut reads the raw input: narrow (and concatenate) it to the GEMM's bf16 operand
@@ -295,15 +297,15 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
         if skip is not None:
             raise ValueError("resblock with concatenated input must have a shortcut conv")
         sc = x
-    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True)
+    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True, gn_rows=g.HW)
     # temporal half: GroupNorm statistics across frames, (3,1,1) conv over the frame axis, AlphaBlender
     t = ops.groupnorm(s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True)
     t = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=temb_t, rv=g.rv(RV_BATCH),
-                 out_f32=True)
+                 out_f32=True, gn_rows=g.HW)
     t = ops.groupnorm(t, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True)
     # alpha*s + (1-alpha)*(s + conv2(t)) == s + (1-alpha)*conv2(t)
     return ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=s, s1=1.0,
-                    out_f32=True)
+                    out_f32=True, gn_rows=g.HW)
 
 
 def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor):
@@ -362,7 +364,8 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     ff = dense(n, p.t_ff1, act=ACT_GEGLU)
     # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t); bf16 because proj_out reads it as its GEMM operand
     mix = dense(ff, p.t_ff2, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
-    return dense(mix, p.proj_out, res1=x, out_f32=True)
+    # the next resblock's GroupNorm consumes this tensor: fused statistics where a 128-row tile stays inside a frame
+    return dense(mix, p.proj_out, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0)
 
 
 class PackedUNet:
@@ -448,7 +451,7 @@ class PackedUNet:
     def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None):
         """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms)."""
         x = ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b, res1=stem_add,
-                     out_f32=True)
+                     out_f32=True, gn_rows=g.HW)
         skips, geoms = [x], [g]
         for res, att, ds in self.down:
             for i, r in enumerate(res):
@@ -459,7 +462,7 @@ class PackedUNet:
                 geoms.append(g)
             if ds is not None:
                 x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1],
-                             out_f32=True)
+                             out_f32=True, gn_rows=g.down().HW)
                 g = g.down()
                 skips.append(x)
                 geoms.append(g)
@@ -479,7 +482,7 @@ class PackedUNet:
             if us is not None:
                 x = ops.upsample2x(x, g.BF, g.H, g.W)
                 g = g.up()
-                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True)
+                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True, gn_rows=g.HW)
         h = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, self.norm_out.eps, NS=g.BF, R=g.HW, silu=True)
         # conv_out: N padded to 32 rows of zeros, only the first `cout` columns are stored (fp32)
         return ops.gemm(h, self.conv_out_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_out_b,

@@ -2,6 +2,7 @@
 device pointers + the current CUDA stream.  No computation happens in PyTorch here."""
 from __future__ import annotations
 
+import os
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -43,8 +44,12 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
          rowvec: Optional[torch.Tensor] = None, rv: Tuple[int, int, int, int] = (RV_NONE, 1, 1, 1),
          act: int = ACT_NONE, s0: float = 1.0, res1: Optional[torch.Tensor] = None, s1: float = 1.0,
          res2: Optional[torch.Tensor] = None, s2: float = 1.0, out: Optional[torch.Tensor] = None,
-         out_f32: bool = False, n_store: int = 0, checker: bool = False) -> torch.Tensor:
+         out_f32: bool = False, n_store: int = 0, checker: bool = False, gn_rows: int = 0) -> torch.Tensor:
     """out = s0*act(A (*) Bw^T [+ A1 Bw1^T] + bias + rowvec[g(m)]) + s1*res1 + s2*res2   (see lkgd_gemm).
+
+    ``gn_rows`` > 0 (fp32 outputs): also accumulate the GroupNorm statistics of the output per (frame image of
+    ``gn_rows`` rows, channel) in the epilogue; they travel with the returned tensor (``gn_stats_of``) and let the
+    ``groupnorm`` that consumes it skip its statistics pass.
 
     LINEAR: ``A`` is [M, K] (may be a column slice of a wider row-major matrix).  CONV3X3: ``A`` is contiguous
     [NIMG, Hin, Win, C], ``conv=(NIMG, Hin, Win, stride)``, ``Bw`` [N, 9*C].  TCONV3: ``A`` contiguous
@@ -114,11 +119,30 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     a.res2_f32 = int(res2 is not None and res2.dtype == torch.float32)
     lib = L.load()
     fn = lib.lkgd_gemm_simt_check if checker else lib.lkgd_gemm
+    stats = None
+    if gn_rows > 0 and not checker and not os.environ.get("LKGD_NO_FUSED_GN"):   # switch: A/B measurements only
+        stats = torch.zeros((M // gn_rows, N, 2), device=A.device, dtype=torch.float64)
+        a.gn_stats, a.gn_rows = stats.data_ptr(), gn_rows
     if L.PROF.enabled:
         L.PROF.meta = {"flops": 2.0 * M * N * (taps * a.K0 + a.K1), "mode": mode, "M": M, "N": N,
                        "K": taps * a.K0 + a.K1}
     L.check(fn(C.byref(a), _stream()), "lkgd_gemm")
+    _set_gn_stats(out, stats, gn_rows)
     return out
+
+
+def _set_gn_stats(t: torch.Tensor, stats: Optional[torch.Tensor], gn_rows: int = 0) -> None:
+    """Attach (or, with None, drop) fused GroupNorm statistics.  Every op that writes a tensor in place drops them."""
+    if stats is None:
+        if hasattr(t, "_gn_stats"):
+            del t._gn_stats
+    else:
+        t._gn_stats = (stats, gn_rows)
+
+
+def gn_stats_of(t: Optional[torch.Tensor]):
+    """(stats [frames, C, 2] float64, rows per frame) accumulated by the producing ``gemm``, or None."""
+    return getattr(t, "_gn_stats", None) if t is not None else None
 
 
 def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor]):
@@ -152,10 +176,22 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     lib = L.load()
     if out is None:
         out = torch.empty((NS * R, Ct), device=x1.device, dtype=bf16)
-    if L.PROF.enabled:   # algorithmic bytes: input read twice (statistics, then normalise) + bf16 output
-        L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2)}
     ws_bytes = lib.lkgd_groupnorm_workspace(NS, Ct)
     ws = torch.empty(ws_bytes, device=x1.device, dtype=torch.uint8)
+    st1, st2 = gn_stats_of(x1), gn_stats_of(x2)
+    fused = (not return_stats and st1 is not None and (x2 is None or (st2 is not None and st2[1] == st1[1]))
+             and R % st1[1] == 0 and st1[0].shape[0] * st1[1] == NS * R)
+    if fused:
+        if L.PROF.enabled:   # algorithmic bytes: ONE read of the input + bf16 output
+            L.PROF.meta = {"bytes": NS * R * Ct * (x1.element_size() + 2)}
+        L.check(lib.lkgd_groupnorm_from_stats(x1.data_ptr(), C1, st1[0].data_ptr(), _ptr(x2), C2,
+                                              st2[0].data_ptr() if x2 is not None else None, NS, R, R // st1[1],
+                                              groups, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
+                                              int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                              _stream()), "lkgd_groupnorm_from_stats")
+        return out
+    if L.PROF.enabled:   # algorithmic bytes: input read twice (statistics, then normalise) + bf16 output
+        L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2)}
     L.check(lib.lkgd_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
                                eps, int(silu), int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
                                _stream()), "lkgd_groupnorm")
@@ -170,6 +206,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise ValueError("layernorm: x must be contiguous bf16/fp32 [M, C]")
     if sum_out is not None and (sum_out.dtype != x.dtype or not sum_out.is_contiguous()):
         raise ValueError("layernorm: sum_out must be contiguous and of x's dtype")
+    if sum_out is not None:
+        _set_gn_stats(sum_out, None)
     M, Cn = x.shape
     if addvec is not None and (addvec.dtype != torch.float32 or addvec.dim() != 2 or addvec.shape[-1] != Cn
                                or addvec.stride(1) != 1):
@@ -261,6 +299,7 @@ def axpy_f32(x: torch.Tensor, y: torch.Tensor, alpha: float = 1.0) -> torch.Tens
             or x.numel() != y.numel():
         raise ValueError("axpy_f32: contiguous fp32 tensors of equal size")
     L.check(L.load().lkgd_axpy_f32(x.data_ptr(), alpha, y.data_ptr(), x.numel(), _stream()), "lkgd_axpy_f32")
+    _set_gn_stats(y, None)
     return y
 
 
@@ -359,6 +398,7 @@ def axpby(x: torch.Tensor, alpha: float, y: torch.Tensor, beta: float) -> torch.
         raise ValueError("axpby: contiguous bf16/fp32 tensors of equal size")
     L.check(L.load().lkgd_axpby(x.data_ptr(), int(x.dtype == torch.float32), alpha, y.data_ptr(),
                                 int(y.dtype == torch.float32), beta, x.numel(), _stream()), "lkgd_axpby")
+    _set_gn_stats(y, None)
     return y
 
 

@@ -275,6 +275,48 @@ def test_small_linear_and_timestep_embedding(cuda):
     assert rel_l2(e, torch.cat([arg.cos(), arg.sin()], -1)) < 1e-5
 
 
+@pytest.mark.parametrize("mode", ["conv", "tconv", "linear", "conv_s2"])
+def test_gemm_fused_groupnorm_statistics(cuda, mode):
+    """lkgd_gemm(gn_stats) + lkgd_groupnorm_from_stats == lkgd_gemm + lkgd_groupnorm (spatial: statistics per frame;
+    temporal: across frames; two-source concatenation), and the raw sums match torch."""
+    from lkgd_b200 import ops
+    from lkgd_b200.ops import A_CONV3X3, A_LINEAR, A_TCONV3
+    B, Fr, H, W, Ci, Co = 2, 3, 16, 24, 64, 96
+    HW = H * W
+    kw, taps, gn_rows = {}, 1, HW
+    if mode == "conv":
+        kw, taps = dict(mode=A_CONV3X3, conv=(B * Fr, H, W, 1)), 9
+    elif mode == "conv_s2":
+        kw, taps, gn_rows = dict(mode=A_CONV3X3, conv=(B * Fr, H, W, 2)), 9, (H // 2) * (W // 2)
+    elif mode == "tconv":
+        kw, taps = dict(mode=A_TCONV3, tconv=(B, Fr, HW)), 3
+    M_in = B * Fr * HW
+    M = B * Fr * gn_rows
+    A = rnd(M_in, Ci, dev=cuda)
+    Wt = rnd(Co, taps * Ci, dev=cuda, scale=(taps * Ci) ** -0.5)
+    bias = rnd(Co, dev=cuda, dtype=torch.float32)
+    res = rnd(M, Co, dev=cuda, dtype=torch.float32, seed=3)
+    plain = ops.gemm(A, Wt, bias=bias, res1=res, s0=0.7, out_f32=True, **kw)
+    fused = ops.gemm(A, Wt, bias=bias, res1=res, s0=0.7, out_f32=True, gn_rows=gn_rows, **kw)
+    assert torch.equal(plain, fused)
+    st, rows = ops.gn_stats_of(fused)
+    assert rows == gn_rows and ops.gn_stats_of(plain) is None
+    x = fused.double().view(B * Fr, gn_rows, Co)
+    assert rel_l2(st[..., 0], x.sum(1)) < 1e-5 and rel_l2(st[..., 1], (x * x).sum(1)) < 1e-5
+    g, b = rnd(Co, dev=cuda, dtype=torch.float32, seed=5), rnd(Co, dev=cuda, dtype=torch.float32, seed=6)
+    for NS, R in ((B * Fr, gn_rows), (B, Fr * gn_rows)):
+        a = ops.groupnorm(plain, g, b, 1e-5, NS=NS, R=R, silu=True)
+        f = ops.groupnorm(fused, g, b, 1e-5, NS=NS, R=R, silu=True)
+        assert rel_l2(f, a) < 2e-3       # bf16 outputs; statistics agree to ~1e-6
+    g2, b2 = rnd(2 * Co, dev=cuda, dtype=torch.float32, seed=7), rnd(2 * Co, dev=cuda, dtype=torch.float32, seed=8)
+    other = ops.gemm(A, Wt, bias=bias, out_f32=True, gn_rows=gn_rows, **kw)
+    a = ops.groupnorm(plain, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other.clone(), silu=False)
+    f = ops.groupnorm(fused, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other, silu=False)
+    assert rel_l2(f, a) < 2e-3
+    ops.axpby(res, 0.5, fused, 1.0)      # an in-place update drops the (now stale) statistics
+    assert ops.gn_stats_of(fused) is None
+
+
 def test_small_linear_result_does_not_depend_on_alignment(cuda):
     """Parameters trained in the flat fp32 buffer are views at 4-byte granularity; the same numbers must give the same
     bits wherever they live (a 1-ulp difference in the latent-knowledge context flips bf16 roundings downstream)."""
