@@ -48,6 +48,49 @@ constexpr int AT_SMEM = AT_TILE /*Q*/ + AT_NS * AT_KV /*K*/ + AT_NS * AT_KV /*V*
 //                  p = 2^(s c - m) -> packed bf16 pairs -> tcgen05.st into the P columns -> p_full.
 // Shared-memory bandwidth was the co-bottleneck of the earlier versions (P written with st.shared and read back by the
 // tensor core: 32 KB of the 64 KB smem traffic per step).
+// ---- packed fp32x2 helpers (FFMA2 / FADD2: one issue slot for two elements)
+__device__ __forceinline__ uint64_t at_pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void at_upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t at_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t at_add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the FMA / ALU pipes (no MUFU): x = n + r with n = round(x) taken from the mantissa of x + 1.5 * 2^23,
+// 2^r on [-0.5, 0.5] as a degree-3 minimax polynomial (max relative error 7.5e-5, 15x below the bf16 rounding of P),
+// 2^n added into the exponent field.  x is clamped at -126 (also maps the -inf of masked keys to ~1e-38).
+__device__ __forceinline__ uint64_t at_exp2_poly2(uint64_t X) {
+  float x0, x1;
+  at_upk2(X, x0, x1);
+  X = at_pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t MAGIC = at_pk2(12582912.0f, 12582912.0f), NMAGIC = at_pk2(-12582912.0f, -12582912.0f);
+  const uint64_t T = at_add2(X, MAGIC);
+  const uint64_t N = at_add2(T, NMAGIC);
+  const uint64_t R = at_fma2(N, at_pk2(-1.0f, -1.0f), X);
+  uint64_t P = at_fma2(at_pk2(0.0551716685f, 0.0551716685f), R, at_pk2(0.2426111251f, 0.2426111251f));
+  P = at_fma2(P, R, at_pk2(0.6932609677f, 0.6932609677f));
+  P = at_fma2(P, R, at_pk2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  at_upk2(T, t0, t1);
+  at_upk2(P, p0, p1);
+  return at_pk2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+                __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
+
+// POLY: every POLY-th pair of exponentials is evaluated on the FMA pipes instead of the MUFU pipe (0 = none).  d = 64
+// attention is bound by the 16 ex2 / clock / SM of the MUFU pipe; the FMA pipes are otherwise nearly idle here.
+template <int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -184,12 +227,35 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
       }
       // p = 2^(s*c - m) in f32, packed to bf16 pairs in place (word j = keys 2j, 2j+1)
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (POLY < 0) {        // scalar reference formulation (A/B only)
 #pragma unroll
-      for (int i = 0; i < AT_BH; i += 2) {
-        const float p0 = ex2f(fmaf(__uint_as_float(s[i]), sc, -m_run));
-        const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), sc, -m_run));
-        ls4[(i >> 1) & 3] += p0 + p1;
-        s[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < AT_BH; i += 2) {
+          const float p0 = ex2f(fmaf(__uint_as_float(s[i]), sc, -m_run));
+          const float p1 = ex2f(fmaf(__uint_as_float(s[i + 1]), sc, -m_run));
+          ls4[(i >> 1) & 3] += p0 + p1;
+          s[i >> 1] = pack_bf16x2(p0, p1);
+        }
+      } else {
+        const uint64_t SC2 = at_pk2(sc, sc), NM2 = at_pk2(-m_run, -m_run);
+        uint64_t LS[2] = {0ull, 0ull};
+#pragma unroll
+        for (int j = 0; j < AT_BH / 2; ++j) {
+          const uint64_t X = at_fma2(at_pk2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), SC2, NM2);
+          uint64_t P;
+          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+            P = at_exp2_poly2(X);
+          } else {
+            float x0, x1;
+            at_upk2(X, x0, x1);
+            P = at_pk2(ex2f(x0), ex2f(x1));
+          }
+          LS[j & 1] = at_add2(LS[j & 1], P);
+          float p0, p1;
+          at_upk2(P, p0, p1);
+          s[j] = pack_bf16x2(p0, p1);
+        }
+        at_upk2(LS[0], ls4[0], ls4[1]);
+        at_upk2(LS[1], ls4[2], ls4[3]);
       }
       if (h > 0) {
         mbar_wait(pv_done, (h - 1) & 1);        // P_{h-1} V_{h-1} has landed: O may be rescaled, P may be overwritten
@@ -453,12 +519,26 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   p.lse = lse;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr = true;
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
-  attn_flash_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // tuning switch (tools/bench_attn.py, LKGD_ATTN_POLY_AB): -1 scalar formulation, 0 packed without offload, 3 / 4 every
+  // third / fourth pair on the FMA pipes.  Measured in one process at L0 / L1: -1: 7.15 / 0.90 ms, 0: 7.33 / 0.90,
+  // 4: 6.63 / 0.81, 3: 6.60 / 0.81.
+  const char* pe = getenv("LKGD_ATTN_POLY");
+  const int poly = pe ? atoi(pe) : 3;
+  switch (poly) {
+    case -1: attn_flash_kernel<-1><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case 0: attn_flash_kernel<0><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case 4: attn_flash_kernel<4><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    default: attn_flash_kernel<3><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+  }
   return launch_epilogue();
 }
 

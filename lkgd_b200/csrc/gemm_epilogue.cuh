@@ -258,7 +258,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
     }
     if (p.act == LKGD_ACT_SILU) {
 #pragma unroll
-      for (int j = 0; j < CW; ++j) v[j] = silu_f(v[j]);
+      for (int j = 0; j < CW; ++j) v[j] = silu_fast(v[j]);
     }
     if (p.s0 != 1.0f) {
 #pragma unroll

@@ -138,7 +138,7 @@ __global__ void gn_finalize_frames_kernel(const double* __restrict__ st1, int C1
   }
 }
 
-__global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
                                 const float2* __restrict__ ss, int silu, __nv_bfloat16* __restrict__ out) {
   const int ns = blockIdx.y;
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
@@ -167,7 +167,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, const void* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float y = fmaf(f[u][i], sc[i], sf[i]);
-          f[u][i] = silu ? silu_f(y) : y;
+          f[u][i] = silu ? silu_fast(y) : y;
         }
         *reinterpret_cast<uint4*>(out + ((long long)ns * g.R + rr) * g.C + v * 8) =
             make_uint4(pack_bf16x2(f[u][0], f[u][1]), pack_bf16x2(f[u][2], f[u][3]), pack_bf16x2(f[u][4], f[u][5]),

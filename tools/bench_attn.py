@@ -15,12 +15,19 @@ for i in only:
     v = qkv[:, 2 * C:]
     f = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], v, n_img=n_img, heads=heads, d=64, Nq=N, Nk=N, out=out)
     f(); f()
-    ts = []
+    # LKGD_ATTN_POLY_AB=0,2,3,4: time the variants interleaved in one process (the library reads the switch per call)
+    variants = os.environ.get("LKGD_ATTN_POLY_AB", "").split(",") if os.environ.get("LKGD_ATTN_POLY_AB") else [None]
+    ts = {pv: [] for pv in variants}
     for _ in range(5):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); f(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[2]
-    print(json.dumps(dict(name=name, n_img=n_img, heads=heads, N=N, ms=round(ms, 4),
-                          tflops=round(4.0 * n_img * heads * N * N * 64 / ms / 1e9, 1))), flush=True)
+        for pv in variants:
+            if pv is not None:
+                os.environ["LKGD_ATTN_POLY"] = pv
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); f(); e1.record(); torch.cuda.synchronize()
+            ts[pv].append(e0.elapsed_time(e1))
+    for pv in variants:
+        ms = sorted(ts[pv])[2]
+        print(json.dumps(dict(name=name, poly=pv, n_img=n_img, heads=heads, N=N, ms=round(ms, 4),
+                              tflops=round(4.0 * n_img * heads * N * N * 64 / ms / 1e9, 1))), flush=True)
+    os.environ.pop("LKGD_ATTN_POLY", None)
