@@ -511,6 +511,11 @@ def main():
         at = by.get("lkgd_attention")
         if at:
             roof["attention_tflops"] = at["flops"] / (at["ms"] * 1e-3) / 1e12
+        # bandwidth-bound glue: algorithmic bytes (ops.* record them per call) / summed CUDA-event time, against the
+        # measured HBM copy bandwidth
+        roof["hbm_glue"] = {k: {"ms": round(v["ms"], 3), "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                "frac_of_hbm_peak": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 3)}
+                            for k, v in by.items() if v["bytes"] > 0 and v["ms"] > 0}
         if args.profile_out:
             json.dump({"by_kernel": by, "gemm_calls": [dict(meta, ms=a.elapsed_time(b)) for n, a, b, meta in
                                                         _lib.PROF.records if n == "lkgd_gemm" and meta]},

@@ -103,7 +103,7 @@ class Profiler:
 
 
 PROF = Profiler()
-_TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
+_TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_groupnorm_from_stats", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
           "lkgd_small_linear", "lkgd_timestep_embedding", "lkgd_pack_input", "lkgd_unpack_output",
           "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_cast_bf16", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_axpy_f32",
           "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32",

@@ -101,40 +101,40 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const float*
   }
 }
 
-// Same as gn_finalize_kernel, but the per-(sample, channel) sums are gathered from the per-(frame image, channel) sums
-// that the producing GEMM launches accumulated (two sources = the channel concatenation of the up blocks).
-__global__ void gn_finalize_frames_kernel(const double* __restrict__ st1, int C1, const double* __restrict__ st2, int C2,
-                                          int fps, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          float eps, int groups, int R, float2* __restrict__ ss /* [NS][C] */) {
-  extern __shared__ double shd[];   // [C][2] sums of this sample, then mean / rstd per group (floats) behind them
+// Same result as gn_finalize_kernel, but the sums are gathered from the per-(frame image, channel) sums that the
+// producing GEMM launches accumulated (two sources = the channel concatenation of the up blocks).  One CTA of 128
+// threads per (sample, group): cpg channels x fps frames x 2 doubles are reduced through shared memory, so the
+// temporal GroupNorms (2 samples x 25 frames) are not two serial CTAs.
+__global__ void __launch_bounds__(128) gn_finalize_frames_kernel(const double* __restrict__ st1, int C1,
+                                                                 const double* __restrict__ st2, int C2, int fps,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps, int groups,
+                                                                 int R, float2* __restrict__ ss /* [NS][C] */) {
+  __shared__ double red[2][128];
   const int C = C1 + C2;
-  float* gmean = reinterpret_cast<float*>(shd + 2 * C);
-  float* grstd = gmean + groups;
-  const int ns = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double* st = c < C1 ? st1 + ((size_t)ns * fps * C1 + c) * 2 : st2 + ((size_t)ns * fps * C2 + (c - C1)) * 2;
-    const size_t pitch = (size_t)(c < C1 ? C1 : C2) * 2;
-    double s = 0.0, q = 0.0;
-    for (int f = 0; f < fps; ++f) { s += st[f * pitch]; q += st[f * pitch + 1]; }
-    shd[2 * c] = s; shd[2 * c + 1] = q;
-  }
-  __syncthreads();
   const int cpg = C / groups;
-  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) { s += shd[2 * c]; q += shd[2 * c + 1]; }
-    const double n = (double)cpg * R;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gmean[gi] = (float)mean;
-    grstd[gi] = (float)(1.0 / sqrt(var + (double)eps));
+  const int ns = blockIdx.x / groups, gi = blockIdx.x % groups;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < cpg * fps; i += blockDim.x) {
+    const int c = gi * cpg + i % cpg, f = i / cpg;
+    const double* st = c < C1 ? st1 + (((size_t)ns * fps + f) * C1 + c) * 2
+                              : st2 + (((size_t)ns * fps + f) * C2 + (c - C1)) * 2;
+    s += st[0]; q += st[1];
   }
+  red[0][threadIdx.x] = s; red[1][threadIdx.x] = q;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int gi = c / cpg;
-    const float sc = grstd[gi] * gamma[c];
-    ss[(size_t)ns * C + c] = make_float2(sc, beta[c] - gmean[gi] * sc);
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { red[0][threadIdx.x] += red[0][threadIdx.x + o]; red[1][threadIdx.x] += red[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double n = (double)cpg * R;
+  const double mean = red[0][0] / n;
+  double var = red[1][0] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float fmean = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  for (int c = gi * cpg + threadIdx.x; c < (gi + 1) * cpg; c += blockDim.x) {
+    const float sc = rstd * gamma[c];
+    ss[(size_t)ns * C + c] = make_float2(sc, beta[c] - fmean * sc);
   }
 }
 
@@ -369,9 +369,8 @@ extern "C" int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const doubl
   GnGeom g = gn_geom(C1, C2, R, x_f32);
   const size_t sums_bytes = (size_t)NS * C * 2 * sizeof(double);
   float2* ss = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sums_bytes);
-  const size_t sh = (size_t)C * 2 * sizeof(double) + 2 * groups * sizeof(float);
-  if (sh > 48 * 1024) return LKGD_ESHAPE;
-  gn_finalize_frames_kernel<<<NS, 256, sh, st>>>(stats1, C1, stats2, C2, frames_per_sample, gamma, beta, eps, groups, R, ss);
+  gn_finalize_frames_kernel<<<NS * groups, 128, 0, st>>>(stats1, C1, stats2, C2, frames_per_sample, gamma, beta, eps, groups,
+                                                          R, ss);
   int rc = launch_epilogue();
   if (rc) return rc;
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);

@@ -11,11 +11,13 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     --profile-from-start off -k regex:gemm_tcgen05 --csv --log-file $out/${tag}_gemm_traffic_c3.csv $B \
     > $out/${tag}_gemm_traffic_c3.log 2>&1
-for spec in "0 gemm_ff1_L0_geglu" "11 gemm_conv_L0_res32" "9 gemm_ff2_L2_res32"; do
+for spec in "0 gemm_ff1_L0_geglu" "11 gemm_conv_L0_res32" "3 gemm_proj_L0_res32"; do
   set -- $spec
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -f \
       -o $out/${tag}_$2 python tools/bench_gemm.py --only $1 --iters 1 > $out/${tag}_$2.log 2>&1
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 2 -c 1 -f \
     -o $out/${tag}_attn_L0 python tools/bench_attn.py 0 > $out/${tag}_attn_L0.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:gn_apply -s 2 -c 1 -f \
+    -o $out/${tag}_gn_apply_L0 python tools/bench_norm.py > $out/${tag}_gn_apply_L0.log 2>&1
 ls -la $out
