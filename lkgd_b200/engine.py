@@ -377,7 +377,9 @@ class PackedUNet:
         self.c0 = cfg.block_out_channels[0]
         self.cin = cfg.in_channels
         self.cin_pad = 64
-        self.conv_in_w, self.conv_in_b = _conv3x3_weight(unet.conv_in, cin_pad=self.cin_pad)
+        # a model may present a merged stem (the flow variant folds its second, gated conv_in into one 12-channel conv)
+        stem = unet._stem_conv() if hasattr(unet, "_stem_conv") else unet.conv_in
+        self.conv_in_w, self.conv_in_b = _conv3x3_weight(stem, cin_pad=self.cin_pad)
         te, ae = unet.time_embedding, unet.add_embedding
         self.te = tuple(_f32(t) for t in (te.linear_1.weight, te.linear_1.bias, te.linear_2.weight, te.linear_2.bias))
         self.ae = tuple(_f32(t) for t in (ae.linear_1.weight, ae.linear_1.bias, ae.linear_2.weight, ae.linear_2.bias))

@@ -194,8 +194,8 @@ class _Base(nn.Module):
         if sample.ndim != 5:
             raise ValueError(f"sample must be [batch, frames, channels, height, width], got {tuple(sample.shape)}")
         B, F, C, H, W = sample.shape
-        if C != self.config.in_channels:
-            raise ValueError(f"sample has {C} channels, the model expects {self.config.in_channels}")
+        if C != self._sample_channels():
+            raise ValueError(f"sample has {C} channels, the model expects {self._sample_channels()}")
         n_down = sum(1 for d in pk.down if d[2] is not None)
         if H % (1 << n_down) or W % (1 << n_down):
             # the reference has no upsample_size forwarding, skip shapes would not match
@@ -205,6 +205,9 @@ class _Base(nn.Module):
 
     def _context(self, encoder_hidden_states: torch.Tensor, *extra) -> torch.Tensor:
         return encoder_hidden_states.to(torch.float32).contiguous()
+
+    def _sample_channels(self) -> int:
+        return self.config.in_channels
 
 
 class UNetSpatioTemporalConditionControlNetModel(_Base):
@@ -353,6 +356,41 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
 
 
 # --------------------------------------------------------------------------------------------------- LKGD
+class UNetSpatioTemporalConditionModelFlow(UNetSpatioTemporalConditionControlNetModel):
+    """The reference's flow-stem UNet (``models/unet_spatio_temporal_condition_flow.py``): the
+    ControlNet-accepting UNet plus ``initialize_conv_in()`` - a second stem ``conv_in2`` (a copy of ``conv_in``) gated
+    per output channel by ``conv_in2_alpha`` (:260-273).  ``forward`` takes a 12-channel sample (noise | condition |
+    second condition, :494-502):  conv_in(cat(noise, cond)) + conv_in2(cat(noise, cond2)) * alpha.
+
+    Both stems are linear in the sample, so the engine runs them as ONE 3x3 implicit-GEMM conv over the 12 channels with
+    weights merged at pack time (noise taps: W1 + alpha W2; cond: W1; cond2: alpha W2; bias b1 + alpha b2) - no second
+    launch, no extra pass over the [B*F, 320, H, W] stem output."""
+
+    def initialize_conv_in(self):
+        c = self.conv_in
+        self.conv_in2 = M.Conv2d(c.in_channels, c.out_channels, 3, padding=1).to(c.weight.device, c.weight.dtype)
+        self.conv_in2_alpha = nn.Parameter(torch.zeros(1, c.out_channels, 1, 1, device=c.weight.device,
+                                                       dtype=c.weight.dtype))
+        self.conv_in2.load_state_dict(c.state_dict())
+        self.invalidate()
+
+    def _sample_channels(self) -> int:
+        if not hasattr(self, "conv_in2"):
+            return self.config.in_channels
+        n = self.config.in_channels // 2
+        return 3 * n
+
+    def _stem_conv(self):
+        if not hasattr(self, "conv_in2"):
+            return self.conv_in
+        n = self.config.in_channels // 2
+        w1, w2 = self.conv_in.weight.detach().float(), self.conv_in2.weight.detach().float()
+        a = self.conv_in2_alpha.detach().float().reshape(-1, 1, 1, 1)
+        w = torch.cat([w1[:, :n] + a * w2[:, :n], w1[:, n:], a * w2[:, n:]], dim=1)
+        b = self.conv_in.bias.detach().float() + a.reshape(-1) * self.conv_in2.bias.detach().float()
+        return SimpleNamespace(weight=w, bias=b)
+
+
 class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetModel):
     """LKGD UNet: the latent-knowledge block (reference unet_spatio_temporal_condition.py:197-225,536-613) fuses the
     CLIP embedding with domain / flow ViT features (grouped 1x1 conv, quaternion linear, rFFT magnitude / phase

@@ -23,6 +23,7 @@ Everything is plain PyTorch on CPU in fp32 (or fp64 for self-consistency checks)
 from .blocks import *  # noqa: F401,F403
 from .unet import (  # noqa: F401
     UNetSpatioTemporalConditionControlNetModel,
+    UNetSpatioTemporalConditionModelFlow,
     UNetSpatioTemporalConditionModel,
     SVD_XT_CONFIG,
     REDUCED_CONFIG,

@@ -147,8 +147,11 @@ class UNetSpatioTemporalConditionControlNetModel(nn.Module):
     def _condition(self, encoder_hidden_states, *extra):
         return encoder_hidden_states
 
+    def _stem(self, sample):
+        return self.conv_in(sample)
+
     def _body(self, sample, emb, ctx, b, f, down_block_additional_residuals, mid_block_additional_residual):
-        sample = self.conv_in(sample)
+        sample = self._stem(sample)
         iof = torch.zeros(b, f, dtype=sample.dtype, device=sample.device)
         skips: Tuple[torch.Tensor, ...] = (sample,)
         for blk in self.down_blocks:
@@ -182,6 +185,27 @@ class UNetSpatioTemporalConditionControlNetModel(nn.Module):
         out = self._body(sample.flatten(0, 1), emb, ctx, b, f, down_block_additional_residuals,
                          mid_block_additional_residual)
         return SimpleNamespace(sample=out) if return_dict else (out,)
+
+
+# --------------------------------------------------------------------------- flow stem
+class UNetSpatioTemporalConditionModelFlow(UNetSpatioTemporalConditionControlNetModel):
+    """The ControlNet-accepting UNet with the second, gated input stem of the reference's flow pipelines
+    (``models/unet_spatio_temporal_condition_flow.py:260-273,494-502``): the sample carries THREE 4-channel groups
+    (noise | condition | second condition); ``conv_in`` sees (noise, condition), ``conv_in2`` - created by
+    ``initialize_conv_in()`` as a copy of ``conv_in`` - sees (noise, second condition) and is scaled per output channel
+    by ``conv_in2_alpha`` (zero-initialised, so a fresh stem leaves the model unchanged)."""
+
+    def initialize_conv_in(self):
+        c = self.conv_in
+        self.conv_in2 = nn.Conv2d(c.in_channels, c.out_channels, 3, padding=1).to(c.weight.device, c.weight.dtype)
+        self.conv_in2_alpha = nn.Parameter(torch.zeros(1, c.out_channels, 1, 1, device=c.weight.device,
+                                                       dtype=c.weight.dtype))
+        self.conv_in2.load_state_dict(c.state_dict())
+
+    def _stem(self, sample):
+        noise, cond, cond2 = sample.chunk(3, dim=-3)                                    # reference :494
+        return self.conv_in(torch.cat([noise, cond], -3)) + \
+            self.conv_in2(torch.cat([noise, cond2], -3)) * self.conv_in2_alpha          # :499-502
 
 
 # --------------------------------------------------------------------------- LKGD (A.7, A.8)

@@ -45,6 +45,31 @@ def test_unet_vs_reference(cuda):
     assert ea < 1e-2 and eb < 1e-2
 
 
+def test_flow_stem_unet_vs_reference(cuda):
+    """the flow-stem UNet (two gated stems merged into one 12-channel implicit-GEMM conv at pack time)
+    against the reference's own models/unet_spatio_temporal_condition_flow.py run through the shim."""
+    import os
+    from golden_util import HERE
+    from lkgd_b200.unet import UNetSpatioTemporalConditionModelFlow
+    FG = np.load(os.path.join(HERE, "golden", "flow_golden.npz"))
+    p = UNetSpatioTemporalConditionModelFlow(**REDUCED4)
+    p.initialize_conv_in()
+    p = fill_seeded_(p).to(cuda)
+    assert sorted(n for n, _ in p.named_parameters() if n.startswith("conv_in")) == list(FG["flow/param_names"])
+    sample = seeded_tensor("flow/sample", (B, F, 12, H, W)).to(cuda)
+    _, ctx, ids = (v.to(cuda) for v in unet_inputs())
+    a = p(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0]
+    with torch.no_grad():
+        p.conv_in2_alpha.zero_()
+    p.invalidate()
+    b = p(sample, T_STEP, ctx, added_time_ids=ids).sample
+    ea, eb = rel(a, FG["flow/out"]), rel(b, FG["flow/out_alpha0"])
+    print("flow-stem unet rel-L2", ea, eb)
+    assert ea < 1e-2 and eb < 1e-2
+    with pytest.raises(ValueError):
+        p(sample[:, :, :8], T_STEP, ctx, added_time_ids=ids)
+
+
 def test_unet_residual_injection_vs_reference(cuda):
     p = _product_unet(cuda)
     sample, ctx, ids = (v.to(cuda) for v in unet_inputs())

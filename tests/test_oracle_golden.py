@@ -104,6 +104,32 @@ def test_unet_forward_matches_reference():
     assert int(G["unet/n_params"]) == sum(p.numel() for p in o.parameters())
 
 
+def test_flow_stem_unet_matches_reference():
+    """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
+    by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""
+    import numpy as np
+    import oracle as O
+    FG = np.load(os.path.join(HERE, "golden", "flow_golden.npz"))
+    o = O.UNetSpatioTemporalConditionModelFlow(**REDUCED4)
+    o.initialize_conv_in()
+    o = fill_seeded_(o).eval()
+    assert sorted(n for n, _ in o.named_parameters() if n.startswith("conv_in")) == list(FG["flow/param_names"])
+    sample = seeded_tensor("flow/sample", (B, F, 12, H, W))
+    _, ctx, ids = unet_inputs()
+    with torch.no_grad():
+        a = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids, return_dict=False)[0]
+        o.conv_in2_alpha.zero_()
+        b = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids).sample
+    assert rel(a, FG["flow/out"]) < 1e-6
+    assert rel(b, FG["flow/out_alpha0"]) < 1e-6
+    # a fresh stem (alpha = 0) is the plain 8-channel UNet on (noise | condition)
+    base = O.UNetSpatioTemporalConditionControlNetModel(**REDUCED4)
+    base.load_state_dict({k: v for k, v in o.state_dict().items() if not k.startswith("conv_in2")})
+    with torch.no_grad():
+        c = base.eval()(sample[:, :, :8], torch.tensor(T_STEP), ctx, added_time_ids=ids).sample
+    assert rel(c, FG["flow/out_alpha0"]) < 1e-6
+
+
 def test_unet_residual_injection_matches_reference():
     """F6: the residual add sits inside the down-block loop (multipliers (2,2,2,2,1,1) for the 2-level config)."""
     o = _oracle_unet()
