@@ -298,6 +298,104 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
+// fp32 rows whose vector count splits evenly over LPR lanes (C = 320 / 640 / 1280: 5 vectors of 8 channels per lane on
+// 8 / 16 / 32 lanes): a warp normalises 32 / LPR rows per pass, so the two reductions are log2(LPR) shuffle steps shared
+// by all its rows (the row-per-warp kernel above spends 10 steps per row and leaves 3/8 of the lanes idle at C = 320),
+// gamma / beta live in registers for the whole kernel, and two passes are in flight per warp.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int M, int C,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             const float* __restrict__ addvec, int addvec_ld,
+                                                             int rv_mode, int rv_HW, int rv_F, int rv_B,
+                                                             float* sum_out, __nv_bfloat16* __restrict__ out) {
+  constexpr int RW = 32 / LPR;     // rows per warp pass
+  constexpr int U = 2;             // passes in flight
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.0f / (float)C;
+  float gg[VPL][8], bb[VPL][8];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = l + LPR * k;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+    gg[k][0] = g0.x; gg[k][1] = g0.y; gg[k][2] = g0.z; gg[k][3] = g0.w; gg[k][4] = g1.x; gg[k][5] = g1.y; gg[k][6] = g1.z; gg[k][7] = g1.w;
+    bb[k][0] = b0.x; bb[k][1] = b0.y; bb[k][2] = b0.z; bb[k][3] = b0.w; bb[k][4] = b1.x; bb[k][5] = b1.y; bb[k][6] = b1.z; bb[k][7] = b1.w;
+  }
+  for (long long row0 = warp_id * (RW * U); row0 < M; row0 += warps * (RW * U)) {
+    float f[U][VPL][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * RW + sub;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (row < M) {
+          const float4* p4 = reinterpret_cast<const float4*>(x + row * C + (l + LPR * k) * 8);
+          const float4 a = p4[0], b = p4[1];
+          f[u][k][0] = a.x; f[u][k][1] = a.y; f[u][k][2] = a.z; f[u][k][3] = a.w;
+          f[u][k][4] = b.x; f[u][k][5] = b.y; f[u][k][6] = b.z; f[u][k][7] = b.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[u][k][i] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * RW + sub;
+      const bool live = row < M;
+      if (addvec != nullptr && live) {
+        const float* av = addvec + (size_t)ln_rowvec_index(rv_mode, row, rv_HW, rv_F, rv_B) * addvec_ld;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + (l + LPR * k) * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + (l + LPR * k) * 8) + 1);
+          f[u][k][0] += a0.x; f[u][k][1] += a0.y; f[u][k][2] += a0.z; f[u][k][3] += a0.w;
+          f[u][k][4] += a1.x; f[u][k][5] += a1.y; f[u][k][6] += a1.z; f[u][k][7] += a1.w;
+        }
+      }
+      if (sum_out != nullptr && live) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          float4* o4 = reinterpret_cast<float4*>(sum_out + row * C + (l + LPR * k) * 8);
+          o4[0] = make_float4(f[u][k][0], f[u][k][1], f[u][k][2], f[u][k][3]);
+          o4[1] = make_float4(f[u][k][4], f[u][k][5], f[u][k][6], f[u][k][7]);
+        }
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += f[u][k][i];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = f[u][k][i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = (f[u][k][i] - mean) * rstd * gg[k][i] + bb[k][i];
+          *reinterpret_cast<uint4*>(out + row * C + (l + LPR * k) * 8) =
+              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                         pack_bf16x2(y[6], y[7]));
+        }
+      }
+    }
+  }
+}
+
 static GnGeom gn_geom(int C1, int C2, int R, int x_f32) {
   GnGeom g;
   g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
@@ -405,6 +503,22 @@ extern "C" int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* 
                                                             rv_HW, rv_F, rv_B, sum_out,                            \
                                                             reinterpret_cast<__nv_bfloat16*>(out));                \
   } while (0)
+  // fp32 rows of 5 vectors per lane on 8 / 16 / 32 lanes (C = 320 / 640 / 1280): the rows-per-warp kernel
+  if (x_f32 && C % 40 == 0 && (C / 40 == 8 || C / 40 == 16 || C / 40 == 32) && !getenv("LKGD_LN_ROWWARP")) {
+    const int lpr = C / 40, rows_per_warp_iter = (32 / lpr) * 2;
+    long long g_ = ((long long)M + 8 * rows_per_warp_iter - 1) / (8 * rows_per_warp_iter);
+    if (g_ > sm_count()) g_ = sm_count();        // 234 registers: one persistent CTA per SM, grid-stride over rows
+    const float* xf = reinterpret_cast<const float*>(x);
+    float* so = reinterpret_cast<float*>(sum_out);
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+    if (lpr == 8)
+      layernorm_rows_kernel<8, 5><<<(unsigned)g_, 256, 0, st>>>(xf, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, rv_HW, rv_F, rv_B, so, ob);
+    else if (lpr == 16)
+      layernorm_rows_kernel<16, 5><<<(unsigned)g_, 256, 0, st>>>(xf, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, rv_HW, rv_F, rv_B, so, ob);
+    else
+      layernorm_rows_kernel<32, 5><<<(unsigned)g_, 256, 0, st>>>(xf, M, C, gamma, beta, eps, addvec, addvec_ld, rv_mode, rv_HW, rv_F, rv_B, so, ob);
+    return launch_epilogue();
+  }
   switch (nv) {
     case 1: LN_LAUNCH(1, 4); break;
     case 2: LN_LAUNCH(2, 4); break;

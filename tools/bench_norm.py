@@ -7,14 +7,26 @@ from lkgd_b200 import ops
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
 
 
+AB = os.environ.get("LKGD_BENCH_AB")     # name of a library switch to A/B in-process (interleaved calls)
+
+
 def timeit(f, n=5):
     f(); f()
-    ts = []
-    for _ in range(n):
+    ts, tb = [], []
+    for i in range(n * (2 if AB else 1)):
+        alt = AB is not None and (i & 1)
+        if AB:
+            if alt:
+                os.environ[AB] = "1"
+            else:
+                os.environ.pop(AB, None)
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); f(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        (tb if alt else ts).append(e0.elapsed_time(e1))
+    if AB:
+        os.environ.pop(AB, None)
+        print(f"    A/B {AB}: unset {sorted(ts)[n // 2]:.4f} ms, set {sorted(tb)[n // 2]:.4f} ms", flush=True)
     return sorted(ts)[n // 2]
 
 
