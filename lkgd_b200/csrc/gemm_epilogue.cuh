@@ -339,9 +339,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
         if (col < n_store) {
           long long frame;
           if (p.mode == LKGD_A_LINEAR) frame = tc.c1 / p.gn_rows;
-          else if (p.mode == LKGD_A_CONV3X3) frame = tc.c3;
+          else if (p.mode == LKGD_A_CONV3X3) frame = tc.c3 + (lane_base >> p.px_shift);   // >= 32 pixels per image
           else frame = (long long)tc.c3 * p.F + tc.c2;
-          atomicAdd(p.gn_stats + ((size_t)frame * n_cols + col) * 2 + (lane >> 4), (double)w[0]);
+          if (p.mode != LKGD_A_CONV3X3 || frame < p.nimg)      // the last tile of a multi-image group may have no image
+            atomicAdd(p.gn_stats + ((size_t)frame * n_cols + col) * 2 + (lane >> 4), (double)w[0]);
         }
       } else {
 #pragma unroll

@@ -39,6 +39,7 @@ struct GemmParams {
   int epi_bufs;                      // 2 KB residual / output staging buffers per epilogue warp: 2 or 4
   int kb0, ntaps, kb1, k0;           // k-blocks per tap, taps, k-blocks of segment 1, channels per tap
   int H, W, TW, TH, tw_shift, tiles_w, tiles_h;  // conv output geometry + tile patch (TW a power of two)
+  int px_shift, IPT, nimg;             // conv: log2(TW * TH) pixels per image in a tile, images per tile (128 >> px_shift)
   int HW, F, tiles_p;                  // tconv
   int m_tiles, n_tiles;
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
@@ -77,10 +78,10 @@ __device__ __forceinline__ void tile_origin(const GemmParams& p, int m_tile, Til
     t.c1 = m_tile * BM; t.c2 = 0; t.c3 = 0;
   } else if (p.mode == LKGD_A_CONV3X3) {
     int per_img = p.tiles_w * p.tiles_h;
-    int img = m_tile / per_img, r = m_tile % per_img;
+    int grp = m_tile / per_img, r = m_tile % per_img;
     t.c1 = (r % p.tiles_w) * p.TW;   // w0
     t.c2 = (r / p.tiles_w) * p.TH;   // h0
-    t.c3 = img;
+    t.c3 = grp * p.IPT;              // first image of the tile (small images: several images share a tile)
   } else {  // TCONV3: tile = (bf, tile_p)
     int bf = m_tile / p.tiles_p;
     t.c1 = (m_tile % p.tiles_p) * BM;  // p0
@@ -95,8 +96,8 @@ __device__ __forceinline__ long long tile_row(const GemmParams& p, const TileCoo
     int m = t.c1 + r;
     return m < p.M ? m : -1;
   } else if (p.mode == LKGD_A_CONV3X3) {
-    int w = t.c1 + (r & (p.TW - 1)), h = t.c2 + (r >> p.tw_shift);
-    return (w < p.W && h < p.H) ? ((long long)t.c3 * p.H + h) * p.W + w : -1;
+    int w = t.c1 + (r & (p.TW - 1)), h = t.c2 + ((r >> p.tw_shift) & (p.TH - 1)), img = t.c3 + (r >> p.px_shift);
+    return (w < p.W && h < p.H && img < p.nimg) ? ((long long)img * p.H + h) * p.W + w : -1;
   } else {
     int pp = t.c1 + r;
     return pp < p.HW ? ((long long)(t.c3 * p.F + t.c2)) * p.HW + pp : -1;
@@ -286,14 +287,18 @@ static int choose_bn(int N, bool geglu) {
   return 256;  // tail tile handled by TMA zero-fill + store masking
 }
 
-static void choose_patch(int H, int W, int& TW, int& TH) {
-  // TW * TH = 128 pixels per tile; minimise padded area, prefer wide patches (longer contiguous runs)
+static void choose_patch(int H, int W, int nimg, int& TW, int& TH, int& IPT) {
+  // TW * TH * IPT = 128 rows per tile (all powers of two); minimise the padded row count, prefer wide patches (longer
+  // contiguous runs) and one image per tile.  Small feature maps (9 x 16 at the bottom of the SVD UNet) put several
+  // images in a tile instead of padding 9 rows to 16; at least 32 pixels per image, so that the 32 rows of an epilogue
+  // warp stay inside one frame (the fused GroupNorm statistics are per frame).
   long best = -1;
-  for (int tw = 128; tw >= 8; tw >>= 1) {
-    int th = 128 / tw;
-    long area = (long)((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
-    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
-  }
+  for (int ipt = 1; ipt <= 4; ipt <<= 1)
+    for (int tw = 128 / ipt; tw >= 8; tw >>= 1) {
+      int th = 128 / ipt / tw;
+      long area = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((nimg + ipt - 1) / ipt) * 128;
+      if (best < 0 || area < best) { best = area; TW = tw; TH = th; IPT = ipt; }
+    }
 }
 
 // CTA pairs (cta_group::2) halve the weight-tile traffic per SM but couple the two CTAs' epilogues to one MMA stream.
@@ -340,13 +345,16 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
     const int Ho = (a->Hin - 1) / s + 1, Wo = (a->Win - 1) / s + 1;
     if ((long long)a->NIMG * Ho * Wo != a->M) return LKGD_ESHAPE;
     p.H = Ho; p.W = Wo;
-    choose_patch(Ho, Wo, p.TW, p.TH);
+    choose_patch(Ho, Wo, a->NIMG, p.TW, p.TH, p.IPT);
+    p.nimg = a->NIMG;
     p.tw_shift = 0;
     while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+    p.px_shift = 0;
+    while ((1 << p.px_shift) < p.TW * p.TH) ++p.px_shift;
     p.tiles_w = (Wo + p.TW - 1) / p.TW; p.tiles_h = (Ho + p.TH - 1) / p.TH;
-    p.m_tiles = a->NIMG * p.tiles_w * p.tiles_h;
+    p.m_tiles = ((a->NIMG + p.IPT - 1) / p.IPT) * p.tiles_w * p.tiles_h;
     p.ntaps = 9;
-    uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.IPT};
     const uint64_t C = a->K0;
     if (s == 1) {
       uint64_t dims[4] = {C, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->NIMG};
