@@ -98,8 +98,9 @@ class PackedResBlock:
         if s.conv_shortcut is not None:
             self.wsc = _b16(s.conv_shortcut.weight.reshape(self.cout, self.cin))
             self.bsc = _f32(s.conv_shortcut.bias)
+            self.b2sc = (self.b2 + self.bsc).contiguous()      # conv2 + fused shortcut segment share one bias
         else:
-            self.wsc = self.bsc = None
+            self.wsc = self.bsc = self.b2sc = None
         self.tn1, self.tn2 = Norm.of(t.norm1), Norm.of(t.norm2)
         c = self.cout
         # Conv3d weight [C, C, 3, 1, 1] -> [C, kt, Cin]
@@ -290,14 +291,15 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
                  out_f32=True, gn_rows=g.HW)        # only GroupNorm reads it: keep fp32 instead of rounding twice
     h = ops.groupnorm(h, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True)
     if p.wsc is not None:
-        # the 1x1 shortcut reads the raw input: narrow (and concatenate) it to the GEMM's bf16 operand
+        # the 1x1 shortcut conv reads the raw input: narrow (and concatenate) it to a bf16 operand and run it as the
+        # SECOND K segment of conv2 (centre tap) - one launch, no fp32 shortcut tensor written and read back
         xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
-        sc = ops.gemm(xa, p.wsc, bias=p.bsc, out_f32=True)
+        s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2sc, A1=xa, Bw1=p.wsc, out_f32=True,
+                     gn_rows=g.HW)
     else:
         if skip is not None:
             raise ValueError("resblock with concatenated input must have a shortcut conv")
-        sc = x
-    s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True, gn_rows=g.HW)
+        s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=x, out_f32=True, gn_rows=g.HW)
     # temporal half: GroupNorm statistics across frames, (3,1,1) conv over the frame axis, AlphaBlender
     t = ops.groupnorm(s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True)
     t = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=temb_t, rv=g.rv(RV_BATCH),

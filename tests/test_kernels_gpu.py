@@ -127,6 +127,24 @@ def test_gemm_conv3x3(cuda, NIMG, H, W, Cin, Cout, stride):
     assert rel_l2(got, ref) < 4e-3
 
 
+@pytest.mark.parametrize("NIMG,H,W,Cin,C1,Cout", [(3, 16, 24, 64, 128, 96), (7, 9, 16, 128, 192, 64), (2, 18, 32, 64, 72, 160)])
+def test_gemm_conv3x3_with_fused_1x1_shortcut(cuda, NIMG, H, W, Cin, C1, Cout):
+    """conv2 of a resblock with its 1x1 shortcut conv as the second K segment (centre tap over the raw block input):
+    conv3x3(h) + conv1x1(x) in one launch (diffusers ResnetBlock2D.conv2 + conv_shortcut)."""
+    from lkgd_b200 import ops
+    h = rnd(NIMG, Cin, H, W, dev=cuda)
+    x = rnd(NIMG, C1, H, W, dev=cuda, seed=11)
+    w = rnd(Cout, Cin, 3, 3, dev=cuda, scale=(9 * Cin) ** -0.5)
+    ws = rnd(Cout, C1, 1, 1, dev=cuda, scale=C1 ** -0.5, seed=12)
+    b = rnd(Cout, dev=cuda, dtype=torch.float32)
+    ref = F.conv2d(h.float(), w.float(), b, padding=1) + F.conv2d(x.float(), ws.float())
+    out = ops.gemm(h.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(),
+                   mode=ops.A_CONV3X3, conv=(NIMG, H, W, 1), bias=b, out_f32=True,
+                   A1=x.permute(0, 2, 3, 1).reshape(NIMG * H * W, C1).contiguous(), Bw1=ws.reshape(Cout, C1).contiguous())
+    got = out.view(NIMG, H, W, Cout).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref) < 4e-3
+
+
 @pytest.mark.parametrize("B_,Fr,HW,C,N", [(2, 5, 200, 64, 64), (1, 8, 1024, 32, 32), (2, 3, 144, 128, 128),
                                           (1, 1, 64, 64, 64)])
 def test_gemm_tconv3(cuda, B_, Fr, HW, C, N):
