@@ -136,11 +136,12 @@ LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t 
 /* Same normalisation with the statistics already accumulated by the producing lkgd_gemm launches (gn_stats):
  * stats1 / stats2 are [NS * frames_per_sample][C1 or C2][2] doubles (per frame image, channel); frames_per_sample = 1
  * for the spatial GroupNorms (NS = B*F) and F for the temporal ones (NS = B, statistics across frames).  One pass over
- * the tensor instead of two. */
+ * the tensor instead of two.  raw_out (bf16 [NS, R, C1+C2], may be NULL) additionally receives the UN-normalised,
+ * concatenated input narrowed to bf16: the operand of the resblock's 1x1 conv_shortcut, for free in the same pass. */
 LKGD_API int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const double* stats1, const void* x2, int32_t C2,
                    const double* stats2, int32_t NS, int32_t R, int32_t frames_per_sample, int32_t groups,
                    const float* gamma, const float* beta, float eps, int32_t silu, int32_t x_f32, void* out,
-                   void* workspace, size_t ws_bytes, void* stream);
+                   void* raw_out, void* workspace, size_t ws_bytes, void* stream);
 
 /* LayerNorm over the last axis of a [M, C] bf16 matrix (C <= 2048, C % 8 == 0) with optional fused
  *   s = x + addvec[g(m)]   (fp32 addvec [G, C], row pitch addvec_ld floats (0 = C); frame positional embedding or

@@ -44,8 +44,8 @@ SIGNATURES = {
     "lkgd_gemm_simt_check": (i32, [C.POINTER(GemmArgs), vp]),
     "lkgd_groupnorm_workspace": (sz, [i32, i32]),
     "lkgd_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, sz, vp]),
-    "lkgd_groupnorm_from_stats": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, sz,
-                                        vp]),
+    "lkgd_groupnorm_from_stats": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, i32, vp, vp, vp,
+                                        sz, vp]),
     "lkgd_layernorm": (i32, [vp, i32, i32, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "lkgd_attention": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
     "lkgd_attention_simt_check": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(128) gn_finalize_frames_kernel(const double* _
 }
 
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2, GnGeom g,
-                                const float2* __restrict__ ss, int silu, __nv_bfloat16* __restrict__ out) {
+                                const float2* __restrict__ ss, int silu, __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ raw /* optional: the un-normalised input, narrowed */) {
   const int ns = blockIdx.y;
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
   const int r0 = blockIdx.x * g.rows_per_cta;
@@ -164,6 +165,10 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const void* __restrict
     for (int u = 0; u < 4; ++u) {
       const int rr = r + u * g.rows_par;
       if (rr < r1) {
+        if (raw != nullptr)      // the resblock's 1x1 shortcut reads the raw (concatenated) input as a bf16 GEMM operand
+          *reinterpret_cast<uint4*>(raw + ((long long)ns * g.R + rr) * g.C + v * 8) =
+              make_uint4(pack_bf16x2(f[u][0], f[u][1]), pack_bf16x2(f[u][2], f[u][3]), pack_bf16x2(f[u][4], f[u][5]),
+                         pack_bf16x2(f[u][6], f[u][7]));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float y = fmaf(f[u][i], sc[i], sf[i]);
@@ -448,20 +453,21 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
                                                                  eps, groups, C, R, ss);
   rc = launch_epilogue();
   if (rc) return rc;
-  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out));
+  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out), nullptr);
   return launch_epilogue();
 }
 
 extern "C" int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const double* stats1, const void* x2, int32_t C2,
                                          const double* stats2, int32_t NS, int32_t R, int32_t frames_per_sample,
                                          int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
-                                         int32_t x_f32, void* out, void* workspace, size_t ws_bytes, void* stream) {
+                                         int32_t x_f32, void* out, void* raw_out, void* workspace, size_t ws_bytes,
+                                         void* stream) {
   if (x2 == nullptr) C2 = 0;
   const int C = C1 + C2;
   if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
   if (frames_per_sample <= 0 || R % frames_per_sample || stats1 == nullptr || (x2 != nullptr && stats2 == nullptr))
     return LKGD_ESHAPE;
-  if (!aligned16(x1) || !aligned16(out) || (x2 && !aligned16(x2))) return LKGD_EALIGN;
+  if (!aligned16(x1) || !aligned16(out) || (x2 && !aligned16(x2)) || (raw_out && !aligned16(raw_out))) return LKGD_EALIGN;
   if (ws_bytes < lkgd_groupnorm_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GnGeom g = gn_geom(C1, C2, R, x_f32);
@@ -472,7 +478,8 @@ extern "C" int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const doubl
   int rc = launch_epilogue();
   if (rc) return rc;
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
-  gn_apply_kernel<<<grid, g.vecs * g.rows_par, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out));
+  gn_apply_kernel<<<grid, g.vecs * g.rows_par, 0, st>>>(x1, x2, g, ss, silu, reinterpret_cast<__nv_bfloat16*>(out),
+                                                         reinterpret_cast<__nv_bfloat16*>(raw_out));
   return launch_epilogue();
 }
 

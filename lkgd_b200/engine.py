@@ -284,7 +284,13 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
     """x (and skip) are fp32 stream tensors; returns the fp32 block output."""
     temb_s = cond.temb(p.off_s, p.cout)
     temb_t = cond.temb(p.off_t, p.cout)
-    h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
+    # blocks with a 1x1 shortcut conv need their raw (concatenated) input as a bf16 GEMM operand: the GroupNorm pass
+    # that reads it anyway writes that copy too
+    xa = None
+    if p.wsc is not None:
+        h, xa = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True, want_raw=True)
+    else:
+        h = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True)
     # gn_rows: the epilogue also accumulates the GroupNorm statistics of what it stores (per frame image, channel), so
     # the GroupNorm that consumes the tensor reads it once instead of twice
     h = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=temb_s, rv=g.rv(RV_BATCH),
@@ -293,7 +299,8 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
     if p.wsc is not None:
         # the 1x1 shortcut conv reads the raw input: narrow (and concatenate) it to a bf16 operand and run it as the
         # SECOND K segment of conv2 (centre tap) - one launch, no fp32 shortcut tensor written and read back
-        xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
+        if xa is None:           # no fused statistics for this input (e.g. ControlNet-injected skips): narrow it here
+            xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
         s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2sc, A1=xa, Bw1=p.wsc, out_f32=True,
                      gn_rows=g.HW)
     else:

@@ -160,9 +160,11 @@ def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------- norms
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, NS: int, R: int,
               x2: Optional[torch.Tensor] = None, groups: int = 32, silu: bool = True,
-              out: Optional[torch.Tensor] = None, return_stats: bool = False):
+              out: Optional[torch.Tensor] = None, return_stats: bool = False, want_raw: bool = False):
     """x1 [NS*R, C1] (+ x2 [NS*R, C2]) bf16 or fp32 channels-last -> [NS*R, C1+C2] bf16.
-    ``return_stats``: also return the per-(sample, channel) sums the backward reuses."""
+    ``return_stats``: also return the per-(sample, channel) sums the backward reuses.
+    ``want_raw``: return ``(out, raw)`` where ``raw`` is the un-normalised (concatenated) input narrowed to bf16 - written
+    by the same pass when the statistics come fused from the producers, else ``None`` (the caller narrows it itself)."""
     _need_cuda(x1, x2, gamma, beta)
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
@@ -182,19 +184,22 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     fused = (not return_stats and st1 is not None and (x2 is None or (st2 is not None and st2[1] == st1[1]))
              and R % st1[1] == 0 and st1[0].shape[0] * st1[1] == NS * R)
     if fused:
-        if L.PROF.enabled:   # algorithmic bytes: ONE read of the input + bf16 output
-            L.PROF.meta = {"bytes": NS * R * Ct * (x1.element_size() + 2)}
+        raw = torch.empty((NS * R, Ct), device=x1.device, dtype=bf16) if want_raw else None
+        if L.PROF.enabled:   # algorithmic bytes: ONE read of the input + bf16 output (+ the raw bf16 copy)
+            L.PROF.meta = {"bytes": NS * R * Ct * (x1.element_size() + 2 + (2 if want_raw else 0))}
         L.check(lib.lkgd_groupnorm_from_stats(x1.data_ptr(), C1, st1[0].data_ptr(), _ptr(x2), C2,
                                               st2[0].data_ptr() if x2 is not None else None, NS, R, R // st1[1],
                                               groups, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
-                                              int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
-                                              _stream()), "lkgd_groupnorm_from_stats")
-        return out
+                                              int(x1.dtype == torch.float32), out.data_ptr(), _ptr(raw), ws.data_ptr(),
+                                              ws_bytes, _stream()), "lkgd_groupnorm_from_stats")
+        return (out, raw) if want_raw else out
     if L.PROF.enabled:   # algorithmic bytes: input read twice (statistics, then normalise) + bf16 output
         L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2)}
     L.check(lib.lkgd_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, NS, R, groups, gamma.data_ptr(), beta.data_ptr(),
                                eps, int(silu), int(x1.dtype == torch.float32), out.data_ptr(), ws.data_ptr(), ws_bytes,
                                _stream()), "lkgd_groupnorm")
+    if want_raw:
+        return out, None
     return (out, ws) if return_stats else out
 
 

@@ -331,8 +331,10 @@ def test_gemm_fused_groupnorm_statistics(cuda, mode):
     g2, b2 = rnd(2 * Co, dev=cuda, dtype=torch.float32, seed=7), rnd(2 * Co, dev=cuda, dtype=torch.float32, seed=8)
     other = ops.gemm(A, Wt, bias=bias, out_f32=True, gn_rows=gn_rows, **kw)
     a = ops.groupnorm(plain, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other.clone(), silu=False)
-    f = ops.groupnorm(fused, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other, silu=False)
+    f, raw = ops.groupnorm(fused, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other, silu=False, want_raw=True)
     assert rel_l2(f, a) < 2e-3
+    assert torch.equal(raw, torch.cat([fused, other], 1).to(bf16))       # the shortcut conv's operand, same pass
+    assert ops.groupnorm(plain, g2, b2, 1e-5, NS=B * Fr, R=gn_rows, x2=other.clone(), silu=False, want_raw=True)[1] is None
     ops.axpby(res, 0.5, fused, 1.0)      # an in-place update drops the (now stale) statistics
     assert ops.gn_stats_of(fused) is None
 
