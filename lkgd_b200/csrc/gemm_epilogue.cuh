@@ -29,6 +29,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -83,8 +88,7 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 // GEGLU on NP column pairs in lock step (the Horner chains of the pairs interleave, so no FFMA waits for the previous
 // one): v[i] = (a[i] + bv[i]) * gelu(g[i] + bg[i]).  a / g are accumulator bits, bv / bg point to the tile's bias in smem.
 template <int NP>
-__device__ __forceinline__ void geglu_pairs(const uint32_t* a, const uint32_t* g, const float* bv, const float* bg,
-                                            float* v) {
+__device__ __forceinline__ void geglu_pairs(const uint32_t* a, const uint32_t* g, uint32_t bv, uint32_t bg, float* v) {
   const uint64_t C6 = pk2(2.2999249e-05f, 2.2999249e-05f), C5 = pk2(-6.1149016e-04f, -6.1149016e-04f),
                  C4 = pk2(7.2001889e-03f, 7.2001889e-03f), C3 = pk2(-5.1208213e-02f, -5.1208213e-02f),
                  C2 = pk2(-4.6122226e-01f, -4.6122226e-01f), C1 = pk2(-1.1502144e+00f, -1.1502144e+00f),
@@ -92,8 +96,8 @@ __device__ __forceinline__ void geglu_pairs(const uint32_t* a, const uint32_t* g
   uint64_t V[NP], T[NP], NA[NP], R[NP], P[NP];
 #pragma unroll
   for (int i = 0; i < NP; i += 2) {      // two pairs per 16-byte bias load
-    const float4 b4 = *reinterpret_cast<const float4*>(bv + 2 * i);
-    const float4 g4 = *reinterpret_cast<const float4*>(bg + 2 * i);
+    const float4 b4 = lds_f4(bv + 8 * i);          // shared-space loads (LDS), not generic LD
+    const float4 g4 = lds_f4(bg + 8 * i);
     V[i] = add2(pk2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), pk2(b4.x, b4.y));
     V[i + 1] = add2(pk2(__uint_as_float(a[2 * i + 2]), __uint_as_float(a[2 * i + 3])), pk2(b4.z, b4.w));
     const uint64_t G0 = add2(pk2(__uint_as_float(g[2 * i]), __uint_as_float(g[2 * i + 1])), pk2(g4.x, g4.y));
@@ -152,6 +156,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   const int n_store = min(p.n_store > 0 ? p.n_store : n_cols, out_col_base + bn_out);
   const int nchunks = (bn_out + CW - 1) / CW;
   const long long m = tile_row(p, tc, lane_base + lane);
+  const uint32_t sb_addr = smem_u32(sbias);
   const float* rv = nullptr;
   if (p.rowvec != nullptr && m >= 0)
     rv = p.rowvec + (size_t)rowvec_index(p.rv_mode, (int)m, p.rv_HW, p.rv_F, p.rv_B) * p.rv_ld;
@@ -232,12 +237,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
     // bias of the tile sits in smem (value half, then - GEGLU - the gate half at +bn_out): broadcast LDS.128
     if (GEGLU) {
 #pragma unroll
-      for (int j = 0; j < CW; j += 8)
-        geglu_pairs<4>(a + j, g + (GEGLU ? j : 0), sbias + c * CW + j, sbias + bn_out + c * CW + j, v + j);
+      for (int j = 0; j < CW; j += 16)     // 8 pairs in lock step: +1.2 % over 4 (same-box A/B)
+        geglu_pairs<8>(a + j, g + (GEGLU ? j : 0), sb_addr + (c * CW + j) * 4, sb_addr + (bn_out + c * CW + j) * 4, v + j);
     } else {
 #pragma unroll
       for (int j = 0; j < CW; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * CW + j);
+        const float4 b4 = lds_f4(sb_addr + (c * CW + j) * 4);
         v[j] = __uint_as_float(a[j]) + b4.x;
         v[j + 1] = __uint_as_float(a[j + 1]) + b4.y;
         v[j + 2] = __uint_as_float(a[j + 2]) + b4.z;
