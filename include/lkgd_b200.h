@@ -233,6 +233,14 @@ LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, con
                         float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W,
                         float sigma, float sigma_next, void* stream);
 
+/* Bidirectional "direct fusion" Euler step (pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667,
+ * SURVEY 8f N3): v and x are fp32 [2S, F, C, H, W] (forward samples, then their time-reversed partners), weights fp32
+ * [F] = linspace(1, 0, F).  x0 = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1) per half; the forward half keeps
+ * w[f] x0_fwd[f] + (1-w[f]) x0_bwd[F-1-f], the backward half its frame flip; x_next = x + (x - x0) / sigma *
+ * (sigma_next - sigma).  One launch instead of ~15 elementwise / flip / cat ATen kernels. */
+LKGD_API int lkgd_fusion_euler_step(const float* v, const float* x, const float* weights, float* x_next, int32_t S,
+                   int32_t F, int32_t C, int32_t H, int32_t W, float sigma, float sigma_next, void* stream);
+
 /* ======================================================================================================
  * Training step (LoRA fine-tuning): the backward of the path above.  Reference: train_models/train_svd_lora.py
  * :1445-1689 - EDM preconditioning :1503-1530, loss :1651-1672, accelerator.backward :1683 (PyTorch autograd of the

@@ -244,6 +244,33 @@ __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg
   x_next[idx] = xs + deriv * (sigma_next - sigma);
 }
 
+// Bidirectional ("direct fusion") Euler step of the reference's trans pipelines
+// (pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667): the batch holds a forward half and a
+// time-reversed half; their denoised predictions x0 are blended frame by frame, x0 = w[f] x0_fwd[f] + (1 - w[f])
+// x0_bwd[F-1-f] with w = linspace(1, 0, F), the backward half takes the flipped blend, then both halves take the Euler
+// step.  One thread per (sample, frame, channel, pixel) of the FORWARD half computes both outputs.
+__global__ void fusion_euler_kernel(const float* __restrict__ v, const float* __restrict__ x,
+                                    const float* __restrict__ w, float* __restrict__ x_next, int S, int F, int CHW,
+                                    float sigma, float sigma_next) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long half = (long long)S * F * CHW;
+  if (idx >= half) return;
+  const int e = (int)(idx % CHW);
+  const int f = (int)((idx / CHW) % F);
+  const int s = (int)(idx / ((long long)CHW * F));
+  const long long ib = half + ((long long)s * F + (F - 1 - f)) * CHW + e;   // backward half, mirrored frame
+  const float s2 = sigma * sigma + 1.0f;
+  const float k = -sigma / sqrtf(s2);
+  const float xf = x[idx], xb = x[ib];
+  const float x0f = v[idx] * k + xf / s2;
+  const float x0b = v[ib] * k + xb / s2;
+  const float wf = w[f];
+  const float x0 = x0f * wf + x0b * (1.0f - wf);
+  const float dt = sigma_next - sigma;
+  x_next[idx] = xf + (xf - x0) / sigma * dt;
+  x_next[ib] = xb + (xb - x0) / sigma * dt;
+}
+
 __global__ void axpy_f32_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) y[idx] = fmaf(alpha, x[idx], y[idx]);
@@ -362,6 +389,16 @@ extern "C" int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, c
   const long long total = (long long)S * F * C * H * W;
   cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, S, F,
                                                                   C, H * W, sigma, sigma_next);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_fusion_euler_step(const float* v, const float* x, const float* weights, float* x_next, int32_t S,
+                                      int32_t F, int32_t C, int32_t H, int32_t W, float sigma, float sigma_next,
+                                      void* stream) {
+  if (S <= 0 || F <= 0 || C <= 0 || H <= 0 || W <= 0 || sigma <= 0.f) return LKGD_ESHAPE;
+  const long long half = (long long)S * F * C * H * W;
+  fusion_euler_kernel<<<blocks_for(half, 256), 256, 0, ST(stream)>>>(v, x, weights, x_next, S, F, C * H * W, sigma,
+                                                                     sigma_next);
   return launch_epilogue();
 }
 

@@ -407,6 +407,21 @@ def axpby(x: torch.Tensor, alpha: float, y: torch.Tensor, beta: float) -> torch.
     return y
 
 
+def fusion_euler_step(v: torch.Tensor, x: torch.Tensor, weights: torch.Tensor, sigma: float, sigma_next: float):
+    """Bidirectional Euler step (lkgd_fusion_euler_step): v, x fp32 [2S, F, C, H, W], weights fp32 [F]."""
+    _need_cuda(v, x, weights)
+    if v.dtype != torch.float32 or x.dtype != torch.float32 or v.shape != x.shape or v.dim() != 5 or v.shape[0] % 2 \
+            or not v.is_contiguous() or not x.is_contiguous():
+        raise ValueError("fusion_euler_step: contiguous fp32 [2S, F, C, H, W] tensors of equal shape expected")
+    S2, F, Cn, H, W = v.shape
+    if weights.dtype != torch.float32 or weights.numel() != F or not weights.is_contiguous():
+        raise ValueError("fusion_euler_step: weights must be contiguous fp32 [F]")
+    out = torch.empty_like(x)
+    L.check(L.load().lkgd_fusion_euler_step(v.data_ptr(), x.data_ptr(), weights.data_ptr(), out.data_ptr(), S2 // 2, F,
+                                            Cn, H, W, sigma, sigma_next, _stream()), "lkgd_fusion_euler_step")
+    return out
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 copy (a residual-stream tensor that a GEMM reads raw)."""
     _need_cuda(x)

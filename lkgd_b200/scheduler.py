@@ -192,6 +192,27 @@ class EulerDiscreteScheduler:
             return (prev,)
         return EulerDiscreteSchedulerOutput(prev_sample=prev)
 
+    def step_direct_fusion(self, model_output: torch.Tensor, timestep, sample: torch.Tensor,
+                           generator: Optional[torch.Generator] = None, consume_rng: bool = False) -> torch.Tensor:
+        """The ``direct_fusion`` branch of the reference's trans pipelines
+        (pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667): ``model_output`` / ``sample`` hold the
+        forward samples followed by their time-reversed partners; returns the next latents (one fused kernel).
+        ``consume_rng``: draw the noise tensor the reference draws and never uses (:646-648), for RNG-stream parity."""
+        if self.config.prediction_type != "v_prediction":
+            raise NotImplementedError("the fused CUDA step implements v_prediction (the SVD configuration)")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        if consume_rng:
+            torch.randn(model_output.shape, dtype=model_output.dtype, device=model_output.device, generator=generator)
+        sigma = float(self._sigmas_host[self._step_index])
+        sigma_next = float(self._sigmas_host[self._step_index + 1])
+        F = model_output.shape[1]
+        w = torch.linspace(1, 0, F).to(model_output.device)
+        out = ops.fusion_euler_step(model_output.to(torch.float32).contiguous(), sample.to(torch.float32).contiguous(),
+                                    w, sigma, sigma_next)
+        self._step_index += 1
+        return out.to(model_output.dtype)
+
     def step_cfg_rows(self, pred_rows: torch.Tensor, guidance: Optional[torch.Tensor], sample: torch.Tensor,
                       cfg: bool, want_v: bool = False):
         """Fused CFG combine + Euler update straight from the UNet's channels-last fp32 prediction

@@ -164,6 +164,25 @@ class EulerDiscreteScheduler:
             return (prev,)
         return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
+    def step_direct_fusion(self, model_output, timestep, sample, generator=None):
+        """The ``direct_fusion`` branch of the reference's trans pipelines, restated
+        (``pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667``): forward and time-reversed halves of
+        the batch share one blended denoised prediction."""
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        torch.randn(model_output.shape, dtype=model_output.dtype, generator=generator)     # drawn, never used (:646-648)
+        x0 = model_output * (-sigma / (sigma ** 2 + 1) ** 0.5) + (sample / (sigma ** 2 + 1))          # :655
+        fwd, bwd = x0.chunk(2)
+        w = torch.linspace(1, 0, fwd.shape[1]).to(fwd.device).unsqueeze(0)
+        w = w[(...,) + (None,) * (fwd.ndim - w.ndim)]
+        x0 = fwd * w + bwd.flip(dims=[1]) * (1 - w)                                                  # :661
+        x0 = torch.cat([x0, x0.flip(dims=[1])], dim=0)
+        derivative = (sample - x0) / sigma
+        dt = self.sigmas[self._step_index + 1] - sigma
+        self._step_index += 1
+        return sample + derivative * dt
+
     def add_noise(self, original_samples, noise, timesteps):
         sigmas = self.sigmas.to(device=original_samples.device, dtype=original_samples.dtype)
         sched_t = self.timesteps.to(original_samples.device)

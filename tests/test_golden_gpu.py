@@ -29,6 +29,24 @@ def test_scheduler_kernels_vs_reference_trajectory(cuda, n):
     assert s.step_index == n
 
 
+def test_direct_fusion_step_vs_reference_lines(cuda):
+    """lkgd_fusion_euler_step (one kernel) against the trajectory of the reference's own direct_fusion
+    lines (tests/golden/make_fusion_golden.py); fp32 tolerance of the scheduler: 1e-4 (observed ~1e-7)."""
+    import os
+    from golden_util import HERE
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    FG = np.load(os.path.join(HERE, "golden", "fusion_golden.npz"))["traj"]
+    s = EulerDiscreteScheduler(**SCHED)
+    s.set_timesteps(10, device=cuda)
+    x = (seeded_tensor("fusion/x0", (2, 5, 4, 8, 8)) * s.init_noise_sigma).to(cuda)
+    worst = 0.0
+    for i, ts in enumerate(s.timesteps):
+        x = s.step_direct_fusion(seeded_tensor(f"fusion/v{i}", x.shape).to(cuda), ts, x)
+        worst = max(worst, rel(x, FG[i]))
+    print("direct-fusion worst rel-L2", worst)
+    assert worst < 1e-4 and s.step_index == 10
+
+
 def _product_unet(cuda, cls=None, cfg=REDUCED4, seed=0):
     from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
     cls = cls or UNetSpatioTemporalConditionControlNetModel

@@ -43,6 +43,19 @@ def test_scheduler_trajectory_bit_exact(n):
         x = o.prev_sample
 
 
+def test_direct_fusion_step_matches_reference_lines():
+    """the bidirectional ``direct_fusion`` Euler step against a trajectory produced by executing the
+    reference's own lines (tests/golden/make_fusion_golden.py) - bit-exact in fp32."""
+    FG = np.load(os.path.join(HERE, "golden", "fusion_golden.npz"))["traj"]
+    s = O.EulerDiscreteScheduler(**SCHED)
+    s.set_timesteps(10)
+    x = seeded_tensor("fusion/x0", (2, 5, 4, 8, 8)) * s.init_noise_sigma
+    for i, ts in enumerate(s.timesteps):
+        x = s.step_direct_fusion(seeded_tensor(f"fusion/v{i}", x.shape), ts, x)
+        assert np.array_equal(x.numpy(), FG[i]), i
+    assert s.step_index == 10
+
+
 def test_scheduler_add_noise_and_errors():
     s = O.EulerDiscreteScheduler(**SCHED)
     orig, noise = seeded_tensor("sched/orig", (4, 2, 4, 4, 4)), seeded_tensor("sched/noise", (4, 2, 4, 4, 4))
