@@ -253,6 +253,38 @@ def test_attention_cross_kv_len(cuda):
     assert rel_l2(out.float(), chk.float()) < 6e-3
 
 
+@pytest.mark.parametrize("Nk", [1, 5, 63, 64, 65, 129])
+def test_attention_short_and_ragged_kv(cuda, Nk):
+    """KV lengths around the 64-key step of the softmax pipeline (single partial step, exactly one step, one key over)."""
+    from lkgd_b200 import ops
+    n_img, heads, d, Nq = 2, 2, 64, 200
+    q = rnd(n_img * Nq, heads * d, dev=cuda)
+    k = rnd(n_img * Nk, heads * d, dev=cuda, seed=1)
+    v = rnd(n_img * Nk, heads * d, dev=cuda, seed=2)
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=Nq, Nk=Nk)
+    assert rel_l2(out.float(), _attn_ref(q, k, v, n_img, heads, d, Nq, Nk)) < 6e-3
+
+
+def test_attention_growing_row_maximum_rescales(cuda):
+    """Keys whose scores grow block after block (row maxima rise by far more than the lazy-rescale threshold of 2^8
+    several times, for some rows only): exercises the deferred O rescale in TMEM and the running sum correction."""
+    from lkgd_b200 import ops
+    n_img, heads, d, N = 1, 2, 64, 640
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(n_img * N, heads * d, generator=g)
+    k = torch.randn(n_img * N, heads * d, generator=g)
+    ramp = (torch.arange(N) // 64).float()                     # 10 steps of 64 keys
+    k = k + q.mean(0, keepdim=True) * 0.0                        # keep k random ...
+    k = k * (1.0 + 0.9 * ramp)[:, None]                          # ... but ever larger: later blocks dominate
+    q[: N // 2] *= 3.0                                           # half of the rows see steeper growth than the others
+    v = torch.randn(n_img * N, heads * d, generator=g)
+    q, k, v = (t.to(torch.bfloat16).to(cuda) for t in (q, k, v))
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N)
+    ref = _attn_ref(q, k, v, n_img, heads, d, N, N)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) < 8e-3
+
+
 def test_attention_svd_l0_vs_checker(cuda):
     from lkgd_b200 import ops
     n_img, heads, d, N = 1, 5, 64, 9216
