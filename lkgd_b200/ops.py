@@ -121,7 +121,7 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     fn = lib.lkgd_gemm_simt_check if checker else lib.lkgd_gemm
     stats = None
     if gn_rows > 0 and not checker and not os.environ.get("LKGD_NO_FUSED_GN"):   # switch: A/B measurements only
-        stats = torch.zeros((M // gn_rows, N, 2), device=A.device, dtype=torch.float64)
+        stats = STATS_ARENA.take(M // gn_rows, N, A.device)
         a.gn_stats, a.gn_rows = stats.data_ptr(), gn_rows
     if L.PROF.enabled:
         L.PROF.meta = {"flops": 2.0 * M * N * (taps * a.K0 + a.K1), "mode": mode, "M": M, "N": N,
@@ -129,6 +129,37 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     L.check(fn(C.byref(a), _stream()), "lkgd_gemm")
     _set_gn_stats(out, stats, gn_rows)
     return out
+
+
+class _StatsArena:
+    """One zeroed fp64 buffer per forward for all fused GroupNorm statistics (a C3 step has ~105 producers: one memset
+    instead of 105 fill launches).  ``begin`` is called at the start of a forward; slices are valid until the next
+    ``begin`` on the same stream.  Falls back to ``torch.zeros`` when it is not active or too small (it then grows at
+    the next ``begin``)."""
+
+    def __init__(self):
+        self.buf, self.off, self.want = None, 0, 8 << 20      # doubles
+
+    def begin(self, device) -> None:
+        if self.buf is None or self.buf.device != device or self.buf.numel() < self.want:
+            self.buf = torch.empty(self.want, device=device, dtype=torch.float64)
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, frames: int, n: int, device) -> torch.Tensor:
+        need = frames * n * 2
+        if self.buf is None or self.buf.device != device:
+            return torch.zeros((frames, n, 2), device=device, dtype=torch.float64)
+        if self.off + need > self.buf.numel():
+            self.want = max(self.want, 2 * (self.off + need))
+            self.off += need                                   # keep counting so that `want` covers the whole forward
+            return torch.zeros((frames, n, 2), device=device, dtype=torch.float64)
+        out = self.buf[self.off:self.off + need].view(frames, n, 2)
+        self.off += need
+        return out
+
+
+STATS_ARENA = _StatsArena()
 
 
 def _set_gn_stats(t: torch.Tensor, stats: Optional[torch.Tensor], gn_rows: int = 0) -> None:

@@ -306,6 +306,7 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
         if added_time_ids is None:
             raise ValueError("added_time_ids is required")
         pk = self.packed()
+        ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         ctx_all = self._context(encoder_hidden_states, *extra)
         ids = added_time_ids.to(x.device)
         ctx_t = None
@@ -754,6 +755,7 @@ class ControlNetSDVModel(_Base):
                        conditioning_scale: float = 1.0):
         """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
         pk = self.packed()
+        ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         convs, zero = self._cn_pack()
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
         cond = Conditioning(pk, emb, encoder_hidden_states.to(torch.float32).contiguous())
