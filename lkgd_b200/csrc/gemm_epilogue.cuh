@@ -319,9 +319,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
         // over them with a halving butterfly (7 shuffles) that leaves ONE of the 8 totals in each lane, which then
         // issues one fp64 atomic: 32 atomics per 32 x 16 chunk.
         float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 us[PO];
+#pragma unroll
+        for (int j = 0; j < PO; ++j) us[j] = lds128(buf + o_co + 512 * j);     // all loads first (see below)
 #pragma unroll
         for (int j = 0; j < PO; ++j) {
-          const uint4 u = lds128(buf + o_co + 512 * j);
+          const uint4 u = us[j];
           const bool ok = col_ok && orow[j] != nullptr;
           if (ok) *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = u;
           const float x0 = ok ? __uint_as_float(u.x) : 0.f, x1 = ok ? __uint_as_float(u.y) : 0.f,
@@ -350,10 +353,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
             atomicAdd(p.gn_stats + ((size_t)frame * n_cols + col) * 2 + (lane >> 4), (double)w[0]);
         }
       } else {
+        // every LDS is issued before the first store: with the load inside the predicated store the compiler emitted
+        // LDS -> STG -> (branch) -> LDS into the SAME registers -> STG ..., paying the shared-memory latency three times
+        // per chunk and a write-after-read wait on the store's operand read (20 % of the samples of the qkv L0 launch)
+        uint4 us[PO];
+#pragma unroll
+        for (int j = 0; j < PO; ++j) us[j] = lds128(buf + o_co + 512 * j);
 #pragma unroll
         for (int j = 0; j < PO; ++j) {
-          if (col_ok && orow[j] != nullptr)
-            *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = lds128(buf + o_co + 512 * j);
+          if (col_ok && orow[j] != nullptr) *reinterpret_cast<uint4*>(orow[j] + (size_t)n_out * OES) = us[j];
         }
       }
       __syncwarp();            // staging buffer free again (next prefetch may overwrite it)
