@@ -265,6 +265,14 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         spatial = self.quaternion_lora_fuse(torch.cat([lh, ld, lf, texts], -1))                     # [B,1,512]
 
         ffts = [torch.fft.rfft(v, dim=-1) for v in (lh, ld, lf)]                                    # [B,1,129]
+        if getattr(self, "canonical_zero_phase", False):
+            # The unconditional CFG half feeds an all-zero CLIP embedding (pipeline...controlnet.py:206-212), so ``lh`` is
+            # exactly zero there and the phase fed to ``fuse_fft_pha`` is the angle of 0 + 0j - decided by the SIGN of the
+            # zeros the FFT library returns: torch's CPU backend (pocketfft) returns -0 real parts in 63 of the 129 bins
+            # (angle = pi), cuFFT - what the reference runs on the GPU - returns +0 everywhere (angle = 0; checked on a
+            # B200, tests/test_unet_gpu.py::test_lkgd_zero_embedding_follows_the_gpu_fft).  Default: this module's CPU
+            # behaviour, bit for bit.  With the switch set the zeros are canonicalised to +0 = the GPU reference.
+            ffts = [torch.complex(v.real + 0.0, v.imag + 0.0) for v in ffts]
         mags = [torch.abs(v) for v in ffts] + [self.quaternion_lora_texts_fft_mag.expand(ffts[0].shape)]
         phas = [torch.angle(v) for v in ffts] + [self.quaternion_lora_texts_fft_pha.expand(ffts[0].shape)]
         mag = self.quaternion_lora_fuse_fft_mag(torch.cat([m[..., :-1] for m in mags], -1))          # [B,1,256]

@@ -199,6 +199,41 @@ def test_lkgd_unet_parity(cuda):
     assert rel_l2(got_m, got) < 1e-2
 
 
+def test_lkgd_zero_embedding_follows_the_gpu_fft(cuda):
+    """The unconditional CFG half has an all-zero CLIP embedding: the latent-knowledge block then takes the phase of an
+    all-zero spectrum, which is the sign of the FFT library's zeros - pi in 63 bins on torch's CPU FFT, 0 on cuFFT (the
+    reference's GPU arithmetic).  The CUDA path must equal the reference's modules RUN ON THE GPU (the oracle's
+    conditioning block moved to cuda: conv1d + cuFFT + the same linears), and the CPU oracle with
+    ``canonical_zero_phase`` (zeros canonicalised to +0)."""
+    import copy
+    import oracle as O
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionModel
+    cfg = dict(REDUCED_CONFIG, cross_attention_dim=1024)
+    o, p = _pair(O.UNetSpatioTemporalConditionModel, UNetSpatioTemporalConditionModel, cfg, cuda)
+    g = torch.Generator().manual_seed(11)
+    ctx = torch.cat([torch.zeros(1, 1, 1024), torch.randn(1, 1, 1024, generator=g)])      # [uncond = 0 | cond]
+    dom, flo = torch.randn(1, 1, 1000, generator=g), torch.randn(1, 1, 1000, generator=g)
+    z = torch.fft.rfft(torch.zeros(1, 1, 256, device=cuda), dim=-1)
+    assert not torch.signbit(z.real).any() and not torch.signbit(z.imag).any()           # cuFFT: +0 everywhere
+    got = p._context(ctx.to(cuda), dom.to(cuda), flo.to(cuda))
+    with torch.no_grad():
+        ref_gpu = copy.deepcopy(o).to(cuda)._condition(ctx.to(cuda), dom.to(cuda), flo.to(cuda))
+        ref_cpu = o._condition(ctx, dom, flo)
+        o.canonical_zero_phase = True
+        ref_canon = o._condition(ctx, dom, flo)
+    for row in range(2):
+        assert rel_l2(got[row], ref_gpu[row]) < 1e-5, row
+        assert rel_l2(got[row], ref_canon[row]) < 1e-5, row
+    print("zero-embedding row: CPU-FFT reference differs from the GPU-FFT reference by", rel_l2(ref_cpu[0], ref_gpu[0]))
+    x, _, ids = _inputs(cfg, 2, 8, 32, 32, 1024)
+    with torch.no_grad():
+        ref = o(x, 1.3, ctx, dom, flo, added_time_ids=ids, return_dict=False)[0]
+    out = p(x.to(cuda), 1.3, ctx.to(cuda), dom.to(cuda), flo.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(out, ref)
+    print("lkgd unet, zero uncond embedding, rel_l2", err)
+    assert err < 1e-2
+
+
 def test_sampling_loop_parity(cuda):
     """3 CFG Euler-Karras steps: fp32 scheduler/CFG kernel <= 1e-4 given the same prediction; trajectory <= 2e-2."""
     import oracle as O
