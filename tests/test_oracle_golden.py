@@ -172,6 +172,24 @@ def test_lkgd_conditioning_matches_reference():
     assert rel(a2, G["lkgd/out_b2"]) < 1e-5
 
 
+def test_lkgd_zero_embedding_phase_switch_only_touches_exact_zeros():
+    """oracle.UNetSpatioTemporalConditionModel.canonical_zero_phase: for a non-zero embedding the conditioning is
+    unchanged bit for bit; for the all-zero embedding of the unconditional CFG half it replaces the CPU FFT's -0 real
+    parts (phase pi in 63 bins) by +0 (phase 0, what cuFFT returns) - see the GPU test of the same name family."""
+    import oracle as O
+    o = fill_seeded_(O.UNetSpatioTemporalConditionModel(**dict(REDUCED4, cross_attention_dim=1024))).eval()
+    ctx = torch.cat([torch.zeros(1, 1, 1024), seeded_tensor("lkgd/ctx", (1, 1, 1024))])
+    dom, flo = seeded_tensor("lkgd/domain", (1, 1, 1000)), seeded_tensor("lkgd/flow", (1, 1, 1000))
+    with torch.no_grad():
+        a = o._condition(ctx, dom, flo)
+        o.canonical_zero_phase = True
+        b = o._condition(ctx, dom, flo)
+    assert torch.equal(a[1], b[1])                      # generic spectrum: nothing to canonicalise
+    z = torch.fft.rfft(torch.zeros(256))
+    if torch.signbit(z.real).any():                     # this torch build's CPU FFT has the artefact
+        assert not torch.equal(a[0], b[0])
+
+
 def test_controlnet_matches_reference():
     cfg = {k: v for k, v in REDUCED4.items() if k != "up_block_types"}
     o = fill_seeded_(O.ControlNetSDVModel(**cfg, conditioning_channels=2), seed=1).eval()
