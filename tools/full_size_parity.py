@@ -102,7 +102,7 @@ else:
 t_ref = time.time() - t1
 d = (got.double().cpu() - ref.double())
 rel = float(d.norm() / ref.double().norm())
-res = dict(config=f"SVD-XT LKGD UNet, LoRA r={a.rank}, {a.frames} frames {a.h}x{a.w} latents, CFG batch 2, fp32 CPU oracle vs CUDA path",
+res = dict(config=f"SVD-XT {'plain' if a.plain else 'LKGD'} UNet, LoRA r={a.rank}, {a.frames} frames {a.h}x{a.w} latents, CFG batch 2, fp32 CPU oracle vs CUDA path",
            rel_l2=rel, max_abs=float(d.abs().max()), ref_rms=float(ref.double().pow(2).mean().sqrt()),
            finite=bool(torch.isfinite(got).all()), tolerance=1e-2, oracle_seconds=round(t_ref, 1),
            build_seconds=round(t_build, 1), host_threads=torch.get_num_threads())
