@@ -223,8 +223,10 @@ class TransformerSpatioTemporalModel(nn.Module):
         frame_idx = torch.arange(f, device=x.device).repeat(b, 1).reshape(-1)
         emb = self.time_pos_embed(timestep_embedding(frame_idx, self.in_channels).to(x.dtype))[:, None, :]
         for blk, tblk in zip(self.transformer_blocks, self.temporal_transformer_blocks):
-            x = blk(x, encoder_hidden_states)
-            xm = tblk(x + emb, f, time_context)
+            # keyword calls, as diffusers does: the reference's patched forwards (patch/patch.py:390-399, :582-587)
+            # take (hidden_states, attention_mask, encoder_hidden_states, ...) positionally
+            x = blk(x, encoder_hidden_states=encoder_hidden_states)
+            xm = tblk(x + emb, num_frames=f, encoder_hidden_states=time_context)
             x = self.time_mixer(x, xm, image_only_indicator)
         x = self.proj_out(x)
         x = x.reshape(bf, h, w, c).permute(0, 3, 1, 2).contiguous()

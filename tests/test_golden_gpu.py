@@ -53,6 +53,21 @@ def _product_unet(cuda, cls=None, cfg=REDUCED4, seed=0):
     return fill_seeded_(cls(**cfg), seed=seed).to(cuda)
 
 
+def test_unet_vs_reference_with_patched_blocks(cuda):
+    """CUDA path vs the reference UNet whose transformer blocks ran the reference's own forwards (patch/patch.py:390-686
+    via apply_patch, joint attention off) on torch-primitive blocks - a golden with no oracle block arithmetic in the
+    transformer blocks (tests/golden/make_patch_golden.py)."""
+    import os
+    from golden_util import HERE
+    PG = np.load(os.path.join(HERE, "golden", "patch_golden.npz"))
+    p = _product_unet(cuda)
+    sample, ctx, ids = (v.to(cuda) for v in unet_inputs())
+    a = p(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0]
+    err = rel(a, PG["patch/unet_out"])
+    print("rel-L2 vs patched-reference UNet", err)
+    assert err < 1e-2
+
+
 def test_unet_vs_reference(cuda):
     p = _product_unet(cuda)
     sample, ctx, ids = (v.to(cuda) for v in unet_inputs())

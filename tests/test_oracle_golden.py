@@ -117,6 +117,40 @@ def test_unet_forward_matches_reference():
     assert int(G["unet/n_params"]) == sum(p.numel() for p in o.parameters())
 
 
+PG = np.load(os.path.join(HERE, "golden", "patch_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,dim,heads,dh,xdim", [("d16", 32, 2, 16, 32), ("d64", 128, 2, 64, 48)])
+def test_transformer_blocks_match_the_references_own_forwards(tag, dim, heads, dh, xdim):
+    """The oracle's BasicTransformerBlock / TemporalBasicTransformerBlock against vectors produced by executing the
+    reference's in-tree restatement of those forwards (patch/patch.py:390-580 and :582-686 through apply_patch, joint
+    attention off) on blocks built from plain torch primitives + F.scaled_dot_product_attention - no oracle arithmetic
+    on the golden side (tests/golden/make_patch_golden.py)."""
+    BF, N, Fr = 8, 24, 4
+    x = seeded_tensor(f"patch/{tag}/x", (BF, N, dim))
+    sb = fill_seeded_(O.BasicTransformerBlock(dim, heads, dh, xdim), seed=11).eval()
+    tb = fill_seeded_(O.TemporalBasicTransformerBlock(dim, dim, heads, dh, xdim), seed=12).eval()
+    with torch.no_grad():
+        a = sb(x, encoder_hidden_states=seeded_tensor(f"patch/{tag}/ctx", (BF, 1, xdim)))
+        a3 = sb(x, encoder_hidden_states=seeded_tensor(f"patch/{tag}/ctx3", (BF, 3, xdim)))
+        b = tb(x, num_frames=Fr, encoder_hidden_states=seeded_tensor(f"patch/{tag}/tctx", ((BF // Fr) * N, 1, xdim)))
+    assert rel(a, PG[f"patch/spatial_{tag}"]) < 1e-6
+    assert rel(a3, PG[f"patch/spatial_{tag}_kv3"]) < 1e-6
+    assert rel(b, PG[f"patch/temporal_{tag}"]) < 1e-6
+
+
+def test_unet_matches_the_reference_unet_with_patched_blocks():
+    """Whole reduced UNet: the reference's UNet file with all 12 transformer blocks driven by the reference's own
+    patch/patch.py forwards (independent block internals) == the oracle, and == the golden made with oracle blocks."""
+    o = _oracle_unet()
+    sample, ctx, ids = unet_inputs()
+    with torch.no_grad():
+        a = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids, return_dict=False)[0]
+    assert int(PG["patch/n_blocks"]) == 12
+    assert rel(a, PG["patch/unet_out"]) < 2e-6
+    assert rel(G["unet/out"], PG["patch/unet_out"]) < 2e-6
+
+
 def test_flow_stem_unet_matches_reference():
     """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
     by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""
