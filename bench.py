@@ -29,13 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (unet config key, frames, h, w, lora rank, lkgd)
-    "C3": ("svd_xt", 25, 72, 128, 64, True),
-    "C2": ("svd_xt", 14, 72, 128, 0, False),
-    "C1": ("reduced", 8, 32, 32, 0, False),
+    # name: (unet config key, frames, h, w, lora rank, lkgd)           BASELINE.json configs[i]
+    "C3": ("svd_xt", 25, 72, 128, 64, True),        # [2] headline: SVD-XT 25f + LoRA r=64 + LKGD conditioning
+    "C2": ("svd_xt", 14, 72, 128, 0, False),        # [1] SVD 14f
+    "C4": ("svd_xt", 14, 72, 128, 0, False),        # [3] C2 + ControlNetSDVModel (flow condition, 2 channels)
+    "C4d": ("svd_xt", 14, 72, 128, 0, False),       # [3] ... depth condition, 3 channels
+    "C1": ("reduced", 8, 32, 32, 0, False),         # [0] reduced config
     # LoRA fine-tuning step (BASELINE.json configs[4]): forward + backward + clip + AdamW, 14 frames 320x512, b=1 / GPU
     "C5": ("svd_xt", 14, 40, 64, 64, True),
 }
+CONTROLNET_CHANNELS = {"C4": 2, "C4d": 3}
 
 
 def peaks():
@@ -91,26 +94,29 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_inputs(S, F, h, w, lkgd, device="cpu", seed=0):
+def synth_inputs(S, F, h, w, lkgd, device="cpu", seed=0, xdim=1024):
     """latents ~ N(0,1) (scaled by init_noise_sigma later), image_latents ~ N(0,1) with a zero uncond
     half, CLIP embedding ~ N(0,1) with a zero uncond half, domain / flow features ~ N(0,1)."""
     g = torch.Generator().manual_seed(seed)
     noise = torch.randn(S, F, 4, h, w, generator=g)
     cond_lat = torch.randn(S, 1, 4, h, w, generator=g).repeat(1, F, 1, 1, 1)
     image_latents = torch.cat([torch.zeros_like(cond_lat), cond_lat])
-    emb = torch.randn(S, 1, 1024, generator=g)
+    emb = torch.randn(S, 1, xdim, generator=g)
     image_embeddings = torch.cat([torch.zeros_like(emb), emb])
     extra = (torch.randn(1, 1, 1000, generator=g), torch.randn(1, 1, 1000, generator=g)) if lkgd else ()
     return noise, image_latents, image_embeddings, extra
 
 
-def init_weights_(model, seed=0):
+def init_weights_(model, seed=0, zero_conv_std=None):
     """Default-initialiser-equivalent random weights generated directly on the GPU (no checkpoints exist here);
     zero-inits that would hide work are overridden as in SURVEY 8(d)."""
     g = torch.Generator(device="cuda").manual_seed(seed)
     with torch.no_grad():
         for n, p in model.named_parameters():
-            if n.endswith("mix_factor"):
+            if zero_conv_std and ("controlnet_down_blocks" in n or "controlnet_mid_block" in n
+                                  or "controlnet_cond_embedding.conv_out" in n):
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda") * zero_conv_std)   # zero convs (SURVEY 8d)
+            elif n.endswith("mix_factor"):
                 p.copy_(torch.rand(p.shape, generator=g, device="cuda") * 2 - 1)
             elif "lora_B" in n or n.startswith("quaternion_lora_texts"):
                 p.copy_(torch.randn(p.shape, generator=g, device="cuda") * 0.02)
@@ -144,14 +150,42 @@ def build_ours(workload, device):
     unet = unet.to_empty(device=device)
     init_weights_(unet)
     unet.invalidate()
-    pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))
+    cn = None
+    if workload in CONTROLNET_CHANNELS:
+        from lkgd_b200.unet import ControlNetSDVModel
+        with torch.device("meta"):
+            cn = ControlNetSDVModel(**{k: v for k, v in cfg.items() if k != "up_block_types"},
+                                    conditioning_channels=CONTROLNET_CHANNELS[workload])
+        cn = cn.to_empty(device=device)
+        init_weights_(cn, seed=1, zero_conv_std=0.02)
+        cn.invalidate()
+    pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG), controlnet=cn)
     return pipe, cfg, (F, h, w, rank, lkgd)
 
 
 def workload_desc(workload):
     key, F, h, w, lrank, lkgd = CONFIGS[workload]
+    cn = CONTROLNET_CHANNELS.get(workload)
     return (f"{workload}: SVD-XT CFG denoise step, {F} frames 576x1024 ({h}x{w} latents), CFG batch 2, LoRA r={lrank} "
-            f"folded in the temporal qkv GEMMs, LKGD cond={lkgd}; 1 sample per GPU")
+            f"folded in the temporal qkv GEMMs, LKGD cond={lkgd}"
+            + (f", ControlNetSDVModel ({cn}-channel condition at 576x1024) + residual injection" if cn else "")
+            + "; 1 sample per GPU")
+
+
+def step_flops(workload, cfg, F, h, w, lrank, as_reference=False):
+    """Algorithmic FLOPs of one denoise step.  ``as_reference``: count the KV-length-1 cross-attention as the reference
+    executes it (to_q / to_k / per-token to_out); default: what the CUDA path executes."""
+    from lkgd_b200.flops import controlnet_flops, unet_flops
+    f = unet_flops(cfg, 2, F, h, w, lora_rank=lrank, count_dead_cross_attn=as_reference)["total"]
+    if workload in CONTROLNET_CHANNELS:
+        f += controlnet_flops(cfg, 2, F, h, w, CONTROLNET_CHANNELS[workload], count_dead_cross_attn=as_reference)["total"]
+    return f
+
+
+def synth_controlnet_cond(workload, F, h, w, seed=0):
+    """controlnet_cond ~ U(-1, 1) [F, Cc, 8h, 8w] (the pipeline duplicates it for CFG)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.rand(F, CONTROLNET_CHANNELS[workload], 8 * h, 8 * w, generator=g) * 2 - 1
 
 
 def gemm_traffic():
@@ -167,59 +201,84 @@ def gemm_traffic():
         return None
 
 
-def cpu_oracle_rate(workload, max_seconds=40.0, iters=4):
-    """Times the oracle (fp32 PyTorch, eager, all host threads) on a BOUNDED sample of the workload: the same
-    full-width UNet on a reduced frame count / latent size, scaled to denoise steps/s by algorithmic FLOPs."""
+def _build_oracle(workload, Fs):
+    """fp32 CPU oracle of the workload's modules (UNet [+ LoRA] [+ ControlNet]) with random weights."""
     import oracle as O
-    from lkgd_b200.flops import unet_flops
     from lkgd_b200.unet import REDUCED_CONFIG, SVD_XT_CONFIG
     key, F, h, w, rank, lkgd = CONFIGS[workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = dict(SVD_XT_CONFIG if key == "svd_xt" else REDUCED_CONFIG)
-    if key == "svd_xt":
-        Fs, hs, ws = 2, 16, 16          # sample: full-width SVD-XT UNet, CFG batch 2, 2 frames, 16x16 latents
-    else:
-        Fs, hs, ws = F, h, w
-    cfg["num_frames"] = Fs
+    cfg = dict(SVD_XT_CONFIG if key == "svd_xt" else REDUCED_CONFIG, num_frames=Fs)
     if lkgd:
         cfg["cross_attention_dim"] = 1024
     cls = O.UNetSpatioTemporalConditionModel if lkgd else O.UNetSpatioTemporalConditionControlNetModel
     torch.manual_seed(0)
-    t0 = time.time()
     with torch.device("meta"):
         model = cls(**cfg)
         if rank:
             O.add_lora(model, rank)
-    model = model.to_empty(device="cpu")
+        cn = None
+        if workload in CONTROLNET_CHANNELS:
+            cn = O.ControlNetSDVModel(**{k: v for k, v in cfg.items() if k != "up_block_types"},
+                                      conditioning_channels=CONTROLNET_CHANNELS[workload])
+    mods = [model.to_empty(device="cpu")] + ([cn.to_empty(device="cpu")] if cn is not None else [])
     with torch.no_grad():
-        for p in model.parameters():
-            p.uniform_(-0.02, 0.02)
-    model.eval()
+        for m in mods:
+            for p in m.parameters():
+                p.uniform_(-0.02, 0.02)
+            m.eval()
+    return cfg, mods[0], (mods[1] if cn is not None else None)
+
+
+def cpu_oracle_rate(workload, max_seconds=40.0, iters=4, full_size=False):
+    """Times the oracle (fp32 PyTorch, eager, all host threads) on the host cores.
+
+    ``full_size=False`` (the `cpu_baseline` leg of our own line: ~10-30 s): a BOUNDED sample - the same full-width
+    modules at 2 frames of 16x16 latents - scaled to the workload by algorithmic FLOPs; labelled ``extrapolated``.
+    ``full_size=True`` (the `--impl reference` arm): ONE real step of the workload itself (25 / 14 frames, 72x128
+    latents, CFG batch 2: ~160 / 90 / 123 TFLOP of eager fp32, minutes), nothing scaled."""
+    import oracle as O
+    key, F, h, w, rank, lkgd = CONFIGS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if full_size or key != "svd_xt":
+        Fs, hs, ws = F, h, w
+    else:
+        Fs, hs, ws = 2, 16, 16          # sample: full-width SVD-XT UNet, CFG batch 2, 2 frames, 16x16 latents
+    t0 = time.time()
+    cfg, model, cn = _build_oracle(workload, Fs)
     build_s = time.time() - t0
-    noise, img_lat, emb, extra = synth_inputs(1, Fs, hs, ws, lkgd)
+    noise, img_lat, emb, extra = synth_inputs(1, Fs, hs, ws, lkgd, xdim=cfg["cross_attention_dim"])
     sched = O.EulerDiscreteScheduler(**O.scheduler.SVD_SCHEDULER_CONFIG)
     sched.set_timesteps(25)
     ids = O.add_time_ids_inference(6, 127, 0.02, 1)
     lat = noise * sched.init_noise_sigma
+    kw = {}
+    if cn is not None:
+        cc = synth_controlnet_cond(workload, Fs, hs, ws).unsqueeze(0)
+        kw = dict(controlnet=cn, controlnet_cond=torch.cat([cc, cc]))       # the pipeline duplicates it for CFG (D3)
     times = []
     t_start = time.time()
-    for it in range(max(2, iters)):
+    for it in range(1 if full_size else max(2, iters)):
         sched._step_index = None
         t1 = time.time()
-        O.denoise_loop(model, sched, lat, img_lat, emb, ids, 25, 1.0, 3.0, unet_extra_args=extra, max_steps=1)
+        O.denoise_loop(model, sched, lat, img_lat, emb, ids, 25, 1.0, 3.0, unet_extra_args=extra, max_steps=1, **kw)
         times.append(time.time() - t1)
         if time.time() - t_start > max_seconds:
             break
     t_step = min(times[1:]) if len(times) > 1 else times[0]
-    f_sample = unet_flops(cfg, 2, Fs, hs, ws, lora_rank=rank)["total"]
-    f_full = unet_flops(dict(cfg, num_frames=F), 2, F, h, w, lora_rank=rank)["total"]
+    f_sample = step_flops(workload, cfg, Fs, hs, ws, rank, as_reference=True)
+    f_full = step_flops(workload, dict(cfg, num_frames=F), F, h, w, rank, as_reference=True)
     value = (1.0 / t_step) * (f_sample / f_full)
-    return dict(value=value, unit="denoise_steps/s", cores=cores, kind="port",
-                sample=(f"oracle (fp32 PyTorch eager, {cores} threads) full-width UNet CFG step at {Fs} frames "
-                        f"{hs}x{ws} latents: {t_step:.2f} s/step = {f_sample / t_step / 1e12:.3f} TFLOP/s; scaled to the "
-                        f"{F}f {h}x{w} step by algorithmic FLOPs ({f_sample / 1e12:.2f} vs {f_full / 1e12:.1f} TFLOP); "
-                        f"model build {build_s:.0f} s not timed")), t_step
+    what = (f"oracle (fp32 PyTorch eager, {cores} threads), full-width modules, one CFG denoise step at {Fs} frames "
+            f"{hs}x{ws} latents: {t_step:.2f} s/step = {f_sample / t_step / 1e12:.3f} TFLOP/s")
+    if full_size or key != "svd_xt":
+        what += "; this IS the workload's size - measured, not scaled"
+    else:
+        what += (f"; EXTRAPOLATED to the {F}f {h}x{w} step by algorithmic FLOPs ({f_sample / 1e12:.2f} vs "
+                 f"{f_full / 1e12:.1f} TFLOP as the reference executes them)")
+    what += f"; model build {build_s:.0f} s not timed"
+    return dict(value=value, unit="denoise_steps/s", cores=cores, kind="port", sample=what,
+                extrapolated=not (full_size or key != "svd_xt"), timed_steps=len(times),
+                seconds_per_timed_step=t_step), t_step
 
 
 def train_flops(cfg, B, F, h, w, rank):
@@ -362,19 +421,28 @@ def run_train(args):
 
 
 def run_reference(args):
+    """The reference's CPU path on the host cores: ONE real, full-size denoise step of the oracle port (the reference
+    itself cannot be installed here: diffusers 0.27.2 / peft / core_qnn are absent).  ``steps`` / ``warmup`` of the
+    printed line say what was actually timed (1 / 0): a full-size step is minutes of CPU work, so K steps are not run;
+    ``--ref-sample`` switches to the bounded, FLOP-scaled sample (seconds) and labels the line ``extrapolated``."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" is one bounded sample (full-width UNet, CFG batch 2, 2 frames of 16x16 latents); W untimed + K timed
-    cb, t_step = cpu_oracle_rate(args.workload, max_seconds=150.0, iters=min(args.warmup, 1) + min(args.steps, 6))
-    key, F, h, w, lrank, lkgd = CONFIGS[args.workload]
+    if args.workload == "C5":
+        args.workload = "C3"
+    full = not args.ref_sample
+    cb, t_step = cpu_oracle_rate(args.workload, max_seconds=150.0, iters=3, full_size=full)
     line = {
         "impl": "reference", "metric": "denoise_steps_per_s", "value": cb["value"], "unit": "denoise_steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "n_gpus": args.gpus, "steps": cb["timed_steps"] if full else args.steps, "warmup": 0 if full else args.warmup,
+        "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "extrapolated": cb["extrapolated"],
         "config": {"workload": workload_desc(args.workload),
                    "reference_arm": "the reference's CPU PyTorch path (fp32 oracle port; the reference itself cannot be "
-                                    "installed: no diffusers/peft/core_qnn), every step a bounded sample, FLOP-scaled"},
+                                    "installed: no diffusers/peft/core_qnn). " +
+                                    ("ONE real full-size step timed (steps=1, warmup=0: minutes of CPU per step)" if full
+                                     else "every step a bounded sample, FLOP-scaled (extrapolated)")},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "denoise_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -390,6 +458,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", action="store_true",
+                    help="--impl reference: time the bounded 2-frame 16x16 sample (seconds, FLOP-scaled) instead of one "
+                         "real full-size step (minutes)")
+    ap.add_argument("--no-extra-sections", action="store_true",
+                    help="N >= 2: skip the CFG-pair-split and data-parallel C5 sections after the sample-sharded timing")
     ap.add_argument("--no-graph", action="store_true", help="C5: run the training step eagerly (no CUDA graph replay)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel event breakdown to this JSON file")
     ap.add_argument("--profiler-step", action="store_true",
@@ -411,13 +484,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from lkgd_b200 import _lib, ops
-    from lkgd_b200.flops import unet_flops
     ops.device_check(local)
 
     pipe, cfg, (F, h, w, lrank, lkgd) = build_ours(args.workload, device)
     S = 1   # one initial-frame sample per GPU (weak scaling: every rank denoises its own sample)
-    noise, img_lat, emb, extra = synth_inputs(S, F, h, w, lkgd, seed=rank)
+    noise, img_lat, emb, extra = synth_inputs(S, F, h, w, lkgd, seed=rank, xdim=cfg["cross_attention_dim"])
     kw = dict(domain_features=extra[0], flow_features=extra[1]) if lkgd else {}
+    if args.workload in CONTROLNET_CHANNELS:
+        kw["controlnet_condition"] = synth_controlnet_cond(args.workload, F, h, w, seed=rank)
     st = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, **kw)
     lat0 = (noise * pipe.scheduler.init_noise_sigma).to(device)
     n_sig = 25
@@ -429,23 +503,29 @@ def main():
 
     # ---------------------------------------------------------------- device-resident timing
     lat = lat0
+    l0 = ops.launch_count()
+    lat, _ = pipe.denoise_step(st, 0, lat)               # eager: lazy weight packing, one-time kernel attributes
+    launches_per_step = ops.launch_count() - l0          # a CUDA-graph replay re-issues exactly these launches
+    graphed = False
+    if not args.no_graph and hasattr(pipe, "capture"):
+        pipe.capture(st, lat0)
+        graphed = True
     for i in range(args.warmup):
         lat, _ = pipe.denoise_step(st, i % n_sig, lat)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = ops.launch_count()
+    sampler_all = ClockSampler(local)
+    sampler_all.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         lat, _ = pipe.denoise_step(st, (args.warmup + i) % n_sig, lat)
     e1.record()
+    host_ms = (time.perf_counter() - t_host0) * 1e3      # time the host spent ISSUING the K steps (launch path)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     finite = bool(torch.isfinite(lat).all())
 
     # ---------------------------------------------------------------- end to end through the public API
@@ -457,10 +537,13 @@ def main():
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    lat_d = torch.empty_like(lat0)
     for i in range(args.steps):
-        lat_d = pin_noise.to(device, non_blocking=True)
-        st["image_latents"] = pin_img.to(device, non_blocking=True)
-        st["image_embeddings"] = pin_emb.to(device, non_blocking=True)
+        # this step's inputs come from pinned host memory into the step's static device buffers (the CUDA graph reads
+        # them in place); the result goes back to the host
+        lat_d.copy_(pin_noise, non_blocking=True)
+        st["image_latents"].copy_(pin_img, non_blocking=True)
+        st["image_embeddings"].copy_(pin_emb, non_blocking=True)
         out, _ = pipe.denoise_step(st, (args.warmup + i) % n_sig, lat_d)
         pin_out.copy_(out, non_blocking=True)
     e3.record()
@@ -470,10 +553,20 @@ def main():
     if args.profiler_step and rank == 0:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        pipe.denoise_step(st, 5, lat0)
+        pipe.denoise_step(st, 5, lat0, eager=True)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
 
+    # per-rank device time and SM clock (attribution of the N > 1 efficiency: there is no data-path collective, so any
+    # loss is the slowest rank's clock / host launch path - value uses the MAX over ranks)
+    my_clk = sampler_all.stop()
+    mine = {"rank": rank, "ms_per_step": ms / args.steps, "e2e_ms_per_step": ms_e2e / args.steps,
+            "host_ms_per_step": host_ms / args.steps, "sm_mhz": my_clk.get("sm_mhz"),
+            "power_w_max": my_clk.get("power_w_max"), "reasons": my_clk.get("reasons")}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -483,7 +576,7 @@ def main():
     roof = None
     if rank == 0:
         _lib.PROF.records, _lib.PROF.enabled = [], True
-        pipe.denoise_step(st, 5, lat0)
+        pipe.denoise_step(st, 5, lat0, eager=True)       # per-launch CUDA events need the eager path (no graph replay)
         torch.cuda.synchronize()
         _lib.PROF.enabled = False
         by = {}
@@ -521,10 +614,19 @@ def main():
                                                         _lib.PROF.records if n == "lkgd_gemm" and meta]},
                       open(args.profile_out, "w"), indent=1)
 
+    # ---------------------------------------------------------------- N >= 2: the other multi-GPU paths of north_star
+    extra_sections = {}
+    if world >= 2 and not args.no_extra_sections and args.workload == "C3":
+        extra_sections["cfg_pair_split"] = section_cfg_split(args, pipe, F, h, w, lkgd, ms / args.steps, device, rank, world)
+        del pipe, st
+        torch.cuda.empty_cache()
+        extra_sections["c5_data_parallel_training"] = section_c5_dp(args, device, rank, world)
+
     if rank == 0:
         steps_total = args.steps * world
         value = steps_total / (ms * 1e-3)
-        flops = unet_flops(cfg, 2, F, h, w, lora_rank=lrank)["total"]
+        flops = step_flops(args.workload, cfg, F, h, w, lrank)                       # what the CUDA path executes
+        flops_ref = step_flops(args.workload, cfg, F, h, w, lrank, as_reference=True)
         line = {
             "metric": "denoise_steps_per_s", "value": value, "unit": "denoise_steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -532,16 +634,25 @@ def main():
             "config": {"workload": workload_desc(args.workload),
                        "frames_per_s_per_gpu": F * args.steps / (ms * 1e-3),
                        "algorithmic_tflop_per_step": flops / 1e12,
+                       "reference_executed_tflop_per_step": flops_ref / 1e12,
+                       "flops_note": "algorithmic = executed by the CUDA path: the KV-length-1 cross-attention is ONE "
+                                     "[C,D] mat-vec per batch element; the reference also runs to_q / to_k / a per-token "
+                                     "to_out whose result does not depend on the query (SURVEY F7) - not counted as achieved",
                        "model_tflops_per_gpu": flops / 1e12 / (ms / args.steps * 1e-3),
+                       "cuda_graph": graphed, "host_issue_ms_per_step": per_rank[0]["host_ms_per_step"],
                        "l2": "per-step working set (3 GB bf16 weights + multi-GB activations) >> 126 MB L2; "
                              "no explicit flush needed",
                        "output_finite": finite},
             "e2e": {"value": steps_total / (ms_e2e * 1e-3), "unit": "denoise_steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "clocks": clocks,
+            "gpu_launches_note": "launches of our kernels per step (counted on the eager step) x steps; a CUDA-graph "
+                                 "replay re-issues exactly these launches",
+            "clocks": my_clk,
+            "per_rank": per_rank,
             "roofline": roof,
         }
+        line.update(extra_sections)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_oracle_rate(args.workload)
@@ -552,6 +663,110 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def section_cfg_split(args, pipe, F, h, w, lkgd, unsplit_ms, device, rank, world):
+    """north_star: "the CFG cond/uncond pair ... split across GPUs, with no collective in the UNet".  Ranks (2k, 2k+1)
+    denoise sample k together: rank 2k the unconditional half, 2k+1 the conditional half (batch 1 each), ONE all-gather
+    of the fp32 prediction per step, the fused CFG + Euler kernel on both (latents stay replicated).  Latency mode:
+    reports ms/step against the unsplit step, the split-vs-unsplit difference and whether the pair's latents are equal."""
+    import torch.distributed as dist
+    from lkgd_b200.distributed import CFGPair
+    if world % 2:
+        return {"skipped": "odd number of ranks"}
+    pair = CFGPair.from_world()
+    k = rank // 2
+    noise, img_lat, emb, extra = synth_inputs(1, F, h, w, lkgd, seed=k)
+    kw = dict(domain_features=extra[0], flow_features=extra[1]) if lkgd else {}
+    st = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, cfg_pair=pair, **kw)
+    lat0 = (noise * pipe.scheduler.init_noise_sigma).to(device)
+    lat = lat0
+    for i in range(max(2, args.warmup)):
+        lat, _ = pipe.denoise_step(st, i, lat, eager=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        lat, _ = pipe.denoise_step(st, (3 + i) % 25, lat, eager=True)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # correctness on the same inputs: one split step vs the unsplit batch-2 step on this rank
+    split, _ = pipe.denoise_step(st, 3, lat0, eager=True)
+    st_whole = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, **kw)
+    whole, _ = pipe.denoise_step(st_whole, 3, lat0, eager=True)
+    other = split.clone()
+    dist.broadcast(other, src=2 * k, group=pair.group)
+    mine = {"split_vs_unsplit": _rel(split, whole), "replicated": bool(torch.equal(other, split))}
+    allr = [None] * world
+    dist.all_gather_object(allr, mine)
+    nbytes = F * h * w * 4 * 4
+    return {"ms_per_step": float(t[0]), "unsplit_ms_per_step": unsplit_ms, "ratio_vs_unsplit": float(t[0]) / unsplit_ms,
+            "pairs": world // 2, "samples_per_s_equiv": (world // 2) / (float(t[0]) * 1e-3),
+            "allgather_bytes_per_step_per_rank": nbytes, "cuda_graph": False,
+            "split_vs_unsplit_rel_l2_max": max(r["split_vs_unsplit"] for r in allr),
+            "replicated": all(r["replicated"] for r in allr),
+            "what": "ranks (2k,2k+1) share sample k: uncond half on 2k, cond half on 2k+1 (batch 1 each), one NCCL "
+                    "all-gather of the fp32 prediction per step, fused CFG+Euler on both ranks; max-over-ranks device time"}
+
+
+def section_c5_dp(args, device, rank, world):
+    """BASELINE.json configs[4]: the LoRA fine-tuning step, data parallel: every rank its own sample, ONE flat NCCL
+    all-reduce of the LoRA (+ quaternion) gradients per optimizer step (train_models/train_svd_lora.py:1300-1302,1683)."""
+    import torch.distributed as dist
+    from lkgd_b200.training import LoraTrainer
+    pipe, cfg, (F, h, w, lrank, lkgd) = build_ours("C5", device)
+    tr = LoraTrainer(pipe.unet, lr=1e-4, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    B = 1
+    b = [torch.randn(B, F, 4, h, w, generator=g), torch.randn(B, F, 4, h, w, generator=g), torch.tensor([1.3] * B),
+         torch.randn(B, 4, h, w, generator=g), torch.randn(B, 1, 1024, generator=g),
+         torch.tensor([[5.0, 0.02, 127.0]] * B)]
+    if lkgd:
+        b += [torch.randn(B, 1, 1000, generator=g), torch.randn(B, 1, 1000, generator=g)]
+    b = [t.to(device) for t in b]
+    # correctness of the collective on real gradients: all-reduce(SUM) == sum of the gathered per-rank gradients
+    tr.forward_backward(*b)
+    mine = tr.flat_g.clone()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    expect = torch.stack(parts).double().sum(0)
+    tr.optimizer_step()
+    reduced_is_sum = _rel(tr.flat_g, expect)
+    other = tr.flat_p.clone()
+    dist.broadcast(other, src=0)
+    replicated = bool(torch.equal(other, tr.flat_p))
+    distinct = _rel(parts[0], parts[-1]) > 1e-3          # ranks really worked on different samples
+    if not args.no_graph:
+        tr.capture(*b)
+    for _ in range(max(2, args.warmup)):
+        tr.train_step(*b)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.train_step(*b)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = torch.tensor([float(replicated), float(torch.isfinite(loss).all())], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    flops = train_flops(cfg, B, F, h, w, lrank)
+    return {"metric": "train_steps_per_s", "value": world / (float(t[0]) * 1e-3), "unit": "train_steps/s",
+            "ms_per_step": float(t[0]), "n_gpus": world, "scaling": "weak",
+            "allreduce_bytes_per_step": int(tr.flat_g.numel() * 4), "trainable_parameters": int(tr.flat_p.numel()),
+            "reduced_is_sum_rel_l2": reduced_is_sum, "params_replicated": bool(ok[0] > 0), "loss_finite": bool(ok[1] > 0),
+            "ranks_had_distinct_gradients": bool(distinct), "cuda_graph": not args.no_graph,
+            "model_tflops_per_gpu": flops / 1e12 / (float(t[0]) * 1e-3),
+            "what": f"C5: {F} frames 320x512 ({h}x{w} latents), batch 1 per GPU, LoRA r={lrank} + LKGD quaternion tensors; "
+                    "forward+backward graph replay -> one flat NCCL all-reduce(SUM) -> clip + AdamW (1/world in-kernel)"}
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 4
+#define LKGD_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -197,9 +197,12 @@ LKGD_API int lkgd_polar(const float* a, const float* b, float* o0, float* o1, in
  */
 /* out[n,f,h,w,0:C0] = src0[n % N0, f, :, h, w] * scale0 ; out[..., C0:C0+C1] = src1[n % N1, ...]; rest 0.
  * src are fp32 NCHW-per-frame [N?, F, C?, H, W]; out is bf16 [N, F, H, W, Cpad].  Fuses the CFG duplication,
- * scheduler.scale_model_input and the image-latent concat (pipeline...controlnet.py:579-584). */
-LKGD_API int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* src1, int32_t N1,
-                    int32_t C1, void* out, int32_t N, int32_t F, int32_t H, int32_t W, int32_t Cpad, void* stream);
+ * scheduler.scale_model_input and the image-latent concat (pipeline...controlnet.py:579-584).
+ * scale0_dev (may be NULL): DEVICE scalar that replaces scale0 - the per-step 1/sqrt(sigma^2+1) of a denoise step
+ * captured once in a CUDA graph and replayed for every sigma. */
+LKGD_API int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* scale0_dev,
+                    const float* src1, int32_t N1, int32_t C1, void* out, int32_t N, int32_t F, int32_t H, int32_t W,
+                    int32_t Cpad, void* stream);
 /* src fp32 [N*F, H, W, ld] channels-last -> dst fp32 [N, F, C, H, W]. */
 LKGD_API int lkgd_unpack_output(const float* src, int32_t ld, float* dst, int32_t NF, int32_t C, int32_t H, int32_t W,
                        void* stream);
@@ -228,10 +231,13 @@ LKGD_API int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int3
  *   x_next = x + (x - x0) / sigma * (sigma_next - sigma)
  * x / x_next are fp32 [S, F, C, H, W] (reference layout).  cfg == 0: v = pred.  ld == 0: pred is laid out like x
  * ([2S or S, F, C, H, W], the reference's own layout) instead of channels-last rows.
+ * v_out / x0_out (may be NULL) receive the guided prediction and x0 (`pred_original_sample` of the reference's
+ * scheduler output, :506,:527).  x_next may alias x.  sigmas_dev (may be NULL): DEVICE [sigma, sigma_next] replacing the
+ * two host scalars (CUDA-graph replay).
  * Replaces pipeline...controlnet.py:614-616 and utils/scheduling_euler_discrete_karras_fix.py:481-520. */
 LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
-                        float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W,
-                        float sigma, float sigma_next, void* stream);
+                        float* x_next, float* v_out, float* x0_out, int32_t S, int32_t F, int32_t C, int32_t H,
+                        int32_t W, float sigma, float sigma_next, const float* sigmas_dev, void* stream);
 
 /* Bidirectional "direct fusion" Euler step (pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667,
  * SURVEY 8f N3): v and x are fp32 [2S, F, C, H, W] (forward samples, then their time-reversed partners), weights fp32

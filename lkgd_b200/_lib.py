@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -55,7 +55,7 @@ SIGNATURES = {
     "lkgd_axpy_f32": (i32, [vp, f32, vp, i64, vp]),
     "lkgd_scale_f32": (i32, [vp, f32, vp, i64, vp]),
     "lkgd_polar": (i32, [vp, vp, vp, vp, i32, i32, vp]),
-    "lkgd_pack_input": (i32, [vp, i32, i32, f32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "lkgd_pack_input": (i32, [vp, i32, i32, f32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     "lkgd_unpack_output": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "lkgd_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "lkgd_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -63,7 +63,7 @@ SIGNATURES = {
     "lkgd_cast_bf16": (i32, [vp, vp, i64, vp]),
     "lkgd_concat_channels": (i32, [vp, i32, vp, i32, i32, vp, i64, vp]),
     "lkgd_axpby": (i32, [vp, i32, f32, vp, i32, f32, i64, vp]),
-    "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
+    "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
     "lkgd_fusion_euler_step": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
     # ---- training step
     "lkgd_attention_lse": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]),

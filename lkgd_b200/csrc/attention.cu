@@ -517,14 +517,13 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e);
-    attr = true;
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -565,11 +564,10 @@ extern "C" int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, in
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   const float sl2 = scale * 1.4426950408889634f;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_temporal_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * TAttn<64>::TILE);
     if (e != cudaSuccess) return set_cuda_error(e);
-    attr = true;
   }
   switch (d) {
     case 16: attn_temporal_kernel<16><<<grid, 128, 4 * 3 * TAttn<16>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;

@@ -574,11 +574,10 @@ template <int D>
 static int launch_attn_bwd(const AttnBwdParams& p, int n_img, cudaStream_t st) {
   constexpr int TILE = BB * D * 2;
   const int smem_dq = 4 * TILE, smem_dkv = 4 * TILE + 2 * BB * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
     cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
-    attr = true;
   }
   dim3 grid((p.N + BB - 1) / BB, p.heads, n_img);
   attn_bwd_dq_kernel<D><<<grid, 128, smem_dq, st>>>(p);
@@ -641,11 +640,10 @@ extern "C" int lkgd_attention_temporal_bwd(const void* qkv, const void* dO, void
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dqkv);
   const float sl2 = scale * 1.4426950408889634f;
 #define TB_SMEM(D) (4 * (4 * 32 * (D) * 2 + 3 * 32 * 4))
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM(64));
     if (e != cudaSuccess) return set_cuda_error(e);
-    attr = true;
   }
   switch (d) {
     case 16: attn_temporal_bwd_kernel<16><<<grid, 128, TB_SMEM(16), st>>>(x, g, o, B, F, HW, heads, scale, sl2); break;

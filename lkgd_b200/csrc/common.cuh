@@ -17,6 +17,18 @@ int sm_count();
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
               const uint32_t* box);
 
+// One-time per-DEVICE set-up (cudaFuncSetAttribute is per device): true the first time it is called for the calling
+// thread's current device with this flag word (one bit per device ordinal).
+struct DeviceOnce {
+  unsigned long long bits = 0;
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return !(__atomic_fetch_or(&bits, bit, __ATOMIC_ACQ_REL) & bit);
+  }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace lkgd

@@ -464,11 +464,10 @@ using namespace lkgd;
 
 template <bool CTA2, int EG>
 static int launch_gemm(const GemmParams& p, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<CTA2, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
   }
   const int smem_bytes = 1024 + p.stages * p.stage_bytes + EG * 4 * p.epi_bufs * EPI_BUF_BYTES + BIAS_BYTES + BAR_BYTES;
   const int sms = sm_count();

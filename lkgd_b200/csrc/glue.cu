@@ -83,11 +83,12 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int M, in
 
 // out[n,f,h,w,c] (bf16, Cpad channels) from NCHW-per-frame fp32 sources; thread = one pixel, 8 channels per store
 __global__ void pack_input_kernel(const float* __restrict__ s0, int N0, int C0, float scale0,
-                                  const float* __restrict__ s1, int N1, int C1, __nv_bfloat16* __restrict__ out,
-                                  int N, int F, int HW, int Cpad) {
+                                  const float* __restrict__ scale0_dev, const float* __restrict__ s1, int N1, int C1,
+                                  __nv_bfloat16* __restrict__ out, int N, int F, int HW, int Cpad) {
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * F * HW;
   if (pix >= total) return;
+  if (scale0_dev != nullptr) scale0 = __ldg(scale0_dev);     // per-step scalar of a replayed CUDA graph
   const int p = (int)(pix % HW);
   const int f = (int)((pix / HW) % F);
   const int n = (int)(pix / ((long long)HW * F));
@@ -217,12 +218,18 @@ __global__ void scale_f32_kernel(const float* __restrict__ x, float alpha, float
   if (idx < n) y[idx] = alpha * x[idx];
 }
 
+// x_next may alias x (in-place update of a CUDA graph's static latent buffer): every thread reads its x before it writes.
 __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg, const float* __restrict__ guidance,
-                                 const float* __restrict__ x, float* __restrict__ x_next, float* __restrict__ v_out,
-                                 int S, int F, int C, int HW, float sigma, float sigma_next) {
+                                 const float* x, float* x_next, float* __restrict__ v_out, float* __restrict__ x0_out,
+                                 int S, int F, int C, int HW, float sigma, float sigma_next,
+                                 const float* __restrict__ sigmas_dev) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)S * F * C * HW;
   if (idx >= total) return;
+  if (sigmas_dev != nullptr) {                               // per-step scalars of a replayed CUDA graph
+    sigma = __ldg(sigmas_dev);
+    sigma_next = __ldg(sigmas_dev + 1);
+  }
   const int p = (int)(idx % HW);
   const int c = (int)((idx / HW) % C);
   const int f = (int)((idx / ((long long)HW * C)) % F);
@@ -240,6 +247,7 @@ __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg
   const float xs = x[idx];
   const float s2 = sigma * sigma + 1.0f;
   const float x0 = v * (-sigma / sqrtf(s2)) + xs / s2;
+  if (x0_out) x0_out[idx] = x0;
   const float deriv = (xs - x0) / sigma;
   x_next[idx] = xs + deriv * (sigma_next - sigma);
 }
@@ -310,14 +318,14 @@ extern "C" int lkgd_timestep_embedding(const float* t, int32_t M, int32_t dim, f
   return launch_epilogue();
 }
 
-extern "C" int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* src1, int32_t N1,
-                               int32_t C1, void* out, int32_t N, int32_t F, int32_t H, int32_t W, int32_t Cpad,
-                               void* stream) {
+extern "C" int lkgd_pack_input(const float* src0, int32_t N0, int32_t C0, float scale0, const float* scale0_dev,
+                               const float* src1, int32_t N1, int32_t C1, void* out, int32_t N, int32_t F, int32_t H,
+                               int32_t W, int32_t Cpad, void* stream) {
   if (src1 == nullptr) { C1 = 0; N1 = 1; }
   if (N <= 0 || F <= 0 || Cpad % 8 || C0 + C1 > Cpad || N0 <= 0 || N1 <= 0) return LKGD_ESHAPE;
   if (!aligned16(out)) return LKGD_EALIGN;
   const long long total = (long long)N * F * H * W;
-  pack_input_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src0, N0, C0, scale0, src1, N1, C1,
+  pack_input_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src0, N0, C0, scale0, scale0_dev, src1, N1, C1,
                                                                    reinterpret_cast<__nv_bfloat16*>(out), N, F,
                                                                    H * W, Cpad);
   return launch_epilogue();
@@ -383,12 +391,13 @@ extern "C" int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, in
 }
 
 extern "C" int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, const float* guidance, const float* x,
-                                   float* x_next, float* v_out, int32_t S, int32_t F, int32_t C, int32_t H,
-                                   int32_t W, float sigma, float sigma_next, void* stream) {
-  if (S <= 0 || F <= 0 || C <= 0 || (ld != 0 && C > ld) || sigma <= 0.f) return LKGD_ESHAPE;
+                                   float* x_next, float* v_out, float* x0_out, int32_t S, int32_t F, int32_t C,
+                                   int32_t H, int32_t W, float sigma, float sigma_next, const float* sigmas_dev,
+                                   void* stream) {
+  if (S <= 0 || F <= 0 || C <= 0 || (ld != 0 && C > ld) || (sigmas_dev == nullptr && sigma <= 0.f)) return LKGD_ESHAPE;
   const long long total = (long long)S * F * C * H * W;
-  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, S, F,
-                                                                  C, H * W, sigma, sigma_next);
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, x0_out, S,
+                                                                  F, C, H * W, sigma, sigma_next, sigmas_dev);
   return launch_epilogue();
 }
 

@@ -440,10 +440,9 @@ extern "C" int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
   const int threads = g.vecs * g.rows_par;
   const size_t sh1 = (size_t)threads * 16 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
   }
   gn_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, g, reinterpret_cast<double*>(workspace));
   int rc = launch_epilogue();

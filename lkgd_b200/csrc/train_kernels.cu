@@ -680,11 +680,10 @@ extern "C" int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, in
   const int threads = g.vecs * g.rows_par;
   const size_t sh_pro = (size_t)(2 * C + 4 * groups) * sizeof(float);
   const size_t sh1 = sh_pro + (size_t)threads * 16 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr = true;
   }
   gn_bwd_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, reinterpret_cast<const __nv_bfloat16*>(dy), g,
                                                   reinterpret_cast<const double*>(fwd_sums), gamma, beta,

@@ -5,8 +5,12 @@ from __future__ import annotations
 from typing import Dict
 
 
-def unet_flops(cfg: dict, B: int, F: int, H: int, W: int, lora_rank: int = 0, count_dead_cross_attn: bool = True
-               ) -> Dict[str, float]:
+def unet_flops(cfg: dict, B: int, F: int, H: int, W: int, lora_rank: int = 0, count_dead_cross_attn: bool = True,
+               encoder_only: bool = False) -> Dict[str, float]:
+    """``count_dead_cross_attn``: True counts the KV-length-1 cross-attention as the REFERENCE executes it (to_q, to_k
+    and a per-token to_out whose result is independent of the query); False counts what lkgd_b200 executes
+    (one [C, D] mat-vec per batch element).  ``encoder_only``: conv_in + down blocks + mid block (the part a
+    ControlNetSDVModel copies, models/controlnet_sdv.py:219-316)."""
     chans = cfg["block_out_channels"]
     n = len(chans)
     heads = cfg["num_attention_heads"]
@@ -59,6 +63,9 @@ def unet_flops(cfg: dict, B: int, F: int, H: int, W: int, lora_rank: int = 0, co
     res(c, c, h, w)
     tr(c, h, w, xdim[-1])
     res(c, c, h, w)
+    if encoder_only:
+        out["total"] = sum(out.values())
+        return out
     rc = list(reversed(chans))
     rh = list(reversed(lpb))
     rx = list(reversed(xdim))
@@ -72,5 +79,38 @@ def unet_flops(cfg: dict, B: int, F: int, H: int, W: int, lora_rank: int = 0, co
             h, w = h * 2, w * 2
             out["conv3x3"] += 2 * 9 * c * c * BF * h * w
     out["conv3x3"] += 2 * 9 * c * cfg["out_channels"] * BF * h * w
+    out["total"] = sum(out.values())
+    return out
+
+
+def controlnet_flops(cfg: dict, B: int, F: int, H: int, W: int, cond_channels: int = 3,
+                     cond_embed_channels=(16, 32, 96, 256), count_dead_cross_attn: bool = True) -> Dict[str, float]:
+    """ControlNetSDVModel.forward (models/controlnet_sdv.py:441-578): the UNet's encoder + mid block, the pixel-resolution
+    condition encoder (:64-119: conv3x3 Cc->16, then per level conv3x3 c->c and conv3x3 stride 2 c->c', zero conv3x3
+    256->C0 at latent resolution) and the 12 + 1 zero 1x1 convs (:290-316)."""
+    out = unet_flops(cfg, B, F, H, W, 0, count_dead_cross_attn, encoder_only=True)
+    out.pop("total")
+    BF = B * F
+    h, w = 8 * H, 8 * W
+    ce = list(cond_embed_channels)
+    f = 2 * 9 * cond_channels * ce[0] * BF * h * w
+    for i in range(len(ce) - 1):
+        f += 2 * 9 * ce[i] * ce[i] * BF * h * w
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        f += 2 * 9 * ce[i] * ce[i + 1] * BF * h * w
+    f += 2 * 9 * ce[-1] * cfg["block_out_channels"][0] * BF * h * w
+    out["cond_embedding"] = float(f)
+    chans = cfg["block_out_channels"]
+    n = len(chans)
+    lpb = cfg["layers_per_block"]
+    lpb = tuple(lpb) if isinstance(lpb, (tuple, list)) else (lpb,) * n
+    z, h, w = 2 * chans[0] * chans[0] * BF * H * W, H, W
+    for i in range(n):
+        z += lpb[i] * 2 * chans[i] * chans[i] * BF * h * w
+        if i != n - 1:
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            z += 2 * chans[i] * chans[i] * BF * h * w
+    z += 2 * chans[-1] * chans[-1] * BF * h * w
+    out["zero_convs"] = float(z)
     out["total"] = sum(out.values())
     return out

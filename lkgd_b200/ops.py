@@ -24,9 +24,37 @@ def _stream():
 
 
 def _need_cuda(*ts):
+    """Every operand on ONE CUDA device, and that device current: the C ABI launches on the calling thread's current
+    device with the stream handle it is given, so a tensor of another device would be an illegal address (or a silent
+    peer access).  The module / pipeline / trainer entry points switch devices themselves (``on_own_device``)."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise ValueError("lkgd_b200 kernels take CUDA tensors only (there is no CPU path)")
+        if dev is None:
+            dev = t.device.index
+        elif t.device.index != dev:
+            raise ValueError(f"lkgd_b200 op with operands on cuda:{dev} and cuda:{t.device.index}")
+    if dev is not None and dev != torch.cuda.current_device():
+        raise ValueError(f"lkgd_b200 op on cuda:{dev} tensors while the current device is "
+                         f"cuda:{torch.cuda.current_device()}: call it under `with torch.cuda.device({dev})`")
+
+
+def on_own_device(fn):
+    """Method decorator for the public entry points (module forward, pipeline step, trainer step): runs the call with
+    the object's own CUDA device current, like a PyTorch module of the reference would on any device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrap(self, *a, **k):
+        dev = getattr(self, "device", None)
+        if not isinstance(dev, torch.device) or dev.type != "cuda" or dev.index in (None, torch.cuda.current_device()):
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrap
 
 
 def launch_count() -> int:
@@ -134,28 +162,41 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
 class _StatsArena:
     """One zeroed fp64 buffer per forward for all fused GroupNorm statistics (a C3 step has ~105 producers: one memset
     instead of 105 fill launches).  ``begin`` is called at the start of a forward; slices are valid until the next
-    ``begin`` on the same stream.  Falls back to ``torch.zeros`` when it is not active or too small (it then grows at
-    the next ``begin``)."""
+    ``begin`` on the same (device, stream) - every (device, stream) pair has its own buffer, so two models, two devices
+    or two streams in one process never share statistics.  Falls back to ``torch.zeros`` when it is not active or too
+    small (it then grows at the next ``begin``)."""
+
+    class _Slot:
+        __slots__ = ("buf", "off", "want")
+
+        def __init__(self):
+            self.buf, self.off, self.want = None, 0, 8 << 20      # doubles
 
     def __init__(self):
-        self.buf, self.off, self.want = None, 0, 8 << 20      # doubles
+        self.slots = {}
+
+    @staticmethod
+    def _key(device):
+        return (device.index, torch.cuda.current_stream(device).cuda_stream)
 
     def begin(self, device) -> None:
-        if self.buf is None or self.buf.device != device or self.buf.numel() < self.want:
-            self.buf = torch.empty(self.want, device=device, dtype=torch.float64)
-        self.buf.zero_()
-        self.off = 0
+        s = self.slots.setdefault(self._key(device), self._Slot())
+        if s.buf is None or s.buf.numel() < s.want:
+            s.buf = torch.empty(s.want, device=device, dtype=torch.float64)
+        s.buf.zero_()
+        s.off = 0
 
     def take(self, frames: int, n: int, device) -> torch.Tensor:
         need = frames * n * 2
-        if self.buf is None or self.buf.device != device:
+        s = self.slots.get(self._key(device))
+        if s is None or s.buf is None:
             return torch.zeros((frames, n, 2), device=device, dtype=torch.float64)
-        if self.off + need > self.buf.numel():
-            self.want = max(self.want, 2 * (self.off + need))
-            self.off += need                                   # keep counting so that `want` covers the whole forward
+        if s.off + need > s.buf.numel():
+            s.want = max(s.want, 2 * (s.off + need))
+            s.off += need                                      # keep counting so that `want` covers the whole forward
             return torch.zeros((frames, n, 2), device=device, dtype=torch.float64)
-        out = self.buf[self.off:self.off + need].view(frames, n, 2)
-        self.off += need
+        out = s.buf[s.off:s.off + need].view(frames, n, 2)
+        s.off += need
         return out
 
 
@@ -360,9 +401,13 @@ def polar(a: torch.Tensor, b: torch.Tensor, mode: int):
 
 
 # ----------------------------------------------------------------------------------------------- glue
-def pack_input(src0: torch.Tensor, scale0: float, src1: Optional[torch.Tensor], N: int, Cpad: int) -> torch.Tensor:
-    """src [N?,F,C?,H,W] fp32 -> bf16 [N*F*H*W, Cpad] channels-last (see lkgd_pack_input)."""
-    _need_cuda(src0, src1)
+def pack_input(src0: torch.Tensor, scale0: float, src1: Optional[torch.Tensor], N: int, Cpad: int,
+               scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src [N?,F,C?,H,W] fp32 -> bf16 [N*F*H*W, Cpad] channels-last (see lkgd_pack_input).  ``scale_dev``: fp32 device
+    scalar that replaces ``scale0`` (a step captured in a CUDA graph reads its per-step scale from device memory)."""
+    _need_cuda(src0, src1, scale_dev)
+    if scale_dev is not None and (scale_dev.dtype != torch.float32 or scale_dev.numel() < 1):
+        raise ValueError("pack_input: scale_dev must be an fp32 device scalar")
     src0 = src0.to(torch.float32).contiguous()
     N0, F, C0, H, W = src0.shape
     N1 = C1 = 0
@@ -370,8 +415,8 @@ def pack_input(src0: torch.Tensor, scale0: float, src1: Optional[torch.Tensor], 
         src1 = src1.to(torch.float32).contiguous()
         N1, _, C1 = src1.shape[:3]
     out = torch.empty((N * F * H * W, Cpad), device=src0.device, dtype=bf16)
-    L.check(L.load().lkgd_pack_input(src0.data_ptr(), N0, C0, scale0, _ptr(src1), max(N1, 1), C1, out.data_ptr(), N,
-                                     F, H, W, Cpad, _stream()), "lkgd_pack_input")
+    L.check(L.load().lkgd_pack_input(src0.data_ptr(), N0, C0, scale0, _ptr(scale_dev), _ptr(src1), max(N1, 1), C1,
+                                     out.data_ptr(), N, F, H, W, Cpad, _stream()), "lkgd_pack_input")
     return out
 
 
@@ -466,11 +511,15 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torch.Tensor, sigma: float,
-                   sigma_next: float, *, cfg: bool, want_v: bool = False):
+                   sigma_next: float, *, cfg: bool, want_v: bool = False, want_x0: bool = False,
+                   sigmas_dev: Optional[torch.Tensor] = None, in_place: bool = False):
     """pred fp32: channels-last rows [(2)S*F*H*W, ld] (2-D) or the latent's own layout [(2)S,F,C,H,W] (5-D);
-    x fp32 [S,F,C,H,W] -> (x_next, v or None)."""
-    _need_cuda(pred, guidance, x)
+    x fp32 [S,F,C,H,W] -> (x_next, v or None) (-> (x_next, v, x0) with ``want_x0``).  ``sigmas_dev``: fp32 device
+    [sigma, sigma_next] replacing the host scalars; ``in_place``: write x_next over x (CUDA-graph replay)."""
+    _need_cuda(pred, guidance, x, sigmas_dev)
     S, F, Cn, H, W = x.shape
+    if in_place and not x.is_contiguous():
+        raise ValueError("cfg_euler_step: in_place needs a contiguous latent")
     x = x.contiguous()
     if pred.dtype != torch.float32 or x.dtype != torch.float32:
         raise ValueError("cfg_euler_step works in fp32")
@@ -483,12 +532,13 @@ def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torc
         ld = pred.stride(0)
         if pred.shape[0] != (2 if cfg else 1) * S * F * H * W:
             raise ValueError("prediction rows do not match the latent")
-    x_next = torch.empty_like(x)
+    x_next = x if in_place else torch.empty_like(x)
     v = torch.empty_like(x) if want_v else None
+    x0 = torch.empty_like(x) if want_x0 else None
     L.check(L.load().lkgd_cfg_euler_step(pred.data_ptr(), ld, int(cfg), _ptr(guidance), x.data_ptr(),
-                                         x_next.data_ptr(), _ptr(v), S, F, Cn, H, W, sigma, sigma_next, _stream()),
-            "lkgd_cfg_euler_step")
-    return x_next, v
+                                         x_next.data_ptr(), _ptr(v), _ptr(x0), S, F, Cn, H, W, sigma, sigma_next,
+                                         _ptr(sigmas_dev), _stream()), "lkgd_cfg_euler_step")
+    return (x_next, v, x0) if want_x0 else (x_next, v)
 
 
 # ----------------------------------------------------------------------------------------------- training step

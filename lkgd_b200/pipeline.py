@@ -77,6 +77,7 @@ class StableVideoDiffusionPipeline:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma.to(latents.device)
 
+    @ops.on_own_device
     @torch.no_grad()
     def prepare(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, num_frames: Optional[int] = None,
                 num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
@@ -100,12 +101,17 @@ class StableVideoDiffusionPipeline:
         lkgd = isinstance(unet, UNetSpatioTemporalConditionModel)
         if lkgd and (domain_features is None or flow_features is None):
             raise ValueError("the LKGD UNet needs domain_features and flow_features")
+        # the incoming conditioning already carries the reference's num_videos_per_prompt repetition (`_encode_image` /
+        # `_encode_vae_image` repeat it, :204,:234): S = batch_size * num_videos_per_prompt samples
+        if num_videos_per_prompt < 1 or S % num_videos_per_prompt:
+            raise ValueError(f"the conditioning batch ({S} samples) is not a multiple of num_videos_per_prompt="
+                             f"{num_videos_per_prompt}")
         fps = fps - 1                              # reference :482: the model was conditioned on fps - 1
-        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, torch.float32, S,
-                                                num_videos_per_prompt, do_cfg).to(device)
+        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, torch.float32,
+                                                S // num_videos_per_prompt, num_videos_per_prompt, do_cfg).to(device)
         sched.set_timesteps(num_inference_steps, device=device)
         guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames).unsqueeze(0).to(device)
-        self._guidance_scale = _append_dims(guidance.repeat(S * num_videos_per_prompt, 1), 5)
+        self._guidance_scale = _append_dims(guidance.repeat(S, 1), 5)
         if controlnet_condition is not None and self.controlnet is None:
             raise ValueError("controlnet_condition given but the pipeline has no controlnet")
         if controlnet_condition is not None:
@@ -116,7 +122,7 @@ class StableVideoDiffusionPipeline:
             controlnet_condition = cc.to(device=device, dtype=torch.float32)
         if cfg_pair is not None and (not do_cfg or controlnet_condition is not None):
             raise ValueError("cfg_pair needs classifier-free guidance and (for now) no ControlNet")
-        return dict(cfg_pair=cfg_pair, S=S * num_videos_per_prompt, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
+        return dict(cfg_pair=cfg_pair, S=S, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
                     w=image_latents.shape[-1], do_cfg=do_cfg, added_time_ids=added_time_ids,
                     guidance=guidance.reshape(-1).to(torch.float32).contiguous(),
                     image_latents=image_latents.to(device=device, dtype=torch.float32).contiguous(),
@@ -124,12 +130,90 @@ class StableVideoDiffusionPipeline:
                     controlnet_cond_scale=controlnet_cond_scale,
                     extra=(domain_features.to(device), flow_features.to(device)) if lkgd else ())
 
+    @property
+    def device(self):
+        return self.unet.device
+
+    def _step_body(self, st: dict, latents: torch.Tensor, scale, t, sigmas_dev=None, in_place=False, want_v=False):
+        """pack -> [ControlNet] -> UNet -> CFG + Euler for the unsplit batch.  ``scale`` / ``t`` are host floats on the
+        eager path and fp32 device scalars inside a captured graph."""
+        sched, unet = self.scheduler, self.unet
+        pk = unet.packed()
+        dev_scalars = torch.is_tensor(scale)
+        # CFG duplication + scale_model_input + concat(image_latents) + layout, one kernel (:579-584)
+        x = ops.pack_input(latents, 0.0 if dev_scalars else scale, st["image_latents"], N=st["n_batch"], Cpad=pk.cin_pad,
+                           scale_dev=scale if dev_scalars else None)
+        g = Geom(st["n_batch"], st["F"], st["h"], st["w"])
+        kw = {}
+        if st["controlnet_condition"] is not None:
+            down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
+                                                       st["controlnet_condition"], st["controlnet_cond_scale"])
+            kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
+        rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
+                                   added_time_ids=st["added_time_ids"], **kw)
+        return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
+                                   want_v=want_v, sigmas_dev=sigmas_dev, in_place=in_place)
+
+    @ops.on_own_device
     @torch.no_grad()
-    def denoise_step(self, st: dict, i: int, latents: torch.Tensor, want_v: bool = False):
+    def capture(self, st: dict, latents: torch.Tensor) -> dict:
+        """Captures ONE denoise step for the loop state ``st`` in a CUDA graph: every shape is static
+        across the 25 steps, only four scalars change (1/sqrt(sigma^2+1), sigma, sigma_next, t = 0.25 ln sigma) - they
+        live in a 16-byte device buffer refreshed from a device-resident table before each replay, the latents are
+        updated in place in a static buffer.  ~800 kernel launches, their ctypes calls, TMA-descriptor encodes and
+        allocations become one ``cudaGraphLaunch``.  Call after at least one eager ``denoise_step`` (lazy weight packing
+        and one-time kernel attributes must not happen under capture).  The conditioning tensors in ``st`` are the
+        graph's static inputs: refresh them with ``copy_`` (not by rebinding the dict entries)."""
+        if st.get("cfg_pair") is not None:
+            raise ValueError("the CFG pair split exchanges predictions with NCCL every step: not captured")
+        sched = self.scheduler
+        dev = self.unet.device
+        sig = np.asarray(sched._sigmas_host, dtype=np.float32)
+        ts = np.asarray(sched._timesteps_host, dtype=np.float32)
+        tab = np.stack([np.asarray([float(1.0 / np.sqrt(np.float32(s) ** 2 + 1)) for s in sig[:-1]], dtype=np.float32),
+                        sig[:-1], sig[1:], ts], axis=1)
+        G = dict(table=torch.from_numpy(np.ascontiguousarray(tab)).to(dev), lat=latents.to(dev).clone().contiguous(),
+                 params=torch.zeros(4, device=dev, dtype=torch.float32), n=len(ts))
+        G["params"].copy_(G["table"][0])
+        keep = G["lat"].clone()
+
+        def body():
+            sched.index_for(0)
+            self._step_body(st, G["lat"], G["params"][0:1], G["params"][3:4], sigmas_dev=G["params"][1:3], in_place=True)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()                                   # warm the allocator / statistics arena off the default stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        G["lat"].copy_(keep)
+        G["graph"] = graph
+        st["graph"] = G
+        return st
+
+    @ops.on_own_device
+    @torch.no_grad()
+    def denoise_step(self, st: dict, i: int, latents: torch.Tensor, want_v: bool = False, eager: bool = False):
         """One iteration of the reference's denoising loop (:577-619) for step index ``i``: fused
         dup/scale/concat/layout kernel -> [ControlNet] -> UNet -> fused CFG + Euler-Karras kernel.
-        ``latents``: fp32 [S,F,4,h,w] on the device.  Returns (next latents, guided prediction or None)."""
+        ``latents``: fp32 [S,F,4,h,w] on the device.  Returns (next latents, guided prediction or None).
+        After ``capture(st, ...)`` the step is a CUDA-graph replay and the returned latents ARE the graph's static
+        buffer (updated in place by the next call); ``eager=True`` / ``want_v`` keep the kernel-by-kernel path."""
         sched, unet = self.scheduler, self.unet
+        G = st.get("graph")
+        if G is not None and not eager and not want_v:
+            if not 0 <= i < G["n"]:
+                raise IndexError("step index outside the captured schedule")
+            if latents.data_ptr() != G["lat"].data_ptr():
+                G["lat"].copy_(latents, non_blocking=True)
+            G["params"].copy_(G["table"][i], non_blocking=True)
+            G["graph"].replay()
+            sched.index_for(i + 1)
+            return G["lat"], None
         pk = unet.packed()
         sched.index_for(i)
         sigma = float(sched._sigmas_host[i])
@@ -146,18 +230,7 @@ class StableVideoDiffusionPipeline:
                                        added_time_ids=st["added_time_ids"], batch_slice=(lo, hi))
             rows = pair.exchange(rows)
             return sched.step_cfg_rows(rows, st["guidance"], latents, cfg=True, want_v=want_v)
-        # CFG duplication + scale_model_input + concat(image_latents) + layout, one kernel (:579-584)
-        x = ops.pack_input(latents, scale, st["image_latents"], N=st["n_batch"], Cpad=pk.cin_pad)
-        g = Geom(st["n_batch"], st["F"], st["h"], st["w"])
-        kw = {}
-        if st["controlnet_condition"] is not None:
-            down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
-                                                       st["controlnet_condition"], st["controlnet_cond_scale"])
-            kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
-        rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
-                                   added_time_ids=st["added_time_ids"], **kw)
-        return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
-                                   want_v=want_v)
+        return self._step_body(st, latents, scale, t, want_v=want_v)
 
     @torch.no_grad()
     def __call__(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, num_frames: Optional[int] = None,
@@ -167,7 +240,8 @@ class StableVideoDiffusionPipeline:
                  controlnet_condition: Optional[torch.Tensor] = None, controlnet_cond_scale: float = 1.0,
                  domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
                  cfg_pair=None, output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
-                 return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False):
+                 return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False,
+                 use_cuda_graph: bool = False):
         if output_type != "latent":
             raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
                              "VAE of your choice (SURVEY.md section 8f, N1)")
@@ -184,6 +258,8 @@ class StableVideoDiffusionPipeline:
             if max_steps is not None and i >= max_steps:
                 break
             latents, v = self.denoise_step(st, i, latents, want_v=return_trajectory)
+            if i == 0 and use_cuda_graph and not return_trajectory and cfg_pair is None:
+                self.capture(st, latents)              # steps 1.. replay the captured graph (same kernels, same order)
             if return_trajectory:
                 preds.append(v)
                 traj.append(latents)

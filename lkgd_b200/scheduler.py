@@ -182,15 +182,28 @@ class EulerDiscreteScheduler:
             self._init_step_index(timestep)
         if consume_rng:   # reference quirk D5 (:485-489)
             torch.randn(model_output.shape, dtype=model_output.dtype, device=model_output.device, generator=generator)
+        if not self.is_scale_input_called:      # reference :470-474 (logger.warning)
+            import logging
+            logging.getLogger(__name__).warning(
+                "The `scale_model_input` function should be called before `step` to ensure correct denoising. "
+                "See `StableDiffusionPipeline` for a usage example.")
         sigma = float(self._sigmas_host[self._step_index])
         sigma_next = float(self._sigmas_host[self._step_index + 1])
-        pred = model_output.to(torch.float32)
-        prev, _ = ops.cfg_euler_step(pred, None, sample.to(torch.float32), sigma, sigma_next, cfg=False)
-        prev = prev.to(model_output.dtype)
+        if model_output.shape != sample.shape:
+            raise ValueError("model_output and sample must have the same shape")
+        # the update is elementwise: any shape the reference accepts (4-D image latents, 5-D video latents, ...) is one
+        # flat fp32 vector for the fused kernel; upcast like the reference (:481), cast back (:520)
+        shape = sample.shape
+        pred = model_output.to(torch.float32).reshape(1, 1, 1, 1, -1)
+        with torch.cuda.device(sample.device):
+            prev, _, x0 = ops.cfg_euler_step(pred, None, sample.to(torch.float32).reshape(1, 1, 1, 1, -1), sigma,
+                                             sigma_next, cfg=False, want_x0=True)
+        prev = prev.reshape(shape).to(model_output.dtype)
+        x0 = x0.reshape(shape).to(model_output.dtype)
         self._step_index += 1
         if not return_dict:
             return (prev,)
-        return EulerDiscreteSchedulerOutput(prev_sample=prev)
+        return EulerDiscreteSchedulerOutput(prev_sample=prev, pred_original_sample=x0)
 
     def step_direct_fusion(self, model_output: torch.Tensor, timestep, sample: torch.Tensor,
                            generator: Optional[torch.Generator] = None, consume_rng: bool = False) -> torch.Tensor:
@@ -214,12 +227,15 @@ class EulerDiscreteScheduler:
         return out.to(model_output.dtype)
 
     def step_cfg_rows(self, pred_rows: torch.Tensor, guidance: Optional[torch.Tensor], sample: torch.Tensor,
-                      cfg: bool, want_v: bool = False):
+                      cfg: bool, want_v: bool = False, sigmas_dev: Optional[torch.Tensor] = None,
+                      in_place: bool = False):
         """Fused CFG combine + Euler update straight from the UNet's channels-last fp32 prediction
-        (pipeline/pipeline_stable_video_diffusion_controlnet.py:614-619 in one kernel)."""
+        (pipeline/pipeline_stable_video_diffusion_controlnet.py:614-619 in one kernel).  ``sigmas_dev`` / ``in_place``:
+        the CUDA-graph form (per-step sigmas read from device memory, latents updated in their static buffer)."""
         sigma = float(self._sigmas_host[self._step_index])
         sigma_next = float(self._sigmas_host[self._step_index + 1])
-        out = ops.cfg_euler_step(pred_rows, guidance, sample, sigma, sigma_next, cfg=cfg, want_v=want_v)
+        out = ops.cfg_euler_step(pred_rows, guidance, sample, sigma, sigma_next, cfg=cfg, want_v=want_v,
+                                 sigmas_dev=sigmas_dev, in_place=in_place)
         self._step_index += 1
         return out
 

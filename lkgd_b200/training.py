@@ -474,6 +474,11 @@ class LoraTrainer:
         if repack:
             self.repack()
 
+    @property
+    def device(self):
+        return self.unet.device
+
+    @ops.on_own_device
     def train_step(self, *args, **kw) -> torch.Tensor:
         if self._graph is not None:
             return self._graphed_step(*args)
@@ -486,6 +491,7 @@ class LoraTrainer:
     # once and replayed.  The optimizer (host-side step count) and the NCCL all-reduce stay outside the graphs.
     _graph = None
 
+    @ops.on_own_device
     def capture(self, *batch):
         """Captures forward_backward (and the repack) for batches shaped like ``batch`` (device tensors: latents, noise,
         sigmas, cond_latents, encoder_hidden_states, added_time_ids[, domain_features, flow_features]).  Call after at

@@ -292,6 +292,7 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
             raise ValueError("ControlNet residuals must be [batch*frames, C, H, W] tensors or ChannelsLast")
         return ops.nchw_to_nhwc(r)
 
+    @ops.on_own_device
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor, *extra,
                        down_block_additional_residuals=None, mid_block_additional_residual=None,
@@ -334,11 +335,13 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
                 ops.axpby(self._residual_rows(r, gs), float(m), s, 1.0)
         return pk.decoder(x, skips, gm, cond)
 
+    @ops.on_own_device
     @torch.no_grad()
     def forward_rows(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, *extra, **kw):
         x, g = self._pack_sample(sample, self.packed())
         return self.forward_packed(x, g, timestep, encoder_hidden_states, *extra, **kw), g
 
+    @ops.on_own_device
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor,
                 down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
@@ -631,6 +634,7 @@ class UNetSpatioTemporalConditionModel(UNetSpatioTemporalConditionControlNetMode
         ops.grouped1x1_bwd_w(dcat[:, 256:512], S.dom_i, gw("dconv.weight"))
         ops.grouped1x1_bwd_w(dcat[:, 512:768], S.flo_i, gw("fconv.weight"))
 
+    @ops.on_own_device
     @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states,
                 domain_features, flow_features,
@@ -749,6 +753,7 @@ class ControlNetSDVModel(_Base):
             self._cn = (packed, zero)
         return self._cn
 
+    @ops.on_own_device
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
                        added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor] = None,
@@ -782,6 +787,7 @@ class ControlNetSDVModel(_Base):
         mid = ChannelsLast(ops.gemm(ops.cast_bf16(x), zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
         return down, mid
 
+    @ops.on_own_device
     @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor, added_time_ids: torch.Tensor,

@@ -71,7 +71,13 @@ class Attention(nn.Module):
         self.to_v = nn.Linear(kv_dim, inner, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
 
+    # softmax(QK^T) of a 72x128 latent frame (9216 tokens) is 1.7 GB per image and head group: self-attention over
+    # that many tokens is evaluated image by image (same arithmetic, bounded memory) - full-size parity runs only
+    CHUNK_TOKENS = 4096
+
     def forward(self, x, encoder_hidden_states=None):
+        if encoder_hidden_states is None and x.shape[1] >= self.CHUNK_TOKENS and x.shape[0] > 1:
+            return torch.cat([self.forward(x[i:i + 1]) for i in range(x.shape[0])], 0)
         ctx = x if encoder_hidden_states is None else encoder_hidden_states
         b, n, _ = x.shape
         q = self.to_q(x).view(b, n, self.heads, self.dim_head).transpose(1, 2)

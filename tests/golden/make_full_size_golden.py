@@ -105,7 +105,7 @@ def run(name):
         if cn is not None:
             down, mid = cn(x, c["t"], ctx, ids, controlnet_cond=cond, conditioning_scale=1.0, return_dict=False)
             kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
-            out["cn_mid"] = mid.half().numpy()
+            out["cn_mid"] = mid[:, :128].half().numpy()          # first 128 of 1280 channels: keeps the fixture small
             out["cn_down_norms"] = np.asarray([float(d.double().norm()) for d in down])
         y = u(x, c["t"], ctx, *extra, added_time_ids=ids, return_dict=False, **kw)[0]
     t_fwd = time.time() - t1

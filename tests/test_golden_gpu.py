@@ -22,11 +22,31 @@ def test_scheduler_kernels_vs_reference_trajectory(cuda, n):
     for i, ts in enumerate(s.timesteps):
         xin = s.scale_model_input(x, ts)
         assert rel(xin, G[f"sched{n}/scaled"][i]) < 1e-6
-        x = s.step(seeded_tensor(f"sched/v{i}", x.shape).to(cuda), ts, x).prev_sample
+        o = s.step(seeded_tensor(f"sched/v{i}", x.shape).to(cuda), ts, x)
+        x = o.prev_sample
         worst = max(worst, rel(x, G[f"sched{n}/traj"][i]))
+        worst = max(worst, rel(o.pred_original_sample, G[f"sched{n}/x0"][i]))     # reference :506,:527
     print("scheduler worst rel-L2", worst)
     assert worst < 1e-4
     assert s.step_index == n
+
+
+def test_scheduler_step_accepts_any_shape(cuda):
+    """The reference's step is elementwise on any shape (4-D image latents, 2-D ...): same numbers as the 5-D call."""
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    outs = []
+    for shape in ((1, 3, 4, 8, 8), (3, 4, 8, 8), (12, 64), (768,)):
+        s = EulerDiscreteScheduler(**SCHED)
+        s.set_timesteps(10, device=cuda)
+        x = (seeded_tensor("sched/x0", (1, 3, 4, 8, 8)) * s.init_noise_sigma).to(cuda).reshape(shape)
+        v = seeded_tensor("sched/v0", (1, 3, 4, 8, 8)).to(cuda).reshape(shape)
+        s.scale_model_input(x, s.timesteps[0])
+        o = s.step(v, s.timesteps[0], x)
+        assert o.prev_sample.shape == x.shape and o.pred_original_sample.shape == x.shape
+        outs.append(o.prev_sample.flatten())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert rel(outs[0], G["sched10/traj"][0]) < 1e-4
 
 
 def test_direct_fusion_step_vs_reference_lines(cuda):

@@ -164,6 +164,15 @@ def test_pipeline_argument_checks():
         p.prepare(emb, lat, controlnet_condition=torch.zeros(4, 2, 128, 128))
     with pytest.raises(ValueError, match="generators"):
         p.prepare_latents(2, 4, 8, 16, 16, torch.float32, "cpu", [torch.Generator()])
+    # num_videos_per_prompt: the conditioning arrives already repeated (reference `_encode_image` :204 /
+    # `_encode_vae_image` :234), so 2 prompts x 2 videos = 4 samples, 8 CFG rows - counted once, not twice
+    emb4, lat4 = torch.zeros(8, 1, 32), torch.zeros(8, 4, 4, 16, 16)
+    st = p.prepare(emb4, lat4, num_videos_per_prompt=2)
+    assert st["S"] == 4 and st["n_batch"] == 8 and tuple(st["added_time_ids"].shape) == (8, 3)
+    assert tuple(p.guidance_scale.shape) == (4, 4, 1, 1, 1)
+    assert tuple(p.prepare_latents(st["S"], 4, 8, 16, 16, torch.float32, "cpu", None).shape) == (4, 4, 4, 16, 16)
+    with pytest.raises(ValueError, match="num_videos_per_prompt"):
+        p.prepare(emb, lat, num_videos_per_prompt=2)
     with torch.device("meta"):
         lk = UNetSpatioTemporalConditionModel(**dict(REDUCED4, cross_attention_dim=1024))
     with pytest.raises(ValueError, match="domain_features"):

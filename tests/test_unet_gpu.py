@@ -325,3 +325,40 @@ def test_full_25_step_trajectory(cuda, name):
     assert max(forced) < 1e-2, forced
     assert max(free) < 2e-2, free
     assert rel_l2(got, ref) < 2e-2
+
+
+def test_cuda_graph_replay_equals_the_eager_loop(cuda):
+    """the denoise step captured once in a CUDA graph (per-step scalars read from device memory,
+    latents updated in place) must reproduce the kernel-by-kernel loop over all 25 steps - same kernels, same order; the
+    only run-to-run noise is the order of the fp64 atomics of the fused GroupNorm statistics."""
+    import oracle as O
+    from oracle.scheduler import SVD_SCHEDULER_CONFIG
+    from lkgd_b200 import ops
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import REDUCED_CONFIG, ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    torch.manual_seed(3)
+    oc = O.ControlNetSDVModel.from_unet(o, conditioning_channels=2)
+    _randomise_zero_inits(oc, seed=2)
+    pc = ControlNetSDVModel.from_unet(p, conditioning_channels=2)
+    pc.load_state_dict(oc.state_dict(), strict=True)
+    S, F, h, w = 1, 8, 32, 32
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(S, F, 4, h, w, generator=g)
+    img_lat = torch.cat([torch.zeros(S, F, 4, h, w), torch.randn(S, 1, 4, h, w, generator=g).repeat(1, F, 1, 1, 1)])
+    emb = torch.cat([torch.zeros(S, 1, 32), torch.randn(S, 1, 32, generator=g)])
+    cond = torch.rand(F, 2, 8 * h, 8 * w, generator=g) * 2 - 1
+    for controlnet, kw in ((None, {}), (pc.to(cuda), dict(controlnet_condition=cond))):
+        pipe = StableVideoDiffusionPipeline(p, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG), controlnet=controlnet)
+        eager = pipe(emb, img_lat, num_frames=F, num_inference_steps=25, latents=noise, return_dict=False, **kw)
+        n0 = ops.launch_count()
+        graphed = pipe(emb, img_lat, num_frames=F, num_inference_steps=25, latents=noise, return_dict=False,
+                       use_cuda_graph=True, **kw)
+        launches = ops.launch_count() - n0
+        err = rel_l2(graphed, eager)
+        print("controlnet" if controlnet is not None else "plain", "graph vs eager rel-L2", err,
+              "host-issued launches with the graph:", launches)
+        assert err < 1e-5
+        assert bool(torch.isfinite(graphed).all())
