@@ -15,8 +15,8 @@
 
 namespace lkgd {
 
-constexpr int AT_BQ = 128, AT_D = 64;
-constexpr int AT_TILE = AT_BQ * AT_D * 2;  // 16 KB
+constexpr int AT_BQ = 128, AT_D = 64;     // AT_D: width of one SWIZZLE_128B sub-tile (64 bf16 = 128 bytes)
+constexpr int AT_SUBQ = AT_BQ * AT_D * 2;  // 16 KB: 128 query rows x 64 head channels
 constexpr int AT_THREADS = 192;
 
 struct AttnParams {
@@ -34,9 +34,20 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 constexpr int AT_BH = 64;                 // keys per softmax step == keys per K/V stage
-constexpr int AT_KV = AT_BH * AT_D * 2;   // 8 KB: one 64-key K (or V) stage
-constexpr int AT_NS = 3;                  // K/V stages: two steps of look-ahead cover the TMA latency
-constexpr int AT_SMEM = AT_TILE /*Q*/ + AT_NS * AT_KV /*K*/ + AT_NS * AT_KV /*V*/ + 128;
+constexpr int AT_SUBKV = AT_BH * AT_D * 2; // 8 KB: 64 keys x 64 head channels
+// Head width D = 64 (also serves d = 16 / 32 through zero-filled TMA boxes) or 128 (the reference's default heads
+// (5,10,10,20) give 1280 / 10 = 128 at level 2, models/unet_spatio_temporal_condition_controlnet.py:93).  A D = 128 tile
+// is two 64-channel SWIZZLE_128B sub-tiles side by side: Q K^T runs 8 k-steps over them, P V two N = 64 halves.
+template <int D>
+struct AttnCfg {
+  static constexpr int NSUB = D / AT_D;                       // 1 or 2
+  static constexpr int TILE = NSUB * AT_SUBQ;                 // Q tile bytes
+  static constexpr int KV = NSUB * AT_SUBKV;                  // one 64-key K (or V) stage
+  static constexpr int NS = D == 64 ? 3 : 2;                  // K/V stages (ring)
+  static constexpr int SMEM = TILE + 2 * NS * KV + 128;
+  static constexpr int TMEM_MAIN = D == 64 ? 128 : 256;       // S (64 columns) | O (D columns)
+  static constexpr int CTAS = D == 64 ? 3 : 2;                // resident CTAs per SM
+};
 
 // Pipeline (per CTA; THREE CTAs share an SM - 64 KB smem, 160 TMEM columns and <= 96 registers each - so that three
 // softmax warps per scheduler hide each other's barrier / TMEM / fence latencies and keep the MUFU pipe, which bounds
@@ -90,8 +101,10 @@ __device__ __forceinline__ uint64_t at_exp2_poly2(uint64_t X) {
 
 // POLY: every POLY-th pair of exponentials is evaluated on the FMA pipes instead of the MUFU pipe (0 = none).  d = 64
 // attention is bound by the 16 ex2 / clock / SM of the MUFU pipe; the FMA pipes are otherwise nearly idle here.
-template <int POLY>
-__global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+template <int POLY, int D>
+__global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int AT_TILE = Cfg::TILE, AT_KV = Cfg::KV, AT_NS = Cfg::NS, NSUB = Cfg::NSUB;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE;
@@ -122,42 +135,53 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
       tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
     }
     __syncwarp();
-    tmem_alloc_keep_permit(tmem_slot, 128);
-    tmem_alloc(tmem_slot + 1, 32);
+    if (D == 64) {
+      tmem_alloc_keep_permit(tmem_slot, Cfg::TMEM_MAIN);
+      tmem_alloc(tmem_slot + 1, 32);
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_MAIN);     // D = 128: S | O | P fit one 256-column allocation (two CTAs per SM)
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_BH;   // S at columns 0..63, O at 64..127
-  const uint32_t tmem_P = tmem_slot[1];                            // 128 x 64 bf16 = 32 columns
+  const uint32_t tmem_P = D == 64 ? tmem_slot[1] : tmem_base + AT_BH + D;   // 128 x 64 bf16 = 32 columns
 
   if (warp == 4) {
     if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE);
-      tma_load_4d(sQ, &p.tmQ, q_full, 0, head, q0, img);
+#pragma unroll
+      for (int sb = 0; sb < NSUB; ++sb) tma_load_4d(sQ + sb * AT_SUBQ, &p.tmQ, q_full, sb * AT_D, head, q0, img);
       int st = 0, ph = 1;
       for (int j = 0; j < H; ++j) {
         while (!mbar_try_wait(&kv_empty[st], ph)) __nanosleep(64);   // off the critical path: back off
         mbar_expect_tx(&kv_full[st], 2 * AT_KV);
-        tma_load_4d(sK + st * AT_KV, &p.tmK, &kv_full[st], 0, head, j * AT_BH, img);
-        tma_load_4d(sV + st * AT_KV, &p.tmV, &kv_full[st], 0, head, j * AT_BH, img);
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) {
+          tma_load_4d(sK + st * AT_KV + sb * AT_SUBKV, &p.tmK, &kv_full[st], sb * AT_D, head, j * AT_BH, img);
+          tma_load_4d(sV + st * AT_KV + sb * AT_SUBKV, &p.tmV, &kv_full[st], sb * AT_D, head, j * AT_BH, img);
+        }
         if (++st == AT_NS) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BH);             // N = 64 keys
-      const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64, B (= V) is MN-major
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      const uint32_t sK0 = smem_u32(sK), sV0 = smem_u32(sV);
+      const uint32_t idesc_o = umma_idesc_bf16(AT_D, 128, 0, 1);   // N = 64 (per 64-channel half), B (= V) is MN-major
+      const uint32_t sQ0 = smem_u32(sQ), sK0 = smem_u32(sK), sV0 = smem_u32(sV);
       int qst = 0, qph = 0;            // K/V stage (and its phase) of the next Q K^T
       auto issue_qk = [&]() {
         mbar_wait(&kv_full[qst], qph);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(sK0 + qst * AT_KV);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        for (int sb = 0; sb < NSUB; ++sb) {        // contraction over the head channels: 64 per sub-tile
+          const uint64_t qdesc = umma_desc_sw128(sQ0 + sb * AT_SUBQ);
+          const uint64_t kdesc = umma_desc_sw128(sK0 + qst * AT_KV + sb * AT_SUBKV);
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (sb | k) != 0);
+        }
         umma_commit(s_full);
         if (++qst == AT_NS) { qst = 0; qph ^= 1; }
       };
@@ -173,9 +197,12 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
         mbar_wait(p_full, h & 1);      // P_h is in smem
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < AT_BH / 16; ++ks) {
-          const uint64_t vdesc = umma_desc_sw128(sV0 + st * AT_KV + ks * 2048);
-          umma_bf16_ts(tmem_O, tmem_P + ks * 8, vdesc, idesc_o, (h | ks) != 0);     // O accumulates in TMEM
+        for (int sb = 0; sb < NSUB; ++sb) {        // output channels: one N = 64 half per V sub-tile
+#pragma unroll
+          for (int ks = 0; ks < AT_BH / 16; ++ks) {
+            const uint64_t vdesc = umma_desc_sw128(sV0 + st * AT_KV + sb * AT_SUBKV + ks * 2048);
+            umma_bf16_ts(tmem_O + sb * AT_D, tmem_P + ks * 8, vdesc, idesc_o, (h | ks) != 0);   // O accumulates in TMEM
+          }
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
         if (rescale) {
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < AT_D; c += 16) {
+          for (int c = 0; c < D; c += 16) {
             uint32_t t[16];
             tmem_ld16(tmem_O + lane_addr + c, t);
             tmem_ld_wait();
@@ -286,12 +313,12 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
     const float inv = 1.0f / l_run;
     __nv_bfloat16* orow = p.out + ((size_t)img * p.Nq + q0 + r) * p.ldo + head * p.d;
 #pragma unroll
-    for (int c = 0; c < AT_D; c += 32) {
+    for (int c = 0; c < D; c += 32) {
       uint32_t t[32];
       tmem_ld32(tmem_O + lane_addr + c, t);
       tmem_ld_wait();
       if (q0 + r < p.Nq) {
-        if (p.d == AT_D) {
+        if (p.d == D) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8)
             *reinterpret_cast<uint4*>(orow + c + i) =
@@ -313,8 +340,8 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_flash_kernel(const __grid_
   if (warp == 4) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc(tmem_base, 128);
-    tmem_dealloc(tmem_P, 32);
+    tmem_dealloc(tmem_base, Cfg::TMEM_MAIN);
+    if (D == 64) tmem_dealloc(tmem_P, 32);
   }
 }
 
@@ -505,7 +532,7 @@ using namespace lkgd;
 static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                           void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
                           int32_t Nk, float scale, float* lse, void* stream) {
-  if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d > AT_D || d % 8 || d <= 0) return LKGD_ESHAPE;
+  if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d % 8 || d <= 0 || (d > AT_D && d != 128)) return LKGD_ESHAPE;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return LKGD_EALIGN;
   if (heads > 65535 || n_img > 65535) return LKGD_ESHAPE;
   AttnParams p;
@@ -517,26 +544,32 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  constexpr int AT_SMEM = AttnCfg<64>::SMEM, AT_SMEM128 = AttnCfg<128>::SMEM;
   static DeviceOnce attr;
   if (attr.first()) {
-    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<-1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM128);
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d == 128) {
+    attn_flash_kernel<3, 128><<<grid, AT_THREADS, AT_SMEM128, st>>>(p);
+    return launch_epilogue();
+  }
   // tuning switch (tools/bench_attn.py, LKGD_ATTN_POLY_AB): -1 scalar formulation, 0 packed without offload, 3 / 4 every
   // third / fourth pair on the FMA pipes.  Measured in one process at L0 / L1: -1: 7.15 / 0.90 ms, 0: 7.33 / 0.90,
   // 4: 6.63 / 0.81, 3: 6.60 / 0.81.
   const char* pe = getenv("LKGD_ATTN_POLY");
   const int poly = pe ? atoi(pe) : 3;
   switch (poly) {
-    case -1: attn_flash_kernel<-1><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
-    case 0: attn_flash_kernel<0><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
-    case 4: attn_flash_kernel<4><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
-    default: attn_flash_kernel<3><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case -1: attn_flash_kernel<-1, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case 0: attn_flash_kernel<0, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case 4: attn_flash_kernel<4, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    default: attn_flash_kernel<3, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
   }
   return launch_epilogue();
 }
@@ -567,12 +600,14 @@ extern "C" int lkgd_attention_temporal(const void* qkv, void* out, int32_t B, in
   static DeviceOnce attr;
   if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_temporal_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * TAttn<64>::TILE);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * TAttn<128>::TILE);
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   switch (d) {
     case 16: attn_temporal_kernel<16><<<grid, 128, 4 * 3 * TAttn<16>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
     case 32: attn_temporal_kernel<32><<<grid, 128, 4 * 3 * TAttn<32>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
     case 64: attn_temporal_kernel<64><<<grid, 128, 4 * 3 * TAttn<64>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
+    case 128: attn_temporal_kernel<128><<<grid, 128, 4 * 3 * TAttn<128>::TILE, st>>>(x, o, B, F, HW, heads, sl2); break;
     default: return LKGD_ESHAPE;
   }
   return launch_epilogue();

@@ -230,7 +230,9 @@ def _attn_ref(q, k, v, n_img, heads, d, Nq, Nk):
 
 
 @pytest.mark.parametrize("n_img,heads,d,N", [(2, 2, 64, 128), (2, 5, 64, 576), (3, 2, 16, 1024), (1, 4, 32, 144),
-                                             (2, 10, 64, 2304), (1, 1, 64, 100)])
+                                             (2, 10, 64, 2304), (1, 1, 64, 100),
+                                             # d = 128: the reference-default heads (5,10,10,20) at level 2
+                                             (2, 10, 128, 576), (1, 2, 128, 100), (3, 1, 128, 1090)])
 def test_attention_self(cuda, n_img, heads, d, N):
     from lkgd_b200 import ops
     Cn = heads * d
@@ -253,11 +255,12 @@ def test_attention_cross_kv_len(cuda):
     assert rel_l2(out.float(), chk.float()) < 6e-3
 
 
+@pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("Nk", [1, 5, 63, 64, 65, 129])
-def test_attention_short_and_ragged_kv(cuda, Nk):
+def test_attention_short_and_ragged_kv(cuda, Nk, d):
     """KV lengths around the 64-key step of the softmax pipeline (single partial step, exactly one step, one key over)."""
     from lkgd_b200 import ops
-    n_img, heads, d, Nq = 2, 2, 64, 200
+    n_img, heads, Nq = 2, 2, 200
     q = rnd(n_img * Nq, heads * d, dev=cuda)
     k = rnd(n_img * Nk, heads * d, dev=cuda, seed=1)
     v = rnd(n_img * Nk, heads * d, dev=cuda, seed=2)
@@ -297,7 +300,7 @@ def test_attention_svd_l0_vs_checker(cuda):
 
 
 @pytest.mark.parametrize("B_,Fr,HW,heads,d", [(2, 8, 64, 2, 16), (2, 25, 144, 5, 64), (1, 14, 100, 4, 32),
-                                              (1, 1, 40, 2, 64)])
+                                              (1, 1, 40, 2, 64), (2, 25, 72, 10, 128), (1, 14, 33, 1, 128)])
 def test_attention_temporal(cuda, B_, Fr, HW, heads, d):
     from lkgd_b200 import ops
     Cn = heads * d

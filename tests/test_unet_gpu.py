@@ -362,3 +362,55 @@ def test_cuda_graph_replay_equals_the_eager_loop(cuda):
               "host-issued launches with the graph:", launches)
         assert err < 1e-5
         assert bool(torch.isfinite(graphed).all())
+
+
+def test_unet_reference_default_heads_d128(cuda):
+    """The reference's DEFAULT `num_attention_heads=(5, 10, 10, 20)` (models/unet_spatio_temporal_condition_controlnet.py:93)
+    gives 1280 / 10 = 128-wide heads at level 2.  Same head layout at a quarter of the widths (80/160/320/320 channels:
+    d = 16 / 16 / 32 ... would not reach 128), so: three levels of 64 / 128 / 256 channels with heads (1, 2, 2) ->
+    d = 64 / 64 / 128, spatial, temporal and KV>1 cross attention on the d = 128 path."""
+    import oracle as O
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(sample_size=32, in_channels=8, out_channels=4,
+               down_block_types=("CrossAttnDownBlockSpatioTemporal",) * 3,
+               up_block_types=("CrossAttnUpBlockSpatioTemporal",) * 3,
+               block_out_channels=(64, 128, 256), addition_time_embed_dim=32, projection_class_embeddings_input_dim=96,
+               layers_per_block=1, cross_attention_dim=64, transformer_layers_per_block=1,
+               num_attention_heads=(1, 2, 2), num_frames=6, time_context_order="b_major")
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    assert p.down_blocks[2].attentions[0].dim_head == 128
+    x, ctx, ids = _inputs(cfg, 2, 6, 32, 48, 64)
+    with torch.no_grad():
+        ref = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+    got = p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(got, ref)
+    print("d=128 heads rel_l2", err)
+    assert err < 1e-2
+    ctx3 = torch.randn(2, 3, 64, generator=torch.Generator().manual_seed(5))       # KV length 3: general cross-attention
+    with torch.no_grad():
+        ref3 = o(x, 0.9, ctx3, added_time_ids=ids, return_dict=False)[0]
+    got3 = p(x.to(cuda), 0.9, ctx3.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    assert rel_l2(got3, ref3) < 1e-2
+
+
+def test_default_constructed_unet_runs(cuda):
+    """a default-constructed UNet (reference-default heads (5,10,10,20), d = 128 at level 2) must run."""
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    with torch.device("meta"):
+        u = UNetSpatioTemporalConditionControlNetModel(num_frames=2)
+    u = u.to_empty(device=cuda)
+    g = torch.Generator(device=cuda).manual_seed(0)
+    with torch.no_grad():
+        for n, p_ in u.named_parameters():
+            if p_.ndim >= 2:
+                p_.copy_((torch.rand(p_.shape, generator=g, device=cuda) * 2 - 1) * p_[0].numel() ** -0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p_.fill_(1.0)
+            else:
+                p_.zero_()
+    u.invalidate()
+    assert u.config.num_attention_heads == (5, 10, 10, 20)
+    x = torch.randn(1, 2, 8, 16, 16, device=cuda)
+    out = u(x, 1.0, torch.randn(1, 1, 1024, device=cuda), added_time_ids=torch.tensor([[6.0, 127.0, 0.02]], device=cuda),
+            return_dict=False)[0]
+    assert tuple(out.shape) == (1, 2, 4, 16, 16) and bool(torch.isfinite(out).all())
