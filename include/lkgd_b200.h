@@ -113,6 +113,11 @@ typedef struct lkgd_gemm_args {
    * re-reads the tensor for its statistics. */
   double* gn_stats;   /* NULL = off                                           */
   int32_t gn_rows;
+  /* Optional bf16 copy of an fp32 output, [M, ldo2] (NULL = off; n_store % 8 == 0, ldo2 % 8 == 0): the tensor stays in the
+   * fp32 residual stream AND is the A operand of the next GEMM without a separate narrowing pass - the ControlNet's skip
+   * tensors feeding its zero convs (models/controlnet_sdv.py:558-571). */
+  void* out2;
+  int32_t ldo2;
 } lkgd_gemm_args;
 
 LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);

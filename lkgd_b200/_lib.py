@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("act", i32), ("s0", f32), ("res1", vp), ("ldr1", i32), ("s1", f32),
         ("res2", vp), ("ldr2", i32), ("s2", f32),
         ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32), ("res1_f32", i32), ("res2_f32", i32),
-        ("rv_ld", i32), ("gn_stats", vp), ("gn_rows", i32),
+        ("rv_ld", i32), ("gn_stats", vp), ("gn_rows", i32), ("out2", vp), ("ldo2", i32),
     ]
 
 

@@ -27,6 +27,13 @@ struct AttnParams {
   float* lse;       // optional [n_img, heads, Nq]: log2-domain log-sum-exp of the scaled scores (training backward)
 };
 
+// three-input maximum (FMNMX3): one ALU-pipe instruction per key pair of the row-maximum scan instead of two
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -235,8 +242,12 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
       }
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < AT_BH; i += 2)
-        m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+      for (int i = 0; i < AT_BH; i += 2) {
+        if (POLY == 4)      // A/B: the two-instruction form (POLY = 4 is the comparison variant of tools/bench_attn.py)
+          m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+        else
+          m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+      }
       const float m_blk = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
       // lazy rescale: decided now, applied to O (below) only after P_{h-1} V_{h-1} has landed
       float alpha = 1.0f;
@@ -269,7 +280,8 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
         for (int j = 0; j < AT_BH / 2; ++j) {
           const uint64_t X = at_fma2(at_pk2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), SC2, NM2);
           uint64_t P;
-          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+          constexpr int PEFF = POLY == 4 ? 3 : POLY;      // POLY = 4: the r01 kernel (every third pair, two-instruction max)
+          if (PEFF > 0 && (j % (PEFF > 0 ? PEFF : 1)) == PEFF - 1) {
             P = at_exp2_poly2(X);
           } else {
             float x0, x1;
@@ -560,9 +572,8 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
     attn_flash_kernel<3, 128><<<grid, AT_THREADS, AT_SMEM128, st>>>(p);
     return launch_epilogue();
   }
-  // tuning switch (tools/bench_attn.py, LKGD_ATTN_POLY_AB): -1 scalar formulation, 0 packed without offload, 3 / 4 every
-  // third / fourth pair on the FMA pipes.  Measured in one process at L0 / L1: -1: 7.15 / 0.90 ms, 0: 7.33 / 0.90,
-  // 4: 6.63 / 0.81, 3: 6.60 / 0.81.
+  // tuning switch (tools/bench_attn.py, LKGD_ATTN_POLY_AB): -1 scalar formulation, 0 packed without offload, 3 every
+  // third pair on the FMA pipes + FMNMX3 row maximum, 4 = 3 with the two-instruction maximum (the r01 kernel).
   const char* pe = getenv("LKGD_ATTN_POLY");
   const int poly = pe ? atoi(pe) : 3;
   switch (poly) {

@@ -84,6 +84,7 @@ __global__ void gemm_check_kernel(const lkgd_gemm_args a) {
                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res2)[m * a.ldr2 + n_out]));
   if (a.out_f32) reinterpret_cast<float*>(a.out)[m * a.ldo + n_out] = v;
   else reinterpret_cast<__nv_bfloat16*>(a.out)[m * a.ldo + n_out] = __float2bfloat16(v);
+  if (a.out2 && a.out_f32) reinterpret_cast<__nv_bfloat16*>(a.out2)[m * a.ldo2 + n_out] = __float2bfloat16(v);
 }
 
 // one thread per (image, head, query); two passes over the keys (max, then exp-sum + PV), d <= 128

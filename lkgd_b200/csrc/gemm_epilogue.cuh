@@ -295,6 +295,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       }
       __syncwarp();            // every lane has consumed its residual row before the buffer is reused for the output
     }
+    if (OES == 4 && p.out2 != nullptr && m >= 0) {
+      // bf16 copy of the fp32 output for the GEMM that reads this tensor next (ControlNet zero convs over the skips):
+      // the owning lane writes its row's 16 columns as one 32-byte sector, straight from registers
+      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)m * p.ldo2 + n_out;
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        if (n_out + 8 * q < n_store)
+          *reinterpret_cast<uint4*>(o2 + 8 * q) =
+              make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+      }
+    }
     if (p.fast_io) {
       // stage the output chunk (row per lane), then write it out with 16-byte pieces coalesced along rows
       const uint32_t own = buf + lane * OB;

@@ -57,6 +57,8 @@ struct GemmParams {
   int fast_io;                         // 1: every out / residual row segment is 16-byte addressable
   double* gn_stats;                    // fused GroupNorm statistics [frames][N][2] (nullptr = off)
   int gn_rows;                         // rows per frame image
+  void* out2;                          // optional bf16 copy of an fp32 output
+  int ldo2;
 };
 
 __device__ __forceinline__ int rowvec_index(int mode, int m, int HW, int F, int B) {
@@ -446,6 +448,13 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
     if (a->res2) { const int es = a->res2_f32 ? 4 : 2; ok = ok && aligned16(a->res2) && ((size_t)a->ldr2 * es) % 16 == 0 && (n_store * es) % 16 == 0; }
     if ((a->bias && !aligned16(a->bias)) || (a->rowvec && !aligned16(a->rowvec))) return LKGD_EALIGN;
     p.fast_io = ok ? 1 : 0;
+  }
+  p.out2 = a->out2; p.ldo2 = a->ldo2;
+  if (a->out2 != nullptr) {
+    const int n_cols = geglu ? a->N / 2 : a->N;
+    const int n_store = a->n_store > 0 ? a->n_store : n_cols;
+    if (!a->out_f32 || geglu || n_store % 8) return LKGD_ESHAPE;
+    if (!aligned16(a->out2) || a->ldo2 % 8 || a->ldo2 < n_store) return LKGD_EALIGN;
   }
   p.gn_stats = a->gn_stats; p.gn_rows = a->gn_rows;
   if (a->gn_stats != nullptr) {

@@ -280,8 +280,10 @@ class Conditioning:
         return self.xt_all[:, pc.off:pc.off + pc.wov.shape[0]]
 
 
-def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor], g: Geom, cond: Conditioning):
-    """x (and skip) are fp32 stream tensors; returns the fp32 block output."""
+def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor], g: Geom, cond: Conditioning,
+                 want_bf16: bool = False):
+    """x (and skip) are fp32 stream tensors; returns the fp32 block output (``want_bf16``: and its bf16 copy, written
+    by the same epilogue)."""
     temb_s = cond.temb(p.off_s, p.cout)
     temb_t = cond.temb(p.off_t, p.cout)
     # blocks with a 1x1 shortcut conv need their raw (concatenated) input as a bf16 GEMM operand: the GroupNorm pass
@@ -314,7 +316,7 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
     t = ops.groupnorm(t, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True)
     # alpha*s + (1-alpha)*(s + conv2(t)) == s + (1-alpha)*conv2(t)
     return ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=s, s1=1.0,
-                    out_f32=True, gn_rows=g.HW)
+                    out_f32=True, gn_rows=g.HW, want_bf16=want_bf16)
 
 
 def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor):
@@ -328,7 +330,8 @@ def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom,
     return ops.gemm(a, wo, bias=pc.bo, res1=h, out_f32=True)
 
 
-def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Conditioning, tctx_mode: int):
+def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Conditioning, tctx_mode: int,
+                    want_bf16: bool = False):
     C = p.c
     kv1 = cond.ctx.shape[1] == 1
     h = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False)
@@ -374,7 +377,7 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t); bf16 because proj_out reads it as its GEMM operand
     mix = dense(ff, p.t_ff2, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
     # the next resblock's GroupNorm consumes this tensor: fused statistics where a 128-row tile stays inside a frame
-    return dense(mix, p.proj_out, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0)
+    return dense(mix, p.proj_out, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0, want_bf16=want_bf16)
 
 
 class PackedUNet:
@@ -459,29 +462,41 @@ class PackedUNet:
         ops.axpy_f32(a, e)
         return e
 
-    def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None):
-        """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms)."""
-        x = ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b, res1=stem_add,
-                     out_f32=True, gn_rows=g.HW)
-        skips, geoms = [x], [g]
+    def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None,
+                bf16_skips: bool = False):
+        """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms, geometry of
+        the mid block).  ``bf16_skips``: every skip tensor and the mid output are ``(fp32, bf16 copy)`` pairs - the copy
+        is written by the epilogue that produces the tensor and feeds the ControlNet's zero convs without a narrowing pass
+        (the downsampler also reads it instead of narrowing its input itself)."""
+        wb = bf16_skips
+
+        def both(t):                 # (fp32, bf16) -> fp32 stream tensor, bf16 copy (None when not requested)
+            return t if wb else (t, None)
+
+        x, xb = both(ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b,
+                              res1=stem_add, out_f32=True, gn_rows=g.HW, want_bf16=wb))
+        skips, geoms = [(x, xb) if wb else x], [g]
         for res, att, ds in self.down:
             for i, r in enumerate(res):
-                x = run_resblock(r, x, None, g, cond)
                 if att is not None:
-                    x = run_transformer(att[i], x, g, cond, self.tctx_mode)
-                skips.append(x)
+                    x = run_resblock(r, x, None, g, cond)
+                    x, xb = both(run_transformer(att[i], x, g, cond, self.tctx_mode, want_bf16=wb))
+                else:
+                    x, xb = both(run_resblock(r, x, None, g, cond, want_bf16=wb))
+                skips.append((x, xb) if wb else x)
                 geoms.append(g)
             if ds is not None:
-                x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1],
-                             out_f32=True, gn_rows=g.down().HW)
+                x, xb = both(ops.gemm(xb if xb is not None else ops.cast_bf16(x), ds[0], mode=A_CONV3X3,
+                                      conv=(g.BF, g.H, g.W, 2), bias=ds[1], out_f32=True, gn_rows=g.down().HW,
+                                      want_bf16=wb))
                 g = g.down()
-                skips.append(x)
+                skips.append((x, xb) if wb else x)
                 geoms.append(g)
         res, att = self.mid
         x = run_resblock(res[0], x, None, g, cond)
-        for a, r in zip(att, res[1:]):
+        for j, (a, r) in enumerate(zip(att, res[1:])):
             x = run_transformer(a, x, g, cond, self.tctx_mode)
-            x = run_resblock(r, x, None, g, cond)
+            x = run_resblock(r, x, None, g, cond, want_bf16=wb and j == len(att) - 1)
         return x, skips, geoms, g
 
     def decoder(self, x: torch.Tensor, skips: List[torch.Tensor], g: Geom, cond: Conditioning) -> torch.Tensor:

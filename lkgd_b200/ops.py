@@ -72,8 +72,12 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
          rowvec: Optional[torch.Tensor] = None, rv: Tuple[int, int, int, int] = (RV_NONE, 1, 1, 1),
          act: int = ACT_NONE, s0: float = 1.0, res1: Optional[torch.Tensor] = None, s1: float = 1.0,
          res2: Optional[torch.Tensor] = None, s2: float = 1.0, out: Optional[torch.Tensor] = None,
-         out_f32: bool = False, n_store: int = 0, checker: bool = False, gn_rows: int = 0) -> torch.Tensor:
+         out_f32: bool = False, n_store: int = 0, checker: bool = False, gn_rows: int = 0,
+         out2: Optional[torch.Tensor] = None, want_bf16: bool = False):
     """out = s0*act(A (*) Bw^T [+ A1 Bw1^T] + bias + rowvec[g(m)]) + s1*res1 + s2*res2   (see lkgd_gemm).
+
+    ``want_bf16`` (fp32 outputs): also write a bf16 copy of the output in the same epilogue and return ``(out, out2)``
+    (``out2`` may be given); the copy is the A operand of the GEMM that reads this tensor next.
 
     ``gn_rows`` > 0 (fp32 outputs): also accumulate the GroupNorm statistics of the output per (frame image of
     ``gn_rows`` rows, channel) in the epilogue; they travel with the returned tensor (``gn_stats_of``) and let the
@@ -145,6 +149,14 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     a.out, a.ldo, a.out_f32, a.n_store = out.data_ptr(), out.stride(0), int(out_f32), n_store
     a.res1_f32 = int(res1 is not None and res1.dtype == torch.float32)
     a.res2_f32 = int(res2 is not None and res2.dtype == torch.float32)
+    if want_bf16 or out2 is not None:
+        if not out_f32:
+            raise ValueError("want_bf16 / out2: the primary output must be fp32")
+        if out2 is None:
+            out2 = torch.empty((M, n_out), device=A.device, dtype=bf16)
+        elif out2.dtype != bf16 or out2.dim() != 2 or out2.shape[0] != M or out2.stride(1) != 1 or not out2.is_cuda:
+            raise ValueError("out2 must be a bf16 [M, >=n] row-major CUDA matrix")
+        a.out2, a.ldo2 = out2.data_ptr(), out2.stride(0)
     lib = L.load()
     fn = lib.lkgd_gemm_simt_check if checker else lib.lkgd_gemm
     stats = None
@@ -156,7 +168,7 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
                        "K": taps * a.K0 + a.K1}
     L.check(fn(C.byref(a), _stream()), "lkgd_gemm")
     _set_gn_stats(out, stats, gn_rows)
-    return out
+    return (out, out2) if out2 is not None else out
 
 
 class _StatsArena:

@@ -146,9 +146,13 @@ class StableVideoDiffusionPipeline:
         g = Geom(st["n_batch"], st["F"], st["h"], st["w"])
         kw = {}
         if st["controlnet_condition"] is not None:
-            down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
-                                                       st["controlnet_condition"], st["controlnet_cond_scale"])
-            kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
+            if st.get("fuse_controlnet", True):
+                # residual injection fused into the UNet forward: the ControlNet's zero convs add onto the UNet's skips
+                kw = dict(fused_controlnet=(self.controlnet, st["controlnet_condition"], st["controlnet_cond_scale"]))
+            else:   # the reference's hand-off: 12 + 1 residual tensors, added by the UNet (:585-607)
+                down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
+                                                           st["controlnet_condition"], st["controlnet_cond_scale"])
+                kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
         rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
                                    added_time_ids=st["added_time_ids"], **kw)
         return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
@@ -241,13 +245,14 @@ class StableVideoDiffusionPipeline:
                  domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
                  cfg_pair=None, output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
                  return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, fuse_controlnet: bool = True):
         if output_type != "latent":
             raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
                              "VAE of your choice (SURVEY.md section 8f, N1)")
         st = self.prepare(image_embeddings, image_latents, num_frames, num_inference_steps, min_guidance_scale,
                           max_guidance_scale, fps, motion_bucket_id, noise_aug_strength, num_videos_per_prompt,
                           controlnet_condition, controlnet_cond_scale, domain_features, flow_features, cfg_pair)
+        st["fuse_controlnet"] = fuse_controlnet
         device = self.unet.device
         latents = self.prepare_latents(st["S"], st["F"], self.unet.config.in_channels, st["h"], st["w"],
                                        torch.float32, device, generator, latents).to(torch.float32).contiguous()

@@ -296,14 +296,23 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor, *extra,
                        down_block_additional_residuals=None, mid_block_additional_residual=None,
-                       added_time_ids: torch.Tensor = None, batch_slice: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                       added_time_ids: torch.Tensor = None, batch_slice: Optional[Tuple[int, int]] = None,
+                       fused_controlnet=None) -> torch.Tensor:
         """Engine-layout forward.  ``x``: bf16 channels-last rows [B*F*H*W, 64] (input channels zero-padded to 64,
         see ``ops.pack_input``).  Returns the fp32 channels-last prediction [B*F*H*W, out_channels].
 
         ``batch_slice=(lo, hi)``: ``x`` holds only rows ``lo:hi`` of the batch that ``encoder_hidden_states`` /
         ``added_time_ids`` (and the LKGD features) describe - the CFG pair split across two GPUs.  The
         conditioning is computed for the whole batch (it is microscopic) so that the temporal cross-attention can
-        index every half's context exactly like the unsplit reference batch does (diffusers 0.27.2 quirk F8)."""
+        index every half's context exactly like the unsplit reference batch does (diffusers 0.27.2 quirk F8).
+
+        ``fused_controlnet=(controlnet, controlnet_cond, conditioning_scale)``: ControlNet residual injection FUSED into
+        this forward (BASELINE.json configs[3]).  The UNet's encoder runs first; the ControlNet then runs on the same
+        packed input and its 12 + 1 zero 1x1 convs (models/controlnet_sdv.py:558-571) add ``m_i * scale * conv(skip_cn)``
+        straight onto this UNet's skip tensors in their GEMM epilogue (residual read + fused GroupNorm statistics of the
+        sum, F6 multipliers folded into the epilogue scale) - no residual tensors, no axpby passes, no narrowing passes,
+        and the decoder's GroupNorms keep their one-read path
+        (models/unet_spatio_temporal_condition_controlnet.py:453-462,472-473)."""
         if added_time_ids is None:
             raise ValueError("added_time_ids is required")
         pk = self.packed()
@@ -323,7 +332,17 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
             raise ValueError("encoder_hidden_states / added_time_ids batch does not match sample")
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), ids)
         cond = Conditioning(pk, emb, ctx_all, ctx_t)
+        x_in = x
         x, skips, geoms, gm = pk.encoder(x, g, cond)
+        if fused_controlnet is not None:
+            if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
+                    or batch_slice is not None:
+                raise ValueError("fused_controlnet excludes explicit residuals and batch_slice")
+            cn, cn_cond, cn_scale = fused_controlnet
+            per_block = [len(d[0]) + (1 if d[2] is not None else 0) for d in pk.down]
+            per_block[0] += 1
+            mult = residual_multipliers(len(pk.down), per_block)
+            x = cn.inject_packed(x_in, g, timestep, encoder_hidden_states, ids, cn_cond, cn_scale, skips, mult, x)
         if mid_block_additional_residual is not None:
             ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)
         if down_block_additional_residuals is not None:
@@ -736,12 +755,16 @@ class ControlNetSDVModel(_Base):
                 getattr(net, name).load_state_dict(getattr(unet, name).state_dict())
         return net.to(unet.device)
 
+    COND_CPAD = 8      # channels of the packed condition frames (2 = flow, 3 = depth / rgb, zero-padded to 16 bytes)
+
     def _cn_pack(self):
         if getattr(self, "_cn", None) is None:
             ce = self.controlnet_cond_embedding
             convs = [ce.conv_in] + list(ce.blocks) + [ce.conv_out]
             packed = []
-            cin_pad = 64
+            cin_pad = self.COND_CPAD
+            if ce.conv_in.in_channels > cin_pad:
+                raise ValueError(f"conditioning_channels > {cin_pad} is not supported")
             for cv in convs:
                 cout = cv.out_channels
                 cout_pad = (cout + 15) // 16 * 16
@@ -753,14 +776,9 @@ class ControlNetSDVModel(_Base):
             self._cn = (packed, zero)
         return self._cn
 
-    @ops.on_own_device
-    @torch.no_grad()
-    def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
-                       added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor] = None,
-                       conditioning_scale: float = 1.0):
-        """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
+    def _encode(self, x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond, bf16_skips):
+        """Condition encoder (pixel resolution, models/controlnet_sdv.py:98-119) + the copied UNet encoder + mid block."""
         pk = self.packed()
-        ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         convs, zero = self._cn_pack()
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
         cond = Conditioning(pk, emb, encoder_hidden_states.to(torch.float32).contiguous())
@@ -769,7 +787,9 @@ class ControlNetSDVModel(_Base):
             if controlnet_cond.ndim != 5:
                 raise ValueError("controlnet_cond must be [batch, frames, channels, height, width]")
             b_, f_, cc, hc, wc = controlnet_cond.shape
-            e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=64)
+            # 2 / 3 condition channels padded to 8 (one 16-byte pixel), not to a 64-channel k-block: the TMA box
+            # zero-fills the rest of the k-block on chip, HBM sees 16 bytes per pixel instead of 128
+            e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=self.COND_CPAD)
             hh, ww = hc, wc
             for i, (w, b, stride, _) in enumerate(convs):
                 last = i == len(convs) - 1
@@ -780,12 +800,43 @@ class ControlNetSDVModel(_Base):
             if (hh, ww) != (g.H, g.W) or b_ * f_ != g.BF:
                 raise ValueError("controlnet_cond resolution must be 8x the latent resolution")
             stem_add = e
-        x, skips, geoms, gm = pk.encoder(x, g, cond, stem_add=stem_add)
+        return pk.encoder(x, g, cond, stem_add=stem_add, bf16_skips=bf16_skips), zero
+
+    @ops.on_own_device
+    @torch.no_grad()
+    def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
+                       added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor] = None,
+                       conditioning_scale: float = 1.0):
+        """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
+        ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
+        (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
+                                                    controlnet_cond, bf16_skips=True)
         s = float(conditioning_scale)
-        down = [ChannelsLast(ops.gemm(ops.cast_bf16(sk), w, bias=b, s0=s), gs.BF, gs.H, gs.W)
-                for sk, (w, b), gs in zip(skips, zero[:-1], geoms)]
-        mid = ChannelsLast(ops.gemm(ops.cast_bf16(x), zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
+        down = [ChannelsLast(ops.gemm(skb, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
+                for (_, skb), (w, b), gs in zip(skips, zero[:-1], geoms)]
+        mid = ChannelsLast(ops.gemm(xm[1], zero[-1][0], bias=zero[-1][1], s0=s), gm.BF, gm.H, gm.W)
         return down, mid
+
+    @torch.no_grad()
+    def inject_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
+                      added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor], conditioning_scale: float,
+                      unet_skips: List[torch.Tensor], multipliers: Sequence[int], unet_mid: torch.Tensor) -> torch.Tensor:
+        """The fused form of ``forward_packed`` + the UNet's residual adds: every zero conv writes
+        ``unet_skip += m_i * scale * (W skip_cn + b)`` in place in its epilogue (fp32 residual read, fused GroupNorm
+        statistics of the sum where a 128-row tile stays inside one frame), the mid zero conv does the same on the UNet's
+        mid sample, which is returned.  Runs inside the UNet's forward: shares its statistics arena (no ``begin``).
+        zip truncation as in the reference (:453-462): extra skips / residuals are ignored."""
+        (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
+                                                    controlnet_cond, bf16_skips=True)
+        s = float(conditioning_scale)
+        for i, ((_, skb), (w, b), gs, m, us) in enumerate(zip(skips, zero[:-1], geoms, multipliers, unet_skips)):
+            if us.shape != (gs.M, w.shape[0]):
+                raise ValueError("ControlNet and UNet skip shapes differ")
+            ops.gemm(skb, w, bias=b, s0=s * float(m), res1=us, s1=1.0, out=us, out_f32=True,
+                     gn_rows=gs.HW if gs.HW % 128 == 0 else 0)
+        ops.gemm(xm[1], zero[-1][0], bias=zero[-1][1], s0=s, res1=unet_mid, s1=1.0, out=unet_mid, out_f32=True,
+                 gn_rows=gm.HW if gm.HW % 128 == 0 else 0)
+        return unet_mid
 
     @ops.on_own_device
     @torch.no_grad()

@@ -414,3 +414,47 @@ def test_default_constructed_unet_runs(cuda):
     out = u(x, 1.0, torch.randn(1, 1, 1024, device=cuda), added_time_ids=torch.tensor([[6.0, 127.0, 0.02]], device=cuda),
             return_dict=False)[0]
     assert tuple(out.shape) == (1, 2, 4, 16, 16) and bool(torch.isfinite(out).all())
+
+
+def test_fused_controlnet_injection_equals_the_residual_handoff(cuda):
+    """BASELINE.json configs[3] "residual injection fused into UNet blocks": the fused path (zero convs add
+    m_i * scale * conv(skip_cn) onto the UNet's skips in their epilogue, no residual tensors, no axpby) against (a) the
+    reference's hand-off through 12 + 1 residual tensors on the same kernels and (b) the fp32 oracle."""
+    import oracle as O
+    from lkgd_b200 import _lib, ops
+    from lkgd_b200.engine import Geom
+    from lkgd_b200.unet import REDUCED_CONFIG, ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    torch.manual_seed(7)
+    oc = O.ControlNetSDVModel.from_unet(o, conditioning_channels=3).eval()
+    _randomise_zero_inits(oc, seed=2)
+    pc = ControlNetSDVModel.from_unet(p, conditioning_channels=3)
+    pc.load_state_dict(oc.state_dict(), strict=True)
+    pc = pc.to(cuda)
+    x, ctx, ids = _inputs(cfg, 2, 8, 32, 32, 32)
+    cond = torch.rand(2, 8, 3, 256, 256, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    with torch.no_grad():
+        d_ref, m_ref = oc(x, 1.2, ctx, ids, controlnet_cond=cond, conditioning_scale=0.8, return_dict=False)
+        ref = o(x, 1.2, ctx, down_block_additional_residuals=d_ref, mid_block_additional_residual=m_ref,
+                added_time_ids=ids, return_dict=False)[0]
+    xc, cc, ic, condc = x.to(cuda), ctx.to(cuda), ids.to(cuda), cond.to(cuda)
+    pk = p.packed()
+    xr = ops.pack_input(xc, 1.0, None, N=2, Cpad=pk.cin_pad)
+    g = Geom(2, 8, 32, 32)
+    n0 = ops.launch_count()
+    _lib.PROF.records, _lib.PROF.enabled = [], True
+    rows = p.forward_packed(xr, g, 1.2, cc, added_time_ids=ic, fused_controlnet=(pc, condc, 0.8))
+    torch.cuda.synchronize()
+    _lib.PROF.enabled = False
+    names = [r[0] for r in _lib.PROF.records]
+    assert "lkgd_axpby" not in names and "lkgd_cast_bf16" not in names, set(names)      # nothing but GEMM epilogues
+    fused = ops.unpack_output(rows, 2, 8, 4, 32, 32)
+    down, mid = pc.forward_packed(xr, g, 1.2, cc, ic, condc, 0.8)
+    rows2 = p.forward_packed(xr, g, 1.2, cc, added_time_ids=ic, down_block_additional_residuals=down,
+                             mid_block_additional_residual=mid)
+    handoff = ops.unpack_output(rows2, 2, 8, 4, 32, 32)
+    print("fused vs hand-off", rel_l2(fused, handoff), "fused vs oracle", rel_l2(fused, ref), "launches", ops.launch_count() - n0)
+    assert rel_l2(fused, handoff) < 4e-3        # the hand-off rounds every residual to bf16 first; the fused add is fp32
+    assert rel_l2(fused, ref) < 1e-2
+    assert rel_l2(handoff, ref) < 1e-2
