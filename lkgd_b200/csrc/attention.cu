@@ -563,24 +563,24 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<-1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM128);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM128);
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d == 128) {
-    attn_flash_kernel<3, 128><<<grid, AT_THREADS, AT_SMEM128, st>>>(p);
+    attn_flash_kernel<4, 128><<<grid, AT_THREADS, AT_SMEM128, st>>>(p);
     return launch_epilogue();
   }
   // tuning switch (tools/bench_attn.py, LKGD_ATTN_POLY_AB): -1 scalar formulation, 0 packed without offload, 3 every
   // third pair on the FMA pipes + FMNMX3 row maximum, 4 = 3 with the two-instruction maximum (the r01 kernel).
   const char* pe = getenv("LKGD_ATTN_POLY");
-  const int poly = pe ? atoi(pe) : 3;
+  const int poly = pe ? atoi(pe) : 4;      // FMNMX3 (3) measured 3 % SLOWER than two FMNMX at L0 (6.18 vs 6.01 ms): half rate
   switch (poly) {
     case -1: attn_flash_kernel<-1, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
     case 0: attn_flash_kernel<0, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
-    case 4: attn_flash_kernel<4, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
-    default: attn_flash_kernel<3, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    case 3: attn_flash_kernel<3, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
+    default: attn_flash_kernel<4, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
   }
   return launch_epilogue();
 }

@@ -149,6 +149,166 @@ class _Base(nn.Module):
         self.invalidate()
         return hits
 
+    def add_adapter(self, adapter_config, adapter_name: str = "default") -> List[str]:
+        """``unet.add_adapter(LoraConfig(...), adapter_name)`` as the reference calls it
+        (train_models/train_svd_lora.py:1081-1102; run_models/run_inference_flow_lora.py:326-331).  ``adapter_config`` is
+        anything shaped like a peft ``LoraConfig`` (attributes or dict keys ``r``, ``lora_alpha``, ``init_lora_weights``,
+        ``target_modules``, ``layers_to_transform``, ``layers_pattern``) - peft itself is not needed.  Module selection
+        follows peft 0.10's ``check_target_module_exists``: a list of ``target_modules`` matches a module whose name equals
+        or ends with ``"." + target``, a string is a full-match regex; with ``layers_to_transform`` the module must also
+        sit under ``<layers_pattern>.<index>.`` with the index listed."""
+        def get(k, default=None):
+            if isinstance(adapter_config, dict):
+                return adapter_config.get(k, default)
+            return getattr(adapter_config, k, default)
+
+        r = get("r")
+        if not isinstance(r, int) or r <= 0:
+            raise ValueError(f"`r` should be a positive integer value but the value passed is {r}")
+        if get("lora_dropout", 0.0):
+            raise NotImplementedError("lora_dropout > 0 is not supported (the reference trains with 0.0)")
+        targets = get("target_modules")
+        if targets is None:
+            raise ValueError("Please specify `target_modules` in `peft_config`")
+        layers = get("layers_to_transform")
+        layers = [layers] if isinstance(layers, int) else layers
+        patterns = get("layers_pattern")
+        patterns = [patterns] if isinstance(patterns, str) else (list(patterns) if patterns else [])
+
+        def wanted(key: str) -> bool:
+            if isinstance(targets, str):
+                found = re.fullmatch(targets, key) is not None
+            else:
+                found = any(key == t or key.endswith("." + t) for t in targets)
+            if found and layers is not None:
+                m = None
+                if not patterns:
+                    m = re.match(r".*\.[^.]*\.(\d+)\.", key)
+                for pat in patterns:
+                    m = re.match(rf".*\.{pat}\.(\d+)\.", key)
+                    if m is not None:
+                        break
+                found = m is not None and int(m.group(1)) in layers
+            return found
+
+        names = [n for n, m in self.named_modules() if isinstance(m, M.Linear) and ".lora_" not in n
+                 and not n.endswith("base_layer") and wanted(n)]
+        taken = [n for n, m in self.named_modules() if isinstance(m, M.LoraLinear) and wanted(n)]
+        if taken:
+            raise ValueError(f"{len(taken)} target modules already carry an adapter (e.g. {taken[0]}): one adapter per "
+                             "module is supported")
+        if not names:
+            raise ValueError(f"Target modules {targets} not found in the base model. Please check the target modules "
+                             "and try again.")
+        alpha = get("lora_alpha", r)
+        return self._wrap_lora(names, r, r if alpha is None else alpha, get("init_lora_weights", True), adapter_name)
+
+    def _wrap_lora(self, names, r, lora_alpha, init_lora_weights, adapter_name):
+        for name in names:
+            parent_name, _, leaf = name.rpartition(".")
+            parent = self.get_submodule(parent_name) if parent_name else self
+            old = parent[int(leaf)] if leaf.isdigit() else getattr(parent, leaf)
+            if isinstance(old, M.LoraLinear):
+                raise ValueError(f"{name} already carries an adapter")
+            new = M.LoraLinear(old, r, lora_alpha, init_lora_weights, adapter_name)
+            if leaf.isdigit():
+                parent[int(leaf)] = new
+            else:
+                setattr(parent, leaf, new)
+        self.invalidate()
+        return list(names)
+
+    # -------------------------------------------------------------------- construction from reference artefacts
+    @classmethod
+    def from_config(cls, config, **overrides):
+        """Builds the module from a diffusers-style config (dict / namespace / ``FrozenDict``): keys the constructor does
+        not know (``_class_name``, ``_diffusers_version``, ``_name_or_path`` ...) are ignored like ``ConfigMixin`` does."""
+        import inspect
+        cfg = dict(config) if isinstance(config, dict) else dict(vars(config))
+        cfg.update(overrides)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items() if k in accepted}
+        return cls(**kw)
+
+    @classmethod
+    def from_reference(cls, module, device=None):
+        """Drop-in conversion of a live reference module (``models/unet_spatio_temporal_condition*.py`` /
+        ``models/controlnet_sdv.py`` instance, with or without peft LoRA wrappers): same config, same ``state_dict``
+        (run_models/run_inference.py:279-281 hands such instances to the pipeline)."""
+        net = cls.from_config(module.config)
+        sd = {k: v.detach() for k, v in module.state_dict().items()}
+        net._adopt_state_dict(sd)
+        dev = device if device is not None else next(iter(sd.values())).device
+        return net.to(dev)
+
+    def _adopt_state_dict(self, sd, strict: bool = True):
+        """load_state_dict that first creates the LoRA wrappers the checkpoint implies (``<m>.base_layer.weight`` +
+        ``<m>.lora_A.<adapter>.weight``; rank from the tensor shape, lora_alpha = rank as the reference configures it)."""
+        pat = re.compile(r"^(.*)\.lora_A\.([^.]+)\.weight$")
+        groups = {}
+        for k, v in sd.items():
+            m = pat.match(k)
+            if m:
+                groups.setdefault((m.group(2), v.shape[0]), []).append(m.group(1))
+        for (adapter, r), names in groups.items():
+            self._wrap_lora(names, r, r, "gaussian", adapter)
+        return self.load_state_dict(sd, strict=strict)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, device=None,
+                        torch_dtype=None, **config_overrides):
+        """``Model.from_pretrained(dir, subfolder="unet")`` for a LOCAL diffusers model directory (``config.json`` +
+        ``diffusion_pytorch_model.safetensors`` / ``.fp16.safetensors`` / ``.bin``), as run_models/run_inference.py:279-280
+        and train_svd_lora.py:1022-1027 call it.  There is no hub download here (no network): a repo id raises."""
+        import json
+        import os
+        root = pretrained_model_name_or_path
+        if subfolder:
+            root = os.path.join(root, subfolder)
+        cfg_path = os.path.join(root, "config.json")
+        if not os.path.isfile(cfg_path):
+            raise EnvironmentError(f"{cfg_path} not found: lkgd_b200 loads local diffusers model directories only "
+                                   "(download the checkpoint with the reference's tooling first)")
+        with open(cfg_path) as f:
+            config = json.load(f)
+        net = cls.from_config(config, **config_overrides)
+        for name in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors",
+                     "diffusion_pytorch_model.bin"):
+            path = os.path.join(root, name)
+            if os.path.isfile(path):
+                break
+        else:
+            raise EnvironmentError(f"no diffusion_pytorch_model.safetensors / .bin under {root}")
+        if path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            sd = load_file(path)
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+        net._adopt_state_dict(sd)
+        if torch_dtype is not None and torch_dtype != torch.float32:
+            # the engine keeps fp32 masters and packs bf16 operands itself; a half-precision checkpoint is upcast
+            pass
+        return net.to(device) if device is not None else net
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True):
+        """Writes ``config.json`` + ``diffusion_pytorch_model.safetensors`` in the diffusers layout (``from_pretrained``
+        here and ``ModelMixin.from_pretrained`` of the reference read it)."""
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(self.config).items()}
+        cfg["_class_name"] = type(self).__name__
+        cfg["_diffusers_version"] = "0.27.2"
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        sd = {k: v.detach().to("cpu").contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, "diffusion_pytorch_model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "diffusion_pytorch_model.bin"))
+        return save_directory
+
     def merge_lora(self):
         """W += scaling * B A (reference models/lora_layer.py:300-361)."""
         for m in self.modules():

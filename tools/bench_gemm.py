@@ -30,6 +30,10 @@ SHAPES = [
     ("tconv_L3_f32", "tconv", (2, 25, 144), 1280, 1280, "f32"),
     ("tconv_L0_res32", "tconv", (2, 25, 9216), 320, 320, "res32"),
     ("proj_L3_res32", "lin", 7200, 1280, 1280, "res32"),
+    # ControlNet condition encoder at pixel resolution (C4, 28 frames of 576x1024): thin layers
+    ("cond1_k8_silu", "conv", (28, 576, 1024), 16, 8, "silu"),
+    ("cond1_k64_silu", "conv", (28, 576, 1024), 16, 64, "silu"),
+    ("cond2_k16_silu", "conv", (28, 576, 1024), 16, 16, "silu"),
 ]
 
 
@@ -64,6 +68,8 @@ def run(shape, iters, flush, ab=None):
         bytes_ += M * N * 4
     elif epi == "f32":
         kw.update(out_f32=True)
+    elif epi == "silu":
+        kw.update(act=1)
     out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if out_b == 4 else bf16)
     for _ in range(2):
         ops.gemm(A, W, bias=bias, out=out, **kw)
