@@ -417,6 +417,41 @@ class LoraTrainer:
                 out.append((f"{base}.lora_B.{m.adapter_name}.weight", s["B"][i]))
         return out + list(self.lk_grads.items())
 
+    def state_tensors(self):
+        """(qualified name, fp32 parameter view, exp_avg view, exp_avg_sq view) of every trainable tensor, in the
+        module's ``named_parameters()`` order - the order the reference hands to its optimizer
+        (``filter(requires_grad, unet.parameters())``, train_svd_lora.py:1179; == train_svd_lora_train.txt)."""
+        base = self.flat_p.data_ptr()
+        by_name = {}
+        for name, g in self.named_grads():
+            off = (g.data_ptr() - self.flat_g.data_ptr()) // 4
+            n = g.numel()
+            by_name[name] = (self.flat_p[off:off + n].view(g.shape), self.flat_m[off:off + n].view(g.shape),
+                             self.flat_v[off:off + n].view(g.shape))
+        order = [n for n, _ in self.unet.named_parameters() if n in by_name]
+        if len(order) != len(by_name):
+            raise RuntimeError("trainable tensors are missing from the module's parameter list")
+        assert base == self.flat_p.data_ptr()
+        return [(n,) + by_name[n] for n in order]
+
+    def save_state(self, output_dir: str, global_step: int, lora_name: Optional[str] = None, **kw) -> str:
+        """``checkpoint-<global_step>`` directory as the reference's loop writes it (lkgd_b200/checkpoint.py)."""
+        from . import checkpoint
+        return checkpoint.save_state(self, output_dir, global_step, lora_name or self._adapter_name(), **kw)
+
+    def load_state(self, path: str, lora_name: Optional[str] = None, **kw) -> int:
+        from . import checkpoint
+        self._graph_stale()
+        return checkpoint.load_state(self, path, lora_name or self._adapter_name(), **kw)
+
+    def _adapter_name(self) -> str:
+        return self.layers[0].src.temporal_transformer_blocks[0].attn1.to_q.adapter_name
+
+    def _graph_stale(self):
+        """Parameters restored from a checkpoint are copied INTO the flat buffer the captured graphs read, so the graphs
+        stay valid; the latent-knowledge block's derived matrices are rebuilt inside the graph on every replay."""
+        return None
+
     # ---- one training step
     def forward_backward(self, latents: torch.Tensor, noise: torch.Tensor, sigmas: torch.Tensor,
                          cond_latents: torch.Tensor, encoder_hidden_states: torch.Tensor, added_time_ids: torch.Tensor,

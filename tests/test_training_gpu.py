@@ -215,3 +215,43 @@ def test_trained_adapters_survive_the_wire_format(cuda, tmp_path):
     a = p(x, 1.3, ctx, dom, flo, added_time_ids=ids).sample
     b = fresh(x, 1.3, ctx, dom, flo, added_time_ids=ids).sample
     assert torch.equal(a, b)
+
+
+def test_checkpoint_directory_round_trip(cuda, tmp_path):
+    """`checkpoint-<step>` directories (reference train_svd_lora.py:1702-1748 save, :1364-1387 resume) with
+    the real trainer: two steps -> save -> a fresh model + trainer resumes -> its third step equals the original's third
+    step bit for bit (same kernels, same Adam moments, same step count); the graph-captured trainer resumes too."""
+    import oracle as O
+    from lkgd_b200 import checkpoint as C
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionModel
+    cfg = dict(REDUCED_CONFIG, cross_attention_dim=1024)
+    lat, noise, cond, ctx, sig = _train_inputs(2, 8, 16, 16, 1024)
+    ids = O.add_time_ids_training(5, 127, 0.02, 2)
+    g = torch.Generator().manual_seed(2)
+    extra = (torch.randn(2, 1, 1000, generator=g), torch.randn(2, 1, 1000, generator=g))
+    batch = [t.to(cuda) for t in (lat, noise, sig, cond, ctx, ids) + extra]
+
+    def make(seed):
+        _, p = _pair(O.UNetSpatioTemporalConditionModel, UNetSpatioTemporalConditionModel, cfg, cuda, lora=dict(r=4),
+                     seed=seed)
+        return LoraTrainer(p, lr=1e-3)
+
+    a = make(0)
+    for _ in range(2):
+        a.train_step(*batch)
+    path = a.save_state(str(tmp_path), global_step=80, checkpoints_total_limit=3)
+    assert sorted(__import__("os").listdir(path)) == ["default", "optimizer.bin", "random_states_0.pkl", "scheduler.bin"]
+    loss_a = float(a.train_step(*batch))
+    b = make(0)                      # same frozen weights (same seed), fresh adapters / optimizer
+    with torch.no_grad():
+        b.flat_p.add_(0.05)          # make sure the restore really overwrites the trainable state
+    b.repack()
+    assert C.resume_from_checkpoint(b, str(tmp_path), "latest", num_update_steps_per_epoch=100) == (80, 0, 80)
+    assert b.step_count == 2
+    loss_b = float(b.train_step(*batch))
+    assert loss_a == loss_b
+    assert torch.equal(a.flat_p, b.flat_p) and torch.equal(a.flat_m, b.flat_m) and torch.equal(a.flat_v, b.flat_v)
+    # names / order of optimizer.bin == the module's trainable parameters
+    sd = torch.load(__import__("os").path.join(path, "optimizer.bin"), weights_only=False)
+    assert sd["param_names"] == [n for n, _ in b.unet.named_parameters() if "lora_" in n]
