@@ -915,7 +915,11 @@ class ControlNetSDVModel(_Base):
                 getattr(net, name).load_state_dict(getattr(unet, name).state_dict())
         return net.to(unet.device)
 
-    COND_CPAD = 8      # channels of the packed condition frames (2 = flow, 3 = depth / rgb, zero-padded to 16 bytes)
+    # channels of the packed condition frames (2 = flow, 3 = depth / rgb).  Padding to one full 64-channel k-block is the
+    # FASTER choice on this path: with 8 channels (16 bytes per pixel) the TMA box is 7/8 out-of-bounds fill and the conv
+    # takes 6.2 ms instead of 2.3 ms at 28 x 576 x 1024 (profiles/r02d_thin_conv.txt; ncu: every warp waits on the load
+    # barriers, DRAM 1 %), which outweighs the 1.2 ms saved in the pack kernel
+    COND_CPAD = 64
 
     def _cn_pack(self):
         if getattr(self, "_cn", None) is None:
@@ -947,8 +951,6 @@ class ControlNetSDVModel(_Base):
             if controlnet_cond.ndim != 5:
                 raise ValueError("controlnet_cond must be [batch, frames, channels, height, width]")
             b_, f_, cc, hc, wc = controlnet_cond.shape
-            # 2 / 3 condition channels padded to 8 (one 16-byte pixel), not to a 64-channel k-block: the TMA box
-            # zero-fills the rest of the k-block on chip, HBM sees 16 bytes per pixel instead of 128
             e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=self.COND_CPAD)
             hh, ww = hc, wc
             for i, (w, b, stride, _) in enumerate(convs):
