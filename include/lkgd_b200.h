@@ -229,6 +229,13 @@ LKGD_API int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int3
 LKGD_API int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int32_t y_f32, float beta, int64_t n,
                void* stream);
 
+/* out[m, :] = srcs[g(m)][m, :] over bf16 [M, C] matrices (C % 8 == 0; srcs = HOST array of n_src <= 8 device pointers, g as
+ * for the row vectors above).  Temporal cross-attention with KV length > 1 under the diffusers 0.27.2 context order: row m
+ * of the temporal batch attends to context g(m) = TCTX_0272 (transformer_temporal.py `time_context` broadcast), so
+ * the attention is evaluated once per context and this kernel keeps, per row, the result of its own context. */
+LKGD_API int lkgd_select_rows(const void* const* srcs, int32_t n_src, void* out, int64_t M, int32_t C, int32_t rv_mode,
+                     int32_t rv_HW, int32_t rv_F, int32_t rv_B, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Fused classifier-free-guidance combine + Euler (Karras sigmas, v-prediction) step, fp32.
  *   v      = u + g[f] * (c - u)           u = pred[s], c = pred[S + s]   (pred channels-last fp32 [2S*F,H,W,ld])

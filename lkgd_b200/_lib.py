@@ -63,6 +63,7 @@ SIGNATURES = {
     "lkgd_cast_bf16": (i32, [vp, vp, i64, vp]),
     "lkgd_concat_channels": (i32, [vp, i32, vp, i32, i32, vp, i64, vp]),
     "lkgd_axpby": (i32, [vp, i32, f32, vp, i32, f32, i64, vp]),
+    "lkgd_select_rows": (i32, [vp, i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
     "lkgd_fusion_euler_step": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
     # ---- training step

@@ -411,6 +411,44 @@ extern "C" int lkgd_fusion_euler_step(const float* v, const float* x, const floa
   return launch_epilogue();
 }
 
+// out[m, :] = srcs[g(m)][m, :]  (bf16 rows, 16-byte vectors): the per-row choice between attention results computed against
+// different contexts - temporal cross-attention with more than one key under the diffusers 0.27.2 context order, where
+// row m of the temporal batch attends to context g(m) = ((m / (HW F)) HW + m % HW) % B.
+struct SelectSrcs { const uint4* p[8]; };
+__device__ __forceinline__ int sel_index(int mode, long long m, int HW, int F, int B) {
+  switch (mode) {
+    case LKGD_RV_FRAME: return (int)(m / HW);
+    case LKGD_RV_FRAMEPOS: return (int)((m / HW) % F);
+    case LKGD_RV_BATCH: return (int)(m / ((long long)HW * F));
+    case LKGD_RV_TCTX_0272: return (int)(((m / ((long long)HW * F)) * HW + (m % HW)) % B);
+    default: return 0;
+  }
+}
+__global__ void select_rows_kernel(SelectSrcs srcs, int n_src, uint4* __restrict__ out, long long M, int C8, int mode,
+                                   int HW, int F, int B) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  const long long m = idx / C8;
+  int g = sel_index(mode, m, HW, F, B);
+  g = g < n_src ? g : n_src - 1;
+  out[idx] = __ldg(srcs.p[g] + idx);
+}
+
+extern "C" int lkgd_select_rows(const void* const* srcs, int32_t n_src, void* out, int64_t M, int32_t C, int32_t rv_mode,
+                                int32_t rv_HW, int32_t rv_F, int32_t rv_B, void* stream) {
+  if (srcs == nullptr || n_src <= 0 || n_src > 8 || M <= 0 || C <= 0 || C % 8 || rv_HW <= 0 || rv_F <= 0 || rv_B <= 0)
+    return LKGD_ESHAPE;
+  SelectSrcs s;
+  for (int i = 0; i < 8; ++i) {
+    s.p[i] = reinterpret_cast<const uint4*>(srcs[i < n_src ? i : n_src - 1]);
+    if (!aligned16(s.p[i])) return LKGD_EALIGN;
+  }
+  if (!aligned16(out)) return LKGD_EALIGN;
+  select_rows_kernel<<<blocks_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(s, n_src, reinterpret_cast<uint4*>(out), M,
+                                                                            C / 8, rv_mode, rv_HW, rv_F, rv_B);
+  return launch_epilogue();
+}
+
 extern "C" int lkgd_axpy_f32(const float* x, float alpha, float* y, int64_t n, void* stream) {
   if (n <= 0) return LKGD_ESHAPE;
   axpy_f32_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(x, alpha, y, n);

@@ -319,14 +319,23 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
                     out_f32=True, gn_rows=g.HW, want_bf16=want_bf16)
 
 
-def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor):
-    """KV > 1: h + to_out(attention(to_q(n), to_k(ctx), to_v(ctx))); rows of batch b see ctx[b]."""
+def _cross_general(pc: PackedCross, n: torch.Tensor, ctx: torch.Tensor, g: Geom, h: torch.Tensor,
+                   tctx_0272: bool = False):
+    """KV > 1: h + to_out(attention(to_q(n), to_k(ctx), to_v(ctx))); rows of batch b see ctx[b].
+    ``tctx_0272``: the temporal block under the diffusers 0.27.2 context order - row m of the temporal batch sees
+    ctx[((m / (HW F)) HW + m % HW) % B]: the attention is evaluated against every context (B is the CFG batch,
+    the keys are few) and ``select_rows`` keeps each row's own."""
     wq, wkv, wo = pc.general()
     B, L, D = ctx.shape
     c = pc.heads * pc.d
     q = ops.gemm(n, wq)
     kv = ops.gemm(ctx.reshape(B * L, D).to(bf16).contiguous(), wkv)
-    a = ops.attention(q, kv[:, :c], kv[:, c:], n_img=B, heads=pc.heads, d=pc.d, Nq=g.F * g.HW, Nk=L)
+    if tctx_0272 and B > 1:
+        per_ctx = [ops.attention(q, kv[j * L:(j + 1) * L, :c], kv[j * L:(j + 1) * L, c:], n_img=1, heads=pc.heads,
+                                 d=pc.d, Nq=g.M, Nk=L) for j in range(B)]
+        a = ops.select_rows(per_ctx, (RV_TCTX_0272, g.HW, g.F, B))
+    else:
+        a = ops.attention(q, kv[:, :c], kv[:, c:], n_img=B, heads=pc.heads, d=pc.d, Nq=g.F * g.HW, Nk=L)
     return ops.gemm(a, wo, bias=pc.bo, res1=h, out_f32=True)
 
 
@@ -366,12 +375,10 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
                           rv=(tctx_mode, g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
     else:
-        if tctx_mode != RV_BATCH and g.B > 1:
-            raise NotImplementedError("temporal cross-attention with KV length > 1 needs time_context_order="
-                                      "'b_major' (or batch 1): the 0.27.2 (hw,b) interleave is only implemented "
-                                      "for the KV-length-1 context the reference always uses")
+        if tctx_mode != RV_BATCH and cond.ctx_t.shape[0] != cond.ctx.shape[0]:
+            raise NotImplementedError("temporal cross-attention with KV length > 1 under a CFG pair split")
         n = ops.layernorm(t, p.t_ln2.g, p.t_ln2.b, p.t_ln2.eps)
-        t = _cross_general(p.t_cross, n, cond.ctx, g, t)
+        t = _cross_general(p.t_cross, n, cond.ctx, g, t, tctx_0272=tctx_mode != RV_BATCH)
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps)
     ff = dense(n, p.t_ff1, act=ACT_GEGLU)
     # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t); bf16 because proj_out reads it as its GEMM operand
@@ -450,20 +457,22 @@ class PackedUNet:
                     pc.wov = getattr(self, name + "_w")[pc.off:pc.off + pc.wov.shape[0]]
 
     # ------------------------------------------------------------------------------------------
-    def time_embedding(self, timestep: torch.Tensor, added_time_ids: torch.Tensor) -> torch.Tensor:
-        """emb = time_embedding(Timesteps(t)) + add_embedding(Timesteps(added_time_ids).reshape(B,-1)) in fp32."""
+    def time_embedding(self, timestep: torch.Tensor, added_time_ids: torch.Tensor, te=None, ae=None) -> torch.Tensor:
+        """emb = time_embedding(Timesteps(t)) + add_embedding(Timesteps(added_time_ids).reshape(B,-1)) in fp32.
+        ``te`` / ``ae``: another head's MLP weights (the joint UNet's y heads)."""
+        te, ae = te or self.te, ae or self.ae
         B = added_time_ids.shape[0]
         t = timestep.to(torch.float32).reshape(-1).expand(B).contiguous()
         e = ops.timestep_embedding(t, self.c0)
-        e = ops.small_linear(ops.small_linear(e, self.te[0], self.te[1], act_out=SL_SILU), self.te[2], self.te[3])
+        e = ops.small_linear(ops.small_linear(e, te[0], te[1], act_out=SL_SILU), te[2], te[3])
         a = ops.timestep_embedding(added_time_ids.to(torch.float32).reshape(-1), self.cfg.addition_time_embed_dim)
         a = a.reshape(B, -1)
-        a = ops.small_linear(ops.small_linear(a, self.ae[0], self.ae[1], act_out=SL_SILU), self.ae[2], self.ae[3])
+        a = ops.small_linear(ops.small_linear(a, ae[0], ae[1], act_out=SL_SILU), ae[2], ae[3])
         ops.axpy_f32(a, e)
         return e
 
     def encoder(self, x: torch.Tensor, g: Geom, cond: Conditioning, stem_add: Optional[torch.Tensor] = None,
-                bf16_skips: bool = False):
+                bf16_skips: bool = False, stem: Optional[torch.Tensor] = None):
         """conv_in (+ ControlNet condition embedding) -> down blocks -> mid.  Returns (sample, skips, geoms, geometry of
         the mid block).  ``bf16_skips``: every skip tensor and the mid output are ``(fp32, bf16 copy)`` pairs - the copy
         is written by the epilogue that produces the tensor and feeds the ControlNet's zero convs without a narrowing pass
@@ -473,8 +482,13 @@ class PackedUNet:
         def both(t):                 # (fp32, bf16) -> fp32 stream tensor, bf16 copy (None when not requested)
             return t if wb else (t, None)
 
-        x, xb = both(ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b,
-                              res1=stem_add, out_f32=True, gn_rows=g.HW, want_bf16=wb))
+        if stem is not None:         # conv_in already applied by the caller (per-sample input heads of the joint UNet)
+            if wb or stem_add is not None:
+                raise ValueError("a precomputed stem excludes stem_add / bf16_skips")
+            x, xb = stem, None
+        else:
+            x, xb = both(ops.gemm(x, self.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=self.conv_in_b,
+                                  res1=stem_add, out_f32=True, gn_rows=g.HW, want_bf16=wb))
         skips, geoms = [(x, xb) if wb else x], [g]
         for res, att, ds in self.down:
             for i, r in enumerate(res):

@@ -482,6 +482,20 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def select_rows(srcs, rv: Tuple[int, int, int, int]) -> torch.Tensor:
+    """out[m] = srcs[g(m)][m] over equally shaped contiguous bf16 [M, C] matrices (see lkgd_select_rows)."""
+    _need_cuda(*srcs)
+    M, Cn = srcs[0].shape
+    for t in srcs:
+        if t.dtype != bf16 or not t.is_contiguous() or t.shape != (M, Cn):
+            raise ValueError("select_rows: contiguous bf16 [M, C] matrices of one shape expected")
+    out = torch.empty_like(srcs[0])
+    arr = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+    L.check(L.load().lkgd_select_rows(arr, len(srcs), out.data_ptr(), M, Cn, rv[0], rv[1], rv[2], rv[3], _stream()),
+            "lkgd_select_rows")
+    return out
+
+
 def axpby(x: torch.Tensor, alpha: float, y: torch.Tensor, beta: float) -> torch.Tensor:
     """y = alpha*x + beta*y in place; x and y each bf16 or fp32."""
     _need_cuda(x, y)

@@ -276,3 +276,80 @@ class StableVideoDiffusionPipeline:
         if not return_dict:
             return latents
         return StableVideoDiffusionPipelineOutput(frames=latents)
+
+
+class StableVideoDiffusionSmoothPipeline(StableVideoDiffusionPipeline):
+    """Latent-space part of the reference's ``smooth`` pipeline (pipeline/pipeline_stable_video_diffusion_smooth.py,
+    SURVEY 8f N3): a long clip of ``T`` frames is re-noised to step ``start_step`` (:520) and denoised in windows of at
+    most ``num_frames`` frames whose boundaries are re-drawn at random every step (:526-534); every window runs the UNet
+    on [window, time-flipped window] x CFG with the window's first / last frame as the conditioning image (:546-575),
+    keeps the forward half's guided prediction (:589-590), and ONE Euler step updates all frames (:593).
+
+    Per window: the fused pack kernel (CFG duplication + scale + concat + layout), the UNet, the fused CFG kernel."""
+
+    @staticmethod
+    def get_chunks(flen: int, num_frames: int, rng=None):
+        rng = np.random if rng is None else rng          # the reference draws from numpy's global stream
+        x_index = torch.arange(flen)
+        rand_first = rng.randint(0, num_frames) + 1
+        chunks = x_index[rand_first:].split(num_frames, dim=0)
+        chunks = [x_index[:rand_first]] + list(chunks) if len(chunks[0]) > 0 else [x_index[:rand_first]]
+        return [[int(i) for i in chunk] for chunk in chunks]
+
+    @ops.on_own_device
+    @torch.no_grad()
+    def __call__(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, original_image_latents: torch.Tensor,
+                 num_frames: Optional[int] = None, start_step: int = 0, num_inference_steps: int = 25,
+                 min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0, fps: int = 7,
+                 motion_bucket_id: int = 127, noise_aug_strength: float = 0.02, generator=None,
+                 noise: Optional[torch.Tensor] = None, chunk_rng=None, output_type: str = "latent",
+                 return_dict: bool = True):
+        """``image_embeddings`` [2T,1,D] / ``image_latents`` [2T,4,h,w]: per FRAME, unconditional (zeros) half first
+        (:441, :462-469); ``original_image_latents`` [1,T,4,h,w]: the clip's scaled VAE latents (:464)."""
+        if output_type != "latent":
+            raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent'")
+        unet, sched = self.unet, self.scheduler
+        device = unet.device
+        do_cfg = max_guidance_scale > 1.0
+        if not do_cfg:
+            raise ValueError("the smooth pipeline is defined for classifier-free guidance (max_guidance_scale > 1)")
+        T = original_image_latents.shape[1]
+        if image_latents.shape[0] != 2 * T or image_embeddings.shape[0] != 2 * T:
+            raise ValueError("image_latents / image_embeddings must hold 2*T per-frame entries (uncond half first)")
+        num_frames = num_frames if num_frames is not None else unet.config.num_frames
+        ids = self._get_add_time_ids(fps - 1, motion_bucket_id, noise_aug_strength, torch.float32, 1, 1, True)
+        ids4 = torch.cat([ids] * 2, dim=0).to(device)                      # :541
+        sched.set_timesteps(num_inference_steps, device=device)
+        if not 0 <= start_step < num_inference_steps:
+            raise ValueError("start_step outside the schedule")
+        x0 = original_image_latents.to(device=device, dtype=torch.float32).contiguous()
+        if noise is None:
+            gdev = generator.device if generator is not None else device
+            noise = torch.randn(x0.shape, generator=generator, device=gdev, dtype=torch.float32)
+        latents = sched.add_noise(x0, noise.to(device), sched.timesteps[[start_step]]).contiguous()      # :520
+        img_lat = image_latents.to(device=device, dtype=torch.float32)
+        img_emb = image_embeddings.to(device)
+        h, w = x0.shape[-2:]
+        pk = unet.packed()
+        for i in range(start_step, num_inference_steps):
+            sched.index_for(i)
+            sigma, sigma_next = float(sched._sigmas_host[i]), float(sched._sigmas_host[i + 1])
+            t = float(sched._timesteps_host[i])
+            scale = float(1.0 / np.sqrt(np.float32(sigma) ** 2 + 1))
+            noise_pred = torch.empty_like(latents)
+            for chunk in self.get_chunks(T, num_frames, chunk_rng):
+                n = len(chunk)
+                lc = latents[:, chunk]
+                pair = torch.cat([lc, lc.flip(dims=[1])], dim=0).contiguous()                      # :549-551
+                first = [chunk[0], chunk[-1], chunk[0] + T, chunk[-1] + T]                         # :553-556
+                cur_lat = img_lat[first].unsqueeze(1).repeat(1, n, 1, 1, 1).contiguous()
+                x = ops.pack_input(pair, scale, cur_lat, N=4, Cpad=pk.cin_pad)                     # :565-569, one kernel
+                rows = unet.forward_packed(x, Geom(4, n, h, w), t, img_emb[first].contiguous(), added_time_ids=ids4)
+                g = torch.linspace(min_guidance_scale, max_guidance_scale, n, device=device, dtype=torch.float32)
+                _, v = ops.cfg_euler_step(rows, g.contiguous(), pair, sigma, sigma_next, cfg=True, want_v=True)   # :580-587
+                noise_pred[:, chunk] = v[:1]                                                       # :589-590
+            latents, _ = ops.cfg_euler_step(noise_pred.contiguous(), None, latents, sigma, sigma_next, cfg=False)   # :593
+            sched._step_index = i + 1
+        if not return_dict:
+            return latents
+        return StableVideoDiffusionPipelineOutput(frames=latents)

@@ -490,10 +490,10 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
             ctx_all, ids = ctx_all[lo:hi].contiguous(), ids[lo:hi].contiguous()
         if ctx_all.shape[0] != g.B or ids.shape[0] != g.B:
             raise ValueError("encoder_hidden_states / added_time_ids batch does not match sample")
-        emb = pk.time_embedding(self._timestep_tensor(timestep, x), ids)
+        emb = self._embedding(pk, self._timestep_tensor(timestep, x), ids)
         cond = Conditioning(pk, emb, ctx_all, ctx_t)
         x_in = x
-        x, skips, geoms, gm = pk.encoder(x, g, cond)
+        x, skips, geoms, gm = pk.encoder(x, g, cond, stem=self._stem_rows(pk, x, g))
         if fused_controlnet is not None:
             if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
                     or batch_slice is not None:
@@ -513,6 +513,12 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
             for s, r, m, gs in zip(skips, down_block_additional_residuals, mult, geoms):
                 ops.axpby(self._residual_rows(r, gs), float(m), s, 1.0)
         return pk.decoder(x, skips, gm, cond)
+
+    def _embedding(self, pk: PackedUNet, t: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        return pk.time_embedding(t, ids)
+
+    def _stem_rows(self, pk: PackedUNet, x: torch.Tensor, g: Geom) -> Optional[torch.Tensor]:
+        return None                      # conv_in runs inside the encoder
 
     @ops.on_own_device
     @torch.no_grad()
@@ -536,6 +542,90 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
         if not return_dict:
             return (out,)
         return UNetSpatioTemporalConditionOutput(sample=out)
+
+
+# --------------------------------------------------------------------------------------------------- x / y input heads
+class UNetSpatioTemporalConditionJointModel(UNetSpatioTemporalConditionControlNetModel):
+    """``models/unet_spatio_temporal_condition_joint.py``: a second set of input heads - ``conv_in_y``,
+    ``time_embedding_y``, ``add_embedding_y`` (``add_y_input_head`` :251-280; the weight-free ``time_proj`` /
+    ``add_time_proj`` need no copy) - and a forward that sends every sample of the batch through the x or the y heads
+    according to ``lora_mask["xy_lora"]`` / ``lora_mask["yx_lora"]`` (:483-500; installed by the reference's
+    ``patch.set_patch_lora_mask``, patch/patch.py:872-896, or ``set_lora_mask`` here).  The body is the plain UNet's:
+    only the stem conv (one implicit-GEMM launch per sample, written into one row matrix) and the fp32 embedding MLPs
+    differ per sample."""
+
+    def add_y_input_head(self):
+        import copy
+        self.conv_in_y = copy.deepcopy(self.conv_in)
+        self.time_embedding_y = copy.deepcopy(self.time_embedding)
+        self.add_embedding_y = copy.deepcopy(self.add_embedding)
+        self.invalidate()
+
+    def load_y_input_head(self, path):
+        """Reference :281-284: a ``torch.save``d dict of the four head state_dicts (``time_proj`` has no tensors)."""
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        for name in ("conv_in", "time_embedding", "add_embedding"):
+            getattr(self, name + "_y").load_state_dict(sd[name])
+        self.invalidate()
+
+    def set_lora_mask(self, lora_name: str, lora_mask):
+        """What ``patch.set_patch_lora_mask(unet, lora_name, mask)`` stores on the model (patch/patch.py:880-884)."""
+        if not hasattr(self, "lora_mask"):
+            self.lora_mask = dict()
+        self.lora_mask[lora_name] = torch.as_tensor(lora_mask, dtype=torch.bool)
+
+    def invalidate(self):
+        super().invalidate()
+        self._y = None
+
+    def _y_pack(self):
+        if getattr(self, "_y", None) is None:
+            if not hasattr(self, "conv_in_y"):
+                raise AttributeError("call add_y_input_head() first")      # the reference fails on conv_in_dict likewise
+            pk = self.packed()
+            w, b = _conv3x3_weight(self.conv_in_y, cin_pad=pk.cin_pad)
+            te, ae = self.time_embedding_y, self.add_embedding_y
+            self._y = (w, b,
+                       tuple(_f32(t) for t in (te.linear_1.weight, te.linear_1.bias, te.linear_2.weight, te.linear_2.bias)),
+                       tuple(_f32(t) for t in (ae.linear_1.weight, ae.linear_1.bias, ae.linear_2.weight, ae.linear_2.bias)))
+        return self._y
+
+    def _branches(self, batch: int) -> List[bool]:
+        """True = y heads, per sample.  The masks are repeat-interleaved to the batch like the reference (:485-486)."""
+        xm, ym = self.lora_mask["xy_lora"], self.lora_mask["yx_lora"]
+        xm = xm.repeat_interleave(batch // len(xm)).tolist()
+        ym = ym.repeat_interleave(batch // len(ym)).tolist()
+        if len(xm) != batch or len(ym) != batch or any(a == b for a, b in zip(xm, ym)):
+            raise ValueError("xy_lora / yx_lora masks must partition the batch")
+        if not any(xm) or not any(ym):
+            raise ValueError("both input heads need at least one sample (the reference's input_layers fails on an empty "
+                             "branch, :415)")
+        return ym
+
+    def _embedding(self, pk, t, ids):
+        B = ids.shape[0]
+        if t.numel() not in (1, B):
+            raise ValueError("timestep must be a scalar or a [batch] tensor")
+        _, _, te_y, ae_y = self._y_pack()
+        ex, ey = pk.time_embedding(t, ids), pk.time_embedding(t, ids, te=te_y, ae=ae_y)
+        for b, is_y in enumerate(self._branches(B)):
+            if is_y:
+                ex[b].copy_(ey[b])
+        return ex
+
+    def _stem_rows(self, pk, x, g):
+        wy, by, _, _ = self._y_pack()
+        rows = g.F * g.HW
+        out = torch.empty((g.M, pk.c0), device=x.device, dtype=torch.float32)
+        for b, is_y in enumerate(self._branches(g.B)):
+            ops.gemm(x[b * rows:(b + 1) * rows], wy if is_y else pk.conv_in_w, mode=A_CONV3X3, conv=(g.F, g.H, g.W, 1),
+                     bias=by if is_y else pk.conv_in_b, out=out[b * rows:(b + 1) * rows], out_f32=True)
+        return out
+
+    def forward_packed(self, x, g, timestep, encoder_hidden_states, *extra, **kw):
+        if kw.get("batch_slice") is not None or kw.get("fused_controlnet") is not None:
+            raise ValueError("the joint UNet supports neither the CFG pair split nor the fused ControlNet path")
+        return super().forward_packed(x, g, timestep, encoder_hidden_states, *extra, **kw)
 
 
 # --------------------------------------------------------------------------------------------------- LKGD

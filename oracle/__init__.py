@@ -24,6 +24,7 @@ from .blocks import *  # noqa: F401,F403
 from .unet import (  # noqa: F401
     UNetSpatioTemporalConditionControlNetModel,
     UNetSpatioTemporalConditionModelFlow,
+    UNetSpatioTemporalConditionJointModel,
     UNetSpatioTemporalConditionModel,
     SVD_XT_CONFIG,
     REDUCED_CONFIG,
@@ -31,4 +32,5 @@ from .unet import (  # noqa: F401
 from .controlnet import ControlNetSDVModel  # noqa: F401
 from .lora import LoraLinear, add_lora, merge_lora  # noqa: F401
 from .scheduler import EulerDiscreteScheduler  # noqa: F401
-from .pipeline import guidance_ramp, cfg_combine, denoise_loop, add_time_ids_inference, add_time_ids_training  # noqa: F401
+from .pipeline import (guidance_ramp, cfg_combine, denoise_loop, add_time_ids_inference, add_time_ids_training,  # noqa: F401
+                       smooth_chunks, smooth_loop)

@@ -88,3 +88,53 @@ def train_loss(model_pred, noisy_latents, target, sigmas):
     w = (1 + s ** 2) * (s ** -2.0)
     loss = torch.mean((w.float() * (denoised.float() - target.float()) ** 2).reshape(target.shape[0], -1), dim=1)
     return loss.mean()
+
+
+def smooth_chunks(total_frames: int, num_frames: int, rng=None):
+    """``get_chunks`` of the smooth pipeline (pipeline/pipeline_stable_video_diffusion_smooth.py:526-534): a first chunk
+    of random length 1..num_frames, then chunks of ``num_frames``.  ``rng``: object with ``randint`` (default
+    ``numpy.random``, the reference's global stream)."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    x_index = torch.arange(total_frames)
+    rand_first = rng.randint(0, num_frames) + 1
+    chunks = x_index[rand_first:].split(num_frames, dim=0)
+    chunks = [x_index[:rand_first]] + list(chunks) if len(chunks[0]) > 0 else [x_index[:rand_first]]
+    return [[int(i) for i in chunk] for chunk in chunks]
+
+
+@torch.no_grad()
+def smooth_loop(unet, scheduler, original_image_latents, noise, image_latents, image_embeddings, added_time_ids,
+                num_frames: int, start_step: int, num_inference_steps: int = 25, min_guidance_scale: float = 1.0,
+                max_guidance_scale: float = 3.0, rng=None, return_chunks: bool = False):
+    """Denoising part of the reference's ``smooth`` pipeline (pipeline/pipeline_stable_video_diffusion_smooth.py:
+    :520 add_noise at ``start_step``, :526-534 random chunking per step, :546-590 per chunk a [chunk, flipped chunk] pair
+    with first / last frame conditioning, CFG, the forward half's prediction kept, :593 one Euler step over all frames).
+    ``original_image_latents`` [1,T,4,h,w] (scaled VAE latents), ``image_latents`` / ``image_embeddings`` per FRAME
+    [2T,...] (uncond first), ``added_time_ids`` [2,3] (CFG-duplicated once; the loop duplicates it again, :541)."""
+    T = original_image_latents.shape[1]
+    scheduler.set_timesteps(num_inference_steps)
+    timesteps = scheduler.timesteps
+    latents = scheduler.add_noise(original_image_latents, noise, timesteps[[start_step]])
+    ids4 = torch.cat([added_time_ids] * 2, dim=0)
+    used = []
+    for i in range(start_step, len(timesteps)):
+        t = timesteps[i]
+        chunks = smooth_chunks(T, num_frames, rng)
+        used.append(chunks)
+        noise_pred = torch.empty_like(latents)
+        for chunk in chunks:
+            lc = latents[:, chunk]
+            lc = torch.cat([lc, lc.flip(dims=[1])], dim=0)
+            first = [chunk[0], chunk[-1], chunk[0] + T, chunk[-1] + T]
+            cur_lat = image_latents[first].unsqueeze(1).repeat(1, len(chunk), 1, 1, 1)
+            cur_emb = image_embeddings[first]
+            x = scheduler.scale_model_input(torch.cat([lc] * 2), t)
+            x = torch.cat([x, cur_lat], dim=2)
+            pred = unet(x, t, cur_emb, added_time_ids=ids4, return_dict=False)[0]
+            g = torch.linspace(min_guidance_scale, max_guidance_scale, len(chunk)).unsqueeze(0)[..., None, None, None]
+            u, c = pred.chunk(2)
+            pred = u + g * (c - u)
+            noise_pred[:, chunk] = pred[:len(pred) // 2]
+        latents = scheduler.step(noise_pred, t, latents).prev_sample
+    return (latents, used) if return_chunks else latents

@@ -208,6 +208,54 @@ class UNetSpatioTemporalConditionModelFlow(UNetSpatioTemporalConditionControlNet
             self.conv_in2(torch.cat([noise, cond2], -3)) * self.conv_in2_alpha          # :499-502
 
 
+# --------------------------------------------------------------------------- x / y input heads
+class UNetSpatioTemporalConditionJointModel(UNetSpatioTemporalConditionControlNetModel):
+    """``models/unet_spatio_temporal_condition_joint.py``: a second set of INPUT heads (``conv_in_y``,
+    ``time_embedding_y``, ``add_embedding_y``; ``add_y_input_head`` :251-280 deep-copies the x heads) and a forward that
+    routes every sample of the batch through the x or the y heads according to the boolean masks
+    ``lora_mask["xy_lora"]`` / ``lora_mask["yx_lora"]`` (:483-500; set by ``patch.set_patch_lora_mask``,
+    patch/patch.py:872-896).  ``add_time_proj`` is shared (:414), the body is the plain UNet's.  ``timestep`` must be a
+    [batch] tensor (the reference indexes it with the masks)."""
+
+    def add_y_input_head(self):
+        import copy
+        self.conv_in_y = copy.deepcopy(self.conv_in)
+        self.time_embedding_y = copy.deepcopy(self.time_embedding)
+        self.add_embedding_y = copy.deepcopy(self.add_embedding)
+
+    def _masks(self, batch):
+        x_mask, y_mask = self.lora_mask["xy_lora"], self.lora_mask["yx_lora"]
+        return (x_mask.repeat_interleave(batch // len(x_mask)), y_mask.repeat_interleave(batch // len(y_mask)))
+
+    def forward(self, sample, timestep, encoder_hidden_states, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, return_dict=True, added_time_ids=None):
+        b, f = sample.shape[:2]
+        t = timestep.expand(b) if timestep.ndim else timestep[None].expand(b)
+        x_mask, y_mask = self._masks(b)
+        c0 = self.config.block_out_channels[0]
+        stem = torch.empty(b * f, c0, *sample.shape[-2:], dtype=sample.dtype)
+        emb = torch.empty(b * f, c0 * 4, dtype=sample.dtype)
+        for mask, conv, te, ae in ((x_mask, self.conv_in, self.time_embedding, self.add_embedding),
+                                   (y_mask, self.conv_in_y, self.time_embedding_y, self.add_embedding_y)):
+            if not mask.any():
+                continue
+            e = te(timestep_embedding(t[mask], c0).to(sample.dtype))                                   # :404-410
+            ids = timestep_embedding(added_time_ids[mask].flatten(), self.config.addition_time_embed_dim)
+            e = e + ae(ids.reshape(int(mask.sum()), -1).to(e.dtype))                                      # :414-418
+            fm = mask.repeat_interleave(f)
+            emb[fm] = e.repeat_interleave(f, dim=0)                                                      # :425, :499-500
+            stem[fm] = conv(sample[mask].flatten(0, 1))                                                  # :430, :497-498
+        ctx = encoder_hidden_states.repeat_interleave(f, dim=0)
+        self._joint_stem = stem
+        out = self._body(sample.flatten(0, 1), emb, ctx, b, f, down_block_additional_residuals,
+                         mid_block_additional_residual)
+        self._joint_stem = None
+        return SimpleNamespace(sample=out) if return_dict else (out,)
+
+    def _stem(self, sample):
+        return self._joint_stem
+
+
 # --------------------------------------------------------------------------- LKGD (A.7, A.8)
 class QuaternionLinear(nn.Module):
     """``core_qnn.quaternion_layers.QuaternionLinearAutograd`` (un-vendored, un-pinned; F5/U5).

@@ -199,3 +199,29 @@ def test_pipeline_loop_vs_reference(cuda):
     errs = [rel(x, G["pipe/steps"][i]) for i, x in enumerate(traj)]
     print("pipeline per-step latents rel-L2", errs)
     assert max(errs) < 2e-2 and rel(final, G["pipe/final"]) < 2e-2
+
+
+def test_joint_input_head_unet_vs_reference(cuda):
+    """UNetSpatioTemporalConditionJointModel (x / y input heads chosen per sample) against the reference's
+    own file run through the shim (tests/golden/make_joint_golden.py); per-sample timesteps / added-time ids."""
+    import os
+    from golden_util import HERE
+    from test_oracle_golden import JOINT_MASKS, joint_inputs
+    from lkgd_b200.unet import UNetSpatioTemporalConditionJointModel
+    JG = np.load(os.path.join(HERE, "golden", "joint_golden.npz"))
+    u = UNetSpatioTemporalConditionJointModel(**REDUCED4)
+    u.add_y_input_head()
+    u = fill_seeded_(u).to(cuda)
+    assert sorted(n for n, _ in u.named_parameters() if "_y." in n) == list(JG["joint/param_names"])
+    sample, ctx, ids, ts = (v.to(cuda) for v in joint_inputs())
+    for tag, (xy, yx) in JOINT_MASKS.items():
+        u.set_lora_mask("xy_lora", xy)
+        u.set_lora_mask("yx_lora", yx)
+        out = u(sample, ts, ctx, added_time_ids=ids, return_dict=False)[0]
+        err = rel(out, JG[f"joint/out_{tag}"])
+        print("joint", tag, err)
+        assert err < 1e-2, tag
+    u.set_lora_mask("xy_lora", [1, 1, 1, 1])
+    u.set_lora_mask("yx_lora", [0, 0, 0, 0])
+    with pytest.raises(ValueError, match="at least one sample"):
+        u(sample, ts, ctx, added_time_ids=ids)

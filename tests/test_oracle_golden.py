@@ -151,6 +151,34 @@ def test_unet_matches_the_reference_unet_with_patched_blocks():
     assert rel(G["unet/out"], PG["patch/unet_out"]) < 2e-6
 
 
+JOINT_MASKS = {"alt": ([1, 0, 1, 0], [0, 1, 0, 1]), "pair": ([1, 0], [0, 1]), "yxxx": ([0, 1, 1, 1], [1, 0, 0, 0])}
+
+
+def joint_inputs():
+    sample = seeded_tensor("joint/sample", (4, F, 8, H, W))
+    ctx = seeded_tensor("joint/ctx", (4, 1, 32))
+    ids = torch.tensor([[6.0, 127.0, 0.02], [6.0, 60.0, 0.02], [6.0, 127.0, 0.1], [12.0, 127.0, 0.02]])
+    ts = torch.tensor([1.4439898729, 0.3, 1.4439898729, -0.7])
+    return sample, ctx, ids, ts
+
+
+def test_joint_input_head_unet_matches_reference():
+    """the x / y input-head UNet against the reference's own models/unet_spatio_temporal_condition_joint.py
+    run through the shim with masks installed by the reference's patch.set_patch_lora_mask
+    (tests/golden/make_joint_golden.py): per-sample timesteps and added-time ids, three mask layouts."""
+    JG = np.load(os.path.join(HERE, "golden", "joint_golden.npz"))
+    o = O.UNetSpatioTemporalConditionJointModel(**REDUCED4)
+    o.add_y_input_head()
+    o = fill_seeded_(o).eval()
+    assert sorted(n for n, _ in o.named_parameters() if "_y." in n) == list(JG["joint/param_names"])
+    sample, ctx, ids, ts = joint_inputs()
+    for tag, (xy, yx) in JOINT_MASKS.items():
+        o.lora_mask = {"xy_lora": torch.tensor(xy, dtype=torch.bool), "yx_lora": torch.tensor(yx, dtype=torch.bool)}
+        with torch.no_grad():
+            a = o(sample, ts, ctx, added_time_ids=ids, return_dict=False)[0]
+        assert rel(a, JG[f"joint/out_{tag}"]) < 1e-6, tag
+
+
 def test_flow_stem_unet_matches_reference():
     """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
     by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""

@@ -121,10 +121,13 @@ def test_unet_full_depth_svd_xt_width(cuda):
     assert err < 1e-2
 
 
-def test_unet_kv_longer_than_one(cuda):
+@pytest.mark.parametrize("order", ["b_major", "hw_major_0272"])
+def test_unet_kv_longer_than_one(cuda, order):
+    """Cross-attention with 3 keys at batch 2.  Under the pinned diffusers 0.27.2 order the temporal block's row
+    (b, p) attends to context (b*HW + p) % B: evaluated per context + lkgd_select_rows."""
     import oracle as O
     from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
-    cfg = dict(REDUCED_CONFIG, time_context_order="b_major")
+    cfg = dict(REDUCED_CONFIG, time_context_order=order)
     o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
     x, _, ids = _inputs(cfg, 2, 8, 32, 32, 32)
     ctx = torch.randn(2, 3, 32, generator=torch.Generator().manual_seed(5))
@@ -468,3 +471,38 @@ def test_fused_controlnet_injection_equals_the_residual_handoff(cuda):
     assert rel_l2(fused, handoff) < 8e-3
     assert rel_l2(fused, ref) < 1e-2
     assert rel_l2(handoff, ref) < 1e-2
+
+
+def test_smooth_pipeline_vs_oracle(cuda):
+    """the `smooth` sampler (pipeline/pipeline_stable_video_diffusion_smooth.py:520-593 - re-noise a long
+    clip to `start_step`, random windows per step, [window, flipped window] x CFG, first / last frame conditioning, one
+    Euler step over all frames) against the oracle's restatement of those lines, same window draws."""
+    import numpy as np
+    import oracle as O
+    from oracle.scheduler import SVD_SCHEDULER_CONFIG
+    from lkgd_b200.pipeline import StableVideoDiffusionSmoothPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    T, nf, h, w, start = 11, 4, 16, 16, 19
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(1, T, 4, h, w, generator=g) * 0.18215
+    noise = torch.randn(1, T, 4, h, w, generator=g)
+    lat = torch.randn(T, 4, h, w, generator=g)
+    img_lat = torch.cat([torch.zeros_like(lat), lat])
+    emb = torch.randn(T, 1, 32, generator=g)
+    img_emb = torch.cat([torch.zeros_like(emb), emb])
+    osched = O.EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG)
+    ids = O.add_time_ids_inference(6, 127, 0.02, 1)
+    ref, chunks = O.smooth_loop(o, osched, x0, noise, img_lat, img_emb, ids, nf, start, 25, 1.0, 3.0,
+                                rng=np.random.RandomState(3), return_chunks=True)
+    assert len(chunks) == 25 - start and all(sorted(sum(c, [])) == list(range(T)) for c in chunks)
+    assert len({len(c[0]) for c in chunks}) > 1                      # the first window's length really varies
+    pipe = StableVideoDiffusionSmoothPipeline(p, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))
+    got = pipe(img_emb, img_lat, x0, num_frames=nf, start_step=start, num_inference_steps=25, noise=noise,
+               chunk_rng=np.random.RandomState(3), return_dict=False)
+    err = rel_l2(got, ref)
+    print("smooth pipeline rel-L2 after", 25 - start, "steps:", err)
+    assert err < 2e-2
+    assert pipe.get_chunks(T, nf, np.random.RandomState(3)) == chunks[0]
