@@ -21,6 +21,8 @@ constexpr int AT_THREADS = 192;
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
+  const __nv_bfloat16* q;   // QT variant: the softmax threads load their own Q row (row pitch ldq elements)
+  int ldq;
   __nv_bfloat16* out;
   int ldo, heads, d, Nq, Nk;
   float scale_log2;
@@ -45,15 +47,19 @@ constexpr int AT_SUBKV = AT_BH * AT_D * 2; // 8 KB: 64 keys x 64 head channels
 // Head width D = 64 (also serves d = 16 / 32 through zero-filled TMA boxes) or 128 (the reference's default heads
 // (5,10,10,20) give 1280 / 10 = 128 at level 2, models/unet_spatio_temporal_condition_controlnet.py:93).  A D = 128 tile
 // is two 64-channel SWIZZLE_128B sub-tiles side by side: Q K^T runs 8 k-steps over them, P V two N = 64 halves.
-template <int D>
+// QT ("Q in tensor memory", D = 64 only): Q never touches shared memory - every softmax thread loads its own query row
+// from global memory and stores it into 32 TMEM columns, and Q K^T is a TS-form MMA (A from TMEM) like P V.  Per 64-key
+// step the tensor core then reads 16 KB of operands from smem instead of 32 KB (the 16 KB Q tile re-read by every one of
+// the four N = 64 MMAs was half of it), at the price of 192 TMEM columns per CTA: two CTAs per SM instead of three.
+template <int D, bool QT = false>
 struct AttnCfg {
   static constexpr int NSUB = D / AT_D;                       // 1 or 2
-  static constexpr int TILE = NSUB * AT_SUBQ;                 // Q tile bytes
+  static constexpr int TILE = QT ? 0 : NSUB * AT_SUBQ;        // Q tile bytes in smem
   static constexpr int KV = NSUB * AT_SUBKV;                  // one 64-key K (or V) stage
-  static constexpr int NS = D == 64 ? 3 : 2;                  // K/V stages (ring)
+  static constexpr int NS = QT ? 4 : (D == 64 ? 3 : 2);       // K/V stages (ring)
   static constexpr int SMEM = TILE + 2 * NS * KV + 128;
-  static constexpr int TMEM_MAIN = D == 64 ? 128 : 256;       // S (64 columns) | O (D columns)
-  static constexpr int CTAS = D == 64 ? 3 : 2;                // resident CTAs per SM
+  static constexpr int TMEM_MAIN = (D == 64 && !QT) ? 128 : 256;   // S (64 columns) | O (D columns) [| P | Q]
+  static constexpr int CTAS = (D == 64 && !QT) ? 3 : 2;       // resident CTAs per SM
 };
 
 // Pipeline (per CTA; THREE CTAs share an SM - 64 KB smem, 160 TMEM columns and <= 96 registers each - so that three
@@ -108,9 +114,10 @@ __device__ __forceinline__ uint64_t at_exp2_poly2(uint64_t X) {
 
 // POLY: every POLY-th pair of exponentials is evaluated on the FMA pipes instead of the MUFU pipe (0 = none).  d = 64
 // attention is bound by the 16 ex2 / clock / SM of the MUFU pipe; the FMA pipes are otherwise nearly idle here.
-template <int POLY, int D>
-__global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kernel(const __grid_constant__ AttnParams p) {
-  using Cfg = AttnCfg<D>;
+template <int POLY, int D, bool QT = false>
+__global__ void __launch_bounds__(AT_THREADS, AttnCfg<D, QT>::CTAS) attn_flash_kernel(const __grid_constant__ AttnParams p) {
+  static_assert(!QT || D == 64, "Q in TMEM is built for 64-wide heads");
+  using Cfg = AttnCfg<D, QT>;
   constexpr int AT_TILE = Cfg::TILE, AT_KV = Cfg::KV, AT_NS = Cfg::NS, NSUB = Cfg::NSUB;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_init(q_full, 1);
+      mbar_init(q_full, QT ? 128 : 1);
       for (int i = 0; i < AT_NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
       mbar_init(s_full, 1);
       mbar_init(s_free, 4);
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
       tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
     }
     __syncwarp();
-    if (D == 64) {
+    if (D == 64 && !QT) {
       tmem_alloc_keep_permit(tmem_slot, Cfg::TMEM_MAIN);
       tmem_alloc(tmem_slot + 1, 32);
     } else {
@@ -154,13 +161,16 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_BH;   // S at columns 0..63, O at 64..127
-  const uint32_t tmem_P = D == 64 ? tmem_slot[1] : tmem_base + AT_BH + D;   // 128 x 64 bf16 = 32 columns
+  const uint32_t tmem_P = (D == 64 && !QT) ? tmem_slot[1] : tmem_base + AT_BH + D;   // 128 x 64 bf16 = 32 columns
+  const uint32_t tmem_Q = tmem_base + AT_BH + D + 32;                                // QT: 128 x 64 bf16 = 32 columns
 
   if (warp == 4) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, AT_TILE);
+      if (!QT) {
+        mbar_expect_tx(q_full, AT_TILE);
 #pragma unroll
-      for (int sb = 0; sb < NSUB; ++sb) tma_load_4d(sQ + sb * AT_SUBQ, &p.tmQ, q_full, sb * AT_D, head, q0, img);
+        for (int sb = 0; sb < NSUB; ++sb) tma_load_4d(sQ + sb * AT_SUBQ, &p.tmQ, q_full, sb * AT_D, head, q0, img);
+      }
       int st = 0, ph = 1;
       for (int j = 0; j < H; ++j) {
         while (!mbar_try_wait(&kv_empty[st], ph)) __nanosleep(64);   // off the critical path: back off
@@ -187,12 +197,16 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
           const uint64_t qdesc = umma_desc_sw128(sQ0 + sb * AT_SUBQ);
           const uint64_t kdesc = umma_desc_sw128(sK0 + qst * AT_KV + sb * AT_SUBKV);
 #pragma unroll
-          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (sb | k) != 0);
+          for (int k = 0; k < AT_D / 16; ++k) {
+            if (QT) umma_bf16_ts(tmem_S, tmem_Q + k * 8, kdesc + 2 * k, idesc_s, k != 0);   // A = Q from TMEM
+            else umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (sb | k) != 0);
+          }
         }
         umma_commit(s_full);
         if (++qst == AT_NS) { qst = 0; qph ^= 1; }
       };
       mbar_wait(q_full, 0);
+      if (QT) tc_fence_after();
       issue_qk();
       int st = 0;                      // K/V stage of P_h V_h
       for (int h = 0; h < H; ++h) {
@@ -223,6 +237,22 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
     // O rows in TMEM by 2^(m_old - m_new).  p = 2^(s*c - m) <= 256 otherwise, exact enough in bf16 / fp32.
     const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    if (QT) {
+      // this thread's query row: 64 bf16 (zero beyond d / beyond Nq) -> 32 TMEM columns, word j = channels 2j, 2j+1
+      uint32_t qw[32];
+      const bool row_ok = q0 + r < p.Nq;
+      const __nv_bfloat16* qrow = p.q + ((size_t)img * p.Nq + (row_ok ? q0 + r : 0)) * p.ldq + head * p.d;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok && c * 8 < p.d) u = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+        qw[4 * c] = u.x; qw[4 * c + 1] = u.y; qw[4 * c + 2] = u.z; qw[4 * c + 3] = u.w;
+      }
+      tmem_st32(tmem_Q + lane_addr, qw);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_full);
+    }
     float m_run = -INFINITY, l_run = 0.f;
     const float sc = p.scale_log2;
     for (int h = 0; h < H; ++h) {
@@ -353,7 +383,7 @@ __global__ void __launch_bounds__(AT_THREADS, AttnCfg<D>::CTAS) attn_flash_kerne
     tc_fence_after();
     __syncwarp();
     tmem_dealloc(tmem_base, Cfg::TMEM_MAIN);
-    if (D == 64) tmem_dealloc(tmem_P, 32);
+    if (D == 64 && !QT) tmem_dealloc(tmem_P, 32);
   }
 }
 
@@ -553,6 +583,7 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   if ((rc = attn_tmap(&p.tmK, k, ldk, heads, d, Nk, n_img, AT_BH))) return rc;
   if ((rc = attn_tmap(&p.tmV, v, ldv, heads, d, Nk, n_img, AT_BH))) return rc;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.ldq = ldq;
   p.ldo = ldo; p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
@@ -564,6 +595,7 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM128);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<4, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, true>::SMEM);
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
@@ -576,6 +608,13 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   // third pair on the FMA pipes + FMNMX3 row maximum, 4 = 3 with the two-instruction maximum (the r01 kernel).
   const char* pe = getenv("LKGD_ATTN_POLY");
   const int poly = pe ? atoi(pe) : 4;      // FMNMX3 (3) measured 3 % SLOWER than two FMNMX at L0 (6.18 vs 6.01 ms): half rate
+  // LKGD_ATTN_QT=1: Q as a TMEM operand (two CTAs per SM) - A/B switch of tools/bench_attn.py; needs 16-byte aligned rows
+  if (const char* qt = getenv("LKGD_ATTN_QT")) {
+    if (atoi(qt) == 1 && aligned16(q) && (heads * d) % 8 == 0 && d % 8 == 0) {
+      attn_flash_kernel<4, 64, true><<<grid, AT_THREADS, AttnCfg<64, true>::SMEM, st>>>(p);
+      return launch_epilogue();
+    }
+  }
   switch (poly) {
     case -1: attn_flash_kernel<-1, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;
     case 0: attn_flash_kernel<0, 64><<<grid, AT_THREADS, AT_SMEM, st>>>(p); break;

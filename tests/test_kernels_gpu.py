@@ -255,6 +255,23 @@ def test_attention_cross_kv_len(cuda):
     assert rel_l2(out.float(), chk.float()) < 6e-3
 
 
+@pytest.mark.parametrize("n_img,heads,d,Nq,Nk", [(2, 5, 64, 576, 576), (1, 2, 64, 200, 77), (2, 3, 32, 300, 129),
+                                                 (1, 2, 16, 130, 64), (1, 5, 64, 2304, 2304)])
+def test_attention_q_in_tmem_variant(cuda, monkeypatch, n_img, heads, d, Nq, Nk):
+    """LKGD_ATTN_QT=1: the variant that keeps Q in tensor memory (TS-form Q K^T, two CTAs per SM) - same results as the
+    default kernel (same arithmetic, same order) and as the fp32 reference."""
+    from lkgd_b200 import ops
+    q = rnd(n_img * Nq, heads * d, dev=cuda)
+    k = rnd(n_img * Nk, heads * d, dev=cuda, seed=1)
+    v = rnd(n_img * Nk, heads * d, dev=cuda, seed=2)
+    base = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=Nq, Nk=Nk)
+    monkeypatch.setenv("LKGD_ATTN_QT", "1")
+    qt = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=Nq, Nk=Nk)
+    monkeypatch.delenv("LKGD_ATTN_QT")
+    assert rel_l2(qt.float(), _attn_ref(q, k, v, n_img, heads, d, Nq, Nk)) < 6e-3
+    assert rel_l2(qt.float(), base.float()) < 1e-3
+
+
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("Nk", [1, 5, 63, 64, 65, 129])
 def test_attention_short_and_ragged_kv(cuda, Nk, d):

@@ -15,13 +15,16 @@ for i in only:
     v = qkv[:, 2 * C:]
     f = lambda: ops.attention(qkv[:, :C], qkv[:, C:2 * C], v, n_img=n_img, heads=heads, d=64, Nq=N, Nk=N, out=out)
     f(); f()
-    # LKGD_ATTN_POLY_AB=0,2,3,4: time the variants interleaved in one process (the library reads the switch per call)
-    variants = os.environ.get("LKGD_ATTN_POLY_AB", "").split(",") if os.environ.get("LKGD_ATTN_POLY_AB") else [None]
+    # LKGD_ATTN_POLY_AB=0,2,3,4 / LKGD_ATTN_QT_AB=0,1: time the variants interleaved in one process (the library reads the
+    # switches per call)
+    var_name = "LKGD_ATTN_QT" if os.environ.get("LKGD_ATTN_QT_AB") else "LKGD_ATTN_POLY"
+    ab = os.environ.get("LKGD_ATTN_QT_AB") or os.environ.get("LKGD_ATTN_POLY_AB")
+    variants = ab.split(",") if ab else [None]
     ts = {pv: [] for pv in variants}
     for _ in range(5):
         for pv in variants:
             if pv is not None:
-                os.environ["LKGD_ATTN_POLY"] = pv
+                os.environ[var_name] = pv
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); f(); e1.record(); torch.cuda.synchronize()
@@ -30,4 +33,4 @@ for i in only:
         ms = sorted(ts[pv])[2]
         print(json.dumps(dict(name=name, poly=pv, n_img=n_img, heads=heads, N=N, ms=round(ms, 4),
                               tflops=round(4.0 * n_img * heads * N * N * 64 / ms / 1e9, 1))), flush=True)
-    os.environ.pop("LKGD_ATTN_POLY", None)
+    os.environ.pop(var_name, None)
