@@ -182,6 +182,52 @@ class PackedCross:
         return self._general
 
 
+def _partners(mask: torch.Tensor, batch: int) -> List[int]:
+    """Partner sample of every sample under the reference's swap ``enc[~m] = n[m]; enc[m] = n[~m]`` with ``m`` the mask
+    repeat-interleaved over the batch (patch/patch.py:444-456): the k-th unmasked sample pairs with the k-th masked one."""
+    if mask is None:
+        raise ValueError("joint attention needs a joint attention mask (patch.set_joint_attention_mask)")
+    if batch % len(mask):
+        raise ValueError(f"batch {batch} is not a multiple of the joint attention mask length {len(mask)}")
+    m = mask.repeat_interleave(batch // len(mask)).tolist()
+    t = [i for i, v in enumerate(m) if v]
+    f = [i for i, v in enumerate(m) if not v]
+    if len(t) != len(f):
+        raise ValueError("the joint attention mask must select half of the batch")
+    out = [0] * batch
+    for a, b in zip(f, t):
+        out[a], out[b] = b, a
+    return out
+
+
+class PackedJoint:
+    """Joint-attention branch of a patched block (patch/patch.py ToMeBlock): ``attn1n`` projections + the post layer and
+    ``joint_scale`` folded into its output projection: post(to_out(a)) * s = a (s P Wo)^T + s P bo."""
+
+    def __init__(self, blk, spatial: bool):
+        if not hasattr(blk, "attn1n") or blk.post is None:
+            raise ValueError("joint attention is enabled on a block without joint layers: call "
+                             "patch.initialize_joint_layers(unet) after patch.apply_patch(unet)")
+        a = blk.attn1n
+        wq, _ = _merged_weight(a.to_q)
+        wk, _ = _merged_weight(a.to_k)
+        wv, _ = _merged_weight(a.to_v)
+        wo, bo = _merged_weight(a.to_out[0])
+        if blk.post == "conv":
+            pw = blk.conv1n.weight.detach().double()
+            w_post, b_post = pw @ wo.double(), pw @ bo.double()
+        else:
+            sc = blk.scale1n.detach().double().reshape(-1)
+            w_post, b_post = sc[:, None] * wo.double(), sc * bo.double()
+        s = float(blk.joint_scale) if spatial else 1.0        # the temporal branch has no joint_scale (patch.py:655)
+        self.wq = wq.to(bf16).contiguous()
+        self.wkv = torch.cat([wk, wv], 0).to(bf16).contiguous()
+        self.post_w = (w_post * s).float().to(bf16).contiguous()
+        self.post_b = (b_post * s).float().contiguous()
+        self.mask = blk.joint_attn_mask
+        self.flip = bool(blk.flip) and spatial
+
+
 class PackedTransformer:
     def __init__(self, t: M.TransformerSpatioTemporalModel, fold_lora: bool):
         self.heads, self.d, self.c = t.heads, t.dim_head, t.in_channels
@@ -199,6 +245,8 @@ class PackedTransformer:
         self.t_qkv, self.t_out = _qkv(tb.attn1, fold_lora), _dense(tb.attn1.to_out[0], fold_lora)
         self.t_cross = PackedCross(tb.attn2)
         self.t_ff1, self.t_ff2 = _geglu(tb.ff, fold_lora)
+        self.s_joint = PackedJoint(sb, True) if sb.joint_active() else None
+        self.t_joint = PackedJoint(tb, False) if tb.joint_active() else None
         self.alpha = float(torch.sigmoid(t.time_mixer.mix_factor.detach().float()).item())
         pe = t.time_pos_embed
         self.pe = (_f32(pe.linear_1.weight), _f32(pe.linear_1.bias), _f32(pe.linear_2.weight), _f32(pe.linear_2.bias))
@@ -351,6 +399,25 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, Nq=g.HW,
                       Nk=g.HW)
     h = dense(a, p.s_out, res1=h, out_f32=True)
+    if p.s_joint is not None:
+        # joint attention (patch/patch.py:434-492): queries of sample i against the keys / values of its PARTNER sample,
+        # addressed in place (row offsets into the fused projection; with `flip` frame f meets the partner's frame
+        # F-1-f); post layer and joint_scale are folded into the output projection, which accumulates onto h in place
+        J = p.s_joint
+        rows = g.F * g.HW
+        qn, kvn = ops.gemm(n, J.wq), ops.gemm(n, J.wkv)
+        an = torch.empty((g.M, C), device=n.device, dtype=bf16)
+        for i, pi in enumerate(_partners(J.mask, g.B)):
+            if not J.flip:
+                ops.attention(qn[i * rows:(i + 1) * rows], kvn[pi * rows:(pi + 1) * rows, :C],
+                              kvn[pi * rows:(pi + 1) * rows, C:], n_img=g.F, heads=p.heads, d=p.d, Nq=g.HW, Nk=g.HW,
+                              out=an[i * rows:(i + 1) * rows])
+            else:
+                for f in range(g.F):
+                    q0, k0 = i * rows + f * g.HW, pi * rows + (g.F - 1 - f) * g.HW
+                    ops.attention(qn[q0:q0 + g.HW], kvn[k0:k0 + g.HW, :C], kvn[k0:k0 + g.HW, C:], n_img=1,
+                                  heads=p.heads, d=p.d, Nq=g.HW, Nk=g.HW, out=an[q0:q0 + g.HW])
+        h = ops.gemm(an, J.post_w, bias=J.post_b, res1=h, out=h, out_f32=True)
     if kv1:
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross),
                           rv=g.rv(RV_BATCH), sum_out=h)
@@ -370,6 +437,18 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     qkv = dense(n, p.t_qkv)
     a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
     t = dense(a, p.t_out, res1=t, out_f32=True)
+    if p.t_joint is not None:
+        # temporal joint attention (patch/patch.py:617-658): pixel (b, p)'s frames attend to the partner sample's frames
+        # at the same pixel.  The fused [q | k | v] buffer of the temporal kernel is written directly in partner order:
+        # q from every sample's own rows, k / v from the partner's rows (one projection launch per sample, no copy)
+        J = p.t_joint
+        rows = g.F * g.HW
+        buf = torch.empty((g.M, 3 * C), device=n.device, dtype=bf16)
+        ops.gemm(n, J.wq, out=buf[:, :C])
+        for i, pi in enumerate(_partners(J.mask, g.B)):
+            ops.gemm(n[pi * rows:(pi + 1) * rows], J.wkv, out=buf[i * rows:(i + 1) * rows, C:])
+        an = ops.attention_temporal(buf, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
+        t = ops.gemm(an, J.post_w, bias=J.post_b, res1=t, out=t, out_f32=True)
     if kv1:
         # under a CFG pair split ctx_t holds every half's context: index it exactly as the unsplit batch would
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),

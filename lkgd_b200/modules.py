@@ -81,7 +81,52 @@ class FeedForward(Container):
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), Linear(dim * mult, dim_out or dim)])
 
 
-class BasicTransformerBlock(Container):
+class _JointAttention:
+    """State of the reference's joint-attention patch (``patch/patch.py`` ToMeBlock) on a transformer
+    block: a second attention ``attn1n`` whose keys / values come from the PARTNER sample of the batch, a zero-initialised
+    post layer (``conv1n`` = bias-free Linear, or ``scale1n``) and the switches the reference keeps on the patched block.
+    Parameter names equal the reference's (``...transformer_blocks.0.attn1n.to_q.weight``, ``...conv1n.weight``)."""
+    enable_joint_attention = False          # patch.py:104 is True by default once PATCHED; un-patched blocks have none
+    joint_scale = 1.0
+    patched = False                         # set by lkgd_b200.patch.apply_patch
+    flip = False                            # _tome_info["args"]["flip"] (spatial block only, :458-464)
+    joint_attn_mask = None
+    post = None
+    add_norm = False
+
+    def initialize_joint_layers(self, post: str = "conv", add_norm: bool = False):
+        """``ToMeBlock.initialize_joint_layers`` (patch/patch.py:143-172)."""
+        import copy
+        if add_norm:
+            raise NotImplementedError("add_norm=True (AdaLayerNormContinuous on the joint branch) is not built")
+        if post not in ("conv", "scale"):
+            raise NotImplementedError(f"post={post!r}: 'conv' and 'scale' are built ('conv_fuse' is not)")
+        self.attn1n = copy.deepcopy(self.attn1)
+        c = self.attn1.to_out[0].out_features
+        dev, dt = self.attn1.to_out[0].weight.device, self.attn1.to_out[0].weight.dtype
+        if post == "scale":
+            self.scale1n = nn.Parameter(torch.zeros(1, 1, c, device=dev, dtype=dt))
+        else:
+            self.conv1n = Linear(c, c, bias=False, device=dev, dtype=dt)
+            if dev.type != "meta":
+                nn.init.zeros_(self.conv1n.weight)
+        self.post, self.add_norm, self.joint_scale = post, add_norm, 1.0
+
+    @property
+    def post_joint(self):
+        return self.scale1n if self.post == "scale" else self.conv1n
+
+    def set_joint_attention(self, enable: bool = True):
+        self.enable_joint_attention = enable
+
+    def set_joint_scale(self, scale: float = 1.0):
+        self.joint_scale = scale
+
+    def joint_active(self) -> bool:
+        return bool(self.patched and self.enable_joint_attention)
+
+
+class BasicTransformerBlock(_JointAttention, Container):
     def __init__(self, dim, heads, dim_head, cross_attention_dim):
         super().__init__()
         self.norm_type, self.only_cross_attention, self.pos_embed = "layer_norm", False, None
@@ -94,7 +139,7 @@ class BasicTransformerBlock(Container):
         self.ff = FeedForward(dim)
 
 
-class TemporalBasicTransformerBlock(Container):
+class TemporalBasicTransformerBlock(_JointAttention, Container):
     def __init__(self, dim, time_mix_inner_dim, heads, dim_head, cross_attention_dim):
         super().__init__()
         self.is_res = dim == time_mix_inner_dim

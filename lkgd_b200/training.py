@@ -48,6 +48,8 @@ def res_train_weights(p: PackedResBlock) -> NS:
 
 def tr_train_weights(p: PackedTransformer) -> NS:
     if getattr(p, "_tw", None) is None:
+        if p.s_joint is not None or p.t_joint is not None:
+            raise NotImplementedError("training through the joint-attention branch is not built (inference only)")
         for d in (p.proj_in, p.proj_out, p.s_qkv, p.s_out, p.s_ff2, p.t_ffin2, p.t_out, p.t_ff2, p.s_ff1, p.t_ffin1,
                   p.t_ff1):
             if d.lora_a is not None:

@@ -122,8 +122,47 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim)
 
+    # ---- joint attention between paired samples (reference ``patch/patch.py`` ToMeBlock): off by default
+    enable_joint_attention = False
+    joint_scale = 1.0
+    flip = False                 # ``_tome_info["args"]["flip"]`` (:460-464)
+    num_frames = None            # ``_tome_info["size"][1]``
+
+    def initialize_joint_layers(self, post="conv"):
+        """``ToMeBlock.initialize_joint_layers`` (:143-172): a copy of attn1 + a zero-initialised post layer."""
+        import copy
+        self.attn1n = copy.deepcopy(self.attn1)
+        c = self.attn1.to_out[0].out_features
+        if post == "scale":
+            self.scale1n = nn.Parameter(torch.zeros(1, 1, c))
+        elif post == "conv":
+            self.conv1n = nn.Linear(c, c, bias=False)
+            nn.init.zeros_(self.conv1n.weight)
+        else:
+            raise ValueError(post)
+        self.post = post
+
+    def _partner(self, n, mask):
+        """:452-456 - joint_enc[~m] = n[m]; joint_enc[m] = n[~m] with the mask repeat-interleaved over the batch."""
+        m = mask.repeat_interleave(n.shape[0] // len(mask), dim=0)
+        out = torch.empty_like(n)
+        out[~m] = n[m]
+        out[m] = n[~m]
+        return out
+
+    def _post(self, y):
+        return self.conv1n(y) if self.post == "conv" else self.scale1n * y
+
     def forward(self, x, encoder_hidden_states):
-        x = x + self.attn1(self.norm1(x))
+        n = self.norm1(x)
+        a = self.attn1(n)
+        if self.enable_joint_attention:                                   # :434-492
+            enc = self._partner(n, self.joint_attn_mask)
+            if self.flip:
+                f = self.num_frames
+                enc = enc.reshape(-1, f, *enc.shape[1:]).flip(dims=[1]).reshape(enc.shape)
+            a = a + self._post(self.attn1n(n, enc)) * self.joint_scale
+        x = x + a
         x = x + self.attn2(self.norm2(x), encoder_hidden_states)
         x = x + self.ff(self.norm3(x))
         return x
@@ -145,6 +184,9 @@ class TemporalBasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(time_mix_inner_dim, eps=1e-5)
         self.ff = FeedForward(time_mix_inner_dim)
 
+    enable_joint_attention = False
+    initialize_joint_layers = BasicTransformerBlock.initialize_joint_layers
+
     def forward(self, x, num_frames: int, encoder_hidden_states):
         bf, n, c = x.shape
         b = bf // num_frames
@@ -153,7 +195,11 @@ class TemporalBasicTransformerBlock(nn.Module):
         x = self.ff_in(self.norm_in(x))
         if self.is_res:
             x = x + res
-        x = self.attn1(self.norm1(x)) + x
+        nh = self.norm1(x)
+        a = self.attn1(nh)
+        if self.enable_joint_attention:                                   # :617-658 (no joint_scale, no flip here)
+            a = a + BasicTransformerBlock._post(self, self.attn1n(nh, BasicTransformerBlock._partner(self, nh, self.joint_attn_mask)))
+        x = a + x
         x = self.attn2(self.norm2(x), encoder_hidden_states) + x
         y = self.ff(self.norm3(x))
         x = y + x if self.is_res else y

@@ -25,6 +25,7 @@ class Attention(nn.Module):
         super().__init__()
         inner = heads * dim_head
         self.heads = heads
+        self.out_dim = query_dim                 # read by ToMeBlock.initialize_joint_layers (patch/patch.py:147-151)
         kv = query_dim if cross_attention_dim is None else cross_attention_dim
         self.to_q = nn.Linear(query_dim, inner, bias=False)
         self.to_k = nn.Linear(kv, inner, bias=False)

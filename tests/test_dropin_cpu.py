@@ -121,3 +121,42 @@ def test_from_pretrained_and_save_pretrained(tmp_path):
     with pytest.raises(EnvironmentError, match="local"):
         U.UNetSpatioTemporalConditionControlNetModel.from_pretrained("stabilityai/stable-video-diffusion-img2vid",
                                                                      subfolder="unet")
+
+
+def test_joint_attention_patch_api_on_cpu():
+    """lkgd_b200.patch mirrors the reference's patch/patch.py entry points: parameter names of the joint layers equal the
+    reference's (golden from the reference's own initialize_joint_layers), switches land on the blocks, errors are loud."""
+    import numpy as np
+    from lkgd_b200 import modules as M, patch
+    from lkgd_b200.engine import _partners
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    JG = np.load(os.path.join(HERE, "golden", "joint_attention_golden.npz"))
+    u = UNetSpatioTemporalConditionControlNetModel(**REDUCED4)
+    patch.apply_patch(u, flip=True, with_temporal_block=True)
+    patch.initialize_joint_layers(u, post="conv")
+    assert sorted(n for n, _ in u.named_parameters() if "1n" in n) == list(JG["ja/param_names"])
+    blocks = [m for m in u.modules() if isinstance(m, (M.BasicTransformerBlock, M.TemporalBasicTransformerBlock))]
+    assert len(blocks) == 12 and all(b.patched and b.enable_joint_attention for b in blocks)
+    assert all(b.flip == isinstance(b, M.BasicTransformerBlock) for b in blocks)        # flip acts in the spatial block
+    assert all(float(b.conv1n.weight.abs().max()) == 0.0 for b in blocks)                # zero-initialised (:152-153)
+    patch.set_joint_attention_mask(u, [0, 1, 0, 1])
+    patch.set_joint_scale(u, 0.5)
+    patch.set_joint_attention(u, False, name_filter="up_blocks")
+    assert all(b.joint_scale == 0.5 and b.joint_attn_mask.tolist() == [False, True, False, True] for b in blocks)
+    on = [n for n, b in u.named_modules() if isinstance(b, M.BasicTransformerBlock) and b.enable_joint_attention]
+    assert on and all("up_blocks" not in n for n in on)
+    assert _partners(torch.tensor([0, 1, 0, 1], dtype=torch.bool), 4) == [1, 0, 3, 2]
+    assert _partners(torch.tensor([0, 1], dtype=torch.bool), 4) == [2, 3, 0, 1]           # repeat_interleave: x x y y
+    with pytest.raises(ValueError, match="half"):
+        _partners(torch.tensor([1, 1, 1, 0], dtype=torch.bool), 4)
+    patch.remove_patch(u)
+    assert not any(b.patched or b.enable_joint_attention for b in blocks)
+    with pytest.raises(NotImplementedError):
+        patch.apply_patch(u, single_dir=True)
+    u.add_lora(4)
+    patch.set_patch_lora_mask(u, "default", [1, 0])
+    with pytest.raises(NotImplementedError, match="masked"):
+        patch.hack_lora_forward(u)
+    patch.set_patch_lora_mask(u, "default", [1, 1])
+    patch.hack_lora_forward(u)
+    assert u.lora_mask["default"].tolist() == [True, True]

@@ -225,3 +225,37 @@ def test_joint_input_head_unet_vs_reference(cuda):
     u.set_lora_mask("yx_lora", [0, 0, 0, 0])
     with pytest.raises(ValueError, match="at least one sample"):
         u(sample, ts, ctx, added_time_ids=ids)
+
+
+@pytest.mark.parametrize("tag", ["conv", "conv_flip", "scale_pair"])
+def test_joint_attention_patch_vs_reference(cuda, tag):
+    """lkgd_b200.patch (apply_patch / initialize_joint_layers / set_joint_attention_mask / set_joint_scale)
+    + the engine's joint-attention branch against the reference's own patch/patch.py forwards with joint attention ON
+    (tests/golden/make_joint_attention_golden.py)."""
+    import os
+    from golden_util import HERE
+    from test_oracle_golden import JA_CASES, ja_inputs
+    from lkgd_b200 import patch
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    JG = np.load(os.path.join(HERE, "golden", "joint_attention_golden.npz"))
+    post, flip, temporal, mask, jscale = JA_CASES[tag]
+    u = UNetSpatioTemporalConditionControlNetModel(**REDUCED4)
+    patch.apply_patch(u, flip=flip, with_spatial_block=True, with_temporal_block=temporal)
+    patch.initialize_joint_layers(u, post=post)
+    u = fill_seeded_(u).to(cuda)
+    if tag == "conv":
+        assert sorted(n for n, _ in u.named_parameters() if "1n" in n) == list(JG["ja/param_names"])
+    patch.set_joint_attention_mask(u, mask)
+    patch.set_joint_scale(u, jscale)
+    sample, ctx, ids = (v.to(cuda) for v in ja_inputs())
+    out = u(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0]
+    err = rel(out, JG[f"ja/out_{tag}"])
+    print("joint attention", tag, err)
+    assert err < 1e-2
+    if tag == "conv":
+        patch.set_joint_attention(u, False)
+        off = u(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0]
+        assert rel(off, JG["ja/out_off"]) < 1e-2 and rel(out, off) > 5e-2
+        patch.remove_patch(u)
+        assert rel(u(sample, torch.tensor(T_STEP, device=cuda), ctx, added_time_ids=ids, return_dict=False)[0],
+                   JG["ja/out_off"]) < 1e-2

@@ -179,6 +179,47 @@ def test_joint_input_head_unet_matches_reference():
         assert rel(a, JG[f"joint/out_{tag}"]) < 1e-6, tag
 
 
+JA_CASES = {"conv": ("conv", False, True, [0, 1, 0, 1], 1.0), "conv_flip": ("conv", True, False, [0, 1, 0, 1], 0.7),
+            "scale_pair": ("scale", False, True, [0, 1], 1.0)}      # post, flip, temporal blocks too, mask, joint_scale
+
+
+def ja_inputs():
+    sample = seeded_tensor("ja/sample", (4, F, 8, H, W))
+    ctx = seeded_tensor("ja/ctx", (4, 1, 32))
+    return sample, ctx, torch.tensor([[6.0, 127.0, 0.02]] * 4)
+
+
+@pytest.mark.parametrize("tag", list(JA_CASES))
+def test_joint_attention_matches_the_references_patch(tag):
+    """the oracle's joint-attention branch (second attention over the partner sample, post layer,
+    joint_scale, frame flip; spatial and temporal blocks) against the reference's own patch/patch.py ToMeBlock forwards
+    with enable_joint_attention = True, run on torch-primitive blocks (tests/golden/make_joint_attention_golden.py)."""
+    JG = np.load(os.path.join(HERE, "golden", "joint_attention_golden.npz"))
+    post, flip, temporal, mask, jscale = JA_CASES[tag]
+    o = O.UNetSpatioTemporalConditionControlNetModel(**REDUCED4)
+    for m in o.modules():
+        if isinstance(m, O.BasicTransformerBlock) or (temporal and isinstance(m, O.TemporalBasicTransformerBlock)):
+            m.initialize_joint_layers(post)
+    o = fill_seeded_(o).eval()
+    if tag == "conv":
+        assert sorted(n for n, _ in o.named_parameters() if "1n" in n) == list(JG["ja/param_names"])
+    for m in o.modules():
+        if hasattr(m, "attn1n"):
+            m.enable_joint_attention, m.joint_scale, m.flip, m.num_frames = True, jscale, flip, F
+            m.joint_attn_mask = torch.tensor(mask, dtype=torch.bool)
+    sample, ctx, ids = ja_inputs()
+    with torch.no_grad():
+        a = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids, return_dict=False)[0]
+    assert rel(a, JG[f"ja/out_{tag}"]) < 2e-6
+    if tag == "conv":
+        for m in o.modules():
+            if hasattr(m, "attn1n"):
+                m.enable_joint_attention = False
+        with torch.no_grad():
+            b = o(sample, torch.tensor(T_STEP), ctx, added_time_ids=ids, return_dict=False)[0]
+        assert rel(b, JG["ja/out_off"]) < 2e-6 and rel(a, b) > 5e-2          # the branch matters
+
+
 def test_flow_stem_unet_matches_reference():
     """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
     by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""
