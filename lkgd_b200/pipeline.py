@@ -118,7 +118,11 @@ class StableVideoDiffusionPipeline:
             cc = controlnet_condition
             if cc.ndim == 4:
                 cc = cc.unsqueeze(0)
-            cc = torch.cat([cc] * 2) if do_cfg else cc      # reference :547-550 duplicates unconditionally (D3)
+            # reference :547-550 duplicates the condition for the two CFG halves (D3): kept as ONE copy + a repeat count, the
+            # ControlNet's pixel-resolution condition encoder then runs once per step instead of twice
+            cond_repeat = 2 if do_cfg else 1
+            if cc.shape[0] * cond_repeat != n_lat:
+                raise ValueError("controlnet_condition batch does not match the conditioning batch")
             controlnet_condition = cc.to(device=device, dtype=torch.float32)
         if cfg_pair is not None and (not do_cfg or controlnet_condition is not None):
             raise ValueError("cfg_pair needs classifier-free guidance and (for now) no ControlNet")
@@ -128,6 +132,7 @@ class StableVideoDiffusionPipeline:
                     image_latents=image_latents.to(device=device, dtype=torch.float32).contiguous(),
                     image_embeddings=image_embeddings.to(device), controlnet_condition=controlnet_condition,
                     controlnet_cond_scale=controlnet_cond_scale,
+                    controlnet_cond_repeat=(2 if do_cfg else 1) if controlnet_condition is not None else 1,
                     extra=(domain_features.to(device), flow_features.to(device)) if lkgd else ())
 
     @property
@@ -148,10 +153,12 @@ class StableVideoDiffusionPipeline:
         if st["controlnet_condition"] is not None:
             if st.get("fuse_controlnet", True):
                 # residual injection fused into the UNet forward: the ControlNet's zero convs add onto the UNet's skips
-                kw = dict(fused_controlnet=(self.controlnet, st["controlnet_condition"], st["controlnet_cond_scale"]))
+                kw = dict(fused_controlnet=(self.controlnet, st["controlnet_condition"], st["controlnet_cond_scale"],
+                                            st["controlnet_cond_repeat"]))
             else:   # the reference's hand-off: 12 + 1 residual tensors, added by the UNet (:585-607)
                 down, mid = self.controlnet.forward_packed(x, g, t, st["image_embeddings"], st["added_time_ids"],
-                                                           st["controlnet_condition"], st["controlnet_cond_scale"])
+                                                           st["controlnet_condition"], st["controlnet_cond_scale"],
+                                                           cond_repeat=st["controlnet_cond_repeat"])
                 kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
         rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
                                    added_time_ids=st["added_time_ids"], **kw)

@@ -498,11 +498,13 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
             if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
                     or batch_slice is not None:
                 raise ValueError("fused_controlnet excludes explicit residuals and batch_slice")
-            cn, cn_cond, cn_scale = fused_controlnet
+            cn, cn_cond, cn_scale = fused_controlnet[:3]
+            cn_repeat = fused_controlnet[3] if len(fused_controlnet) > 3 else 1
             per_block = [len(d[0]) + (1 if d[2] is not None else 0) for d in pk.down]
             per_block[0] += 1
             mult = residual_multipliers(len(pk.down), per_block)
-            x = cn.inject_packed(x_in, g, timestep, encoder_hidden_states, ids, cn_cond, cn_scale, skips, mult, x)
+            x = cn.inject_packed(x_in, g, timestep, encoder_hidden_states, ids, cn_cond, cn_scale, skips, mult, x,
+                                 cond_repeat=cn_repeat)
         if mid_block_additional_residual is not None:
             ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)
         if down_block_additional_residuals is not None:
@@ -1030,8 +1032,12 @@ class ControlNetSDVModel(_Base):
             self._cn = (packed, zero)
         return self._cn
 
-    def _encode(self, x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond, bf16_skips):
-        """Condition encoder (pixel resolution, models/controlnet_sdv.py:98-119) + the copied UNet encoder + mid block."""
+    def _encode(self, x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond, bf16_skips, cond_repeat=1):
+        """Condition encoder (pixel resolution, models/controlnet_sdv.py:98-119) + the copied UNet encoder + mid block.
+        ``cond_repeat``: ``controlnet_cond`` holds batch / cond_repeat samples and every one conditions ``cond_repeat``
+        batch entries (the pipeline feeds the SAME condition frames to both classifier-free-guidance halves,
+        pipeline...controlnet.py:547-550): the seven pixel-resolution convs then run once instead of twice, only the last
+        (latent-resolution) conv is issued per copy, writing straight into its slice of the stem tensor."""
         pk = self.packed()
         convs, zero = self._cn_pack()
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
@@ -1041,28 +1047,32 @@ class ControlNetSDVModel(_Base):
             if controlnet_cond.ndim != 5:
                 raise ValueError("controlnet_cond must be [batch, frames, channels, height, width]")
             b_, f_, cc, hc, wc = controlnet_cond.shape
+            if b_ * cond_repeat * f_ != g.BF:
+                raise ValueError("controlnet_cond batch x frames does not match the sample")
             e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=self.COND_CPAD)
             hh, ww = hc, wc
-            for i, (w, b, stride, _) in enumerate(convs):
-                last = i == len(convs) - 1
-                e = ops.gemm(e, w, mode=A_CONV3X3, conv=(b_ * f_, hh, ww, stride), bias=b,
-                             act=0 if last else ACT_SILU)
+            for i, (w, b, stride, _) in enumerate(convs[:-1]):
+                e = ops.gemm(e, w, mode=A_CONV3X3, conv=(b_ * f_, hh, ww, stride), bias=b, act=ACT_SILU)
                 if stride == 2:
                     hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
-            if (hh, ww) != (g.H, g.W) or b_ * f_ != g.BF:
+            if (hh, ww) != (g.H, g.W):
                 raise ValueError("controlnet_cond resolution must be 8x the latent resolution")
-            stem_add = e
+            w, b, _, _ = convs[-1]
+            rows = b_ * f_ * hh * ww
+            stem_add = torch.empty((cond_repeat * rows, w.shape[0]), device=e.device, dtype=bf16)
+            for r in range(cond_repeat):
+                ops.gemm(e, w, mode=A_CONV3X3, conv=(b_ * f_, hh, ww, 1), bias=b, out=stem_add[r * rows:(r + 1) * rows])
         return pk.encoder(x, g, cond, stem_add=stem_add, bf16_skips=bf16_skips), zero
 
     @ops.on_own_device
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
                        added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor] = None,
-                       conditioning_scale: float = 1.0):
+                       conditioning_scale: float = 1.0, cond_repeat: int = 1):
         """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
         ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
-                                                    controlnet_cond, bf16_skips=True)
+                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat)
         s = float(conditioning_scale)
         down = [ChannelsLast(ops.gemm(skb, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
                 for (_, skb), (w, b), gs in zip(skips, zero[:-1], geoms)]
@@ -1072,14 +1082,15 @@ class ControlNetSDVModel(_Base):
     @torch.no_grad()
     def inject_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
                       added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor], conditioning_scale: float,
-                      unet_skips: List[torch.Tensor], multipliers: Sequence[int], unet_mid: torch.Tensor) -> torch.Tensor:
+                      unet_skips: List[torch.Tensor], multipliers: Sequence[int], unet_mid: torch.Tensor,
+                      cond_repeat: int = 1) -> torch.Tensor:
         """The fused form of ``forward_packed`` + the UNet's residual adds: every zero conv writes
         ``unet_skip += m_i * scale * (W skip_cn + b)`` in place in its epilogue (fp32 residual read, fused GroupNorm
         statistics of the sum where a 128-row tile stays inside one frame), the mid zero conv does the same on the UNet's
         mid sample, which is returned.  Runs inside the UNet's forward: shares its statistics arena (no ``begin``).
         zip truncation as in the reference (:453-462): extra skips / residuals are ignored."""
         (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
-                                                    controlnet_cond, bf16_skips=True)
+                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat)
         s = float(conditioning_scale)
         for i, ((_, skb), (w, b), gs, m, us) in enumerate(zip(skips, zero[:-1], geoms, multipliers, unet_skips)):
             if us.shape != (gs.M, w.shape[0]):
