@@ -145,7 +145,12 @@ def save_state(trainer, output_dir: str, global_step: int, lora_name: str = "def
 def load_state(trainer, path: str, lora_name: str = "default", process_index: int = 0, restore_rng: bool = True) -> int:
     """``accelerator.load_state(path)`` + the reference's ``load_model_hook`` (:1157-1172): adapter tensors, Adam moments,
     step count and RNG states.  Returns the global step encoded in the directory name."""
+    # the trainer OWNS the kernel-ready pack of its UNet (its gradient slots are keyed by the packed layers and `repack`
+    # refreshes their bf16 operands in place from the flat fp32 parameters): loading adapter tensors must not drop it
+    pack = getattr(trainer.unet, "_packed", None)
     res = lora_io.load_lora_weights(trainer.unet, os.path.join(path, lora_name), adapter_name=lora_name, strict=True)
+    if pack is not None:
+        trainer.unet._packed = pack
     if not res["loaded"]:
         raise ValueError(f"no adapter tensors found under {path}/{lora_name}")
     opt = os.path.join(path, OPTIMIZER_NAME)

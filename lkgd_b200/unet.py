@@ -4,9 +4,13 @@ signatures and error behaviour as the reference classes, with the forward pass e
   UNetSpatioTemporalConditionControlNetModel  <- models/unet_spatio_temporal_condition_controlnet.py:69-245,358-508
   UNetSpatioTemporalConditionModel (LKGD)     <- models/unet_spatio_temporal_condition.py:72-298,448-693
   ControlNetSDVModel                          <- models/controlnet_sdv.py:160-316,441-578,581-638
+  UNetSpatioTemporalConditionModelFlow        <- models/unet_spatio_temporal_condition_flow.py (second, gated input stem)
+  UNetSpatioTemporalConditionJointModel       <- models/unet_spatio_temporal_condition_joint.py (x / y input heads)
 
-Inference only in this round (``forward`` runs under no_grad; training backward is SURVEY.md section 8 row a14/a15,
-not built yet)."""
+``forward`` is the inference path (runs under no_grad).  The LoRA fine-tuning step (SURVEY.md section 8 rows a14 / a15:
+forward with saved activations, hand-scheduled backward, clip + AdamW, flat gradient all-reduce) lives in
+``lkgd_b200/training.py`` and works on the same modules; construction from reference artefacts (``from_reference``,
+``from_pretrained``, ``add_adapter``) is on ``_Base`` below."""
 from __future__ import annotations
 
 import math
