@@ -340,6 +340,7 @@ class LoraTrainer:
         if not getattr(unet, "fold_lora", True):
             raise ValueError("training needs the LoRA pairs folded into the GEMM (fold_lora=True)")
         pk = unet.packed()
+        self._pk = pk            # the trainer owns this pack: gradient slots are keyed by its layers (see forward_backward)
         self.layers = [a for blk in pk.down if blk[1] for a in blk[1]] + list(pk.mid[1]) + \
                       [a for blk in pk.up if blk[1] for a in blk[1]]
         mods = []
@@ -464,6 +465,10 @@ class LoraTrainer:
         gradients are accumulated into the flat gradient buffer."""
         unet = self.unet
         pk = unet.packed()
+        if pk is not self._pk:
+            raise RuntimeError("the UNet was re-packed (invalidate() / load_state_dict / .to) after this LoraTrainer was "
+                               "built: its gradient slots and bf16 operand views belong to the previous pack - build a new "
+                               "trainer, or restore adapters through LoraTrainer.load_state")
         dev = unet.device
         B, F, Cl, h, w = latents.shape
         f32 = torch.float32
