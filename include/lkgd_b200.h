@@ -229,6 +229,19 @@ LKGD_API int lkgd_concat_channels(const void* a, int32_t Ca, const void* b, int3
 LKGD_API int lkgd_axpby(const void* x, int32_t x_f32, float alpha, void* y, int32_t y_f32, float beta, int64_t n,
                void* stream);
 
+/* Thin 3x3 convolutions (pad 1, stride 1) of the ControlNet condition encoder at pixel resolution
+ * (models/controlnet_sdv.py:64-119, `ControlNetConditioningEmbeddingSVD`): HBM-bound layers with 2-32 channels.
+ *   lkgd_cond_conv_in : x fp32 planar [N, Cc, H, W] (Cc <= 4; the reference's `controlnet_cond` flattened over batch and
+ *                       frames), weight fp32 [16, Cc, 3, 3], bias fp32 [16] -> out bf16 channels-last [N, H, W, 16] = SiLU(conv)
+ *                       (`conv_in` + `F.silu`, :104-105; also replaces the fp32 -> bf16 channels-last pack).
+ *   lkgd_thin_conv3x3 : x bf16 [N, H, W, Cin], weight bf16 [9, Cout, Cin] (tap-major: weight.permute(2,3,0,1)), bias fp32
+ *                       [Cout] -> out bf16 [N, H, W, Cout], optional SiLU; (Cin, Cout) in {(16,16), (16,32), (32,32)}
+ *                       (the stride-1 `blocks[2i]` convs + `F.silu`, :107-109). */
+LKGD_API int lkgd_cond_conv_in(const float* x, int32_t N, int32_t Cc, int32_t H, int32_t W, const float* weight,
+                      const float* bias, void* out, void* stream);
+LKGD_API int lkgd_thin_conv3x3(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, const void* weight,
+                      const float* bias, int32_t silu, void* out, void* stream);
+
 /* out[m, :] = srcs[g(m)][m, :] over bf16 [M, C] matrices (C % 8 == 0; srcs = HOST array of n_src <= 8 device pointers, g as
  * for the row vectors above).  Temporal cross-attention with KV length > 1 under the diffusers 0.27.2 context order: row m
  * of the temporal batch attends to context g(m) = TCTX_0272 (transformer_temporal.py `time_context` broadcast), so

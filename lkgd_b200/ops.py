@@ -482,6 +482,40 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cond_conv_in(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x fp32 [N, Cc, H, W] -> bf16 channels-last rows [N*H*W, 16] = SiLU(conv3x3(x) + bias) (lkgd_cond_conv_in)."""
+    _need_cuda(x, weight, bias)
+    x = x.to(torch.float32).contiguous()
+    N, Cc, H, W = x.shape
+    if weight.dtype != torch.float32 or not weight.is_contiguous() or tuple(weight.shape) != (16, Cc, 3, 3) \
+            or bias.dtype != torch.float32 or bias.numel() != 16:
+        raise ValueError("cond_conv_in: weight fp32 [16, Cc, 3, 3], bias fp32 [16]")
+    out = torch.empty((N * H * W, 16), device=x.device, dtype=bf16)
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": N * H * W * (Cc * 4 + 32), "flops": 2.0 * N * H * W * 9 * Cc * 16}
+    L.check(L.load().lkgd_cond_conv_in(x.data_ptr(), N, Cc, H, W, weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                       _stream()), "lkgd_cond_conv_in")
+    return out
+
+
+def thin_conv3x3(x: torch.Tensor, weight9: torch.Tensor, bias: torch.Tensor, N: int, H: int, W: int,
+                 silu: bool = True) -> torch.Tensor:
+    """x bf16 rows [N*H*W, Cin], weight9 bf16 [9, Cout, Cin] -> bf16 rows [N*H*W, Cout] (lkgd_thin_conv3x3)."""
+    _need_cuda(x, weight9, bias)
+    Cin = x.shape[-1]
+    Cout = weight9.shape[1]
+    if x.dtype != bf16 or not x.is_contiguous() or x.numel() != N * H * W * Cin or weight9.dtype != bf16 \
+            or not weight9.is_contiguous() or tuple(weight9.shape) != (9, Cout, Cin) or bias.dtype != torch.float32 \
+            or bias.numel() != Cout:
+        raise ValueError("thin_conv3x3: x bf16 [N*H*W, Cin], weight bf16 [9, Cout, Cin], bias fp32 [Cout]")
+    out = torch.empty((N * H * W, Cout), device=x.device, dtype=bf16)
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": N * H * W * (Cin + Cout) * 2, "flops": 2.0 * N * H * W * 9 * Cin * Cout}
+    L.check(L.load().lkgd_thin_conv3x3(x.data_ptr(), N, H, W, Cin, Cout, weight9.data_ptr(), bias.data_ptr(), int(silu),
+                                       out.data_ptr(), _stream()), "lkgd_thin_conv3x3")
+    return out
+
+
 def select_rows(srcs, rv: Tuple[int, int, int, int]) -> torch.Tensor:
     """out[m] = srcs[g(m)][m] over equally shaped contiguous bf16 [M, C] matrices (see lkgd_select_rows)."""
     _need_cuda(*srcs)

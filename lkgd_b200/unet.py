@@ -14,6 +14,7 @@ forward with saved activations, hand-scheduled backward, clip + AdamW, flat grad
 from __future__ import annotations
 
 import math
+import os
 import re
 from dataclasses import dataclass
 from types import SimpleNamespace
@@ -1025,11 +1026,20 @@ class ControlNetSDVModel(_Base):
             cin_pad = self.COND_CPAD
             if ce.conv_in.in_channels > cin_pad:
                 raise ValueError(f"conditioning_channels > {cin_pad} is not supported")
-            for cv in convs:
+            for i, cv in enumerate(convs):
                 cout = cv.out_channels
                 cout_pad = (cout + 15) // 16 * 16
-                w, b = _conv3x3_weight(cv, cin_pad=cin_pad, cout_pad=cout_pad)
-                packed.append((w, b, cv.stride[0], cout_pad))
+                # the bandwidth-bound thin layers at pixel resolution have their own kernels (csrc/thin_conv.cu): the stem
+                # reads the fp32 condition frames directly, the stride-1 16 -> 16 / 32 -> 32 convs run on mma.sync tiles
+                if i == 0 and cout == 16 and cv.in_channels <= 4 and not os.environ.get("LKGD_NO_THIN_CONV"):
+                    packed.append(("stem", _f32(cv.weight), _f32(cv.bias), 1, cout_pad))
+                elif i > 0 and cv.stride[0] == 1 and (cv.in_channels, cout) in ((16, 16), (32, 32), (16, 32)) \
+                        and cin_pad == cv.in_channels and not os.environ.get("LKGD_NO_THIN_CONV"):
+                    w9 = cv.weight.detach().float().permute(2, 3, 0, 1).reshape(9, cout, cv.in_channels)
+                    packed.append(("thin", w9.to(bf16).contiguous(), _f32(cv.bias), 1, cout_pad))
+                else:
+                    w, b = _conv3x3_weight(cv, cin_pad=cin_pad, cout_pad=cout_pad)
+                    packed.append((w, b, cv.stride[0], cout_pad))
                 cin_pad = cout_pad
             zero = [(cv.weight.detach().reshape(cv.out_channels, cv.in_channels).to(bf16).contiguous(), _f32(cv.bias))
                     for cv in list(self.controlnet_down_blocks) + [self.controlnet_mid_block]]
@@ -1053,9 +1063,18 @@ class ControlNetSDVModel(_Base):
             b_, f_, cc, hc, wc = controlnet_cond.shape
             if b_ * cond_repeat * f_ != g.BF:
                 raise ValueError("controlnet_cond batch x frames does not match the sample")
-            e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=self.COND_CPAD)
             hh, ww = hc, wc
-            for i, (w, b, stride, _) in enumerate(convs[:-1]):
+            e = None
+            for entry in convs[:-1]:
+                if entry[0] == "stem":           # (kind, fp32 weight, bias, ...): reads the fp32 frames directly
+                    e = ops.cond_conv_in(controlnet_cond.reshape(b_ * f_, cc, hc, wc), entry[1], entry[2])
+                    continue
+                if entry[0] == "thin":           # (kind, bf16 tap-major weight, bias, ...)
+                    e = ops.thin_conv3x3(e, entry[1], entry[2], b_ * f_, hh, ww, silu=True)
+                    continue
+                w, b, stride, _ = entry
+                if e is None:
+                    e = ops.pack_input(controlnet_cond, 1.0, None, N=b_, Cpad=self.COND_CPAD)
                 e = ops.gemm(e, w, mode=A_CONV3X3, conv=(b_ * f_, hh, ww, stride), bias=b, act=ACT_SILU)
                 if stride == 2:
                     hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1

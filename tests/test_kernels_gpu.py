@@ -584,3 +584,42 @@ def test_gemm_cta_pairs_match_single_cta_conv(cuda, n, h, w, ci, co, stride):
     Wt = rnd(co, 3 * ci, dev=cuda, scale=(3 * ci) ** -0.5, seed=6)
     one, two = _both_gemm_variants(lambda: ops.gemm(At, Wt, mode=ops.A_TCONV3, tconv=(Bt, Ft, HWt), out_f32=True))
     assert torch.equal(one, two)
+
+
+@pytest.mark.parametrize("N,Cc,H,W", [(2, 2, 64, 96), (1, 3, 50, 70), (3, 1, 17, 33), (1, 4, 8, 256)])
+def test_cond_conv_in(cuda, N, Cc, H, W):
+    """ControlNet condition stem (models/controlnet_sdv.py:104-105): fp32 planar frames -> SiLU(conv3x3) in bf16
+    channels-last, against torch conv2d."""
+    from lkgd_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(N, Cc, H, W, generator=g) * 2 - 1
+    w = torch.randn(16, Cc, 3, 3, generator=g) * (Cc * 9) ** -0.5
+    b = torch.randn(16, generator=g) * 0.1
+    ref = torch.nn.functional.silu(torch.nn.functional.conv2d(x, w, b, padding=1)).permute(0, 2, 3, 1).reshape(-1, 16)
+    out = ops.cond_conv_in(x.to(cuda), w.to(cuda), b.to(cuda))
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (N * H * W, 16)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,silu", [(2, 64, 96, 16, 16, True), (1, 50, 70, 32, 32, True), (3, 9, 33, 16, 32, False),
+                                                 (1, 4, 32, 16, 16, True), (2, 130, 5, 32, 32, False)])
+def test_thin_conv3x3(cuda, N, H, W, Cin, Cout, silu):
+    """Stride-1 thin convs of the condition encoder (controlnet_sdv.py:107-109) on mma.sync tiles with a cp.async halo:
+    image borders, partial 4 x 32 tiles, both channel widths - against torch conv2d on the same bf16 operands."""
+    from lkgd_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(N, H, W, Cin, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (Cin * 9) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    w9 = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous()
+    out = ops.thin_conv3x3(x.reshape(-1, Cin).to(cuda), w9.to(cuda), b.to(cuda), N, H, W, silu=silu)
+    assert rel_l2(out.float(), ref) < 4e-3
+    # same numbers as the tcgen05 implicit-GEMM path it replaces
+    wk = w.float().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).to(cuda)
+    via_gemm = ops.gemm(x.reshape(-1, Cin).to(cuda), wk, mode=ops.A_CONV3X3, conv=(N, H, W, 1), bias=b.to(cuda),
+                        act=ops.ACT_SILU if silu else ops.ACT_NONE)
+    assert rel_l2(out.float(), via_gemm.float()) < 4e-3
