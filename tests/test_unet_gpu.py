@@ -506,3 +506,40 @@ def test_smooth_pipeline_vs_oracle(cuda):
     print("smooth pipeline rel-L2 after", 25 - start, "steps:", err)
     assert err < 2e-2
     assert pipe.get_chunks(T, nf, np.random.RandomState(3)) == chunks[0]
+
+
+@pytest.mark.parametrize("kv", [1, 3])
+def test_lora_on_all_attention_projections_inference(cuda, kv):
+    """run_models/run_inference_flow_lora.py:326-331: LoraConfig(r, target_modules=["to_k","to_q","to_v","to_out.0"]) -
+    adapters on every attention projection (spatial + temporal, attn1 + attn2).  The engine folds them: fused-qkv second K
+    segment, out-projection second segment, merged into the KV-length-1 cross-attention vectors / the general KV>1 path."""
+    import oracle as O
+    from oracle.lora import ALL_ATTN_PROJ
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG, time_context_order="b_major" if kv > 1 else "hw_major_0272")
+    torch.manual_seed(0)
+    o = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    O.add_lora(o, 8, target=ALL_ATTN_PROJ)
+    p = UNetSpatioTemporalConditionControlNetModel(**cfg)
+    hit = p.add_adapter(dict(r=8, lora_alpha=8, init_lora_weights="gaussian", target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    assert len(hit) == 6 * 2 * 2 * 4
+    _randomise_zero_inits(o)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if "lora_B" in n:
+                prm.copy_((torch.randn(prm.shape, generator=torch.Generator().manual_seed(len(n))) * 0.05)
+                          .to(torch.bfloat16).float())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    x, ctx, ids = _inputs(cfg, 2, 8, 32, 32, 32)
+    if kv > 1:
+        ctx = torch.randn(2, kv, 32, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+        plain = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    got = p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(got, ref)
+    print("all-projection LoRA, KV", kv, "rel_l2", err)
+    assert err < 1e-2
+    p.merge_lora()
+    assert rel_l2(p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0], ref) < 1e-2
