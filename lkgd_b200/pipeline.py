@@ -162,6 +162,16 @@ class StableVideoDiffusionPipeline:
                 kw = dict(down_block_additional_residuals=down, mid_block_additional_residual=mid)
         rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
                                    added_time_ids=st["added_time_ids"], **kw)
+        if st.get("direct_fusion"):
+            # trans pipelines (pipeline_stable_video_diffusion_trans_controlnet.py:637-667): the batch is [forward samples |
+            # their time-reversed partners]; the guided prediction takes the bidirectional x0 blend instead of the plain step
+            if sigmas_dev is not None:
+                raise ValueError("direct_fusion is not captured in the CUDA graph")
+            i = sched._step_index
+            _, v = ops.cfg_euler_step(rows, st["guidance"] if st["do_cfg"] else None, latents,
+                                      float(sched._sigmas_host[i]), float(sched._sigmas_host[i + 1]), cfg=st["do_cfg"],
+                                      want_v=True)
+            return sched.step_direct_fusion(v, sched.timesteps[i], latents), (v if want_v else None)
         return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
                                    want_v=want_v, sigmas_dev=sigmas_dev, in_place=in_place)
 
@@ -252,7 +262,7 @@ class StableVideoDiffusionPipeline:
                  domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
                  cfg_pair=None, output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
                  return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False,
-                 use_cuda_graph: bool = False, fuse_controlnet: bool = True):
+                 use_cuda_graph: bool = False, fuse_controlnet: bool = True, direct_fusion: bool = False):
         if output_type != "latent":
             raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
                              "VAE of your choice (SURVEY.md section 8f, N1)")
@@ -260,6 +270,9 @@ class StableVideoDiffusionPipeline:
                           max_guidance_scale, fps, motion_bucket_id, noise_aug_strength, num_videos_per_prompt,
                           controlnet_condition, controlnet_cond_scale, domain_features, flow_features, cfg_pair)
         st["fuse_controlnet"] = fuse_controlnet
+        st["direct_fusion"] = direct_fusion
+        if direct_fusion and (use_cuda_graph or cfg_pair is not None or st["S"] % 2):
+            raise ValueError("direct_fusion needs an even number of samples (forward | reversed) and the eager loop")
         device = self.unet.device
         latents = self.prepare_latents(st["S"], st["F"], self.unet.config.in_channels, st["h"], st["w"],
                                        torch.float32, device, generator, latents).to(torch.float32).contiguous()

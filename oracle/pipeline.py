@@ -40,7 +40,8 @@ def add_time_ids_training(fps: float, motion_bucket_id: float, noise_aug_strengt
 def denoise_loop(unet, scheduler, latents, image_latents, image_embeddings, added_time_ids,
                  num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
                  controlnet=None, controlnet_cond=None, controlnet_cond_scale: float = 1.0,
-                 unet_extra_args: tuple = (), return_trajectory: bool = False, max_steps: Optional[int] = None):
+                 unet_extra_args: tuple = (), return_trajectory: bool = False, max_steps: Optional[int] = None,
+                 direct_fusion: bool = False):
     """``latents`` [S,F,4,h,w] (already scaled by init_noise_sigma); ``image_latents`` / ``image_embeddings`` /
     ``added_time_ids`` already CFG-duplicated ([2S,...], uncond first).  ``unet_extra_args`` are the LKGD
     positional (domain_features, flow_features)."""
@@ -64,7 +65,10 @@ def denoise_loop(unet, scheduler, latents, image_latents, image_embeddings, adde
                           return_dict=False, **kw)[0]
         if do_cfg:
             noise_pred = cfg_combine(noise_pred, g)
-        latents = scheduler.step(noise_pred, t, latents).prev_sample
+        if direct_fusion:      # pipeline_stable_video_diffusion_trans_controlnet.py:637-667 (forward half | time-reversed half)
+            latents = scheduler.step_direct_fusion(noise_pred, t, latents)
+        else:
+            latents = scheduler.step(noise_pred, t, latents).prev_sample
         if return_trajectory:
             preds.append(noise_pred.clone())
             traj.append(latents.clone())

@@ -543,3 +543,60 @@ def test_lora_on_all_attention_projections_inference(cuda, kv):
     assert err < 1e-2
     p.merge_lora()
     assert rel_l2(p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0], ref) < 1e-2
+
+
+@pytest.mark.parametrize("direct_fusion", [False, True])
+def test_trans_pipeline_loop_joint_attention(cuda, direct_fusion):
+    """The reference's `trans` pipelines (pipeline_stable_video_diffusion_trans.py:541-575,
+    pipeline_..._trans_controlnet.py:637-667) are the CFG loop on a batch of TWO coupled samples with the joint-attention
+    patch switched on (utils/util.py:531-608): CFG batch [uncond x, uncond y, cond x, cond y], mask [0,1,0,1];
+    `direct_fusion` replaces the Euler step by the bidirectional x0 blend.  4 steps against the oracle."""
+    import oracle as O
+    from oracle.scheduler import SVD_SCHEDULER_CONFIG
+    from lkgd_b200 import patch
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    torch.manual_seed(0)
+    o = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    p = UNetSpatioTemporalConditionControlNetModel(**cfg)
+    for m in o.modules():
+        if isinstance(m, (O.BasicTransformerBlock, O.TemporalBasicTransformerBlock)):
+            m.initialize_joint_layers("conv")
+    patch.apply_patch(p, flip=False, with_spatial_block=True, with_temporal_block=True)
+    patch.initialize_joint_layers(p, post="conv")
+    _randomise_zero_inits(o)
+    g = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if "conv1n" in n:
+                prm.copy_((torch.randn(prm.shape, generator=g) * prm.shape[1] ** -0.5).to(torch.bfloat16).float())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    mask = [0, 1, 0, 1]
+    for m in o.modules():
+        if hasattr(m, "attn1n"):
+            m.enable_joint_attention, m.joint_attn_mask, m.num_frames = True, torch.tensor(mask, dtype=torch.bool), 8
+    patch.set_joint_attention_mask(p, mask)
+    S, F, h, w = 2, 8, 16, 16
+    noise = torch.randn(S, F, 4, h, w, generator=g)
+    cond = torch.randn(S, 1, 4, h, w, generator=g).repeat(1, F, 1, 1, 1)
+    img_lat = torch.cat([torch.zeros_like(cond), cond])
+    emb = torch.randn(S, 1, 32, generator=g)
+    img_emb = torch.cat([torch.zeros_like(emb), emb])
+    osched = O.EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG)
+    osched.set_timesteps(25)
+    ids = O.add_time_ids_inference(6, 127, 0.02, S)
+    ref = O.denoise_loop(o, osched, noise * osched.init_noise_sigma, img_lat, img_emb, ids, 25, 1.0, 3.0, max_steps=4,
+                         direct_fusion=direct_fusion)
+    pipe = StableVideoDiffusionPipeline(p, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))
+    got = pipe(img_emb, img_lat, num_frames=F, num_inference_steps=25, latents=noise, max_steps=4, return_dict=False,
+               direct_fusion=direct_fusion)
+    err = rel_l2(got, ref)
+    print("trans loop, direct_fusion =", direct_fusion, "rel-L2", err)
+    assert err < 2e-2
+    patch.set_joint_attention(p, False)
+    off = pipe(img_emb, img_lat, num_frames=F, num_inference_steps=25, latents=noise, max_steps=4, return_dict=False,
+               direct_fusion=direct_fusion)
+    assert rel_l2(off, ref) > 2 * err          # the coupling between the two samples is really there
