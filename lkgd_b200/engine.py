@@ -37,14 +37,23 @@ def _b16(t: torch.Tensor) -> torch.Tensor:
 
 
 def _lin_parts(mod):
-    """(weight fp32 [N,K], bias fp32 | None, lora (A [r,K], B*scaling [N,r]) | None) of a Linear / LoraLinear."""
+    """(weight fp32 [N,K], bias fp32 | None, lora) of a Linear / LoraLinear.  ``lora`` is None or
+    (A [r,K], B*scaling [N,r], masks): all ACTIVE adapters stacked along r (their updates add up, reference
+    models/lora_layer.py:425-442); ``masks`` = None, or a list of (row_lo, row_hi, bool mask over the batch) for the
+    layers on which the masked forward (patch/patch.py:57-92) restricts at least one adapter to some samples (mask None =
+    that adapter acts on every sample)."""
     if isinstance(mod, M.LoraLinear):
         base = mod.base_layer
         lora = None
-        if not mod.merged:
-            a = mod.lora_A[mod.adapter_name].weight
-            b = mod.lora_B[mod.adapter_name].weight
-            lora = (_f32(a), _f32(b) * mod.scaling)
+        ads = [] if mod.merged else mod.adapters()
+        if ads:
+            a = torch.cat([_f32(x[1]) for x in ads], 0)
+            b = torch.cat([_f32(x[2]) * x[3] for x in ads], 1)
+            masks, off = [], 0
+            for _, aw, _, _, m in ads:            # once one adapter is masked every adapter gets its own column range
+                masks.append((off, off + aw.shape[0], m))
+                off += aw.shape[0]
+            lora = (a, b, masks if any(m[2] is not None for m in masks) else None)
         return _f32(base.weight), (None if base.bias is None else _f32(base.bias)), lora
     return _f32(mod.weight), (None if mod.bias is None else _f32(mod.bias)), None
 
@@ -52,6 +61,10 @@ def _lin_parts(mod):
 def _merged_weight(mod) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     w, b, lora = _lin_parts(mod)
     if lora is not None:
+        if lora[2] is not None:
+            raise NotImplementedError("a per-sample masked LoRA adapter (patch.hack_lora_forward) sits on a projection "
+                                      "whose adapters are merged at pack time (cross-attention attn2, GEGLU proj): "
+                                      "masked adapters are built for attn1 / attn1n / proj_in / proj_out / ff.net.2")
         w = w + lora[1] @ lora[0]          # W + s * B A   (reference models/lora_layer.py:406)
     return w, b
 
@@ -85,6 +98,7 @@ class Dense:
     b: Optional[torch.Tensor]
     lora_a: Optional[torch.Tensor] = None    # [r_pad, K] bf16   (t = x A^T)
     lora_b: Optional[torch.Tensor] = None    # [N, r_pad] bf16   (scaled B)
+    lora_masks: Optional[list] = None        # [(row_lo, row_hi of lora_a, bool mask over the batch)]: masked adapters
 
 
 class PackedResBlock:
@@ -115,39 +129,49 @@ def _dense(mod, fold_lora: bool) -> Dense:
     w, b, lora = _lin_parts(mod)
     if lora is None:
         return Dense(w.to(bf16).contiguous(), b)
-    if not fold_lora:
-        return Dense((w + lora[1] @ lora[0]).to(bf16).contiguous(), b)
-    a, bs = lora
+    a, bs, masks = lora
+    if not fold_lora and masks is None:
+        return Dense((w + bs @ a).to(bf16).contiguous(), b)
     r = a.shape[0]
     r_pad = (r + 7) // 8 * 8
     ap = torch.zeros(r_pad, a.shape[1], device=a.device)
     ap[:r] = a
     bp = torch.zeros(bs.shape[0], r_pad, device=a.device)
     bp[:, :r] = bs
-    return Dense(w.to(bf16).contiguous(), b, ap.to(bf16).contiguous(), bp.to(bf16).contiguous())
+    return Dense(w.to(bf16).contiguous(), b, ap.to(bf16).contiguous(), bp.to(bf16).contiguous(), masks)
 
 
-def _qkv(attn: M.Attention, fold_lora: bool) -> Dense:
-    """Fused [3C, C] projection; LoRA on q/k/v becomes one [3r, C] down-projection and a block-diagonal
-    [3C, 3r] up-projection consumed as the GEMM's second K segment."""
-    parts = [_lin_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
+def _fused(mods, fold_lora: bool, mask_map=None) -> Dense:
+    """Several projections of ONE input fused into one [sum N, K] GEMM (q|k|v, or k|v of the joint branch); LoRA adapters
+    become one stacked [n_proj * r, K] down-projection and a block-diagonal [sum N, n_proj * r] up-projection consumed as the
+    GEMM's second K segment.  ``mask_map(i, mask)``: optional re-indexing of projection i's per-sample adapter masks."""
+    parts = [_lin_parts(m) for m in mods]
     has_lora = any(p[2] is not None for p in parts)
-    if not has_lora or not fold_lora:
+    masked = any(p[2] is not None and p[2][2] is not None for p in parts)
+    if not has_lora or (not fold_lora and not masked):
         ws = [(p[0] + p[2][1] @ p[2][0]) if p[2] is not None else p[0] for p in parts]
         return Dense(torch.cat(ws, 0).to(bf16).contiguous(), None)
+    np_ = len(parts)
     n, k = parts[0][0].shape
     r = max(p[2][0].shape[0] for p in parts if p[2] is not None)
     r_pad = (r + 7) // 8 * 8
-    a_cat = torch.zeros(3 * r_pad, k, device=parts[0][0].device)
-    b_blk = torch.zeros(3 * n, 3 * r_pad, device=parts[0][0].device)
+    a_cat = torch.zeros(np_ * r_pad, k, device=parts[0][0].device)
+    b_blk = torch.zeros(np_ * n, np_ * r_pad, device=parts[0][0].device)
+    masks = []
     for i, p in enumerate(parts):
         if p[2] is None:
             continue
-        a, bs = p[2]
+        a, bs, ms = p[2]
         a_cat[i * r_pad:i * r_pad + a.shape[0]] = a
         b_blk[i * n:(i + 1) * n, i * r_pad:i * r_pad + a.shape[0]] = bs
+        for lo, hi, m in (ms or []):
+            masks.append((i * r_pad + lo, i * r_pad + hi, mask_map(i, m) if mask_map is not None else m))
     w = torch.cat([p[0] for p in parts], 0)
-    return Dense(w.to(bf16).contiguous(), None, a_cat.to(bf16).contiguous(), b_blk.to(bf16).contiguous())
+    return Dense(w.to(bf16).contiguous(), None, a_cat.to(bf16).contiguous(), b_blk.to(bf16).contiguous(), masks or None)
+
+
+def _qkv(attn: M.Attention, fold_lora: bool) -> Dense:
+    return _fused((attn.to_q, attn.to_k, attn.to_v), fold_lora)
 
 
 def _geglu(ff: M.FeedForward, fold_lora: bool):
@@ -201,31 +225,49 @@ def _partners(mask: torch.Tensor, batch: int) -> List[int]:
 
 
 class PackedJoint:
-    """Joint-attention branch of a patched block (patch/patch.py ToMeBlock): ``attn1n`` projections + the post layer and
-    ``joint_scale`` folded into its output projection: post(to_out(a)) * s = a (s P Wo)^T + s P bo."""
+    """Joint-attention branch of a patched block (patch/patch.py ToMeBlock): ``attn1n`` projections (their LoRA adapters
+    folded like everywhere else, per-sample masks included) + the post layer and ``joint_scale`` folded into its output
+    projection: post(to_out(a)) * s = a (s P Wo)^T + (a A^T) (s P B)^T + s P bo."""
 
-    def __init__(self, blk, spatial: bool):
+    def __init__(self, blk, spatial: bool, fold_lora: bool = True):
         if not hasattr(blk, "attn1n") or blk.post is None:
             raise ValueError("joint attention is enabled on a block without joint layers: call "
                              "patch.initialize_joint_layers(unet) after patch.apply_patch(unet)")
         a = blk.attn1n
-        wq, _ = _merged_weight(a.to_q)
-        wk, _ = _merged_weight(a.to_k)
-        wv, _ = _merged_weight(a.to_v)
-        wo, bo = _merged_weight(a.to_out[0])
-        if blk.post == "conv":
-            pw = blk.conv1n.weight.detach().double()
-            w_post, b_post = pw @ wo.double(), pw @ bo.double()
-        else:
-            sc = blk.scale1n.detach().double().reshape(-1)
-            w_post, b_post = sc[:, None] * wo.double(), sc * bo.double()
-        s = float(blk.joint_scale) if spatial else 1.0        # the temporal branch has no joint_scale (patch.py:655)
-        self.wq = wq.to(bf16).contiguous()
-        self.wkv = torch.cat([wk, wv], 0).to(bf16).contiguous()
-        self.post_w = (w_post * s).float().to(bf16).contiguous()
-        self.post_b = (b_post * s).float().contiguous()
         self.mask = blk.joint_attn_mask
         self.flip = bool(blk.flip) and spatial
+        self.q = _dense(a.to_q, fold_lora)
+        # k / v are projected from every sample's OWN rows and read by the partner; the reference projects the swapped
+        # tensor, with the adapter masks of to_k / to_v stored inverted (patch.py:889-892): position i of the swapped
+        # tensor holds sample partner(i), so sample j's rows carry the adapter iff stored_mask[partner(j)]
+        def remap(_, m):
+            if self.mask is None:
+                raise ValueError("masked adapters on attn1n.to_k / to_v need the joint attention mask")
+            batch = max(len(m), len(self.mask))
+            part = _partners(self.mask, batch)
+            mm = m.repeat_interleave(batch // len(m)).tolist()
+            return torch.tensor([mm[part[j]] for j in range(batch)], dtype=torch.bool)
+        self.kv = _fused((a.to_k, a.to_v), fold_lora, mask_map=remap)
+        wo, bo, lora = _lin_parts(a.to_out[0])
+        if blk.post == "conv":
+            P = blk.conv1n.weight.detach().double()
+        else:
+            P = torch.diag(blk.scale1n.detach().double().reshape(-1))
+        s = float(blk.joint_scale) if spatial else 1.0        # the temporal branch has no joint_scale (patch.py:655)
+        P = P * s
+        w_post = (P @ wo.double()).float()
+        b_post = (P @ bo.double()).float().contiguous() if bo is not None else None
+        if lora is None:
+            self.out = Dense(w_post.to(bf16).contiguous(), b_post)
+        else:
+            la, lb, masks = lora
+            r = la.shape[0]
+            r_pad = (r + 7) // 8 * 8
+            ap = torch.zeros(r_pad, la.shape[1], device=la.device)
+            ap[:r] = la
+            bp = torch.zeros(lb.shape[0], r_pad, device=la.device)
+            bp[:, :r] = (P @ lb.double()).float()
+            self.out = Dense(w_post.to(bf16).contiguous(), b_post, ap.to(bf16).contiguous(), bp.to(bf16).contiguous(), masks)
 
 
 class PackedTransformer:
@@ -245,8 +287,8 @@ class PackedTransformer:
         self.t_qkv, self.t_out = _qkv(tb.attn1, fold_lora), _dense(tb.attn1.to_out[0], fold_lora)
         self.t_cross = PackedCross(tb.attn2)
         self.t_ff1, self.t_ff2 = _geglu(tb.ff, fold_lora)
-        self.s_joint = PackedJoint(sb, True) if sb.joint_active() else None
-        self.t_joint = PackedJoint(tb, False) if tb.joint_active() else None
+        self.s_joint = PackedJoint(sb, True, fold_lora) if sb.joint_active() else None
+        self.t_joint = PackedJoint(tb, False, fold_lora) if tb.joint_active() else None
         self.alpha = float(torch.sigmoid(t.time_mixer.mix_factor.detach().float()).item())
         pe = t.time_pos_embed
         self.pe = (_f32(pe.linear_1.weight), _f32(pe.linear_1.bias), _f32(pe.linear_2.weight), _f32(pe.linear_2.bias))
@@ -291,11 +333,42 @@ class Geom:
         return Geom(self.B, self.F, self.H * 2, self.W * 2)
 
 
-def dense(x: torch.Tensor, d: Dense, **kw) -> torch.Tensor:
-    """x W^T (+ LoRA second segment) through lkgd_gemm."""
+def _mask_ranges(mask: torch.Tensor, batch: int, rows: int):
+    """Row ranges [lo, hi) of the samples an adapter mask selects (mask repeat-interleaved over the batch, as the masked
+    forward does with the Linear's leading dimension, patch/patch.py:75-76); adjacent samples are merged."""
+    if batch % len(mask):
+        raise ValueError(f"batch {batch} is not a multiple of the LoRA mask length {len(mask)}")
+    m = mask.repeat_interleave(batch // len(mask)).tolist()
+    out = []
+    for i, v in enumerate(m):
+        if v:
+            if out and out[-1][1] == i * rows:
+                out[-1][1] = (i + 1) * rows
+            else:
+                out.append([i * rows, (i + 1) * rows])
+    return out
+
+
+def lora_down(x: torch.Tensor, d: Dense, batch: Optional[int]) -> torch.Tensor:
+    """t = x A^T for the stacked adapters.  Adapters masked to some samples (patch.hack_lora_forward) contribute zero rows
+    elsewhere: their columns of t are computed sample range by sample range into a zeroed buffer."""
+    if not d.lora_masks:
+        return ops.gemm(x, d.lora_a)
+    if batch is None:
+        raise ValueError("masked LoRA adapters need the batch size of the activation")
+    M_ = x.shape[0]
+    rows = M_ // batch
+    t = torch.zeros((M_, d.lora_a.shape[0]), device=x.device, dtype=bf16)
+    for lo, hi, mask in d.lora_masks:
+        for r0, r1 in ([[0, M_]] if mask is None else _mask_ranges(mask, batch, rows)):
+            ops.gemm(x[r0:r1], d.lora_a[lo:hi], out=t[r0:r1, lo:hi])
+    return t
+
+
+def dense(x: torch.Tensor, d: Dense, batch: Optional[int] = None, **kw) -> torch.Tensor:
+    """x W^T (+ LoRA second segment) through lkgd_gemm.  ``batch``: samples in x (needed only for masked adapters)."""
     if d.lora_a is not None:
-        t = ops.gemm(x, d.lora_a)
-        return ops.gemm(x, d.w, bias=d.b, A1=t, Bw1=d.lora_b, **kw)
+        return ops.gemm(x, d.w, bias=d.b, A1=lora_down(x, d, batch), Bw1=d.lora_b, **kw)
     return ops.gemm(x, d.w, bias=d.b, **kw)
 
 
@@ -392,20 +465,20 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     C = p.c
     kv1 = cond.ctx.shape[1] == 1
     h = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False)
-    h = dense(h, p.proj_in, out_f32=True)                                             # fp32 hidden stream
+    h = dense(h, p.proj_in, batch=g.B, out_f32=True)                                  # fp32 hidden stream
     # ---- spatial block (patch/patch.py:390-580)
     n = ops.layernorm(h, p.s_ln1.g, p.s_ln1.b, p.s_ln1.eps)
-    qkv = dense(n, p.s_qkv)
+    qkv = dense(n, p.s_qkv, batch=g.B)
     a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, Nq=g.HW,
                       Nk=g.HW)
-    h = dense(a, p.s_out, res1=h, out_f32=True)
+    h = dense(a, p.s_out, batch=g.B, res1=h, out_f32=True)
     if p.s_joint is not None:
         # joint attention (patch/patch.py:434-492): queries of sample i against the keys / values of its PARTNER sample,
         # addressed in place (row offsets into the fused projection; with `flip` frame f meets the partner's frame
         # F-1-f); post layer and joint_scale are folded into the output projection, which accumulates onto h in place
         J = p.s_joint
         rows = g.F * g.HW
-        qn, kvn = ops.gemm(n, J.wq), ops.gemm(n, J.wkv)
+        qn, kvn = dense(n, J.q, batch=g.B), dense(n, J.kv, batch=g.B)
         an = torch.empty((g.M, C), device=n.device, dtype=bf16)
         for i, pi in enumerate(_partners(J.mask, g.B)):
             if not J.flip:
@@ -417,7 +490,7 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
                     q0, k0 = i * rows + f * g.HW, pi * rows + (g.F - 1 - f) * g.HW
                     ops.attention(qn[q0:q0 + g.HW], kvn[k0:k0 + g.HW, :C], kvn[k0:k0 + g.HW, C:], n_img=1,
                                   heads=p.heads, d=p.d, Nq=g.HW, Nk=g.HW, out=an[q0:q0 + g.HW])
-        h = ops.gemm(an, J.post_w, bias=J.post_b, res1=h, out=h, out_f32=True)
+        h = dense(an, J.out, batch=g.B, res1=h, out=h, out_f32=True)
     if kv1:
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross),
                           rv=g.rv(RV_BATCH), sum_out=h)
@@ -426,17 +499,17 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         h = _cross_general(p.s_cross, n, cond.ctx, g, h)
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps)
     ff = dense(n, p.s_ff1, act=ACT_GEGLU)
-    xs = dense(ff, p.s_ff2, res1=h, out_f32=True)                                     # x_spatial
+    xs = dense(ff, p.s_ff2, batch=g.B, res1=h, out_f32=True)                                     # x_spatial
     # ---- temporal block (patch/patch.py:582-686) on the same rows, frame stride HW*C
     t0 = torch.empty_like(xs)
     n = ops.layernorm(xs, p.t_lnin.g, p.t_lnin.b, p.t_lnin.eps, addvec=p.pos_emb(g.F), rv=g.rv(RV_FRAMEPOS),
                       sum_out=t0)                                                      # t0 = x_spatial + emb[f]
     ff = dense(n, p.t_ffin1, act=ACT_GEGLU)
-    t = dense(ff, p.t_ffin2, res1=t0, out_f32=True)
+    t = dense(ff, p.t_ffin2, batch=g.B, res1=t0, out_f32=True)
     n = ops.layernorm(t, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
-    qkv = dense(n, p.t_qkv)
+    qkv = dense(n, p.t_qkv, batch=g.B)
     a = ops.attention_temporal(qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
-    t = dense(a, p.t_out, res1=t, out_f32=True)
+    t = dense(a, p.t_out, batch=g.B, res1=t, out_f32=True)
     if p.t_joint is not None:
         # temporal joint attention (patch/patch.py:617-658): pixel (b, p)'s frames attend to the partner sample's frames
         # at the same pixel.  The fused [q | k | v] buffer of the temporal kernel is written directly in partner order:
@@ -444,11 +517,16 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         J = p.t_joint
         rows = g.F * g.HW
         buf = torch.empty((g.M, 3 * C), device=n.device, dtype=bf16)
-        ops.gemm(n, J.wq, out=buf[:, :C])
-        for i, pi in enumerate(_partners(J.mask, g.B)):
-            ops.gemm(n[pi * rows:(pi + 1) * rows], J.wkv, out=buf[i * rows:(i + 1) * rows, C:])
+        dense(n, J.q, batch=g.B, out=buf[:, :C])
+        if J.kv.lora_a is None:
+            for i, pi in enumerate(_partners(J.mask, g.B)):
+                ops.gemm(n[pi * rows:(pi + 1) * rows], J.kv.w, out=buf[i * rows:(i + 1) * rows, C:])
+        else:       # adapters on to_k / to_v: project once in natural order, then place each sample's rows at its partner
+            kvn = dense(n, J.kv, batch=g.B)
+            for i, pi in enumerate(_partners(J.mask, g.B)):
+                buf[i * rows:(i + 1) * rows, C:].copy_(kvn[pi * rows:(pi + 1) * rows])
         an = ops.attention_temporal(buf, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
-        t = ops.gemm(an, J.post_w, bias=J.post_b, res1=t, out=t, out_f32=True)
+        t = dense(an, J.out, batch=g.B, res1=t, out=t, out_f32=True)
     if kv1:
         # under a CFG pair split ctx_t holds every half's context: index it exactly as the unsplit batch would
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
@@ -461,9 +539,10 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps)
     ff = dense(n, p.t_ff1, act=ACT_GEGLU)
     # AlphaBlender: alpha*x_spatial + (1-alpha)*(ff_out + t); bf16 because proj_out reads it as its GEMM operand
-    mix = dense(ff, p.t_ff2, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
+    mix = dense(ff, p.t_ff2, batch=g.B, s0=1.0 - p.alpha, res1=t, s1=1.0 - p.alpha, res2=xs, s2=p.alpha)
     # the next resblock's GroupNorm consumes this tensor: fused statistics where a 128-row tile stays inside a frame
-    return dense(mix, p.proj_out, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0, want_bf16=want_bf16)
+    return dense(mix, p.proj_out, batch=g.B, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0,
+                 want_bf16=want_bf16)
 
 
 class PackedUNet:

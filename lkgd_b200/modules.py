@@ -327,6 +327,50 @@ class LoraLinear(Container):
                 raise ValueError(f"Unknown initialization {init_lora_weights=}")
             if init_lora_weights is not False:
                 nn.init.zeros_(b)
+        self.scalings = {adapter_name: self.scaling}
+        self.ranks = {adapter_name: r}
+        self.active_adapters = [adapter_name]      # peft `set_adapters`: every listed adapter adds up
+        self.lora_mask = {}                        # adapter -> bool mask over the batch (patch.set_patch_lora_mask)
+        self.masked_forward = False                # patch.hack_lora_forward: per-sample masked adapters (patch.py:57-92)
+
+    def update_layer(self, adapter_name: str, r: int, lora_alpha: float, init_lora_weights="gaussian"):
+        """A further adapter on the same layer (reference models/lora_layer.py:85-130)."""
+        if adapter_name in self.lora_A:
+            raise ValueError(f"adapter {adapter_name!r} already exists on this layer")
+        if r <= 0:
+            raise ValueError(f"`r` should be a positive integer value but the value passed is {r}")
+        base = self.base_layer
+        dev, dt = base.weight.device, base.weight.dtype
+        self.lora_A[adapter_name] = Linear(base.in_features, r, bias=False, device=dev, dtype=dt)
+        self.lora_B[adapter_name] = Linear(r, base.out_features, bias=False, device=dev, dtype=dt)
+        a, b = self.lora_A[adapter_name].weight, self.lora_B[adapter_name].weight
+        if a.device.type != "meta":
+            if init_lora_weights is True:
+                nn.init.kaiming_uniform_(a, a=math.sqrt(5))
+            elif isinstance(init_lora_weights, str) and init_lora_weights.lower() == "gaussian":
+                nn.init.normal_(a, std=1 / r)
+            if init_lora_weights is not False:
+                nn.init.zeros_(b)
+        self.scalings[adapter_name] = lora_alpha / r
+        self.ranks[adapter_name] = r
+        self.active_adapters.append(adapter_name)
+
+    def adapters(self):
+        """[(name, A weight, B weight, scaling, mask | None)] of the active adapters; the mask is None unless the masked
+        forward is switched on and the adapter's mask leaves some sample out."""
+        out = []
+        for name in self.active_adapters:
+            if name not in self.lora_A:
+                continue
+            mask = None
+            if self.masked_forward:
+                if name not in self.lora_mask:
+                    raise KeyError(f"masked LoRA forward without a mask for adapter {name!r} (patch.set_patch_lora_mask)")
+                mask = self.lora_mask[name]
+                if bool(mask.all()):
+                    mask = None
+            out.append((name, self.lora_A[name].weight, self.lora_B[name].weight, self.scalings[name], mask))
+        return out
 
     @property
     def in_features(self):

@@ -12,9 +12,8 @@ the sum lands in the residual stream through one GEMM epilogue.
 Function names, arguments and defaults follow the reference (``apply_patch`` :719-806, ``remove_patch`` :820-838,
 ``initialize_joint_layers`` :966-977, ``set_joint_attention`` :938-950, ``set_joint_scale`` :952-964,
 ``set_joint_attention_mask`` :985-1001, ``set_patch_lora_mask`` :872-896).  Not built: ``add_norm=True``,
-``post="conv_fuse"``, ``single_dir``, and the per-sample masked multi-adapter LoRA forward (``hack_lora_forward``
-:911-922 with several adapters on one module) - ``hack_lora_forward`` accepts models whose adapters are unmasked or
-masked all-true, and raises otherwise."""
+``post="conv_fuse"``, ``single_dir``; the per-sample masked LoRA forward (``hack_lora_forward`` :911-922) is built for the
+GEMM-path projections and refuses partial masks on attn2 / the GEGLU projection (merged at pack time)."""
 from __future__ import annotations
 
 import torch
@@ -126,14 +125,15 @@ def set_patch_lora_mask(model, lora_name, lora_mask):
 
 
 def hack_lora_forward(model):
-    """Reference :911-922 switches every LoRA Linear to the per-sample masked forward (:57-92).  The engine folds an
-    adapter into its GEMM for the whole batch, which equals the masked forward only when the adapter's mask is all-true
-    (the reference's ``single_lora`` set-up, utils/util.py:601-602): anything else is refused, loudly."""
+    """Reference :911-922 switches every LoRA Linear to the per-sample masked forward (:57-92): an adapter acts only on the
+    samples its ``lora_mask`` selects.  Here the switch is a flag on the LoRA modules; the engine computes a masked
+    adapter's down-projection sample range by sample range (``engine.lora_down``).  Masked adapters are built for the
+    GEMM-path projections (attn1 / attn1n q, k, v, out; proj_in / proj_out; ff.net.2); on attn2 and the GEGLU projection,
+    whose adapters are merged at pack time, a partial mask raises when the model is packed."""
     for net in _models(model):
         for name, m in net.named_modules():
             if isinstance(m, M.LoraLinear):
-                mask = getattr(m, "lora_mask", {}).get(m.adapter_name)
-                if mask is not None and not bool(mask.all()):
-                    raise NotImplementedError(f"{name}: adapter {m.adapter_name!r} is masked to a subset of the batch; the "
-                                              "per-sample masked LoRA forward (patch.py:57-92) is not built")
+                m.masked_forward = True
+        if hasattr(net, "invalidate"):
+            net.invalidate()
     return model

@@ -347,6 +347,8 @@ class LoraTrainer:
         for p in self.layers:
             attn = p.src.temporal_transformer_blocks[0].attn1
             trio = (attn.to_q, attn.to_k, attn.to_v)
+            if any(isinstance(m, M.LoraLinear) and (len(m.lora_A) != 1 or m.masked_forward) for m in trio):
+                raise NotImplementedError("training supports ONE unmasked adapter per layer")
             if not all(isinstance(m, M.LoraLinear) and not m.merged for m in trio):
                 raise ValueError("every temporal attn1 q/k/v projection must carry an unmerged LoRA adapter "
                                  "(unet.add_lora(r) with the default target)")

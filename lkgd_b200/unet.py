@@ -198,15 +198,33 @@ class _Base(nn.Module):
 
         names = [n for n, m in self.named_modules() if isinstance(m, M.Linear) and ".lora_" not in n
                  and not n.endswith("base_layer") and wanted(n)]
-        taken = [n for n, m in self.named_modules() if isinstance(m, M.LoraLinear) and wanted(n)]
+        taken = [(n, m) for n, m in self.named_modules() if isinstance(m, M.LoraLinear) and wanted(n)]
+        if any(adapter_name in m.lora_A for _, m in taken):
+            raise ValueError(f"adapter {adapter_name!r} already exists on {taken[0][0]}")
+        alpha0 = get("lora_alpha", r)
+        for _, m in taken:                 # a further adapter on layers that already carry one (peft update_layer)
+            m.update_layer(adapter_name, r, r if alpha0 is None else alpha0, get("init_lora_weights", True))
         if taken:
-            raise ValueError(f"{len(taken)} target modules already carry an adapter (e.g. {taken[0]}): one adapter per "
-                             "module is supported")
+            self.invalidate()
+        if not names and taken:
+            return [n for n, _ in taken]
         if not names:
             raise ValueError(f"Target modules {targets} not found in the base model. Please check the target modules "
                              "and try again.")
         alpha = get("lora_alpha", r)
-        return self._wrap_lora(names, r, r if alpha is None else alpha, get("init_lora_weights", True), adapter_name)
+        return [n for n, _ in taken] + self._wrap_lora(names, r, r if alpha is None else alpha,
+                                                      get("init_lora_weights", True), adapter_name)
+
+    def set_adapters(self, adapter_names, weights=None):
+        """peft ``set_adapters`` (utils/util.py:596-597): the listed adapters are active on every LoRA layer that has
+        them; their updates add up."""
+        if weights is not None:
+            raise NotImplementedError("per-adapter weights are not supported")
+        names = [adapter_names] if isinstance(adapter_names, str) else list(adapter_names)
+        for m in self.modules():
+            if isinstance(m, M.LoraLinear):
+                m.active_adapters = [n for n in names if n in m.lora_A]
+        self.invalidate()
 
     def _wrap_lora(self, names, r, lora_alpha, init_lora_weights, adapter_name):
         for name in names:
@@ -318,8 +336,10 @@ class _Base(nn.Module):
         """W += scaling * B A (reference models/lora_layer.py:300-361)."""
         for m in self.modules():
             if isinstance(m, M.LoraLinear) and not m.merged:
-                a, b = m.lora_A[m.adapter_name].weight, m.lora_B[m.adapter_name].weight
-                m.base_layer.weight.data += ((b.float() @ a.float()) * m.scaling).to(m.base_layer.weight.dtype)
+                for _, a, b, sc, mask in m.adapters():
+                    if mask is not None:
+                        raise ValueError("a per-sample masked adapter cannot be merged into the base weight")
+                    m.base_layer.weight.data += ((b.float() @ a.float()) * sc).to(m.base_layer.weight.dtype)
                 m.merged = True
         self.invalidate()
 

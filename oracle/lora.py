@@ -36,6 +36,25 @@ class LoraLinear(nn.Module):
             raise ValueError(f"Unknown initialization {init_lora_weights=}")
         if init_lora_weights is not False:
             nn.init.zeros_(self.lora_B[adapter_name].weight)
+        self.scalings = {adapter_name: self.scaling}
+        self.active_adapters = [adapter_name]
+        self.lora_mask = {}              # adapter -> bool mask over the batch (patch.set_patch_lora_mask)
+        self.masked_forward = False      # patch.hack_lora_forward replaces forward by the masked one (patch.py:57-92)
+
+    def update_layer(self, adapter_name: str, r: int, lora_alpha: float, init_lora_weights="gaussian"):
+        """A further adapter on the same layer (``lora_layer.py:85-130``); all adapters in ``active_adapters`` add up."""
+        if adapter_name in self.lora_A:
+            raise ValueError(f"adapter {adapter_name!r} exists")
+        self.lora_A[adapter_name] = nn.Linear(self.base_layer.in_features, r, bias=False)
+        self.lora_B[adapter_name] = nn.Linear(r, self.base_layer.out_features, bias=False)
+        if isinstance(init_lora_weights, str) and init_lora_weights.lower() == "gaussian":
+            nn.init.normal_(self.lora_A[adapter_name].weight, std=1 / r)
+        elif init_lora_weights is True:
+            nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=math.sqrt(5))
+        if init_lora_weights is not False:
+            nn.init.zeros_(self.lora_B[adapter_name].weight)
+        self.scalings[adapter_name] = lora_alpha / r
+        self.active_adapters.append(adapter_name)
 
     @property
     def in_features(self):
@@ -67,9 +86,19 @@ class LoraLinear(nn.Module):
         result = self.base_layer(x)
         if self.merged:
             return result
-        a, b = self.lora_A[self.adapter_name], self.lora_B[self.adapter_name]
-        out = result + b(a(x.to(a.weight.dtype))) * self.scaling
-        return out.to(result.dtype)
+        dt = result.dtype
+        for name in self.active_adapters:
+            if name not in self.lora_A:
+                continue
+            a, b, s = self.lora_A[name], self.lora_B[name], self.scalings[name]
+            x = x.to(a.weight.dtype)
+            if self.masked_forward:                                   # patch/patch.py:74-88
+                m = self.lora_mask[name]
+                m = m.repeat_interleave(x.shape[0] // len(m), dim=0)
+                result[m] += b(a(x[m])) * s
+            else:                                                     # models/lora_layer.py:425-442
+                result = result + b(a(x)) * s
+        return result.to(dt)
 
 
 TEMPORAL_QKV = r".*temporal_transformer_blocks\.0\.attn1\.to_[qkv]$"     # train_svd_lora.py:1081-1088
@@ -81,11 +110,16 @@ def add_lora(model: nn.Module, r: int, lora_alpha: float = None, target: str = T
     """Wrap every ``nn.Linear`` whose qualified name matches ``target`` (peft ``add_adapter``)."""
     lora_alpha = r if lora_alpha is None else lora_alpha
     pat = re.compile(target)
-    hits = [n for n, m in model.named_modules() if isinstance(m, nn.Linear) and pat.match(n)]
+    hits = [n for n, m in model.named_modules() if isinstance(m, (nn.Linear, LoraLinear)) and pat.match(n)
+            and ".lora_" not in n and not n.endswith("base_layer")]
     for name in hits:
         parent_name, _, leaf = name.rpartition(".")
         parent = model.get_submodule(parent_name) if parent_name else model
-        wrapped = LoraLinear(getattr(parent, leaf) if not leaf.isdigit() else parent[int(leaf)], r, lora_alpha,
+        old = getattr(parent, leaf) if not leaf.isdigit() else parent[int(leaf)]
+        if isinstance(old, LoraLinear):                       # a further adapter on an already wrapped layer
+            old.update_layer(adapter_name, r, lora_alpha, init_lora_weights)
+            continue
+        wrapped = LoraLinear(old, r, lora_alpha,
                              init_lora_weights, adapter_name)
         if leaf.isdigit():
             parent[int(leaf)] = wrapped

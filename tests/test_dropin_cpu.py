@@ -153,10 +153,25 @@ def test_joint_attention_patch_api_on_cpu():
     assert not any(b.patched or b.enable_joint_attention for b in blocks)
     with pytest.raises(NotImplementedError):
         patch.apply_patch(u, single_dir=True)
-    u.add_lora(4)
-    patch.set_patch_lora_mask(u, "default", [1, 0])
-    with pytest.raises(NotImplementedError, match="masked"):
-        patch.hack_lora_forward(u)
-    patch.set_patch_lora_mask(u, "default", [1, 1])
+    # several adapters per layer + per-sample masks (utils/util.py:566-603: y_lora / xy_lora / yx_lora, set_adapters,
+    # hack_lora_forward, set_patch_lora_mask)
+    cfg_ = dict(r=4, lora_alpha=4, init_lora_weights="gaussian", target_modules=["attn1.to_q", "attn1.to_k"])
+    first = u.add_adapter(cfg_, adapter_name="xy_lora")
+    second = u.add_adapter(dict(cfg_, r=8), adapter_name="yx_lora")
+    assert sorted(first) == sorted(second) and len(first) == 24
+    lin = u.get_submodule(first[0])
+    assert sorted(lin.lora_A) == ["xy_lora", "yx_lora"] and lin.ranks == {"xy_lora": 4, "yx_lora": 8}
+    assert [a[0] for a in lin.adapters()] == ["xy_lora", "yx_lora"] and all(a[4] is None for a in lin.adapters())
+    u.set_adapters(["yx_lora"])
+    assert [a[0] for a in lin.adapters()] == ["yx_lora"]
+    u.set_adapters(["xy_lora", "yx_lora"])
+    patch.set_patch_lora_mask(u, "xy_lora", [1, 0])
+    patch.set_patch_lora_mask(u, "yx_lora", [1, 1])
     patch.hack_lora_forward(u)
-    assert u.lora_mask["default"].tolist() == [True, True]
+    ads = {a[0]: a[4] for a in lin.adapters()}
+    assert ads["xy_lora"].tolist() == [True, False] and ads["yx_lora"] is None          # all-true mask = unmasked
+    assert u.lora_mask["xy_lora"].tolist() == [True, False]
+    with pytest.raises(ValueError, match="already exists"):
+        u.add_adapter(cfg_, adapter_name="xy_lora")
+    with pytest.raises(ValueError, match="masked adapter cannot be merged"):
+        u.merge_lora()

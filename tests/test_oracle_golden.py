@@ -220,6 +220,25 @@ def test_joint_attention_matches_the_references_patch(tag):
         assert rel(b, JG["ja/out_off"]) < 2e-6 and rel(a, b) > 5e-2          # the branch matters
 
 
+def test_masked_multi_adapter_lora_matches_the_references_hacked_forward():
+    """patch/patch.py:57-92 (`lora_forward_hack`) on the reference's own LoRA layer with two adapters and per-sample masks
+    (tests/golden/make_lora_mask_golden.py): the oracle's LoraLinear reproduces the stock and the masked forward exactly."""
+    LG = np.load(os.path.join(HERE, "golden", "lora_mask_golden.npz"))
+    l = O.LoraLinear(torch.nn.Linear(32, 48), 4, 4, "gaussian", "xy_lora")
+    l.update_layer("yx_lora", 8, 4)
+    assert sorted(n for n, _ in l.named_parameters()) == list(LG["loramask/names"])
+    l = fill_seeded_(l, seed=3)
+    x = seeded_tensor("loramask/x", (8, 5, 32))
+    with torch.no_grad():
+        assert rel(l(x), LG["loramask/y_unmasked"]) < 1e-6
+        l.masked_forward = True
+        l.lora_mask = {"xy_lora": torch.tensor([1, 0, 1, 0], dtype=torch.bool),
+                       "yx_lora": torch.tensor([0, 1, 0, 1], dtype=torch.bool)}
+        assert rel(l(x), LG["loramask/y_masked"]) < 1e-6
+        l.lora_mask = {"xy_lora": torch.tensor([1, 1], dtype=torch.bool), "yx_lora": torch.tensor([0, 1], dtype=torch.bool)}
+        assert rel(l(x), LG["loramask/y_masked2"]) < 1e-6
+
+
 def test_flow_stem_unet_matches_reference():
     """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
     by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""

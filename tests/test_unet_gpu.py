@@ -600,3 +600,66 @@ def test_trans_pipeline_loop_joint_attention(cuda, direct_fusion):
     off = pipe(img_emb, img_lat, num_frames=F, num_inference_steps=25, latents=noise, max_steps=4, return_dict=False,
                direct_fusion=direct_fusion)
     assert rel_l2(off, ref) > 2 * err          # the coupling between the two samples is really there
+
+
+JOINT_LORA_TARGET = r".*attn1n?\.(to_q|to_k|to_v|to_out\.0)|.*attentions\.\d+\.proj_(in|out)|.*ff\.net\.2"
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_joint_attention_with_masked_multi_adapter_lora(cuda, flip):
+    """The reference's `trans` set-up in full (utils/util.py:531-608): joint-attention patch + TWO adapters per layer
+    (xy_lora on the x samples, yx_lora on the y samples; `hack_lora_forward` + `set_patch_lora_mask`, inverted masks on
+    attn1n.to_k / to_v whose input is the partner's hidden state) on every GEMM-path projection, against the oracle's
+    restatement of patch/patch.py:57-92 (pinned by lora_mask_golden.npz) and :434-492 / :617-658 (joint_attention_golden)."""
+    import oracle as O
+    from lkgd_b200 import patch
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    torch.manual_seed(0)
+    o = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    p = UNetSpatioTemporalConditionControlNetModel(**cfg)
+    for m in o.modules():
+        if isinstance(m, (O.BasicTransformerBlock, O.TemporalBasicTransformerBlock)):
+            m.initialize_joint_layers("conv")
+    patch.apply_patch(p, flip=flip, with_spatial_block=True, with_temporal_block=True)
+    patch.initialize_joint_layers(p, post="conv")
+    for name, r in (("xy_lora", 8), ("yx_lora", 16)):
+        O.add_lora(o, r, target=JOINT_LORA_TARGET + "$", adapter_name=name)
+        p.add_adapter(dict(r=r, lora_alpha=r, init_lora_weights="gaussian", target_modules=JOINT_LORA_TARGET), name)
+    _randomise_zero_inits(o)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if "conv1n" in n or "lora_B" in n:
+                prm.copy_((torch.randn(prm.shape, generator=g) * 0.6 * prm.shape[1] ** -0.5).to(torch.bfloat16).float())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    jmask, masks = [0, 1, 0, 1], {"xy_lora": [1, 0, 1, 0], "yx_lora": [0, 1, 0, 1]}
+    for name, m in o.named_modules():
+        if hasattr(m, "attn1n"):
+            m.enable_joint_attention, m.joint_attn_mask, m.flip, m.num_frames = True, torch.tensor(jmask, dtype=torch.bool), \
+                flip and isinstance(m, O.BasicTransformerBlock), 8
+        if isinstance(m, O.LoraLinear):          # what patch.set_patch_lora_mask + hack_lora_forward do (patch.py:872-922)
+            m.masked_forward = True
+            for a, mk in masks.items():
+                t = torch.tensor(mk, dtype=torch.bool)
+                m.lora_mask[a] = ~t if ("attn1n.to_k" in name or "attn1n.to_v" in name) else t
+    patch.set_joint_attention_mask(p, jmask)
+    for a, mk in masks.items():
+        patch.set_patch_lora_mask(p, a, mk)
+    p.set_adapters(["xy_lora", "yx_lora"])
+    patch.hack_lora_forward(p)
+    x, ctx, ids = _inputs(cfg, 4, 8, 16, 16, 32)
+    with torch.no_grad():
+        ref = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+    got = p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(got, ref)
+    # the masks matter: the same model with both adapters on every sample differs
+    for m in o.modules():
+        if isinstance(m, O.LoraLinear):
+            m.masked_forward = False
+    with torch.no_grad():
+        unmasked = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+    print("joint attention + masked adapters, flip =", flip, "rel-L2", err, "| masked vs unmasked", rel_l2(unmasked, ref))
+    assert err < 1e-2
+    assert rel_l2(unmasked, ref) > 3 * err
