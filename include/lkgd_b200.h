@@ -65,7 +65,8 @@ LKGD_API uint64_t lkgd_launch_count(void);
  * has N/2 columns: out = (acc_h + b_h) * gelu_erf(acc_g + b_g).
  */
 enum { LKGD_A_LINEAR = 0, LKGD_A_CONV3X3 = 1, LKGD_A_TCONV3 = 2 };
-enum { LKGD_ACT_NONE = 0, LKGD_ACT_SILU = 1, LKGD_ACT_GEGLU = 2 };
+/* GELU: exact (erf) form; QUICK_GELU: x * sigmoid(1.702 x) (the CLIP vision tower's MLP, transformers activations.py) */
+enum { LKGD_ACT_NONE = 0, LKGD_ACT_SILU = 1, LKGD_ACT_GEGLU = 2, LKGD_ACT_GELU = 3, LKGD_ACT_QUICK_GELU = 4 };
 /* row -> rowvec index g(m) with HW = rows per frame, F frames, B = batch:
  *   NONE; FRAME: m/HW; FRAMEPOS: (m/HW)%F; BATCH: m/(HW*F);
  *   TCTX_0272: ((m/(HW*F))*HW + m%HW) % B  (diffusers 0.27.2 temporal-context quirk) */
@@ -162,7 +163,9 @@ LKGD_API int lkgd_layernorm(const void* x, int32_t M, int32_t C, const float* ga
  * Spatial self-attention (and general cross-attention), flash-style on tcgen05: per (image, head)
  *   O = softmax(Q K^T * scale) V,  non-causal, no mask.
  * q/k/v point at the first head's first element; consecutive heads are `d` elements apart inside a token row;
- * token rows are ld{q,k,v} elements apart; images are Nq (resp. Nk) rows apart.  d in {16,32,64}.
+ * token rows are ld{q,k,v} elements apart; images are Nq (resp. Nk) rows apart.  d % 8 == 0, d <= 128 (d <= 64: three CTAs
+ * per SM; 64 < d <= 128: two 64-channel sub-tiles, two CTAs per SM - the reference-default UNet heads (5,10,10,20) give d = 128,
+ * the CLIP ViT-H image encoder d = 80).
  * Replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0 for transformer_blocks.*.attn1/attn2. */
 LKGD_API int lkgd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
                    int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, float scale,
@@ -241,6 +244,12 @@ LKGD_API int lkgd_cond_conv_in(const float* x, int32_t N, int32_t Cc, int32_t H,
                       const float* bias, void* out, void* stream);
 LKGD_API int lkgd_thin_conv3x3(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, const void* weight,
                       const float* bias, int32_t silu, void* out, void* stream);
+
+/* Non-overlapping patch unfold for the ViT patch embedding (CLIPVisionEmbeddings.patch_embedding, a Conv2d with
+ * kernel = stride = P, no bias): x fp32 [N, C, H, W] -> out bf16 [N * (H/P) * (W/P), Kpad] with column (c * P + py) * P + px
+ * (the Conv2d weight's own flattening), zero beyond C*P*P; the embedding itself is then one lkgd_gemm. */
+LKGD_API int lkgd_patchify(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t P, void* out, int32_t Kpad,
+                  void* stream);
 
 /* out[m, :] = srcs[g(m)][m, :] over bf16 [M, C] matrices (C % 8 == 0; srcs = HOST array of n_src <= 8 device pointers, g as
  * for the row vectors above).  Temporal cross-attention with KV length > 1 under the diffusers 0.27.2 context order: row m

@@ -11,7 +11,7 @@ ABI_VERSION = 5
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 RV_NONE, RV_FRAME, RV_FRAMEPOS, RV_BATCH, RV_TCTX_0272 = 0, 1, 2, 3, 4
 SL_NONE, SL_SILU, SL_LEAKY = 0, 1, 3
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "lkgd_axpby": (i32, [vp, i32, f32, vp, i32, f32, i64, vp]),
     "lkgd_cond_conv_in": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "lkgd_thin_conv3x3": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "lkgd_patchify": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "lkgd_select_rows": (i32, [vp, i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
     "lkgd_fusion_euler_step": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),

@@ -574,7 +574,7 @@ using namespace lkgd;
 static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                           void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq,
                           int32_t Nk, float scale, float* lse, void* stream) {
-  if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d % 8 || d <= 0 || (d > AT_D && d != 128)) return LKGD_ESHAPE;
+  if (n_img <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d % 8 || d <= 0 || d > 128) return LKGD_ESHAPE;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return LKGD_EALIGN;
   if (heads > 65535 || n_img > 65535) return LKGD_ESHAPE;
   AttnParams p;
@@ -600,7 +600,7 @@ static int attention_impl(const void* q, int32_t ldq, const void* k, int32_t ldk
   }
   dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d == 128) {
+  if (d > AT_D) {      // 72 .. 128: the two-sub-tile kernel; TMA zero-fills the channels beyond d (CLIP ViT-H: d = 80)
     attn_flash_kernel<4, 128><<<grid, AT_THREADS, AT_SMEM128, st>>>(p);
     return launch_epilogue();
   }

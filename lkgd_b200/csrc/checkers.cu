@@ -75,6 +75,8 @@ __global__ void gemm_check_kernel(const lkgd_gemm_args a) {
   }
   if (a.rowvec) v += a.rowvec[(size_t)chk_rowvec_index(a.rv_mode, m, max(a.rv_HW, 1), max(a.rv_F, 1), max(a.rv_B, 1)) * (a.rv_ld > 0 ? a.rv_ld : n_cols) + n_out];
   if (a.act == LKGD_ACT_SILU) v = silu_f(v);
+  else if (a.act == LKGD_ACT_GELU) v = gelu_erf_f(v);
+  else if (a.act == LKGD_ACT_QUICK_GELU) v = v / (1.0f + expf(-1.702f * v));
   v *= a.s0;
   if (a.res1)
     v += a.s1 * (a.res1_f32 ? reinterpret_cast<const float*>(a.res1)[m * a.ldr1 + n_out]

@@ -264,6 +264,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
     if (p.act == LKGD_ACT_SILU) {
 #pragma unroll
       for (int j = 0; j < CW; ++j) v[j] = silu_fast(v[j]);
+    } else if (p.act == LKGD_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = gelu_erf_fast(v[j]);
+    } else if (p.act == LKGD_ACT_QUICK_GELU) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
     }
     if (p.s0 != 1.0f) {
 #pragma unroll

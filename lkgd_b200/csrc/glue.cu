@@ -411,6 +411,42 @@ extern "C" int lkgd_fusion_euler_step(const float* v, const float* x, const floa
   return launch_epilogue();
 }
 
+// ViT patch unfold: one thread per (patch, 8 output columns)
+__global__ void patchify_kernel(const float* __restrict__ x, int C, int H, int W, int P, __nv_bfloat16* __restrict__ out,
+                                int Kpad, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k8 = Kpad / 8;
+  const int kc = (int)(idx % k8) * 8;
+  const long long patch = idx / k8;
+  const int gw = W / P, gh = H / P;
+  const int px0 = (int)(patch % gw), py0 = (int)((patch / gw) % gh);
+  const long long n = patch / ((long long)gw * gh);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = kc + i;
+    float val = 0.f;
+    if (k < C * P * P) {
+      const int c = k / (P * P), r = k % (P * P), py = r / P, px = r % P;
+      val = __ldg(x + ((n * C + c) * H + (py0 * P + py)) * (long long)W + px0 * P + px);
+    }
+    v[i] = val;
+  }
+  *reinterpret_cast<uint4*>(out + patch * Kpad + kc) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+extern "C" int lkgd_patchify(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t P, void* out, int32_t Kpad,
+                             void* stream) {
+  if (N <= 0 || C <= 0 || P <= 0 || H % P || W % P || Kpad % 8 || Kpad < C * P * P) return LKGD_ESHAPE;
+  if (!aligned16(out)) return LKGD_EALIGN;
+  const long long total = (long long)N * (H / P) * (W / P) * (Kpad / 8);
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, C, H, W, P, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                  Kpad, total);
+  return launch_epilogue();
+}
+
 // out[m, :] = srcs[g(m)][m, :]  (bf16 rows, 16-byte vectors): the per-row choice between attention results computed against
 // different contexts - temporal cross-attention with more than one key under the diffusers 0.27.2 context order, where
 // row m of the temporal batch attends to context g(m) = ((m / (HW F)) HW + m % HW) % B.

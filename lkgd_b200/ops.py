@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU, ACT_NONE, ACT_SILU, RV_BATCH, RV_FRAME, RV_FRAMEPOS,
+from ._lib import (A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, RV_BATCH, RV_FRAME, RV_FRAMEPOS,
                    RV_NONE, RV_TCTX_0272, GemmArgs)
 
 bf16 = torch.bfloat16
@@ -513,6 +513,16 @@ def thin_conv3x3(x: torch.Tensor, weight9: torch.Tensor, bias: torch.Tensor, N: 
         L.PROF.meta = {"bytes": N * H * W * (Cin + Cout) * 2, "flops": 2.0 * N * H * W * 9 * Cin * Cout}
     L.check(L.load().lkgd_thin_conv3x3(x.data_ptr(), N, H, W, Cin, Cout, weight9.data_ptr(), bias.data_ptr(), int(silu),
                                        out.data_ptr(), _stream()), "lkgd_thin_conv3x3")
+    return out
+
+
+def patchify(x: torch.Tensor, P: int, Kpad: int) -> torch.Tensor:
+    """x fp32 [N, C, H, W] -> bf16 [N * (H/P) * (W/P), Kpad] patch rows in the Conv2d weight's column order (lkgd_patchify)."""
+    _need_cuda(x)
+    x = x.to(torch.float32).contiguous()
+    N, Cn, H, W = x.shape
+    out = torch.empty((N * (H // P) * (W // P), Kpad), device=x.device, dtype=bf16)
+    L.check(L.load().lkgd_patchify(x.data_ptr(), N, Cn, H, W, P, out.data_ptr(), Kpad, _stream()), "lkgd_patchify")
     return out
 
 

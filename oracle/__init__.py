@@ -34,3 +34,4 @@ from .lora import LoraLinear, add_lora, merge_lora  # noqa: F401
 from .scheduler import EulerDiscreteScheduler  # noqa: F401
 from .pipeline import (guidance_ramp, cfg_combine, denoise_loop, add_time_ids_inference, add_time_ids_training,  # noqa: F401
                        smooth_chunks, smooth_loop)
+from .clip import CLIPVisionModelWithProjection, CLIP_VIT_H_14  # noqa: F401,E402

@@ -239,6 +239,36 @@ def test_masked_multi_adapter_lora_matches_the_references_hacked_forward():
         assert rel(l(x), LG["loramask/y_masked2"]) < 1e-6
 
 
+@pytest.mark.parametrize("act,heads,hid", [("gelu", 2, 160), ("quick_gelu", 4, 64)])
+def test_clip_oracle_matches_transformers(act, heads, hid):
+    """SURVEY 8f N1 (CLIP half): the oracle's CLIPVisionModelWithProjection - a restatement of the un-vendored
+    transformers class the reference pipelines call (pipeline...controlnet.py:174-214) - against the `transformers` package
+    installed in this image, identical state_dict (80- and 16-wide heads, both activations)."""
+    tf = pytest.importorskip("transformers")
+    cfg = dict(hidden_size=hid, intermediate_size=2 * hid, num_hidden_layers=3, num_attention_heads=heads, image_size=56,
+               patch_size=14, num_channels=3, projection_dim=48, hidden_act=act, layer_norm_eps=1e-5)
+    torch.manual_seed(0)
+    hf = tf.CLIPVisionModelWithProjection(tf.CLIPVisionConfig(**cfg)).eval()
+    o = O.CLIPVisionModelWithProjection(**cfg).eval()
+    o.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.endswith("position_ids")}, strict=True)
+    x = seeded_tensor("clip/x", (2, 3, 56, 56))
+    with torch.no_grad():
+        assert rel(o(x).image_embeds, hf(pixel_values=x).image_embeds) < 1e-5
+
+
+def test_image_preprocessing_matches_the_references_function():
+    """lkgd_b200/preprocess.py (anti-aliased resize of `_encode_image`) against the reference's own
+    `_resize_with_antialiasing` run here (tests/golden/make_preprocess_golden.py; fp16 fixture)."""
+    from lkgd_b200.preprocess import clip_pixel_values, resize_with_antialiasing
+    PG_ = np.load(os.path.join(HERE, "golden", "preprocess_golden.npz"))
+    for tag, shape in {"576x1024": (1, 3, 576, 1024), "224x300": (1, 3, 224, 300)}.items():
+        img = seeded_tensor(f"pre/{tag}", shape).sigmoid()
+        got = resize_with_antialiasing(img * 2.0 - 1.0, (224, 224))
+        assert float((got - t(PG_[f"pre/{tag}"]).float()).abs().max()) < 2e-3
+    pv = clip_pixel_values(seeded_tensor("pre/576x1024", (1, 3, 576, 1024)).sigmoid())
+    assert tuple(pv.shape) == (1, 3, 224, 224) and abs(float(pv.mean())) < 1.0
+
+
 def test_flow_stem_unet_matches_reference():
     """the reference's flow-stem UNet (models/unet_spatio_temporal_condition_flow.py, run through the shim
     by tests/golden/make_flow_golden.py) against the oracle restatement; conv_in2 / conv_in2_alpha keep their names."""

@@ -663,3 +663,64 @@ def test_joint_attention_with_masked_multi_adapter_lora(cuda, flip):
     print("joint attention + masked adapters, flip =", flip, "rel-L2", err, "| masked vs unmasked", rel_l2(unmasked, ref))
     assert err < 1e-2
     assert rel_l2(unmasked, ref) > 3 * err
+
+
+@pytest.mark.parametrize("name", ["d80_gelu", "d16_quick", "vit_h_14"])
+def test_clip_image_encoder(cuda, name):
+    """SURVEY 8f N1 (CLIP half): lkgd_b200.clip.CLIPVisionModelWithProjection against the oracle (pinned against the
+    `transformers` implementation on the CPU): 80-wide heads (the ViT-H head size, two-sub-tile attention kernel with
+    zero-filled channels), 16-wide heads + quick-GELU, and the full ViT-H/14 of the SVD checkpoints (632 M parameters,
+    random weights, 2 images)."""
+    import oracle as O
+    from lkgd_b200.clip import CLIP_VIT_H_14, CLIPVisionModelWithProjection
+    cfg = {"d80_gelu": dict(hidden_size=160, intermediate_size=320, num_hidden_layers=3, num_attention_heads=2, image_size=56,
+                            patch_size=14, projection_dim=48, hidden_act="gelu"),
+           "d16_quick": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                             image_size=56, patch_size=14, projection_dim=32, hidden_act="quick_gelu"),
+           "vit_h_14": dict(CLIP_VIT_H_14)}[name]
+    torch.manual_seed(0)
+    o = O.CLIPVisionModelWithProjection(**cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if prm.ndim >= 2 and "embedding" not in n:
+                prm.copy_(((torch.rand(prm.shape, generator=g) * 2 - 1) * prm[0].numel() ** -0.5).to(torch.bfloat16).float())
+            elif "layer_norm" in n or "layrnorm" in n or "layernorm" in n:
+                prm.copy_((1.0 if n.endswith("weight") else 0.0) + 0.1 * torch.randn(prm.shape, generator=g))
+            else:
+                prm.copy_(0.05 * torch.randn(prm.shape, generator=g))
+    p = CLIPVisionModelWithProjection(**cfg)
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    S = cfg["image_size"]
+    x = torch.randn(2, 3, S, S, generator=g)
+    with torch.no_grad():
+        ref = o(x)
+    got = p(x.to(cuda))
+    e_h, e_e = rel_l2(got.last_hidden_state, ref.last_hidden_state), rel_l2(got.image_embeds, ref.image_embeds)
+    print(name, "hidden rel-L2", e_h, "image_embeds rel-L2", e_e)
+    assert tuple(got.image_embeds.shape) == (2, cfg["projection_dim"])
+    assert e_h < 1e-2 and e_e < 1.5e-2
+    with pytest.raises(ValueError, match="doesn't match model"):
+        p(torch.zeros(1, 3, S + 14, S, device=cuda))
+
+
+def test_encode_image_end_to_end(cuda):
+    """`_encode_image` (pipeline...controlnet.py:174-214): anti-aliased resize + CLIP normalisation + image encoder +
+    nvpp repetition + zero unconditional half, feeding the denoise pipeline's `image_embeddings`."""
+    import oracle as O
+    from lkgd_b200.clip import CLIPVisionModelWithProjection
+    from lkgd_b200.preprocess import clip_pixel_values, encode_image
+    cfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, image_size=224,
+               patch_size=14, projection_dim=32, hidden_act="gelu")
+    torch.manual_seed(0)
+    o = O.CLIPVisionModelWithProjection(**cfg).eval()
+    p = CLIPVisionModelWithProjection(**cfg)
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    img = torch.rand(1, 3, 320, 512, generator=torch.Generator().manual_seed(2))
+    emb = encode_image(p, img, num_videos_per_prompt=2, do_classifier_free_guidance=True)
+    assert tuple(emb.shape) == (4, 1, 32) and float(emb[:2].abs().max()) == 0.0 and torch.equal(emb[2], emb[3])
+    with torch.no_grad():
+        ref = o(clip_pixel_values(img)).image_embeds
+    assert rel_l2(emb[2, 0], ref[0]) < 1.5e-2
