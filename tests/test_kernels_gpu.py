@@ -623,3 +623,39 @@ def test_thin_conv3x3(cuda, N, H, W, Cin, Cout, silu):
     via_gemm = ops.gemm(x.reshape(-1, Cin).to(cuda), wk, mode=ops.A_CONV3X3, conv=(N, H, W, 1), bias=b.to(cuda),
                         act=ops.ACT_SILU if silu else ops.ACT_NONE)
     assert rel_l2(out.float(), via_gemm.float()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- CLIP image encoder pieces
+@pytest.mark.parametrize("N,Cn,S,P,Kpad", [(2, 3, 56, 14, 592), (1, 3, 224, 14, 592), (3, 4, 32, 8, 256)])
+def test_patchify(cuda, N, Cn, S, P, Kpad):
+    """Patch rows of the non-overlapping Conv2d (CLIP patch embedding): F.unfold's column order, zero-padded to Kpad."""
+    from lkgd_b200 import ops
+    x = rnd(N, Cn, S, S, dev=cuda, dtype=torch.float32)
+    got = ops.patchify(x, P, Kpad)
+    ref = F.unfold(x, P, stride=P).transpose(1, 2).reshape(-1, Cn * P * P).to(bf16)
+    assert tuple(got.shape) == (N * (S // P) ** 2, Kpad)
+    assert torch.equal(got[:, :Cn * P * P], ref) and float(got[:, Cn * P * P:].abs().max() if Kpad > Cn * P * P else 0) == 0
+
+
+@pytest.mark.parametrize("act", ["gelu", "quick_gelu"])
+def test_gemm_gelu_epilogues(cuda, act):
+    from lkgd_b200 import ops
+    A, W, b = rnd(500, 192, dev=cuda), rnd(320, 192, dev=cuda, scale=0.1), rnd(320, dev=cuda, dtype=torch.float32)
+    code = ops.ACT_GELU if act == "gelu" else ops.ACT_QUICK_GELU
+    out = ops.gemm(A, W, bias=b, act=code)
+    y = A.float() @ W.float().t() + b
+    ref = F.gelu(y) if act == "gelu" else y * torch.sigmoid(1.702 * y)
+    assert rel_l2(out.float(), ref) < 4e-3
+    assert rel_l2(ops.gemm(A, W, bias=b, act=code, checker=True).float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("n_img,heads,d,N", [(2, 16, 80, 257), (1, 2, 80, 17), (2, 3, 96, 300), (1, 2, 72, 64)])
+def test_attention_head_widths_between_64_and_128(cuda, n_img, heads, d, N):
+    """ViT-H heads are 80 wide: the two-sub-tile kernel zero-fills the channels above d."""
+    from lkgd_b200 import ops
+    Cn = heads * d
+    qkv = rnd(n_img * N, 3 * Cn, dev=cuda)
+    q, k, v = qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:]
+    out = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N)
+    ref = _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), n_img, heads, d, N, N)
+    assert rel_l2(out.float(), ref) < 6e-3
