@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 5
+#define LKGD_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -119,6 +119,10 @@ typedef struct lkgd_gemm_args {
    * tensors feeding its zero convs (models/controlnet_sdv.py:558-571). */
   void* out2;
   int32_t ldo2;
+  /* CONV3X3 with stride 2 only. 0: padding 1 on every side (diffusers Downsample2D(padding=1), the UNet). 1: the input is
+   * padded on the bottom / right only, F.pad(x, (0, 1, 0, 1)) + Conv2d(stride=2, padding=0): diffusers
+   * Downsample2D(padding=0) of the VAE encoder; output (Hin - 2) / 2 + 1 rows. */
+  int32_t pad_br;
 } lkgd_gemm_args;
 
 LKGD_API int lkgd_gemm(const lkgd_gemm_args* args, void* stream);
@@ -250,6 +254,21 @@ LKGD_API int lkgd_thin_conv3x3(const void* x, int32_t N, int32_t H, int32_t W, i
  * (the Conv2d weight's own flattening), zero beyond C*P*P; the embedding itself is then one lkgd_gemm. */
 LKGD_API int lkgd_patchify(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t P, void* out, int32_t Kpad,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * VAE (diffusers AutoencoderKLTemporalDecoder, un-vendored; call sites pipeline/pipeline_stable_video_diffusion_controlnet.py
+ * :216-237 `_encode_vae_image`, :268-295 `decode_latents`).  Convolutions, GroupNorms and projections run on lkgd_gemm /
+ * lkgd_groupnorm; these two cover what those do not:
+ *   lkgd_softmax_rows  : out[m, n] = softmax_n(scale * x[m, n]); x fp32 [M, N] (row pitch ldx), out bf16 (row pitch ldo),
+ *                        N % 4 == 0, N <= 16384.  The mid-block `Attention` has ONE 512-wide head (heads = C / 512), which does
+ *                        not fit the flash kernel's TMEM budget: it runs as Q K^T (lkgd_gemm, fp32 out) -> this -> P V^T.
+ *   lkgd_time_conv_out : the decoder's final Conv3d(C, C, (3,1,1), padding (1,0,0)) over the frame axis, fused with the
+ *                        channels-last -> planar unpack: x fp32 rows [NB*F*HW, ldx] (first C columns), weight fp32 [C, C, 3]
+ *                        (= Conv3d weight[..., 0, 0]), bias fp32 [C] -> out fp32 [NB*F, C, H*W]; C in {1, 3, 4}. */
+LKGD_API int lkgd_softmax_rows(const float* x, int64_t ldx, int64_t M, int32_t N, float scale, void* out, int64_t ldo,
+                      void* stream);
+LKGD_API int lkgd_time_conv_out(const float* x, int32_t ldx, const float* weight, const float* bias, float* out, int32_t NB,
+                       int32_t F, int64_t HW, int32_t C, void* stream);
 
 /* out[m, :] = srcs[g(m)][m, :] over bf16 [M, C] matrices (C % 8 == 0; srcs = HOST array of n_src <= 8 device pointers, g as
  * for the row vectors above).  Temporal cross-attention with KV length > 1 under the diffusers 0.27.2 context order: row m

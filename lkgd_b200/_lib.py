@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("act", i32), ("s0", f32), ("res1", vp), ("ldr1", i32), ("s1", f32),
         ("res2", vp), ("ldr2", i32), ("s2", f32),
         ("out", vp), ("ldo", i32), ("out_f32", i32), ("n_store", i32), ("res1_f32", i32), ("res2_f32", i32),
-        ("rv_ld", i32), ("gn_stats", vp), ("gn_rows", i32), ("out2", vp), ("ldo2", i32),
+        ("rv_ld", i32), ("gn_stats", vp), ("gn_rows", i32), ("out2", vp), ("ldo2", i32), ("pad_br", i32),
     ]
 
 
@@ -66,6 +66,8 @@ SIGNATURES = {
     "lkgd_cond_conv_in": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "lkgd_thin_conv3x3": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "lkgd_patchify": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "lkgd_softmax_rows": (i32, [vp, i64, i64, i32, f32, vp, i64, vp]),
+    "lkgd_time_conv_out": (i32, [vp, i32, vp, vp, vp, i32, i32, i64, i32, vp]),
     "lkgd_select_rows": (i32, [vp, i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
     "lkgd_fusion_euler_step": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),

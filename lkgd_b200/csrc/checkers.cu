@@ -24,12 +24,13 @@ __device__ float chk_dot(const lkgd_gemm_args& a, long long m, int n) {
     for (int k = 0; k < a.K0; ++k) acc = fmaf(__bfloat162float(ar[k]), __bfloat162float(Bw[k]), acc);
   } else if (a.a_mode == LKGD_A_CONV3X3) {
     const int s = a.stride;
-    const int Ho = (a.Hin - 1) / s + 1, Wo = (a.Win - 1) / s + 1;
+    const int pad = (s == 2 && a.pad_br) ? 0 : 1;
+    const int Ho = pad ? (a.Hin - 1) / s + 1 : (a.Hin - 2) / 2 + 1, Wo = pad ? (a.Win - 1) / s + 1 : (a.Win - 2) / 2 + 1;
     const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho);
     const long long img = m / ((long long)Wo * Ho);
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
-        const int hi = ho * s + ky - 1, wi = wo * s + kx - 1;
+        const int hi = ho * s + ky - pad, wi = wo * s + kx - pad;
         if (hi < 0 || hi >= a.Hin || wi < 0 || wi >= a.Win) continue;
         const __nv_bfloat16* ar = A + ((img * a.Hin + hi) * a.Win + wi) * a.K0;
         const __nv_bfloat16* br = Bw + (ky * 3 + kx) * a.K0;

@@ -344,7 +344,10 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
   } else if (a->a_mode == LKGD_A_CONV3X3) {
     const int s = a->stride;
     if (s != 1 && s != 2) return LKGD_ESHAPE;
-    const int Ho = (a->Hin - 1) / s + 1, Wo = (a->Win - 1) / s + 1;
+    const bool pad_br = s == 2 && a->pad_br;     // F.pad(x, (0, 1, 0, 1)) + Conv2d(stride 2, padding 0)
+    if (pad_br && (a->Hin < 2 || a->Win < 2)) return LKGD_ESHAPE;
+    const int Ho = pad_br ? (a->Hin - 2) / 2 + 1 : (a->Hin - 1) / s + 1;
+    const int Wo = pad_br ? (a->Win - 2) / 2 + 1 : (a->Win - 1) / s + 1;
     if ((long long)a->NIMG * Ho * Wo != a->M) return LKGD_ESHAPE;
     p.H = Ho; p.W = Wo;
     choose_patch(Ho, Wo, a->NIMG, p.TW, p.TH, p.IPT);
@@ -376,8 +379,13 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
         }
       for (int t = 0; t < 9; ++t) {
         int ky = t / 3, kx = t % 3;
-        p.tap_map[t] = (signed char)((((ky + 1) & 1) * 2) + ((kx + 1) & 1));
-        p.tap_dy[t] = ky == 0 ? -1 : 0; p.tap_dx[t] = kx == 0 ? -1 : 0;
+        if (pad_br) {   // input row 2 y + ky: plane ky & 1 at plane row y + (ky >> 1)
+          p.tap_map[t] = (signed char)(((ky & 1) * 2) + (kx & 1));
+          p.tap_dy[t] = ky == 2 ? 1 : 0; p.tap_dx[t] = kx == 2 ? 1 : 0;
+        } else {
+          p.tap_map[t] = (signed char)((((ky + 1) & 1) * 2) + ((kx + 1) & 1));
+          p.tap_dy[t] = ky == 0 ? -1 : 0; p.tap_dx[t] = kx == 0 ? -1 : 0;
+        }
       }
     }
     if (a->K1) {  // centre-tap segment over an [NIMG, Ho, Wo, K1] tensor

@@ -108,7 +108,9 @@ class PackedResBlock:
         self.n1, self.n2 = Norm.of(s.norm1), Norm.of(s.norm2)
         self.w1, self.b1 = _conv3x3_weight(s.conv1)
         self.w2, self.b2 = _conv3x3_weight(s.conv2)
-        self.temb_w, self.temb_b = _f32(s.time_emb_proj.weight), _f32(s.time_emb_proj.bias)
+        self.has_temb = s.time_emb_proj is not None          # False: the VAE's temporal decoder
+        if self.has_temb:
+            self.temb_w, self.temb_b = _f32(s.time_emb_proj.weight), _f32(s.time_emb_proj.bias)
         if s.conv_shortcut is not None:
             self.wsc = _b16(s.conv_shortcut.weight.reshape(self.cout, self.cin))
             self.bsc = _f32(s.conv_shortcut.bias)
@@ -121,8 +123,11 @@ class PackedResBlock:
         self.tw1 = _b16(t.conv1.weight[..., 0, 0].permute(0, 2, 1).reshape(c, 3 * c))
         self.tw2 = _b16(t.conv2.weight[..., 0, 0].permute(0, 2, 1).reshape(c, 3 * c))
         self.tb1, self.tb2 = _f32(t.conv1.bias), _f32(t.conv2.bias)
-        self.ttemb_w, self.ttemb_b = _f32(t.time_emb_proj.weight), _f32(t.time_emb_proj.bias)
+        if self.has_temb:
+            self.ttemb_w, self.ttemb_b = _f32(t.time_emb_proj.weight), _f32(t.time_emb_proj.bias)
         self.alpha = float(torch.sigmoid(blk.time_mixer.mix_factor.detach().float()).item())
+        if getattr(blk.time_mixer, "switch_spatial_to_temporal_mix", False):
+            self.alpha = 1.0 - self.alpha
 
 
 def _dense(mod, fold_lora: bool) -> Dense:
@@ -405,8 +410,8 @@ def run_resblock(p: PackedResBlock, x: torch.Tensor, skip: Optional[torch.Tensor
                  want_bf16: bool = False):
     """x (and skip) are fp32 stream tensors; returns the fp32 block output (``want_bf16``: and its bf16 copy, written
     by the same epilogue)."""
-    temb_s = cond.temb(p.off_s, p.cout)
-    temb_t = cond.temb(p.off_t, p.cout)
+    temb_s = cond.temb(p.off_s, p.cout) if p.has_temb else None
+    temb_t = cond.temb(p.off_t, p.cout) if p.has_temb else None
     # blocks with a 1x1 shortcut conv need their raw (concatenated) input as a bf16 GEMM operand: the GroupNorm pass
     # that reads it anyway writes that copy too
     xa = None

@@ -155,8 +155,11 @@ class TemporalBasicTransformerBlock(_JointAttention, Container):
 
 
 class AlphaBlender(Container):
-    def __init__(self, alpha=0.5):
+    """``switch_spatial_to_temporal_mix`` (the VAE's temporal decoder): alpha -> 1 - alpha."""
+
+    def __init__(self, alpha=0.5, merge_strategy="learned_with_images", switch_spatial_to_temporal_mix=False):
         super().__init__()
+        self.merge_strategy, self.switch_spatial_to_temporal_mix = merge_strategy, switch_spatial_to_temporal_mix
         self.mix_factor = nn.Parameter(torch.tensor([alpha], dtype=torch.float32))
 
 
@@ -183,7 +186,7 @@ class ResnetBlock2D(Container):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.norm1 = GroupNorm(32, in_channels, eps=eps)
         self.conv1 = Conv2d(in_channels, out_channels, 3, padding=1)
-        self.time_emb_proj = Linear(temb_channels, out_channels)
+        self.time_emb_proj = Linear(temb_channels, out_channels) if temb_channels is not None else None    # None: the VAE
         self.norm2 = GroupNorm(32, out_channels, eps=eps)
         self.conv2 = Conv2d(out_channels, out_channels, 3, padding=1)
         self.conv_shortcut = Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
@@ -196,24 +199,32 @@ class TemporalResnetBlock(Container):
             raise ValueError("temporal resblocks of the SVD UNet have in_channels == out_channels")
         self.norm1 = GroupNorm(32, in_channels, eps=eps)
         self.conv1 = Conv3d(in_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
-        self.time_emb_proj = Linear(temb_channels, out_channels)
+        self.time_emb_proj = Linear(temb_channels, out_channels) if temb_channels is not None else None
         self.norm2 = GroupNorm(32, out_channels, eps=eps)
         self.conv2 = Conv3d(out_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
         self.conv_shortcut = None
 
 
 class SpatioTemporalResBlock(Container):
-    def __init__(self, in_channels, out_channels, temb_channels, eps):
+    """UNet: ``(in, out, temb_channels, eps)``; VAE temporal decoder: ``temb_channels=None, eps=1e-6, temporal_eps=1e-5,
+    merge_factor=0.0, merge_strategy="learned", switch_spatial_to_temporal_mix=True``."""
+
+    def __init__(self, in_channels, out_channels, temb_channels, eps, temporal_eps=None, merge_factor=0.5,
+                 merge_strategy="learned_with_images", switch_spatial_to_temporal_mix=False):
         super().__init__()
         self.spatial_res_block = ResnetBlock2D(in_channels, out_channels, temb_channels, eps)
-        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels, eps)
-        self.time_mixer = AlphaBlender(0.5)
+        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels,
+                                                      eps if temporal_eps is None else temporal_eps)
+        self.time_mixer = AlphaBlender(merge_factor, merge_strategy, switch_spatial_to_temporal_mix)
 
 
 class Downsample2D(Container):
-    def __init__(self, channels):
+    """``padding=0`` (the VAE encoder): the input is padded on the bottom / right only, F.pad(x, (0, 1, 0, 1))."""
+
+    def __init__(self, channels, padding=1):
         super().__init__()
-        self.conv = Conv2d(channels, channels, 3, stride=2, padding=1)
+        self.padding = padding
+        self.conv = Conv2d(channels, channels, 3, stride=2, padding=padding)
 
 
 class Upsample2D(Container):

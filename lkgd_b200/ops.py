@@ -73,7 +73,7 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
          act: int = ACT_NONE, s0: float = 1.0, res1: Optional[torch.Tensor] = None, s1: float = 1.0,
          res2: Optional[torch.Tensor] = None, s2: float = 1.0, out: Optional[torch.Tensor] = None,
          out_f32: bool = False, n_store: int = 0, checker: bool = False, gn_rows: int = 0,
-         out2: Optional[torch.Tensor] = None, want_bf16: bool = False):
+         out2: Optional[torch.Tensor] = None, want_bf16: bool = False, pad_br: bool = False):
     """out = s0*act(A (*) Bw^T [+ A1 Bw1^T] + bias + rowvec[g(m)]) + s1*res1 + s2*res2   (see lkgd_gemm).
 
     ``want_bf16`` (fp32 outputs): also write a bf16 copy of the output in the same epilogue and return ``(out, out2)``
@@ -84,7 +84,8 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
     ``groupnorm`` that consumes it skip its statistics pass.
 
     LINEAR: ``A`` is [M, K] (may be a column slice of a wider row-major matrix).  CONV3X3: ``A`` is contiguous
-    [NIMG, Hin, Win, C], ``conv=(NIMG, Hin, Win, stride)``, ``Bw`` [N, 9*C].  TCONV3: ``A`` contiguous
+    [NIMG, Hin, Win, C], ``conv=(NIMG, Hin, Win, stride)``, ``Bw`` [N, 9*C] (``pad_br``: stride 2 with the input padded on
+    the bottom / right only - diffusers ``Downsample2D(padding=0)`` of the VAE encoder).  TCONV3: ``A`` contiguous
     [B, F, HW, C], ``tconv=(B, F, HW)``, ``Bw`` [N, 3*C]."""
     _need_cuda(A, Bw, bias, A1, Bw1, rowvec, res1, res2, out)
     if A.dtype != bf16 or Bw.dtype != bf16:
@@ -103,7 +104,13 @@ def gemm(A: torch.Tensor, Bw: torch.Tensor, *, mode: int = A_LINEAR, M: Optional
         a.NIMG, a.Hin, a.Win, a.stride = conv
         a.K0 = A.shape[-1]
         s = conv[3]
-        M = conv[0] * ((conv[1] - 1) // s + 1) * ((conv[2] - 1) // s + 1)
+        if pad_br:
+            if s != 2:
+                raise ValueError("pad_br (bottom / right padding only) is the stride-2 convolution of Downsample2D(padding=0)")
+            a.pad_br = 1
+            M = conv[0] * ((conv[1] - 2) // 2 + 1) * ((conv[2] - 2) // 2 + 1)
+        else:
+            M = conv[0] * ((conv[1] - 1) // s + 1) * ((conv[2] - 1) // s + 1)
     elif mode == A_TCONV3:
         if tconv is None or not A.is_contiguous():
             raise ValueError("TCONV3 needs tconv=(B,F,HW) and a contiguous [B,F,HW,C] tensor")
@@ -523,6 +530,41 @@ def patchify(x: torch.Tensor, P: int, Kpad: int) -> torch.Tensor:
     N, Cn, H, W = x.shape
     out = torch.empty((N * (H // P) * (W // P), Kpad), device=x.device, dtype=bf16)
     L.check(L.load().lkgd_patchify(x.data_ptr(), N, Cn, H, W, P, out.data_ptr(), Kpad, _stream()), "lkgd_patchify")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 softmax(scale * x) over the last axis of an fp32 [M, N] matrix (row slices / pitches allowed; lkgd_softmax_rows)."""
+    _need_cuda(x, out)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("softmax_rows: x must be fp32 [M, N] with unit column stride")
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=bf16)
+    elif out.dtype != bf16 or out.dim() != 2 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise ValueError("softmax_rows: out must be bf16 [M, N] with unit column stride")
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": M * N * 6}
+    L.check(L.load().lkgd_softmax_rows(x.data_ptr(), x.stride(0), M, N, scale, out.data_ptr(), out.stride(0), _stream()),
+            "lkgd_softmax_rows")
+    return out
+
+
+def time_conv_out(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, NB: int, F: int, H: int, W: int) -> torch.Tensor:
+    """x fp32 rows [NB*F*H*W, ld] (first C columns) -> fp32 [NB*F, C, H, W] = Conv3d(C, C, (3,1,1), padding (1,0,0)) over the
+    frame axis (lkgd_time_conv_out); weight fp32 [C, C, 3]."""
+    _need_cuda(x, weight, bias)
+    Cn = weight.shape[0]
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[0] != NB * F * H * W or x.shape[1] < Cn:
+        raise ValueError("time_conv_out: x must be fp32 [NB*F*H*W, >= C] rows")
+    if weight.dtype != torch.float32 or not weight.is_contiguous() or tuple(weight.shape) != (Cn, Cn, 3) \
+            or bias.dtype != torch.float32 or bias.numel() != Cn:
+        raise ValueError("time_conv_out: weight fp32 [C, C, 3], bias fp32 [C]")
+    out = torch.empty((NB * F, Cn, H, W), device=x.device, dtype=torch.float32)
+    if L.PROF.enabled:
+        L.PROF.meta = {"bytes": NB * F * H * W * Cn * 8}
+    L.check(L.load().lkgd_time_conv_out(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), NB, F,
+                                        H * W, Cn, _stream()), "lkgd_time_conv_out")
     return out
 
 

@@ -35,3 +35,4 @@ from .scheduler import EulerDiscreteScheduler  # noqa: F401
 from .pipeline import (guidance_ramp, cfg_combine, denoise_loop, add_time_ids_inference, add_time_ids_training,  # noqa: F401
                        smooth_chunks, smooth_loop)
 from .clip import CLIPVisionModelWithProjection, CLIP_VIT_H_14  # noqa: F401,E402
+from .vae import AutoencoderKLTemporalDecoder, SVD_VAE_CONFIG, decode_latents  # noqa: F401,E402

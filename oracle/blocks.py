@@ -208,21 +208,32 @@ class TemporalBasicTransformerBlock(nn.Module):
 
 
 class AlphaBlender(nn.Module):
-    """``AlphaBlender(alpha, "learned_with_images")``: alpha = where(iof, 1, sigmoid(mix_factor))."""
+    """``AlphaBlender(alpha, "learned_with_images")``: alpha = where(iof, 1, sigmoid(mix_factor)) (the UNet);
+    ``"learned"``: alpha = sigmoid(mix_factor) for every frame (the VAE's temporal decoder, which also sets
+    ``switch_spatial_to_temporal_mix``: alpha -> 1 - alpha)."""
 
-    def __init__(self, alpha: float = 0.5):
+    def __init__(self, alpha: float = 0.5, merge_strategy: str = "learned_with_images",
+                 switch_spatial_to_temporal_mix: bool = False):
         super().__init__()
+        if merge_strategy not in ("learned", "learned_with_images"):
+            raise ValueError(f"merge_strategy {merge_strategy!r}")
+        self.merge_strategy, self.switch = merge_strategy, switch_spatial_to_temporal_mix
         self.mix_factor = nn.Parameter(torch.tensor([alpha], dtype=torch.float32))
 
     def forward(self, x_spatial, x_temporal, image_only_indicator):
-        a = torch.where(image_only_indicator.bool(),
-                        torch.ones(1, 1, device=x_spatial.device, dtype=self.mix_factor.dtype),
-                        torch.sigmoid(self.mix_factor)[..., None])
-        if x_spatial.ndim == 5:
-            a = a[:, None, :, None, None]
-        elif x_spatial.ndim == 3:
-            a = a.reshape(-1)[:, None, None]
+        if self.merge_strategy == "learned":
+            a = torch.sigmoid(self.mix_factor)
+        else:
+            a = torch.where(image_only_indicator.bool(),
+                            torch.ones(1, 1, device=x_spatial.device, dtype=self.mix_factor.dtype),
+                            torch.sigmoid(self.mix_factor)[..., None])
+            if x_spatial.ndim == 5:
+                a = a[:, None, :, None, None]
+            elif x_spatial.ndim == 3:
+                a = a.reshape(-1)[:, None, None]
         a = a.to(x_spatial.dtype)
+        if self.switch:
+            a = 1.0 - a
         return a * x_spatial + (1.0 - a) * x_temporal
 
 
@@ -287,18 +298,21 @@ class TransformerSpatioTemporalModel(nn.Module):
 
 # --------------------------------------------------------------------------- resnets (A.3, A.4)
 class ResnetBlock2D(nn.Module):
-    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, eps: float, groups: int = 32):
+    """``temb_channels=None`` (the VAE): no time-embedding projection."""
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int], eps: float, groups: int = 32):
         super().__init__()
         self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps)
         self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
-        self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
         self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps)
         self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
 
-    def forward(self, x, temb):
+    def forward(self, x, temb=None):
         h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        if self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(F.silu(self.norm2(h)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
@@ -308,19 +322,19 @@ class ResnetBlock2D(nn.Module):
 class TemporalResnetBlock(nn.Module):
     """GroupNorm on the 5-D tensor: statistics over (C/32)*F*H*W, i.e. ACROSS frames."""
 
-    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, eps: float):
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int], eps: float):
         super().__init__()
         self.norm1 = nn.GroupNorm(32, in_channels, eps=eps)
         self.conv1 = nn.Conv3d(in_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
-        self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
         self.norm2 = nn.GroupNorm(32, out_channels, eps=eps)
         self.conv2 = nn.Conv3d(out_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
         self.conv_shortcut = nn.Conv3d(in_channels, out_channels, 1) if in_channels != out_channels else None
 
-    def forward(self, x, temb):  # x [B,C,F,H,W], temb [B,F,T]
+    def forward(self, x, temb=None):  # x [B,C,F,H,W], temb [B,F,T]
         h = self.conv1(F.silu(self.norm1(x)))
-        t = self.time_emb_proj(F.silu(temb))[:, :, :, None, None].permute(0, 2, 1, 3, 4)
-        h = h + t
+        if self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(F.silu(temb))[:, :, :, None, None].permute(0, 2, 1, 3, 4)
         h = self.conv2(F.silu(self.norm2(h)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
@@ -328,11 +342,17 @@ class TemporalResnetBlock(nn.Module):
 
 
 class SpatioTemporalResBlock(nn.Module):
-    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, eps: float):
+    """UNet: ``(in, out, temb_channels, eps)``.  VAE temporal decoder: ``temb_channels=None, eps=1e-6, temporal_eps=1e-5,
+    merge_factor=0.0, merge_strategy="learned", switch_spatial_to_temporal_mix=True``."""
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int], eps: float,
+                 temporal_eps: Optional[float] = None, merge_factor: float = 0.5,
+                 merge_strategy: str = "learned_with_images", switch_spatial_to_temporal_mix: bool = False):
         super().__init__()
         self.spatial_res_block = ResnetBlock2D(in_channels, out_channels, temb_channels, eps)
-        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels, eps)
-        self.time_mixer = AlphaBlender(0.5)
+        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels,
+                                                      temporal_eps if temporal_eps is not None else eps)
+        self.time_mixer = AlphaBlender(merge_factor, merge_strategy, switch_spatial_to_temporal_mix)
 
     def forward(self, x, temb, image_only_indicator):
         f = image_only_indicator.shape[-1]
@@ -340,18 +360,23 @@ class SpatioTemporalResBlock(nn.Module):
         bf, c, h, w = x.shape
         b = bf // f
         xs = x[None, :].reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
-        xt = self.temporal_res_block(xs, temb.reshape(b, f, -1))
+        xt = self.temporal_res_block(xs, temb.reshape(b, f, -1) if temb is not None else None)
         x = self.time_mixer(xs, xt, image_only_indicator)
         return x.permute(0, 2, 1, 3, 4).reshape(bf, c, h, w)
 
 
 # --------------------------------------------------------------------------- sampling (A.10)
 class Downsample2D(nn.Module):
-    def __init__(self, channels: int):
+    """``padding=0`` (the VAE encoder): the input is padded (0, 1, 0, 1) - right / bottom only - before the conv."""
+
+    def __init__(self, channels: int, padding: int = 1):
         super().__init__()
-        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+        self.padding = padding
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=padding)
 
     def forward(self, x):
+        if self.padding == 0:
+            x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
         return self.conv(x)
 
 

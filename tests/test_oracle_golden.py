@@ -488,3 +488,59 @@ def test_oracle_fp64_self_consistency():
         a = o(sample, 0.5, ctx, added_time_ids=ids).sample
         b = o.double()(sample.double(), 0.5, ctx.double(), added_time_ids=ids.double()).sample
     assert rel(a, b) < 1e-5
+
+
+def test_vae_state_dict_names():
+    """SURVEY 8f N1 (VAE half; oracle/vae.py is a restatement of the un-vendored diffusers class, parity unpinned): the oracle
+    and the product module expose the SVD checkpoint's `vae/` parameter names and shapes - 374 tensors, 97.74 M parameters -
+    and the structural facts the diffusers class is known by (no post_quant_conv, Conv3d time_conv_out, learned blenders)."""
+    from lkgd_b200.vae import AutoencoderKLTemporalDecoder as P
+    o = O.AutoencoderKLTemporalDecoder(**O.SVD_VAE_CONFIG)
+    p = P(**O.SVD_VAE_CONFIG)
+    so, sp = o.state_dict(), p.state_dict()
+    assert list(so.keys()) == list(sp.keys()) and all(so[k].shape == sp[k].shape for k in so)
+    assert len(so) == 374 and sum(v.numel() for v in so.values()) == 97_742_847
+    for k, shape in {"encoder.conv_in.weight": (128, 3, 3, 3), "encoder.down_blocks.1.resnets.0.conv_shortcut.weight": (256, 128, 1, 1),
+                     "encoder.down_blocks.2.downsamplers.0.conv.weight": (512, 512, 3, 3),
+                     "encoder.mid_block.attentions.0.to_q.weight": (512, 512), "encoder.mid_block.attentions.0.to_out.0.bias": (512,),
+                     "encoder.mid_block.attentions.0.group_norm.weight": (512,), "encoder.conv_out.weight": (8, 512, 3, 3),
+                     "quant_conv.weight": (8, 8, 1, 1), "decoder.conv_in.weight": (512, 4, 3, 3),
+                     "decoder.mid_block.resnets.0.spatial_res_block.conv1.weight": (512, 512, 3, 3),
+                     "decoder.mid_block.resnets.1.temporal_res_block.conv2.weight": (512, 512, 3, 1, 1),
+                     "decoder.mid_block.resnets.0.time_mixer.mix_factor": (1,),
+                     "decoder.mid_block.attentions.0.to_v.bias": (512,),
+                     "decoder.up_blocks.2.resnets.0.spatial_res_block.conv_shortcut.weight": (256, 512, 1, 1),
+                     "decoder.up_blocks.3.resnets.2.temporal_res_block.norm1.weight": (128,),
+                     "decoder.up_blocks.2.upsamplers.0.conv.weight": (256, 256, 3, 3),
+                     "decoder.conv_out.weight": (3, 128, 3, 3), "decoder.time_conv_out.weight": (3, 3, 3, 1, 1)}.items():
+        assert tuple(so[k].shape) == shape, k
+    assert not any(k.startswith("post_quant_conv") or "time_emb_proj" in k or "upsamplers" in k and k.startswith("decoder.up_blocks.3")
+                   for k in so)
+
+
+def test_vae_oracle_semantics():
+    """decode mixes frames only inside one `num_frames` clip; the learned blender is switched (alpha -> 1 - alpha); the encoder's
+    downsample pads bottom / right; `decode_latents` returns [B, 3, F, H, W]."""
+    torch.manual_seed(0)
+    v = O.AutoencoderKLTemporalDecoder(block_out_channels=(32, 32, 64, 64)).eval()
+    z = seeded_tensor("vae/z", (4, 4, 4, 6))
+    with torch.no_grad():
+        a = v.decode(z, num_frames=2).sample
+        b = v.decode(z[:2], num_frames=2).sample
+        c = v.decode(z, num_frames=4).sample
+        assert torch.allclose(a[:2], b, atol=1e-5) and not torch.allclose(a, c, atol=1e-4)
+        for r in v.decoder.mid_block.resnets:
+            r.time_mixer.mix_factor.fill_(-30.0)          # sigmoid -> 0, switched alpha -> 1: spatial branch only
+        for blk in v.decoder.up_blocks:
+            for r in blk.resnets:
+                r.time_mixer.mix_factor.fill_(-30.0)
+        v.decoder.time_conv_out.weight.zero_()
+        v.decoder.time_conv_out.weight[:, :, 1].copy_(torch.eye(3)[..., None, None])
+        d2, d4 = v.decode(z, num_frames=2).sample, v.decode(z, num_frames=4).sample
+        assert torch.allclose(d2, d4, atol=1e-5)          # no temporal path left
+        x = seeded_tensor("vae/x", (1, 32, 6, 6))
+        ds = v.encoder.down_blocks[0].downsamplers[0]
+        assert torch.allclose(ds(x), torch.nn.functional.conv2d(torch.nn.functional.pad(x, (0, 1, 0, 1)), ds.conv.weight,
+                                                                ds.conv.bias, stride=2))
+        out = O.decode_latents(v, seeded_tensor("vae/l", (1, 3, 4, 4, 4)), num_frames=3, decode_chunk_size=2)
+    assert tuple(out.shape) == (1, 3, 3, 32, 32)
