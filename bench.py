@@ -621,6 +621,13 @@ def main():
         del pipe, st
         torch.cuda.empty_cache()
         extra_sections["c5_data_parallel_training"] = section_c5_dp(args, device, rank, world)
+    if world == 1 and not args.no_extra_sections and args.workload == "C3":
+        del pipe, st
+        torch.cuda.empty_cache()
+        try:
+            extra_sections["vae_and_clip"] = section_vae_clip(device)
+        except Exception as ex:   # the side sections must never sink the headline number
+            extra_sections["vae_and_clip"] = {"failed": repr(ex)}
 
     if rank == 0:
         steps_total = args.steps * world
@@ -663,6 +670,50 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def section_vae_clip(device):
+    """The steps either side of the denoise loop at the headline sizes, random weights: temporal VAE decode of
+    25 x 576 x 1024 frames in chunks of 8 (the reference scripts' decode_chunk_size, run_models/run_inference.py:295), VAE
+    encode of one 576x1024 image, CLIP ViT-H/14 embedding of one image.  CUDA events, one warm-up pass each."""
+    from lkgd_b200 import ops
+    from lkgd_b200.clip import CLIP_VIT_H_14, CLIPVisionModelWithProjection
+    from lkgd_b200.flops import vae_flops
+    from lkgd_b200.vae import SVD_VAE_CONFIG, AutoencoderKLTemporalDecoder, decode_latents
+    torch.manual_seed(0)
+    vae = AutoencoderKLTemporalDecoder(**SVD_VAE_CONFIG).to(device)
+    lat = torch.randn(1, 25, 4, 72, 128, device=device)
+    img = torch.rand(1, 3, 576, 1024, device=device) * 2 - 1
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
+
+    l0 = ops.launch_count()
+    dec_ms, frames = timed(lambda: decode_latents(vae, lat, 25, 8), 2)
+    dec_launches = (ops.launch_count() - l0) // 3
+    enc_ms, dist_ = timed(lambda: vae.encode(img).latent_dist.mode(), 3)
+    fl = vae_flops(SVD_VAE_CONFIG, 25, 72, 128)
+    out = {"vae_decode_ms": dec_ms, "frames": 25, "frame_size": [576, 1024], "decode_chunk_size": 8,
+           "vae_decode_tflop": fl["decode"] / 1e12, "vae_decode_tflops": fl["decode"] / 1e12 / (dec_ms * 1e-3),
+           "vae_decode_launches": int(dec_launches), "vae_decode_finite": bool(torch.isfinite(frames).all().item()),
+           "vae_encode_ms": enc_ms, "vae_encode_tflops": fl["encode"] / 1e12 / (enc_ms * 1e-3)}
+    del vae, frames
+    torch.cuda.empty_cache()
+    clip = CLIPVisionModelWithProjection(**CLIP_VIT_H_14).to(device)
+    pv = torch.randn(1, 3, 224, 224, device=device)
+    clip_ms, _ = timed(lambda: clip(pv).image_embeds, 3)
+    out["clip_vit_h_ms"] = clip_ms
+    out["note"] = ("one pipeline call = 1 CLIP + 1 VAE encode + 25 denoise steps + 1 chunked VAE decode; random weights, "
+                   "inputs resident on the device")
+    return out
 
 
 def _rel(a, b):

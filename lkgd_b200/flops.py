@@ -114,3 +114,51 @@ def controlnet_flops(cfg: dict, B: int, F: int, H: int, W: int, cond_channels: i
     out["zero_convs"] = float(z)
     out["total"] = sum(out.values())
     return out
+
+
+def vae_flops(cfg: dict, n_frames: int, h: int, w: int) -> Dict[str, float]:
+    """AutoencoderKLTemporalDecoder (lkgd_b200/vae.py): ``decode`` of ``n_frames`` latent frames of h x w and ``encode`` of
+    ONE 8h x 8w image, with the conv / linear / attention formulas above."""
+    boc = list(cfg["block_out_channels"])
+    lpb, lat, cin, cout = cfg["layers_per_block"], cfg["latent_channels"], cfg["in_channels"], cfg["out_channels"]
+    top = boc[-1]
+
+    def conv(ci, co, px, k=9):
+        return 2.0 * k * ci * co * px
+
+    def attn(c, px_img, n):
+        return n * (4 * 2.0 * px_img * c * c + 4.0 * px_img * px_img * c)
+
+    # ---- temporal decoder
+    px = n_frames * h * w
+
+    def tres(ci, co, px):
+        f = conv(ci, co, px) + conv(co, co, px) + 2 * conv(co, co, px, 3)
+        return f + (conv(ci, co, px, 1) if ci != co else 0.0)
+
+    d = conv(lat, top, px) + lpb * tres(top, top, px) + attn(top, h * w, n_frames)
+    c, hh, ww = top, h, w
+    rev = list(reversed(boc))
+    for i, co in enumerate(rev):
+        p_ = n_frames * hh * ww
+        d += tres(c, co, p_) + lpb * tres(co, co, p_)
+        c = co
+        if i != len(rev) - 1:
+            hh, ww = 2 * hh, 2 * ww
+            d += conv(c, c, n_frames * hh * ww)
+    d += conv(c, cout, n_frames * hh * ww) + conv(cout, cout, n_frames * hh * ww, 3)
+    # ---- encoder (one image)
+    def res(ci, co, px):
+        return conv(ci, co, px) + conv(co, co, px) + (conv(ci, co, px, 1) if ci != co else 0.0)
+
+    H, W = 8 * h, 8 * w
+    e = conv(cin, boc[0], H * W)
+    c = boc[0]
+    for i, co in enumerate(boc):
+        e += res(c, co, H * W) + (lpb - 1) * res(co, co, H * W)
+        c = co
+        if i != len(boc) - 1:
+            H, W = H // 2, W // 2
+            e += conv(c, c, H * W)
+    e += 2 * res(c, c, H * W) + attn(c, H * W, 1) + conv(c, 2 * lat, H * W) + conv(2 * lat, 2 * lat, H * W, 1)
+    return {"decode": float(d), "encode": float(e)}

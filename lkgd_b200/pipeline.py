@@ -2,10 +2,11 @@
 
 Mirrors the denoising part of the reference pipelines' ``__call__``
 (pipeline/pipeline_stable_video_diffusion_controlnet.py:364-646: added-time ids :517-526, timesteps :529,
-latents :535-545, guidance ramp :553-558, loop :577-630).  VAE / CLIP encode-decode sit either side of the hot
-path and are NOT part of this package: the caller passes what ``_encode_image`` /
-``_encode_vae_image`` return (``image_embeddings`` [2S,1,1024] uncond-first, ``image_latents`` [2S,F,4,h,w]) and
-receives latents (``output_type="latent"``).
+latents :535-545, guidance ramp :553-558, loop :577-630).  The loop itself works on what ``_encode_image`` /
+``_encode_vae_image`` return (``image_embeddings`` [2S,1,1024] uncond-first, ``image_latents`` [2S,F,4,h,w]) and yields
+latents (``output_type="latent"``); with ``vae=`` and ``image_encoder=`` registered (SURVEY.md section 8f, N1:
+``lkgd_b200.vae`` / ``lkgd_b200.clip``) ``__call__(image=...)`` also runs the steps either side of it - CLIP embedding,
+noise-augmented VAE encode (:486-513), chunked temporal VAE decode (:268-295, :636) - and returns frames.
 
 Per step the loop launches: one fused pack kernel (CFG duplication + scale_model_input + image-latent concat +
 NCHW->channels-last), [ControlNet], the UNet, and one fused CFG-combine + Euler-Karras kernel reading the UNet's
@@ -20,7 +21,9 @@ import torch
 
 from . import ops
 from .engine import Conditioning, Geom
+from .preprocess import encode_image
 from .scheduler import EulerDiscreteScheduler
+from .vae import decode_latents, encode_vae_image
 from .unet import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionModel
 
 
@@ -40,9 +43,55 @@ class StableVideoDiffusionPipeline:
     """``unet`` may be the plain/ControlNet-accepting UNet or the LKGD UNet (then ``domain_features`` and
     ``flow_features`` are required, the signature the reference's missing LKGD pipeline would have - SURVEY F11)."""
 
-    def __init__(self, unet, scheduler: EulerDiscreteScheduler, controlnet: Optional[ControlNetSDVModel] = None):
+    def __init__(self, unet, scheduler: EulerDiscreteScheduler, controlnet: Optional[ControlNetSDVModel] = None,
+                 vae=None, image_encoder=None):
         self.unet, self.scheduler, self.controlnet = unet, scheduler, controlnet
+        self.vae, self.image_encoder = vae, image_encoder      # the reference's register_modules(vae=, image_encoder=), :122-143
         self._guidance_scale = None
+
+    # ---- the steps either side of the loop (SURVEY 8f N1)
+    @torch.no_grad()
+    def encode_inputs(self, image: torch.Tensor, height: int, width: int, num_frames: int, noise_aug_strength: float = 0.02,
+                      num_videos_per_prompt: int = 1, do_classifier_free_guidance: bool = True, generator=None):
+        """Reference steps 3-4 (:486-513): ``image`` [B, 3, H, W] in [0, 1] -> (``image_embeddings`` [2S, 1, D],
+        ``image_latents`` [2S, F, 4, h, w]); the VAE sees the [-1, 1] image plus ``noise_aug_strength`` * noise."""
+        if self.vae is None or self.image_encoder is None:
+            raise ValueError("encode_inputs needs the pipeline's vae and image_encoder")
+        if image.ndim == 3:
+            image = image.unsqueeze(0)
+        if image.ndim != 4 or image.shape[1] != 3:
+            raise ValueError(f"image must be a [B, 3, H, W] tensor in [0, 1], got {tuple(image.shape)}")
+        if height % 8 != 0 or width % 8 != 0:                       # check_inputs, :297-311
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        image = image.to(torch.float32)
+        emb = encode_image(self.image_encoder, image, num_videos_per_prompt, do_classifier_free_guidance)
+        # VaeImageProcessor.preprocess on a tensor: F.interpolate to (height, width) [default mode], then [0,1] -> [-1,1]
+        if tuple(image.shape[-2:]) != (height, width):
+            image = torch.nn.functional.interpolate(image, size=(height, width))
+        x = 2.0 * image - 1.0
+        gdev = generator.device if generator is not None else x.device
+        noise = torch.randn(x.shape, generator=generator, device=gdev, dtype=x.dtype).to(x.device)
+        x = x + noise_aug_strength * noise
+        lat = encode_vae_image(self.vae, x, num_videos_per_prompt, do_classifier_free_guidance).to(emb.dtype)
+        return emb, lat.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
+
+    @torch.no_grad()
+    def decode_latents(self, latents: torch.Tensor, num_frames: int, decode_chunk_size: int = 14) -> torch.Tensor:
+        """:268-295: [B, F, 4, h, w] -> fp32 [B, 3, F, 8h, 8w]."""
+        if self.vae is None:
+            raise ValueError("decode_latents needs the pipeline's vae")
+        return decode_latents(self.vae, latents, num_frames, decode_chunk_size)
+
+    @staticmethod
+    def tensor2vid(frames: torch.Tensor, output_type: str):
+        """:67-83 for the tensor output types: [B, 3, F, H, W] in [-1, 1] -> ``"pt"`` [B, F, 3, H, W] in [0, 1], ``"np"`` the
+        same as a [B, F, H, W, 3] numpy array."""
+        vid = (frames.permute(0, 2, 1, 3, 4) / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return vid
+        if output_type == "np":
+            return vid.permute(0, 1, 3, 4, 2).float().cpu().numpy()
+        raise ValueError(f"output_type {output_type!r}: 'latent', 'pt' and 'np' are supported")
 
     @property
     def guidance_scale(self):
@@ -254,7 +303,8 @@ class StableVideoDiffusionPipeline:
         return self._step_body(st, latents, scale, t, want_v=want_v)
 
     @torch.no_grad()
-    def __call__(self, image_embeddings: torch.Tensor, image_latents: torch.Tensor, num_frames: Optional[int] = None,
+    def __call__(self, image_embeddings: Optional[torch.Tensor] = None, image_latents: Optional[torch.Tensor] = None,
+                 num_frames: Optional[int] = None,
                  num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
                  fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
                  num_videos_per_prompt: int = 1, generator=None, latents: Optional[torch.Tensor] = None,
@@ -262,10 +312,24 @@ class StableVideoDiffusionPipeline:
                  domain_features: Optional[torch.Tensor] = None, flow_features: Optional[torch.Tensor] = None,
                  cfg_pair=None, output_type: str = "latent", callback_on_step_end: Optional[Callable] = None,
                  return_dict: bool = True, max_steps: Optional[int] = None, return_trajectory: bool = False,
-                 use_cuda_graph: bool = False, fuse_controlnet: bool = True, direct_fusion: bool = False):
-        if output_type != "latent":
-            raise ValueError("lkgd_b200 covers the denoise loop only: use output_type='latent' and decode with the "
-                             "VAE of your choice (SURVEY.md section 8f, N1)")
+                 use_cuda_graph: bool = False, fuse_controlnet: bool = True, direct_fusion: bool = False,
+                 image: Optional[torch.Tensor] = None, height: int = 576, width: int = 1024,
+                 decode_chunk_size: Optional[int] = None):
+        if output_type not in ("latent", "pt", "np"):
+            raise ValueError(f"output_type {output_type!r}: 'latent', 'pt' and 'np' are supported")
+        if output_type != "latent" and (self.vae is None or return_trajectory):
+            raise ValueError("decoded frames need the pipeline's vae (and no return_trajectory): pass vae= to the "
+                             "pipeline or use output_type='latent'")
+        if num_frames is None:
+            num_frames = self.unet.config.num_frames
+        if image is not None:
+            if image_embeddings is not None or image_latents is not None:
+                raise ValueError("pass either image= or (image_embeddings, image_latents)")
+            image_embeddings, image_latents = self.encode_inputs(
+                image, height, width, num_frames, noise_aug_strength, num_videos_per_prompt, max_guidance_scale > 1.0,
+                generator)
+        elif image_embeddings is None or image_latents is None:
+            raise ValueError("pass image= (with vae and image_encoder registered) or image_embeddings and image_latents")
         st = self.prepare(image_embeddings, image_latents, num_frames, num_inference_steps, min_guidance_scale,
                           max_guidance_scale, fps, motion_bucket_id, noise_aug_strength, num_videos_per_prompt,
                           controlnet_condition, controlnet_cond_scale, domain_features, flow_features, cfg_pair)
@@ -293,9 +357,13 @@ class StableVideoDiffusionPipeline:
                 latents = out.pop("latents", latents)
         if return_trajectory:
             return latents, preds, traj
+        frames = latents
+        if output_type != "latent":                                # :632-636
+            chunk = decode_chunk_size if decode_chunk_size is not None else num_frames
+            frames = self.tensor2vid(self.decode_latents(latents, num_frames, chunk), output_type)
         if not return_dict:
-            return latents
-        return StableVideoDiffusionPipelineOutput(frames=latents)
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)
 
 
 class StableVideoDiffusionSmoothPipeline(StableVideoDiffusionPipeline):

@@ -149,3 +149,59 @@ def test_vae_full_size_against_fixture(cuda):
     print("full-size VAE: moments rel-L2", e_m, "decode rel-L2 (every 4th pixel)", e_d, "norm", n, float(G["decode/norm"][0]))
     assert tuple(y.shape) == (2, 3, 576, 1024)
     assert e_m < TOL_FULL and e_d < TOL_FULL and abs(n / float(G["decode/norm"][0]) - 1) < 5e-3
+
+
+def test_pipeline_image_to_frames(cuda):
+    """The whole reference `__call__` (pipeline...controlnet.py:470-646) with the three lkgd_b200 models registered: image ->
+    CLIP embedding + noise-augmented VAE latents -> CFG Euler-Karras loop -> chunked temporal VAE decode -> frames in [0, 1],
+    against the same chain of oracle modules (reduced UNet, small VAE / CLIP, 4 frames, 3 steps)."""
+    import oracle as O
+    from oracle.scheduler import SVD_SCHEDULER_CONFIG
+    from lkgd_b200.clip import CLIPVisionModelWithProjection
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.preprocess import clip_pixel_values
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    from lkgd_b200.vae import AutoencoderKLTemporalDecoder
+    from test_unet_gpu import _pair as unet_pair
+    ucfg = dict(REDUCED_CONFIG)
+    xdim = ucfg["cross_attention_dim"]
+    ou, pu = unet_pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, ucfg, cuda)
+    ov, pv = _pair(cuda, block_out_channels=(32, 32, 64, 64))
+    ccfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, image_size=224,
+                patch_size=14, projection_dim=xdim, hidden_act="gelu")
+    torch.manual_seed(0)
+    oc = O.CLIPVisionModelWithProjection(**ccfg).eval()
+    pc = CLIPVisionModelWithProjection(**ccfg)
+    pc.load_state_dict(oc.state_dict(), strict=True)
+    pc = pc.to(cuda)
+    Fr, Hh, Ww, n, nas = 4, 128, 192, 3, 0.02
+    image = torch.rand(1, 3, Hh, Ww, generator=torch.Generator().manual_seed(5))
+    noise = torch.randn(1, Fr, 4, Hh // 8, Ww // 8, generator=torch.Generator().manual_seed(6))
+    # ---- the oracle chain, written out as the reference pipeline does it
+    with torch.no_grad():
+        emb = oc(clip_pixel_values(image)).image_embeds.unsqueeze(1)
+        emb = torch.cat([torch.zeros_like(emb), emb])
+        aug = torch.randn(image.shape, generator=torch.Generator().manual_seed(7))
+        lat = ov.encode(2.0 * image - 1.0 + nas * aug).latent_dist.mode()
+        img_lat = torch.cat([torch.zeros_like(lat), lat]).unsqueeze(1).repeat(1, Fr, 1, 1, 1)
+        osched = O.EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG)
+        osched.set_timesteps(n)
+        ids = O.add_time_ids_inference(6, 127, nas, 1)
+        final = O.denoise_loop(ou, osched, noise * osched.init_noise_sigma, img_lat, emb, ids, n, 1.0, 3.0)
+        ref = O.decode_latents(ov, final, Fr, decode_chunk_size=3)
+        ref = (ref.permute(0, 2, 1, 3, 4) / 2 + 0.5).clamp(0, 1)
+    pipe = StableVideoDiffusionPipeline(pu, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG), vae=pv, image_encoder=pc)
+    out = pipe(image=image, height=Hh, width=Ww, num_frames=Fr, num_inference_steps=n, fps=7, noise_aug_strength=nas,
+               latents=noise, generator=torch.Generator().manual_seed(7), decode_chunk_size=3, output_type="pt")
+    e = rel_l2(out.frames, ref)
+    print("image -> frames rel-L2", e)
+    assert tuple(out.frames.shape) == (1, Fr, 3, Hh, Ww) and float(out.frames.min()) >= 0 and float(out.frames.max()) <= 1
+    assert e < 2e-2
+    lat_only = pipe(image=image, height=Hh, width=Ww, num_frames=Fr, num_inference_steps=n, fps=7, noise_aug_strength=nas,
+                    latents=noise, generator=torch.Generator().manual_seed(7)).frames
+    assert rel_l2(lat_only, final) < 2e-2
+    npv = pipe(image=image, height=Hh, width=Ww, num_frames=Fr, num_inference_steps=1, latents=noise, output_type="np").frames
+    assert npv.shape == (1, Fr, Hh, Ww, 3)
+    with pytest.raises(ValueError):
+        StableVideoDiffusionPipeline(pu, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))(image=image, num_frames=Fr)
