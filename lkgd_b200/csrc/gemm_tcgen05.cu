@@ -41,6 +41,7 @@ struct GemmParams {
   int H, W, TW, TH, tw_shift, tiles_w, tiles_h;  // conv output geometry + tile patch (TW a power of two)
   int px_shift, IPT, nimg;             // conv: log2(TW * TH) pixels per image in a tile, images per tile (128 >> px_shift)
   int HW, F, tiles_p;                  // tconv
+  int f_fast, bf_total;                // tconv: tiles ordered (pixel tile, frame) instead of (frame, pixel tile)
   int m_tiles, n_tiles;
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   // epilogue
@@ -84,9 +85,10 @@ __device__ __forceinline__ void tile_origin(const GemmParams& p, int m_tile, Til
     t.c1 = (r % p.tiles_w) * p.TW;   // w0
     t.c2 = (r / p.tiles_w) * p.TH;   // h0
     t.c3 = grp * p.IPT;              // first image of the tile (small images: several images share a tile)
-  } else {  // TCONV3: tile = (bf, tile_p)
-    int bf = m_tile / p.tiles_p;
-    t.c1 = (m_tile % p.tiles_p) * BM;  // p0
+  } else {  // TCONV3: tile = (bf, tile_p); big frames: (tile_p, bf), so that the three frame taps of a pixel tile are read
+            // by tiles that run back to back and meet in L2 instead of being one whole frame of traffic apart
+    int bf = p.f_fast ? m_tile % p.bf_total : m_tile / p.tiles_p;
+    t.c1 = (p.f_fast ? m_tile / p.bf_total : m_tile % p.tiles_p) * BM;  // p0
     t.c2 = bf % p.F;                   // f
     t.c3 = bf / p.F;                   // b
   }
@@ -399,6 +401,10 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
     p.HW = a->HW; p.F = a->F;
     p.tiles_p = (a->HW + BM - 1) / BM;
     p.m_tiles = a->NIMG * a->F * p.tiles_p;
+    p.bf_total = a->NIMG * a->F;
+    // one frame of A above 16 MB (the VAE decoder's 144x256 ... 576x1024 levels; the UNet's largest is 5.9 MB): with the
+    // outputs and residuals written in between, the next frame's taps no longer find this frame in the 126 MB L2
+    p.f_fast = (long long)a->HW * a->K0 * 2 > (16ll << 20) && !getenv("LKGD_TCONV_P_FAST");
     p.ntaps = 3;
     for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = 0; p.tap_dy[t] = t - 1; }
     uint32_t box[4] = {BK, BM, 1, 1};

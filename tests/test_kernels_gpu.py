@@ -160,6 +160,25 @@ def test_gemm_tconv3(cuda, B_, Fr, HW, C, N):
     assert rel_l2(got, ref[..., 0]) < 4e-3
 
 
+@pytest.mark.parametrize("B_,Fr", [(1, 4), (2, 3)])
+def test_gemm_tconv3_big_frames_use_the_frame_fastest_tile_order(cuda, B_, Fr):
+    """One frame of A above 16 MB (the VAE decoder's upper levels): tiles are ordered (pixel tile, frame); same result as the
+    SIMT checker, fused GroupNorm statistics included."""
+    from lkgd_b200 import ops
+    HW, C, N = 131072 + 200, 64, 32                       # 16.8 MB per frame, ragged last pixel tile
+    x = rnd(B_ * Fr * HW, C, dev=cuda)
+    w = rnd(N, 3 * C, dev=cuda, scale=(3 * C) ** -0.5)
+    b = rnd(N, dev=cuda, dtype=torch.float32)
+    r = rnd(B_ * Fr * HW, N, dev=cuda, dtype=torch.float32)
+    out = ops.gemm(x, w, mode=ops.A_TCONV3, tconv=(B_, Fr, HW), bias=b, res1=r, out_f32=True, gn_rows=HW)
+    chk = ops.gemm(x, w, mode=ops.A_TCONV3, tconv=(B_, Fr, HW), bias=b, res1=r, out_f32=True, checker=True)
+    assert rel_l2(out, chk) < 1e-5
+    st, rows = ops.gn_stats_of(out)
+    assert rows == HW and tuple(st.shape) == (B_ * Fr, N, 2)
+    ref = torch.stack([chk.view(B_ * Fr, HW, N).double().sum(1), (chk.view(B_ * Fr, HW, N).double() ** 2).sum(1)], -1)
+    assert torch.allclose(st, ref, rtol=1e-6, atol=1e-3)
+
+
 def test_gemm_large_vs_checker(cuda):
     """SVD level-0 projection shape (M = 2*25*72*128 would be 460800; one CFG half of 14 frames here)."""
     from lkgd_b200 import ops

@@ -34,6 +34,18 @@ SHAPES = [
     ("cond1_k8_silu", "conv", (28, 576, 1024), 16, 8, "silu"),
     ("cond1_k64_silu", "conv", (28, 576, 1024), 16, 64, "silu"),
     ("cond2_k16_silu", "conv", (28, 576, 1024), 16, 16, "silu"),
+    # VAE temporal decoder, 8-frame chunk of 576x1024 frames (lkgd_b200/vae.py): top level, 128 channels   [23..]
+    ("vae_conv128_res32gn", "conv", (8, 576, 1024), 128, 128, "res32gn"),
+    ("vae_conv128_res32", "conv", (8, 576, 1024), 128, 128, "res32"),
+    ("vae_conv128_f32gn", "conv", (8, 576, 1024), 128, 128, "f32gn"),
+    ("vae_conv128_f32", "conv", (8, 576, 1024), 128, 128, "f32"),
+    ("vae_conv128_bf16", "conv", (8, 576, 1024), 128, 128, "bf16"),
+    ("vae_tconv128_res32gn", "tconv", (1, 8, 589824), 128, 128, "res32gn"),
+    ("vae_tconv128_f32gn", "tconv", (1, 8, 589824), 128, 128, "f32gn"),
+    ("vae_tconv128_f32", "tconv", (1, 8, 589824), 128, 128, "f32"),
+    ("vae_tconv128_bf16", "tconv", (1, 8, 589824), 128, 128, "bf16"),
+    ("vae_tconv256_res32gn", "tconv", (1, 8, 147456), 256, 256, "res32gn"),
+    ("vae_conv256_res32gn", "conv", (8, 288, 512), 256, 256, "res32gn"),
 ]
 
 
@@ -58,6 +70,10 @@ def run(shape, iters, flush, ab=None):
     W = (torch.randn(N, taps * K0, device=dev, dtype=bf16, generator=g) * (taps * K0) ** -0.5)
     bias = torch.randn(N, device=dev, generator=g)
     n_out = N // 2 if epi == "geglu" else N
+    gn = epi.endswith("gn")
+    if gn:
+        epi = epi[:-2]
+        kw.update(gn_rows=geo[1] * geo[2] if mode == "conv" else geo[2])
     out_b = 4 if epi in ("f32", "res32") else 2
     bytes_ = M * K0 * 2 + N * taps * K0 * 2 + M * n_out * out_b
     if epi == "geglu":
@@ -98,7 +114,7 @@ def run(shape, iters, flush, ab=None):
     if ab:
         mb = sorted(ts_b)[len(ts_b) // 2]
         extra = {"ms_" + ab: round(mb, 4), "ratio": round(mb / ms, 3)}
-    return dict(**extra, name=name, M=M, N=N, K=taps * K0, epi=epi, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
+    return dict(**extra, name=name, M=M, N=N, K=taps * K0, epi=epi + ("+gn" if gn else ""), ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
                 gbs=round(bytes_ / ms / 1e6, 1))
 
 
