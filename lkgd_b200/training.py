@@ -5,10 +5,13 @@ Mirrors one iteration of the reference training loop ``train_models/train_svd_lo
 EDM noising + input preconditioning (:1503-1530), ``unet(inp_noisy_latents, timesteps, encoder_hidden_states,
 [domain_features, flow_features,] added_time_ids=...)`` (:1634-1642), the v-prediction wrapper and weighted MSE
 (:1651-1672), ``accelerator.backward`` (:1683), ``clip_grad_norm_`` (:1684-1686), ``optimizer.step`` (:1687), and the
-DDP gradient all-reduce that ``accelerator.prepare`` installs (:1300-1302).  Trainable parameters are the LoRA pairs
-on ``temporal_transformer_blocks.*.attn1.to_{q,k,v}`` (:1081-1088); every other weight is frozen, so the backward only
-propagates data gradients (GEMMs / convolutions re-run with transposed, tap-flipped weights on the same tcgen05
-kernel) plus the two skinny weight-gradient GEMMs per LoRA pair.
+DDP gradient all-reduce that ``accelerator.prepare`` installs (:1300-1302).  Trainable parameters are the LoRA pairs the
+reference's adapter configurations create: ``temporal_transformer_blocks.*.attn1.to_{q,k,v}`` (:1081-1088, the default) or
+every attention projection ``to_q / to_k / to_v / to_out.0`` of the spatial and temporal blocks, attn1 and attn2 (:1091-1096,
+run_models/run_inference_flow_lora.py:326-331); every other weight is frozen, so the backward only propagates data gradients
+(GEMMs / convolutions re-run with transposed, tap-flipped weights on the same tcgen05 kernel) plus the two skinny
+weight-gradient GEMMs per LoRA pair; the KV-length-1 cross-attention adapters get theirs from the gradient of the
+per-sample cross vectors.
 
 There is no autograd here and no PyTorch compute: the backward schedule is written out per block, the gradient of the
 residual stream is kept in fp32 like the forward stream, GEMM operands are bf16.
@@ -46,21 +49,57 @@ def res_train_weights(p: PackedResBlock) -> NS:
     return p._tw
 
 
+SITES = ("s_qkv", "s_out", "t_qkv", "t_out")     # projections whose LoRA adapters can be trained (self-attention q|k|v, out)
+
+
+def site_modules(p: PackedTransformer, name: str):
+    """The nn modules behind a packed projection, in the row order of its weight."""
+    blk = (p.src.transformer_blocks if name[0] == "s" else p.src.temporal_transformer_blocks)[0]
+    a = blk.attn1
+    return (a.to_q, a.to_k, a.to_v) if name.endswith("qkv") else (a.to_out[0],)
+
+
 def tr_train_weights(p: PackedTransformer) -> NS:
     if getattr(p, "_tw", None) is None:
         if p.s_joint is not None or p.t_joint is not None:
             raise NotImplementedError("training through the joint-attention branch is not built (inference only)")
-        for d in (p.proj_in, p.proj_out, p.s_qkv, p.s_out, p.s_ff2, p.t_ffin2, p.t_out, p.t_ff2, p.s_ff1, p.t_ffin1,
-                  p.t_ff1):
+        for d in (p.proj_in, p.proj_out, p.s_ff2, p.t_ffin2, p.t_ff2, p.s_ff1, p.t_ffin1, p.t_ff1):
             if d.lora_a is not None:
-                raise NotImplementedError("training supports LoRA on the temporal attn1 q/k/v projections only "
-                                          "(the reference's adapter config, train_svd_lora.py:1081-1088)")
+                raise NotImplementedError("training supports LoRA on the attention projections to_q / to_k / to_v / "
+                                          "to_out.0 (the reference's adapter configs, train_svd_lora.py:1081-1096), not on "
+                                          "proj_in / proj_out / the feed-forward layers")
         p._tw = NS(proj_in=_t(p.proj_in.w), proj_out=_t(p.proj_out.w), s_qkv=_t(p.s_qkv.w), s_out=_t(p.s_out.w),
                    s_ff1=_t(p.s_ff1.w), s_ff2=_t(p.s_ff2.w), t_ffin1=_t(p.t_ffin1.w), t_ffin2=_t(p.t_ffin2.w),
                    t_qkv=_t(p.t_qkv.w), t_out=_t(p.t_out.w), t_ff1=_t(p.t_ff1.w), t_ff2=_t(p.t_ff2.w),
-                   lora_aT=None if p.t_qkv.lora_a is None else _t(p.t_qkv.lora_a),
-                   lora_bT=None if p.t_qkv.lora_b is None else _t(p.t_qkv.lora_b))
+                   lora={n: (_t(getattr(p, n).lora_a), _t(getattr(p, n).lora_b)) for n in SITES
+                         if getattr(p, n).lora_a is not None})
     return p._tw
+
+
+def _lora_fwd(S, name: str, x, d, **kw):
+    """y = x W^T + b [+ (x A^T)(s B)^T]; keeps the projection's input and the down-projected rows for the weight gradients."""
+    if d.lora_a is None:
+        return ops.gemm(x, d.w, bias=d.b, **kw)
+    t = ops.gemm(x, d.lora_a)
+    setattr(S, name + "_x", x)
+    setattr(S, name + "_t", t)
+    return ops.gemm(x, d.w, bias=d.b, A1=t, Bw1=d.lora_b, **kw)
+
+
+def _lora_bwd(S, name: str, dy, d, wT, tw, grads):
+    """bf16 gradient of a projection's output -> bf16 gradient of its input; accumulates the adapters' fp32 weight
+    gradients: dB_i += s dy_i^T t_i, dA_i += (dy_i s B_i)^T x."""
+    if d.lora_a is None:
+        return ops.gemm(dy, wT)
+    aT, bT = tw.lora[name]
+    dt = ops.gemm(dy, bT)                                         # [M, n_adapters * r_pad]
+    if grads is not None:
+        x, t = getattr(S, name + "_x"), getattr(S, name + "_t")
+        for ad in grads.get(name, ()):
+            rs = slice(ad["r_lo"], ad["r_lo"] + ad["r"])
+            ops.gemm_tn(dy[:, ad["n_lo"]:ad["n_hi"]], t[:, rs], ad["B"], alpha=ad["scaling"])
+            ops.gemm_tn(dt[:, rs], x, ad["A"])
+    return ops.gemm(dy, wT, A1=dt, Bw1=aT)
 
 
 # ------------------------------------------------------------------------------------------------- resblock
@@ -130,10 +169,10 @@ def transformer_fwd(p: PackedTransformer, x, g: Geom, cond: Conditioning, tctx_m
     h, S.st0 = ops.groupnorm(x, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False, return_stats=True)
     S.h_a = dense(h, p.proj_in, out_f32=True)
     n = ops.layernorm(S.h_a, p.s_ln1.g, p.s_ln1.b, p.s_ln1.eps)
-    S.s_qkv = dense(n, p.s_qkv)
+    S.s_qkv = _lora_fwd(S, "s_qkv", n, p.s_qkv)
     S.s_o, S.s_lse = ops.attention(S.s_qkv[:, :C], S.s_qkv[:, C:2 * C], S.s_qkv[:, 2 * C:], n_img=g.BF, heads=p.heads,
                                    d=p.d, Nq=g.HW, Nk=g.HW, return_lse=True)
-    S.h_b = dense(S.s_o, p.s_out, res1=S.h_a, out_f32=True)
+    S.h_b = _lora_fwd(S, "s_out", S.s_o, p.s_out, res1=S.h_a, out_f32=True)
     n = ops.layernorm(S.h_b, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross), rv=g.rv(RV_BATCH),
                       sum_out=S.h_b)
     S.s_pre, S.xs = _ff_fwd(n, p.s_ff1, p.s_ff2, res1=S.h_b, out_f32=True)
@@ -141,16 +180,10 @@ def transformer_fwd(p: PackedTransformer, x, g: Geom, cond: Conditioning, tctx_m
     n = ops.layernorm(S.xs, p.t_lnin.g, p.t_lnin.b, p.t_lnin.eps, addvec=p.pos_emb(g.F), rv=g.rv(RV_FRAMEPOS),
                       sum_out=S.t0)
     S.t_pre_in, S.t_a = _ff_fwd(n, p.t_ffin1, p.t_ffin2, res1=S.t0, out_f32=True)
-    S.t_n1 = ops.layernorm(S.t_a, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
-    q = p.t_qkv
-    if q.lora_a is not None:
-        S.t_tl = ops.gemm(S.t_n1, q.lora_a)
-        S.t_qkv = ops.gemm(S.t_n1, q.w, bias=q.b, A1=S.t_tl, Bw1=q.lora_b)
-    else:
-        S.t_tl = None
-        S.t_qkv = ops.gemm(S.t_n1, q.w, bias=q.b)
+    n = ops.layernorm(S.t_a, p.t_ln1.g, p.t_ln1.b, p.t_ln1.eps)
+    S.t_qkv = _lora_fwd(S, "t_qkv", n, p.t_qkv)
     a = ops.attention_temporal(S.t_qkv, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
-    S.t_b = dense(a, p.t_out, res1=S.t_a, out_f32=True)
+    S.t_b = _lora_fwd(S, "t_out", a, p.t_out, res1=S.t_a, out_f32=True)
     S.n_tctx = cond.ctx_t.shape[0]
     n = ops.layernorm(S.t_b, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
                       rv=(tctx_mode, g.HW, g.F, S.n_tctx), sum_out=S.t_b)
@@ -167,8 +200,8 @@ def _ff_bwd(gb, pre, w2T, w1T):
 def transformer_bwd(p: PackedTransformer, S, G: torch.Tensor, g: Geom, tctx_mode: int, lora_grads=None,
                     cross_grads=None):
     """G: fp32 gradient of the transformer output; overwritten with the gradient of its input ``x`` and returned.
-    ``lora_grads``: dict with fp32 ``A`` [3, r, C] and ``B`` [3, C, r] accumulators of this layer's q/k/v adapters
-    (+ ``scaling``).  ``cross_grads``: (d_xs [B, C] view, d_xt [n_ctx, C] view) accumulators of the two KV-length-1
+    ``lora_grads``: {site name: [adapter dicts with the fp32 ``A`` [r, K] / ``B`` [N_i, r] accumulators, the adapter's row
+    range in the projection and its column range in the stacked down-projection, ``scaling``]} of this layer.  ``cross_grads``: (d_xs [B, C] view, d_xt [n_ctx, C] view) accumulators of the two KV-length-1
     cross-attention vectors (LKGD conditioning gradient)."""
     tw = tr_train_weights(p)
     M_, C = G.shape
@@ -181,20 +214,9 @@ def transformer_bwd(p: PackedTransformer, S, G: torch.Tensor, g: Geom, tctx_mode
     ops.layernorm_bwd(S.t_b, _ff_bwd(gb, S.t_pre, tw.t_ff2, tw.t_ff1), p.t_ln3.g, p.t_ln3.eps, Gt, g_bf16=gb)
     if cross_grads is not None:
         ops.colsum_grouped(Gt, S.n_tctx, (tctx_mode, g.HW, g.F, S.n_tctx), out=cross_grads[1])
-    da = ops.gemm(gb, tw.t_out)
+    da = _lora_bwd(S, "t_out", gb, p.t_out, tw.t_out, tw, lora_grads)
     dqkv = ops.attention_temporal_bwd(S.t_qkv, da, B=g.B, F=g.F, HW=g.HW, heads=p.heads, d=p.d)
-    if S.t_tl is not None:
-        dtl = ops.gemm(dqkv, tw.lora_bT)                          # [M, 3 r_pad]
-        if lora_grads is not None:
-            r = lora_grads["A"].shape[1]
-            r_pad = S.t_tl.shape[1] // 3
-            for i in range(3):
-                ops.gemm_tn(dqkv[:, i * C:(i + 1) * C], S.t_tl[:, i * r_pad:i * r_pad + r], lora_grads["B"][i],
-                            alpha=lora_grads["scaling"])
-                ops.gemm_tn(dtl[:, i * r_pad:i * r_pad + r], S.t_n1, lora_grads["A"][i])
-        dn = ops.gemm(dqkv, tw.t_qkv, A1=dtl, Bw1=tw.lora_aT)
-    else:
-        dn = ops.gemm(dqkv, tw.t_qkv)
+    dn = _lora_bwd(S, "t_qkv", dqkv, p.t_qkv, tw.t_qkv, tw, lora_grads)
     ops.layernorm_bwd(S.t_a, dn, p.t_ln1.g, p.t_ln1.eps, Gt, g_bf16=gb)
     ops.layernorm_bwd(S.t0, _ff_bwd(gb, S.t_pre_in, tw.t_ffin2, tw.t_ffin1), p.t_lnin.g, p.t_lnin.eps, Gt)
     # ---- spatial block: d xs = d t0 + alpha * d mix
@@ -204,11 +226,12 @@ def transformer_bwd(p: PackedTransformer, S, G: torch.Tensor, g: Geom, tctx_mode
     ops.layernorm_bwd(S.h_b, _ff_bwd(gb, S.s_pre, tw.s_ff2, tw.s_ff1), p.s_ln3.g, p.s_ln3.eps, Gs, g_bf16=gb)
     if cross_grads is not None:
         ops.colsum_grouped(Gs, g.B, g.rv(RV_BATCH), out=cross_grads[0])
-    da = ops.gemm(gb, tw.s_out)
+    da = _lora_bwd(S, "s_out", gb, p.s_out, tw.s_out, tw, lora_grads)
     dqkv = torch.empty((M_, 3 * C), device=dev, dtype=bf16)
     ops.attention_bwd(S.s_qkv[:, :C], S.s_qkv[:, C:2 * C], S.s_qkv[:, 2 * C:], S.s_o, da, S.s_lse, dqkv[:, :C],
                       dqkv[:, C:2 * C], dqkv[:, 2 * C:], n_img=g.BF, heads=p.heads, d=p.d, N=g.HW)
-    ops.layernorm_bwd(S.h_a, ops.gemm(dqkv, tw.s_qkv), p.s_ln1.g, p.s_ln1.eps, Gs, g_bf16=gb)
+    ops.layernorm_bwd(S.h_a, _lora_bwd(S, "s_qkv", dqkv, p.s_qkv, tw.s_qkv, tw, lora_grads), p.s_ln1.g, p.s_ln1.eps, Gs,
+                      g_bf16=gb)
     dh0 = ops.gemm(gb, tw.proj_in)
     ops.groupnorm_bwd(S.x, dh0, S.st0, p.norm.g, p.norm.b, p.norm.eps, NS=g.BF, R=g.HW, silu=False, out1=G, acc1=True)
     return G
@@ -343,44 +366,81 @@ class LoraTrainer:
         self._pk = pk            # the trainer owns this pack: gradient slots are keyed by its layers (see forward_backward)
         self.layers = [a for blk in pk.down if blk[1] for a in blk[1]] + list(pk.mid[1]) + \
                       [a for blk in pk.up if blk[1] for a in blk[1]]
-        mods = []
-        for p in self.layers:
-            attn = p.src.temporal_transformer_blocks[0].attn1
-            trio = (attn.to_q, attn.to_k, attn.to_v)
-            if any(isinstance(m, M.LoraLinear) and (len(m.lora_A) != 1 or m.masked_forward) for m in trio):
-                raise NotImplementedError("training supports ONE unmasked adapter per layer")
-            if not all(isinstance(m, M.LoraLinear) and not m.merged for m in trio):
-                raise ValueError("every temporal attn1 q/k/v projection must carry an unmerged LoRA adapter "
-                                 "(unet.add_lora(r) with the default target)")
-            mods.append(trio)
-        r = mods[0][0].r
         dev = unet.device
+
+        def trainable(m):
+            if not isinstance(m, M.LoraLinear) or m.merged:
+                return False
+            if len(m.lora_A) != 1 or m.masked_forward:
+                raise NotImplementedError("training supports ONE unmasked adapter per layer")
+            return True
+
+        # ---- what is trainable: (layer, site, adapter geometry) for the self-attention projections and the KV-length-1
+        # cross-attention projections (to_q / to_k of a one-key attention receive exactly zero gradient, but they are
+        # optimizer state - weight decay - in the reference, so they are kept)
+        plan, n = [], 0
+        for p in self.layers:
+            tr_train_weights(p)                # raises for adapters on projections the backward does not cover
+            for name in SITES:
+                d = getattr(p, name)
+                mods = site_modules(p, name)
+                if d.lora_a is None:
+                    continue
+                r_pad = d.lora_a.shape[0] // len(mods)
+                n_rows = d.w.shape[0] // len(mods)
+                for i, m in enumerate(mods):
+                    if trainable(m):
+                        plan.append(("site", p, name, m, i * n_rows, (i + 1) * n_rows, i * r_pad))
+                        n += m.r * (m.in_features + m.out_features)
+            for key in ("s_cross", "t_cross"):
+                attn = getattr(p, key)._attn
+                for role, m in (("q", attn.to_q), ("k", attn.to_k), ("v", attn.to_v), ("o", attn.to_out[0])):
+                    if trainable(m):
+                        plan.append(("cross", p, key, m, role))
+                        n += m.r * (m.in_features + m.out_features)
+        if not plan:
+            raise ValueError("no trainable LoRA adapter found: call unet.add_lora(r) / add_adapter(config) first "
+                             "(reference train_svd_lora.py:1081-1102)")
         # the latent-knowledge block's 'quaternion' parameters are trained with the adapters (train_svd_lora.py:1068-1073)
         self.lk_params = [(n_, p_) for n_, p_ in unet.named_parameters() if "quaternion" in n_] \
             if hasattr(unet, "_context_train") else []
-        n = sum(3 * 2 * r * p.c for p in self.layers) + sum(p_.numel() for _, p_ in self.lk_params)
+        n += sum(p_.numel() for _, p_ in self.lk_params)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.sumsq = torch.zeros((), device=dev, dtype=torch.float64)
-        self.slots: Dict[int, Dict] = {}
+        self.slots: Dict[int, Dict] = {}           # id(layer) -> {site: [adapter dicts]}
+        self.cross: List[Dict] = []                # cross-attention adapters, one dict per (layer, s/t cross)
+        self.adapters: List[Dict] = []             # every adapter, flat-buffer order
         off = 0
         with torch.no_grad():
-            for p, trio in zip(self.layers, mods):
-                C = p.c
-                pa = self.flat_p[off:off + 3 * r * C].view(3, r, C)
-                ga = self.flat_g[off:off + 3 * r * C].view(3, r, C)
-                off += 3 * r * C
-                pb = self.flat_p[off:off + 3 * C * r].view(3, C, r)
-                gb = self.flat_g[off:off + 3 * C * r].view(3, C, r)
-                off += 3 * C * r
-                for i, m in enumerate(trio):
-                    a, b = m.lora_A[m.adapter_name].weight, m.lora_B[m.adapter_name].weight
-                    pa[i].copy_(a)
-                    pb[i].copy_(b)
-                    a.data, b.data = pa[i], pb[i]          # the module's parameters now alias the flat buffer
-                self.slots[id(p)] = dict(A=ga, B=gb, pA=pa, pB=pb, scaling=float(trio[0].scaling), r=r)
+            cross_by = {}
+            for e in plan:
+                m = e[3]
+                r, K, N = m.r, m.in_features, m.out_features
+                ad = dict(module=m, r=r, scaling=float(m.scaling))
+                for nm, shape in (("A", (r, K)), ("B", (N, r))):
+                    k = r * K if nm == "A" else N * r
+                    ad["p" + nm] = self.flat_p[off:off + k].view(shape)
+                    ad[nm] = self.flat_g[off:off + k].view(shape)
+                    off += k
+                a_, b_ = m.lora_A[m.adapter_name].weight, m.lora_B[m.adapter_name].weight
+                ad["pA"].copy_(a_)
+                ad["pB"].copy_(b_)
+                a_.data, b_.data = ad["pA"], ad["pB"]          # the module's parameters now alias the flat buffer
+                self.adapters.append(ad)
+                if e[0] == "site":
+                    _, p, name, _, n_lo, n_hi, r_lo = e
+                    ad.update(n_lo=n_lo, n_hi=n_hi, r_lo=r_lo, dense=getattr(p, name), tw=tr_train_weights(p).lora[name])
+                    self.slots.setdefault(id(p), {}).setdefault(name, []).append(ad)
+                else:
+                    _, p, key, _, role = e
+                    c = cross_by.get((id(p), key))
+                    if c is None:
+                        c = cross_by[(id(p), key)] = dict(layer=p, key=key, pc=getattr(p, key), ads={})
+                        self.cross.append(c)
+                    c["ads"][role] = ad
             self.lk_grads: Dict[str, torch.Tensor] = {}
             for name, prm in self.lk_params:
                 k = prm.numel()
@@ -394,32 +454,66 @@ class LoraTrainer:
 
     # ---- fp32 master parameters -> the bf16 operands the GEMMs read (forward: A_cat, B_blk; backward: transposes)
     def repack(self):
-        for p in self.layers:
-            s = self.slots[id(p)]
-            tw = tr_train_weights(p)
-            C, r = p.c, s["r"]
-            r_pad = p.t_qkv.lora_a.shape[0] // 3
-            for i in range(3):
-                ops.cast2d_bf16(s["pA"][i], p.t_qkv.lora_a[i * r_pad:i * r_pad + r])
-                ops.cast2d_bf16(s["pA"][i].t(), tw.lora_aT[:, i * r_pad:i * r_pad + r])
-                ops.cast2d_bf16(s["pB"][i], p.t_qkv.lora_b[i * C:(i + 1) * C, i * r_pad:i * r_pad + r], alpha=s["scaling"])
-                ops.cast2d_bf16(s["pB"][i].t(), tw.lora_bT[i * r_pad:i * r_pad + r, i * C:(i + 1) * C],
-                                alpha=s["scaling"])
+        for ad in self.adapters:
+            if "dense" not in ad:
+                continue
+            d, (aT, bT), r = ad["dense"], ad["tw"], ad["r"]
+            rs = slice(ad["r_lo"], ad["r_lo"] + r)
+            ns = slice(ad["n_lo"], ad["n_hi"])
+            ops.cast2d_bf16(ad["pA"], d.lora_a[rs])
+            ops.cast2d_bf16(ad["pA"].t(), aT[:, rs])
+            ops.cast2d_bf16(ad["pB"], d.lora_b[ns, rs], alpha=ad["scaling"])
+            ops.cast2d_bf16(ad["pB"].t(), bT[rs, ns], alpha=ad["scaling"])
+        for c in self.cross:
+            wv, wo = self._cross_weights(c)
+            c["pc"].wov.copy_(wo @ wv)                     # a view of the batched [sum C, D] cross-vector matrix
         if self.lk_params and not torch.cuda.is_current_stream_capturing():
             self.unet._lk = None          # dense matrices of the latent-knowledge block are rebuilt from the parameters
+
+    @staticmethod
+    def _cross_weights(c):
+        """Effective fp32 to_v [C, D] and to_out [C, C] of a KV-length-1 cross-attention: W + s B A (host-side weight
+        preparation on [C, D]-sized matrices, as at pack time)."""
+        attn = c["pc"]._attn
+        out = []
+        for role, m in (("v", attn.to_v), ("o", attn.to_out[0])):
+            w = (m.base_layer if isinstance(m, M.LoraLinear) else m).weight.detach().float()
+            ad = c["ads"].get(role)
+            if ad is not None:
+                w = w + ad["scaling"] * (ad["pB"] @ ad["pA"])
+            elif isinstance(m, M.LoraLinear) and not m.merged:
+                raise NotImplementedError("frozen, unmerged adapter next to trained ones on a cross-attention")
+            out.append(w)
+        return out
+
+    def _cross_backward(self, cond: Conditioning, d_xs: torch.Tensor, d_xt: torch.Tensor):
+        """Weight gradients of the cross-attention adapters from the gradients of the per-sample cross vectors
+        xs = Wo (Wv ctx) + bo: rank-B outer products on [C, r]-sized matrices (B = batch; negligible next to the step, host-
+        side tensor algebra like the latent-knowledge block's)."""
+        for c in self.cross:
+            pc = c["pc"]
+            spatial = c["key"] == "s_cross"
+            ctx = (cond.ctx if spatial else cond.ctx_t)[:, 0].float()                       # [B, D]
+            dx = (d_xs if spatial else d_xt)[:, pc.off:pc.off + pc.wov.shape[0]]            # [B, C]
+            wv, wo = self._cross_weights(c)
+            u = ctx @ wv.t()                                                                 # [B, C] = to_v(ctx)
+            du = dx @ wo                                                                     # [B, C]
+            for role, lhs, rhs in (("o", dx, u), ("v", du, ctx)):                            # dW = lhs^T rhs
+                ad = c["ads"].get(role)
+                if ad is not None:
+                    ad["B"].add_(lhs.t() @ (rhs @ ad["pA"].t()), alpha=ad["scaling"])
+                    ad["A"].add_((lhs @ ad["pB"]).t() @ rhs, alpha=ad["scaling"])
 
     def named_grads(self):
         """(qualified parameter name, fp32 gradient view) in the reference's naming
         (``...attn1.to_q.lora_A.<adapter>.weight``; train_svd_lora_train.txt)."""
         names = {id(m): n for n, m in self.unet.named_modules()}
         out = []
-        for p in self.layers:
-            attn = p.src.temporal_transformer_blocks[0].attn1
-            s = self.slots[id(p)]
-            for i, m in enumerate((attn.to_q, attn.to_k, attn.to_v)):
-                base = names[id(m)]
-                out.append((f"{base}.lora_A.{m.adapter_name}.weight", s["A"][i]))
-                out.append((f"{base}.lora_B.{m.adapter_name}.weight", s["B"][i]))
+        for ad in self.adapters:
+            m = ad["module"]
+            base = names[id(m)]
+            out.append((f"{base}.lora_A.{m.adapter_name}.weight", ad["A"]))
+            out.append((f"{base}.lora_B.{m.adapter_name}.weight", ad["B"]))
         return out + list(self.lk_grads.items())
 
     def state_tensors(self):
@@ -450,7 +544,7 @@ class LoraTrainer:
         return checkpoint.load_state(self, path, lora_name or self._adapter_name(), **kw)
 
     def _adapter_name(self) -> str:
-        return self.layers[0].src.temporal_transformer_blocks[0].attn1.to_q.adapter_name
+        return self.adapters[0]["module"].adapter_name
 
     def _graph_stale(self):
         """Parameters restored from a checkpoint are copied INTO the flat buffer the captured graphs read, so the graphs
@@ -483,13 +577,14 @@ class LoraTrainer:
         lk_saved = cross = None
         if self.lk_params:
             ctx, lk_saved = unet._context_train(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
+        else:
+            ctx = unet._context(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
+        if self.lk_params or self.cross:
             d_xs = torch.zeros((B, pk.xs_w.shape[0]), device=dev, dtype=f32)    # gradients of every KV=1 cross-attention
             d_xt = torch.zeros((B, pk.xt_w.shape[0]), device=dev, dtype=f32)    # vector, all layers side by side
 
             def cross(p):
                 return (d_xs[:, p.s_cross.off:p.s_cross.off + p.c], d_xt[:, p.t_cross.off:p.t_cross.off + p.c])
-        else:
-            ctx = unet._context(encoder_hidden_states.to(dev), *[e.to(dev) for e in extra])
         emb = pk.time_embedding(timesteps, added_time_ids.to(dev))
         cond = Conditioning(pk, emb, ctx)
         g = Geom(B, F, h, w)
@@ -497,6 +592,8 @@ class LoraTrainer:
         pred = graph.forward(x_in, g, cond)
         loss, dpred = ops.edm_loss(pred, noisy, latents, sigmas, pk.conv_out_w.shape[0])
         graph.backward(dpred, lora_grads=self.slots, cross_grads=cross)
+        if self.cross:
+            self._cross_backward(cond, d_xs, d_xt)
         if lk_saved is not None:
             # cross vectors = ctx @ W^T + b for the concatenated [sum C, 1024] matrices: fold back onto the context
             dctx = ops.small_linear_bwd(d_xs, pk.xs_w)

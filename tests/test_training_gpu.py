@@ -96,6 +96,63 @@ def test_lora_gradients_three_levels_d64(cuda):
     _compare(tr, ref_grads, ref_loss, loss)
 
 
+@pytest.mark.parametrize("target", ["all_attention", "self_attention_out_only"])
+def test_lora_gradients_on_every_attention_projection(cuda, target):
+    """The reference's other adapter configuration (train_svd_lora.py:1091-1096 commented alternative,
+    run_models/run_inference_flow_lora.py:326-331): LoraConfig(target_modules=["to_k","to_q","to_v","to_out.0"]) puts adapters
+    on EVERY attention projection - spatial and temporal, attn1 and attn2.  Gradients of all of them against autograd through
+    the oracle: fused q|k|v and out-projection sites of both self-attentions, to_v / to_out of the KV-length-1
+    cross-attentions (through the per-sample cross vectors), exactly zero for the cross-attentions' to_q / to_k (one key:
+    the softmax is 1 whatever the query)."""
+    import oracle as O
+    from oracle.lora import ALL_ATTN_PROJ
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    torch.manual_seed(0)
+    o = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    p = UNetSpatioTemporalConditionControlNetModel(**cfg)
+    if target == "all_attention":
+        O.add_lora(o, 8, target=ALL_ATTN_PROJ)
+        hit = p.add_adapter(dict(r=8, lora_alpha=8, init_lora_weights="gaussian",
+                                 target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+        assert len(hit) == 6 * 2 * 2 * 4
+    else:
+        O.add_lora(o, 4, target=r".*attn1\.to_out\.0$")
+        hit = p.add_adapter(dict(r=4, lora_alpha=4, init_lora_weights="gaussian", target_modules=["attn1.to_out.0"]))
+        assert len(hit) == 6 * 2
+    from test_unet_gpu import _randomise_zero_inits
+    _randomise_zero_inits(o)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if "lora_B" in n:
+                prm.copy_((torch.randn(prm.shape, generator=torch.Generator().manual_seed(len(n))) * 0.05)
+                          .to(torch.bfloat16).float())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    B = 2
+    lat, noise, cond, ctx, sig = _train_inputs(B, 8, 16, 16, 32)
+    ids = O.add_time_ids_training(5, 127, 0.02, B)
+    ref_loss, ref_grads = _oracle_step(o, lat, noise, cond, ctx, sig, ids)
+    tr = LoraTrainer(p)
+    loss = tr.forward_backward(lat.to(cuda), noise.to(cuda), sig.to(cuda), cond.to(cuda), ctx.to(cuda), ids.to(cuda))
+    got = dict(tr.named_grads())
+    dead = [n for n in ref_grads if ".attn2.to_q." in n or ".attn2.to_k." in n]
+    if target == "all_attention":
+        assert len(dead) == 6 * 2 * 2 * 2
+    for n in dead:                                    # zero in the oracle (up to fp32 noise of a constant softmax), zero here
+        assert float(ref_grads[n].abs().max()) < 1e-6 and float(got[n].abs().max()) == 0.0
+        del ref_grads[n], got[n]
+    tr.named_grads = lambda: list(got.items())
+    _compare(tr, ref_grads, ref_loss, loss)
+    # optimizer steps move every live adapter and reduce the loss
+    tr2 = LoraTrainer(p, lr=2e-3, weight_decay=0.0)
+    args = [t.to(cuda) for t in (lat, noise, sig, cond, ctx, ids)]
+    losses = [float(tr2.train_step(*args)) for _ in range(5)]
+    print(target, "losses", losses)
+    assert losses[-1] < losses[0]
+
+
 def test_train_steps_reduce_loss_and_alias_parameters(cuda):
     """A few optimizer steps on one fixed batch: the loss must fall, and the module's LoRA parameters (state_dict)
     must be the tensors the optimizer kernel updates."""
@@ -118,8 +175,8 @@ def test_train_steps_reduce_loss_and_alias_parameters(cuda):
     # the forward the sampler runs sees the trained adapters: packed operands were refreshed from the parameters
     pk = p.packed()
     lay = tr.layers[0]
-    s = tr.slots[id(lay)]
-    assert torch.equal(lay.t_qkv.lora_a[:s["r"]], s["pA"][0].to(torch.bfloat16))
+    ad = tr.slots[id(lay)]["t_qkv"][0]
+    assert torch.equal(lay.t_qkv.lora_a[:ad["r"]], ad["pA"].to(torch.bfloat16))
 
 
 def test_lkgd_quaternion_and_lora_gradients(cuda):
