@@ -414,7 +414,7 @@ def run_train(args):
                          "kernel_ms_per_step": gm["ms"], "share_of_step": gm["ms"] / total_ms,
                          "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -447,10 +447,35 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "denoise_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's "NCCL version ..." banner when the box
+    exports NCCL_DEBUG=VERSION, seen on the 8-GPU boxes): everything written to fd 1 from here on goes to stderr, and
+    `emit` writes the result line to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -666,7 +691,7 @@ def main():
             except Exception as ex:  # the CPU leg must never sink the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "denoise_steps/s", "cores": os.cpu_count(),
                                         "kind": "port", "sample": f"failed: {ex!r}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
