@@ -599,7 +599,7 @@ extern "C" int lkgd_attention_bwd(const void* q, int32_t ldq, const void* k, int
                                   const void* o, const void* dO, int32_t ldo, const float* lse, void* dq, int32_t lddq,
                                   void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t n_img, int32_t heads,
                                   int32_t d, int32_t N, float scale, void* workspace, size_t ws_bytes, void* stream) {
-  if (n_img <= 0 || heads <= 0 || N <= 0 || (d != 16 && d != 32 && d != 64)) return LKGD_ESHAPE;
+  if (n_img <= 0 || heads <= 0 || N <= 0 || (d != 16 && d != 32 && d != 64 && d != 128)) return LKGD_ESHAPE;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || lddq % 8 || lddk % 8 || lddv % 8) return LKGD_EALIGN;
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) || !aligned16(dO) || !aligned16(dq) ||
       !aligned16(dk) || !aligned16(dv))
@@ -624,6 +624,7 @@ extern "C" int lkgd_attention_bwd(const void* q, int32_t ldq, const void* k, int
   switch (d) {
     case 16: return launch_attn_bwd<16>(p, n_img, st);
     case 32: return launch_attn_bwd<32>(p, n_img, st);
+    case 128: return launch_attn_bwd<128>(p, n_img, st);   // the reference-default heads (5,10,10,20): d = 128 at level 2
     default: return launch_attn_bwd<64>(p, n_img, st);
   }
 }
@@ -644,11 +645,14 @@ extern "C" int lkgd_attention_temporal_bwd(const void* qkv, const void* dO, void
   if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM(64));
     if (e != cudaSuccess) return set_cuda_error(e);
+    e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM(128));
+    if (e != cudaSuccess) return set_cuda_error(e);
   }
   switch (d) {
     case 16: attn_temporal_bwd_kernel<16><<<grid, 128, TB_SMEM(16), st>>>(x, g, o, B, F, HW, heads, scale, sl2); break;
     case 32: attn_temporal_bwd_kernel<32><<<grid, 128, TB_SMEM(32), st>>>(x, g, o, B, F, HW, heads, scale, sl2); break;
     case 64: attn_temporal_bwd_kernel<64><<<grid, 128, TB_SMEM(64), st>>>(x, g, o, B, F, HW, heads, scale, sl2); break;
+    case 128: attn_temporal_bwd_kernel<128><<<grid, 128, TB_SMEM(128), st>>>(x, g, o, B, F, HW, heads, scale, sl2); break;
     default: return LKGD_ESHAPE;
   }
 #undef TB_SMEM

@@ -181,7 +181,8 @@ def test_tconv3_dgrad_via_gemm(cuda):
 
 
 # ------------------------------------------------------------------------------------------------- attention backward
-@pytest.mark.parametrize("n_img,heads,d,N", [(2, 2, 64, 200), (1, 3, 16, 64), (3, 1, 32, 130), (1, 5, 64, 640)])
+@pytest.mark.parametrize("n_img,heads,d,N", [(2, 2, 64, 200), (1, 3, 16, 64), (3, 1, 32, 130), (1, 5, 64, 640),
+                                             (2, 2, 128, 200), (1, 3, 128, 576)])     # d = 128: reference-default heads
 def test_attention_bwd(cuda, n_img, heads, d, N):
     from lkgd_b200 import ops
     C = heads * d
@@ -206,7 +207,8 @@ def test_attention_bwd(cuda, n_img, heads, d, N):
         assert rel_l2(split(got), ref) < 1.2e-2, name
 
 
-@pytest.mark.parametrize("B_,Fr,HW,heads,d", [(1, 14, 40, 2, 64), (2, 8, 33, 4, 16), (1, 25, 17, 1, 32), (1, 32, 8, 2, 64)])
+@pytest.mark.parametrize("B_,Fr,HW,heads,d", [(1, 14, 40, 2, 64), (2, 8, 33, 4, 16), (1, 25, 17, 1, 32), (1, 32, 8, 2, 64),
+                                                  (1, 14, 33, 2, 128), (2, 25, 9, 1, 128)])
 def test_attention_temporal_bwd(cuda, B_, Fr, HW, heads, d):
     from lkgd_b200 import ops
     C = heads * d

@@ -153,6 +153,29 @@ def test_lora_gradients_on_every_attention_projection(cuda, target):
     assert losses[-1] < losses[0]
 
 
+def test_lora_gradients_with_128_wide_heads(cuda):
+    """The reference-default head layout (5,10,10,20) gives 128-wide heads at level 2
+    (models/unet_spatio_temporal_condition_controlnet.py:93): forward with log-sum-exp and both backward kernels at d = 128."""
+    import oracle as O
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(sample_size=16, in_channels=8, out_channels=4,
+               down_block_types=("CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+               up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal"),
+               block_out_channels=(128, 128), addition_time_embed_dim=32, projection_class_embeddings_input_dim=96,
+               layers_per_block=1, cross_attention_dim=64, transformer_layers_per_block=1,
+               num_attention_heads=(1, 1), num_frames=5)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda,
+                 lora=dict(r=8))
+    lat, noise, cond, ctx, sig = _train_inputs(2, 5, 16, 24, 64)
+    ids = O.add_time_ids_training(5, 127, 0.02, 2)
+    ref_loss, ref_grads = _oracle_step(o, lat, noise, cond, ctx, sig, ids)
+    tr = LoraTrainer(p)
+    assert tr.layers[0].d == 128
+    loss = tr.forward_backward(lat.to(cuda), noise.to(cuda), sig.to(cuda), cond.to(cuda), ctx.to(cuda), ids.to(cuda))
+    _compare(tr, ref_grads, ref_loss, loss)
+
+
 def test_train_steps_reduce_loss_and_alias_parameters(cuda):
     """A few optimizer steps on one fixed batch: the loss must fall, and the module's LoRA parameters (state_dict)
     must be the tensors the optimizer kernel updates."""
