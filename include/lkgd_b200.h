@@ -313,7 +313,7 @@ LKGD_API int lkgd_fusion_euler_step(const float* v, const float* x, const float*
 LKGD_API int lkgd_attention_lse(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                                 void* out, int32_t ldo, int32_t n_img, int32_t heads, int32_t d, int32_t Nq, int32_t Nk,
                                 float scale, float* lse, void* stream);
-/* Backward of O = softmax(Q K^T scale) V per (image, head), self-attention (Nq = Nk = N), d in {16,32,64}.
+/* Backward of O = softmax(Q K^T scale) V per (image, head), self-attention (Nq = Nk = N), d in {16,32,64,128}.
  * o / dO share the pitch ldo; dq / dk / dv may be column slices of one fused [rows, 3C] gradient.
  * workspace: lkgd_attention_bwd_workspace(n_img, heads, N) bytes. */
 LKGD_API size_t lkgd_attention_bwd_workspace(int32_t n_img, int32_t heads, int32_t N);
