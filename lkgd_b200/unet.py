@@ -381,6 +381,10 @@ class _Base(nn.Module):
         B, F, C, H, W = sample.shape
         if C != self._sample_channels():
             raise ValueError(f"sample has {C} channels, the model expects {self._sample_channels()}")
+        if F > 32:
+            # the temporal attention kernels keep one frame per lane; the reference's pipelines run 14 / 25 frames per call
+            # (long videos go through the `smooth` sampler's windows of `num_frames`)
+            raise ValueError(f"at most 32 frames per forward, got {F}")
         n_down = sum(1 for d in pk.down if d[2] is not None)
         if H % (1 << n_down) or W % (1 << n_down):
             # the reference has no upsample_size forwarding, skip shapes would not match

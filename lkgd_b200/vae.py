@@ -317,7 +317,6 @@ class AutoencoderKLTemporalDecoder(nn.Module):
     @torch.no_grad()
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         """x [B, 3, H, W] (H, W multiples of 8) -> ``.latent_dist`` over fp32 moments [B, 2*latent, H/8, W/8]."""
-        pk = self._pack()
         c = self.config
         if x.ndim != 4 or x.shape[1] != c.in_channels:
             raise ValueError(f"encode expects [B, {c.in_channels}, H, W], got {tuple(x.shape)}")
@@ -325,6 +324,7 @@ class AutoencoderKLTemporalDecoder(nn.Module):
         down = len(c.block_out_channels) - 1
         if H % (1 << down) or W % (1 << down):
             raise ValueError(f"image height and width must be multiples of {1 << down}")
+        pk = self._pack()
         dev = self.device
         ops.STATS_ARENA.begin(dev)
         rows = ops.pack_input(x.to(dev)[:, None], 1.0, None, n, IN_CPAD)                  # [n*H*W, 64] bf16
@@ -353,16 +353,16 @@ class AutoencoderKLTemporalDecoder(nn.Module):
     def decode(self, z: torch.Tensor, num_frames: int, return_dict: bool = True):
         """z [B*num_frames, latent, h, w] -> ``.sample`` [B*num_frames, 3, 8h, 8w]; the temporal layers mix the ``num_frames``
         consecutive frames of each batch element (the reference passes one ``decode_chunk_size`` chunk at a time)."""
-        pk = self._pack()
         c = self.config
         if z.ndim != 4 or z.shape[1] != c.latent_channels or num_frames <= 0 or z.shape[0] % num_frames:
             raise ValueError(f"decode expects [B*num_frames, {c.latent_channels}, h, w], got {tuple(z.shape)} with "
                              f"num_frames={num_frames}")
-        dev = self.device
         n, _, H, W = z.shape
         up = len(c.block_out_channels) - 1
-        if n * H * W * (1 << (2 * up)) * max(c.block_out_channels[0], 4) >= 2 ** 31 * 4:
-            raise ValueError("decode chunk too large for one launch: lower decode_chunk_size")
+        if n * H * W * (1 << (2 * up)) >= 2 ** 31:
+            raise ValueError("decode chunk too large for one launch (2^31 output pixels): lower decode_chunk_size")
+        pk = self._pack()
+        dev = self.device
         g = Geom(n // num_frames, num_frames, H, W)
         ops.STATS_ARENA.begin(dev)
         rows = ops.pack_input(z.to(dev)[:, None], 1.0, None, n, IN_CPAD)

@@ -185,3 +185,46 @@ def test_flop_model_matches_baseline_md():
     c2 = unet_flops(dict(SVD_XT_CONFIG, num_frames=14), 2, 14, 72, 128)["total"] / 1e12
     c3 = unet_flops(SVD_XT_CONFIG, 2, 25, 72, 128, lora_rank=64)["total"] / 1e12
     assert abs(c2 - 89.6) < 0.6 and abs(c3 - 160.9) < 0.6
+
+
+def test_vae_and_clip_argument_checks():
+    """SURVEY 8f N1 modules: constructor / argument errors are raised before anything touches the device, and a CPU call
+    fails loudly (no fallback)."""
+    from lkgd_b200.clip import CLIPVisionModelWithProjection
+    from lkgd_b200.flops import vae_flops
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel
+    from lkgd_b200.vae import SVD_VAE_CONFIG, AutoencoderKLTemporalDecoder
+    with pytest.raises(ValueError, match="multiples of 32"):
+        AutoencoderKLTemporalDecoder(block_out_channels=(24, 32, 64, 64))
+    with pytest.raises(ValueError, match="channel counts"):
+        AutoencoderKLTemporalDecoder(block_out_channels=(32, 32), out_channels=2)
+    v = AutoencoderKLTemporalDecoder(block_out_channels=(32, 32, 32, 32))
+    with pytest.raises(ValueError, match="encode expects"):
+        v.encode(torch.zeros(1, 4, 64, 64))
+    with pytest.raises(ValueError, match="multiples of 8"):
+        v.encode(torch.zeros(1, 3, 60, 64))
+    with pytest.raises(ValueError, match="decode expects"):
+        v.decode(torch.zeros(5, 4, 8, 8), num_frames=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        v.decode(torch.zeros(4, 4, 8, 8), num_frames=2)
+    with pytest.raises(ValueError, match="hidden_act"):
+        CLIPVisionModelWithProjection(hidden_size=64, num_attention_heads=4, hidden_act="relu")
+    with pytest.raises(ValueError, match="head width"):
+        CLIPVisionModelWithProjection(hidden_size=60, num_attention_heads=4)
+    f = vae_flops(SVD_VAE_CONFIG, 25, 72, 128)
+    assert 170e12 < f["decode"] < 177e12 and 2.5e12 < f["encode"] < 2.7e12
+    with torch.device("meta"):
+        u = UNetSpatioTemporalConditionControlNetModel(**REDUCED4)
+    pipe = StableVideoDiffusionPipeline(u, EulerDiscreteScheduler(**SCHED))
+    with pytest.raises(ValueError, match="vae and image_encoder"):
+        pipe.encode_inputs(torch.zeros(1, 3, 64, 64), 64, 64, 4)
+    with pytest.raises(ValueError, match="needs the pipeline's vae"):
+        pipe.decode_latents(torch.zeros(1, 4, 4, 8, 8), 4)
+    with pytest.raises(ValueError, match="pass image="):
+        pipe(num_frames=4)
+    with pytest.raises(ValueError, match="decoded frames need"):
+        pipe(torch.zeros(2, 1, 32), torch.zeros(2, 4, 4, 16, 16), output_type="pt")
+    vid = pipe.tensor2vid(torch.full((1, 3, 2, 4, 4), 3.0), "np")
+    assert vid.shape == (1, 2, 4, 4, 3) and float(vid.max()) == 1.0
