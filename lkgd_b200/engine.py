@@ -254,11 +254,24 @@ class PackedJoint:
             return torch.tensor([mm[part[j]] for j in range(batch)], dtype=torch.bool)
         self.kv = _fused((a.to_k, a.to_v), fold_lora, mask_map=remap)
         wo, bo, lora = _lin_parts(a.to_out[0])
+        s = float(blk.joint_scale) if spatial else 1.0        # the temporal branch has no joint_scale (patch.py:655)
+        self.fuse = None
         if blk.post == "conv":
             P = blk.conv1n.weight.detach().double()
-        else:
+        elif blk.post == "scale":
             P = torch.diag(blk.scale1n.detach().double().reshape(-1))
-        s = float(blk.joint_scale) if spatial else 1.0        # the temporal branch has no joint_scale (patch.py:655)
+        else:
+            # conv_fuse (patch.py:488-494): [out_masked | out_partner] -> one [2C, 2C] layer -> (masked, partner) halves.  The
+            # output projection stays plain; a second two-segment GEMM per sample mixes a sample's rows with its partner's:
+            #   masked sample s:   W[:C, :C] o_s + W[:C, C:] o_p        unmasked sample s:   W[C:, C:] o_s + W[C:, :C] o_p
+            # The temporal forward has no conv_fuse branch at all (:647-650): the raw attention output is added.
+            P = torch.eye(wo.shape[0], dtype=torch.float64, device=wo.device)
+            if spatial:
+                c = wo.shape[0]
+                W = blk.conv1n.weight.detach().float() * s
+                s = 1.0
+                self.fuse = {True: (W[:c, :c].to(bf16).contiguous(), W[:c, c:].to(bf16).contiguous()),
+                             False: (W[c:, c:].to(bf16).contiguous(), W[c:, :c].to(bf16).contiguous())}
         P = P * s
         w_post = (P @ wo.double()).float()
         b_post = (P @ bo.double()).float().contiguous() if bo is not None else None
@@ -495,7 +508,15 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
                     q0, k0 = i * rows + f * g.HW, pi * rows + (g.F - 1 - f) * g.HW
                     ops.attention(qn[q0:q0 + g.HW], kvn[k0:k0 + g.HW, :C], kvn[k0:k0 + g.HW, C:], n_img=1,
                                   heads=p.heads, d=p.d, Nq=g.HW, Nk=g.HW, out=an[q0:q0 + g.HW])
-        h = dense(an, J.out, batch=g.B, res1=h, out=h, out_f32=True)
+        if J.fuse is None:
+            h = dense(an, J.out, batch=g.B, res1=h, out=h, out_f32=True)
+        else:
+            o = dense(an, J.out, batch=g.B)                     # plain to_out; the fuse layer sees it next to the partner's
+            mm = J.mask.repeat_interleave(g.B // len(J.mask)).tolist()
+            for i, pi in enumerate(_partners(J.mask, g.B)):
+                w_self, w_cross = J.fuse[bool(mm[i])]
+                ops.gemm(o[i * rows:(i + 1) * rows], w_self, A1=o[pi * rows:(pi + 1) * rows], Bw1=w_cross,
+                         res1=h[i * rows:(i + 1) * rows], out=h[i * rows:(i + 1) * rows], out_f32=True)
     if kv1:
         n = ops.layernorm(h, p.s_ln3.g, p.s_ln3.b, p.s_ln3.eps, addvec=cond.cross_vec(p.s_cross),
                           rv=g.rv(RV_BATCH), sum_out=h)

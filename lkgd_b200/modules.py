@@ -99,15 +99,16 @@ class _JointAttention:
         import copy
         if add_norm:
             raise NotImplementedError("add_norm=True (AdaLayerNormContinuous on the joint branch) is not built")
-        if post not in ("conv", "scale"):
-            raise NotImplementedError(f"post={post!r}: 'conv' and 'scale' are built ('conv_fuse' is not)")
+        if post not in ("conv", "scale", "conv_fuse"):
+            raise ValueError(f"Unkown post processing type {post}")            # (sic) the reference's assert message
         self.attn1n = copy.deepcopy(self.attn1)
         c = self.attn1.to_out[0].out_features
         dev, dt = self.attn1.to_out[0].weight.device, self.attn1.to_out[0].weight.dtype
         if post == "scale":
             self.scale1n = nn.Parameter(torch.zeros(1, 1, c, device=dev, dtype=dt))
         else:
-            self.conv1n = Linear(c, c, bias=False, device=dev, dtype=dt)
+            k = 2 * c if post == "conv_fuse" else c         # conv_fuse: ONE layer over [masked sample | partner] (:154-157)
+            self.conv1n = Linear(k, k, bias=False, device=dev, dtype=dt)
             if dev.type != "meta":
                 nn.init.zeros_(self.conv1n.weight)
         self.post, self.add_norm, self.joint_scale = post, add_norm, 1.0

@@ -11,8 +11,9 @@ the sum lands in the residual stream through one GEMM epilogue.
 
 Function names, arguments and defaults follow the reference (``apply_patch`` :719-806, ``remove_patch`` :820-838,
 ``initialize_joint_layers`` :966-977, ``set_joint_attention`` :938-950, ``set_joint_scale`` :952-964,
-``set_joint_attention_mask`` :985-1001, ``set_patch_lora_mask`` :872-896).  Not built: ``add_norm=True``,
-``post="conv_fuse"``, ``single_dir``; the per-sample masked LoRA forward (``hack_lora_forward`` :911-922) is built for the
+``set_joint_attention_mask`` :985-1001, ``set_patch_lora_mask`` :872-896).  Not built: ``add_norm=True`` (the
+reference's own forward hands ``timestep=None`` to that AdaLayerNormContinuous, :396,:448 - it cannot run with the stock
+``TransformerSpatioTemporalModel``), ``single_dir`` (commented out in the reference, "bug in lora mask", :461-467); the per-sample masked LoRA forward (``hack_lora_forward`` :911-922) is built for the
 GEMM-path projections and refuses partial masks on attn2 / the GEGLU projection (merged at pack time)."""
 from __future__ import annotations
 

@@ -138,6 +138,9 @@ class BasicTransformerBlock(nn.Module):
         elif post == "conv":
             self.conv1n = nn.Linear(c, c, bias=False)
             nn.init.zeros_(self.conv1n.weight)
+        elif post == "conv_fuse":                      # :154-157: one [2C, 2C] layer over [masked sample | its partner]
+            self.conv1n = nn.Linear(2 * c, 2 * c, bias=False)
+            nn.init.zeros_(self.conv1n.weight)
         else:
             raise ValueError(post)
         self.post = post
@@ -153,6 +156,17 @@ class BasicTransformerBlock(nn.Module):
     def _post(self, y):
         return self.conv1n(y) if self.post == "conv" else self.scale1n * y
 
+    def _post_spatial(self, y):
+        if self.post != "conv_fuse":
+            return self._post(y)
+        # :488-494 - the masked rows and the unmasked rows (k-th with k-th) go through ONE layer side by side
+        m = self.joint_attn_mask.repeat_interleave(y.shape[0] // len(self.joint_attn_mask), dim=0)
+        fx, fy = self.conv1n(torch.cat([y[m], y[~m]], dim=-1)).chunk(2, dim=-1)
+        out = y.clone()
+        out[m] = fx
+        out[~m] = fy
+        return out
+
     def forward(self, x, encoder_hidden_states):
         n = self.norm1(x)
         a = self.attn1(n)
@@ -161,7 +175,7 @@ class BasicTransformerBlock(nn.Module):
             if self.flip:
                 f = self.num_frames
                 enc = enc.reshape(-1, f, *enc.shape[1:]).flip(dims=[1]).reshape(enc.shape)
-            a = a + self._post(self.attn1n(n, enc)) * self.joint_scale
+            a = a + self._post_spatial(self.attn1n(n, enc)) * self.joint_scale
         x = x + a
         x = x + self.attn2(self.norm2(x), encoder_hidden_states)
         x = x + self.ff(self.norm3(x))
@@ -198,7 +212,9 @@ class TemporalBasicTransformerBlock(nn.Module):
         nh = self.norm1(x)
         a = self.attn1(nh)
         if self.enable_joint_attention:                                   # :617-658 (no joint_scale, no flip here)
-            a = a + BasicTransformerBlock._post(self, self.attn1n(nh, BasicTransformerBlock._partner(self, nh, self.joint_attn_mask)))
+            an = self.attn1n(nh, BasicTransformerBlock._partner(self, nh, self.joint_attn_mask))
+            # :647-650 - the temporal forward knows "conv" and "scale" only: under "conv_fuse" there is NO post layer here
+            a = a + (an if self.post == "conv_fuse" else BasicTransformerBlock._post(self, an))
         x = a + x
         x = self.attn2(self.norm2(x), encoder_hidden_states) + x
         y = self.ff(self.norm3(x))

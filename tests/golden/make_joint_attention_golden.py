@@ -69,7 +69,10 @@ ctx = seeded_tensor("ja/ctx", (B, 1, 32))
 ids = torch.tensor([[6.0, 127.0, 0.02]] * B)
 t = torch.tensor(1.4439898729)
 cases = {"conv": ("conv", False, True, [0, 1, 0, 1], 1.0), "conv_flip": ("conv", True, False, [0, 1, 0, 1], 0.7),
-         "scale_pair": ("scale", False, True, [0, 1], 1.0)}
+         "scale_pair": ("scale", False, True, [0, 1], 1.0),
+         # post = "conv_fuse" (:154-157, :488-494; most of the reference's gradio configurations): one [2C, 2C] layer over
+         # [masked sample | partner]; the temporal forward has no branch for it and adds the raw attention output
+         "conv_fuse": ("conv_fuse", False, True, [0, 1, 0, 1], 0.8), "conv_fuse_flip": ("conv_fuse", True, False, [1, 0], 1.0)}
 for tag, (post, flip, temporal, mask, jscale) in cases.items():
     unet = build(post, flip, temporal)
     ref_patch.set_joint_attention_mask(unet, mask)

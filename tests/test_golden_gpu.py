@@ -227,7 +227,7 @@ def test_joint_input_head_unet_vs_reference(cuda):
         u(sample, ts, ctx, added_time_ids=ids)
 
 
-@pytest.mark.parametrize("tag", ["conv", "conv_flip", "scale_pair"])
+@pytest.mark.parametrize("tag", ["conv", "conv_flip", "scale_pair", "conv_fuse", "conv_fuse_flip"])
 def test_joint_attention_patch_vs_reference(cuda, tag):
     """lkgd_b200.patch (apply_patch / initialize_joint_layers / set_joint_attention_mask / set_joint_scale)
     + the engine's joint-attention branch against the reference's own patch/patch.py forwards with joint attention ON

@@ -180,7 +180,8 @@ def test_joint_input_head_unet_matches_reference():
 
 
 JA_CASES = {"conv": ("conv", False, True, [0, 1, 0, 1], 1.0), "conv_flip": ("conv", True, False, [0, 1, 0, 1], 0.7),
-            "scale_pair": ("scale", False, True, [0, 1], 1.0)}      # post, flip, temporal blocks too, mask, joint_scale
+            "scale_pair": ("scale", False, True, [0, 1], 1.0),      # post, flip, temporal blocks too, mask, joint_scale
+            "conv_fuse": ("conv_fuse", False, True, [0, 1, 0, 1], 0.8), "conv_fuse_flip": ("conv_fuse", True, False, [1, 0], 1.0)}
 
 
 def ja_inputs():
