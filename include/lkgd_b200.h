@@ -69,8 +69,11 @@ enum { LKGD_A_LINEAR = 0, LKGD_A_CONV3X3 = 1, LKGD_A_TCONV3 = 2 };
 enum { LKGD_ACT_NONE = 0, LKGD_ACT_SILU = 1, LKGD_ACT_GEGLU = 2, LKGD_ACT_GELU = 3, LKGD_ACT_QUICK_GELU = 4 };
 /* row -> rowvec index g(m) with HW = rows per frame, F frames, B = batch:
  *   NONE; FRAME: m/HW; FRAMEPOS: (m/HW)%F; BATCH: m/(HW*F);
- *   TCTX_0272: ((m/(HW*F))*HW + m%HW) % B  (diffusers 0.27.2 temporal-context quirk) */
-enum { LKGD_RV_NONE = 0, LKGD_RV_FRAME = 1, LKGD_RV_FRAMEPOS = 2, LKGD_RV_BATCH = 3, LKGD_RV_TCTX_0272 = 4 };
+ *   TCTX_0272: ((m/(HW*F))*HW + m%HW) % B  (diffusers 0.27.2 temporal-context quirk)
+ *   BATCH_TCTX: (m/(HW*F))*B + TCTX_0272(m): a [B*B, N] table - the row's OWN sample picks the matrix (per-sample masked
+ *               LoRA adapters on the temporal attn2 projections, patch/patch.py:57-92), the 0.27.2 rule picks the context */
+enum { LKGD_RV_NONE = 0, LKGD_RV_FRAME = 1, LKGD_RV_FRAMEPOS = 2, LKGD_RV_BATCH = 3, LKGD_RV_TCTX_0272 = 4,
+       LKGD_RV_BATCH_TCTX = 5 };
 
 typedef struct lkgd_gemm_args {
   int32_t a_mode;     /* LKGD_A_*                                             */

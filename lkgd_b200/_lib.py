@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
-RV_NONE, RV_FRAME, RV_FRAMEPOS, RV_BATCH, RV_TCTX_0272 = 0, 1, 2, 3, 4
+RV_NONE, RV_FRAME, RV_FRAMEPOS, RV_BATCH, RV_TCTX_0272, RV_BATCH_TCTX = 0, 1, 2, 3, 4, 5
 SL_NONE, SL_SILU, SL_LEAKY = 0, 1, 3
 
 i32, f32, vp, i64, sz = C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_size_t

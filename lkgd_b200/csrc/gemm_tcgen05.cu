@@ -68,6 +68,7 @@ __device__ __forceinline__ int rowvec_index(int mode, int m, int HW, int F, int 
     case LKGD_RV_FRAMEPOS: return (m / HW) % F;
     case LKGD_RV_BATCH: return m / (HW * F);
     case LKGD_RV_TCTX_0272: return ((m / (HW * F)) * HW + (m % HW)) % B;
+    case LKGD_RV_BATCH_TCTX: return (m / (HW * F)) * B + ((m / (HW * F)) * HW + (m % HW)) % B;
     default: return 0;
   }
 }

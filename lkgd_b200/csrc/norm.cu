@@ -191,6 +191,10 @@ __device__ __forceinline__ int ln_rowvec_index(int mode, long long m, int HW, in
     case LKGD_RV_FRAMEPOS: return (int)((m / HW) % F);
     case LKGD_RV_BATCH: return (int)(m / ((long long)HW * F));
     case LKGD_RV_TCTX_0272: return (int)(((m / ((long long)HW * F)) * HW + (m % HW)) % B);
+    case LKGD_RV_BATCH_TCTX: {
+      const long long b = m / ((long long)HW * F);
+      return (int)(b * B + (b * HW + (m % HW)) % B);
+    }
     default: return 0;
   }
 }

@@ -23,7 +23,7 @@ import torch
 from . import modules as M
 from . import ops
 from .ops import (A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU, ACT_NONE, ACT_SILU, RV_BATCH, RV_FRAMEPOS, RV_NONE,
-                  RV_TCTX_0272, bf16)
+                  RV_BATCH_TCTX, RV_TCTX_0272, bf16)
 
 SL_SILU, SL_LEAKY = 1, 3
 
@@ -186,18 +186,51 @@ def _geglu(ff: M.FeedForward, fold_lora: bool):
 
 
 class PackedCross:
-    """attn2: fp32 to_v / to_out for the KV-length-1 collapse + bf16 q/k/v/out for KV > 1."""
+    """attn2: fp32 to_v / to_out for the KV-length-1 collapse + bf16 q/k/v/out for KV > 1.
+
+    Per-sample MASKED adapters (patch.hack_lora_forward, patch/patch.py:57-92) on to_v / to_out.0 make the collapsed matrix a
+    function of the sample: ``variant(key)`` builds (and caches) ``(Wo + sum_a s B A)(Wv + sum_a s B A)`` for the adapters
+    that are active on it, ``patterns(B)`` says which samples share a matrix (to_q / to_k never matter with one key)."""
 
     def __init__(self, attn: M.Attention):
         self.heads, self.d = attn.heads, attn.dim_head
-        wv, _ = _merged_weight(attn.to_v)
-        wo, self.bo = _merged_weight(attn.to_out[0])
-        # softmax over ONE key is exactly 1, so attn2(x, ctx) = to_out(to_v(ctx)) = (Wo Wv) ctx + bo for every query:
-        # one [C, D] matrix per cross-attention, product taken in fp64
-        self.wov = (wo.double() @ wv.double()).float().contiguous()
-        self.off = 0                # column offset inside the batched cross-vector matrix (set by PackedUNet)
         self._attn = attn
         self._general = None
+        self._variants = {}
+        self.masked = any(isinstance(m, M.LoraLinear) and not m.merged and any(a[4] is not None for a in m.adapters())
+                          for m in (attn.to_v, attn.to_out[0]))
+        if self.masked:
+            self._ads = [[] if not isinstance(m, M.LoraLinear) or m.merged else m.adapters() for m in (attn.to_v, attn.to_out[0])]
+            self.bo = _lin_parts(attn.to_out[0])[1]
+            self.wov = self.variant(tuple(tuple(True for _ in ads) for ads in self._ads))
+        else:
+            wv, _ = _merged_weight(attn.to_v)
+            wo, self.bo = _merged_weight(attn.to_out[0])
+            # softmax over ONE key is exactly 1, so attn2(x, ctx) = to_out(to_v(ctx)) = (Wo Wv) ctx + bo for every query:
+            # one [C, D] matrix per cross-attention, product taken in fp64
+            self.wov = (wo.double() @ wv.double()).float().contiguous()
+        self.off = 0                # column offset inside the batched cross-vector matrix (set by PackedUNet)
+
+    def variant(self, key) -> torch.Tensor:
+        if key not in self._variants:
+            ws = []
+            for mod, ads, on in zip((self._attn.to_v, self._attn.to_out[0]), self._ads, key):
+                w = _lin_parts(mod)[0].double()
+                for (_, a, b, sc, _), active in zip(ads, on):
+                    if active:
+                        w = w + sc * (b.detach().double() @ a.detach().double())
+                ws.append(w)
+            self._variants[key] = (ws[1] @ ws[0]).float().contiguous()
+        return self._variants[key]
+
+    def patterns(self, batch: int):
+        """{variant key: [samples]} under the reference's ``mask.repeat_interleave(batch // len(mask))``."""
+        out = {}
+        for b in range(batch):
+            key = tuple(tuple(True if m is None else bool(m[b // max(batch // len(m), 1)]) for (_, _, _, _, m) in ads)
+                        for ads in self._ads)
+            out.setdefault(key, []).append(b)
+        return out
 
     def general(self):
         if self._general is None:
@@ -405,9 +438,40 @@ class Conditioning:
         self.ctx_t = ctx if ctx_t is None else ctx_t
         self.temb_all = ops.small_linear(emb, pk.temb_w, pk.temb_b, act_in=SL_SILU)
         self.xs_all = self.xt_all = None
+        self.t_table = False      # xt_all is a [B * n_ctx, C] table (RV_BATCH_TCTX): masked adapters on temporal attn2
         if ctx.shape[1] == 1 and pk.xs_w is not None:
             self.xs_all = ops.small_linear(ctx[:, 0].contiguous(), pk.xs_w, pk.xs_b)
             self.xt_all = ops.small_linear(self.ctx_t[:, 0].contiguous(), pk.xt_w, pk.xt_b)
+            if pk.masked_cross:
+                self._masked_cross(pk)
+
+    def _masked_cross(self, pk: "PackedUNet"):
+        """Per-sample masked LoRA adapters on attn2.to_v / to_out.0: the cross vector of sample b uses the matrix of b's
+        adapter pattern.  Spatial (and b-major temporal) rows are per sample anyway; under the 0.27.2 temporal context
+        order the row's own sample picks the MATRIX while (row % B) picks the CONTEXT, so the temporal vectors become a
+        [B * B, C] table addressed with RV_BATCH_TCTX."""
+        B, n_ctx = self.ctx.shape[0], self.ctx_t.shape[0]
+        if n_ctx != B:
+            raise NotImplementedError("masked cross-attention adapters under a CFG pair split")
+        if pk.tctx_mode == RV_TCTX_0272 and any(not sp for sp, _ in pk.masked_cross):
+            self.xt_all = self.xt_all.repeat(B, 1)             # row b * B + g = vector of context g (unmasked layers)
+            self.t_table = True
+        ctx0, ctxt0 = self.ctx[:, 0].contiguous(), self.ctx_t[:, 0].contiguous()
+        for spatial, pc in pk.masked_cross:
+            cols = slice(pc.off, pc.off + pc.wov.shape[0])
+            for key, rows in pc.patterns(B).items():
+                w = pc.variant(key)
+                if spatial or not self.t_table:
+                    idx = torch.tensor(rows, device=ctx0.device)
+                    src = (ctx0 if spatial else ctxt0).index_select(0, idx)
+                    (self.xs_all if spatial else self.xt_all)[idx, cols] = ops.small_linear(src, w, pc.bo)
+                else:
+                    v = ops.small_linear(ctxt0, w, pc.bo)                               # [n_ctx, C]: every context
+                    for b in rows:
+                        self.xt_all[b * B:(b + 1) * B, cols] = v
+
+    def t_rv(self, tctx_mode: int) -> int:
+        return RV_BATCH_TCTX if self.t_table and tctx_mode == RV_TCTX_0272 else tctx_mode
 
     def temb(self, off: int, n: int):       # time_emb_proj(SiLU(emb)) -> [B, Cout] (view)
         return self.temb_all[:, off:off + n]
@@ -556,7 +620,7 @@ def run_transformer(p: PackedTransformer, x: torch.Tensor, g: Geom, cond: Condit
     if kv1:
         # under a CFG pair split ctx_t holds every half's context: index it exactly as the unsplit batch would
         n = ops.layernorm(t, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
-                          rv=(tctx_mode, g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
+                          rv=(cond.t_rv(tctx_mode), g.HW, g.F, cond.ctx_t.shape[0]), sum_out=t)
     else:
         if tctx_mode != RV_BATCH and cond.ctx_t.shape[0] != cond.ctx.shape[0]:
             raise NotImplementedError("temporal cross-attention with KV length > 1 under a CFG pair split")
@@ -625,6 +689,8 @@ class PackedUNet:
             r.temb_w = r.temb_b = r.ttemb_w = r.ttemb_b = None
         self.temb_w, self.temb_b = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
         self.xs_w = self.xs_b = self.xt_w = self.xt_b = None
+        self.masked_cross = [(key == "s_cross", getattr(t, key)) for t in tr for key in ("s_cross", "t_cross")
+                             if getattr(t, key).masked]
         if tr:
             for name, key in (("xs", "s_cross"), ("xt", "t_cross")):
                 off, w, b = 0, [], []

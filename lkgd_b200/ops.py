@@ -10,7 +10,7 @@ import torch
 
 from . import _lib as L
 from ._lib import (A_CONV3X3, A_LINEAR, A_TCONV3, ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, RV_BATCH, RV_FRAME, RV_FRAMEPOS,
-                   RV_NONE, RV_TCTX_0272, GemmArgs)
+                   RV_BATCH_TCTX, RV_NONE, RV_TCTX_0272, GemmArgs)
 
 bf16 = torch.bfloat16
 

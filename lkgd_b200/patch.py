@@ -14,7 +14,8 @@ Function names, arguments and defaults follow the reference (``apply_patch`` :71
 ``set_joint_attention_mask`` :985-1001, ``set_patch_lora_mask`` :872-896).  Not built: ``add_norm=True`` (the
 reference's own forward hands ``timestep=None`` to that AdaLayerNormContinuous, :396,:448 - it cannot run with the stock
 ``TransformerSpatioTemporalModel``), ``single_dir`` (commented out in the reference, "bug in lora mask", :461-467); the per-sample masked LoRA forward (``hack_lora_forward`` :911-922) is built for the
-GEMM-path projections and refuses partial masks on attn2 / the GEGLU projection (merged at pack time)."""
+GEMM-path projections and the KV-length-1 cross-attentions (one collapsed matrix per adapter pattern) and refuses partial
+masks on the GEGLU projection / attn2 with KV length > 1 (merged at pack time)."""
 from __future__ import annotations
 
 import torch

@@ -665,6 +665,57 @@ def test_joint_attention_with_masked_multi_adapter_lora(cuda, flip):
     assert rel_l2(unmasked, ref) > 3 * err
 
 
+@pytest.mark.parametrize("order", ["hw_major_0272", "b_major"])
+def test_masked_adapters_on_every_attention_projection(cuda, order):
+    """`hack_lora_forward` + `set_patch_lora_mask` with adapters on EVERY attention projection (the usual
+    target_modules=["to_k","to_q","to_v","to_out.0"]): also attn2, whose KV-length-1 collapse then needs one (Wo Wv) matrix per
+    adapter pattern - and, under the diffusers 0.27.2 temporal context order, a [B*B, C] table: the row's own sample selects
+    the matrix (the reference masks by row position, patch/patch.py:74-77), row % B selects the context."""
+    import oracle as O
+    from oracle.lora import ALL_ATTN_PROJ
+    from lkgd_b200 import patch
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG, time_context_order=order)
+    torch.manual_seed(0)
+    o = O.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    p = UNetSpatioTemporalConditionControlNetModel(**cfg)
+    for name, r in (("xy_lora", 8), ("yx_lora", 4)):
+        O.add_lora(o, r, target=ALL_ATTN_PROJ, adapter_name=name)
+        p.add_adapter(dict(r=r, lora_alpha=r, init_lora_weights="gaussian", target_modules=["to_k", "to_q", "to_v", "to_out.0"]),
+                      name)
+    _randomise_zero_inits(o)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, prm in o.named_parameters():
+            if "lora_B" in n:
+                prm.copy_((torch.randn(prm.shape, generator=g) * (0.8 if ".attn2." in n else 0.6) * prm.shape[1] ** -0.5)
+                          .to(torch.bfloat16).float())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(cuda)
+    masks = {"xy_lora": [1, 0, 1, 1], "yx_lora": [0, 1, 0, 1]}         # three different adapter patterns over four samples
+    for name, m in o.named_modules():
+        if isinstance(m, O.LoraLinear):
+            m.masked_forward = True
+            for a, mk in masks.items():
+                m.lora_mask[a] = torch.tensor(mk, dtype=torch.bool)
+    for a, mk in masks.items():
+        patch.set_patch_lora_mask(p, a, mk)
+    p.set_adapters(["xy_lora", "yx_lora"])
+    patch.hack_lora_forward(p)
+    x, ctx, ids = _inputs(cfg, 4, 8, 16, 16, 32)
+    with torch.no_grad():
+        ref = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+        for m in o.modules():
+            if isinstance(m, O.LoraLinear) and m.in_features == 32:       # attn2.to_k / to_v: unmask only the cross-attention
+                m.masked_forward = False
+        cross_unmasked = o(x, 0.9, ctx, added_time_ids=ids, return_dict=False)[0]
+    got = p(x.to(cuda), 0.9, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(got, ref)
+    print("masked adapters incl. attn2,", order, "rel-L2", err, "| attn2 masks matter:", rel_l2(cross_unmasked, ref))
+    assert err < 1e-2
+    assert rel_l2(cross_unmasked, ref) > 3 * err
+
+
 @pytest.mark.parametrize("name", ["d80_gelu", "d16_quick", "vit_h_14"])
 def test_clip_image_encoder(cuda, name):
     """SURVEY 8f N1 (CLIP half): lkgd_b200.clip.CLIPVisionModelWithProjection against the oracle (pinned against the
