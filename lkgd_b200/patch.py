@@ -130,12 +130,52 @@ def hack_lora_forward(model):
     """Reference :911-922 switches every LoRA Linear to the per-sample masked forward (:57-92): an adapter acts only on the
     samples its ``lora_mask`` selects.  Here the switch is a flag on the LoRA modules; the engine computes a masked
     adapter's down-projection sample range by sample range (``engine.lora_down``).  Masked adapters are built for the
-    GEMM-path projections (attn1 / attn1n q, k, v, out; proj_in / proj_out; ff.net.2); on attn2 and the GEGLU projection,
-    whose adapters are merged at pack time, a partial mask raises when the model is packed."""
+    GEMM-path projections (attn1 / attn1n q, k, v, out; proj_in / proj_out; ff.net.2) and the KV-length-1 cross-attentions
+    (``engine.PackedCross``: one collapsed matrix per adapter pattern); on the GEGLU projection and attn2 with more than one
+    key, whose adapters are merged at pack time, a partial mask raises when the model is packed."""
     for net in _models(model):
         for name, m in net.named_modules():
             if isinstance(m, M.LoraLinear):
                 m.masked_forward = True
         if hasattr(net, "invalidate"):
             net.invalidate()
+    return model
+
+
+def update_patch(model, **kwargs):
+    """Reference :841-853: sets attributes on every patched module (the UNet itself carries ``_tome_info`` too)."""
+    for net in _models(model):
+        for _, m in net.named_modules():
+            if hasattr(m, "_tome_info"):
+                for k, v in kwargs.items():
+                    setattr(m, k, v)
+        if hasattr(net, "invalidate"):
+            net.invalidate()
+    return model
+
+
+def collect_from_patch(model, attr: str = "tome"):
+    """Reference :856-870: {module name: attribute} over the modules that have ``attr``."""
+    out = {}
+    for net in _models(model):
+        for name, m in net.named_modules():
+            if hasattr(m, attr):
+                out[name] = getattr(m, attr)
+    return out
+
+
+def set_joint_layer_requires_grad(model, adapter_names, requires_grad: bool):
+    """Reference :898-909 / :110-133: requires_grad of the named adapters inside ``attn1n`` and of the post layer."""
+    if isinstance(adapter_names, str):
+        adapter_names = [adapter_names]
+    for _, _, m in _patched(model):
+        if not hasattr(m, "attn1n"):
+            continue
+        for sub in m.attn1n.modules():
+            if isinstance(sub, M.LoraLinear):
+                for d in (sub.lora_A, sub.lora_B):
+                    for key, layer in d.items():
+                        if key in adapter_names:
+                            layer.requires_grad_(requires_grad)
+        m.post_joint.requires_grad_(requires_grad)
     return model

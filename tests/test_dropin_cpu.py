@@ -149,10 +149,21 @@ def test_joint_attention_patch_api_on_cpu():
     assert _partners(torch.tensor([0, 1], dtype=torch.bool), 4) == [2, 3, 0, 1]           # repeat_interleave: x x y y
     with pytest.raises(ValueError, match="half"):
         _partners(torch.tensor([1, 1, 1, 0], dtype=torch.bool), 4)
+    patch.update_patch(u, joint_scale=0.25)                                               # :841-853
+    assert set(patch.collect_from_patch(u, "joint_scale").values()) == {0.25}             # :856-870
+    for prm in u.parameters():
+        prm.requires_grad_(False)
+    patch.set_joint_layer_requires_grad(u, ["xy_lora"], True)                             # no adapter yet: the post layers
+    assert sorted(n for n, prm in u.named_parameters() if prm.requires_grad) == \
+        sorted(n for n, _ in u.named_parameters() if n.endswith("conv1n.weight"))
+    for prm in u.parameters():
+        prm.requires_grad_(True)
     patch.remove_patch(u)
     assert not any(b.patched or b.enable_joint_attention for b in blocks)
     with pytest.raises(NotImplementedError):
         patch.apply_patch(u, single_dir=True)
+    with pytest.raises(ValueError, match="Unkown post processing type"):
+        blocks[0].initialize_joint_layers(post="mlp")
     # several adapters per layer + per-sample masks (utils/util.py:566-603: y_lora / xy_lora / yx_lora, set_adapters,
     # hack_lora_forward, set_patch_lora_mask)
     cfg_ = dict(r=4, lora_alpha=4, init_lora_weights="gaussian", target_modules=["attn1.to_q", "attn1.to_k"])
