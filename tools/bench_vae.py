@@ -1,6 +1,7 @@
 """Per-kernel breakdown of the VAE's temporal decode at the headline size (8-frame chunk of 576x1024 frames, SVD widths,
 random weights): CUDA events around every C-ABI call (lkgd_b200._lib.PROF), GEMM launches listed by shape.
-usage: python tools/bench_vae.py [frames=8] [out.json]"""
+usage: python tools/bench_vae.py [frames=8] [out.json]
+       ncu --profile-from-start off ... python tools/bench_vae.py 8 --profiler     (ONE decode between cudaProfilerStart / Stop)"""
 import json
 import os
 import sys
@@ -13,6 +14,9 @@ from lkgd_b200 import _lib  # noqa: E402
 from lkgd_b200.flops import vae_flops  # noqa: E402
 from lkgd_b200.vae import SVD_VAE_CONFIG, AutoencoderKLTemporalDecoder  # noqa: E402
 
+PROFILER = "--profiler" in sys.argv
+if PROFILER:
+    sys.argv.remove("--profiler")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -21,6 +25,12 @@ z = torch.randn(n, 4, 72, 128, device=dev)
 for _ in range(2):
     vae.decode(z, num_frames=n)
 torch.cuda.synchronize()
+if PROFILER:
+    torch.cuda.cudart().cudaProfilerStart()
+    vae.decode(z, num_frames=n)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    sys.exit(0)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(3):

@@ -14,6 +14,8 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
 B4="python bench.py --workload C4 --steps 1 --warmup 3 --no-cpu-baseline --profiler-step"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $out/${tag}_launches_c4.csv $B4 > $out/${tag}_launches_c4.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $out/${tag}_launches_vae_decode8.csv python tools/bench_vae.py 8 --profiler > $out/${tag}_launches_vae.log 2>&1
 for spec in "0 gemm_ff1_L0_geglu" "11 gemm_conv_L0_res32" "3 gemm_proj_L0_res32"; do
   set -- $spec
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -f \
