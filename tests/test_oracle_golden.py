@@ -545,3 +545,112 @@ def test_vae_oracle_semantics():
                                                                 ds.conv.bias, stride=2))
         out = O.decode_latents(v, seeded_tensor("vae/l", (1, 3, 4, 4, 4)), num_frames=3, decode_chunk_size=2)
     assert tuple(out.shape) == (1, 3, 3, 32, 32)
+
+
+LDM_AUTOENCODER = "torchtitan/experiments/flux/model/autoencoder.py"     # an on-disk CompVis / LDM KL-autoencoder
+
+
+def _ldm_autoencoder():
+    """The image's site-packages hold an INDEPENDENT implementation of the KL-VAE the SVD VAE descends from (torchtitan's Flux
+    autoencoder = the CompVis latent-diffusion `Encoder` / `Decoder`: GroupNorm(32, eps 1e-6) + swish ResnetBlocks,
+    (0,1,0,1)-padded stride-2 downsampling, single-head mid attention, nearest upsampling).  Loaded by path (no torchtitan
+    package import)."""
+    import importlib.util
+    import sysconfig
+    path = os.path.join(sysconfig.get_paths()["purelib"], LDM_AUTOENCODER)
+    if not os.path.isfile(path):
+        pytest.skip(f"{LDM_AUTOENCODER} is not installed")
+    spec = importlib.util.spec_from_file_location("ldm_autoencoder_pin", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _ldm_to_diffusers(name, n_levels, decoder):
+    """The published LDM -> diffusers VAE key mapping (diffusers `convert_ldm_vae_checkpoint`)."""
+    import re
+    name = name.replace("nin_shortcut", "conv_shortcut").replace("norm_out", "conv_norm_out")
+    name = re.sub(r"^mid\.block_(\d)\.", lambda m: f"mid_block.resnets.{int(m.group(1)) - 1}.", name)
+    name = re.sub(r"^mid\.attn_1\.", "mid_block.attentions.0.", name)
+    for a, b in (("attentions.0.norm.", "attentions.0.group_norm."), ("attentions.0.q.", "attentions.0.to_q."),
+                 ("attentions.0.k.", "attentions.0.to_k."), ("attentions.0.v.", "attentions.0.to_v."),
+                 ("attentions.0.proj_out.", "attentions.0.to_out.0.")):
+        name = name.replace(a, b)
+    name = re.sub(r"^down\.(\d)\.block\.(\d)\.", r"down_blocks.\1.resnets.\2.", name)
+    name = re.sub(r"^down\.(\d)\.downsample\.", r"down_blocks.\1.downsamplers.0.", name)
+    name = re.sub(r"^up\.(\d)\.block\.(\d)\.", lambda m: f"up_blocks.{n_levels - 1 - int(m.group(1))}.resnets.{m.group(2)}.", name)
+    name = re.sub(r"^up\.(\d)\.upsample\.", lambda m: f"up_blocks.{n_levels - 1 - int(m.group(1))}.upsamplers.0.", name)
+    return name
+
+
+def test_vae_oracle_spatial_skeleton_matches_an_independent_ldm_autoencoder():
+    """diffusers is not installed, but the KL-autoencoder the SVD VAE was initialised from is on disk in an
+    independent implementation.  With the published LDM -> diffusers key mapping the oracle's ENCODER must reproduce it
+    exactly (ResnetBlock eps / activation / shortcut, bottom-right padded downsampling, the single-head attention block and
+    its scale, conv_norm_out / conv_out), and the oracle's TEMPORAL DECODER with its temporal branch switched off (mix_factor
+    -> -inf, i.e. switched alpha = 1; identity time_conv_out) must reproduce the LDM decoder frame by frame (block order,
+    channel wiring, upsampler placement).  What stays restated-only for the VAE: the temporal branch itself
+    (TemporalResnetBlock / AlphaBlender with switch_spatial_to_temporal_mix / Conv3d time_conv_out) and quant_conv."""
+    L = _ldm_autoencoder()
+    boc, z = (32, 64, 128, 128), 4
+    kw = dict(resolution=64, in_channels=3, ch=boc[0], ch_mult=[c // boc[0] for c in boc], num_res_blocks=2, z_channels=z)
+    torch.manual_seed(0)
+    enc = fill_seeded_(L.Encoder(**kw)).eval()
+    dec = fill_seeded_(L.Decoder(out_ch=3, **kw), seed=1).eval()
+    o = fill_seeded_(O.AutoencoderKLTemporalDecoder(block_out_channels=boc, latent_channels=z), seed=2).eval()
+    sd = o.state_dict()
+    n_mapped = 0
+    for part, ref in (("encoder", enc), ("decoder", dec)):
+        for k, v in ref.state_dict().items():
+            name = _ldm_to_diffusers(k, len(boc), part == "decoder")
+            if part == "decoder" and (".resnets." in name) and "mid_block.attentions" not in name:
+                name = name.replace(".resnets.", ".resnets.").replace(".norm1", ".spatial_res_block.norm1") \
+                    .replace(".conv1", ".spatial_res_block.conv1").replace(".norm2", ".spatial_res_block.norm2") \
+                    .replace(".conv2", ".spatial_res_block.conv2").replace(".conv_shortcut", ".spatial_res_block.conv_shortcut")
+            key = f"{part}.{name}"
+            assert key in sd, (k, key)
+            if v.ndim == 4 and sd[key].ndim == 2:          # 1x1 convs of the LDM attention block are Linears in diffusers
+                v = v[:, :, 0, 0]
+            assert sd[key].shape == v.shape, (key, sd[key].shape, v.shape)
+            sd[key] = v.clone()
+            n_mapped += 1
+    assert n_mapped == len(enc.state_dict()) + len(dec.state_dict())
+    # every encoder tensor of the oracle is now the LDM's; of the decoder everything except the temporal branch
+    assert sum(k.startswith("encoder.") for k in sd) == len(enc.state_dict())
+    assert sum(k.startswith("decoder.") and "temporal_res_block" not in k and "time_mixer" not in k and "time_conv_out" not in k
+               for k in sd) == len(dec.state_dict())
+    for k in sd:
+        if k.endswith("time_mixer.mix_factor"):
+            sd[k] = torch.full_like(sd[k], -40.0)          # sigmoid -> 0; switched blender: alpha = 1 -> spatial branch only
+    sd["decoder.time_conv_out.weight"] = torch.zeros_like(sd["decoder.time_conv_out.weight"])
+    sd["decoder.time_conv_out.weight"][:, :, 1, 0, 0] = torch.eye(3)
+    sd["decoder.time_conv_out.bias"] = torch.zeros(3)
+    sd["quant_conv.weight"] = torch.eye(2 * z)[:, :, None, None].clone()
+    sd["quant_conv.bias"] = torch.zeros(2 * z)
+    o.load_state_dict(sd, strict=True)
+    x = torch.tanh(seeded_tensor("ldm/x", (2, 3, 64, 48)))
+    zz = seeded_tensor("ldm/z", (6, z, 8, 6))
+    with torch.no_grad():
+        ref_m, ref_d = enc(x), dec(zz)
+        got_m = o.encode(x).latent_dist
+        got_d = o.decode(zz, num_frames=3).sample
+    assert rel(torch.cat([got_m.mean, got_m.logvar], 1), ref_m) < 2e-6
+    assert rel(got_d, ref_d) < 1e-5          # 14 blocks, each blended as 1.0 * spatial + 4e-18 * temporal in fp32
+
+
+def test_timestep_embedding_matches_an_independent_implementation():
+    """`Timesteps(C, flip_sin_to_cos=True, downscale_freq_shift=0)` (restated from diffusers) against the
+    sinusoidal embedding of torchtitan's Flux layers (same image, independent code): cos | sin halves over exp(-ln(1e4) k / half)."""
+    import importlib.util
+    import sysconfig
+    path = os.path.join(sysconfig.get_paths()["purelib"], "torchtitan/experiments/flux/model/layers.py")
+    if not os.path.isfile(path):
+        pytest.skip("torchtitan's flux layers are not installed")
+    src = open(path).read()
+    start = src.index("def timestep_embedding(")
+    ns = {"math": __import__("math"), "torch": torch, "Tensor": torch.Tensor}
+    exec(src[start:src.index("\nclass ", start)], ns)                      # the function only (the module imports more)
+    ts = torch.tensor([0.0, 0.25 * float(np.log(0.002)), 1.6377, 999.0])
+    for dim in (256, 320):
+        ref = ns["timestep_embedding"](ts, dim, time_factor=1.0)
+        assert rel(O.timestep_embedding(ts, dim), ref) < 1e-6
