@@ -654,3 +654,38 @@ def test_timestep_embedding_matches_an_independent_implementation():
     for dim in (256, 320):
         ref = ns["timestep_embedding"](ts, dim, time_factor=1.0)
         assert rel(O.timestep_embedding(ts, dim), ref) < 1e-6
+
+
+def test_quaternion_linear_is_the_hamilton_product():
+    """SURVEY A.7 / U5 (core_qnn is un-vendored; the block signs were recalled): with 1x1 blocks the layer must be the Hamilton
+    product  weight (x) input  of quaternion algebra.  Checked against scipy's independent quaternion composition
+    (`Rotation`: unit quaternions, scalar-last, q and -q identified) and against the defining identities i^2 = j^2 = k^2 =
+    ijk = -1.  A single wrong sign in the 4x4 block pattern breaks both."""
+    from scipy.spatial.transform import Rotation
+    from oracle.unet import QuaternionLinear
+    q = QuaternionLinear(4, 4)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(8):
+        w = torch.randn(4, generator=g, dtype=torch.float64)
+        x = torch.randn(4, generator=g, dtype=torch.float64)
+        w, x = w / w.norm(), x / x.norm()
+        with torch.no_grad():
+            for n_, v in zip(("r_weight", "i_weight", "j_weight", "k_weight"), w):
+                getattr(q, n_).copy_(v.reshape(1, 1).float())
+            q.bias.zero_()
+            y = q(x.float()[None])[0].double()                          # (r, i, j, k)
+        as_xyzw = lambda t: np.array([t[1], t[2], t[3], t[0]], dtype=np.float64)
+        ref = (Rotation.from_quat(as_xyzw(w)) * Rotation.from_quat(as_xyzw(x))).as_quat()      # w (x) x, scalar last
+        got = as_xyzw(y.numpy())
+        assert min(np.abs(got - ref).max(), np.abs(got + ref).max()) < 1e-6
+    unit = {"1": [1, 0, 0, 0], "i": [0, 1, 0, 0], "j": [0, 0, 1, 0], "k": [0, 0, 0, 1]}
+
+    def mul(a, b):
+        with torch.no_grad():
+            for n_, v in zip(("r_weight", "i_weight", "j_weight", "k_weight"), a):
+                getattr(q, n_).fill_(float(v))
+            return q(torch.tensor([b], dtype=torch.float32))[0].tolist()
+    assert mul(unit["i"], unit["i"]) == [-1, 0, 0, 0] and mul(unit["j"], unit["j"]) == [-1, 0, 0, 0]
+    assert mul(unit["k"], unit["k"]) == [-1, 0, 0, 0]
+    assert mul(unit["i"], unit["j"]) == unit["k"] and mul(unit["j"], unit["k"]) == unit["i"] and mul(unit["k"], unit["i"]) == unit["j"]
+    assert mul(unit["j"], unit["i"]) == [0, 0, 0, -1]
