@@ -45,6 +45,8 @@ __device__ __forceinline__ void b_cp16(uint32_t dst, const void* src, uint32_t b
 __device__ __forceinline__ void b_cp_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void b_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void b_cp_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float b_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams p)
   using T = BT<D>;
   constexpr int TILE = BB * T::ROW;
   extern __shared__ __align__(128) uint8_t bsm[];
-  const uint32_t sQ = smem_u32(bsm), sdO = sQ + TILE, sK = sdO + TILE, sV = sK + TILE;
+  const uint32_t sQ = smem_u32(bsm), sdO = sQ + TILE, sKV = sdO + TILE;      // then [K0 | V0 | K1 | V1]: double-buffered stream
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BB, head = blockIdx.y, img = blockIdx.z;
   const long long img_row = (long long)img * p.N;
@@ -130,12 +132,19 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams p)
     for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
 
   const int T_kv = (p.N + BB - 1) / BB;
+  load_tile<D, BB, 128>(sKV, kb, p.ldk, 0, p.N);
+  load_tile<D, BB, 128>(sKV + TILE, vb, p.ldv, 0, p.N);
+  b_cp_commit();
   for (int j = 0; j < T_kv; ++j) {
-    __syncthreads();                       // previous K / V tiles fully consumed
-    load_tile<D, BB, 128>(sK, kb, p.ldk, j * BB, p.N);
-    load_tile<D, BB, 128>(sV, vb, p.ldv, j * BB, p.N);
-    b_cp_wait_all();
-    __syncthreads();
+    b_cp_wait0();
+    __syncthreads();                       // tile j has landed; every warp is done with tile j-1, whose buffer is refilled now
+    if (j + 1 < T_kv) {
+      const uint32_t nb = sKV + ((j + 1) & 1) * 2 * TILE;
+      load_tile<D, BB, 128>(nb, kb, p.ldk, (j + 1) * BB, p.N);
+      load_tile<D, BB, 128>(nb + TILE, vb, p.ldv, (j + 1) * BB, p.N);
+      b_cp_commit();
+    }
+    const uint32_t sK = sKV + (j & 1) * 2 * TILE, sV = sK + TILE;
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -197,9 +206,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams p
   using T = BT<D>;
   constexpr int TILE = BB * T::ROW;
   extern __shared__ __align__(128) uint8_t bsm[];
-  const uint32_t sK = smem_u32(bsm), sV = sK + TILE, sQ = sV + TILE, sdO = sQ + TILE;
-  float* s_lse = reinterpret_cast<float*>(bsm + 4 * TILE);
-  float* s_dv = s_lse + BB;
+  const uint32_t sK = smem_u32(bsm), sV = sK + TILE, sQD = sV + TILE;       // then [Q0 | dO0 | Q1 | dO1]: double-buffered stream
+  float* s_stat = reinterpret_cast<float*>(bsm + 6 * TILE);                 // [lse0 | Dv0 | lse1 | Dv1], BB floats each
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * BB, head = blockIdx.y, img = blockIdx.z;
   const long long img_row = (long long)img * p.N;
@@ -226,17 +234,26 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams p
     for (int e = 0; e < 4; ++e) { dk[n][e] = 0.f; dv[n][e] = 0.f; }
 
   const int T_q = (p.N + BB - 1) / BB;
-  for (int j = 0; j < T_q; ++j) {
-    __syncthreads();
-    load_tile<D, BB, 128>(sQ, qb, p.ldq, j * BB, p.N);
-    load_tile<D, BB, 128>(sdO, dob, p.ldo, j * BB, p.N);
+  auto stream_tile = [&](int t) {
+    const uint32_t nb = sQD + (t & 1) * 2 * TILE;
+    load_tile<D, BB, 128>(nb, qb, p.ldq, t * BB, p.N);
+    load_tile<D, BB, 128>(nb + TILE, dob, p.ldo, t * BB, p.N);
+    b_cp_commit();
     if (threadIdx.x < BB) {
-      const int r = j * BB + threadIdx.x;
-      s_lse[threadIdx.x] = r < p.N ? lse_b[r] : INFINITY;     // 2^(-inf) = 0: out-of-range queries contribute nothing
-      s_dv[threadIdx.x] = r < p.N ? dv_b[r] : 0.f;
+      const int r = t * BB + threadIdx.x;
+      float* st_ = s_stat + (t & 1) * 2 * BB;
+      st_[threadIdx.x] = r < p.N ? lse_b[r] : INFINITY;        // 2^(-inf) = 0: out-of-range queries contribute nothing
+      st_[BB + threadIdx.x] = r < p.N ? dv_b[r] : 0.f;
     }
-    b_cp_wait_all();
-    __syncthreads();
+  };
+  stream_tile(0);
+  for (int j = 0; j < T_q; ++j) {
+    b_cp_wait0();
+    __syncthreads();                       // tile j has landed; every warp is done with tile j-1, whose buffer is refilled now
+    if (j + 1 < T_q) stream_tile(j + 1);
+    const uint32_t sQ = sQD + (j & 1) * 2 * TILE, sdO = sQ + TILE;
+    const float* s_lse = s_stat + (j & 1) * 2 * BB;
+    const float* s_dv = s_lse + BB;
     float st[8][4], dpt[8][4];       // S^T and dP^T: rows = this warp's 16 keys, columns = 64 queries
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -573,7 +590,7 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const __nv_bfloa
 template <int D>
 static int launch_attn_bwd(const AttnBwdParams& p, int n_img, cudaStream_t st) {
   constexpr int TILE = BB * D * 2;
-  const int smem_dq = 4 * TILE, smem_dkv = 4 * TILE + 2 * BB * 4;
+  const int smem_dq = 6 * TILE, smem_dkv = 6 * TILE + 4 * BB * 4;
   static DeviceOnce attr;
   if (attr.first()) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
