@@ -149,7 +149,8 @@ LKGD_API int lkgd_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t 
 /* Same normalisation with the statistics already accumulated by the producing lkgd_gemm launches (gn_stats):
  * stats1 / stats2 are [NS * frames_per_sample][C1 or C2][2] doubles (per frame image, channel); frames_per_sample = 1
  * for the spatial GroupNorms (NS = B*F) and F for the temporal ones (NS = B, statistics across frames).  One pass over
- * the tensor instead of two.  raw_out (bf16 [NS, R, C1+C2], may be NULL) additionally receives the UN-normalised,
+ * the tensor instead of two; the workspace is left exactly as lkgd_groupnorm leaves it (per-(sample, channel) sums first),
+ * so lkgd_groupnorm_bwd can take it as fwd_sums.  raw_out (bf16 [NS, R, C1+C2], may be NULL) additionally receives the UN-normalised,
  * concatenated input narrowed to bf16: the operand of the resblock's 1x1 conv_shortcut, for free in the same pass. */
 LKGD_API int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const double* stats1, const void* x2, int32_t C2,
                    const double* stats2, int32_t NS, int32_t R, int32_t frames_per_sample, int32_t groups,

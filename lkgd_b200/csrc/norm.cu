@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(128) gn_finalize_frames_kernel(const double* _
                                                                  const double* __restrict__ st2, int C2, int fps,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps, int groups,
-                                                                 int R, float2* __restrict__ ss /* [NS][C] */) {
+                                                                 int R, float2* __restrict__ ss /* [NS][C] */,
+                                                                 double* __restrict__ sums /* [NS][C][2] */) {
   __shared__ double red[2][128];
   const int C = C1 + C2;
   const int cpg = C / groups;
@@ -135,6 +136,15 @@ __global__ void __launch_bounds__(128) gn_finalize_frames_kernel(const double* _
   for (int c = gi * cpg + threadIdx.x; c < (gi + 1) * cpg; c += blockDim.x) {
     const float sc = rstd * gamma[c];
     ss[(size_t)ns * C + c] = make_float2(sc, beta[c] - fmean * sc);
+    // per-(sample, channel) sums in the layout lkgd_groupnorm leaves behind: what the GroupNorm backward re-reads
+    double cs = 0.0, cq = 0.0;
+    for (int f = 0; f < fps; ++f) {
+      const double* st = c < C1 ? st1 + (((size_t)ns * fps + f) * C1 + c) * 2
+                                : st2 + (((size_t)ns * fps + f) * C2 + (c - C1)) * 2;
+      cs += st[0]; cq += st[1];
+    }
+    sums[((size_t)ns * C + c) * 2] = cs;
+    sums[((size_t)ns * C + c) * 2 + 1] = cq;
   }
 }
 
@@ -477,7 +487,7 @@ extern "C" int lkgd_groupnorm_from_stats(const void* x1, int32_t C1, const doubl
   const size_t sums_bytes = (size_t)NS * C * 2 * sizeof(double);
   float2* ss = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + sums_bytes);
   gn_finalize_frames_kernel<<<NS * groups, 128, 0, st>>>(stats1, C1, stats2, C2, frames_per_sample, gamma, beta, eps, groups,
-                                                          R, ss);
+                                                          R, ss, reinterpret_cast<double*>(workspace));
   int rc = launch_epilogue();
   if (rc) return rc;
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);

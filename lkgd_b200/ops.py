@@ -272,7 +272,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     ws_bytes = lib.lkgd_groupnorm_workspace(NS, Ct)
     ws = torch.empty(ws_bytes, device=x1.device, dtype=torch.uint8)
     st1, st2 = gn_stats_of(x1), gn_stats_of(x2)
-    fused = (not return_stats and st1 is not None and (x2 is None or (st2 is not None and st2[1] == st1[1]))
+    fused = (st1 is not None and (x2 is None or (st2 is not None and st2[1] == st1[1]))
              and R % st1[1] == 0 and st1[0].shape[0] * st1[1] == NS * R)
     if fused:
         raw = torch.empty((NS * R, Ct), device=x1.device, dtype=bf16) if want_raw else None
@@ -283,6 +283,8 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
                                               groups, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
                                               int(x1.dtype == torch.float32), out.data_ptr(), _ptr(raw), ws.data_ptr(),
                                               ws_bytes, _stream()), "lkgd_groupnorm_from_stats")
+        if return_stats:                     # the workspace now holds the per-(sample, channel) sums, as after lkgd_groupnorm
+            return out, ws
         return (out, raw) if want_raw else out
     if L.PROF.enabled:   # algorithmic bytes: input read twice (statistics, then normalise) + bf16 output
         L.PROF.meta = {"bytes": NS * R * Ct * (2 * x1.element_size() + 2)}

@@ -107,8 +107,10 @@ def resblock_fwd(p: PackedResBlock, x, skip, g: Geom, cond: Conditioning):
     """engine.run_resblock with the tensors the backward needs kept (GroupNorm inputs + statistics)."""
     S = NS(x=x, skip=skip)
     h, S.st1 = ops.groupnorm(x, p.n1.g, p.n1.b, p.n1.eps, NS=g.BF, R=g.HW, x2=skip, silu=True, return_stats=True)
+    # gn_rows: the producing GEMM's epilogue accumulates the GroupNorm statistics of what it stores (as in inference); the
+    # fused GroupNorm leaves the same per-(sample, channel) sums behind that the backward re-reads
     S.c1 = ops.gemm(h, p.w1, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b1, rowvec=cond.temb(p.off_s, p.cout),
-                    rv=g.rv(RV_BATCH), out_f32=True)
+                    rv=g.rv(RV_BATCH), out_f32=True, gn_rows=g.HW)
     h, S.st2 = ops.groupnorm(S.c1, p.n2.g, p.n2.b, p.n2.eps, NS=g.BF, R=g.HW, silu=True, return_stats=True)
     if p.wsc is not None:
         xa = ops.cast_bf16(x) if skip is None else ops.concat_channels(x, skip)
@@ -117,13 +119,13 @@ def resblock_fwd(p: PackedResBlock, x, skip, g: Geom, cond: Conditioning):
         if skip is not None:
             raise ValueError("resblock with concatenated input must have a shortcut conv")
         sc = x
-    S.s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True)
+    S.s = ops.gemm(h, p.w2, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=p.b2, res1=sc, out_f32=True, gn_rows=g.HW)
     t, S.st3 = ops.groupnorm(S.s, p.tn1.g, p.tn1.b, p.tn1.eps, NS=g.B, R=g.F * g.HW, silu=True, return_stats=True)
     S.c3 = ops.gemm(t, p.tw1, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb1, rowvec=cond.temb(p.off_t, p.cout),
-                    rv=g.rv(RV_BATCH), out_f32=True)
+                    rv=g.rv(RV_BATCH), out_f32=True, gn_rows=g.HW)
     t, S.st4 = ops.groupnorm(S.c3, p.tn2.g, p.tn2.b, p.tn2.eps, NS=g.B, R=g.F * g.HW, silu=True, return_stats=True)
     out = ops.gemm(t, p.tw2, mode=A_TCONV3, tconv=(g.B, g.F, g.HW), bias=p.tb2, s0=1.0 - p.alpha, res1=S.s, s1=1.0,
-                   out_f32=True)
+                   out_f32=True, gn_rows=g.HW)
     return out, S
 
 
@@ -188,7 +190,7 @@ def transformer_fwd(p: PackedTransformer, x, g: Geom, cond: Conditioning, tctx_m
     n = ops.layernorm(S.t_b, p.t_ln3.g, p.t_ln3.b, p.t_ln3.eps, addvec=cond.cross_vec_t(p.t_cross),
                       rv=(tctx_mode, g.HW, g.F, S.n_tctx), sum_out=S.t_b)
     S.t_pre, mix = _ff_fwd(n, p.t_ff1, p.t_ff2, s0=1.0 - p.alpha, res1=S.t_b, s1=1.0 - p.alpha, res2=S.xs, s2=p.alpha)
-    out = dense(mix, p.proj_out, res1=x, out_f32=True)
+    out = dense(mix, p.proj_out, res1=x, out_f32=True, gn_rows=g.HW if g.HW % 128 == 0 else 0)
     return out, S
 
 
@@ -249,7 +251,8 @@ class TrainGraph:
     def forward(self, x: torch.Tensor, g: Geom, cond: Conditioning) -> torch.Tensor:
         pk, tape = self.pk, self.tape
         tm = pk.tctx_mode
-        x = ops.gemm(x, pk.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=pk.conv_in_b, out_f32=True)
+        x = ops.gemm(x, pk.conv_in_w, mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=pk.conv_in_b, out_f32=True,
+                     gn_rows=g.HW)
         skips = [x]
         tape.append(("skip", 0))
         for res, att, ds in pk.down:
@@ -263,7 +266,8 @@ class TrainGraph:
                 skips.append(x)
             if ds is not None:
                 gin = g
-                x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1], out_f32=True)
+                x = ops.gemm(ops.cast_bf16(x), ds[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 2), bias=ds[1], out_f32=True,
+                             gn_rows=g.down().HW)
                 g = g.down()
                 tape.append(("down", ds, gin))
                 tape.append(("skip", len(skips)))
@@ -288,7 +292,7 @@ class TrainGraph:
                 gin = g
                 x = ops.upsample2x(x, g.BF, g.H, g.W)
                 g = g.up()
-                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True)
+                x = ops.gemm(x, us[0], mode=A_CONV3X3, conv=(g.BF, g.H, g.W, 1), bias=us[1], out_f32=True, gn_rows=g.HW)
                 tape.append(("up", us, gin, g))
         h, st = ops.groupnorm(x, pk.norm_out.g, pk.norm_out.b, pk.norm_out.eps, NS=g.BF, R=g.HW, silu=True,
                               return_stats=True)
@@ -588,6 +592,7 @@ class LoraTrainer:
         emb = pk.time_embedding(timesteps, added_time_ids.to(dev))
         cond = Conditioning(pk, emb, ctx)
         g = Geom(B, F, h, w)
+        ops.STATS_ARENA.begin(dev)            # one zeroed buffer for the fused GroupNorm statistics of this forward
         graph = TrainGraph(pk)
         pred = graph.forward(x_in, g, cond)
         loss, dpred = ops.edm_loss(pred, noisy, latents, sigmas, pk.conv_out_w.shape[0])
