@@ -68,6 +68,32 @@ def test_unet_step_parity_reduced(cuda, B, order):
     assert err < 1e-2
 
 
+@pytest.mark.parametrize("B,Fr,H,W", [(1, 1, 16, 16), (3, 2, 8, 24), (2, 32, 8, 8), (5, 3, 16, 8)])
+def test_unet_edge_geometries(cuda, B, Fr, H, W):
+    """Edge cases of the step's geometry: a single frame (every temporal conv / attention / 5-D GroupNorm degenerates), an odd
+    batch (the 0.27.2 temporal-context order then wraps unevenly over the pixels), the 32-frame maximum of the temporal
+    kernels, the smallest latents the two-level configuration divides; and the argument errors either side of them."""
+    import oracle as O
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    x, ctx, ids = _inputs(cfg, B, Fr, H, W, 32)
+    with torch.no_grad():
+        ref = o(x, 0.7, ctx, added_time_ids=ids, return_dict=False)[0]
+    got = p(x.to(cuda), 0.7, ctx.to(cuda), added_time_ids=ids.to(cuda), return_dict=False)[0]
+    err = rel_l2(got, ref)
+    print("geometry", (B, Fr, H, W), "rel_l2", err)
+    assert got.shape == ref.shape and err < 1e-2
+    with pytest.raises(ValueError, match="at most 32 frames"):
+        p(torch.zeros(1, 33, 8, 8, 8, device=cuda), 0.7, ctx[:1].to(cuda), added_time_ids=ids[:1].to(cuda))
+    with pytest.raises(ValueError, match="divisible by 2"):
+        p(torch.zeros(1, 2, 8, 9, 8, device=cuda), 0.7, ctx[:1].to(cuda), added_time_ids=ids[:1].to(cuda))
+    with pytest.raises(ValueError, match="channels"):
+        p(torch.zeros(1, 2, 4, 8, 8, device=cuda), 0.7, ctx[:1].to(cuda), added_time_ids=ids[:1].to(cuda))
+    with pytest.raises(ValueError, match="batch does not match"):
+        p(x.to(cuda), 0.7, torch.cat([ctx, ctx]).to(cuda), added_time_ids=ids.to(cuda))
+
+
 def test_unet_wider_config_d64_and_tensor_timestep(cuda):
     """3-level config with 64-wide heads (the SVD head size) and non-power-of-two frames."""
     import oracle as O
