@@ -356,6 +356,36 @@ def test_full_25_step_trajectory(cuda, name):
     assert rel_l2(got, ref) < 2e-2
 
 
+@pytest.mark.parametrize("S,steps,graph", [(1, 4, False), (3, 3, True), (2, 1, False)])
+def test_pipeline_without_classifier_free_guidance(cuda, S, steps, graph):
+    """`max_guidance_scale <= 1` switches classifier-free guidance off (reference pipeline :485, :579, :612): no batch
+    duplication, no CFG combine - the conditioning arrives with batch S, the Euler step consumes the raw prediction.  Also a
+    one-step schedule and an odd number of samples; with and without the CUDA graph."""
+    import oracle as O
+    from oracle.scheduler import SVD_SCHEDULER_CONFIG
+    from lkgd_b200.pipeline import StableVideoDiffusionPipeline
+    from lkgd_b200.scheduler import EulerDiscreteScheduler
+    from lkgd_b200.unet import REDUCED_CONFIG, UNetSpatioTemporalConditionControlNetModel
+    cfg = dict(REDUCED_CONFIG)
+    o, p = _pair(O.UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionControlNetModel, cfg, cuda)
+    Fr, h, w = 4, 16, 16
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(S, Fr, 4, h, w, generator=g)
+    img_lat = torch.randn(S, 1, 4, h, w, generator=g).repeat(1, Fr, 1, 1, 1)
+    emb = torch.randn(S, 1, 32, generator=g)
+    osched = O.EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG)
+    osched.set_timesteps(steps)
+    ids = O.add_time_ids_inference(6, 127, 0.02, S, do_cfg=False)
+    with torch.no_grad():
+        ref = O.denoise_loop(o, osched, noise * osched.init_noise_sigma, img_lat, emb, ids, steps, 1.0, 1.0)
+    pipe = StableVideoDiffusionPipeline(p, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))
+    got = pipe(emb, img_lat, num_frames=Fr, num_inference_steps=steps, fps=7, min_guidance_scale=1.0, max_guidance_scale=1.0,
+               latents=noise, use_cuda_graph=graph).frames
+    err = rel_l2(got, ref)
+    print("no CFG, S", S, "steps", steps, "graph", graph, "rel-L2", err)
+    assert tuple(got.shape) == (S, Fr, 4, h, w) and err < 1e-2
+
+
 def test_cuda_graph_replay_equals_the_eager_loop(cuda):
     """the denoise step captured once in a CUDA graph (per-step scalars read from device memory,
     latents updated in place) must reproduce the kernel-by-kernel loop over all 25 steps - same kernels, same order; the
