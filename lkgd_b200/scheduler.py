@@ -74,7 +74,7 @@ class EulerDiscreteScheduler:
     # ------------------------------------------------------------------ schedule (host)
     def _train_sigmas(self) -> np.ndarray:
         a = self._alphas_cumprod
-        return np.array(((1 - a) / a) ** 0.5)      # float32 tensor -> float32 ndarray, as the reference
+        return (((1 - a) / a) ** 0.5).numpy()      # float32 tensor -> float32 ndarray (np.array(tensor) in the reference)
 
     def _install(self, sigmas: np.ndarray, timesteps: np.ndarray, device):
         sig32 = sigmas.astype(np.float32)

@@ -41,7 +41,7 @@ class EulerDiscreteScheduler:
         else:
             raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
         self.alphas_cumprod = torch.cumprod(1.0 - self.betas, dim=0)
-        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)[::-1].copy()
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()[::-1].copy()
         timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy()
         if use_karras_sigmas:
             log_sigmas = np.log(sigmas)
@@ -99,7 +99,7 @@ class EulerDiscreteScheduler:
         else:
             raise ValueError(f"{c.timestep_spacing} is not supported. Please make sure to choose one of "
                              "'linspace', 'leading' or 'trailing'.")
-        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         log_sigmas = np.log(sigmas)
         if c.interpolation_type == "linear":
             sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
