@@ -205,3 +205,30 @@ def test_pipeline_image_to_frames(cuda):
     assert npv.shape == (1, Fr, Hh, Ww, 3)
     with pytest.raises(ValueError):
         StableVideoDiffusionPipeline(pu, EulerDiscreteScheduler(**SVD_SCHEDULER_CONFIG))(image=image, num_frames=Fr)
+
+
+def test_vae_full_size_chunk_invariance(cuda):
+    """Size-independent property at the headline size (25 frames of 576x1024, SVD widths, 14.7 M output rows in one launch, ~54 GB):
+    with the temporal branch switched off (mix_factor -> -inf: the switched blender's alpha is exactly 1; identity time_conv_out)
+    every frame is decoded independently, so ONE 25-frame chunk must equal the reference scripts' chunks of 8 (8, 8, 8, 1) bit for
+    bit - row indexing, tile order (pixel-tile-major temporal convs above 16 MB per frame), fused GroupNorm statistics and the
+    NCHW unpack at full size."""
+    from lkgd_b200.vae import SVD_VAE_CONFIG, AutoencoderKLTemporalDecoder
+    torch.manual_seed(0)
+    vae = AutoencoderKLTemporalDecoder(**SVD_VAE_CONFIG)
+    with torch.no_grad():
+        for n, prm in vae.named_parameters():
+            if n.endswith("mix_factor"):
+                prm.fill_(-40.0)
+        w = vae.decoder.time_conv_out.weight
+        w.zero_()
+        w[:, :, 1, 0, 0] = torch.eye(3)
+        vae.decoder.time_conv_out.bias.zero_()
+    vae = vae.to(cuda)
+    z = torch.randn(25, 4, 72, 128, device=cuda)
+    full = vae.decode(z, num_frames=25).sample
+    assert tuple(full.shape) == (25, 3, 576, 1024) and bool(torch.isfinite(full).all())
+    parts = torch.cat([vae.decode(z[i:i + 8], num_frames=z[i:i + 8].shape[0]).sample for i in range(0, 25, 8)])
+    assert torch.equal(full, parts) and float(parts.abs().mean()) > 1e-2
+    del full, parts
+    torch.cuda.empty_cache()
