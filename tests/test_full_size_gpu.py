@@ -95,3 +95,44 @@ def test_full_size_c4_controlnet_14_frames(cuda):
     print("C4 full-size rel-L2: unet", err, "controlnet mid residual", err_mid, json.loads(str(G["meta"])))
     assert err_mid < 1.5e-2
     assert err < 1e-2
+
+
+def test_full_size_c5_training_step(cuda):
+    """BASELINE.json configs[4]: ONE full-size LoRA fine-tuning step (SVD-XT-width LKGD UNet, r = 64, 14 frames of 40x64 latents,
+    batch 1): loss and gradients of the hand-scheduled CUDA backward against autograd through the fp32 oracle
+    (tests/golden/make_train_golden.py: loss, the gradient norm of all 125 trainable tensors, eight complete gradient tensors).
+    Tolerances as in tests/test_training_gpu.py: loss 1e-2 relative, every tensor 5e-2, all norms together 3e-2."""
+    import make_train_golden as TG
+    from lkgd_b200.training import LoraTrainer
+    from lkgd_b200.unet import UNetSpatioTemporalConditionModel
+    G = _fixture("c5")
+    u = UNetSpatioTemporalConditionModel(**TG.config())
+    u.add_lora(TG.RANK)
+    u = fill_seeded_(u).to(cuda)
+    lat, noise, cond, ctx, sig, ids, extra = TG.inputs()
+    tr = LoraTrainer(u)
+    loss = tr.forward_backward(lat.to(cuda), noise.to(cuda), sig.to(cuda), cond.to(cuda), ctx.to(cuda), ids.to(cuda),
+                               *(e.to(cuda) for e in extra))
+    got = dict(tr.named_grads())
+    names = [str(n) for n in G["names"]]
+    assert sorted(got) == sorted(names) and len(names) == 125
+    ref_loss = float(G["loss"])
+    assert abs(float(loss) - ref_loss) < 1e-2 * abs(ref_loss), (float(loss), ref_loss)
+    norms = {n: float(v) for n, v in zip(names, G["norms"])}
+    worst = max((abs(float(got[n].double().norm()) / norms[n] - 1.0), n) for n in names if norms[n] > 1e-12)
+    num = den = 0.0
+    worst_full = (0.0, "")
+    for key in G.files:
+        if not key.startswith("grad/"):
+            continue
+        n = key[5:]
+        ref = torch.from_numpy(G[key].astype(np.float32))
+        e = rel_l2(got[n], ref)
+        num += float((got[n].double().cpu() - ref.double()).pow(2).sum())
+        den += float(ref.double().pow(2).sum())
+        worst_full = max(worst_full, (e, n))
+    print(f"C5 full-size: loss {float(loss):.6f} vs {ref_loss:.6f}; worst gradient-norm deviation {worst[0]:.3e} ({worst[1]}); "
+          f"complete tensors: all {((num / den) ** 0.5):.3e}, worst {worst_full[0]:.3e} ({worst_full[1]})",
+          json.loads(str(G["meta"])))
+    assert worst[0] < 5e-2, worst
+    assert worst_full[0] < 5e-2 and (num / den) ** 0.5 < 3e-2
