@@ -11,6 +11,8 @@
 // mma.sync m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix from XOR-swizzled smem tiles; the problems are small
 // (training runs 14 frames at 40x64 latents) and the backward is a fraction of the step, so the legacy tensor path is
 // adequate here; the forward stays on tcgen05.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -604,6 +606,11 @@ static int launch_attn_bwd(const AttnBwdParams& p, int n_img, cudaStream_t st) {
   return launch_epilogue();
 }
 
+// attention_bwd_tc.cu: the same two passes on tcgen05 / TMEM (64-wide heads)
+int attn_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* dO, int ldo,
+                const float* lse, const float* dvec, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int n_img,
+                int heads, int N, float scale, cudaStream_t st);
+
 }  // namespace lkgd
 
 using namespace lkgd;
@@ -630,6 +637,9 @@ extern "C" int lkgd_attention_bwd(const void* q, int32_t ldq, const void* k, int
       reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dO), ldo, rows, heads, d, N, dvec);
   int rc = launch_epilogue();
   if (rc) return rc;
+  // 64-wide heads (the SVD checkpoints): tcgen05 / TMEM kernels; LKGD_ATTN_BWD_MMA=1 keeps the mma.sync pair (A/B switch)
+  if (d == 64 && !getenv("LKGD_ATTN_BWD_MMA"))
+    return attn_bwd_tc(q, ldq, k, ldk, v, ldv, dO, ldo, lse, dvec, dq, lddq, dk, lddk, dv, lddv, n_img, heads, N, scale, st);
   AttnBwdParams p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.k = reinterpret_cast<const __nv_bfloat16*>(k);
   p.v = reinterpret_cast<const __nv_bfloat16*>(v); p.dO = reinterpret_cast<const __nv_bfloat16*>(dO);

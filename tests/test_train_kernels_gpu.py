@@ -182,7 +182,10 @@ def test_tconv3_dgrad_via_gemm(cuda):
 
 # ------------------------------------------------------------------------------------------------- attention backward
 @pytest.mark.parametrize("n_img,heads,d,N", [(2, 2, 64, 200), (1, 3, 16, 64), (3, 1, 32, 130), (1, 5, 64, 640),
-                                             (2, 2, 128, 200), (1, 3, 128, 576)])     # d = 128: reference-default heads
+                                             (2, 2, 128, 200), (1, 3, 128, 576),      # d = 128: reference-default heads
+                                             # d = 64 runs on the tcgen05 / TMEM kernels: ragged tails of the 128-row
+                                             # resident tile and of the 64-row streamed tile, one tile, the C5 level-0 size
+                                             (3, 1, 64, 130), (1, 2, 64, 64), (2, 1, 64, 65), (1, 5, 64, 2560)])
 def test_attention_bwd(cuda, n_img, heads, d, N):
     from lkgd_b200 import ops
     C = heads * d
@@ -205,6 +208,29 @@ def test_attention_bwd(cuda, n_img, heads, d, N):
                       d=d, N=N)
     for name, got, ref in (("dq", dqkv[:, :C], qf.grad), ("dk", dqkv[:, C:2 * C], kf.grad), ("dv", dqkv[:, 2 * C:], vf.grad)):
         assert rel_l2(split(got), ref) < 1.2e-2, name
+
+
+def test_attention_bwd_tcgen05_equals_the_mma_sync_kernels(cuda, monkeypatch):
+    """64-wide heads: the tcgen05 / TMEM backward (attention_bwd_tc.cu) against the mma.sync pair it replaces
+    (LKGD_ATTN_BWD_MMA=1) on the same inputs - two independent implementations of the same formulas."""
+    from lkgd_b200 import ops
+    n_img, heads, d, N = 2, 3, 64, 333
+    C = heads * d
+    qkv = rnd(n_img * N, 3 * C, dev=cuda, seed=5)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    o, lse = ops.attention(q, k, v, n_img=n_img, heads=heads, d=d, Nq=N, Nk=N, return_lse=True)
+    dO = rnd(n_img * N, C, dev=cuda, seed=6)
+    outs = []
+    for legacy in (False, True):
+        if legacy:
+            monkeypatch.setenv("LKGD_ATTN_BWD_MMA", "1")
+        else:
+            monkeypatch.delenv("LKGD_ATTN_BWD_MMA", raising=False)
+        g = torch.zeros_like(qkv)
+        ops.attention_bwd(q, k, v, o, dO, lse, g[:, :C], g[:, C:2 * C], g[:, 2 * C:], n_img=n_img, heads=heads, d=d, N=N)
+        outs.append(g)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        assert rel_l2(outs[0][:, i * C:(i + 1) * C].float(), outs[1][:, i * C:(i + 1) * C].float()) < 6e-3, name
 
 
 @pytest.mark.parametrize("B_,Fr,HW,heads,d", [(1, 14, 40, 2, 64), (2, 8, 33, 4, 16), (1, 25, 17, 1, 32), (1, 32, 8, 2, 64),
