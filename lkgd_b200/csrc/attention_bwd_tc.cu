@@ -27,7 +27,7 @@ namespace lkgd {
 constexpr int TB_ROWS = 128, TB_STEP = 64, TB_D = 64;
 constexpr int TB_RES = TB_ROWS * TB_D * 2;      // 16 KB resident tile
 constexpr int TB_STR = TB_STEP * TB_D * 2;      // 8 KB streamed tile
-constexpr int TB_NS = 2;                        // streamed stages
+constexpr int TB_NS = 3;                        // streamed stages
 constexpr int TB_THREADS = 192;
 constexpr int TB_SMEM = 2 * TB_RES + TB_NS * 2 * TB_STR + 2 * 2 * TB_STEP * 4 + 256;
 
@@ -56,6 +56,48 @@ __device__ __forceinline__ float tb_ex2_poly(float x) {
   p = fmaf(p, r, 0.6932609677f);
   p = fmaf(p, r, 0.9999280572f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
+// ---- packed fp32x2 helpers (FFMA2 / FADD2 / FMUL2: one issue slot for two elements), as in attention.cu
+__device__ __forceinline__ uint64_t tb_pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void tb_upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t tb_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t tb_add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t tb_mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t tb_ex2_poly2(uint64_t X) {
+  float x0, x1;
+  tb_upk2(X, x0, x1);
+  X = tb_pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t MAGIC = tb_pk2(12582912.0f, 12582912.0f), NMAGIC = tb_pk2(-12582912.0f, -12582912.0f);
+  const uint64_t T = tb_add2(X, MAGIC);
+  const uint64_t N = tb_add2(T, NMAGIC);
+  const uint64_t R = tb_fma2(N, tb_pk2(-1.0f, -1.0f), X);
+  uint64_t P = tb_fma2(tb_pk2(0.0551716685f, 0.0551716685f), R, tb_pk2(0.2426111251f, 0.2426111251f));
+  P = tb_fma2(P, R, tb_pk2(0.6932609677f, 0.6932609677f));
+  P = tb_fma2(P, R, tb_pk2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  tb_upk2(T, t0, t1);
+  tb_upk2(P, p0, p1);
+  return tb_pk2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+                __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
 }
 
 template <bool DKV>
@@ -155,11 +197,11 @@ __global__ void __launch_bounds__(TB_THREADS, 2) attn_bwd_tc_kernel(const __grid
     for (int j = 0; j < T; ++j) {
       float* st_ = s_stat + (j & 1) * 2 * TB_STEP;
       if (DKV) {
-        // statistics of the 64 queries of this step: thread t < 64 fetches lse, t >= 64 fetches Dv (out of range: +inf / 0,
-        // so that 2^(-inf) = 0 removes the query)
+        // NEGATED statistics of the 64 queries of this step: thread t < 64 fetches -lse, t >= 64 fetches -Dv (out of range:
+        // -inf / 0, so that 2^(-inf) = 0 removes the query)
         const int q = j * TB_STEP + (r & 63);
-        float v = r < 64 ? INFINITY : 0.f;
-        if (q < p.N) v = r < 64 ? p.lse[stat_base + q] : p.dvec[stat_base + q];
+        float v = r < 64 ? -INFINITY : 0.f;
+        if (q < p.N) v = r < 64 ? -p.lse[stat_base + q] : -p.dvec[stat_base + q];
         st_[r] = v;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -173,26 +215,34 @@ __global__ void __launch_bounds__(TB_THREADS, 2) attn_bwd_tc_kernel(const __grid
         tmem_ld32(tmem_T1 + lane_addr + hf * 32, s);
         tmem_ld32(tmem_T2 + lane_addr + hf * 32, dp);
         tmem_ld_wait();
+        const uint64_t SC2 = tb_pk2(sc, sc);
+        const uint64_t NL2r = tb_pk2(-lse_r, -lse_r), ND2r = tb_pk2(-dv_r, -dv_r);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int col = hf * 32 + i;
-          float l0, l1, d0, d1;
+          uint64_t NL2 = NL2r, ND2 = ND2r;
           if (DKV) {
-            const float2 lv = *reinterpret_cast<const float2*>(st_ + col);
-            const float2 dv = *reinterpret_cast<const float2*>(st_ + TB_STEP + col);
-            l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
+            NL2 = *reinterpret_cast<const uint64_t*>(st_ + col);
+            ND2 = *reinterpret_cast<const uint64_t*>(st_ + TB_STEP + col);
+          }
+          const uint64_t X = tb_fma2(tb_pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), SC2, NL2);
+          uint64_t P;
+          if ((i >> 1) % 3 == 2) {
+            P = tb_ex2_poly2(X);
           } else {
-            l0 = l1 = lse_r; d0 = d1 = dv_r;
+            float x0, x1;
+            tb_upk2(X, x0, x1);
+            P = tb_pk2(tb_ex2(x0), tb_ex2(x1));
           }
-          const float x0 = fmaf(__uint_as_float(s[i]), sc, -l0), x1 = fmaf(__uint_as_float(s[i + 1]), sc, -l1);
-          float p0, p1;
-          if ((i >> 1) % 3 == 2) { p0 = tb_ex2_poly(x0); p1 = tb_ex2_poly(x1); }
-          else { p0 = tb_ex2(x0); p1 = tb_ex2(x1); }
-          if (!DKV) {                                // zero-filled keys beyond the sequence would still give 2^(-lse)
-            if (col >= valid) p0 = 0.f;
-            if (col + 1 >= valid) p1 = 0.f;
+          if (!DKV && valid < TB_STEP) {             // zero-filled keys beyond the sequence would still give 2^(-lse)
+            float p0, p1;
+            tb_upk2(P, p0, p1);
+            P = tb_pk2(col < valid ? p0 : 0.f, col + 1 < valid ? p1 : 0.f);
           }
-          const float g0 = p0 * (__uint_as_float(dp[i]) - d0), g1 = p1 * (__uint_as_float(dp[i + 1]) - d1);
+          const uint64_t G = tb_mul2(P, tb_add2(tb_pk2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), ND2));
+          float p0, p1, g0, g1;
+          tb_upk2(P, p0, p1);
+          tb_upk2(G, g0, g1);
           s[i >> 1] = pack_bf16x2(p0, p1);
           dp[i >> 1] = pack_bf16x2(g0, g1);
         }
