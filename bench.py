@@ -369,6 +369,12 @@ def run_train(args):
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
         tr._graph = None                         # per-kernel event breakdown on the eager path
+        if args.profiler_step:                   # ncu launch list of ONE eager training step (--profile-from-start off)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
+            step(dev)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
         _lib.PROF.records, _lib.PROF.enabled = [], True
         step(dev)
         torch.cuda.synchronize()

@@ -292,6 +292,24 @@ static int choose_bn(int N, bool geglu) {
   return 256;  // tail tile handled by TMA zero-fill + store masking
 }
 
+// Few row tiles (the lower UNet levels of a 14-frame 40x64 training clip: 560 / 2240 rows): the widest tile leaves most
+// SMs without work (35 tiles for the level-3 convs).  Narrower tiles that still fit ONE wave trade MMA width for SMs.
+// Cost model fitted to tools/bench_gemm.py on the train_* shapes (tile time ~ BN + 64, waves = ceil(tiles / 148)):
+// level-3 conv 87 -> 44 us with BN = 64, level-2 linear 25.6 -> 21.4 us with BN = 160; the level-2 convs (100 tiles) and
+// every inference shape keep their tile.
+static void refine_bn(GemmParams& p, int N, bool geglu) {
+  if (geglu || getenv("LKGD_GEMM_BN") || getenv("LKGD_GEMM_NO_REFINE")) return;
+  if (N % 64 || (long long)p.m_tiles * p.n_tiles >= 148) return;
+  static const int cand[] = {160, 128, 64};
+  long long best = ((long long)p.m_tiles * p.n_tiles + 147) / 148 * (p.BN + 64);
+  for (int bn : cand) {
+    if (bn >= p.BN || N % bn) continue;
+    const long long tiles = (long long)p.m_tiles * (N / bn);
+    const long long cost = (tiles + 147) / 148 * (bn + 64);
+    if (cost < best) { best = cost; p.BN = bn; p.n_tiles = N / bn; }
+  }
+}
+
 static void choose_patch(int H, int W, int nimg, int& TW, int& TH, int& IPT) {
   // TW * TH * IPT = 128 rows per tile (all powers of two); minimise the padded row count, prefer wide patches (longer
   // contiguous runs) and one image per tile.  Small feature maps (9 x 16 at the bottom of the SVD UNet) put several
@@ -422,6 +440,7 @@ static int fill_params(const lkgd_gemm_args* a, GemmParams& p, bool& cta2) {
   } else {
     return LKGD_ESHAPE;
   }
+  refine_bn(p, a->N, geglu);
   cta2 = use_cta_pairs(p.m_tiles, p.n_tiles, p.BN, (long long)p.ntaps * a->K0 + a->K1);
   const int bn_load = cta2 ? p.BN / 2 : p.BN;
   {

@@ -43,22 +43,59 @@ __device__ __forceinline__ void gnb_load_x(const void* x1, const void* x2, const
 }
 
 // smem prologue shared by both passes: per-channel a[c] = rstd*gamma, b[c] = beta - mean*rstd*gamma, plus the group's
-// mean / rstd, from the forward's per-channel (sum, sum of squares)
-__device__ __forceinline__ void gnb_prologue(const GnbGeom& g, int ns, const double* fsums, const float* gamma,
-                                             const float* beta, float* sa, float* sb, float* gmean, float* grstd) {
+// mean / rstd, from the forward's per-channel (sum, sum of squares); with ``bsums`` (pass 2) also the group means of
+// g and g * xhat from pass 1.  Eight lanes per group, four groups per warp and round, every load of a round in flight
+// together (the thread-per-group loop this replaces was cpg dependent L2 round trips: ~20 us of the 22-30 us the two
+// passes took at the lower UNet levels).
+__device__ __forceinline__ void gnb_prologue(const GnbGeom& g, int ns, const double* fsums, const double* bsums,
+                                             const float* gamma, const float* beta, float* sa, float* sb, float* gmean,
+                                             float* grstd, float* m1, float* m2) {
   const int cpg = g.C / g.groups;
-  for (int gi = threadIdx.x; gi < g.groups; gi += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-      s += fsums[((size_t)ns * g.C + c) * 2];
-      q += fsums[((size_t)ns * g.C + c) * 2 + 1];
+  const double n = (double)cpg * g.R;
+  const int nw = blockDim.x >> 5;
+  if (nw > 0) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+    if (w < nw) {
+      for (int g0 = w * 4; g0 < g.groups; g0 += nw * 4) {
+        const int gi = g0 + sub;
+        double s = 0.0, q = 0.0, bs = 0.0, bq = 0.0;
+        if (gi < g.groups) {
+          for (int c = gi * cpg + sl; c < (gi + 1) * cpg; c += 8) {
+            const size_t at = ((size_t)ns * g.C + c) * 2;
+            s += fsums[at]; q += fsums[at + 1];
+            if (bsums != nullptr) { bs += bsums[at]; bq += bsums[at + 1]; }
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o);
+          bs += __shfl_xor_sync(0xffffffffu, bs, o); bq += __shfl_xor_sync(0xffffffffu, bq, o);
+        }
+        if (gi < g.groups && sl == 0) {
+          const double mean = s / n;
+          double var = q / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          gmean[gi] = (float)mean;
+          grstd[gi] = (float)(1.0 / sqrt(var + (double)g.eps));
+          if (bsums != nullptr) { m1[gi] = (float)(bs / n); m2[gi] = (float)(bq / n); }
+        }
+      }
     }
-    const double n = (double)cpg * g.R;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gmean[gi] = (float)mean;
-    grstd[gi] = (float)(1.0 / sqrt(var + (double)g.eps));
+  } else {                     // fewer than 32 threads (a handful of rows): thread per group
+    for (int gi = threadIdx.x; gi < g.groups; gi += blockDim.x) {
+      double s = 0.0, q = 0.0, bs = 0.0, bq = 0.0;
+      for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+        const size_t at = ((size_t)ns * g.C + c) * 2;
+        s += fsums[at]; q += fsums[at + 1];
+        if (bsums != nullptr) { bs += bsums[at]; bq += bsums[at + 1]; }
+      }
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gmean[gi] = (float)mean;
+      grstd[gi] = (float)(1.0 / sqrt(var + (double)g.eps));
+      if (bsums != nullptr) { m1[gi] = (float)(bs / n); m2[gi] = (float)(bq / n); }
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
@@ -87,7 +124,7 @@ __global__ void gn_bwd_stats_kernel(const void* __restrict__ x1, const void* __r
   float* grstd = gmean + g.groups;
   float* red = grstd + g.groups;   // [threads][16]
   const int ns = blockIdx.y;
-  gnb_prologue(g, ns, fsums, gamma, beta, sa, sb, gmean, grstd);
+  gnb_prologue(g, ns, fsums, nullptr, gamma, beta, sa, sb, gmean, grstd, nullptr, nullptr);
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
   const int cpg = g.C / g.groups;
   const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
@@ -141,18 +178,7 @@ __global__ void gn_bwd_apply_kernel(const void* __restrict__ x1, const void* __r
   float* m2 = m1 + g.groups;       // [groups] mean(g * xhat)
   const int ns = blockIdx.y;
   const int cpg = g.C / g.groups;
-  gnb_prologue(g, ns, fsums, gamma, beta, sa, sb, gmean, grstd);
-  for (int gi = threadIdx.x; gi < g.groups; gi += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-      s += bsums[((size_t)ns * g.C + c) * 2];
-      q += bsums[((size_t)ns * g.C + c) * 2 + 1];
-    }
-    const double n = (double)cpg * g.R;
-    m1[gi] = (float)(s / n);
-    m2[gi] = (float)(q / n);
-  }
-  __syncthreads();
+  gnb_prologue(g, ns, fsums, bsums, gamma, beta, sa, sb, gmean, grstd, m1, m2);
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
   const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
   float a[8], b[8], gm[8], xm[8], xr[8], k1[8], k2[8];
@@ -575,6 +601,45 @@ __global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, int lddy
   float* o = dx + (size_t)m * lddx + k;
   *o = accumulate ? *o + acc : acc;
 }
+// The same product for long contractions (N >= 512: the concatenated cross-attention matrices, [sum C, 1024] = 56 MB at
+// SVD width): a CTA owns 8 output columns and all of N, each thread reads one 32-byte sector of W per n (whole sectors,
+// K / 8 CTAs in flight instead of K / 128), block reduction in a fixed order (no atomics: bit-reproducible).
+__global__ void __launch_bounds__(256) small_linear_bwd_x_wide_kernel(
+    const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act_out,
+    const float* __restrict__ W, float* __restrict__ dx, int lddx, int N, int K, int accumulate) {
+  __shared__ float red[8][8];
+  const int k0 = blockIdx.x * 8;
+  const int m = blockIdx.y;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float g = dy[(size_t)m * lddy + n];
+    if (act_out) g *= act_grad_from_out(y[(size_t)m * ldy + n], act_out);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k0 + 4));
+    acc[0] = fmaf(g, w0.x, acc[0]); acc[1] = fmaf(g, w0.y, acc[1]);
+    acc[2] = fmaf(g, w0.z, acc[2]); acc[3] = fmaf(g, w0.w, acc[3]);
+    acc[4] = fmaf(g, w1.x, acc[4]); acc[5] = fmaf(g, w1.y, acc[5]);
+    acc[6] = fmaf(g, w1.z, acc[6]); acc[7] = fmaf(g, w1.w, acc[7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x >> 5][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    float* o = dx + (size_t)m * lddx + k0 + threadIdx.x;
+    *o = accumulate ? *o + s : s;
+  }
+}
 // dW[n, k] += sum_m dy'[m, n] * act_in(x[m, k]);  db[n] += sum_m dy'[m, n]
 __global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                                           int act_out, const float* __restrict__ x, int ldx, float* __restrict__ dW,
@@ -642,14 +707,23 @@ __global__ void hamilton_bwd_kernel(const float* __restrict__ dWt, int in, int o
   dk[idx] += D(0, 3) - D(3, 0) + D(1, 2) - D(2, 1);
 }
 
-static GnbGeom gnb_geom(int C1, int C2, int R, int x_f32, int groups, int silu, float eps) {
+static GnbGeom gnb_geom(int C1, int C2, int NS, int R, int x_f32, int groups, int silu, float eps) {
   GnbGeom g;
   g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
   g.groups = groups; g.silu = silu; g.eps = eps;
   g.rows_par = 256 / g.vecs;
   if (g.rows_par < 1) g.rows_par = 1;
   if (g.rows_par > R) g.rows_par = R;
-  g.rows_per_cta = g.rows_par * 8;
+  // up to 8 row passes per thread, fewer when that would leave SMs without a CTA (the lower UNet levels of a training
+  // clip: 14 x 40 rows at level 3)
+  int passes = 8;
+  if (const char* e = getenv("LKGD_GNB_PASSES")) {       // tuning experiments only
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) passes = v;
+  } else {
+    while (passes > 1 && (long long)((R + g.rows_par * passes - 1) / (g.rows_par * passes)) * NS < 148) --passes;
+  }
+  g.rows_per_cta = g.rows_par * passes;
   return g;
 }
 
@@ -673,7 +747,7 @@ extern "C" int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, in
     return LKGD_EALIGN;
   if (ws_bytes < lkgd_groupnorm_bwd_workspace(NS, C) || workspace == nullptr) return LKGD_EWS;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  GnbGeom g = gnb_geom(C1, C2, R, x_f32, groups, silu, eps);
+  GnbGeom g = gnb_geom(C1, C2, NS, R, x_f32, groups, silu, eps);
   cudaError_t e = cudaMemsetAsync(workspace, 0, lkgd_groupnorm_bwd_workspace(NS, C), st);
   if (e != cudaSuccess) return set_cuda_error(e);
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
@@ -854,8 +928,13 @@ extern "C" int lkgd_small_linear_bwd(const float* dy, int32_t lddy, const float*
   int rc = LKGD_OK;
   if (dx != nullptr) {
     if (W == nullptr) return LKGD_ESHAPE;
-    dim3 grid((K + 127) / 128, M);
-    small_linear_bwd_x_kernel<<<grid, 128, 0, st>>>(dy, lddy, y, ldy, act_out, W, dx, lddx, M, N, K, dx_accumulate);
+    if (N >= 512 && K % 8 == 0 && aligned16(W)) {
+      small_linear_bwd_x_wide_kernel<<<dim3(K / 8, M), 256, 0, st>>>(dy, lddy, y, ldy, act_out, W, dx, lddx, N, K,
+                                                                    dx_accumulate);
+    } else {
+      dim3 grid((K + 127) / 128, M);
+      small_linear_bwd_x_kernel<<<grid, 128, 0, st>>>(dy, lddy, y, ldy, act_out, W, dx, lddx, M, N, K, dx_accumulate);
+    }
     if ((rc = launch_epilogue())) return rc;
   }
   if (dW != nullptr || db != nullptr) {

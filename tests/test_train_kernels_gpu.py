@@ -311,3 +311,29 @@ def test_cast2d(cuda):
     ops.cast2d_bf16(src[:, 10:42], dst[:, 16:48], alpha=-2.0)
     assert torch.equal(dst[:, 16:48], (src[:, 10:42] * -2.0).to(bf16))
     assert float(dst[:, :16].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K,act", [(2, 96, 200, 3), (1, 1500, 1024, 0), (3, 777, 64, 3), (2, 512, 1000, 0)])
+def test_small_linear_bwd(cuda, M, N, K, act):
+    """dx / dW / db of the fp32 linear (latent-knowledge block, cross-attention vectors) against autograd; N >= 512 with
+    K % 8 == 0 takes the wide kernel (one CTA per 8 output columns), everything else the column-per-thread kernel."""
+    from lkgd_b200 import ops
+    x = rnd(M, K, dev=cuda, dtype=torch.float32, seed=1).requires_grad_(True)
+    W = (rnd(N, K, dev=cuda, dtype=torch.float32, seed=2) * 0.1).requires_grad_(True)
+    b = rnd(N, dev=cuda, dtype=torch.float32, seed=3).requires_grad_(True)
+    dy = rnd(M, N, dev=cuda, dtype=torch.float32, seed=4)
+    y = F.linear(x, W, b)
+    if act == 3:
+        y = F.leaky_relu(y, 0.1)
+    y.backward(dy)
+    dW = torch.full((N, K), 0.5, device=cuda)
+    db = torch.full((N,), -1.0, device=cuda)
+    dx = ops.small_linear_bwd(dy, W.detach(), x=x.detach(), y=y.detach() if act else None, act_out=act, dW=dW, db=db)
+    assert rel_l2(dx, x.grad) < 1e-5
+    assert rel_l2(dW - 0.5, W.grad) < 1e-5
+    assert rel_l2(db + 1.0, b.grad) < 1e-5
+    acc = torch.full((M, K + 8), 2.0, device=cuda)[:, :K]        # accumulate into a strided destination
+    ops.small_linear_bwd(dy, W.detach(), y=y.detach() if act else None, act_out=act, dx=acc)
+    assert rel_l2(acc - 2.0, x.grad) < 1e-5
+    again = ops.small_linear_bwd(dy, W.detach(), y=y.detach() if act else None, act_out=act)
+    assert torch.equal(again, dx)                                 # fixed reduction order

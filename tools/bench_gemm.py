@@ -46,6 +46,15 @@ SHAPES = [
     ("vae_tconv128_bf16", "tconv", (1, 8, 589824), 128, 128, "bf16"),
     ("vae_tconv256_res32gn", "tconv", (1, 8, 147456), 256, 256, "res32gn"),
     ("vae_conv256_res32gn", "conv", (8, 288, 512), 256, 256, "res32gn"),
+    # training shapes (C5: 14 frames, 40x64 latents): few 128-row tiles at the lower levels   [34..]
+    ("train_conv_L3", "conv", (14, 5, 8), 1280, 1280, "f32"),
+    ("train_conv_L2", "conv", (14, 10, 16), 1280, 1280, "f32"),
+    ("train_conv_L1", "conv", (14, 20, 32), 640, 640, "f32"),
+    ("train_tconv_L3", "tconv", (1, 14, 40), 1280, 1280, "f32"),
+    ("train_tconv_L2", "tconv", (1, 14, 160), 1280, 1280, "f32"),
+    ("train_lin_L3", "lin", 560, 1280, 1280, "res32"),
+    ("train_lin_L2", "lin", 2240, 1280, 1280, "res32"),
+    ("train_lin_L2_ff2", "lin", 2240, 1280, 5120, "res32"),
 ]
 
 
