@@ -29,27 +29,36 @@ __device__ __forceinline__ void ld8_any(const void* base, long long off, int is_
 }
 
 // ------------------------------------------------------------------------------------------- GroupNorm backward
-// Same thread layout as the forward kernels (norm.cu): blockDim.x = vecs * rows_par, thread -> (row lane, 8 channels).
+// blockDim.x = vecs * rows_par, thread -> (row lane, 4 channels).  Four channels per thread (not the forward's eight)
+// keep both passes at <= 64 registers: four 256-thread CTAs per SM and two rows of loads in flight per thread - the
+// 8-channel version sat at 96 registers = 2 CTAs / SM and reached a third of the HBM bandwidth on the 46 MB tensors of
+// a training clip (ncu: 44 + 57 us per GroupNorm at level 0).
 struct GnbGeom {
   int C1, C2, C, vecs, rows_par, R, rows_per_cta, x_f32, groups, silu;
   float eps;
 };
 
-__device__ __forceinline__ void gnb_load_x(const void* x1, const void* x2, const GnbGeom& g, long long row, int v,
-                                           float (&f)[8]) {
-  const int c = v * 8;
-  if (c < g.C1) ld8_any(x1, row * g.C1 + c, g.x_f32, f);
-  else ld8_any(x2, row * g.C2 + (c - g.C1), g.x_f32, f);
+__device__ __forceinline__ void ld4_any(const void* base, long long off, int is_f32, float (&f)[4]) {
+  if (is_f32) {
+    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void gnb_load_x(const void* x1, const void* x2, const GnbGeom& g, long long row, int c,
+                                           float (&f)[4]) {
+  if (c < g.C1) ld4_any(x1, row * g.C1 + c, g.x_f32, f);
+  else ld4_any(x2, row * g.C2 + (c - g.C1), g.x_f32, f);
 }
 
-// smem prologue shared by both passes: per-channel a[c] = rstd*gamma, b[c] = beta - mean*rstd*gamma, plus the group's
-// mean / rstd, from the forward's per-channel (sum, sum of squares); with ``bsums`` (pass 2) also the group means of
-// g and g * xhat from pass 1.  Eight lanes per group, four groups per warp and round, every load of a round in flight
-// together (the thread-per-group loop this replaces was cpg dependent L2 round trips: ~20 us of the 22-30 us the two
-// passes took at the lower UNet levels).
+// smem prologue shared by both passes: the groups' mean / rstd from the forward's per-channel (sum, sum of squares);
+// with ``bsums`` (pass 2) also the group means of g and g * xhat from pass 1.  Eight lanes per group, four groups per
+// warp and round, every load of a round in flight together (a thread-per-group loop is cpg dependent L2 round trips).
 __device__ __forceinline__ void gnb_prologue(const GnbGeom& g, int ns, const double* fsums, const double* bsums,
-                                             const float* gamma, const float* beta, float* sa, float* sb, float* gmean,
-                                             float* grstd, float* m1, float* m2) {
+                                             float* gmean, float* grstd, float* m1, float* m2) {
   const int cpg = g.C / g.groups;
   const double n = (double)cpg * g.R;
   const int nw = blockDim.x >> 5;
@@ -98,13 +107,6 @@ __device__ __forceinline__ void gnb_prologue(const GnbGeom& g, int ns, const dou
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
-    const int gi = c / cpg;
-    const float sc = grstd[gi] * gamma[c];
-    sa[c] = sc;
-    sb[c] = beta[c] - gmean[gi] * sc;
-  }
-  __syncthreads();
 }
 
 __device__ __forceinline__ float silu_grad(float z) {
@@ -112,116 +114,151 @@ __device__ __forceinline__ float silu_grad(float z) {
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
-// pass 1: per (sample, channel)  sum g  and  sum g * xhat,   g = dy * act'(z) * gamma
-__global__ void gn_bwd_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+// g = dy * act'(z) * gamma and xhat for one 4-channel piece of a row (z = xhat * gamma + beta)
+__device__ __forceinline__ void gnb_piece(const float (&f)[4], const float (&d)[4], const float (&gm)[4],
+                                          const float (&bt)[4], const float (&xr)[4], const float (&xmr)[4], int silu,
+                                          float (&gg)[4], float (&xh)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xh[i] = fmaf(f[i], xr[i], xmr[i]);
+    const float z = fmaf(xh[i], gm[i], bt[i]);
+    gg[i] = d[i] * (silu ? silu_grad(z) : 1.0f) * gm[i];
+  }
+}
+
+// pass 1: per (sample, channel)  sum g  and  sum g * xhat
+__global__ void __launch_bounds__(1024) gn_bwd_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
                                     const __nv_bfloat16* __restrict__ dy, GnbGeom g,
                                     const double* __restrict__ fsums, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, double* __restrict__ bsums) {
   extern __shared__ float sh[];
-  float* sa = sh;
-  float* sb = sh + g.C;
-  float* gmean = sh + 2 * g.C;
+  float* gmean = sh;
   float* grstd = gmean + g.groups;
-  float* red = grstd + g.groups;   // [threads][16]
+  float* red = grstd + g.groups;   // [8][threads]
   const int ns = blockIdx.y;
-  gnb_prologue(g, ns, fsums, nullptr, gamma, beta, sa, sb, gmean, grstd, nullptr, nullptr);
+  gnb_prologue(g, ns, fsums, nullptr, gmean, grstd, nullptr, nullptr);
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
   const int cpg = g.C / g.groups;
+  const int c0 = v * 4;
   const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
-  float a[8], b[8], gm[8], xm[8], xr[8], s1[8], s2[8];
+  float gm[4], bt[4], xr[4], xmr[4], s1[4], s2[4];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w;
+    bt[0] = b.x; bt[1] = b.y; bt[2] = b.z; bt[3] = b.w;
+  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = v * 8 + i;
-    a[i] = sa[c]; b[i] = sb[c]; gm[i] = gamma[c];
-    xm[i] = gmean[c / cpg]; xr[i] = grstd[c / cpg];
+  for (int i = 0; i < 4; ++i) {
+    const int gi = (c0 + i) / cpg;
+    xr[i] = grstd[gi]; xmr[i] = -gmean[gi] * grstd[gi];
     s1[i] = 0.f; s2[i] = 0.f;
   }
-  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+  for (int r = r0 + rl; r < r1; r += 2 * g.rows_par) {
     const long long row = (long long)ns * g.R + r;
-    float f[8], d[8];
-    gnb_load_x(x1, x2, g, row, v, f);
-    ld8_bf16(dy + row * g.C + v * 8, d);
+    const bool two = r + g.rows_par < r1;
+    const long long rowb = two ? row + g.rows_par : row;
+    float fa[4], da[4], fb[4], db[4], gg[4], xh[4];
+    gnb_load_x(x1, x2, g, row, c0, fa);
+    ld4_any(dy, row * g.C + c0, 0, da);
+    gnb_load_x(x1, x2, g, rowb, c0, fb);
+    ld4_any(dy, rowb * g.C + c0, 0, db);
+    gnb_piece(fa, da, gm, bt, xr, xmr, g.silu, gg, xh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(f[i], a[i], b[i]);
-      const float gg = d[i] * (g.silu ? silu_grad(z) : 1.0f) * gm[i];
-      s1[i] += gg;
-      s2[i] = fmaf(gg, (f[i] - xm[i]) * xr[i], s2[i]);
+    for (int i = 0; i < 4; ++i) { s1[i] += gg[i]; s2[i] = fmaf(gg[i], xh[i], s2[i]); }
+    if (two) {
+      gnb_piece(fb, db, gm, bt, xr, xmr, g.silu, gg, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s1[i] += gg[i]; s2[i] = fmaf(gg[i], xh[i], s2[i]); }
     }
   }
-  float* my = red + (size_t)threadIdx.x * 16;
+  const int T = blockDim.x;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { my[i] = s1[i]; my[8 + i] = s2[i]; }
+  for (int i = 0; i < 4; ++i) { red[i * T + threadIdx.x] = s1[i]; red[(4 + i) * T + threadIdx.x] = s2[i]; }
   __syncthreads();
-  for (int t = threadIdx.x; t < g.vecs * 16; t += blockDim.x) {
-    const int vv = t / 16, comp = t % 16;
+  for (int t = threadIdx.x; t < g.C * 2; t += T) {      // consecutive threads -> consecutive (channel, which) doubles
+    const int c = t >> 1, which = t & 1;
+    const int vv = c >> 2, comp = which * 4 + (c & 3);
     float acc = 0.f;
-    for (int rr = 0; rr < g.rows_par; ++rr) acc += red[((size_t)rr * g.vecs + vv) * 16 + comp];
-    const int c = vv * 8 + (comp & 7);
-    atomicAdd(&bsums[((size_t)ns * g.C + c) * 2 + (comp >> 3)], (double)acc);
+    for (int rr = 0; rr < g.rows_par; ++rr) acc += red[comp * T + rr * g.vecs + vv];
+    atomicAdd(&bsums[((size_t)ns * g.C + c) * 2 + which], (double)acc);
   }
 }
 
 // pass 2: dx = rstd * (g - mean(g) - xhat * mean(g xhat))  [+ add], written to up to three destinations
-__global__ void gn_bwd_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+__device__ __forceinline__ void gnb_store(const GnbGeom& g, long long row, int c0, float (&o)[4],
+                                          const void* __restrict__ add, int add_f32, float* __restrict__ out1, int acc1,
+                                          float* __restrict__ out2, int acc2, __nv_bfloat16* __restrict__ out_bf16) {
+  if (add != nullptr) {
+    float e[4];
+    ld4_any(add, row * g.C + c0, add_f32, e);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] += e[i];
+  }
+  float* dst = nullptr;
+  int acc = 0;
+  if (c0 < g.C1) { if (out1) { dst = out1 + row * g.C1 + c0; acc = acc1; } }
+  else if (out2) { dst = out2 + row * g.C2 + (c0 - g.C1); acc = acc2; }
+  if (dst != nullptr) {
+    if (acc) {
+      const float4 e = *reinterpret_cast<const float4*>(dst);
+      o[0] += e.x; o[1] += e.y; o[2] += e.z; o[3] += e.w;
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (out_bf16 != nullptr)
+    *reinterpret_cast<uint2*>(out_bf16 + row * g.C + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+}
+
+__global__ void __launch_bounds__(1024) gn_bwd_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
                                     const __nv_bfloat16* __restrict__ dy, GnbGeom g, const double* __restrict__ fsums,
                                     const double* __restrict__ bsums, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const void* __restrict__ add, int add_f32,
                                     float* __restrict__ out1, int acc1, float* __restrict__ out2, int acc2,
                                     __nv_bfloat16* __restrict__ out_bf16) {
   extern __shared__ float sh[];
-  float* sa = sh;
-  float* sb = sh + g.C;
-  float* gmean = sh + 2 * g.C;
+  float* gmean = sh;
   float* grstd = gmean + g.groups;
   float* m1 = grstd + g.groups;    // [groups] mean(g)
   float* m2 = m1 + g.groups;       // [groups] mean(g * xhat)
   const int ns = blockIdx.y;
   const int cpg = g.C / g.groups;
-  gnb_prologue(g, ns, fsums, bsums, gamma, beta, sa, sb, gmean, grstd, m1, m2);
+  gnb_prologue(g, ns, fsums, bsums, gmean, grstd, m1, m2);
   const int v = threadIdx.x % g.vecs, rl = threadIdx.x / g.vecs;
+  const int c0 = v * 4;
   const int r0 = blockIdx.x * g.rows_per_cta, r1 = min(r0 + g.rows_per_cta, g.R);
-  float a[8], b[8], gm[8], xm[8], xr[8], k1[8], k2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = v * 8 + i;
-    a[i] = sa[c]; b[i] = sb[c]; gm[i] = gamma[c];
-    xm[i] = gmean[c / cpg]; xr[i] = grstd[c / cpg];
-    k1[i] = m1[c / cpg]; k2[i] = m2[c / cpg];
+  float gm[4], bt[4], xr[4], xmr[4], k1[4], k2[4];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w;
+    bt[0] = b.x; bt[1] = b.y; bt[2] = b.z; bt[3] = b.w;
   }
-  const int c0 = v * 8;
-  for (int r = r0 + rl; r < r1; r += g.rows_par) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = (c0 + i) / cpg;
+    xr[i] = grstd[gi]; xmr[i] = -gmean[gi] * grstd[gi];
+    k1[i] = m1[gi]; k2[i] = m2[gi];
+  }
+  for (int r = r0 + rl; r < r1; r += 2 * g.rows_par) {
     const long long row = (long long)ns * g.R + r;
-    float f[8], d[8], o[8];
-    gnb_load_x(x1, x2, g, row, v, f);
-    ld8_bf16(dy + row * g.C + c0, d);
+    const bool two = r + g.rows_par < r1;
+    const long long rowb = two ? row + g.rows_par : row;
+    float fa[4], da[4], fb[4], db[4], gg[4], xh[4], o[4];
+    gnb_load_x(x1, x2, g, row, c0, fa);
+    ld4_any(dy, row * g.C + c0, 0, da);
+    gnb_load_x(x1, x2, g, rowb, c0, fb);
+    ld4_any(dy, rowb * g.C + c0, 0, db);
+    gnb_piece(fa, da, gm, bt, xr, xmr, g.silu, gg, xh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(f[i], a[i], b[i]);
-      const float gg = d[i] * (g.silu ? silu_grad(z) : 1.0f) * gm[i];
-      const float xh = (f[i] - xm[i]) * xr[i];
-      o[i] = xr[i] * (gg - k1[i] - xh * k2[i]);
-    }
-    if (add != nullptr) {
-      float e[8];
-      ld8_any(add, row * g.C + c0, add_f32, e);
+    for (int i = 0; i < 4; ++i) o[i] = xr[i] * (gg[i] - k1[i] - xh[i] * k2[i]);
+    gnb_store(g, row, c0, o, add, add_f32, out1, acc1, out2, acc2, out_bf16);
+    if (two) {
+      gnb_piece(fb, db, gm, bt, xr, xmr, g.silu, gg, xh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += e[i];
+      for (int i = 0; i < 4; ++i) o[i] = xr[i] * (gg[i] - k1[i] - xh[i] * k2[i]);
+      gnb_store(g, rowb, c0, o, add, add_f32, out1, acc1, out2, acc2, out_bf16);
     }
-    float* dst = nullptr;
-    int acc = 0;
-    if (c0 < g.C1) { if (out1) { dst = out1 + row * g.C1 + c0; acc = acc1; } }
-    else if (out2) { dst = out2 + row * g.C2 + (c0 - g.C1); acc = acc2; }
-    if (dst != nullptr) {
-      if (acc) {
-        float e[8];
-        ld8_f32(dst, e);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += e[i];
-      }
-      st8_f32(dst, o);
-    }
-    if (out_bf16 != nullptr) st8_bf16(out_bf16 + row * g.C + c0, o);
   }
 }
 
@@ -709,19 +746,24 @@ __global__ void hamilton_bwd_kernel(const float* __restrict__ dWt, int in, int o
 
 static GnbGeom gnb_geom(int C1, int C2, int NS, int R, int x_f32, int groups, int silu, float eps) {
   GnbGeom g;
-  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 8; g.R = R; g.x_f32 = x_f32;
+  g.C1 = C1; g.C2 = C2; g.C = C1 + C2; g.vecs = g.C / 4; g.R = R; g.x_f32 = x_f32;
   g.groups = groups; g.silu = silu; g.eps = eps;
   g.rows_par = 256 / g.vecs;
   if (g.rows_par < 1) g.rows_par = 1;
   if (g.rows_par > R) g.rows_par = R;
-  // up to 8 row passes per thread, fewer when that would leave SMs without a CTA (the lower UNet levels of a training
-  // clip: 14 x 40 rows at level 3)
-  int passes = 8;
+  // row passes per thread (two rows in flight at a time): about four CTAs per SM in ONE wave - every CTA pays the
+  // prologue and 2 C double atomics, and with few samples (temporal norms: NS = batch) all of them hit the same
+  // addresses
+  int passes;
   if (const char* e = getenv("LKGD_GNB_PASSES")) {       // tuning experiments only
-    const int v = atoi(e);
-    if (v >= 1 && v <= 64) passes = v;
+    passes = atoi(e);
+    if (passes < 1 || passes > 64) passes = 8;
   } else {
-    while (passes > 1 && (long long)((R + g.rows_par * passes - 1) / (g.rows_par * passes)) * NS < 148) --passes;
+    const long long slots = ((long long)R + g.rows_par - 1) / g.rows_par * NS;
+    passes = (int)((slots + 591) / 592);
+    passes = (passes + 1) & ~1;
+    if (passes < 2) passes = 2;
+    if (passes > 32) passes = 32;
   }
   g.rows_per_cta = g.rows_par * passes;
   return g;
@@ -740,7 +782,7 @@ extern "C" int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, in
                                   size_t ws_bytes, void* stream) {
   if (x2 == nullptr) C2 = 0;
   const int C = C1 + C2;
-  if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 8 > 1024) return LKGD_ESHAPE;
+  if (NS <= 0 || R <= 0 || C <= 0 || groups <= 0 || C % groups || C1 % 8 || C2 % 8 || C / 4 > 1024) return LKGD_ESHAPE;
   if (dy == nullptr || fwd_sums == nullptr) return LKGD_ESHAPE;
   if (!aligned16(x1) || !aligned16(dy) || (x2 && !aligned16(x2)) || (add && !aligned16(add)) ||
       (out1 && !aligned16(out1)) || (out2 && !aligned16(out2)) || (out_bf16 && !aligned16(out_bf16)))
@@ -752,13 +794,9 @@ extern "C" int lkgd_groupnorm_bwd(const void* x1, int32_t C1, const void* x2, in
   if (e != cudaSuccess) return set_cuda_error(e);
   dim3 grid((R + g.rows_per_cta - 1) / g.rows_per_cta, NS);
   const int threads = g.vecs * g.rows_par;
-  const size_t sh_pro = (size_t)(2 * C + 4 * groups) * sizeof(float);
-  const size_t sh1 = sh_pro + (size_t)threads * 16 * sizeof(float);
-  static DeviceOnce attr;
-  if (attr.first()) {
-    cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  }
+  const size_t sh_pro = (size_t)(4 * groups) * sizeof(float);
+  const size_t sh1 = (size_t)(2 * groups + threads * 8) * sizeof(float);
+  if (sh_pro > 48 * 1024 || sh1 > 48 * 1024) return LKGD_ESHAPE;
   gn_bwd_stats_kernel<<<grid, threads, sh1, st>>>(x1, x2, reinterpret_cast<const __nv_bfloat16*>(dy), g,
                                                   reinterpret_cast<const double*>(fwd_sums), gamma, beta,
                                                   reinterpret_cast<double*>(workspace));

@@ -30,7 +30,7 @@ def timeit(f, n=5):
     return sorted(ts)[n // 2]
 
 
-for name, M, C in [("L0", 460800, 320), ("L1", 115200, 640), ("L2", 28800, 1280)]:
+for name, M, C in ([] if "train" in sys.argv else [("L0", 460800, 320), ("L1", 115200, 640), ("L2", 28800, 1280)]):
     x = torch.randn(M, C, device="cuda")
     g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
     out = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
@@ -43,3 +43,21 @@ for name, M, C in [("L0", 460800, 320), ("L1", 115200, 640), ("L2", 28800, 1280)
     for NS in (50, 2):
         ms = timeit(lambda: ops.groupnorm(x, g, b, 1e-5, NS=NS, R=M // NS, silu=True, out=out))
         print(json.dumps(dict(op=f"groupnorm NS={NS}", level=name, ms=round(ms, 4), gbs=round(M * C * 10 / ms / 1e6))), flush=True)
+
+if "train" in sys.argv:   # GroupNorm backward on the C5 training clip's shapes (14 frames, 40x64 latents)
+    for name, F_, HW, C in [("L0", 14, 2560, 320), ("L1", 14, 640, 640), ("L2", 14, 160, 1280), ("L3", 14, 40, 1280)]:
+        for NS, R in ((F_, HW), (1, F_ * HW)):
+            M = NS * R
+            x = torch.randn(M, C, device="cuda")
+            g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+            dy = torch.randn(M, C, device="cuda", dtype=torch.bfloat16)
+            G = torch.zeros(M, C, device="cuda")
+            ob = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+            _, st = ops.groupnorm(x, g, b, 1e-5, NS=NS, R=R, silu=True, return_stats=True)
+            ms = timeit(lambda: ops.groupnorm_bwd(x, dy, st, g, b, 1e-5, NS=NS, R=R, silu=True, out1=G, acc1=True))
+            print(json.dumps(dict(op=f"groupnorm_bwd NS={NS} acc", level=name, ms=round(ms, 4),
+                                  gbs=round(M * C * 20 / ms / 1e6))), flush=True)
+            ms = timeit(lambda: ops.groupnorm_bwd(x, dy, st, g, b, 1e-5, NS=NS, R=R, silu=True, out_bf16=ob))
+            print(json.dumps(dict(op=f"groupnorm_bwd NS={NS} bf16", level=name, ms=round(ms, 4),
+                                  gbs=round(M * C * 14 / ms / 1e6))), flush=True)
+    sys.exit(0)
