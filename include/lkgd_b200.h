@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LKGD_ABI_VERSION 6
+#define LKGD_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define LKGD_API __attribute__((visibility("default")))
@@ -385,6 +385,22 @@ LKGD_API int lkgd_adamw(float* p, const float* g, float* m, float* v, int64_t n,
  * scaled bf16 copies of gradient tensors). */
 LKGD_API int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, void* dst, int64_t ldd, int32_t rows,
                               int32_t cols, float alpha, void* stream);
+/* The same cast for a TABLE of jobs in ONE launch (ABI v7): after every optimizer step the trainer rewrites four small
+ * bf16 operands per adapter (A, A^T, s B, s B^T - the repack after train_svd_lora.py:1687 optimizer.step()), 192
+ * launches of a few microseconds each for the 48 adapters of the reference configuration.  ``jobs`` is a DEVICE array of
+ * n_jobs descriptors (built once: the master parameters and the operands never move); max_elems >= rows * cols of every
+ * job. */
+typedef struct lkgd_cast2d_job {
+  const float* src;
+  int64_t lds;      /* row pitch of src in floats                        */
+  int64_t src_cs;   /* column stride of src (1, or a pitch: transposed view) */
+  void* dst;        /* bf16                                              */
+  int64_t ldd;      /* row pitch of dst in elements                      */
+  int32_t rows, cols;
+  float alpha;
+  int32_t reserved;
+} lkgd_cast2d_job;
+LKGD_API int lkgd_cast2d_bf16_batch(const lkgd_cast2d_job* jobs, int32_t n_jobs, int32_t max_elems, void* stream);
 
 
 /* ---- backward of the fp32 conditioning helpers (latent-knowledge block under autograd,

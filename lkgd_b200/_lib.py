@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblkgd_b200.so"
 
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
@@ -16,6 +16,12 @@ RV_NONE, RV_FRAME, RV_FRAMEPOS, RV_BATCH, RV_TCTX_0272, RV_BATCH_TCTX = 0, 1, 2,
 SL_NONE, SL_SILU, SL_LEAKY = 0, 1, 3
 
 i32, f32, vp, i64, sz = C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_size_t
+
+
+class Cast2dJob(C.Structure):
+    """Mirror of ``lkgd_cast2d_job``."""
+    _fields_ = [("src", vp), ("lds", i64), ("src_cs", i64), ("dst", vp), ("ldd", i64), ("rows", i32), ("cols", i32),
+                ("alpha", f32), ("reserved", i32)]
 
 
 class GemmArgs(C.Structure):
@@ -92,6 +98,7 @@ SIGNATURES = {
     "lkgd_sumsq": (i32, [vp, i64, vp, vp]),
     "lkgd_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
     "lkgd_cast2d_bf16": (i32, [vp, i64, i64, vp, i64, i32, i32, f32, vp]),
+    "lkgd_cast2d_bf16_batch": (i32, [vp, i32, i32, vp]),
     "lkgd_small_linear_bwd": (i32, [vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
     "lkgd_polar_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "lkgd_grouped1x1_bwd_w": (i32, [vp, i32, vp, i32, vp, i32, i32, vp]),
@@ -117,7 +124,7 @@ _TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_groupnorm_from_stats", "lkgd_laye
           "lkgd_cond_conv_in", "lkgd_thin_conv3x3", "lkgd_select_rows", "lkgd_attention_lse", "lkgd_attention_bwd", "lkgd_attention_temporal_bwd", "lkgd_groupnorm_bwd",
           "lkgd_layernorm_bwd", "lkgd_geglu_fwd", "lkgd_geglu_bwd", "lkgd_colsum_grouped", "lkgd_downsum2x",
           "lkgd_zero_stuff2x", "lkgd_gemm_tn", "lkgd_edm_precondition", "lkgd_edm_loss", "lkgd_sumsq", "lkgd_adamw",
-          "lkgd_cast2d_bf16"}
+          "lkgd_cast2d_bf16", "lkgd_cast2d_bf16_batch"}
 
 
 def _timed(name, fn):

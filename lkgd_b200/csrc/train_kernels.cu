@@ -615,6 +615,15 @@ __global__ void cast2d_bf16_kernel(const float* __restrict__ src, long long lds,
   dst[r * ldd + c] = __float2bfloat16(src[r * lds + c * cs] * alpha);
 }
 
+// one launch for a table of casts (blockIdx.y = job): the LoRA repack after the optimizer step
+__global__ void cast2d_bf16_batch_kernel(const lkgd_cast2d_job* __restrict__ jobs) {
+  const lkgd_cast2d_job j = jobs[blockIdx.y];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)j.rows * j.cols) return;
+  const long long r = idx / j.cols;
+  const int c = (int)(idx % j.cols);
+  reinterpret_cast<__nv_bfloat16*>(j.dst)[r * j.ldd + c] = __float2bfloat16(j.src[r * j.lds + c * j.src_cs] * j.alpha);
+}
 
 // ------------------------------------------------------------------------------------------- small fp32 backward
 // (latent-knowledge conditioning block, reference models/unet_spatio_temporal_condition.py:536-595 under autograd)
@@ -952,6 +961,12 @@ extern "C" int lkgd_cast2d_bf16(const float* src, int64_t lds, int64_t src_cs, v
   const long long n = (long long)rows * cols;
   cast2d_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, lds, src_cs, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, alpha);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_cast2d_bf16_batch(const lkgd_cast2d_job* jobs, int32_t n_jobs, int32_t max_elems, void* stream) {
+  if (jobs == nullptr || n_jobs <= 0 || n_jobs > 65535 || max_elems <= 0) return LKGD_ESHAPE;
+  cast2d_bf16_batch_kernel<<<dim3((max_elems + 255) / 256, n_jobs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs);
   return launch_epilogue();
 }
 

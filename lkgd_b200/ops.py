@@ -898,6 +898,37 @@ def cast2d_bf16(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> tor
     return dst
 
 
+class Cast2dBatch:
+    """A fixed table of ``cast2d_bf16`` jobs run as ONE launch (``lkgd_cast2d_bf16_batch``): ``jobs`` is a list of
+    ``(src fp32 2-D, dst bf16 2-D, alpha)``; the tensors must stay where they are (the table holds raw pointers)."""
+
+    def __init__(self, jobs):
+        if not jobs:
+            raise ValueError("Cast2dBatch: no jobs")
+        arr = (L.Cast2dJob * len(jobs))()
+        self.keep = []
+        self.max_elems = 0
+        dev = jobs[0][0].device
+        for k, (src, dst, alpha) in enumerate(jobs):
+            _need_cuda(src, dst)
+            if (src.dtype != torch.float32 or dst.dtype != bf16 or src.dim() != 2 or dst.dim() != 2
+                    or src.shape != dst.shape or dst.stride(1) != 1 or src.device != dev or dst.device != dev):
+                raise ValueError("cast2d_bf16: fp32 -> bf16 2-D tensors of equal shape, dst with unit column stride")
+            j = arr[k]
+            j.src, j.lds, j.src_cs = src.data_ptr(), src.stride(0), src.stride(1)
+            j.dst, j.ldd = dst.data_ptr(), dst.stride(0)
+            j.rows, j.cols, j.alpha = src.shape[0], src.shape[1], float(alpha)
+            self.max_elems = max(self.max_elems, src.shape[0] * src.shape[1])
+            self.keep.append((src, dst))
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = raw.to(dev)
+        self.n = len(jobs)
+
+    def run(self):
+        L.check(L.load().lkgd_cast2d_bf16_batch(self.table.data_ptr(), self.n, self.max_elems, _stream()),
+                "lkgd_cast2d_bf16_batch")
+
+
 def small_linear_bwd(dy: torch.Tensor, W: Optional[torch.Tensor] = None, *, x: Optional[torch.Tensor] = None,
                      y: Optional[torch.Tensor] = None, act_out: int = 0, want_dx: bool = True,
                      dx: Optional[torch.Tensor] = None, dW: Optional[torch.Tensor] = None,

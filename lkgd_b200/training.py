@@ -364,6 +364,7 @@ class LoraTrainer:
         self.unet, self.group, self.world = unet, group, world_size
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.step_count = 0
+        self._repack_batch = None
         if not getattr(unet, "fold_lora", True):
             raise ValueError("training needs the LoRA pairs folded into the GEMM (fold_lora=True)")
         pk = unet.packed()
@@ -458,16 +459,19 @@ class LoraTrainer:
 
     # ---- fp32 master parameters -> the bf16 operands the GEMMs read (forward: A_cat, B_blk; backward: transposes)
     def repack(self):
-        for ad in self.adapters:
-            if "dense" not in ad:
-                continue
-            d, (aT, bT), r = ad["dense"], ad["tw"], ad["r"]
-            rs = slice(ad["r_lo"], ad["r_lo"] + r)
-            ns = slice(ad["n_lo"], ad["n_hi"])
-            ops.cast2d_bf16(ad["pA"], d.lora_a[rs])
-            ops.cast2d_bf16(ad["pA"].t(), aT[:, rs])
-            ops.cast2d_bf16(ad["pB"], d.lora_b[ns, rs], alpha=ad["scaling"])
-            ops.cast2d_bf16(ad["pB"].t(), bT[rs, ns], alpha=ad["scaling"])
+        if self._repack_batch is None:       # the master parameters and the operands never move: one table, one launch
+            jobs = []
+            for ad in self.adapters:
+                if "dense" not in ad:
+                    continue
+                d, (aT, bT), r = ad["dense"], ad["tw"], ad["r"]
+                rs = slice(ad["r_lo"], ad["r_lo"] + r)
+                ns = slice(ad["n_lo"], ad["n_hi"])
+                jobs += [(ad["pA"], d.lora_a[rs], 1.0), (ad["pA"].t(), aT[:, rs], 1.0),
+                         (ad["pB"], d.lora_b[ns, rs], ad["scaling"]), (ad["pB"].t(), bT[rs, ns], ad["scaling"])]
+            self._repack_batch = ops.Cast2dBatch(jobs) if jobs else False
+        if self._repack_batch:
+            self._repack_batch.run()
         for c in self.cross:
             wv, wo = self._cross_weights(c)
             c["pc"].wov.copy_(wo @ wv)                     # a view of the batched [sum C, D] cross-vector matrix

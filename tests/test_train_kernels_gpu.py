@@ -337,3 +337,29 @@ def test_small_linear_bwd(cuda, M, N, K, act):
     assert rel_l2(acc - 2.0, x.grad) < 1e-5
     again = ops.small_linear_bwd(dy, W.detach(), y=y.detach() if act else None, act_out=act)
     assert torch.equal(again, dx)                                 # fixed reduction order
+
+
+def test_cast2d_batch_equals_the_single_casts(cuda):
+    """One launch over a table of jobs (the LoRA repack) writes what the per-job casts write, bit for bit: plain,
+    transposed-view and scaled sources, destinations that are slices of wider operands."""
+    from lkgd_b200 import ops
+    pA = rnd(64, 320, dev=cuda, dtype=torch.float32, seed=1)
+    pB = rnd(960, 64, dev=cuda, dtype=torch.float32, seed=2)
+    small = rnd(3, 5, dev=cuda, dtype=torch.float32, seed=3)
+
+    def dsts():
+        return (torch.zeros(128, 320, device=cuda, dtype=bf16), torch.zeros(320, 128, device=cuda, dtype=bf16),
+                torch.zeros(1920, 128, device=cuda, dtype=bf16), torch.zeros(128, 1920, device=cuda, dtype=bf16),
+                torch.zeros(3, 8, device=cuda, dtype=bf16))
+
+    def jobs(d):
+        return [(pA, d[0][64:128], 1.0), (pA.t(), d[1][:, 64:128], 1.0), (pB, d[2][960:, :64], 0.25),
+                (pB.t(), d[3][:64, 960:], 0.25), (small, d[4][:, :5], -2.0)]
+    ref, got = dsts(), dsts()
+    for src, dst, alpha in jobs(ref):
+        ops.cast2d_bf16(src, dst, alpha=alpha)
+    batch = ops.Cast2dBatch(jobs(got))
+    batch.run()
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    assert float(got[0][64:128].float().abs().sum()) > 0 and float(got[0][:64].float().abs().sum()) == 0
