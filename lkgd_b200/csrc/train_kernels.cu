@@ -438,6 +438,39 @@ __global__ void __launch_bounds__(512) colsum_grouped_kernel(const float* __rest
   }
 }
 
+// One group (batch 1 per GPU, the reference's training configuration: every row belongs to the same context vector):
+// no per-row group arithmetic, 16-byte loads, four rows in flight per thread; block = 32 column quads x 16 row lanes.
+__global__ void __launch_bounds__(512) colsum_all_kernel(const float* __restrict__ G, long long M, int C,
+                                                         int rows_per_cta, float* __restrict__ out) {
+  __shared__ float4 red[16][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + tx * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (c < C) {
+    const float* base = G + c;
+    for (long long r = r0 + ty; r < r1; r += 64) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + 16 * u;
+        v[u] = rr < r1 ? __ldg(reinterpret_cast<const float4*>(base + rr * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      a.x += v[0].x + v[2].x; a.y += v[0].y + v[2].y; a.z += v[0].z + v[2].z; a.w += v[0].w + v[2].w;
+      b.x += v[1].x + v[3].x; b.y += v[1].y + v[3].y; b.z += v[1].z + v[3].z; b.w += v[1].w + v[3].w;
+    }
+  }
+  red[ty][tx] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float4 s = red[0][tx];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) { s.x += red[i][tx].x; s.y += red[i][tx].y; s.z += red[i][tx].z; s.w += red[i][tx].w; }
+    atomicAdd(out + c, s.x); atomicAdd(out + c + 1, s.y); atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- resampling gradients
 // nearest-2x upsample backward: out[n,h,w,:] = sum of the 2x2 block of in [N,2H,2W,C]
 __global__ void downsum2x_kernel(const void* __restrict__ in, int in_f32, float* __restrict__ out, int N, int H, int W,
@@ -880,6 +913,10 @@ extern "C" int lkgd_colsum_grouped(const float* G, int64_t M, int32_t C, int32_t
   if (rpc < 64) rpc = 64;
   const int rows_per_cta = (int)rpc;
   dim3 grid(col_blocks, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+  if (n_groups == 1 && C % 4 == 0 && aligned16(G)) {
+    colsum_all_kernel<<<grid, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, out);
+    return launch_epilogue();
+  }
   colsum_grouped_kernel<<<grid, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(G, M, C, rows_per_cta, rv_mode, rv_HW,
                                                                                    rv_F, rv_B, n_groups, out, ldo);
   return launch_epilogue();

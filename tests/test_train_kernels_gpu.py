@@ -110,6 +110,14 @@ def test_colsum_grouped(cuda):
         out = ops.colsum_grouped(G, n, (mode, HW, Fr, B_))
         ref = torch.zeros(n, C, device=cuda).index_add_(0, idx, G)
         assert rel_l2(out, ref) < 1e-5, mode
+    # one group (batch 1 per GPU): the 16-byte-load kernel; ragged row count, column count not a multiple of 128,
+    # accumulation into a slice of a wider destination
+    for M1, C1 in [(1234, 320), (77, 100), (35840, 1280)]:
+        G1 = rnd(M1, C1, dev=cuda, dtype=torch.float32, seed=2)
+        wide = torch.full((1, C1 + 64), 0.5, device=cuda)
+        ops.colsum_grouped(G1, 1, (ops.RV_BATCH, M1, 1, 1), out=wide[:, 32:32 + C1])
+        assert rel_l2(wide[:, 32:32 + C1] - 0.5, G1.double().sum(0, keepdim=True).float()) < 1e-5
+        assert float((wide[:, :32] - 0.5).abs().max()) == 0 and float((wide[:, 32 + C1:] - 0.5).abs().max()) == 0
 
 
 def test_downsum_and_zero_stuff(cuda):
