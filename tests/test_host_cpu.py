@@ -43,20 +43,22 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.lkgd_strerror(0) is not None and b"shape" in lib.lkgd_strerror(-1).lower()
 
 
-def test_gemm_args_struct_layout_matches_c(lib, tmp_path):
-    """sizeof / offsetof of lkgd_gemm_args as gcc sees the header == the ctypes mirror."""
-    from lkgd_b200._lib import GemmArgs
+@pytest.mark.parametrize("cname,pyname", [("lkgd_gemm_args", "GemmArgs"), ("lkgd_cast2d_job", "Cast2dJob")])
+def test_gemm_args_struct_layout_matches_c(lib, tmp_path, cname, pyname):
+    """sizeof / offsetof of the ABI's descriptor structs as gcc sees the header == the ctypes mirrors."""
+    from lkgd_b200 import _lib
     import ctypes as C
-    fields = [f[0] for f in GemmArgs._fields_]
-    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "lkgd_b200.h"\nint main(){printf("%zu", sizeof(lkgd_gemm_args));' \
-        + "".join(f'printf(" %zu", offsetof(lkgd_gemm_args, {f}));' for f in fields) + "return 0;}\n"
+    S = getattr(_lib, pyname)
+    fields = [f[0] for f in S._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "lkgd_b200.h"\nint main(){printf("%zu", sizeof(' + cname + '));' \
+        + "".join(f'printf(" %zu", offsetof({cname}, {f}));' for f in fields) + "return 0;}\n"
     src = tmp_path / "layout.c"
     src.write_text(prog)
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     vals = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
-    assert vals[0] == C.sizeof(GemmArgs)
-    assert vals[1:] == [getattr(GemmArgs, f).offset for f in fields]
+    assert vals[0] == C.sizeof(S)
+    assert vals[1:] == [getattr(S, f).offset for f in fields]
 
 
 def test_error_codes_without_a_gpu(lib):
