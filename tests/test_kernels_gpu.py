@@ -33,6 +33,42 @@ def test_gemm_linear(cuda, M, N, K):
     assert rel_l2(out.float(), chk.float()) < 3e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(560, 1280, 1280), (2240, 1280, 640), (560, 640, 2560), (256, 1280, 320)])
+def test_gemm_narrow_tiles_of_few_row_problems(cuda, monkeypatch, M, N, K):
+    """Few row tiles (training clip at the lower UNet levels): the GEMM picks a narrower N tile that still fits one
+    wave (refine_bn: BN = 160 / 128 / 64 instead of 256).  Every epilogue family on those tiles equals the widest-tile
+    result bit for bit (the contraction order per output element does not depend on the tile width) and the SIMT
+    checker within bf16 rounding; the fused GroupNorm statistics equal the sums of the stored tensor."""
+    from lkgd_b200 import ops
+    A = rnd(M, K, dev=cuda)
+    W = rnd(N, K, dev=cuda, scale=K ** -0.5)
+    b = rnd(N, dev=cuda, dtype=torch.float32)
+    res = rnd(M, N, dev=cuda, dtype=torch.float32, seed=3)
+    res_b = rnd(M, N, dev=cuda, seed=4)
+    rows = 128 if M % 128 == 0 else 0
+
+    def run():
+        outs = [ops.gemm(A, W, bias=b), ops.gemm(A, W, bias=b, act=ops.ACT_SILU, res1=res_b, s1=0.5),
+                ops.gemm(A, W, bias=b, res1=res, s0=0.7, out_f32=True, gn_rows=rows),
+                ops.gemm(A, W, bias=b, out_f32=True, want_bf16=True)[1]]
+        st = ops.gn_stats_of(outs[2])
+        return outs, (st[0].clone() if st is not None else None)
+    narrow, st_n = run()
+    monkeypatch.setenv("LKGD_GEMM_NO_REFINE", "1")
+    wide, st_w = run()
+    monkeypatch.delenv("LKGD_GEMM_NO_REFINE")
+    for a, w in zip(narrow, wide):
+        assert torch.equal(a, w)
+    chk = ops.gemm(A, W, bias=b, res1=res, s0=0.7, out_f32=True, checker=True)
+    assert rel_l2(narrow[2], chk) < 1e-5
+    ref = A.float() @ W.float().t() + b
+    assert rel_l2(narrow[0].float(), ref) < 4e-3
+    if rows:
+        x = narrow[2].double().view(M // rows, rows, N)
+        assert rel_l2(st_n[..., 0], x.sum(1)) < 1e-5 and rel_l2(st_n[..., 1], (x * x).sum(1)) < 1e-5
+        assert rel_l2(st_n, st_w) < 1e-9
+
+
 def test_gemm_column_slice_and_f32_out(cuda):
     from lkgd_b200 import ops
     M, K, N = 512, 64, 192
