@@ -767,18 +767,32 @@ def section_cfg_split(args, pipe, F, h, w, lkgd, unsplit_ms, device, rank, world
     kw = dict(domain_features=extra[0], flow_features=extra[1]) if lkgd else {}
     st = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, cfg_pair=pair, **kw)
     lat0 = (noise * pipe.scheduler.init_noise_sigma).to(device)
-    lat = lat0
-    for i in range(max(2, args.warmup)):
-        lat, _ = pipe.denoise_step(st, i, lat, eager=True)
-    dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        lat, _ = pipe.denoise_step(st, (3 + i) % 25, lat, eager=True)
-    e1.record()
-    dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+    def timed(eager=True):
+        lat = lat0
+        for i in range(max(2, args.warmup)):
+            lat, _ = pipe.denoise_step(st, i, lat, eager=eager)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            lat, _ = pipe.denoise_step(st, (3 + i) % 25, lat, eager=eager)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt
+    peer = pair.peer is not None          # prepare() mapped the partner's prediction buffer (symmetric memory)
+    t_nccl = None
+    if peer:                              # the same steps through the NCCL all-gather, for comparison
+        keep, pair.peer = pair.peer, None
+        t_nccl = float(timed()[0])
+        pair.peer = keep
+    t_eager = timed()
+    t, graphed = t_eager, False
+    if peer and not args.no_graph:        # no collective on the path any more: the split step is ONE graph replay
+        pipe.capture(st, lat0)
+        t, graphed = timed(eager=False), True
     # correctness on the same inputs: one split step vs the unsplit batch-2 step on this rank
     split, _ = pipe.denoise_step(st, 3, lat0, eager=True)
     st_whole = pipe.prepare(emb, img_lat, num_frames=F, num_inference_steps=25, **kw)
@@ -791,11 +805,16 @@ def section_cfg_split(args, pipe, F, h, w, lkgd, unsplit_ms, device, rank, world
     nbytes = F * h * w * 4 * 4
     return {"ms_per_step": float(t[0]), "unsplit_ms_per_step": unsplit_ms, "ratio_vs_unsplit": float(t[0]) / unsplit_ms,
             "pairs": world // 2, "samples_per_s_equiv": (world // 2) / (float(t[0]) * 1e-3),
-            "allgather_bytes_per_step_per_rank": nbytes, "cuda_graph": False,
+            "exchange": "peer memory: the fused CFG + Euler kernel reads the partner's half over NVLink, one device-side "
+                        "barrier per step, no collective" if peer else "NCCL all-gather (symmetric memory unavailable: "
+                        + str(pair.peer_error) + ")",
+            "ms_per_step_nccl_allgather": t_nccl,
+            "ms_per_step_eager_launches": float(t_eager[0]),
+            "exchanged_bytes_per_step_per_rank": nbytes, "cuda_graph": graphed,
             "split_vs_unsplit_rel_l2_max": max(r["split_vs_unsplit"] for r in allr),
             "replicated": all(r["replicated"] for r in allr),
-            "what": "ranks (2k,2k+1) share sample k: uncond half on 2k, cond half on 2k+1 (batch 1 each), one NCCL "
-                    "all-gather of the fp32 prediction per step, fused CFG+Euler on both ranks; max-over-ranks device time"}
+            "what": "ranks (2k,2k+1) share sample k: uncond half on 2k, cond half on 2k+1 (batch 1 each), one exchange "
+                    "of the fp32 prediction per step, fused CFG+Euler on both ranks; max-over-ranks device time"}
 
 
 def section_c5_dp(args, device, rank, world):

@@ -296,6 +296,16 @@ LKGD_API int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, con
                         float* x_next, float* v_out, float* x0_out, int32_t S, int32_t F, int32_t C, int32_t H,
                         int32_t W, float sigma, float sigma_next, const float* sigmas_dev, void* stream);
 
+/* The same step with the two halves of the CFG batch at SEPARATE bases (each fp32 channels-last rows [S*F, H, W, ld]):
+ * the CFG-pair split (two GPUs share one sample) keeps every rank's prediction in peer-mapped memory and
+ * passes its own buffer for one half and the partner's mapping for the other - the kernel reads the partner's half over
+ * NVLink, so exchange, guidance combine (pipeline...controlnet.py:614-616) and Euler step are ONE kernel and no
+ * all-gather runs (ABI v7). */
+LKGD_API int lkgd_cfg_euler_step_pair(const float* pred_uncond, const float* pred_cond, int32_t ld, const float* guidance,
+                             const float* x, float* x_next, float* v_out, float* x0_out, int32_t S, int32_t F,
+                             int32_t C, int32_t H, int32_t W, float sigma, float sigma_next, const float* sigmas_dev,
+                             void* stream);
+
 /* Bidirectional "direct fusion" Euler step (pipeline/pipeline_stable_video_diffusion_trans_controlnet.py:639-667,
  * SURVEY 8f N3): v and x are fp32 [2S, F, C, H, W] (forward samples, then their time-reversed partners), weights fp32
  * [F] = linspace(1, 0, F).  x0 = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1) per half; the forward half keeps

@@ -76,6 +76,7 @@ SIGNATURES = {
     "lkgd_time_conv_out": (i32, [vp, i32, vp, vp, vp, i32, i32, i64, i32, vp]),
     "lkgd_select_rows": (i32, [vp, i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "lkgd_cfg_euler_step": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
+    "lkgd_cfg_euler_step_pair": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
     "lkgd_fusion_euler_step": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp]),
     # ---- training step
     "lkgd_attention_lse": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]),
@@ -119,7 +120,7 @@ class Profiler:
 PROF = Profiler()
 _TIMED = {"lkgd_gemm", "lkgd_groupnorm", "lkgd_groupnorm_from_stats", "lkgd_layernorm", "lkgd_attention", "lkgd_attention_temporal",
           "lkgd_small_linear", "lkgd_timestep_embedding", "lkgd_pack_input", "lkgd_unpack_output",
-          "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_cast_bf16", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_fusion_euler_step", "lkgd_axpy_f32",
+          "lkgd_upsample2x", "lkgd_concat_channels", "lkgd_cast_bf16", "lkgd_axpby", "lkgd_cfg_euler_step", "lkgd_cfg_euler_step_pair", "lkgd_fusion_euler_step", "lkgd_axpy_f32",
           "lkgd_nchw_to_nhwc", "lkgd_nhwc_to_nchw", "lkgd_polar", "lkgd_scale_f32",
           "lkgd_cond_conv_in", "lkgd_thin_conv3x3", "lkgd_select_rows", "lkgd_attention_lse", "lkgd_attention_bwd", "lkgd_attention_temporal_bwd", "lkgd_groupnorm_bwd",
           "lkgd_layernorm_bwd", "lkgd_geglu_fwd", "lkgd_geglu_bwd", "lkgd_colsum_grouped", "lkgd_downsum2x",

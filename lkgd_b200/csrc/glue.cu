@@ -219,7 +219,10 @@ __global__ void scale_f32_kernel(const float* __restrict__ x, float alpha, float
 }
 
 // x_next may alias x (in-place update of a CUDA graph's static latent buffer): every thread reads its x before it writes.
-__global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg, const float* __restrict__ guidance,
+// pred_c != nullptr (ld > 0): the conditional half lives at its own base (row s, not S + s) - the CFG-pair split, where one
+// of the two bases is the PARTNER GPU's buffer mapped into this address space (read over NVLink, no all-gather)
+__global__ void cfg_euler_kernel(const float* __restrict__ pred, const float* __restrict__ pred_c, int ld, int cfg,
+                                 const float* __restrict__ guidance,
                                  const float* x, float* x_next, float* __restrict__ v_out, float* __restrict__ x0_out,
                                  int S, int F, int C, int HW, float sigma, float sigma_next,
                                  const float* __restrict__ sigmas_dev) {
@@ -237,7 +240,8 @@ __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld, int cfg
   float v, cnd = 0.f;
   if (ld > 0) {   // channels-last prediction rows
     v = pred[(((size_t)s * F + f) * HW + p) * ld + c];
-    if (cfg) cnd = pred[(((size_t)(S + s) * F + f) * HW + p) * ld + c];
+    if (cfg) cnd = pred_c != nullptr ? pred_c[(((size_t)s * F + f) * HW + p) * ld + c]
+                                     : pred[(((size_t)(S + s) * F + f) * HW + p) * ld + c];
   } else {        // ld == 0: prediction in the latent's own [.,F,C,H,W] layout
     v = pred[idx];
     if (cfg) cnd = pred[total + idx];
@@ -396,8 +400,21 @@ extern "C" int lkgd_cfg_euler_step(const float* pred, int32_t ld, int32_t cfg, c
                                    void* stream) {
   if (S <= 0 || F <= 0 || C <= 0 || (ld != 0 && C > ld) || (sigmas_dev == nullptr && sigma <= 0.f)) return LKGD_ESHAPE;
   const long long total = (long long)S * F * C * H * W;
-  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, ld, cfg, guidance, x, x_next, v_out, x0_out, S,
-                                                                  F, C, H * W, sigma, sigma_next, sigmas_dev);
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred, nullptr, ld, cfg, guidance, x, x_next, v_out,
+                                                                  x0_out, S, F, C, H * W, sigma, sigma_next, sigmas_dev);
+  return launch_epilogue();
+}
+
+extern "C" int lkgd_cfg_euler_step_pair(const float* pred_uncond, const float* pred_cond, int32_t ld,
+                                        const float* guidance, const float* x, float* x_next, float* v_out,
+                                        float* x0_out, int32_t S, int32_t F, int32_t C, int32_t H, int32_t W, float sigma,
+                                        float sigma_next, const float* sigmas_dev, void* stream) {
+  if (pred_uncond == nullptr || pred_cond == nullptr || guidance == nullptr) return LKGD_ESHAPE;
+  if (S <= 0 || F <= 0 || C <= 0 || ld <= 0 || C > ld || (sigmas_dev == nullptr && sigma <= 0.f)) return LKGD_ESHAPE;
+  const long long total = (long long)S * F * C * H * W;
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(pred_uncond, pred_cond, ld, 1, guidance, x, x_next,
+                                                                  v_out, x0_out, S, F, C, H * W, sigma, sigma_next,
+                                                                  sigmas_dev);
   return launch_epilogue();
 }
 

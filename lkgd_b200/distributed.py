@@ -3,8 +3,11 @@
 The denoise step shards only where it splits naturally:
   * independent samples -> ``shard_range``: every rank denoises its own samples, NO data-path collective;
   * the classifier-free-guidance pair -> ``CFGPair``: rank 2k runs the unconditional half, rank 2k+1 the conditional
-    half (batch 1 each), and ONE exchange per step (an all-gather of the [S*F*H*W, 4] fp32 prediction, 3.7 MB at
-    25 frames 72x128) feeds the fused CFG + Euler kernel, which both ranks run so the latents stay replicated.
+    half (batch 1 each), and ONE exchange per step feeds the fused CFG + Euler kernel, which both ranks run so the latents
+    stay replicated.  The exchange is peer memory where the box offers it (``CFGPair.enable_peer``: each rank's [S*F*H*W, 4]
+    fp32 prediction, 3.7 MB at 25 frames 72x128, sits in a symmetric buffer and ``lkgd_cfg_euler_step_pair`` reads the
+    partner's half over NVLink inside the combine kernel: one device-side barrier, no collective, and the whole split step
+    can be captured in a CUDA graph), else an NCCL / gloo all-gather (``CFGPair.exchange``).
   * LoRA training -> ``allreduce_flat_``: replicas; the ONE flat fp32 gradient buffer of all trainable tensors is summed
     with a single all-reduce per optimizer step (the averaging 1/world is folded into the optimizer kernel) - what DDP's
     bucketed all-reduce does for the reference (train_models/train_svd_lora.py:1300-1302,1683).
@@ -37,6 +40,7 @@ class CFGPair:
         if role not in (0, 1):
             raise ValueError("role must be 0 (uncond) or 1 (cond)")
         self.group, self.role = group, role
+        self.peer, self.peer_error = None, None
 
     @staticmethod
     def from_world() -> "CFGPair":
@@ -54,6 +58,48 @@ class CFGPair:
     def batch_slice(self, S: int) -> Tuple[int, int]:
         """Rows of the CFG-duplicated batch [uncond(S) | cond(S)] this rank computes."""
         return self.role * S, (self.role + 1) * S
+
+    # ---- exchange over peer memory (NVLink / NVSwitch): no collective, the combine kernel reads the partner's half
+    def enable_peer(self, n_rows: int, ld: int, device) -> bool:
+        """Allocates this rank's prediction buffer in symmetric (peer-mapped) memory and maps the partner's
+        (``torch.distributed._symmetric_memory``: CUDA VMM allocations exchanged inside the pair's group).  Two slots,
+        used alternately by consecutive steps, so ONE device-side barrier per step orders both the read-after-write of
+        this step and the write-after-read of the step after next.  Collective over the pair; returns False (and leaves
+        the NCCL ``exchange`` as the path) where the rendezvous is not available: CPU / gloo groups, no P2P access."""
+        self.peer = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty((2, n_rows, ld), dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, self.group)
+            other = 1 - hdl.rank
+            theirs = hdl.get_buffer(other, (2, n_rows, ld), torch.float32)
+            ok = torch.ones(1, device=device)
+        except Exception as e:                     # noqa: BLE001 - any failure means "use the collective"
+            self.peer_error = repr(e)
+            ok = torch.zeros(1, device=device) if torch.device(device).type == "cuda" else torch.zeros(1)
+            buf = hdl = theirs = None
+        try:                                       # both ranks must agree, or one would wait in a barrier alone
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        except Exception:                          # noqa: BLE001
+            return False
+        if float(ok) < 1.0:
+            return False
+        self.peer = dict(mine=buf, theirs=theirs, hdl=hdl, n=n_rows, ld=ld, tick=0)
+        return True
+
+    def publish(self, pred_rows: torch.Tensor):
+        """This half's prediction -> the next slot of the symmetric buffer (slots alternate call by call, on both ranks
+        alike), one barrier inside the pair, then the (unconditional rows, conditional rows) the fused CFG + Euler kernel
+        reads: one of the two is the partner's memory."""
+        P = self.peer
+        k = P["tick"] & 1
+        P["tick"] += 1
+        mine, theirs = P["mine"][k], P["theirs"][k]
+        if pred_rows.shape != mine.shape:
+            raise ValueError(f"prediction rows {tuple(pred_rows.shape)} do not match the peer buffer {tuple(mine.shape)}")
+        mine.copy_(pred_rows)
+        P["hdl"].barrier(channel=0, timeout_ms=20000)     # a lost partner traps the kernel instead of hanging the GPU
+        return (mine, theirs) if self.role == 0 else (theirs, mine)
 
     def exchange(self, pred_rows: torch.Tensor) -> torch.Tensor:
         """[n, c] prediction of this half -> [2n, c] (uncond rows first) on both ranks: the one collective per step."""

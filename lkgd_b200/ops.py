@@ -626,12 +626,33 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 def cfg_euler_step(pred: torch.Tensor, guidance: Optional[torch.Tensor], x: torch.Tensor, sigma: float,
                    sigma_next: float, *, cfg: bool, want_v: bool = False, want_x0: bool = False,
-                   sigmas_dev: Optional[torch.Tensor] = None, in_place: bool = False):
+                   sigmas_dev: Optional[torch.Tensor] = None, in_place: bool = False,
+                   pred_cond: Optional[torch.Tensor] = None):
     """pred fp32: channels-last rows [(2)S*F*H*W, ld] (2-D) or the latent's own layout [(2)S,F,C,H,W] (5-D);
     x fp32 [S,F,C,H,W] -> (x_next, v or None) (-> (x_next, v, x0) with ``want_x0``).  ``sigmas_dev``: fp32 device
-    [sigma, sigma_next] replacing the host scalars; ``in_place``: write x_next over x (CUDA-graph replay)."""
-    _need_cuda(pred, guidance, x, sigmas_dev)
+    [sigma, sigma_next] replacing the host scalars; ``in_place``: write x_next over x (CUDA-graph replay).
+    ``pred_cond`` (CFG-pair split): ``pred`` holds the unconditional rows [S*F*H*W, ld] only and ``pred_cond`` the
+    conditional ones at their own base - either may be the partner GPU's peer-mapped buffer."""
+    _need_cuda(pred, guidance, x, sigmas_dev, pred_cond)
     S, F, Cn, H, W = x.shape
+    if pred_cond is not None:
+        if in_place and not x.is_contiguous():
+            raise ValueError("cfg_euler_step: in_place needs a contiguous latent")
+        x = x.contiguous()
+        n = S * F * H * W
+        for t in (pred, pred_cond):
+            if t.dtype != torch.float32 or t.dim() != 2 or t.shape[0] != n or t.stride(1) != 1:
+                raise ValueError("cfg_euler_step(pred_cond=): both halves are fp32 rows [S*F*H*W, ld]")
+        if pred.stride(0) != pred_cond.stride(0) or not cfg or guidance is None or x.dtype != torch.float32:
+            raise ValueError("cfg_euler_step(pred_cond=): equal row pitch, cfg=True, guidance and an fp32 latent expected")
+        x_next = x if in_place else torch.empty_like(x)
+        v = torch.empty_like(x) if want_v else None
+        x0 = torch.empty_like(x) if want_x0 else None
+        L.check(L.load().lkgd_cfg_euler_step_pair(pred.data_ptr(), pred_cond.data_ptr(), pred.stride(0),
+                                                  guidance.data_ptr(), x.data_ptr(), x_next.data_ptr(), _ptr(v), _ptr(x0),
+                                                  S, F, Cn, H, W, sigma, sigma_next, _ptr(sigmas_dev), _stream()),
+                "lkgd_cfg_euler_step_pair")
+        return (x_next, v, x0) if want_x0 else (x_next, v)
     if in_place and not x.is_contiguous():
         raise ValueError("cfg_euler_step: in_place needs a contiguous latent")
     x = x.contiguous()

@@ -16,6 +16,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Union
 
+import os
+
 import numpy as np
 import torch
 
@@ -175,6 +177,12 @@ class StableVideoDiffusionPipeline:
             controlnet_condition = cc.to(device=device, dtype=torch.float32)
         if cfg_pair is not None and (not do_cfg or controlnet_condition is not None):
             raise ValueError("cfg_pair needs classifier-free guidance and (for now) no ControlNet")
+        if cfg_pair is not None and hasattr(cfg_pair, "enable_peer") and not os.environ.get("LKGD_CFG_PAIR_NCCL"):
+            # exchange through peer memory where the box offers it (collective over the pair: every rank prepares)
+            n_rows = S * num_frames * image_latents.shape[-2] * image_latents.shape[-1]
+            ld = int(getattr(self.unet.config, "out_channels", 4))
+            if getattr(cfg_pair, "peer", None) is None or cfg_pair.peer["n"] != n_rows or cfg_pair.peer["ld"] != ld:
+                cfg_pair.enable_peer(n_rows, ld, device)
         return dict(cfg_pair=cfg_pair, S=S, n_batch=n_lat, F=num_frames, h=image_latents.shape[-2],
                     w=image_latents.shape[-1], do_cfg=do_cfg, added_time_ids=added_time_ids,
                     guidance=guidance.reshape(-1).to(torch.float32).contiguous(),
@@ -224,6 +232,32 @@ class StableVideoDiffusionPipeline:
         return sched.step_cfg_rows(rows, st["guidance"] if st["do_cfg"] else None, latents, cfg=st["do_cfg"],
                                    want_v=want_v, sigmas_dev=sigmas_dev, in_place=in_place)
 
+    def _pair_body(self, st: dict, latents: torch.Tensor, scale, t, sigmas_dev=None, in_place=False, want_v=False):
+        """The CFG-pair split of one step (lkgd_b200/distributed.py): this rank runs ONE half of [uncond | cond] with
+        batch S; the halves' predictions meet in the fused CFG + Euler kernel, which both ranks run (replicated latents).
+        With peer memory the kernel reads the partner's half over NVLink (one device-side barrier, capturable in a CUDA
+        graph); else the halves are all-gathered first."""
+        sched, unet = self.scheduler, self.unet
+        pk = unet.packed()
+        pair = st["cfg_pair"]
+        lo, hi = pair.batch_slice(st["S"])
+        if st.get("image_latents_half") is None:
+            st["image_latents_half"] = st["image_latents"][lo:hi].contiguous()
+        dev_scalars = torch.is_tensor(scale)
+        x = ops.pack_input(latents, 0.0 if dev_scalars else scale, st["image_latents_half"], N=st["S"], Cpad=pk.cin_pad,
+                           scale_dev=scale if dev_scalars else None)
+        g = Geom(st["S"], st["F"], st["h"], st["w"])
+        rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
+                                   added_time_ids=st["added_time_ids"], batch_slice=(lo, hi))
+        if pair.peer is not None:          # exchange inside the combine kernel: the partner's half is read over NVLink
+            u, c = pair.publish(rows)
+            return sched.step_cfg_rows(u, st["guidance"], latents, cfg=True, want_v=want_v, pred_cond=c,
+                                       sigmas_dev=sigmas_dev, in_place=in_place)
+        if sigmas_dev is not None:
+            raise ValueError("the CFG pair split over an NCCL all-gather is not captured in a CUDA graph")
+        rows = pair.exchange(rows)
+        return sched.step_cfg_rows(rows, st["guidance"], latents, cfg=True, want_v=want_v)
+
     @ops.on_own_device
     @torch.no_grad()
     def capture(self, st: dict, latents: torch.Tensor) -> dict:
@@ -234,8 +268,10 @@ class StableVideoDiffusionPipeline:
         allocations become one ``cudaGraphLaunch``.  Call after at least one eager ``denoise_step`` (lazy weight packing
         and one-time kernel attributes must not happen under capture).  The conditioning tensors in ``st`` are the
         graph's static inputs: refresh them with ``copy_`` (not by rebinding the dict entries)."""
-        if st.get("cfg_pair") is not None:
-            raise ValueError("the CFG pair split exchanges predictions with NCCL every step: not captured")
+        pair = st.get("cfg_pair")
+        if pair is not None and pair.peer is None:
+            raise ValueError("the CFG pair split exchanges predictions with NCCL every step: not captured "
+                             "(peer memory, CFGPair.enable_peer, makes the split step capturable)")
         sched = self.scheduler
         dev = self.unet.device
         sig = np.asarray(sched._sigmas_host, dtype=np.float32)
@@ -249,7 +285,8 @@ class StableVideoDiffusionPipeline:
 
         def body():
             sched.index_for(0)
-            self._step_body(st, G["lat"], G["params"][0:1], G["params"][3:4], sigmas_dev=G["params"][1:3], in_place=True)
+            step = self._step_body if pair is None else self._pair_body
+            step(st, G["lat"], G["params"][0:1], G["params"][3:4], sigmas_dev=G["params"][1:3], in_place=True)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -258,8 +295,20 @@ class StableVideoDiffusionPipeline:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            body()
+        if pair is not None:
+            # the peer buffer has two slots used by alternate steps: one graph per slot, replayed alternately (both ranks
+            # capture and replay in lockstep - the barrier inside is the only coupling)
+            if pair.peer["tick"] & 1:
+                body()                               # start the pair of captures on slot 0 (the warm-up above took one)
+            with torch.cuda.graph(graph):
+                body()
+            odd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(odd, pool=graph.pool()):
+                body()
+            G["graphs"] = (graph, odd)
+        else:
+            with torch.cuda.graph(graph):
+                body()
         G["lat"].copy_(keep)
         G["graph"] = graph
         st["graph"] = G
@@ -281,7 +330,12 @@ class StableVideoDiffusionPipeline:
             if latents.data_ptr() != G["lat"].data_ptr():
                 G["lat"].copy_(latents, non_blocking=True)
             G["params"].copy_(G["table"][i], non_blocking=True)
-            G["graph"].replay()
+            if "graphs" in G:                        # CFG pair over peer memory: the slot alternates call by call
+                P = st["cfg_pair"].peer
+                G["graphs"][P["tick"] & 1].replay()
+                P["tick"] += 1
+            else:
+                G["graph"].replay()
             sched.index_for(i + 1)
             return G["lat"], None
         pk = unet.packed()
@@ -289,17 +343,8 @@ class StableVideoDiffusionPipeline:
         sigma = float(sched._sigmas_host[i])
         t = float(sched._timesteps_host[i])
         scale = float(1.0 / np.sqrt(np.float32(sigma) ** 2 + 1))
-        pair = st.get("cfg_pair")
-        if pair is not None:
-            # CFG pair split (lkgd_b200/distributed.py): this rank runs one half of [uncond | cond] with batch S, then
-            # the two halves' predictions are exchanged once and both ranks take the fused CFG + Euler step
-            lo, hi = pair.batch_slice(st["S"])
-            x = ops.pack_input(latents, scale, st["image_latents"][lo:hi].contiguous(), N=st["S"], Cpad=pk.cin_pad)
-            g = Geom(st["S"], st["F"], st["h"], st["w"])
-            rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
-                                       added_time_ids=st["added_time_ids"], batch_slice=(lo, hi))
-            rows = pair.exchange(rows)
-            return sched.step_cfg_rows(rows, st["guidance"], latents, cfg=True, want_v=want_v)
+        if st.get("cfg_pair") is not None:
+            return self._pair_body(st, latents, scale, t, want_v=want_v)
         return self._step_body(st, latents, scale, t, want_v=want_v)
 
     @torch.no_grad()

@@ -228,14 +228,14 @@ class EulerDiscreteScheduler:
 
     def step_cfg_rows(self, pred_rows: torch.Tensor, guidance: Optional[torch.Tensor], sample: torch.Tensor,
                       cfg: bool, want_v: bool = False, sigmas_dev: Optional[torch.Tensor] = None,
-                      in_place: bool = False):
+                      in_place: bool = False, pred_cond: Optional[torch.Tensor] = None):
         """Fused CFG combine + Euler update straight from the UNet's channels-last fp32 prediction
         (pipeline/pipeline_stable_video_diffusion_controlnet.py:614-619 in one kernel).  ``sigmas_dev`` / ``in_place``:
         the CUDA-graph form (per-step sigmas read from device memory, latents updated in their static buffer)."""
         sigma = float(self._sigmas_host[self._step_index])
         sigma_next = float(self._sigmas_host[self._step_index + 1])
         out = ops.cfg_euler_step(pred_rows, guidance, sample, sigma, sigma_next, cfg=cfg, want_v=want_v,
-                                 sigmas_dev=sigmas_dev, in_place=in_place)
+                                 sigmas_dev=sigmas_dev, in_place=in_place, pred_cond=pred_cond)
         self._step_index += 1
         return out
 

@@ -43,7 +43,23 @@ def main():
         whole = pipe2(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, return_dict=False, **kw)
         other = split.clone()
         dist.broadcast(other, src=0)
-        res[name] = dict(split_vs_unsplit=rel(split, whole), replicated=bool(torch.equal(other, split)))
+        res[name] = dict(split_vs_unsplit=rel(split, whole), replicated=bool(torch.equal(other, split)),
+                         exchange="peer" if pair.peer is not None else "nccl")
+        if pair.peer is not None:      # the same steps through the NCCL all-gather must give the same latents
+            keep, pair.peer = pair.peer, None
+            os.environ["LKGD_CFG_PAIR_NCCL"] = "1"
+            again = pipe(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, cfg_pair=pair,
+                         return_dict=False, **kw)
+            del os.environ["LKGD_CFG_PAIR_NCCL"]
+            pair.peer = keep
+            res[name]["peer_equals_nccl"] = bool(torch.equal(again, split))
+            # the split step as a CUDA-graph replay (two graphs, one per slot of the peer buffer): three steps again
+            st = pipe.prepare(emb, img, num_frames=F_, num_inference_steps=25, cfg_pair=pair, **kw)
+            x = (lat * pipe.scheduler.init_noise_sigma).to(dev)
+            pipe.capture(st, x)
+            for i in range(3):
+                x, _ = pipe.denoise_step(st, i, x)
+            res[name]["graph_equals_eager"] = bool(torch.equal(x, split.to(dev)))
     if rank == 0:
         print("RESULT " + json.dumps(res), flush=True)
     dist.barrier()

@@ -24,6 +24,9 @@ def test_cfg_pair_split_two_gpus(cuda):
     for name, r in res.items():
         assert r["replicated"], name                       # both ranks hold identical latents after every step
         assert r["split_vs_unsplit"] < 2e-3, (name, r)     # same kernels, batch 1 vs 2: only accumulation-order noise
+        if r.get("exchange") == "peer":                    # partner's half read over NVLink inside the combine kernel
+            assert r["peer_equals_nccl"], name             # ... gives the latents of the all-gather path, bit for bit
+            assert r["graph_equals_eager"], name           # ... and so does the CUDA-graph replay of the split step
 
 
 def test_data_parallel_lora_training_two_gpus(cuda):
