@@ -754,8 +754,10 @@ def _rel(a, b):
 
 def section_cfg_split(args, pipe, F, h, w, lkgd, unsplit_ms, device, rank, world):
     """north_star: "the CFG cond/uncond pair ... split across GPUs, with no collective in the UNet".  Ranks (2k, 2k+1)
-    denoise sample k together: rank 2k the unconditional half, 2k+1 the conditional half (batch 1 each), ONE all-gather
-    of the fp32 prediction per step, the fused CFG + Euler kernel on both (latents stay replicated).  Latency mode:
+    denoise sample k together: rank 2k the unconditional half, 2k+1 the conditional half (batch 1 each), ONE exchange
+    of the fp32 prediction per step - fused into the CFG + Euler kernel over peer memory where the box offers it (the
+    kernel reads the partner's half over NVLink; the NCCL all-gather path is timed beside it), else an all-gather - and
+    the combine kernel on both ranks (latents stay replicated).  Latency mode:
     reports ms/step against the unsplit step, the split-vs-unsplit difference and whether the pair's latents are equal."""
     import torch.distributed as dist
     from lkgd_b200.distributed import CFGPair
