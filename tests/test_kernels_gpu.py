@@ -523,6 +523,21 @@ def test_cfg_euler_step_matches_formula(cuda):
     ref = x + (x - x0) / sig * (sig_n - sig)
     assert rel_l2(v, vv) < 1e-6
     assert rel_l2(xn, ref) < 1e-6
+    # the two halves at separate bases (CFG-pair split: one of them is the partner GPU's peer-mapped buffer; here both are
+    # local, wider-pitched and offset slices): the same bits, also with device sigmas and the in-place latent update
+    n = 2 * 3 * 8 * 8
+    wide_u = torch.zeros(n, 8, device=cuda); wide_c = torch.full((n + 5, 8), 7.0, device=cuda)
+    wide_u[:, :4] = u.reshape(-1, 4); wide_c[5:, :4] = c.reshape(-1, 4)
+    xn2, v2 = ops.cfg_euler_step(wide_u, g, x, sig, sig_n, cfg=True, want_v=True, pred_cond=wide_c[5:])
+    assert torch.equal(xn2, xn) and torch.equal(v2, v)
+    xs = x.clone()
+    xn3, _ = ops.cfg_euler_step(wide_u, g, xs, 1.0, 1.0, cfg=True, pred_cond=wide_c[5:], in_place=True,
+                                sigmas_dev=torch.tensor([sig, sig_n], device=cuda))
+    assert xn3.data_ptr() == xs.data_ptr() and torch.equal(xs, xn)
+    with pytest.raises(ValueError):
+        ops.cfg_euler_step(wide_u, g, x, sig, sig_n, cfg=True, pred_cond=c.reshape(-1, 4))     # different row pitch
+    with pytest.raises(ValueError):
+        ops.cfg_euler_step(wide_u, None, x, sig, sig_n, cfg=False, pred_cond=wide_c[5:])       # needs guidance
 
 
 # ------------------------------------------------------------------------------------------------- fp32 stream
