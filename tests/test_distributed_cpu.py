@@ -88,6 +88,8 @@ def _exchange_worker(rank, world):
     pair = CFGPair.from_world()
     assert pair.role == rank % 2 and pair.batch_slice(3) == ((0, 3) if rank % 2 == 0 else (3, 6))
     mine = torch.full((5, 4), float(rank))
+    # no peer memory on a gloo / CPU group: both ranks agree on the collective (a rank alone in a barrier would hang)
+    assert pair.enable_peer(5, 4, "cpu") is False and pair.peer is None and pair.peer_error is not None
     both = pair.exchange(mine)
     got = gather_samples(torch.full((2,), float(rank)))
     return both, got
