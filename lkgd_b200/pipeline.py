@@ -241,8 +241,11 @@ class StableVideoDiffusionPipeline:
         pk = unet.packed()
         pair = st["cfg_pair"]
         lo, hi = pair.batch_slice(st["S"])
+        # this rank's half of the conditioning latents: a fixed buffer refreshed every step (also inside a captured graph),
+        # so that `st["image_latents"]` stays the one input a caller updates with copy_
         if st.get("image_latents_half") is None:
-            st["image_latents_half"] = st["image_latents"][lo:hi].contiguous()
+            st["image_latents_half"] = torch.empty_like(st["image_latents"][lo:hi]).contiguous()
+        st["image_latents_half"].copy_(st["image_latents"][lo:hi])
         dev_scalars = torch.is_tensor(scale)
         x = ops.pack_input(latents, 0.0 if dev_scalars else scale, st["image_latents_half"], N=st["S"], Cpad=pk.cin_pad,
                            scale_dev=scale if dev_scalars else None)
