@@ -175,8 +175,8 @@ class StableVideoDiffusionPipeline:
             if cc.shape[0] * cond_repeat != n_lat:
                 raise ValueError("controlnet_condition batch does not match the conditioning batch")
             controlnet_condition = cc.to(device=device, dtype=torch.float32)
-        if cfg_pair is not None and (not do_cfg or controlnet_condition is not None):
-            raise ValueError("cfg_pair needs classifier-free guidance and (for now) no ControlNet")
+        if cfg_pair is not None and not do_cfg:
+            raise ValueError("cfg_pair needs classifier-free guidance")
         if cfg_pair is not None and hasattr(cfg_pair, "enable_peer") and not os.environ.get("LKGD_CFG_PAIR_NCCL"):
             # exchange through peer memory where the box offers it (collective over the pair: every rank prepares)
             n_rows = S * num_frames * image_latents.shape[-2] * image_latents.shape[-1]
@@ -250,8 +250,15 @@ class StableVideoDiffusionPipeline:
         x = ops.pack_input(latents, 0.0 if dev_scalars else scale, st["image_latents_half"], N=st["S"], Cpad=pk.cin_pad,
                            scale_dev=scale if dev_scalars else None)
         g = Geom(st["S"], st["F"], st["h"], st["w"])
+        kw = {}
+        if st["controlnet_condition"] is not None:
+            # both halves are conditioned on the SAME frames (reference :547-550 duplicates them, D3): this half takes
+            # the one copy as it is; injection fused into the UNet forward as in the unsplit step
+            if not st.get("fuse_controlnet", True):
+                raise ValueError("the CFG pair split runs the ControlNet fused into the UNet forward")
+            kw = dict(fused_controlnet=(self.controlnet, st["controlnet_condition"], st["controlnet_cond_scale"], 1))
         rows = unet.forward_packed(x, g, t, st["image_embeddings"], *st["extra"],
-                                   added_time_ids=st["added_time_ids"], batch_slice=(lo, hi))
+                                   added_time_ids=st["added_time_ids"], batch_slice=(lo, hi), **kw)
         if pair.peer is not None:          # exchange inside the combine kernel: the partner's half is read over NVLink
             u, c = pair.publish(rows)
             return sched.step_cfg_rows(u, st["guidance"], latents, cfg=True, want_v=want_v, pred_cond=c,

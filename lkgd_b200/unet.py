@@ -524,16 +524,20 @@ class UNetSpatioTemporalConditionControlNetModel(_Base):
         x_in = x
         x, skips, geoms, gm = pk.encoder(x, g, cond, stem=self._stem_rows(pk, x, g))
         if fused_controlnet is not None:
-            if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
-                    or batch_slice is not None:
-                raise ValueError("fused_controlnet excludes explicit residuals and batch_slice")
+            if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+                raise ValueError("fused_controlnet excludes explicit residuals")
             cn, cn_cond, cn_scale = fused_controlnet[:3]
             cn_repeat = fused_controlnet[3] if len(fused_controlnet) > 3 else 1
             per_block = [len(d[0]) + (1 if d[2] is not None else 0) for d in pk.down]
             per_block[0] += 1
             mult = residual_multipliers(len(pk.down), per_block)
-            x = cn.inject_packed(x_in, g, timestep, encoder_hidden_states, ids, cn_cond, cn_scale, skips, mult, x,
-                                 cond_repeat=cn_repeat)
+            cn_ctx, cn_ctx_t = encoder_hidden_states, None
+            if batch_slice is not None:      # one half of the guidance batch (CFG pair split): the ControlNet sees the raw
+                #                              image embeddings of this half, its temporal cross-attention those of both
+                cn_ctx = encoder_hidden_states[lo:hi]
+                cn_ctx_t = encoder_hidden_states if cn.packed().tctx_mode != 3 else None        # RV_BATCH == 3
+            x = cn.inject_packed(x_in, g, timestep, cn_ctx, ids, cn_cond, cn_scale, skips, mult, x,
+                                 cond_repeat=cn_repeat, ctx_t=cn_ctx_t)
         if mid_block_additional_residual is not None:
             ops.axpby(self._residual_rows(mid_block_additional_residual, gm), 1.0, x, 1.0)
         if down_block_additional_residuals is not None:
@@ -1070,7 +1074,8 @@ class ControlNetSDVModel(_Base):
             self._cn = (packed, zero)
         return self._cn
 
-    def _encode(self, x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond, bf16_skips, cond_repeat=1):
+    def _encode(self, x, g, timestep, encoder_hidden_states, added_time_ids, controlnet_cond, bf16_skips, cond_repeat=1,
+                ctx_t=None):
         """Condition encoder (pixel resolution, models/controlnet_sdv.py:98-119) + the copied UNet encoder + mid block.
         ``cond_repeat``: ``controlnet_cond`` holds batch / cond_repeat samples and every one conditions ``cond_repeat``
         batch entries (the pipeline feeds the SAME condition frames to both classifier-free-guidance halves,
@@ -1079,7 +1084,10 @@ class ControlNetSDVModel(_Base):
         pk = self.packed()
         convs, zero = self._cn_pack()
         emb = pk.time_embedding(self._timestep_tensor(timestep, x), added_time_ids.to(x.device))
-        cond = Conditioning(pk, emb, encoder_hidden_states.to(torch.float32).contiguous())
+        # ctx_t: the contexts of the WHOLE guidance batch when this forward holds one half of it (CFG pair split): the
+        # temporal cross-attention of diffusers 0.27.2 indexes them by row, exactly as in the UNet
+        cond = Conditioning(pk, emb, encoder_hidden_states.to(torch.float32).contiguous(),
+                            None if ctx_t is None else ctx_t.to(torch.float32).contiguous())
         stem_add = None
         if controlnet_cond is not None:
             if controlnet_cond.ndim != 5:
@@ -1119,7 +1127,8 @@ class ControlNetSDVModel(_Base):
         """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
         ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
-                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat)
+                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat,
+                                                    ctx_t=ctx_t)
         s = float(conditioning_scale)
         down = [ChannelsLast(ops.gemm(skb, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
                 for (_, skb), (w, b), gs in zip(skips, zero[:-1], geoms)]
@@ -1130,7 +1139,7 @@ class ControlNetSDVModel(_Base):
     def inject_packed(self, x: torch.Tensor, g: Geom, timestep, encoder_hidden_states: torch.Tensor,
                       added_time_ids: torch.Tensor, controlnet_cond: Optional[torch.Tensor], conditioning_scale: float,
                       unet_skips: List[torch.Tensor], multipliers: Sequence[int], unet_mid: torch.Tensor,
-                      cond_repeat: int = 1) -> torch.Tensor:
+                      cond_repeat: int = 1, ctx_t: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The fused form of ``forward_packed`` + the UNet's residual adds: every zero conv writes
         ``unet_skip += m_i * scale * (W skip_cn + b)`` in place in its epilogue (fp32 residual read, fused GroupNorm
         statistics of the sum where a 128-row tile stays inside one frame), the mid zero conv does the same on the UNet's

@@ -20,13 +20,15 @@ def main():
     from lkgd_b200.distributed import CFGPair
     from lkgd_b200.pipeline import StableVideoDiffusionPipeline
     from lkgd_b200.scheduler import EulerDiscreteScheduler
-    from lkgd_b200.unet import UNetSpatioTemporalConditionControlNetModel, UNetSpatioTemporalConditionModel
+    from lkgd_b200.unet import (ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel,
+                                UNetSpatioTemporalConditionModel)
     pair = CFGPair.from_world()
     res = {}
     for name, cls, cfg in (("plain_0272", UNetSpatioTemporalConditionControlNetModel, REDUCED4),
                            ("plain_b_major", UNetSpatioTemporalConditionControlNetModel,
                             dict(REDUCED4, time_context_order="b_major")),
-                           ("lkgd", UNetSpatioTemporalConditionModel, dict(REDUCED4, cross_attention_dim=1024))):
+                           ("lkgd", UNetSpatioTemporalConditionModel, dict(REDUCED4, cross_attention_dim=1024)),
+                           ("controlnet_0272", UNetSpatioTemporalConditionControlNetModel, REDUCED4)):
         F_, H_, W_ = 4, 16, 16
         xd = cfg["cross_attention_dim"]
         unet = fill_seeded_(cls(**cfg)).to(dev)
@@ -36,10 +38,15 @@ def main():
         if name == "lkgd":
             kw = dict(domain_features=seeded_tensor("d/dom", (1, 1, 1000)), flow_features=seeded_tensor("d/flow", (1, 1, 1000)))
         lat = seeded_tensor("d/lat", (1, F_, 4, H_, W_))
-        pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED))
+        cn = None
+        if name.startswith("controlnet"):      # BASELINE configs[3]: ControlNet injection fused into each half's UNet forward
+            cn = fill_seeded_(ControlNetSDVModel(**{k: v for k, v in cfg.items() if k != "up_block_types"},
+                                                 conditioning_channels=2), seed=1).to(dev)
+            kw = dict(controlnet_condition=seeded_tensor("d/cc", (F_, 2, 8 * H_, 8 * W_)))
+        pipe = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED), controlnet=cn)
         split = pipe(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, cfg_pair=pair,
                      return_dict=False, **kw)
-        pipe2 = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED))
+        pipe2 = StableVideoDiffusionPipeline(unet, EulerDiscreteScheduler(**SCHED), controlnet=cn)
         whole = pipe2(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, return_dict=False, **kw)
         other = split.clone()
         dist.broadcast(other, src=0)
