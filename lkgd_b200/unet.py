@@ -1127,8 +1127,7 @@ class ControlNetSDVModel(_Base):
         """Engine-layout forward: returns (list of 12 ``ChannelsLast`` residuals, ``ChannelsLast`` mid residual)."""
         ops.STATS_ARENA.begin(x.device)          # one zeroed buffer for this forward's fused GroupNorm statistics
         (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
-                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat,
-                                                    ctx_t=ctx_t)
+                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat)
         s = float(conditioning_scale)
         down = [ChannelsLast(ops.gemm(skb, w, bias=b, s0=s), gs.BF, gs.H, gs.W)
                 for (_, skb), (w, b), gs in zip(skips, zero[:-1], geoms)]
@@ -1146,7 +1145,8 @@ class ControlNetSDVModel(_Base):
         mid sample, which is returned.  Runs inside the UNet's forward: shares its statistics arena (no ``begin``).
         zip truncation as in the reference (:453-462): extra skips / residuals are ignored."""
         (xm, skips, geoms, gm), zero = self._encode(x, g, timestep, encoder_hidden_states, added_time_ids,
-                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat)
+                                                    controlnet_cond, bf16_skips=True, cond_repeat=cond_repeat,
+                                                    ctx_t=ctx_t)
         s = float(conditioning_scale)
         for i, ((_, skb), (w, b), gs, m, us) in enumerate(zip(skips, zero[:-1], geoms, multipliers, unet_skips)):
             if us.shape != (gs.M, w.shape[0]):

@@ -23,7 +23,9 @@ def test_cfg_pair_split_two_gpus(cuda):
     print(res)
     for name, r in res.items():
         assert r["replicated"], name                       # both ranks hold identical latents after every step
-        assert r["split_vs_unsplit"] < 2e-3, (name, r)     # same kernels, batch 1 vs 2: only accumulation-order noise
+        # same kernels on batch 1 and batch 2: measured bit-identical; a wrong temporal-context order of one half (the
+        # ControlNet's cross-attention once took only its own half's embedding) already shows up at 4e-5
+        assert r["split_vs_unsplit"] < 1e-5, (name, r)
         if r.get("exchange") == "peer":                    # partner's half read over NVLink inside the combine kernel
             assert r["peer_equals_nccl"], name             # ... gives the latents of the all-gather path, bit for bit
             assert r["graph_equals_eager"], name           # ... and so does the CUDA-graph replay of the split step
