@@ -402,7 +402,8 @@ class StableVideoDiffusionPipeline:
             if max_steps is not None and i >= max_steps:
                 break
             latents, v = self.denoise_step(st, i, latents, want_v=return_trajectory)
-            if i == 0 and use_cuda_graph and not return_trajectory and cfg_pair is None:
+            if i == 0 and use_cuda_graph and not return_trajectory and \
+                    (cfg_pair is None or getattr(cfg_pair, "peer", None) is not None):
                 self.capture(st, latents)              # steps 1.. replay the captured graph (same kernels, same order)
             if return_trajectory:
                 preds.append(v)

@@ -67,6 +67,9 @@ def main():
             for i in range(3):
                 x, _ = pipe.denoise_step(st, i, x)
             res[name]["graph_equals_eager"] = bool(torch.equal(x, split.to(dev)))
+            viacall = pipe(emb, img, num_frames=F_, num_inference_steps=25, latents=lat, max_steps=3, cfg_pair=pair,
+                           return_dict=False, use_cuda_graph=True, **kw)
+            res[name]["graph_equals_eager"] &= bool(torch.equal(viacall, split))
     if rank == 0:
         print("RESULT " + json.dumps(res), flush=True)
     dist.barrier()
