@@ -352,6 +352,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
 
 // ------------------------------------------------------------------------------------------- GEGLU
 // pre: [M, 2H] bf16 in the GEMM's tile-interleaved order: tile t holds 128 value columns then their 128 gate columns.
+// Phi(-t), t >= 0, as 2^P(t) with ONE MUFU op: the degree-6 fit of log2(0.5 erfc(t / sqrt 2)) on [0, 6] that the GEMM's
+// GEGLU epilogue uses (gemm_epilogue.cuh `gelu_erf_fast`, tools/fit_gelu.py: 4.8e-5 relative).  With erff both kernels
+// were instruction-bound (ncu: issue slots 83 / 85 % busy at 3.6 / 4.8 TB/s).
+__device__ __forceinline__ float phi_neg_fast(float t) {
+  t = fminf(t, 6.0f);
+  float p = fmaf(2.2999249e-05f, t, -6.1149016e-04f);
+  p = fmaf(p, t, 7.2001889e-03f);
+  p = fmaf(p, t, -5.1208213e-02f);
+  p = fmaf(p, t, -4.6122226e-01f);
+  p = fmaf(p, t, -1.1502144e+00f);
+  p = fmaf(p, t, -1.0000589e+00f);
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(p));
+  return y;
+}
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long M,
                                  int H) {
   const int hv = H / 8;
@@ -365,7 +380,10 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfl
   ld8_bf16(p, a);
   ld8_bf16(p + 128, gt);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = a[i] * gelu_erf_f(gt[i]);
+  for (int i = 0; i < 8; ++i) {      // gelu(x) = relu(x) - |x| Phi(-|x|)
+    const float ax = fabsf(gt[i]);
+    o[i] = a[i] * fmaf(-ax, phi_neg_fast(ax), fmaxf(gt[i], 0.f));
+  }
   st8_bf16(out + m * H + j, o);
 }
 
@@ -383,8 +401,9 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __
   ld8_bf16(pre + off + 128, gt);
   ld8_bf16(dout + m * H + j, d);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {      // one erf per element serves gelu (x * cdf) and its derivative (cdf + x * pdf)
-    const float cdf = 0.5f * (1.0f + erff(gt[i] * 0.70710678118654752f));
+  for (int i = 0; i < 8; ++i) {      // one Phi per element serves gelu (x * cdf) and its derivative (cdf + x * pdf)
+    const float hneg = phi_neg_fast(fabsf(gt[i]));
+    const float cdf = gt[i] >= 0.f ? 1.0f - hneg : hneg;
     da[i] = d[i] * (gt[i] * cdf);
     dg[i] = d[i] * a[i] * fmaf(gt[i] * 0.3989422804014327f, __expf(-0.5f * gt[i] * gt[i]), cdf);
   }
