@@ -131,6 +131,64 @@ def _cfg_split_worker(rank, world, order):
     return sched.step(pred, t, lat).prev_sample
 
 
+def _cfg_split_controlnet_worker(rank, world, give_cn_both_contexts):
+    """The pair split with a ControlNet (BASELINE configs[3]), the oracle as the denoiser: every half runs the ControlNet
+    and the UNet on its own batch entry; under the 0.27.2 context order BOTH models' temporal cross-attentions must index
+    the embeddings of the whole guidance batch."""
+    import oracle as O
+    from lkgd_b200.distributed import CFGPair
+    pair = CFGPair.from_world()
+    F_, H_, W_ = 4, 8, 8
+    unet = fill_seeded_(O.UNetSpatioTemporalConditionControlNetModel(**REDUCED4)).eval()
+    cn = fill_seeded_(O.ControlNetSDVModel(**{k: v for k, v in REDUCED4.items() if k != "up_block_types"},
+                                           conditioning_channels=2), seed=1).eval()
+    sched = O.EulerDiscreteScheduler(**SCHED)
+    sched.set_timesteps(25)
+    lat = seeded_tensor("dist/lat", (1, F_, 4, H_, W_)) * sched.init_noise_sigma
+    img = torch.cat([torch.zeros(1, F_, 4, H_, W_), seeded_tensor("dist/img", (1, 1, 4, H_, W_)).repeat(1, F_, 1, 1, 1)])
+    emb = torch.cat([torch.zeros(1, 1, 32), seeded_tensor("dist/emb", (1, 1, 32))])
+    cc = seeded_tensor("dist/cc", (1, F_, 2, 8 * H_, 8 * W_))
+    ids = O.add_time_ids_inference(6, 127, 0.02, 1)
+    t = sched.timesteps[0]
+    x = sched.scale_model_input(lat, t)
+    lo, hi = pair.batch_slice(1)
+    for model in ((unet, cn) if give_cn_both_contexts else (unet,)):
+        for m in model.modules():
+            if isinstance(m, O.TransformerSpatioTemporalModel):
+                m.cfg_split = (emb, lo)
+    with torch.no_grad():
+        xin = torch.cat([x, img[lo:hi]], dim=2)
+        down, mid = cn(xin, t, encoder_hidden_states=emb[lo:hi], controlnet_cond=cc, added_time_ids=ids[lo:hi],
+                       conditioning_scale=1.0, guess_mode=False, return_dict=False)
+        half = unet(xin, t, emb[lo:hi], added_time_ids=ids[lo:hi], down_block_additional_residuals=down,
+                    mid_block_additional_residual=mid).sample
+    both = pair.exchange(half.reshape(-1, 4)).reshape(2, *half.shape[1:])
+    sched._step_index = 0
+    return sched.step(O.cfg_combine(both, O.guidance_ramp(1.0, 3.0, F_)), t, lat).prev_sample
+
+
+def test_cfg_pair_split_with_controlnet_equals_unsplit_step():
+    import oracle as O
+    out = _run(_cfg_split_controlnet_worker, 2, True)
+    assert torch.equal(out[0], out[1])
+    F_, H_, W_ = 4, 8, 8
+    unet = fill_seeded_(O.UNetSpatioTemporalConditionControlNetModel(**REDUCED4)).eval()
+    cn = fill_seeded_(O.ControlNetSDVModel(**{k: v for k, v in REDUCED4.items() if k != "up_block_types"},
+                                           conditioning_channels=2), seed=1).eval()
+    sched = O.EulerDiscreteScheduler(**SCHED)
+    sched.set_timesteps(25)
+    lat = seeded_tensor("dist/lat", (1, F_, 4, H_, W_)) * sched.init_noise_sigma
+    img = torch.cat([torch.zeros(1, F_, 4, H_, W_), seeded_tensor("dist/img", (1, 1, 4, H_, W_)).repeat(1, F_, 1, 1, 1)])
+    emb = torch.cat([torch.zeros(1, 1, 32), seeded_tensor("dist/emb", (1, 1, 32))])
+    cc = seeded_tensor("dist/cc", (1, F_, 2, 8 * H_, 8 * W_))
+    ref = O.denoise_loop(unet, sched, lat, img, emb, O.add_time_ids_inference(6, 127, 0.02, 1), 25, 1.0, 3.0,
+                         max_steps=1, controlnet=cn, controlnet_cond=torch.cat([cc, cc]))
+    assert rel(out[0], ref) < 1e-5
+    # the design point the CUDA path follows: a ControlNet that sees only its own half's embedding is NOT the reference
+    wrong = _run(_cfg_split_controlnet_worker, 2, False)
+    assert rel(wrong[0], ref) > 1e-5
+
+
 @pytest.mark.parametrize("order", ["hw_major_0272", "b_major"])
 def test_cfg_pair_split_equals_unsplit_step(order):
     import oracle as O
