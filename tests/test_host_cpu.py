@@ -91,6 +91,14 @@ def test_no_cpu_fallback():
     from lkgd_b200 import ops
     with pytest.raises(ValueError, match="CUDA"):
         ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8))
+    # the entry points added with ABI v7 refuse host tensors the same way
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.Cast2dBatch([(torch.zeros(4, 8), torch.zeros(4, 8, dtype=torch.bfloat16), 1.0)])
+    with pytest.raises(ValueError, match="no jobs"):
+        ops.Cast2dBatch([])
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.cfg_euler_step(torch.zeros(16, 4), torch.ones(1), torch.zeros(1, 1, 4, 4, 4), 2.0, 1.0, cfg=True,
+                           pred_cond=torch.zeros(16, 4))
 
 
 def test_module_parameter_names_match_reference_dumps():
